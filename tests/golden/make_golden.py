@@ -1,0 +1,188 @@
+"""Generate the committed golden fixtures by running the UNMODIFIED reference (CPU, fp32).
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+Inputs are produced by this repo's seeded generators (``hybridneuralrendering_b200.synthetic``) and
+weights by ``oracle.render_oracle.random_params`` (numpy PCG64), so only OUTPUTS of the reference
+need to be stored.  The reference ships no tests of its own, so these files are what
+pins the oracle (prompt ③ / SURVEY.md §8c).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_import, render_oracle as ro          # noqa: E402
+from hybridneuralrendering_b200 import synthetic as syn      # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+T = torch.from_numpy
+
+
+def agg_case(name, R, SR, V, H, W, is_train, drop_ratio, dilation_setup, seed, with_grad):
+    d = syn.render_stage_inputs(seed=seed, N=600, R=R, SR=SR, K=8, V=V, H=H, W=W, empty_frac=0.4)
+    g = syn.gather_neighbours(d)
+    opt = ref_import.shipped_opt(use_nearest=V, is_train=is_train, drop_ratio=drop_ratio, dilation_setup=dilation_setup)
+    agg = ref_import.aggregator(opt)
+    P = ro.random_params(seed=seed + 100)
+    missing = agg.load_state_dict(P, strict=False)
+    assert not missing.unexpected_keys, missing
+    assert all(k.startswith("color_branch") for k in missing.missing_keys), missing
+    leaf = {k: T(g[k]).clone().requires_grad_(with_grad) for k in ("sampled_embedding", "sampled_color", "sampled_dir", "sampled_conf")}
+    img = T(d["images_nearest"]).clone()
+    out = agg(leaf["sampled_color"], torch.eye(3), leaf["sampled_dir"], leaf["sampled_conf"], leaf["sampled_embedding"],
+              T(g["sampled_xyz_pers"]), T(g["sampled_xyz"]), T(g["sample_pnt_mask"]), T(d["sample_loc"]), T(d["sample_loc_w"]),
+              T(d["sample_ray_dirs"]), d["vsize"], 0, img_n=img, sample_loc_i_n=T(d["sample_loc_i_n"]),
+              delta_viewdir_n=T(d["delta_viewdir_n"]), frame_weight_n=None, vid_angle_n=None)
+    decoded, ray_valid, weight, conf_coef = out[:4]
+    dr, drf = ref_import.rendering()
+    vz = float(d["vsize"][2])
+    # C1 prologue exactly as the conductor does it (neural_points_volumetric_model.py:331-339)
+    sl = T(d["sample_loc"])
+    rd = torch.cummax(sl[..., 2], dim=-1)[0]
+    rd = torch.cat([rd[..., 1:] - rd[..., :-1], torch.full((1, R, 1), vz)], dim=-1)
+    m = torch.logical_or(rd < 1e-8, rd > 2 * vz).to(torch.float32)
+    rd = rd * (1.0 - m) + m * vz
+    rd = rd * ray_valid.float()
+    bg = torch.ones(1, 3)
+    color, _, opacity, accT, bw, bgT, _ = dr.ray_march(rd, ray_valid, decoded, drf.radiance_render, drf.alpha_blend, bg)
+    res = dict(decoded=decoded, ray_valid=ray_valid, weight=weight, conf_coefficient=conf_coef, ray_dist=rd,
+               ray_color=color, opacity=opacity, acc_transmission=accT, blend_weight=bw, bg_transmission=bgT)
+    if with_grad:
+        rng = np.random.default_rng(seed + 7)
+        gt = T(rng.random((1, R, 3), dtype=np.float32))
+        v = conf_coef.clamp(1e-3, 1 - 1e-3)
+        loss = torch.nn.functional.mse_loss(color, gt) + 1e-4 * torch.mean(torch.log(v) + torch.log(1 - v))
+        loss.backward()
+        res["loss"] = loss.detach()
+        res["gt"] = gt
+        for k, t in leaf.items():
+            res["grad_" + k] = t.grad
+        for k, p in agg.named_parameters():
+            if p.grad is not None:
+                res["gradP_" + k] = p.grad
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **{k: (v.detach().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in res.items()},
+                        meta=np.array([R, SR, V, H, W, int(is_train), seed]), drop_ratio=np.float32(drop_ratio), dilation_setup=np.array(dilation_setup))
+    print(name, "Nv", int(ray_valid.sum()), "decoded", tuple(decoded.shape))
+
+
+def misc_cases():
+    dr, drf = ref_import.rendering()
+    nw = ref_import.networks()
+    rng = np.random.default_rng(3)
+    # positional encoding
+    x = T(rng.standard_normal((7, 5)).astype(np.float32))
+    pe = dict(x=x, pe3=nw.positional_encoding(x, 3), pe4_ori=nw.positional_encoding(x[:, :3], 4, ori=True))
+    # ray generation (no jitter and with jitter); the jitter stream is torch's CPU generator
+    campos = T(np.array([[0.3, -0.1, 2.0]], np.float32))
+    raydir = T(rng.standard_normal((1, 9, 3)).astype(np.float32))
+    rp0, seg0, _, ts0 = dr.near_far_linear_ray_generation(campos, raydir, 40, near=0.1, far=8.0, jitter=0.0)
+    torch.manual_seed(11)
+    rp1, seg1, _, ts1 = dr.near_far_linear_ray_generation(campos, raydir, 40, near=2.0, far=6.0, jitter=0.3)
+    torch.manual_seed(11)
+    noise = torch.rand((1, 9, 40))
+    gen = dict(campos=campos, raydir=raydir, raypos0=rp0, ts0=ts0, raypos1=rp1, ts1=ts1, noise=noise)
+    # standalone ray_march with hand-made tricky values (zero sigma, huge sigma, invalid samples)
+    feats = T(rng.random((1, 6, 9, 4)).astype(np.float32))
+    feats[0, 0, :, 0] = 0.0
+    feats[0, 1, :, 0] = 1e4
+    feats[0, 2, 3:, 0] *= 50
+    valid = T(rng.random((1, 6, 9)) > 0.3)
+    dist = T((rng.random((1, 6, 9)) * 0.02).astype(np.float32)) * valid.float()
+    bg = T(np.array([[1.0, 0.5, 0.25]], np.float32))
+    fr = feats.clone().requires_grad_(True)
+    o = dr.ray_march(dist, valid, fr, drf.radiance_render, drf.alpha_blend, bg)
+    G = T(rng.standard_normal((1, 6, 3)).astype(np.float32))
+    (o[0] * G).sum().backward()
+    rm = dict(feats=feats, valid=valid, dist=dist, bg=bg, G=G, ray_color=o[0], opacity=o[2], accT=o[3], bw=o[4], bgT=o[5], grad_feats=fr.grad)
+    np.savez_compressed(os.path.join(OUT, "misc.npz"), **{"pe_" + k: v.numpy() for k, v in pe.items()},
+                        **{"gen_" + k: v.numpy() for k, v in gen.items()}, **{"rm_" + k: v.detach().numpy() for k, v in rm.items()})
+    print("misc ok")
+
+
+def projection_case():
+    """w2iproject + delta-view loop of the conductor, called as unbound code paths:
+    neural_points_volumetric_model.py:248-255 and :296-310 need the class, which imports cleanly
+    with a pytorch_msssim stub."""
+    import types
+    try:
+        NeuralPointsRayMarching = ref_import.import_with_stubs("models.neural_points_volumetric_model").NeuralPointsRayMarching
+    except Exception as e:  # pragma: no cover
+        print("projection golden skipped:", repr(e))
+        return
+    rng = np.random.default_rng(5)
+    fr = syn.room_frame(H=48, W=64, V=3, patch_num=2, patch_size=2, seed=1)
+    loc_w = T((rng.random((1, 4, 5, 3)) * np.array([6, 5, 3])).astype(np.float32))
+    xy = [NeuralPointsRayMarching.w2iproject(None, loc_w[0], T(fr["intrinsic_nearest"][0]), T(fr["c2w_nearest"][0, v]), None) for v in range(3)]
+    np.savez_compressed(os.path.join(OUT, "proj.npz"), loc_w=loc_w.numpy(), intrinsic=fr["intrinsic_nearest"][0], c2w_n=fr["c2w_nearest"][0],
+                        xy=torch.stack(xy).numpy())
+    print("proj ok")
+
+
+def blur_case():
+    """blur_update_output is a method; call it unbound on a namespace carrying the attributes it
+    reads (base_rendering_model.py:677-786).  Its `.cuda()` on the kernels is patched to a no-op
+    for this CPU run -- the arithmetic is unchanged."""
+    import types
+    try:
+        BaseRenderingModel = ref_import.import_with_stubs("models.base_rendering_model").BaseRenderingModel
+    except Exception as e:  # pragma: no cover
+        print("blur golden skipped:", repr(e))
+        return
+    rng = np.random.default_rng(9)
+    PN, PS, Nk = 3, 8, 10
+    S = PN * PS
+    pred = T(rng.random((1, S * S, 3), dtype=np.float32)).requires_grad_(True)
+    gt = T(rng.random((1, S * S, 3), dtype=np.float32))
+    k = np.zeros((Nk, 9, 9), np.float32)
+    for n in range(Nk):                       # sparse line-like kernels, rows sum to 1
+        taps = rng.integers(2, 9)
+        ii = rng.integers(0, 9, taps); jj = rng.integers(0, 9, taps)
+        k[n, ii, jj] = rng.random(taps).astype(np.float32) + 0.1
+        k[n] /= k[n].sum()
+    # make the argmin non-trivial: gt of patch p := pred blurred with kernel (3p mod Nk) + small noise,
+    # except the last patch whose gt is pred itself (identity candidate wins)
+    import torch.nn.functional as F
+    with torch.no_grad():
+        img = pred.detach().reshape(S, S, 3).permute(2, 0, 1).clone()
+        gimg = gt.reshape(S, S, 3).permute(2, 0, 1).clone()
+        for pi in range(PN):
+            for pj in range(PN):
+                pnum = pi * PN + pj
+                blk = img[:, pi * PS:(pi + 1) * PS, pj * PS:(pj + 1) * PS].reshape(3, 1, PS, PS)
+                if pnum == PN * PN - 1:
+                    tgt = blk
+                else:
+                    kk = T(k[(3 * pnum) % Nk])[None, None]
+                    tgt = F.conv2d(blk, kk, padding=4) / F.conv2d(torch.ones_like(blk), kk, padding=4)
+                gimg[:, pi * PS:(pi + 1) * PS, pj * PS:(pj + 1) * PS] = tgt.reshape(3, PS, PS) + 0.01 * gimg[:, pi * PS:(pi + 1) * PS, pj * PS:(pj + 1) * PS]
+        gt = gimg.permute(1, 2, 0).reshape(1, S * S, 3).contiguous()
+    ns = types.SimpleNamespace(dilation_PatchNum=PN, dilation_PatchSize=PS, gt_image=gt, output={"coarse_raycolor": pred},
+                               xv_patches=[], yv_patches=[], blur_kernels=T(k)[None])
+    orig_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **kw: self
+    try:
+        BaseRenderingModel.blur_update_output(ns)
+    finally:
+        torch.Tensor.cuda = orig_cuda
+    out = ns.output["coarse_raycolor"]
+    G = T(rng.standard_normal((1, S * S, 3)).astype(np.float32))
+    (out * G).sum().backward()
+    np.savez_compressed(os.path.join(OUT, "blur.npz"), pred=pred.detach().numpy(), gt=gt.numpy(), kernels=k[None], out=out.detach().numpy(),
+                        G=G.numpy(), grad_pred=pred.grad.numpy(), meta=np.array([PN, PS, Nk]))
+    print("blur ok")
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(4)
+    agg_case("agg_eval", R=12, SR=5, V=2, H=20, W=24, is_train=False, drop_ratio=0.0, dilation_setup="7_8_1_8", seed=1, with_grad=False)
+    agg_case("agg_train", R=16, SR=6, V=3, H=24, W=20, is_train=True, drop_ratio=0.5, dilation_setup="2_2_1_8", seed=2, with_grad=True)
+    misc_cases()
+    projection_case()
+    blur_case()

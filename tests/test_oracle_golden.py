@@ -1,0 +1,120 @@
+"""Pin the CPU oracle against outputs of the unmodified reference (tests/golden/*.npz, made by
+tests/golden/make_golden.py in the build container).  CPU only."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import render_oracle as ro
+from hybridneuralrendering_b200 import synthetic as syn
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+T = torch.from_numpy
+
+
+def _load(name):
+    return dict(np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False))
+
+
+def _agg_inputs(meta, empty_frac=0.4):
+    R, SR, V, H, W, is_train, seed = [int(x) for x in meta]
+    d = syn.render_stage_inputs(seed=seed, N=600, R=R, SR=SR, K=8, V=V, H=H, W=W, empty_frac=empty_frac)
+    return d, syn.gather_neighbours(d), (R, SR, V, H, W, bool(is_train), seed)
+
+
+def _run_oracle(d, g, P, cfg, dtype=torch.float32, grad=False):
+    c = lambda a: T(a).to(dtype)
+    leaf = {k: c(g[k]).clone().requires_grad_(grad) for k in ("sampled_embedding", "sampled_color", "sampled_dir", "sampled_conf")}
+    Pd = {k: v.to(dtype).clone().requires_grad_(grad) for k, v in P.items()}
+    out = ro.aggregate(Pd, cfg, leaf["sampled_color"], torch.eye(3, dtype=dtype), leaf["sampled_dir"], leaf["sampled_conf"],
+                       leaf["sampled_embedding"], c(g["sampled_xyz_pers"]), c(g["sampled_xyz"]), T(g["sample_pnt_mask"]),
+                       c(d["sample_loc"]), c(d["sample_loc_w"]), c(d["sample_ray_dirs"]), img_n=c(d["images_nearest"]),
+                       sample_loc_i_n=c(d["sample_loc_i_n"]), delta_viewdir_n=c(d["delta_viewdir_n"]))
+    return out, leaf, Pd
+
+
+def test_agg_eval_matches_reference():
+    G = _load("agg_eval")
+    d, g, (R, SR, V, H, W, is_train, seed) = _agg_inputs(G["meta"])
+    P = ro.random_params(seed=seed + 100)
+    cfg = ro.AggCfg(use_nearest=V, is_train=False)
+    (decoded, valid, w, cc), _, _ = _run_oracle(d, g, P, cfg)
+    assert np.array_equal(valid.numpy(), G["ray_valid"])
+    np.testing.assert_allclose(decoded.numpy(), G["decoded"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(w.numpy(), G["weight"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(cc.numpy(), G["conf_coefficient"], rtol=0, atol=0)
+    rd = ro.ray_dist_from_depth(T(d["sample_loc"])[..., 2], valid, float(d["vsize"][2]))
+    np.testing.assert_array_equal(rd.numpy(), G["ray_dist"])
+    o = ro.ray_march(rd, valid, decoded, torch.ones(1, 3))
+    np.testing.assert_allclose(o[0].numpy(), G["ray_color"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(o[2].numpy(), G["opacity"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(o[3].numpy(), G["acc_transmission"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(o[4].numpy(), G["blend_weight"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(o[5].numpy(), G["bg_transmission"], rtol=1e-5, atol=1e-7)
+
+
+def test_agg_train_grads_match_reference():
+    G = _load("agg_train")
+    d, g, (R, SR, V, H, W, is_train, seed) = _agg_inputs(G["meta"])
+    assert is_train
+    P = ro.random_params(seed=seed + 100)
+    cfg = ro.AggCfg(use_nearest=V, is_train=True, drop_ratio=float(G["drop_ratio"]), dilation_setup=str(G["dilation_setup"]))
+    (decoded, valid, w, cc), leaf, Pd = _run_oracle(d, g, P, cfg, grad=True)
+    np.testing.assert_allclose(decoded.detach().numpy(), G["decoded"], rtol=1e-5, atol=1e-6)
+    rd = ro.ray_dist_from_depth(T(d["sample_loc"])[..., 2], valid, float(d["vsize"][2]))
+    color = ro.ray_march(rd, valid, decoded, torch.ones(1, 3))[0]
+    v = cc.clamp(1e-3, 1 - 1e-3)
+    loss = torch.nn.functional.mse_loss(color, T(G["gt"])) + 1e-4 * torch.mean(torch.log(v) + torch.log(1 - v))
+    np.testing.assert_allclose(loss.item(), float(G["loss"]), rtol=1e-5)
+    loss.backward()
+    for k, t in leaf.items():
+        ref = G["grad_" + k]
+        np.testing.assert_allclose(t.grad.numpy(), ref, rtol=2e-4, atol=1e-7 + 1e-4 * np.abs(ref).max(), err_msg=k)
+    n = 0
+    for k, p in Pd.items():
+        key = "gradP_" + k
+        if key not in G:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+            continue
+        ref = G[key]
+        np.testing.assert_allclose(p.grad.numpy(), ref, rtol=2e-4, atol=1e-7 + 2e-4 * np.abs(ref).max(), err_msg=k)
+        n += 1
+    assert n >= 40
+
+
+def test_posenc_raygen_raymarch_match_reference():
+    G = _load("misc")
+    x = T(G["pe_x"])
+    np.testing.assert_array_equal(ro.pos_enc(x, 3).numpy(), G["pe_pe3"])
+    np.testing.assert_array_equal(ro.pos_enc(x[:, :3], 4, ori=True).numpy(), G["pe_pe4_ori"])
+    from oracle import query_oracle as qo
+    rp0, ts0 = qo.ray_candidates(G["gen_campos"], G["gen_raydir"], 40, 0.1, 8.0, None)
+    np.testing.assert_array_equal(ts0, G["gen_ts0"])
+    np.testing.assert_array_equal(rp0, G["gen_raypos0"])
+    rp1, ts1 = qo.ray_candidates(G["gen_campos"], G["gen_raydir"], 40, 2.0, 6.0, G["gen_noise"], jitter=0.3)
+    np.testing.assert_array_equal(ts1, G["gen_ts1"])
+    np.testing.assert_array_equal(rp1, G["gen_raypos1"])
+    f = T(G["rm_feats"]).clone().requires_grad_(True)
+    o = ro.ray_march(T(G["rm_dist"]), T(G["rm_valid"]), f, T(G["rm_bg"]))
+    np.testing.assert_allclose(o[0].detach().numpy(), G["rm_ray_color"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(o[5].detach().numpy(), G["rm_bgT"], rtol=1e-6, atol=1e-12)
+    (o[0] * T(G["rm_G"])).sum().backward()
+    np.testing.assert_allclose(f.grad.numpy(), G["rm_grad_feats"], rtol=1e-5, atol=1e-7)
+
+
+def test_projection_matches_reference():
+    G = _load("proj")
+    xy = ro.project_to_views(T(G["loc_w"])[0], T(G["intrinsic"]), T(G["c2w_n"]))
+    np.testing.assert_allclose(xy.numpy(), G["xy"], rtol=1e-6, atol=1e-4)
+
+
+def test_blur_matches_reference():
+    G = _load("blur")
+    PN, PS, Nk = [int(v) for v in G["meta"]]
+    pred = T(G["pred"]).clone().requires_grad_(True)
+    out, sel = ro.blur_select(pred, T(G["gt"]), T(G["kernels"]), PN, PS)
+    np.testing.assert_allclose(out.detach().numpy(), G["out"], rtol=1e-6, atol=1e-7)
+    (out * T(G["G"])).sum().backward()
+    np.testing.assert_allclose(pred.grad.numpy(), G["grad_pred"], rtol=1e-5, atol=1e-7)
+    assert len(set(sel.tolist())) > 1, "fixture should exercise more than one candidate"
