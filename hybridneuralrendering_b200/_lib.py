@@ -1,0 +1,108 @@
+"""ctypes binding of libhnr.so (the C ABI declared in include/hnr.h).
+
+The product path has NO fallback: if the shared library is missing or was not built for the
+device in use, importing/calling raises.  PyTorch is only used for device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libhnr.so")
+
+_lib = None
+
+vp, i64, i32, f32c = C.c_void_p, C.c_int64, C.c_int32, C.c_float
+
+
+class GridT(C.Structure):
+    _fields_ = [("origin", C.c_float * 3), ("cell", C.c_float * 3), ("dims", C.c_int32 * 3), ("radius2", C.c_float),
+                ("n_cells", C.c_int64), ("P", C.c_int32), ("layers", C.c_int32), ("qhalf_lo", C.c_int32 * 3),
+                ("qhalf_hi", C.c_int32 * 3)]
+
+
+_SIGS = {
+    "hnr_abi_version": (C.c_int, []),
+    "hnr_last_error": (C.c_char_p, []),
+    "hnr_device_arch": (C.c_int, []),
+    "hnr_scan_scratch_elems": (i64, [i64]),
+    "hnr_exclusive_scan_i32": (C.c_int, [vp, vp, i64, vp, vp]),
+    "hnr_grid_build": (C.c_int, [vp, i64, C.POINTER(GridT), i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "hnr_query": (C.c_int, [vp, vp, vp, vp, i64, i64, i64, i64, i64, C.POINTER(GridT)] + [vp] * 19 + [vp]),
+    "hnr_nbr_weights": (C.c_int, [vp, vp, vp, vp, vp, i64, i64, vp, vp, vp, vp]),
+    "hnr_nbr_features": (C.c_int, [vp] * 10 + [vp, i64, i64, i64, vp, vp, vp]),
+    "hnr_nbr_features_bwd": (C.c_int, [vp] * 7 + [vp, i64, i64, vp, vp, vp, vp]),
+    "hnr_alpha_ksum_fwd": (C.c_int, [vp] * 7 + [vp, i64, i64, i64, vp, vp, vp, vp]),
+    "hnr_alpha_ksum_bwd": (C.c_int, [vp] * 8 + [i64, i64, i64, vp, vp, vp, vp, vp]),
+    "hnr_conf_bwd": (C.c_int, [vp] * 5 + [i64, i64, i64, vp, vp]),
+    "hnr_project_views": (C.c_int, [vp] * 5 + [i64, i64, vp, vp, vp]),
+    "hnr_image_gather_fwd": (C.c_int, [C.POINTER(vp), C.POINTER(i64), vp, vp, i64, i64, i64, vp, vp, vp]),
+    "hnr_image_gather_bwd": (C.c_int, [C.POINTER(vp), C.POINTER(i64), vp, vp, vp, i64, i64, i64, vp]),
+    "hnr_blend_fwd": (C.c_int, [vp, vp, vp, vp, i64, i64, vp, vp]),
+    "hnr_blend_bwd": (C.c_int, [vp, vp, vp, vp, vp, i64, i64, vp, vp, vp]),
+    "hnr_linear_fwd": (C.c_int, [C.POINTER(vp), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), vp, vp, vp, i64, vp, i64, i64, i64,
+                                 i64, C.c_int, vp]),
+    "hnr_linear_bwd_data": (C.c_int, [vp, i64, vp, i64, vp, C.POINTER(vp), C.POINTER(i64), C.POINTER(i64), i64, i64, i64, C.c_int, vp]),
+    "hnr_linear_bwd_weight": (C.c_int, [vp, i64, vp, i64, C.POINTER(vp), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), vp, vp, i64,
+                                        i64, i64, C.c_int, vp]),
+    "hnr_composite_fwd": (C.c_int, [vp, vp, vp, C.c_int, vp, vp, f32c, C.c_int, i64, i64, vp, vp, vp, vp, vp, vp, vp]),
+    "hnr_composite_bwd": (C.c_int, [vp] * 11 + [i64, i64, vp, vp]),
+    "hnr_blur_select_fwd": (C.c_int, [vp, vp, vp, i64, i64, i64, i64, vp, vp, vp]),
+    "hnr_blur_select_bwd": (C.c_int, [vp, vp, vp, i64, i64, i64, i64, vp, vp]),
+}
+
+EXPORTED = sorted(_SIGS)
+
+
+def lib():
+    """Return the loaded library, loading it on first use.  Raises if it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  There is no CPU or PyTorch fallback for this path.")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(L, name)       # AttributeError if the symbol is missing -> loud
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(code: int, what: str = "") -> None:
+    if code != 0:
+        msg = lib().hnr_last_error().decode()
+        raise RuntimeError(f"libhnr {what} failed ({code}): {msg}")
+
+
+def ptr(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr())
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(*tensors: torch.Tensor) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("hybridneuralrendering_b200: tensors must live on a CUDA device (no CPU fallback)")
+
+
+def ptr_array(ts: Sequence[Optional[torch.Tensor]]):
+    arr = (vp * len(ts))()
+    for i, t in enumerate(ts):
+        arr[i] = t.data_ptr() if t is not None else None
+    return arr
+
+
+def i64_array(vals: Sequence[int]):
+    return (i64 * len(vals))(*[int(v) for v in vals])

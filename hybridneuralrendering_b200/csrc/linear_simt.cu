@@ -1,0 +1,262 @@
+// Exact-fp32 SIMT linear layers (forward, data-gradient, weight-gradient) used by the training
+// backward pass and as the bit-faithful fp32 path next to the tcgen05 3xTF32 kernels (mlp_tc.cu).
+// One layer = y = act(concat(A1,A2,A3) . W^T + b [+ residual]) with W (N,K) row-major exactly as
+// torch.nn.Linear stores it, so the reference's checkpoints are consumed unchanged
+// (reference layers: models/aggregators/point_aggregators.py:484-683).
+//
+// Classic register-tiled SGEMM: 64x64 CTA tile, BK=16, 256 threads, 4x4 outputs per thread,
+// operands staged through shared memory as [BK][64+pad].  fp32 FFMA only (tensor cores would need
+// the 3xTF32 split; see mlp_tc.cu).
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 64, BN = 64, BK = 16, PADT = 4;
+
+struct Cat3 {
+    const float* p[3];
+    int ld[3];
+    int k[3];        // widths; K = k0+k1+k2
+    int64_t mod[3];  // if > 0 the source has `mod` rows and row m reads row m % mod (a block shared by V views)
+};
+
+__device__ __forceinline__ float cat_load(const Cat3& a, int64_t m, int k) {
+    int s = 0;
+    if (k >= a.k[0]) { k -= a.k[0]; s = 1; if (k >= a.k[1]) { k -= a.k[1]; s = 2; } }
+    if (a.mod[s] > 0) m %= a.mod[s];
+    return a.p[s][m * a.ld[s] + k];
+}
+
+struct Cat3Out {
+    float* p[3];
+    int ld[3];
+    int k[3];
+};
+
+__device__ __forceinline__ void mma_tile(const float (&As)[BK][BM + PADT], const float (&Bs)[BK][BN + PADT], float (&acc)[4][4],
+                                         int ty, int tx) {
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+        float a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+}
+
+// ---------------------------------------------------------------- forward
+// Y[m,n] = act( sum_k A[m,k] W[n,k] + b[n] (+ res[m,n]) )
+__global__ void __launch_bounds__(256)
+linear_fwd_kernel(Cat3 A, const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ res, int ldres,
+                  float* __restrict__ Y, int ldy, int64_t M, int N, int K, int act) {
+    __shared__ float As[BK][BM + PADT];
+    __shared__ float Bs[BK][BN + PADT];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int64_t m0 = (int64_t)blockIdx.x * BM;
+    const int n0 = blockIdx.y * BN;
+    float acc[4][4] = {};
+    const int lk = tid & 15, lr = tid >> 4;   // loader: 16 consecutive threads walk k (contiguous in A and W)
+    for (int k0 = 0; k0 < K; k0 += BK) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int r = lr + 16 * j;
+            int k = k0 + lk;
+            int64_t m = m0 + r;
+            As[lk][r] = (m < M && k < K) ? cat_load(A, m, k) : 0.f;
+            int n = n0 + r;
+            Bs[lk][r] = (n < N && k < K) ? W[(int64_t)n * K + k] : 0.f;
+        }
+        __syncthreads();
+        mma_tile(As, Bs, acc, ty, tx);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int64_t m = m0 + ty * 4 + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int n = n0 + tx * 4 + j;
+            if (n >= N) continue;
+            float v = acc[i][j] + (bias ? bias[n] : 0.f);
+            v = apply_act(v, act);
+            if (res) v += res[m * ldres + n];
+            Y[m * ldy + n] = v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- data gradient
+// dA[m,k] = sum_n dPre[m,n] W[n,k],  dPre = dY * act'(Y)
+__global__ void __launch_bounds__(256)
+linear_bwd_data_kernel(const float* __restrict__ dY, int lddy, const float* __restrict__ Y, int ldy, const float* __restrict__ W,
+                       Cat3Out dA, int64_t M, int N, int K, int act) {
+    __shared__ float As[BK][BM + PADT];   // [n][m]
+    __shared__ float Bs[BK][BN + PADT];   // [n][k]
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int64_t m0 = (int64_t)blockIdx.x * BM;
+    const int kout0 = blockIdx.y * BN;
+    float acc[4][4] = {};
+    for (int n0 = 0; n0 < N; n0 += BK) {
+        {   // dPre tile: contiguous along n
+            const int ln = tid & 15, lr = tid >> 4;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                int r = lr + 16 * j;
+                int64_t m = m0 + r;
+                int n = n0 + ln;
+                float v = 0.f;
+                if (m < M && n < N) {
+                    v = dY[m * lddy + n];
+                    if (act != HNR_ACT_NONE) v *= act_grad_from_out(Y[m * ldy + n], act);
+                }
+                As[ln][r] = v;
+            }
+        }
+        {   // W tile: rows n, contiguous along k
+            const int lc = tid & 63, lr = tid >> 6;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                int nn = lr + 4 * j;
+                int n = n0 + nn, k = kout0 + lc;
+                Bs[nn][lc] = (n < N && k < K) ? W[(int64_t)n * K + k] : 0.f;
+            }
+        }
+        __syncthreads();
+        mma_tile(As, Bs, acc, ty, tx);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int64_t m = m0 + ty * 4 + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int k = kout0 + tx * 4 + j;
+            if (k >= K) continue;
+            int kk = k, s = 0;
+            if (kk >= dA.k[0]) { kk -= dA.k[0]; s = 1; if (kk >= dA.k[1]) { kk -= dA.k[1]; s = 2; } }
+            if (dA.p[s]) dA.p[s][m * dA.ld[s] + kk] = acc[i][j];
+        }
+    }
+}
+
+// ---------------------------------------------------------------- weight gradient
+// dW[n,k] += sum_m dPre[m,n] A[m,k];  db[n] += sum_m dPre[m,n].  grid.z splits M; fp32 atomics.
+__global__ void __launch_bounds__(256)
+linear_bwd_weight_kernel(const float* __restrict__ dY, int lddy, const float* __restrict__ Y, int ldy, Cat3 A,
+                         float* __restrict__ dW, float* __restrict__ db, int64_t M, int N, int K, int act, int64_t m_per_split) {
+    __shared__ float As[BK][BM + PADT];   // [m][n]
+    __shared__ float Bs[BK][BN + PADT];   // [m][k]
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int n0 = blockIdx.x * BM;
+    const int k0 = blockIdx.y * BN;
+    const int64_t mbeg = (int64_t)blockIdx.z * m_per_split;
+    const int64_t mend = (mbeg + m_per_split < M) ? (mbeg + m_per_split) : M;
+    float acc[4][4] = {};
+    float bsum = 0.f;                      // threads with tid<64 own db[n0+tid]
+    const int lc = tid & 63, lr = tid >> 6;
+    for (int64_t mm0 = mbeg; mm0 < mend; mm0 += BK) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int r = lr + 4 * j;
+            int64_t m = mm0 + r;
+            int n = n0 + lc, k = k0 + lc;
+            float v = 0.f;
+            if (m < mend && n < N) {
+                v = dY[m * lddy + n];
+                if (act != HNR_ACT_NONE) v *= act_grad_from_out(Y[m * ldy + n], act);
+            }
+            As[r][lc] = v;
+            Bs[r][lc] = (m < mend && k < K) ? cat_load(A, m, k) : 0.f;
+        }
+        __syncthreads();
+        mma_tile(As, Bs, acc, ty, tx);
+        if (db && blockIdx.y == 0 && tid < 64) {
+#pragma unroll
+            for (int r = 0; r < BK; ++r) bsum += As[r][tid];
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int n = n0 + ty * 4 + i;
+        if (n >= N) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int k = k0 + tx * 4 + j;
+            if (k >= K) continue;
+            atomicAdd(&dW[(int64_t)n * K + k], acc[i][j]);
+        }
+    }
+    if (db && blockIdx.y == 0 && tid < 64 && n0 + tid < N) atomicAdd(&db[n0 + tid], bsum);
+}
+
+bool cat_ok(const float* const* p, const int64_t* ld, const int64_t* k, int64_t K) {
+    int64_t s = 0;
+    for (int i = 0; i < 3; ++i) {
+        if (k[i] < 0) return false;
+        if (k[i] > 0 && ld[i] < k[i]) return false;
+        s += k[i];
+    }
+    (void)p;
+    return s == K;
+}
+
+}  // namespace
+
+extern "C" int hnr_linear_fwd(const float* const* a_ptr, const int64_t* a_ld, const int64_t* a_k, const int64_t* a_mod, const float* W, const float* bias,
+                              const float* res, int64_t ldres, float* Y, int64_t ldy, int64_t M, int64_t N, int64_t K, int act,
+                              void* stream) {
+    HNR_CHECK_ARG(M >= 0 && N > 0 && K > 0 && ldy >= N, "linear_fwd: bad shape");
+    HNR_CHECK_ARG(cat_ok(a_ptr, a_ld, a_k, K), "linear_fwd: concat widths must sum to K");
+    if (M == 0) return HNR_OK;
+    Cat3 A;
+    for (int i = 0; i < 3; ++i) { A.p[i] = a_ptr[i]; A.ld[i] = (int)a_ld[i]; A.k[i] = (int)a_k[i]; A.mod[i] = a_mod ? a_mod[i] : 0; }
+    HNR_CHECK_ARG(!(res && act != HNR_ACT_NONE), "linear_fwd: residual only with act=none");
+    dim3 grid((unsigned)hnr_cdiv(M, BM), (unsigned)hnr_cdiv(N, BN));
+    linear_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A, W, bias, res, (int)ldres, Y, (int)ldy, M, (int)N, (int)K, act);
+    HNR_CHECK_LAUNCH("linear_fwd");
+    return HNR_OK;
+}
+
+extern "C" int hnr_linear_bwd_data(const float* dY, int64_t lddy, const float* Y, int64_t ldy, const float* W, float* const* da_ptr,
+                                   const int64_t* da_ld, const int64_t* a_k, int64_t M, int64_t N, int64_t K, int act, void* stream) {
+    HNR_CHECK_ARG(M >= 0 && N > 0 && K > 0, "linear_bwd_data: bad shape");
+    HNR_CHECK_ARG(cat_ok(nullptr, da_ld, a_k, K), "linear_bwd_data: concat widths must sum to K");
+    if (M == 0) return HNR_OK;
+    Cat3Out dA;
+    for (int i = 0; i < 3; ++i) { dA.p[i] = da_ptr[i]; dA.ld[i] = (int)da_ld[i]; dA.k[i] = (int)a_k[i]; }
+    dim3 grid((unsigned)hnr_cdiv(M, BM), (unsigned)hnr_cdiv(K, BN));
+    linear_bwd_data_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dY, (int)lddy, Y, (int)ldy, W, dA, M, (int)N, (int)K, act);
+    HNR_CHECK_LAUNCH("linear_bwd_data");
+    return HNR_OK;
+}
+
+extern "C" int hnr_linear_bwd_weight(const float* dY, int64_t lddy, const float* Y, int64_t ldy, const float* const* a_ptr,
+                                     const int64_t* a_ld, const int64_t* a_k, const int64_t* a_mod, float* dW, float* db, int64_t M, int64_t N, int64_t K,
+                                     int act, void* stream) {
+    HNR_CHECK_ARG(M >= 0 && N > 0 && K > 0, "linear_bwd_weight: bad shape");
+    HNR_CHECK_ARG(cat_ok(a_ptr, a_ld, a_k, K), "linear_bwd_weight: concat widths must sum to K");
+    if (M == 0) return HNR_OK;
+    Cat3 A;
+    for (int i = 0; i < 3; ++i) { A.p[i] = a_ptr[i]; A.ld[i] = (int)a_ld[i]; A.k[i] = (int)a_k[i]; A.mod[i] = a_mod ? a_mod[i] : 0; }
+    const int64_t tiles = hnr_cdiv(N, BM) * hnr_cdiv(K, BN);
+    int64_t splits = (4 * HNR_NUM_SMS + tiles - 1) / tiles;          // aim at >= 4 CTAs per SM
+    int64_t max_splits = hnr_cdiv(M, 256);
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    if (splits > 65535) splits = 65535;
+    int64_t m_per = hnr_cdiv(hnr_cdiv(M, splits), BK) * BK;
+    splits = hnr_cdiv(M, m_per);
+    dim3 grid((unsigned)hnr_cdiv(N, BM), (unsigned)hnr_cdiv(K, BN), (unsigned)splits);
+    linear_bwd_weight_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dY, (int)lddy, Y, (int)ldy, A, dW, db, M, (int)N, (int)K, act,
+                                                                    m_per);
+    HNR_CHECK_LAUNCH("linear_bwd_weight");
+    return HNR_OK;
+}

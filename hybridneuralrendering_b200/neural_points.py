@@ -1,0 +1,174 @@
+"""Neural point cloud container -- host-side mirror of models/neural_points/neural_points.py.
+
+Same parameter names (so the reference's checkpoints load unchanged): ``xyz (N,3)``,
+``points_embeding (1,N,F)``, ``points_conf (1,N,1)``, ``points_dir (1,N,3)``, ``points_color (1,N,3)``,
+``Rw2c (3,3)``.  Same public methods: ``forward(inputs) -> 14-tuple`` (:702-733), ``set_points``,
+``editing_set_points``, ``prune``, ``grow_points``, ``reset_querier``, ``null_grad``, ``reg_loss``.
+
+``forward`` materialises the gathered (1,R'',SR,K,C) tensors because that is what the reference's
+API returns; the fused renderer (``NeuralPointsRayMarching``) calls ``query`` instead and lets the
+aggregation kernels gather straight from the point tables (168 B per neighbour, never the 304 MB
+``torch.cat`` of the whole cloud the reference does at :712).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .querier import QueryExtras, lighting_fast_querier
+
+
+class NeuralPoints(nn.Module):
+    def __init__(self, num_channels, size, opt, device, checkpoint=None, feature_init_method='rand', reg_weight=0., feedforward=0):
+        super().__init__()
+        assert isinstance(size, int), 'size must be int'
+        self.opt = opt
+        self.grid_vox_sz = 0
+        self.points_conf = self.points_dir = self.points_color = self.eulers = self.Rw2c = None
+        self.xyz = None
+        self.points_embeding = None
+        self.device = torch.device(device)
+        if checkpoint:
+            saved = torch.load(checkpoint, map_location=self.device) if isinstance(checkpoint, str) else checkpoint
+            g = lambda k: saved.get("neural_points." + k)
+            if g("xyz") is not None:
+                self.xyz = nn.Parameter(g("xyz"))
+                self.xyz.requires_grad = getattr(opt, "xyz_grad", 0) > 0
+            for name, flag in (("points_embeding", "feat_grad"), ("points_conf", "conf_grad"), ("points_dir", "dir_grad"),
+                               ("points_color", "color_grad")):
+                if g(name) is not None:
+                    p = nn.Parameter(g(name))
+                    p.requires_grad = getattr(opt, flag, 1) > 0
+                    setattr(self, name, p)
+            if g("eulers") is not None:
+                self.eulers = nn.Parameter(g("eulers"), requires_grad=False)
+            if g("Rw2c") is not None:
+                self.Rw2c = nn.Parameter(g("Rw2c"), requires_grad=False)
+            elif self.xyz is not None:
+                self.Rw2c = torch.eye(3, device=self.xyz.device, dtype=self.xyz.dtype)
+        self.reg_weight = reg_weight
+        if list(opt.query_size)[0] == 0:
+            opt.query_size = opt.kernel_size
+        if getattr(opt, "wcoord_query", 1) <= 0:
+            raise NotImplementedError("only the world-coordinate query (wcoord_query=1) is provided; every shipped config uses it")
+        self.lighting_fast_querier = lighting_fast_querier
+        self.querier = lighting_fast_querier(self.device, opt)
+
+    # ------------------------------------------------------------------ point-set management
+    def reset_querier(self):
+        self.querier.clean_up()
+        del self.querier
+        self.querier = self.lighting_fast_querier(self.device, self.opt)
+
+    def _flag(self, name):
+        return getattr(self.opt, name, 1) > 0
+
+    def prune(self, thresh):
+        mask = self.points_conf[0, ..., 0] >= thresh
+        self.xyz = nn.Parameter(self.xyz[mask, :], requires_grad=getattr(self.opt, "xyz_grad", 0) > 0)
+        for name, flag in (("points_embeding", "feat_grad"), ("points_conf", "conf_grad"), ("points_dir", "dir_grad"),
+                           ("points_color", "color_grad")):
+            t = getattr(self, name)
+            if t is not None:
+                setattr(self, name, nn.Parameter(t[:, mask, :], requires_grad=self._flag(flag)))
+        if self.eulers is not None and self.eulers.dim() > 1:
+            self.eulers = nn.Parameter(self.eulers[mask, :], requires_grad=False)
+        if self.Rw2c is not None and self.Rw2c.dim() > 2:
+            self.Rw2c = nn.Parameter(self.Rw2c[mask, :], requires_grad=False)
+        self.querier.invalidate()
+
+    def grow_points(self, add_xyz, add_embedding, add_color, add_dir, add_conf, add_eulers=None, add_Rw2c=None):
+        self.xyz = nn.Parameter(torch.cat([self.xyz, add_xyz], dim=0), requires_grad=getattr(self.opt, "xyz_grad", 0) > 0)
+        for name, flag, add in (("points_embeding", "feat_grad", add_embedding), ("points_conf", "conf_grad", add_conf),
+                                ("points_dir", "dir_grad", add_dir), ("points_color", "color_grad", add_color)):
+            t = getattr(self, name)
+            if t is not None:
+                setattr(self, name, nn.Parameter(torch.cat([t, add[None, ...]], dim=1), requires_grad=self._flag(flag)))
+        if self.eulers is not None and self.eulers.dim() > 1:
+            self.eulers = nn.Parameter(torch.cat([self.eulers, add_eulers[None, ...]], dim=1), requires_grad=False)
+        if self.Rw2c is not None and self.Rw2c.dim() > 2:
+            self.Rw2c = nn.Parameter(torch.cat([self.Rw2c, add_Rw2c[None, ...]], dim=1), requires_grad=False)
+        self.querier.invalidate()
+
+    def set_points(self, points_xyz, points_embeding, points_color=None, points_dir=None, points_conf=None, parameter=False,
+                   Rw2c=None, eulers=None):
+        opt = self.opt
+        if points_embeding.shape[-1] > opt.point_features_dim:
+            points_embeding = points_embeding[..., :opt.point_features_dim]
+        dc = getattr(opt, "default_conf", -1.0)
+        if 0.0 < dc <= 1.0 and points_conf is not None:
+            points_conf = torch.ones_like(points_conf) * dc
+        wrap = (lambda t, flag: nn.Parameter(t, requires_grad=self._flag(flag))) if parameter else (lambda t, flag: t)
+        self.xyz = nn.Parameter(points_xyz, requires_grad=getattr(opt, "xyz_grad", 0) > 0) if parameter else points_xyz
+        for name, val, mode, flag in (("points_conf", points_conf, opt.point_conf_mode, "conf_grad"),
+                                      ("points_dir", points_dir, opt.point_dir_mode, "dir_grad"),
+                                      ("points_color", points_color, opt.point_color_mode, "color_grad")):
+            if val is None:
+                continue
+            val = wrap(val, flag)
+            if "0" in list(mode):
+                points_embeding = torch.cat([val, points_embeding], dim=-1)
+            if "1" in list(mode):
+                setattr(self, name, val)
+        self.points_embeding = wrap(points_embeding, "feat_grad")
+        if Rw2c is None:
+            self.Rw2c = torch.eye(3, device=points_xyz.device, dtype=points_xyz.dtype)
+        else:
+            self.Rw2c = nn.Parameter(Rw2c, requires_grad=False)
+        self.querier.invalidate()
+
+    def editing_set_points(self, points_xyz, points_embeding, points_color=None, points_dir=None, points_conf=None,
+                           parameter=False, Rw2c=None, eulers=None):
+        dc = getattr(self.opt, "default_conf", -1.0)
+        if 0.0 < dc <= 1.0 and points_conf is not None:
+            points_conf = torch.ones_like(points_conf) * dc
+        self.xyz, self.points_embeding = points_xyz, points_embeding
+        self.points_dir, self.points_conf, self.points_color = points_dir, points_conf, points_color
+        self.Rw2c = torch.eye(3, device=points_xyz.device, dtype=points_xyz.dtype) if Rw2c is None else Rw2c
+        self.querier.invalidate()
+
+    def null_grad(self):
+        self.points_embeding.grad = None
+        self.xyz.grad = None
+
+    def reg_loss(self):
+        return self.reg_weight * torch.mean(torch.pow(self.points_embeding, 2))
+
+    def w2pers(self, point_xyz, camrotc2w, campos):
+        shift = point_xyz[None, ...] - campos[:, None, :]
+        xyz = torch.sum(camrotc2w[:, None, :, :] * shift[:, :, :, None], dim=-2)
+        return torch.stack([xyz[:, :, 0] / xyz[:, :, 2], xyz[:, :, 1] / xyz[:, :, 2], xyz[:, :, 2]], dim=-1)
+
+    # ------------------------------------------------------------------ query
+    def query(self, inputs: Dict, near: Optional[float] = None, far: Optional[float] = None, ts=None):
+        """fused-path entry: run the voxel query only.  `near`/`far` may be passed as python floats to
+        avoid a device->host read of inputs["near"/"far"] (the reference reads them every call, :707).
+        Returns (sample_pidx (1,R'',SR,K) i32, sample_loc (pers), sample_loc_w, sample_ray_dirs,
+        ray_mask (1,R) i8, vsize, extras)."""
+        if near is None:
+            near = float(torch.min(inputs["near"]).item())
+        if far is None:
+            far = float(torch.max(inputs["far"]).item())
+        q = self.querier
+        out = q.query_points(inputs.get("pixel_idx"), None, self.xyz[None, ...], None, inputs.get("h"), inputs.get("w"),
+                             inputs.get("intrinsic"), near, far, inputs["raydir"], inputs["campos"], inputs["camrotc2w"], ts=ts)
+        return out[0], out[1], out[2], out[3], out[4], out[5], q.last
+
+    def forward(self, inputs):
+        """(:702-733) returns the reference's 14-tuple with materialised neighbour gathers."""
+        camrotc2w, campos = inputs["camrotc2w"], inputs["campos"]
+        sample_pidx, sample_loc, sample_loc_w, sample_ray_dirs, ray_mask, vsize, _ = self.query(inputs)
+        point_xyz_pers = self.w2pers(self.xyz, camrotc2w, campos)
+        sample_pnt_mask = sample_pidx >= 0
+        B, R, SR, K = sample_pidx.shape
+        idx = torch.clamp(sample_pidx, min=0).view(-1).long()
+        g = lambda t: None if t is None else torch.index_select(t, 1, idx).view(B, R, SR, K, t.shape[2])
+        sampled_embedding = g(self.points_embeding)
+        sampled_xyz = torch.index_select(self.xyz[None, ...], 1, idx).view(B, R, SR, K, 3)
+        sampled_xyz_pers = torch.index_select(point_xyz_pers, 1, idx).view(B, R, SR, K, 3)
+        sampled_Rw2c = self.Rw2c if self.Rw2c.dim() == 2 else torch.index_select(self.Rw2c, 0, idx).view(B, R, SR, K, 3, 3)
+        return (g(self.points_color), sampled_Rw2c, g(self.points_dir), g(self.points_conf), sampled_embedding, sampled_xyz_pers,
+                sampled_xyz, sample_pnt_mask, sample_loc, sample_loc_w, sample_ray_dirs, ray_mask, vsize, self.grid_vox_sz)

@@ -1,0 +1,372 @@
+"""torch.autograd.Function wrappers around the libhnr kernels.
+
+Every function here launches hand-written CUDA through the C ABI (``_lib``); there is no torch
+fallback.  torch is used for allocation, streams and the autograd tape only.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import check, i64_array, lib, ptr, ptr_array, require_cuda, stream
+
+ACT_NONE, ACT_LRELU, ACT_SIGMOID, ACT_COLOR = 0, 1, 2, 3
+X0_W, E_W, HID, X5_W, AUX_C = 284, 7, 256, 280, 45
+
+# counts kernels launched through the C ABI (bench.py reports it as gpu_launches)
+LAUNCHES = 0
+
+
+def _count(n: int = 1):
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _rows2d(t: torch.Tensor) -> torch.Tensor:
+    """2-D fp32 view with unit inner stride (row stride may exceed the width)."""
+    assert t.dim() == 2
+    if t.dtype != torch.float32 or t.stride(1) != 1:
+        t = t.float().contiguous()
+    return t
+
+
+def make_cam(campos: torch.Tensor, camrot: torch.Tensor, rw2c: Optional[torch.Tensor]) -> torch.Tensor:
+    """21-float device block [campos(3), camrot(9) c2w rotation, rt(9) = Rw2c^T]; built with device
+    ops only (no host sync)."""
+    dev = campos.device
+    rt = rw2c.detach().float().t().reshape(-1) if rw2c is not None else torch.eye(3, device=dev).reshape(-1)
+    return torch.cat([campos.detach().float().reshape(-1)[:3], camrot.detach().float().reshape(-1)[:9], rt.to(dev)]).contiguous()
+
+
+# --------------------------------------------------------------------------------------------
+# dense layer
+# --------------------------------------------------------------------------------------------
+class LinearFn(torch.autograd.Function):
+    """y = act(concat(srcs) W^T + b [+ res]).  `mods[i] > 0`: source i has mods[i] rows reused by
+    every block of mods[i] output rows."""
+
+    @staticmethod
+    def forward(ctx, W, b, res, act: int, M: int, mods: Tuple[int, ...], *srcs):
+        srcs = [_rows2d(s) for s in srcs]
+        assert 1 <= len(srcs) <= 3
+        W = _f32c(W)
+        N, K = W.shape
+        ks = [s.shape[1] for s in srcs] + [0] * (3 - len(srcs))
+        assert sum(ks) == K, (ks, K)
+        require_cuda(W, *srcs)
+        Y = torch.empty((M, N), device=W.device, dtype=torch.float32)
+        padded = list(srcs) + [None] * (3 - len(srcs))
+        lds = [s.stride(0) if s is not None else 0 for s in padded]
+        modl = list(mods) + [0] * (3 - len(mods))
+        resv = _rows2d(res) if res is not None else None
+        bc = _f32c(b) if b is not None else None
+        check(lib().hnr_linear_fwd(ptr_array(padded), i64_array(lds), i64_array(ks), i64_array(modl), ptr(W), ptr(bc), ptr(resv),
+                                   resv.stride(0) if resv is not None else 0, ptr(Y), N, M, N, K, act, stream()), "linear_fwd")
+        _count()
+        ctx.act, ctx.M, ctx.mods, ctx.nsrc, ctx.has_res, ctx.has_b = act, M, modl, len(srcs), res is not None, b is not None
+        ctx.save_for_backward(W, Y, *srcs)
+        return Y
+
+    @staticmethod
+    def backward(ctx, dY):
+        W, Y, *srcs = ctx.saved_tensors
+        dY = _rows2d(dY)
+        N, K = W.shape
+        M, act = ctx.M, ctx.act
+        ks = [s.shape[1] for s in srcs] + [0] * (3 - len(srcs))
+        padded = list(srcs) + [None] * (3 - len(srcs))
+        lds = [s.stride(0) if s is not None else 0 for s in padded]
+        need_src = [ctx.needs_input_grad[6 + i] for i in range(ctx.nsrc)]
+        d_srcs: List[Optional[torch.Tensor]] = [None] * ctx.nsrc
+        if any(need_src) and M > 0:
+            outs = [torch.empty((M, ks[i]), device=W.device, dtype=torch.float32) if need_src[i] else None for i in range(ctx.nsrc)]
+            outs_p = outs + [None] * (3 - ctx.nsrc)
+            check(lib().hnr_linear_bwd_data(ptr(dY), dY.stride(0), ptr(Y), Y.stride(0), ptr(W), ptr_array(outs_p),
+                                            i64_array([o.stride(0) if o is not None else 0 for o in outs_p]), i64_array(ks), M, N, K, act,
+                                            stream()), "linear_bwd_data")
+            _count()
+            for i in range(ctx.nsrc):
+                if outs[i] is not None and ctx.mods[i] > 0:
+                    outs[i] = outs[i].view(-1, ctx.mods[i], ks[i]).sum(dim=0)
+                d_srcs[i] = outs[i]
+        elif any(need_src):
+            d_srcs = [torch.zeros_like(s) if n else None for s, n in zip(srcs, need_src)]
+        dW = db = None
+        if ctx.needs_input_grad[0] or (ctx.has_b and ctx.needs_input_grad[1]):
+            dW = torch.zeros_like(W)
+            db = torch.zeros(N, device=W.device, dtype=torch.float32) if ctx.has_b else None
+            if M > 0:
+                check(lib().hnr_linear_bwd_weight(ptr(dY), dY.stride(0), ptr(Y), Y.stride(0), ptr_array(padded), i64_array(lds),
+                                                  i64_array(ks), i64_array(ctx.mods), ptr(dW), ptr(db), M, N, K, act, stream()),
+                      "linear_bwd_weight")
+                _count()
+        d_res = dY if ctx.has_res else None
+        return (dW, db, d_res, None, None, None, *d_srcs)
+
+
+def linear(srcs: Sequence[torch.Tensor], W, b, act: int = ACT_NONE, res=None, mods: Sequence[int] = (), M: Optional[int] = None):
+    if M is None:
+        M = srcs[0].shape[0]
+    mods = tuple(mods) if mods else tuple([0] * len(srcs))
+    return LinearFn.apply(W, b, res, act, M, mods, *srcs)
+
+
+# --------------------------------------------------------------------------------------------
+# neighbour weights / features
+# --------------------------------------------------------------------------------------------
+class NbrWeightsFn(torch.autograd.Function):
+    """-> weight (S,K) [no grad], conf_coefficient (S,K) [straight-through grad to conf], valid (S) u8."""
+
+    @staticmethod
+    def forward(ctx, xyz, conf, pidx, mask, loc_w):
+        S, K = pidx.shape
+        require_cuda(xyz, pidx, loc_w)
+        weight = torch.empty((S, K), device=xyz.device, dtype=torch.float32)
+        confc = torch.empty((S, K), device=xyz.device, dtype=torch.float32)
+        valid = torch.empty((S,), device=xyz.device, dtype=torch.uint8)
+        check(lib().hnr_nbr_weights(ptr(xyz), ptr(conf), ptr(pidx), ptr(mask), ptr(loc_w), S, K, ptr(weight), ptr(confc), ptr(valid),
+                                    stream()), "nbr_weights")
+        _count()
+        ctx.save_for_backward(pidx)
+        ctx.n_conf = conf.numel() if conf is not None else 0
+        ctx.mark_non_differentiable(weight, valid)
+        return weight, confc, valid
+
+    @staticmethod
+    def backward(ctx, g_weight, g_confc, g_valid):
+        (pidx,) = ctx.saved_tensors
+        d_conf = None
+        if ctx.needs_input_grad[1] and g_confc is not None:
+            S, K = pidx.shape
+            g = _f32c(g_confc)
+            d_conf = torch.zeros(ctx.n_conf, device=pidx.device, dtype=torch.float32)
+            check(lib().hnr_conf_bwd(None, None, None, ptr(pidx), ptr(g), 0, S, K, ptr(d_conf), stream()), "conf_bwd")
+            _count()
+        return None, d_conf, None, None, None
+
+
+class NbrFeaturesFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, emb, color, dirs, xyz, xyz_pers, pidx, mask, vlist, loc_w, loc_pers, raydirs, cam):
+        Nv, K = vlist.shape[0], pidx.shape[1]
+        require_cuda(emb, color, dirs, xyz, pidx, vlist)
+        X0 = torch.empty((Nv * K, X0_W), device=emb.device, dtype=torch.float32)
+        E = torch.empty((Nv * K, E_W), device=emb.device, dtype=torch.float32)
+        check(lib().hnr_nbr_features(ptr(xyz), ptr(xyz_pers), ptr(emb), ptr(color), ptr(dirs), ptr(pidx), ptr(vlist), ptr(loc_w),
+                                     ptr(loc_pers), ptr(raydirs), ptr(cam), Nv, K, emb.shape[-1], ptr(X0), ptr(E), stream()), "nbr_features")
+        _count()
+        ctx.cam, ctx.Nv, ctx.K = cam, Nv, K
+        ctx.shapes = (emb.shape, color.shape, dirs.shape)
+        ctx.save_for_backward(emb, pidx, mask if mask is not None else torch.empty(0, device=emb.device), vlist, raydirs)
+        ctx.has_mask = mask is not None
+        return X0, E
+
+    @staticmethod
+    def backward(ctx, dX0, dE):
+        emb, pidx, mask, vlist, raydirs = ctx.saved_tensors
+        dX0, dE = _f32c(dX0), _f32c(dE)
+        ne, nc, nd = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        d_emb = torch.zeros(ctx.shapes[0], device=emb.device, dtype=torch.float32) if ne else None
+        d_col = torch.zeros(ctx.shapes[1], device=emb.device, dtype=torch.float32) if nc else None
+        d_dir = torch.zeros(ctx.shapes[2], device=emb.device, dtype=torch.float32) if nd else None
+        if ne or nc or nd:
+            check(lib().hnr_nbr_features_bwd(ptr(dX0), ptr(dE), ptr(emb), ptr(pidx), ptr(mask) if ctx.has_mask else None, ptr(vlist),
+                                             ptr(raydirs), ptr(ctx.cam), ctx.Nv, ctx.K, ptr(d_emb), ptr(d_col), ptr(d_dir), stream()),
+                  "nbr_features_bwd")
+            _count()
+        return d_emb, d_col, d_dir, None, None, None, None, None, None, None, None, None
+
+
+class AlphaKSumFn(torch.autograd.Function):
+    """H (Nv*K,256), weight (S,K), confc (S,K) -> sigma (Nv,1), X5 (Nv,280)."""
+
+    @staticmethod
+    def forward(ctx, H, confc, w_alpha, b_alpha, weight, vlist, raydirs, cam):
+        Nv, K = vlist.shape[0], weight.shape[1]
+        H = _f32c(H)
+        w_alpha_c, b_alpha_c, confc_c = _f32c(w_alpha).view(-1), _f32c(b_alpha).view(-1), _f32c(confc)
+        sigma = torch.empty((Nv, 1), device=H.device, dtype=torch.float32)
+        X5 = torch.empty((Nv, X5_W), device=H.device, dtype=torch.float32)
+        araw = torch.empty((Nv * K,), device=H.device, dtype=torch.float32)
+        check(lib().hnr_alpha_ksum_fwd(ptr(H), ptr(weight), ptr(confc_c), ptr(vlist), ptr(w_alpha_c), ptr(b_alpha_c), ptr(raydirs), ptr(cam),
+                                       Nv, K, H.shape[1], ptr(sigma), ptr(X5), ptr(araw), stream()), "alpha_ksum_fwd")
+        _count()
+        ctx.save_for_backward(H, confc_c, w_alpha_c, weight, vlist, araw)
+        ctx.wshape, ctx.bshape = w_alpha.shape, b_alpha.shape
+        return sigma, X5
+
+    @staticmethod
+    def backward(ctx, d_sigma, dX5):
+        H, confc, w_alpha, weight, vlist, araw = ctx.saved_tensors
+        Nv, K = vlist.shape[0], weight.shape[1]
+        d_sigma, dX5 = _f32c(d_sigma), _f32c(dX5)
+        dH = torch.empty_like(H)
+        d_wc = torch.empty((Nv, K), device=H.device, dtype=torch.float32)
+        d_wa = torch.zeros(HID, device=H.device, dtype=torch.float32)
+        d_ba = torch.zeros(1, device=H.device, dtype=torch.float32)
+        check(lib().hnr_alpha_ksum_bwd(ptr(H), ptr(weight), ptr(confc), ptr(vlist), ptr(w_alpha), ptr(araw), ptr(d_sigma), ptr(dX5), Nv, K,
+                                       H.shape[1], ptr(dH), ptr(d_wc), ptr(d_wa), ptr(d_ba), stream()), "alpha_ksum_bwd")
+        _count()
+        d_confc = None
+        if ctx.needs_input_grad[1]:
+            vl = vlist.long()
+            d_confc = torch.zeros_like(confc)
+            d_confc.index_copy_(0, vl, d_wc * weight.index_select(0, vl))
+        return dH, d_confc, d_wa.view(ctx.wshape), d_ba.view(ctx.bshape), None, None, None, None
+
+
+# --------------------------------------------------------------------------------------------
+# image branch
+# --------------------------------------------------------------------------------------------
+def project_views(loc_w: torch.Tensor, w2c: torch.Tensor, Kmat: torch.Tensor, campos: torch.Tensor, campos_n: torch.Tensor):
+    """loc_w (S,3), w2c (V,4,4), Kmat (3,3), campos (3,), campos_n (V,3) -> xy (V,S,2), delta (V,S,3)."""
+    S, V = loc_w.shape[0], w2c.shape[0]
+    loc_w, w2c, Kmat, campos, campos_n = map(_f32c, (loc_w, w2c, Kmat, campos, campos_n))
+    require_cuda(loc_w, w2c, Kmat, campos, campos_n)
+    xy = torch.empty((V, S, 2), device=loc_w.device, dtype=torch.float32)
+    delta = torch.empty((V, S, 3), device=loc_w.device, dtype=torch.float32)
+    check(lib().hnr_project_views(ptr(loc_w), ptr(w2c), ptr(Kmat), ptr(campos), ptr(campos_n), V, S, ptr(xy), ptr(delta), stream()),
+          "project_views")
+    _count()
+    return xy, delta
+
+
+class ImageGatherFn(torch.autograd.Function):
+    """levels NHWC (V,H,W,3),(V,h1,w1,6),(V,h2,w2,12),(V,h3,w3,24); xy (V,S,2) -> aux (V,Nv,45), ok (V,Nv)."""
+
+    @staticmethod
+    def forward(ctx, l0, l1, l2, l3, xy, vlist):
+        lv = [_f32c(l) for l in (l0, l1, l2, l3)]
+        require_cuda(*lv, xy, vlist)
+        V, S, Nv = xy.shape[0], xy.shape[1], vlist.shape[0]
+        hw = []
+        for l in lv:
+            hw += [l.shape[1], l.shape[2]]
+        aux = torch.empty((V, Nv, AUX_C), device=xy.device, dtype=torch.float32)
+        ok = torch.empty((V, Nv), device=xy.device, dtype=torch.float32)
+        check(lib().hnr_image_gather_fwd(ptr_array(lv), i64_array(hw), ptr(xy), ptr(vlist), V, S, Nv, ptr(aux), ptr(ok), stream()),
+              "image_gather_fwd")
+        _count()
+        ctx.hw, ctx.shapes, ctx.dims = hw, [l.shape for l in lv], (V, S, Nv)
+        ctx.save_for_backward(xy, vlist)
+        ctx.mark_non_differentiable(ok)
+        return aux, ok
+
+    @staticmethod
+    def backward(ctx, d_aux, d_ok):
+        xy, vlist = ctx.saved_tensors
+        V, S, Nv = ctx.dims
+        grads = [None] + [torch.zeros(s, device=xy.device, dtype=torch.float32) for s in ctx.shapes[1:]]
+        d_aux = _f32c(d_aux)
+        check(lib().hnr_image_gather_bwd(ptr_array(grads), i64_array(ctx.hw), ptr(xy), ptr(vlist), ptr(d_aux), V, S, Nv, stream()),
+              "image_gather_bwd")
+        _count()
+        return None, grads[1], grads[2], grads[3], None, None
+
+
+class BlendFn(torch.autograd.Function):
+    """aux (V,Nv,45), sig (V*Nv,1), ok (V,Nv), keep (Nv) u8|None -> merged (Nv,45)."""
+
+    @staticmethod
+    def forward(ctx, aux, sig, ok, keep):
+        aux, sig = _f32c(aux), _f32c(sig)
+        V, Nv = aux.shape[0], aux.shape[1]
+        merged = torch.empty((Nv, AUX_C), device=aux.device, dtype=torch.float32)
+        check(lib().hnr_blend_fwd(ptr(aux), ptr(sig), ptr(ok), ptr(keep), V, Nv, ptr(merged), stream()), "blend_fwd")
+        _count()
+        ctx.save_for_backward(aux, sig, ok, keep if keep is not None else torch.empty(0, device=aux.device))
+        ctx.has_keep = keep is not None
+        return merged
+
+    @staticmethod
+    def backward(ctx, d_merged):
+        aux, sig, ok, keep = ctx.saved_tensors
+        V, Nv = aux.shape[0], aux.shape[1]
+        d_aux = torch.empty_like(aux)
+        d_sig = torch.empty_like(sig)
+        check(lib().hnr_blend_bwd(ptr(aux), ptr(sig), ptr(ok), ptr(keep) if ctx.has_keep else None, ptr(_f32c(d_merged)), V, Nv,
+                                  ptr(d_aux), ptr(d_sig), stream()), "blend_bwd")
+        _count()
+        return d_aux, d_sig, None, None
+
+
+# --------------------------------------------------------------------------------------------
+# compositing
+# --------------------------------------------------------------------------------------------
+class CompositeFn(torch.autograd.Function):
+    """feats (R,SR,4); valid (R,SR) u8; either z (R,SR) view with element stride (camera depth) or
+    dist (R,SR).  -> ray_color (R,3), opacity, acc_transmission, blend_weight (R,SR), bg_T (R), dist."""
+
+    @staticmethod
+    def forward(ctx, feats, valid, z, z_stride: int, dist, bg, vsize_z: float, unit_mode: int):
+        feats = _f32c(feats)
+        R, SR = feats.shape[0], feats.shape[1]
+        require_cuda(feats, valid)
+        dev = feats.device
+        color = torch.empty((R, 3), device=dev, dtype=torch.float32)
+        opacity = torch.empty((R, SR), device=dev, dtype=torch.float32)
+        accT = torch.empty((R, SR), device=dev, dtype=torch.float32)
+        bw = torch.empty((R, SR), device=dev, dtype=torch.float32)
+        bgT = torch.empty((R,), device=dev, dtype=torch.float32)
+        dist_out = torch.empty((R, SR), device=dev, dtype=torch.float32)
+        bgc = _f32c(bg).view(-1) if bg is not None else None
+        check(lib().hnr_composite_fwd(ptr(feats), ptr(valid), ptr(z), z_stride, ptr(dist), ptr(bgc), float(vsize_z), int(unit_mode), R, SR,
+                                      ptr(color), ptr(opacity), ptr(accT), ptr(bw), ptr(bgT), ptr(dist_out), stream()), "composite_fwd")
+        _count()
+        ctx.save_for_backward(feats, valid, dist_out, accT, bgT, bgc if bgc is not None else torch.empty(0, device=dev))
+        ctx.has_bg = bgc is not None
+        ctx.mark_non_differentiable(dist_out)
+        return color, opacity, accT, bw, bgT, dist_out
+
+    @staticmethod
+    def backward(ctx, g_color, g_opacity, g_accT, g_bw, g_bgT, g_dist):
+        feats, valid, dist, accT, bgT, bg = ctx.saved_tensors
+        R, SR = feats.shape[0], feats.shape[1]
+        g_feats = torch.empty_like(feats)
+        c = lambda t: _f32c(t) if t is not None else None
+        gc = c(g_color) if g_color is not None else torch.zeros((R, 3), device=feats.device)
+        check(lib().hnr_composite_bwd(ptr(feats), ptr(valid), ptr(dist), ptr(accT), ptr(bgT), ptr(bg) if ctx.has_bg else None, ptr(gc),
+                                      ptr(c(g_opacity)), ptr(c(g_bgT)), ptr(c(g_bw)), ptr(c(g_accT)), R, SR, ptr(g_feats), stream()),
+              "composite_bwd")
+        _count()
+        return g_feats, None, None, None, None, None, None, None
+
+
+# --------------------------------------------------------------------------------------------
+# blur
+# --------------------------------------------------------------------------------------------
+class BlurSelectFn(torch.autograd.Function):
+    """pred, gt (S*S,3) on the patch raster; kernels (Nk,ks,ks) -> best candidate per patch."""
+
+    @staticmethod
+    def forward(ctx, pred, gt, kernels, patch_num: int, patch_size: int):
+        pred, gt, kernels = _f32c(pred), _f32c(gt), _f32c(kernels)
+        require_cuda(pred, gt, kernels)
+        Nk, ks = kernels.shape[0], kernels.shape[1]
+        out = torch.empty_like(pred)
+        sel = torch.empty((patch_num * patch_num,), device=pred.device, dtype=torch.int32)
+        check(lib().hnr_blur_select_fwd(ptr(pred), ptr(gt), ptr(kernels), patch_num, patch_size, Nk, ks, ptr(out), ptr(sel), stream()),
+              "blur_select_fwd")
+        _count()
+        ctx.save_for_backward(kernels, sel)
+        ctx.geom = (patch_num, patch_size, Nk, ks)
+        ctx.mark_non_differentiable(sel)
+        return out, sel
+
+    @staticmethod
+    def backward(ctx, g_out, g_sel):
+        kernels, sel = ctx.saved_tensors
+        pn, ps, Nk, ks = ctx.geom
+        g_out = _f32c(g_out)
+        g_pred = torch.empty_like(g_out)
+        check(lib().hnr_blur_select_bwd(ptr(g_out), ptr(kernels), ptr(sel), pn, ps, Nk, ks, ptr(g_pred), stream()), "blur_select_bwd")
+        _count()
+        return g_pred, None, None, None, None

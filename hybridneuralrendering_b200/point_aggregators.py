@@ -1,0 +1,266 @@
+"""PointAggregator -- host-side mirror of models/aggregators/point_aggregators.py.
+
+Same constructor ``PointAggregator(opt)``, same sub-module names and layer shapes (``block1``,
+``block3``, ``alpha_branch``, ``color_branch``, ``color_feature_branch``, ``aux_merge_weight_block``,
+``aux_block_s1/s2/s3``, ``color_mixup_block``, ``color_final_block``) so ``state_dict``s round-trip
+with the reference, same ``forward`` signature and return tuple (:1427-1522).
+
+The arithmetic runs in libhnr kernels: neighbour features are generated straight from the point
+tables (fused path) or from the gathered tensors (drop-in ``forward``), the dense layers run on the
+hand-written kernels (``ops.linear`` / ``mlp_tc``), the image features are read from the conv
+pyramid with the bilinear-upsample arithmetic folded in.  Only the six tiny pyramid convolutions
+stay in torch/cuDNN.
+
+Supported configuration = the one every shipped script uses: ``viewmlp``,
+``agg_intrp_order=2``, ``agg_distance_kernel=linear``, ``agg_dist_pers=20``, ``LeakyReLU``,
+``feature_guidance``, ``use_delta_view``, ``mixup_mode=partial``, ``learn_residuals``; anything else
+raises instead of silently computing something different.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .ops import ACT_COLOR, ACT_LRELU, ACT_NONE, ACT_SIGMOID
+
+
+def drop_patch_rays(patch_size, patch_num, drop_ratio):
+    """raster positions of the first floor(P^2*ratio) patches (reference :14-23)."""
+    S = patch_size * patch_num
+    n = int(patch_num * patch_num * drop_ratio)
+    rows, cols = divmod(n, patch_num)
+    flag = np.zeros((S, S), dtype=bool)
+    flag[: rows * patch_size, :] = True
+    flag[rows * patch_size:(rows + 1) * patch_size, : cols * patch_size] = True
+    return np.nonzero(flag.reshape(-1))[0]
+
+
+def _mlp(sizes, act_last=True, final: Optional[nn.Module] = None):
+    layers = []
+    for i in range(len(sizes) - 1):
+        layers.append(nn.Linear(sizes[i], sizes[i + 1]))
+        if i < len(sizes) - 2 or act_last:
+            layers.append(nn.LeakyReLU(inplace=True))
+    if final is not None:
+        layers.append(final)
+    return nn.Sequential(*layers)
+
+
+def _conv_block(cin, cout):
+    return nn.Sequential(nn.Conv2d(cin, cout, kernel_size=3, stride=2, padding=1), nn.LeakyReLU(inplace=True),
+                         nn.Conv2d(cout, cout, kernel_size=3, stride=1, padding=1), nn.LeakyReLU(inplace=True))
+
+
+def _init_seq(s):
+    """Xavier-uniform with the gain of the following activation, zero bias (helpers/networks.py init_seq)."""
+    mods = list(s)
+    for a, b in zip(mods[:-1], mods[1:]):
+        if isinstance(a, (nn.Linear, nn.Conv2d)):
+            gain = nn.init.calculate_gain('leaky_relu', b.negative_slope) if isinstance(b, nn.LeakyReLU) else 1.0
+            nn.init.xavier_uniform_(a.weight, gain=gain)
+            nn.init.zeros_(a.bias)
+    if isinstance(mods[-1], (nn.Linear, nn.Conv2d)):
+        nn.init.xavier_uniform_(mods[-1].weight)
+        nn.init.zeros_(mods[-1].bias)
+
+
+class PointAggregator(nn.Module):
+    def __init__(self, opt):
+        super().__init__()
+        self.opt = opt
+        self._check_supported(opt)
+        Fd, H = opt.point_features_dim, opt.shading_feature_num
+        self.dist_dim = 6
+        in0 = Fd + 2 * opt.num_feat_freqs * Fd + 2 * abs(opt.dist_xyz_freq) * self.dist_dim          # 284
+        self.viewdir_channels = 2 * opt.num_viewdir_freqs * 3                                        # 24
+        self.block1 = _mlp([in0] + [H] * opt.shading_feature_mlp_layer1)
+        self.block3 = _mlp([H + 3 + 4] + [H] * opt.shading_feature_mlp_layer3)
+        self.alpha_branch = nn.Sequential(nn.Linear(H, 1))
+        cin = H + self.viewdir_channels
+        self.color_branch = _mlp([cin, H // 2, H // 2, H // 2, 3], act_last=False)         # built, unused (as in the reference)
+        self.color_feature_branch = _mlp([cin, H // 2, H // 2, H // 2])
+        aux_c = 45
+        self.aux_merge_weight_block = _mlp([aux_c + H // 2 + 3, H // 4, H // 4, H // 4, 1], act_last=False, final=nn.Sigmoid())
+        # the reference uses non-inplace LeakyReLU in this block; numerically identical
+        self.aux_block_s1, self.aux_block_s2, self.aux_block_s3 = _conv_block(3, 6), _conv_block(6, 12), _conv_block(12, 24)
+        self.color_mixup_block = _mlp([2 * aux_c, aux_c, aux_c, aux_c], act_last=False)
+        self.color_final_block = nn.Sequential(nn.Linear(H // 2, 3))
+        self.learn_blur_kernel_block = None
+        for m in (self.block1, self.block3, self.alpha_branch, self.color_branch, self.color_feature_branch,
+                  self.aux_merge_weight_block, self.aux_block_s1, self.aux_block_s2, self.aux_block_s3, self.color_mixup_block,
+                  self.color_final_block):
+            _init_seq(m)
+        self.shading_patch_size = 1
+        self.mlp_engine = "simt"          # "simt" (exact fp32) | "tc" (tcgen05 3xTF32, forward/inference)
+
+    @staticmethod
+    def _check_supported(opt):
+        req = dict(which_agg_model="viewmlp", agg_intrp_order=2, agg_distance_kernel="linear", agg_dist_pers=20,
+                   act_type="LeakyReLU", shading_feature_mlp_layer1=2, shading_feature_mlp_layer2=0, shading_feature_mlp_layer3=2,
+                   shading_alpha_mlp_layer=1, shading_color_mlp_layer=4, shading_feature_num=256, point_features_dim=32,
+                   num_feat_freqs=3, dist_xyz_freq=5, num_viewdir_freqs=4, feature_guidance=1, use_delta_view=1,
+                   mixup_mode="partial", learn_residuals=1, apply_pnt_mask=1, agg_weight_norm=1)
+        bad = {k: getattr(opt, k, v) for k, v in req.items() if getattr(opt, k, v) != v}
+        off = [k for k in ("tradition_attention", "refine_blend", "dynamic_weight", "add_idx", "separate_color_decoder",
+                           "large_color_final_block", "use_2D_CNN", "disable_viewdirs", "disable_color_feature", "learnable_blur_kernel",
+                           "downweight_blurry_feats", "dist_xyz_deno") if getattr(opt, k, 0)]
+        if bad or off:
+            raise NotImplementedError(f"PointAggregator: unsupported options {bad} / enabled flags {off}; only the shipped "
+                                      "configuration (SURVEY.md §8d) is implemented, there is no fallback path")
+
+    # ------------------------------------------------------------------ reference helpers kept for API parity
+    def raw2out_density(self, raw_density):
+        return F.softplus(raw_density - 1)
+
+    def raw2out_color(self, raw_color):
+        return torch.sigmoid(raw_color) * (1 + 2 * 0.001) - 0.001
+
+    def gradiant_clamp(self, sampled_conf, min=0.0001, max=1):
+        diff = sampled_conf - torch.clamp(sampled_conf, min=min, max=max)
+        return sampled_conf - diff.detach()
+
+    # ------------------------------------------------------------------ image pyramid (torch/cuDNN, 6 tiny convs)
+    def feature_pyramid(self, img_n: torch.Tensor):
+        """img_n (1,V,H,W,3) -> NHWC levels [(V,H,W,3),(V,h1,w1,6),(V,h2,w2,12),(V,h3,w3,24)]"""
+        img = img_n[0]
+        x = img.permute(0, 3, 1, 2)
+        s1 = self.aux_block_s1(x)
+        s2 = self.aux_block_s2(s1)
+        s3 = self.aux_block_s3(s2)
+        return [img.contiguous()] + [t.permute(0, 2, 3, 1).contiguous() for t in (s1, s2, s3)]
+
+    # ------------------------------------------------------------------ core
+    def _keep_mask(self, R: int, SR: int, vlist: torch.Tensor) -> Optional[torch.Tensor]:
+        """train-time image-feature drop (:1222-1237): uint8 (Nv,) keep flags, or None."""
+        opt = self.opt
+        if not (getattr(opt, "is_train", False) and opt.drop_ratio > 0 and opt.random_position == 1 and opt.use_nearest > 0):
+            return None
+        if not (opt.ray_points and opt.drop_patch and opt.drop_disturb_range == 0):
+            raise NotImplementedError("only the deterministic patch drop (ray_points=1, drop_patch=1, drop_disturb_range=0) is implemented")
+        toks = opt.dilation_setup.split('_')
+        pos = drop_patch_rays(int(toks[1]), int(toks[0]), opt.drop_ratio)
+        if len(pos) and pos.max() >= R:
+            raise IndexError(f"index {int(pos.max())} is out of bounds for axis 0 with size {R}")   # what numpy raises in the reference
+        dropped = torch.zeros(R, dtype=torch.bool, device=vlist.device)
+        dropped[torch.from_numpy(pos).to(vlist.device)] = True
+        return (~dropped[(vlist.long() // SR)]).to(torch.uint8).contiguous()
+
+    def _run(self, tables, pidx, mask, loc_pers, loc_w, raydirs, cam, R, SR, levels, xy, delta, vlist=None):
+        """tables = (xyz (N,3), xyz_pers|None, emb (N,32), color (N,3), dir (N,3), conf (N,)).
+        pidx (S,K) i32; mask (S,K) u8|None; loc_* / raydirs (S,3).  Returns decoded (S,4), valid (S) bool,
+        weight (S,K), conf_coefficient (S,K)."""
+        opt = self.opt
+        xyz, xyz_pers, emb, color, dirs, conf = tables
+        S, K = pidx.shape
+        weight, confc, valid = ops.NbrWeightsFn.apply(xyz, conf, pidx, mask, loc_w)
+        if vlist is None:
+            vlist = torch.nonzero(valid, as_tuple=False).view(-1).to(torch.int32)        # sync (drop-in path only)
+        Nv = vlist.shape[0]
+        decoded = torch.zeros((S, 4), device=pidx.device, dtype=torch.float32)
+        if Nv == 0:
+            return decoded, valid.bool(), weight, confc
+        b1, b3 = self.block1, self.block3
+        X0, E = ops.NbrFeaturesFn.apply(emb, color, dirs, xyz, xyz_pers, pidx, mask, vlist, loc_w, loc_pers, raydirs, cam)
+        h = ops.linear([X0], b1[0].weight, b1[0].bias, ACT_LRELU)
+        h = ops.linear([h], b1[2].weight, b1[2].bias, ACT_LRELU)
+        h = ops.linear([h, E], b3[0].weight, b3[0].bias, ACT_LRELU)
+        h = ops.linear([h], b3[2].weight, b3[2].bias, ACT_LRELU)
+        sigma, X5 = ops.AlphaKSumFn.apply(h, confc, self.alpha_branch[0].weight, self.alpha_branch[0].bias, weight, vlist, raydirs, cam)
+        cf = self.color_feature_branch
+        g = ops.linear([X5], cf[0].weight, cf[0].bias, ACT_LRELU)
+        g = ops.linear([g], cf[2].weight, cf[2].bias, ACT_LRELU)
+        g = ops.linear([g], cf[4].weight, cf[4].bias, ACT_LRELU)
+        V = int(opt.use_nearest)
+        if V > 0:
+            aux, ok = ops.ImageGatherFn.apply(levels[0], levels[1], levels[2], levels[3], xy, vlist)
+            dv = delta.reshape(V, S, 3).index_select(1, vlist.long()).reshape(V * Nv, 3)
+            am = self.aux_merge_weight_block
+            t = ops.linear([aux.view(V * Nv, 45), g, dv], am[0].weight, am[0].bias, ACT_LRELU, mods=(0, Nv, 0), M=V * Nv)
+            t = ops.linear([t], am[2].weight, am[2].bias, ACT_LRELU)
+            t = ops.linear([t], am[4].weight, am[4].bias, ACT_LRELU)
+            sig = ops.linear([t], am[6].weight, am[6].bias, ACT_SIGMOID)
+            merged = ops.BlendFn.apply(aux, sig, ok, self._keep_mask(R, SR, vlist))
+        else:
+            merged = torch.zeros((Nv, 45), device=pidx.device, dtype=torch.float32)
+        gi, gv = g[:, :45], g[:, 45:]
+        cm = self.color_mixup_block
+        m = ops.linear([gi, merged], cm[0].weight, cm[0].bias, ACT_LRELU)
+        m = ops.linear([m], cm[2].weight, cm[2].bias, ACT_LRELU)
+        m = ops.linear([m], cm[4].weight, cm[4].bias, ACT_NONE, res=gi)
+        rgb = ops.linear([m, gv], self.color_final_block[0].weight, self.color_final_block[0].bias, ACT_COLOR)
+        decoded = decoded.index_copy(0, vlist.long(), torch.cat([sigma, rgb], dim=-1))
+        return decoded, valid.bool(), weight, confc
+
+    # ------------------------------------------------------------------ drop-in forward (gathered tensors)
+    def forward(self, sampled_color, sampled_Rw2c, sampled_dir, sampled_conf, sampled_embedding, sampled_xyz_pers, sampled_xyz,
+                sample_pnt_mask, sample_loc, sample_loc_w, sample_ray_dirs, vsize, grid_vox_sz, aux_image=None, pixel_idx=None,
+                img_n=None, vid_angle_n=None, sample_loc_i_n=None, delta_viewdir_n=None, frame_weight_n=None):
+        opt = self.opt
+        B, R, SR, K = sample_pnt_mask.shape
+        assert B == 1, "batch size 1 (as everywhere in the reference)"
+        in_shape = sample_loc_w.shape
+        S = R * SR
+        dev = sample_pnt_mask.device
+        if S == 0:
+            return self._pack(torch.zeros(in_shape[:-1] + (4,), device=dev), torch.zeros(in_shape[:-1], dtype=torch.bool, device=dev), None, None)
+        if sampled_Rw2c.dim() != 2:
+            raise NotImplementedError("per-point Rw2c is not supported (normview is off in every shipped config)")
+        if sampled_conf is None or sampled_color is None or sampled_dir is None:
+            raise NotImplementedError("point_{conf,color,dir}_mode must be '1' (shipped configuration)")
+        f2 = lambda t, c: t.reshape(S * K, c)
+        tables = (f2(sampled_xyz, 3), f2(sampled_xyz_pers, 3), f2(sampled_embedding, sampled_embedding.shape[-1]), f2(sampled_color, 3),
+                  f2(sampled_dir, 3), sampled_conf.reshape(S * K))
+        pidx = torch.arange(S * K, device=dev, dtype=torch.int32).view(S, K)
+        mask = sample_pnt_mask.reshape(S, K).to(torch.uint8).contiguous()
+        cam = ops.make_cam(torch.zeros(3, device=dev), torch.eye(3, device=dev), sampled_Rw2c)
+        levels = xy = delta = None
+        if opt.use_nearest > 0:
+            V = int(opt.use_nearest)
+            levels = self.feature_pyramid(img_n)
+            xy = sample_loc_i_n.reshape(V, S, 2).float().contiguous()
+            delta = delta_viewdir_n.reshape(V, S, 3).float()
+        decoded, valid, weight, confc = self._run(tables, pidx, mask, sample_loc.reshape(S, 3).float().contiguous(),
+                                                  sample_loc_w.reshape(S, 3).float().contiguous(),
+                                                  sample_ray_dirs.reshape(S, 3).float().contiguous(), cam, R, SR, levels, xy, delta)
+        if int(valid.sum()) == 0:   # mirrors the reference's early return (:1444-1446)
+            return self._pack(decoded.view(in_shape[:-1] + (4,)), valid.view(in_shape[:-1]), None, None)
+        return self._pack(decoded.view(in_shape[:-1] + (4,)), valid.view(in_shape[:-1]), weight.view(B, R, SR, K), confc.view(B, R, SR, K))
+
+    def _pack(self, decoded, ray_valid, weight, confc):
+        opt = self.opt
+        if weight is not None and (opt.sparse_loss_weight <= 0) and ("conf_coefficient" not in opt.zero_one_loss_items) and opt.prob == 0:
+            weight, confc = None, None
+        if getattr(opt, "is_train", False):
+            return decoded, ray_valid, weight, confc, self.learn_blur_kernel_block
+        return decoded, ray_valid, weight, confc
+
+    # ------------------------------------------------------------------ fused forward (point tables + indices)
+    def forward_fused(self, points, sample_pidx, sample_loc, sample_loc_w, sample_ray_dirs, campos, camrotc2w, extras=None, img_n=None,
+                      c2w_n=None, intrinsic_n=None, campos_n=None):
+        """points: NeuralPoints.  sample_* as returned by NeuralPoints.query.  Projection into the
+        reference views (P1) runs in-kernel.  Returns decoded (1,R,SR,4), ray_valid, weight, conf_coefficient."""
+        opt = self.opt
+        B, R, SR, K = sample_pidx.shape
+        S = R * SR
+        dev = sample_pidx.device
+        if S == 0:
+            return torch.zeros((1, 0, SR, 4), device=dev), torch.zeros((1, 0, SR), dtype=torch.bool, device=dev), None, None
+        if points.Rw2c is not None and points.Rw2c.dim() != 2:
+            raise NotImplementedError("per-point Rw2c is not supported")
+        tables = (points.xyz, None, points.points_embeding[0], points.points_color[0], points.points_dir[0], points.points_conf.reshape(-1))
+        cam = ops.make_cam(campos, camrotc2w, points.Rw2c)
+        loc_w = sample_loc_w.reshape(S, 3)
+        levels = xy = delta = None
+        if opt.use_nearest > 0:
+            levels = self.feature_pyramid(img_n)
+            w2c = torch.linalg.inv(c2w_n.reshape(-1, 4, 4).float())
+            xy, delta = ops.project_views(loc_w, w2c, intrinsic_n.reshape(3, 3), campos.reshape(-1)[:3], campos_n.reshape(-1, 3))
+        decoded, valid, weight, confc = self._run(tables, sample_pidx.reshape(S, K), None, sample_loc.reshape(S, 3), loc_w,
+                                                  sample_ray_dirs.reshape(S, 3), cam, R, SR, levels, xy, delta,
+                                                  vlist=None if extras is None else extras.vlist)
+        return decoded.view(1, R, SR, 4), valid.view(1, R, SR), weight.view(1, R, SR, K), confc.view(1, R, SR, K)

@@ -1,0 +1,150 @@
+/* libhnr -- C ABI of the B200-native per-ray sample pipeline (drop-in boundary).
+ *
+ * The reference (CVMI-Lab/HybridNeuralRendering) has no FFI layer: its seam is the Python module
+ * API (lighting_fast_querier, NeuralPoints, PointAggregator, ray_march, blur_update_output).  The
+ * host package `hybridneuralrendering_b200` mirrors that API and calls the entry points below
+ * through ctypes.  Each entry point cites the reference code it replaces (paths relative to the
+ * reference repository root).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to caller-owned memory (torch-allocated); the library
+ *     allocates nothing and keeps no pointers between calls;  fp32 / int32 / uint8 only;
+ *   - tensors are dense row-major; sizes are int64_t; `stream` is a cudaStream_t passed as void*;
+ *   - return 0 on success, negative on error (-1 CUDA error, -2 bad argument, -3 unsupported);
+ *     hnr_last_error() returns the message (thread-local);  functions never throw;
+ *   - kernels are compiled for sm_100a only; there is no CPU fallback.
+ */
+#ifndef HNR_H
+#define HNR_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int hnr_abi_version(void);
+const char* hnr_last_error(void);
+int hnr_device_arch(void); /* major*10+minor of the current device (100 on B200) */
+
+/* ---------------------------------------------------------------------------------------------
+ * Voxel-grid neural-point query: models/neural_points/query_point_indices_worldcoords.py
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    float origin[3];     /* ranges[:3] after padding         (get_hyperparameters :46-77) */
+    float cell[3];       /* vsize * vscale                                                 */
+    int32_t dims[3];     /* scaled_vdim                                                    */
+    float radius2;       /* (radius_limit_scale * max(vsize.x, vsize.y))^2 ; 0 = unlimited */
+    int64_t n_cells;     /* dims[0]*dims[1]*dims[2]                                        */
+    int32_t P;           /* max stored points consulted per voxel (opt.P)                  */
+    int32_t layers;      /* (kernel_size[0]+1)/2 shells walked by the neighbour search     */
+    int32_t qhalf_lo[3]; /* occupancy dilation reach below: query_size/2                   */
+    int32_t qhalf_hi[3]; /* and above: (query_size+1)/2 - 1                                */
+} hnr_grid_t;
+
+int64_t hnr_scan_scratch_elems(int64_t n);
+int hnr_exclusive_scan_i32(const int32_t* in, int32_t* out /* n+1 */, int64_t n, int32_t* scratch, void* stream);
+
+/* Occupancy-grid build; replaces build_occ_vox + claim_occ/map_coor2occ/fill_occ2pnts (:237-381, :540-602).
+ * Called once per point-set change (the reference rebuilds per forward, :616).
+ * skip_cell: -1 none, -2 voxel of the first in-grid point (stand-in for the reference's
+ * "occupied slot 0 stores no points" quirk, :366), >=0 explicit linear voxel id.
+ * info int32[8]: [0] occupied voxels [1] max points/voxel [2] skip voxel [3] points dropped with it
+ *                [4] first in-grid point id [5] points stored. */
+int hnr_grid_build(const float* xyz, int64_t N, const hnr_grid_t* g, int32_t skip_cell, int32_t* cell_of_pt /* N */,
+                   int32_t* counts /* n_cells */, int32_t* cell_start /* n_cells+1 */, int32_t* tmp_idx /* N */,
+                   void* pts_sorted /* float4[N] */, uint32_t* occ_bits /* ceil(n_cells/32) */, int32_t* scan_scratch,
+                   int32_t* info /* 8 */, void* stream);
+
+/* One query over R rays; replaces mask_raypos, get_shadingloc, query_neigh_along_ray_layered and
+ * the torch compaction between them (:384-522, :605-711) plus w2pers / ray-dir expansion (:80-103).
+ * ts = the D candidate parameters of near_far_linear_ray_generation
+ * (models/rendering/diff_ray_marching.py:349-392), shared by all rays (ts_stride 0) or per ray
+ * (ts_stride D).  Outputs are sized for R rays; counts_out = {R'' kept rays, Nv valid samples}. */
+int hnr_query(const float* campos, const float* camrot /* c2w rotation 3x3 */, const float* raydir /* R,3 */, const float* ts,
+              int64_t ts_stride, int64_t R, int64_t D, int64_t SR, int64_t K, const hnr_grid_t* g, const int32_t* cell_start,
+              const void* pts_sorted, const uint32_t* occ_bits, float* sample_loc_full /* R,SR,3 zeroed */,
+              int32_t* pidx_full /* R,SR,K */, int32_t* nsamp /* R */, int32_t* nvalid /* R */, int32_t* keep /* R */,
+              int32_t* ray_off /* R+1 */, int32_t* val_off /* R+1 */, int32_t* scan_scratch, int32_t* out_pidx /* R,SR,K */,
+              float* out_loc_pers /* R,SR,3 */, float* out_loc_w, float* out_dirs, int8_t* ray_mask /* R */, int32_t* ray_ids /* R */,
+              int32_t* vlist /* R*SR */, int32_t* counts_out /* 2 */, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Aggregation: models/aggregators/point_aggregators.py, models/neural_points/neural_points.py
+ * ------------------------------------------------------------------------------------------- */
+/* camera block `cam`: 21 floats in DEVICE memory = campos[3], camrot[9] (c2w rotation, row-major),
+ * rt[9] (Rw2c^T row-major, identity unless normview).  Device-resident so no host sync is needed. */
+
+/* inverse-distance weights + confidence clamp for ALL S samples; PointAggregator.linear (:825-833),
+ * normalisation (:1500-1501), gradiant_clamp (:1422-1424).  mask may be NULL (then pidx<0 = masked). */
+int hnr_nbr_weights(const float* xyz, const float* conf, const int32_t* pidx, const uint8_t* mask, const float* loc_w, int64_t S,
+                    int64_t K, float* weight, float* confc, uint8_t* valid, void* stream);
+/* per-neighbour MLP input rows for the Nv valid samples: gather (neural_points.py:708-720), dists
+ * (:1472-1480), positional encodings (helpers/networks.py:175-189), block3 extras (:957-971). */
+int hnr_nbr_features(const float* xyz, const float* xyz_pers /* may be NULL */, const float* emb, const float* color,
+                     const float* dir, const int32_t* pidx, const int32_t* vlist, const float* loc_w, const float* loc_pers,
+                     const float* raydirs, const float* cam, int64_t Nv, int64_t K, int64_t emb_dim, float* X0 /* Nv*K,284 */,
+                     float* E /* Nv*K,7 */, void* stream);
+int hnr_nbr_features_bwd(const float* dX0, const float* dE, const float* emb, const int32_t* pidx, const uint8_t* mask,
+                         const int32_t* vlist, const float* raydirs, const float* cam, int64_t Nv, int64_t K, float* d_emb,
+                         float* d_color, float* d_dir, void* stream);
+/* density head + weighted K-sum + view-dir encoding (:1002-1036) */
+int hnr_alpha_ksum_fwd(const float* H, const float* weight, const float* confc, const int32_t* vlist, const float* w_alpha,
+                       const float* b_alpha, const float* raydirs, const float* cam, int64_t Nv, int64_t K, int64_t hidden,
+                       float* sigma, float* X5 /* Nv,280 */, float* alpha_raw /* Nv*K */, void* stream);
+int hnr_alpha_ksum_bwd(const float* H, const float* weight, const float* confc, const int32_t* vlist, const float* w_alpha,
+                       const float* alpha_raw, const float* d_sigma, const float* dX5, int64_t Nv, int64_t K, int64_t hidden,
+                       float* dH, float* d_wc, float* d_walpha, float* d_balpha, void* stream);
+int hnr_conf_bwd(const float* d_wc, const float* weight, const int32_t* vlist, const int32_t* pidx, const float* d_confc, int64_t Nv,
+                 int64_t S, int64_t K, float* d_conf, void* stream);
+/* w2iproject + delta view dirs (models/neural_points_volumetric_model.py:248-255, :287-310) */
+int hnr_project_views(const float* loc_w, const float* w2c /* V,4,4 */, const float* Kmat /* 3,3 */, const float* campos,
+                      const float* campos_n /* V,3 */, int64_t V, int64_t S, float* xy /* V,S,2 */, float* delta /* V,S,3 */,
+                      void* stream);
+/* pyramid lookup == F.interpolate(bilinear) to full res, zero pixel (0,0), truncated nearest pixel
+ * (:1064-1096, :1193); levels are NHWC: (V,H,W,3),(V,h1,w1,6),(V,h2,w2,12),(V,h3,w3,24) */
+int hnr_image_gather_fwd(const float* const* levels, const int64_t* level_hw /* 8 */, const float* xy, const int32_t* vlist,
+                         int64_t V, int64_t S, int64_t Nv, float* aux /* V,Nv,45 */, float* ok /* V,Nv */, void* stream);
+int hnr_image_gather_bwd(float* const* level_grads, const int64_t* level_hw, const float* xy, const int32_t* vlist, const float* d_aux,
+                         int64_t V, int64_t S, int64_t Nv, void* stream);
+/* multi-view blend (:1199-1217) + train-time drop (:1222-1237) */
+int hnr_blend_fwd(const float* aux, const float* sig, const float* ok, const uint8_t* keep, int64_t V, int64_t Nv, float* merged,
+                  void* stream);
+int hnr_blend_bwd(const float* aux, const float* sig, const float* ok, const uint8_t* keep, const float* d_merged, int64_t V,
+                  int64_t Nv, float* d_aux, float* d_sig, void* stream);
+
+/* dense layers: y = act(concat(A0,A1,A2) W^T + b [+res]); W (N,K) row-major as nn.Linear
+ * (layers built at point_aggregators.py:484-683).  act: 0 none, 1 LeakyReLU(0.01), 2 sigmoid,
+ * 3 sigmoid*1.002-0.001 (raw2out_color :478-482).  a_mod[i] > 0: source i has a_mod[i] rows, shared
+ * by row blocks (the per-sample feature reused for each of the V views). */
+int hnr_linear_fwd(const float* const* a_ptr, const int64_t* a_ld, const int64_t* a_k, const int64_t* a_mod, const float* W,
+                   const float* bias, const float* res, int64_t ldres, float* Y, int64_t ldy, int64_t M, int64_t N, int64_t K, int act,
+                   void* stream);
+int hnr_linear_bwd_data(const float* dY, int64_t lddy, const float* Y, int64_t ldy, const float* W, float* const* da_ptr,
+                        const int64_t* da_ld, const int64_t* a_k, int64_t M, int64_t N, int64_t K, int act, void* stream);
+int hnr_linear_bwd_weight(const float* dY, int64_t lddy, const float* Y, int64_t ldy, const float* const* a_ptr, const int64_t* a_ld,
+                          const int64_t* a_k, const int64_t* a_mod, float* dW, float* db, int64_t M, int64_t N, int64_t K, int act,
+                          void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Compositing: neural_points_volumetric_model.py:331-339 + models/rendering/diff_ray_marching.py:508-557
+ * ------------------------------------------------------------------------------------------- */
+/* pass exactly one of z (camera depth per sample, element stride z_stride) or dist_in (ray_dist) */
+int hnr_composite_fwd(const float* feats /* R,SR,4 */, const uint8_t* valid /* R,SR */, const float* z, int z_stride,
+                      const float* dist_in, const float* bg /* 3 or NULL */, float vsize_z, int unit_mode, int64_t R, int64_t SR,
+                      float* ray_color, float* opacity, float* acc_trans, float* blend_weight, float* bg_trans, float* dist_out,
+                      void* stream);
+int hnr_composite_bwd(const float* feats, const uint8_t* valid, const float* dist, const float* acc_trans, const float* bg_trans,
+                      const float* bg, const float* g_color, const float* g_opacity, const float* g_bg_trans,
+                      const float* g_blend_weight, const float* g_acc_trans, int64_t R, int64_t SR, float* g_feats, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Blur module: models/base_rendering_model.py:677-786
+ * ------------------------------------------------------------------------------------------- */
+int hnr_blur_select_fwd(const float* pred /* S*S,3 */, const float* gt, const float* kernels /* Nk,ks,ks */, int64_t patch_num,
+                        int64_t patch_size, int64_t num_kernels, int64_t kernel_size, float* out, int32_t* select, void* stream);
+int hnr_blur_select_bwd(const float* g_out, const float* kernels, const int32_t* select, int64_t patch_num, int64_t patch_size,
+                        int64_t num_kernels, int64_t kernel_size, float* g_pred, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HNR_H */

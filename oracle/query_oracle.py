@@ -150,6 +150,8 @@ def positions_from_ts(campos, raydir, ts):
     campos, raydir, ts = np.asarray(campos, f32), np.asarray(raydir, f32), np.asarray(ts, f32)
     if ts.ndim == 1:
         ts = ts[None, None, :]
+    elif ts.ndim == 2:
+        ts = ts[None]
     return (campos[:, None, None, :] + (raydir[:, :, None, :] * ts[..., None]).astype(f32)).astype(f32)
 
 

@@ -1,0 +1,146 @@
+"""GPU parity of the aggregation / image branch against the reference goldens and the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import T, assert_close, build_aggregator, cuda, grad_atol, load_golden, run_dropin, run_oracle
+from hybridneuralrendering_b200 import synthetic as syn
+from oracle import render_oracle as ro
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4
+
+
+def _case(meta, empty_frac=0.4):
+    R, SR, V, H, W, is_train, seed = [int(x) for x in meta]
+    d = syn.render_stage_inputs(seed=seed, N=600, R=R, SR=SR, K=8, V=V, H=H, W=W, empty_frac=empty_frac)
+    return d, syn.gather_neighbours(d), (R, SR, V, H, W, bool(is_train), seed)
+
+
+def test_dropin_forward_matches_reference_golden_eval():
+    G = load_golden("agg_eval")
+    d, g, (R, SR, V, H, W, is_train, seed) = _case(G["meta"])
+    agg = build_aggregator(ro.random_params(seed + 100), use_nearest=V, is_train=False)
+    with torch.no_grad():
+        (decoded, valid, w, cc), _ = run_dropin(agg, d, g)
+    np.testing.assert_array_equal(valid.cpu().numpy(), G["ray_valid"])
+    assert_close(decoded, G["decoded"], RTOL, 1e-6)
+    assert_close(w, G["weight"], 1e-5, 1e-7)
+    np.testing.assert_array_equal(cc.cpu().numpy(), G["conf_coefficient"])
+
+
+def test_dropin_train_step_matches_reference_golden_grads():
+    from hybridneuralrendering_b200.diff_ray_marching import ray_march_from_depth
+    G = load_golden("agg_train")
+    d, g, (R, SR, V, H, W, is_train, seed) = _case(G["meta"])
+    agg = build_aggregator(ro.random_params(seed + 100), use_nearest=V, is_train=True, drop_ratio=float(G["drop_ratio"]),
+                           dilation_setup=str(G["dilation_setup"]))
+    (decoded, valid, w, cc, blur_pred), leaf = run_dropin(agg, d, g, grad=True)
+    assert blur_pred is None
+    assert_close(decoded, G["decoded"], RTOL, 1e-6)
+    color, opacity, accT, bw, bgT, dist = ray_march_from_depth(cuda(d["sample_loc"]), valid, decoded, float(d["vsize"][2]), 1, torch.ones(1, 3).cuda())
+    np.testing.assert_array_equal(dist.cpu().numpy(), G["ray_dist"])
+    assert_close(color, G["ray_color"], RTOL, 1e-6)
+    assert_close(opacity, G["opacity"], RTOL, 1e-7)
+    v = cc.clamp(1e-3, 1 - 1e-3)
+    loss = torch.nn.functional.mse_loss(color, cuda(G["gt"])) + 1e-4 * torch.mean(torch.log(v) + torch.log(1 - v))
+    assert_close(loss, G["loss"], 1e-5, 0)
+    loss.backward()
+    for k, t in leaf.items():
+        ref = G["grad_" + k]
+        assert_close(t.grad, ref, RTOL, grad_atol(ref), k)
+    n = 0
+    for k, p in agg.named_parameters():
+        key = "gradP_" + k
+        if key not in G:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+            continue
+        assert_close(p.grad, G[key], RTOL, grad_atol(G[key], 2e-4), k)
+        n += 1
+    assert n >= 40
+
+
+@pytest.mark.parametrize("R,SR,V,empty", [(64, 24, 4, 0.5), (40, 80, 8, 0.3), (8, 3, 0, 0.0), (16, 8, 2, 1.0)])
+def test_dropin_vs_oracle_fp64(R, SR, V, empty):
+    """bigger random cases against the oracle evaluated in fp64 (checks the CUDA path, not fp32 noise)"""
+    seed = R + SR
+    d = syn.render_stage_inputs(seed=seed, N=3000, R=R, SR=SR, K=8, V=max(V, 1), H=30, W=40, empty_frac=empty)
+    g = syn.gather_neighbours(d)
+    P = ro.random_params(seed)
+    cfg = ro.AggCfg(use_nearest=V)
+    (dec_ref, valid_ref, w_ref, cc_ref), _, _ = run_oracle(d, g, P, cfg, dtype=torch.float64)
+    agg = build_aggregator(P, use_nearest=V)
+    with torch.no_grad():
+        (decoded, valid, w, cc), _ = run_dropin(agg, d, g)
+    np.testing.assert_array_equal(valid.cpu().numpy(), valid_ref.numpy())
+    assert_close(decoded, dec_ref, RTOL, 1e-6)
+    if w_ref is not None:
+        assert_close(w, w_ref, 1e-5, 1e-7)
+
+
+def test_fused_tables_path_equals_dropin_path():
+    """the fused path (kernels gather from the point tables through sample_pidx, projection in-kernel)
+    must give what the reference-shaped drop-in path gives on the materialised tensors"""
+    from hybridneuralrendering_b200 import NeuralPoints, make_opt
+    seed, R, SR, V = 3, 48, 24, 4
+    d = syn.render_stage_inputs(seed=seed, N=5000, R=R, SR=SR, K=8, V=V, H=48, W=64, empty_frac=0.4)
+    g = syn.gather_neighbours(d)
+    P = ro.random_params(seed)
+    agg = build_aggregator(P, use_nearest=V)
+    fr = syn.room_frame(H=48, W=64, V=V, patch_num=2, patch_size=2, seed=1)
+    c2w_n, K_n, campos_n = cuda(fr["c2w_nearest"][0]), cuda(fr["intrinsic_nearest"][0]), cuda(fr["campos_nearest"][0])
+    # drop-in inputs: projections computed by the oracle (reference arithmetic)
+    loc_w = T(d["sample_loc_w"])[0]
+    xy = ro.project_to_views(loc_w, T(fr["intrinsic_nearest"][0]), T(fr["c2w_nearest"][0]))
+    dv = ro.delta_viewdirs(loc_w, T(d["campos"][0]), T(fr["campos_nearest"][0]))
+    d2 = dict(d, sample_loc_i_n=xy.numpy(), delta_viewdir_n=dv.numpy())
+    with torch.no_grad():
+        (dec_a, valid_a, w_a, cc_a), _ = run_dropin(agg, d2, g)
+    opt = make_opt(use_nearest=V)
+    pts = NeuralPoints(32, 5000, opt, torch.device("cuda"))
+    pts.set_points(cuda(d["xyz"]), cuda(d["emb"])[None], points_color=cuda(d["color"])[None], points_dir=cuda(d["dir"])[None],
+                   points_conf=cuda(d["conf"])[None], parameter=True)
+    with torch.no_grad():
+        dec_b, valid_b, w_b, cc_b = agg.forward_fused(pts, cuda(d["sample_pidx"]), cuda(d["sample_loc"]), cuda(d["sample_loc_w"]),
+                                                      cuda(d["sample_ray_dirs"]), cuda(d["campos"]), cuda(d["camrotc2w"]), img_n=cuda(d["images_nearest"]),
+                                                      c2w_n=c2w_n, intrinsic_n=K_n, campos_n=campos_n)
+    np.testing.assert_array_equal(valid_a.cpu().numpy(), valid_b.cpu().numpy())
+    assert_close(w_b, w_a, 1e-6, 1e-8)
+    # in-kernel projection vs torch matmul differ by ~1 ulp: a sample whose projection sits within 1e-3 px
+    # of a pixel boundary may pick the neighbouring pixel; allow those few samples to differ
+    diff = (dec_a - dec_b).abs().amax(dim=-1)
+    bad = (diff > 1e-4 * dec_a.abs().amax(dim=-1) + 1e-6).sum().item()
+    assert bad <= max(2, int(0.002 * diff.numel())), bad
+
+
+def test_projection_kernel_matches_reference_golden():
+    from hybridneuralrendering_b200 import ops
+    G = load_golden("proj")
+    loc = cuda(G["loc_w"])[0].reshape(-1, 3)
+    w2c = torch.linalg.inv(cuda(G["c2w_n"]))
+    xy, delta = ops.project_views(loc, w2c, cuda(G["intrinsic"]), torch.zeros(3).cuda(), torch.zeros(3, 3).cuda())
+    assert_close(xy.view(G["xy"].shape), G["xy"], 1e-5, 1e-3)
+
+
+def test_image_gather_equals_interpolate_then_lookup():
+    """pyramid lookup kernel == F.interpolate(bilinear) + zeroed pixel (0,0) + truncated lookup"""
+    from hybridneuralrendering_b200 import ops
+    rng = np.random.default_rng(4)
+    V, H, W, S = 3, 37, 52, 500
+    P = ro.random_params(1)
+    img = T(rng.random((V, H, W, 3), dtype=np.float32))
+    lv = ro.feature_pyramid(img, P)
+    full = ro.full_res_features(lv)                                   # (V,45,H,W)
+    xy = np.stack([rng.uniform(-3, W + 3, (V, S)), rng.uniform(-3, H + 3, (V, S))], -1).astype(np.float32)
+    xy[:, :5] = [[0.3, 0.7]]                                          # the zeroed pixel
+    xy[:, 5:8] = [[-0.5, 2.2]]                                        # (-1,0) truncates to 0: valid
+    xy[:, 8] = [W - 0.01, H - 0.01]
+    px, py = xy[..., 0].astype(np.int32), xy[..., 1].astype(np.int32)
+    bad = (px < 0) | (px >= W) | (py < 0) | (py >= H)
+    pxc, pyc = np.where(bad, 0, px), np.where(bad, 0, py)
+    ref = torch.stack([full[v][:, T(pyc[v]).long(), T(pxc[v]).long()].t() for v in range(V)])
+    levels = [img.cuda()] + [l.permute(0, 2, 3, 1).contiguous().cuda() for l in lv[1:]]
+    vlist = torch.arange(S, dtype=torch.int32).cuda()
+    aux, ok = ops.ImageGatherFn.apply(levels[0], levels[1], levels[2], levels[3], cuda(xy), vlist)
+    np.testing.assert_array_equal(ok.cpu().numpy(), (~bad).astype(np.float32))
+    assert_close(aux, ref, 1e-5, 1e-6)

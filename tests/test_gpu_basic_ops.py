@@ -1,0 +1,158 @@
+"""GPU parity: compositing, blur, dense layers (called through the C ABI via the host wrappers)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import T, assert_close, cuda, grad_atol, load_golden
+from oracle import render_oracle as ro
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4   # north_star: renders / gradients within rtol 1e-4 in fp32
+
+
+def test_ray_march_golden_fwd_bwd():
+    from hybridneuralrendering_b200.diff_ray_marching import alpha_blend, radiance_render, ray_march
+    G = load_golden("misc")
+    f = cuda(G["rm_feats"]).clone().requires_grad_(True)
+    o = ray_march(cuda(G["rm_dist"]), cuda(G["rm_valid"]), f, radiance_render, alpha_blend, cuda(G["rm_bg"]))
+    assert_close(o[0], G["rm_ray_color"], RTOL, 1e-6)
+    assert_close(o[2], G["rm_opacity"], RTOL, 1e-7)
+    assert_close(o[3], G["rm_accT"], RTOL, 1e-12)
+    assert_close(o[4], G["rm_bw"], RTOL, 1e-9)
+    assert_close(o[5], G["rm_bgT"], RTOL, 1e-12)
+    (o[0] * cuda(G["rm_G"])).sum().backward()
+    assert_close(f.grad, G["rm_grad_feats"], RTOL, grad_atol(G["rm_grad_feats"], 1e-6))
+
+
+@pytest.mark.parametrize("R,SR", [(1, 1), (7, 24), (33, 80), (5, 130)])
+def test_ray_march_random_vs_oracle_all_outputs(R, SR):
+    from hybridneuralrendering_b200.diff_ray_marching import alpha_blend, radiance_render, ray_march
+    rng = np.random.default_rng(R * 1000 + SR)
+    feats = T(rng.random((1, R, SR, 4)).astype(np.float32) * np.array([30, 1, 1, 1], np.float32))
+    valid = T(rng.random((1, R, SR)) > 0.25)
+    dist = T((rng.random((1, R, SR)) * 0.03).astype(np.float32))
+    bg = T(np.array([[0.2, 0.9, 1.0]], np.float32))
+    gC, gO, gT, gW, gB = [T(rng.standard_normal(s).astype(np.float32)) for s in ((1, R, 3), (1, R, SR), (1, R, SR), (1, R, SR, 1), (1, R, 1))]
+    fo = feats.double().clone().requires_grad_(True)
+    oo = ro.ray_march(dist.double(), valid, fo, bg.double())
+    (oo[0] * gC).sum().backward(retain_graph=True)
+    g1 = fo.grad.clone(); fo.grad = None
+    ((oo[0] * gC).sum() + (oo[2] * gO).sum() + (oo[3] * gT).sum() + (oo[4] * gW).sum() + (oo[5] * gB).sum()).backward()
+    g2 = fo.grad.clone()
+    fg = feats.cuda().clone().requires_grad_(True)
+    og = ray_march(dist.cuda(), valid.cuda(), fg, radiance_render, alpha_blend, bg.cuda())
+    for i in (0, 2, 3, 4, 5):
+        assert_close(og[i], oo[i], RTOL, 1e-9, f"output {i}")
+    (og[0] * gC.cuda()).sum().backward(retain_graph=True)
+    assert_close(fg.grad, g1, RTOL, grad_atol(g1, 1e-5))
+    fg.grad = None
+    ((og[0] * gC.cuda()).sum() + (og[2] * gO.cuda()).sum() + (og[3] * gT.cuda()).sum() + (og[4] * gW.cuda()).sum() + (og[5] * gB.cuda()).sum()).backward()
+    assert_close(fg.grad, g2, RTOL, grad_atol(g2, 1e-5))
+
+
+def test_ray_dist_prologue_fused():
+    from hybridneuralrendering_b200.diff_ray_marching import ray_march_from_depth
+    rng = np.random.default_rng(5)
+    R, SR, vz = 41, 24, 0.008
+    loc = T(rng.random((1, R, SR, 3)).astype(np.float32))
+    z = np.sort(rng.random((1, R, SR)).astype(np.float32) * 0.3, axis=-1)
+    z[0, :, 5] = z[0, :, 4]            # zero-length segment -> replaced by vsize
+    z[0, :, 9] = z[0, :, 8] - 0.01      # non-monotone depth -> cummax
+    z[0, 3, 12:] = 0.0                  # unfilled slots
+    loc[..., 2] = T(z)
+    valid = T(rng.random((1, R, SR)) > 0.2)
+    feats = T(rng.random((1, R, SR, 4)).astype(np.float32) * np.array([40, 1, 1, 1], np.float32))
+    d_ref = ro.ray_dist_from_depth(loc[..., 2], valid, vz, True)
+    o_ref = ro.ray_march(d_ref, valid, feats, torch.ones(1, 3))
+    color, opacity, accT, bw, bgT, dist = ray_march_from_depth(loc.cuda(), valid.cuda(), feats.cuda(), vz, 1, torch.ones(1, 3).cuda())
+    np.testing.assert_array_equal(dist.cpu().numpy(), d_ref.numpy())      # exact: same float ops
+    assert_close(color, o_ref[0], RTOL, 1e-6)
+    assert_close(bgT, o_ref[5], RTOL, 1e-12)
+
+
+def test_blur_golden_fwd_bwd():
+    from hybridneuralrendering_b200.blur import blur_select
+    G = load_golden("blur")
+    PN, PS, Nk = [int(v) for v in G["meta"]]
+    pred = cuda(G["pred"]).clone().requires_grad_(True)
+    out, sel = blur_select(pred, cuda(G["gt"]), cuda(G["kernels"]), PN, PS)
+    _, sel_ref = ro.blur_select(T(G["pred"]), T(G["gt"]), T(G["kernels"]), PN, PS)
+    np.testing.assert_array_equal(sel.cpu().numpy(), sel_ref.numpy().astype(np.int32))      # argmin index: exact
+    assert_close(out, G["out"], RTOL, 1e-6)
+    (out * cuda(G["G"])).sum().backward()
+    assert_close(pred.grad, G["grad_pred"], RTOL, 1e-6)
+
+
+def test_blur_module_method_dropin_shipped_shape():
+    """7x7 patches of 8x8 with the 36 shipped kernels, through blur_update_output(model)."""
+    import types
+    from hybridneuralrendering_b200.blur import blur_update_output, predefined_blur_kernels
+    rng = np.random.default_rng(1)
+    PN, PS = 7, 8
+    K = predefined_blur_kernels(3)
+    assert K.shape == (36, 9, 9)
+    pred, gt = T(rng.random((1, (PN * PS) ** 2, 3), dtype=np.float32)), T(rng.random((1, (PN * PS) ** 2, 3), dtype=np.float32))
+    ref, sel = ro.blur_select(pred, gt, T(K)[None], PN, PS)
+    m = types.SimpleNamespace(output={"coarse_raycolor": pred.cuda()}, gt_image=gt.cuda(), blur_kernels=T(K)[None], dilation_PatchNum=PN, dilation_PatchSize=PS)
+    blur_update_output(m)
+    assert_close(m.output["coarse_raycolor"], ref, RTOL, 1e-6)
+
+
+@pytest.mark.parametrize("M,N,ks,act", [(1, 1, (5,), 0), (130, 256, (284,), 1), (257, 256, (256, 7), 1), (300, 64, (45, 128, 3), 1),
+                                         (77, 1, (64,), 2), (64, 3, (45, 83), 3), (1000, 45, (45,), 0), (0, 8, (4,), 1)])
+def test_linear_fwd_bwd_vs_torch(M, N, ks, act):
+    from hybridneuralrendering_b200 import ops
+    rng = np.random.default_rng(M + N)
+    K = sum(ks)
+    srcs = [T(rng.standard_normal((M, k)).astype(np.float32)) for k in ks]
+    W, b = T((rng.standard_normal((N, K)) * 0.1).astype(np.float32)), T(rng.standard_normal(N).astype(np.float32))
+    res = T(rng.standard_normal((M, N)).astype(np.float32)) if act == 0 else None
+    G = T(rng.standard_normal((M, N)).astype(np.float32))
+
+    def ref():
+        xs = [s.double().clone().requires_grad_(True) for s in srcs]
+        Wd, bd = W.double().clone().requires_grad_(True), b.double().clone().requires_grad_(True)
+        y = torch.nn.functional.linear(torch.cat(xs, 1), Wd, bd)
+        y = [y, torch.nn.functional.leaky_relu(y, 0.01), torch.sigmoid(y), torch.sigmoid(y) * 1.002 - 0.001][act]
+        if res is not None:
+            y = y + res.double()
+        (y * G.double()).sum().backward()
+        return y, [x.grad for x in xs], Wd.grad, bd.grad
+
+    y_ref, gx_ref, gW_ref, gb_ref = ref()
+    xs = [s.cuda().clone().requires_grad_(True) for s in srcs]
+    Wc, bc = W.cuda().clone().requires_grad_(True), b.cuda().clone().requires_grad_(True)
+    y = ops.linear(xs, Wc, bc, act, res=res.cuda() if res is not None else None)
+    assert_close(y, y_ref, 1e-5, 1e-5)
+    if M > 0:
+        (y * G.cuda()).sum().backward()
+        for a, r in zip(xs, gx_ref):
+            assert_close(a.grad, r, 1e-4, grad_atol(r, 1e-5))
+        assert_close(Wc.grad, gW_ref, 1e-4, grad_atol(gW_ref, 1e-5))
+        assert_close(bc.grad, gb_ref, 1e-4, grad_atol(gb_ref, 1e-5))
+
+
+def test_linear_strided_sources_and_shared_block():
+    """column-slice sources (row stride > width) and a source shared by V row blocks (mods)"""
+    from hybridneuralrendering_b200 import ops
+    rng = np.random.default_rng(0)
+    V, Nv = 3, 50
+    g = T(rng.standard_normal((Nv, 128)).astype(np.float32))
+    a = T(rng.standard_normal((V * Nv, 45)).astype(np.float32))
+    W, b = T((rng.standard_normal((64, 45 + 128)) * 0.1).astype(np.float32)), T(rng.standard_normal(64).astype(np.float32))
+    gd, ad, Wd = g.double().requires_grad_(True), a.double().requires_grad_(True), W.double().requires_grad_(True)
+    y_ref = torch.nn.functional.leaky_relu(torch.nn.functional.linear(torch.cat([ad, gd.repeat(V, 1)], 1), Wd, b.double()), 0.01)
+    y_ref.square().sum().backward()
+    gc, ac, Wc = g.cuda().requires_grad_(True), a.cuda().requires_grad_(True), W.cuda().requires_grad_(True)
+    y = ops.linear([ac, gc], Wc, b.cuda(), 1, mods=(0, Nv), M=V * Nv)
+    assert_close(y, y_ref, 1e-5, 1e-5)
+    y.square().sum().backward()
+    assert_close(gc.grad, gd.grad, 1e-4, grad_atol(gd.grad, 1e-5))
+    assert_close(ac.grad, ad.grad, 1e-4, grad_atol(ad.grad, 1e-5))
+    assert_close(Wc.grad, Wd.grad, 1e-4, grad_atol(Wd.grad, 1e-5))
+    # slices
+    gi, gv = gc[:, :45], gc[:, 45:]
+    W2 = T((rng.standard_normal((3, 128)) * 0.1).astype(np.float32)).cuda()
+    y2 = ops.linear([gi, gv], W2, None, 0)
+    assert_close(y2, g.double() @ W2.cpu().double().t(), 1e-5, 1e-5)
