@@ -75,7 +75,9 @@ __global__ void blur_kernel(const float* __restrict__ pred,      // (S*S,3) rast
             }
             __syncthreads();
             float err = s_err;
-            if (err < best_err) {          // strict: first minimum wins, as torch.argmin
+            // strict <: first minimum wins, as torch.argmin; a NaN error (kernel whose border
+            // normalisation is 0/0) counts as the minimum, again as torch.argmin does
+            if (err < best_err || (err != err && best_err == best_err)) {
                 best_err = err; best = n;
                 bestv[0] = v[0]; bestv[1] = v[1]; bestv[2] = v[2];
             }

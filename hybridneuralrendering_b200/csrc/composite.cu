@@ -146,9 +146,9 @@ extern "C" int hnr_composite_fwd(const float* feats, const uint8_t* valid, const
                                  const float* bg, float vsize_z, int unit_mode, int64_t R, int64_t SR, float* ray_color,
                                  float* opacity, float* acc_trans, float* blend_weight, float* bg_trans, float* dist_out,
                                  void* stream) {
-    HNR_CHECK_ARG(R >= 0 && SR > 0, "composite_fwd: bad shape");
-    HNR_CHECK_ARG((z != nullptr) != (dist_in != nullptr), "composite_fwd: pass exactly one of z / dist_in");
     if (R == 0) return HNR_OK;
+    HNR_CHECK_ARG(R > 0 && SR > 0, "composite_fwd: bad shape");
+    HNR_CHECK_ARG((z != nullptr) != (dist_in != nullptr), "composite_fwd: pass exactly one of z / dist_in");
     const int threads = 256;
     const int64_t blocks = hnr_cdiv(R * 32, threads);
     composite_fwd_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(

@@ -197,14 +197,13 @@ linear_bwd_weight_kernel(const float* __restrict__ dY, int lddy, const float* __
     if (db && blockIdx.y == 0 && tid < 64 && n0 + tid < N) atomicAdd(&db[n0 + tid], bsum);
 }
 
-bool cat_ok(const float* const* p, const int64_t* ld, const int64_t* k, int64_t K) {
+template <typename PP> bool cat_ok(PP p, const int64_t* ld, const int64_t* k, int64_t K) {
     int64_t s = 0;
     for (int i = 0; i < 3; ++i) {
         if (k[i] < 0) return false;
-        if (k[i] > 0 && ld[i] < k[i]) return false;
+        if (k[i] > 0 && p && p[i] && ld[i] < k[i]) return false;
         s += k[i];
     }
-    (void)p;
     return s == K;
 }
 
@@ -213,9 +212,9 @@ bool cat_ok(const float* const* p, const int64_t* ld, const int64_t* k, int64_t 
 extern "C" int hnr_linear_fwd(const float* const* a_ptr, const int64_t* a_ld, const int64_t* a_k, const int64_t* a_mod, const float* W, const float* bias,
                               const float* res, int64_t ldres, float* Y, int64_t ldy, int64_t M, int64_t N, int64_t K, int act,
                               void* stream) {
-    HNR_CHECK_ARG(M >= 0 && N > 0 && K > 0 && ldy >= N, "linear_fwd: bad shape");
-    HNR_CHECK_ARG(cat_ok(a_ptr, a_ld, a_k, K), "linear_fwd: concat widths must sum to K");
     if (M == 0) return HNR_OK;
+    HNR_CHECK_ARG(M > 0 && N > 0 && K > 0 && ldy >= N, "linear_fwd: bad shape");
+    HNR_CHECK_ARG(cat_ok(a_ptr, a_ld, a_k, K), "linear_fwd: concat widths must sum to K");
     Cat3 A;
     for (int i = 0; i < 3; ++i) { A.p[i] = a_ptr[i]; A.ld[i] = (int)a_ld[i]; A.k[i] = (int)a_k[i]; A.mod[i] = a_mod ? a_mod[i] : 0; }
     HNR_CHECK_ARG(!(res && act != HNR_ACT_NONE), "linear_fwd: residual only with act=none");
@@ -227,9 +226,9 @@ extern "C" int hnr_linear_fwd(const float* const* a_ptr, const int64_t* a_ld, co
 
 extern "C" int hnr_linear_bwd_data(const float* dY, int64_t lddy, const float* Y, int64_t ldy, const float* W, float* const* da_ptr,
                                    const int64_t* da_ld, const int64_t* a_k, int64_t M, int64_t N, int64_t K, int act, void* stream) {
-    HNR_CHECK_ARG(M >= 0 && N > 0 && K > 0, "linear_bwd_data: bad shape");
-    HNR_CHECK_ARG(cat_ok(nullptr, da_ld, a_k, K), "linear_bwd_data: concat widths must sum to K");
     if (M == 0) return HNR_OK;
+    HNR_CHECK_ARG(M > 0 && N > 0 && K > 0, "linear_bwd_data: bad shape");
+    HNR_CHECK_ARG(cat_ok(da_ptr, da_ld, a_k, K), "linear_bwd_data: concat widths must sum to K");
     Cat3Out dA;
     for (int i = 0; i < 3; ++i) { dA.p[i] = da_ptr[i]; dA.ld[i] = (int)da_ld[i]; dA.k[i] = (int)a_k[i]; }
     dim3 grid((unsigned)hnr_cdiv(M, BM), (unsigned)hnr_cdiv(K, BN));
@@ -241,9 +240,9 @@ extern "C" int hnr_linear_bwd_data(const float* dY, int64_t lddy, const float* Y
 extern "C" int hnr_linear_bwd_weight(const float* dY, int64_t lddy, const float* Y, int64_t ldy, const float* const* a_ptr,
                                      const int64_t* a_ld, const int64_t* a_k, const int64_t* a_mod, float* dW, float* db, int64_t M, int64_t N, int64_t K,
                                      int act, void* stream) {
-    HNR_CHECK_ARG(M >= 0 && N > 0 && K > 0, "linear_bwd_weight: bad shape");
-    HNR_CHECK_ARG(cat_ok(a_ptr, a_ld, a_k, K), "linear_bwd_weight: concat widths must sum to K");
     if (M == 0) return HNR_OK;
+    HNR_CHECK_ARG(M > 0 && N > 0 && K > 0, "linear_bwd_weight: bad shape");
+    HNR_CHECK_ARG(cat_ok(a_ptr, a_ld, a_k, K), "linear_bwd_weight: concat widths must sum to K");
     Cat3 A;
     for (int i = 0; i < 3; ++i) { A.p[i] = a_ptr[i]; A.ld[i] = (int)a_ld[i]; A.k[i] = (int)a_k[i]; A.mod[i] = a_mod ? a_mod[i] : 0; }
     const int64_t tiles = hnr_cdiv(N, BM) * hnr_cdiv(K, BN);

@@ -91,6 +91,7 @@ def ray_march_from_depth(sample_loc, ray_valid, ray_features, vsize_z, unit_mode
     valid = ray_valid.reshape(N * R, SR).to(torch.uint8).contiguous()
     loc = sample_loc.reshape(N * R, SR, 3).float().contiguous()
     bg = bg_color.reshape(-1, 3).float() if bg_color is not None else None
-    color, opacity, accT, bw, bgT, dist = ops.CompositeFn.apply(ray_features.reshape(N * R, SR, 4), valid, loc.view(-1)[2:], 3, None, bg,
-                                                                float(vsize_z), int(unit_mode))
+    with ops.tag("composite"):
+        color, opacity, accT, bw, bgT, dist = ops.CompositeFn.apply(ray_features.reshape(N * R, SR, 4), valid, loc.view(-1)[2:], 3, None, bg,
+                                                                    float(vsize_z), int(unit_mode))
     return color.view(N, R, 3), opacity.view(N, R, SR), accT.view(N, R, SR), bw.view(N, R, SR, 1), bgT.view(N, R, 1), dist.view(N, R, SR)

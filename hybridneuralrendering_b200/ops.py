@@ -24,6 +24,41 @@ def _count(n: int = 1):
     LAUNCHES += n
 
 
+# optional per-launch device timing (CUDA events on the launching stream); used by profiling.py / bench.py
+TIMERS = None          # None = off, else a list of (tag, start_event, end_event)
+_TAG = ["untagged"]
+
+
+class tag:
+    """`with ops.tag("nbr_mlp"):` labels the launches issued inside for the timers"""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        _TAG.append(self.name)
+
+    def __exit__(self, *a):
+        _TAG.pop()
+
+
+class _launch:
+    def __init__(self, n=1):
+        self.n = n
+
+    def __enter__(self):
+        _count(self.n)
+        if TIMERS is not None:
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.e = torch.cuda.Event(enable_timing=True)
+            self.s.record()
+
+    def __exit__(self, *a):
+        if TIMERS is not None:
+            self.e.record()
+            TIMERS.append((_TAG[-1], self.s, self.e))
+
+
 def _f32c(t: torch.Tensor) -> torch.Tensor:
     if t.dtype != torch.float32:
         t = t.float()
@@ -68,9 +103,9 @@ class LinearFn(torch.autograd.Function):
         modl = list(mods) + [0] * (3 - len(mods))
         resv = _rows2d(res) if res is not None else None
         bc = _f32c(b) if b is not None else None
-        check(lib().hnr_linear_fwd(ptr_array(padded), i64_array(lds), i64_array(ks), i64_array(modl), ptr(W), ptr(bc), ptr(resv),
-                                   resv.stride(0) if resv is not None else 0, ptr(Y), N, M, N, K, act, stream()), "linear_fwd")
-        _count()
+        with _launch():
+            check(lib().hnr_linear_fwd(ptr_array(padded), i64_array(lds), i64_array(ks), i64_array(modl), ptr(W), ptr(bc), ptr(resv),
+                                       resv.stride(0) if resv is not None else 0, ptr(Y), N, M, N, K, act, stream()), "linear_fwd")
         ctx.act, ctx.M, ctx.mods, ctx.nsrc, ctx.has_res, ctx.has_b = act, M, modl, len(srcs), res is not None, b is not None
         ctx.save_for_backward(W, Y, *srcs)
         return Y
@@ -132,11 +167,11 @@ class NbrWeightsFn(torch.autograd.Function):
         weight = torch.empty((S, K), device=xyz.device, dtype=torch.float32)
         confc = torch.empty((S, K), device=xyz.device, dtype=torch.float32)
         valid = torch.empty((S,), device=xyz.device, dtype=torch.uint8)
-        check(lib().hnr_nbr_weights(ptr(xyz), ptr(conf), ptr(pidx), ptr(mask), ptr(loc_w), S, K, ptr(weight), ptr(confc), ptr(valid),
-                                    stream()), "nbr_weights")
-        _count()
+        with _launch():
+            check(lib().hnr_nbr_weights(ptr(xyz), ptr(conf), ptr(pidx), ptr(mask), ptr(loc_w), S, K, ptr(weight), ptr(confc), ptr(valid),
+                                        stream()), "nbr_weights")
         ctx.save_for_backward(pidx)
-        ctx.n_conf = conf.numel() if conf is not None else 0
+        ctx.conf_shape = conf.shape if conf is not None else None
         ctx.mark_non_differentiable(weight, valid)
         return weight, confc, valid
 
@@ -147,7 +182,7 @@ class NbrWeightsFn(torch.autograd.Function):
         if ctx.needs_input_grad[1] and g_confc is not None:
             S, K = pidx.shape
             g = _f32c(g_confc)
-            d_conf = torch.zeros(ctx.n_conf, device=pidx.device, dtype=torch.float32)
+            d_conf = torch.zeros(ctx.conf_shape, device=pidx.device, dtype=torch.float32)
             check(lib().hnr_conf_bwd(None, None, None, ptr(pidx), ptr(g), 0, S, K, ptr(d_conf), stream()), "conf_bwd")
             _count()
         return None, d_conf, None, None, None
@@ -160,9 +195,9 @@ class NbrFeaturesFn(torch.autograd.Function):
         require_cuda(emb, color, dirs, xyz, pidx, vlist)
         X0 = torch.empty((Nv * K, X0_W), device=emb.device, dtype=torch.float32)
         E = torch.empty((Nv * K, E_W), device=emb.device, dtype=torch.float32)
-        check(lib().hnr_nbr_features(ptr(xyz), ptr(xyz_pers), ptr(emb), ptr(color), ptr(dirs), ptr(pidx), ptr(vlist), ptr(loc_w),
-                                     ptr(loc_pers), ptr(raydirs), ptr(cam), Nv, K, emb.shape[-1], ptr(X0), ptr(E), stream()), "nbr_features")
-        _count()
+        with _launch():
+            check(lib().hnr_nbr_features(ptr(xyz), ptr(xyz_pers), ptr(emb), ptr(color), ptr(dirs), ptr(pidx), ptr(vlist), ptr(loc_w),
+                                         ptr(loc_pers), ptr(raydirs), ptr(cam), Nv, K, emb.shape[-1], ptr(X0), ptr(E), stream()), "nbr_features")
         ctx.cam, ctx.Nv, ctx.K = cam, Nv, K
         ctx.shapes = (emb.shape, color.shape, dirs.shape)
         ctx.save_for_backward(emb, pidx, mask if mask is not None else torch.empty(0, device=emb.device), vlist, raydirs)
@@ -196,9 +231,9 @@ class AlphaKSumFn(torch.autograd.Function):
         sigma = torch.empty((Nv, 1), device=H.device, dtype=torch.float32)
         X5 = torch.empty((Nv, X5_W), device=H.device, dtype=torch.float32)
         araw = torch.empty((Nv * K,), device=H.device, dtype=torch.float32)
-        check(lib().hnr_alpha_ksum_fwd(ptr(H), ptr(weight), ptr(confc_c), ptr(vlist), ptr(w_alpha_c), ptr(b_alpha_c), ptr(raydirs), ptr(cam),
-                                       Nv, K, H.shape[1], ptr(sigma), ptr(X5), ptr(araw), stream()), "alpha_ksum_fwd")
-        _count()
+        with _launch():
+            check(lib().hnr_alpha_ksum_fwd(ptr(H), ptr(weight), ptr(confc_c), ptr(vlist), ptr(w_alpha_c), ptr(b_alpha_c), ptr(raydirs), ptr(cam),
+                                           Nv, K, H.shape[1], ptr(sigma), ptr(X5), ptr(araw), stream()), "alpha_ksum_fwd")
         ctx.save_for_backward(H, confc_c, w_alpha_c, weight, vlist, araw)
         ctx.wshape, ctx.bshape = w_alpha.shape, b_alpha.shape
         return sigma, X5
@@ -233,9 +268,9 @@ def project_views(loc_w: torch.Tensor, w2c: torch.Tensor, Kmat: torch.Tensor, ca
     require_cuda(loc_w, w2c, Kmat, campos, campos_n)
     xy = torch.empty((V, S, 2), device=loc_w.device, dtype=torch.float32)
     delta = torch.empty((V, S, 3), device=loc_w.device, dtype=torch.float32)
-    check(lib().hnr_project_views(ptr(loc_w), ptr(w2c), ptr(Kmat), ptr(campos), ptr(campos_n), V, S, ptr(xy), ptr(delta), stream()),
-          "project_views")
-    _count()
+    with _launch():
+        check(lib().hnr_project_views(ptr(loc_w), ptr(w2c), ptr(Kmat), ptr(campos), ptr(campos_n), V, S, ptr(xy), ptr(delta), stream()),
+              "project_views")
     return xy, delta
 
 
@@ -252,9 +287,9 @@ class ImageGatherFn(torch.autograd.Function):
             hw += [l.shape[1], l.shape[2]]
         aux = torch.empty((V, Nv, AUX_C), device=xy.device, dtype=torch.float32)
         ok = torch.empty((V, Nv), device=xy.device, dtype=torch.float32)
-        check(lib().hnr_image_gather_fwd(ptr_array(lv), i64_array(hw), ptr(xy), ptr(vlist), V, S, Nv, ptr(aux), ptr(ok), stream()),
-              "image_gather_fwd")
-        _count()
+        with _launch():
+            check(lib().hnr_image_gather_fwd(ptr_array(lv), i64_array(hw), ptr(xy), ptr(vlist), V, S, Nv, ptr(aux), ptr(ok), stream()),
+                  "image_gather_fwd")
         ctx.hw, ctx.shapes, ctx.dims = hw, [l.shape for l in lv], (V, S, Nv)
         ctx.save_for_backward(xy, vlist)
         ctx.mark_non_differentiable(ok)
@@ -280,8 +315,8 @@ class BlendFn(torch.autograd.Function):
         aux, sig = _f32c(aux), _f32c(sig)
         V, Nv = aux.shape[0], aux.shape[1]
         merged = torch.empty((Nv, AUX_C), device=aux.device, dtype=torch.float32)
-        check(lib().hnr_blend_fwd(ptr(aux), ptr(sig), ptr(ok), ptr(keep), V, Nv, ptr(merged), stream()), "blend_fwd")
-        _count()
+        with _launch():
+            check(lib().hnr_blend_fwd(ptr(aux), ptr(sig), ptr(ok), ptr(keep), V, Nv, ptr(merged), stream()), "blend_fwd")
         ctx.save_for_backward(aux, sig, ok, keep if keep is not None else torch.empty(0, device=aux.device))
         ctx.has_keep = keep is not None
         return merged
@@ -318,9 +353,9 @@ class CompositeFn(torch.autograd.Function):
         bgT = torch.empty((R,), device=dev, dtype=torch.float32)
         dist_out = torch.empty((R, SR), device=dev, dtype=torch.float32)
         bgc = _f32c(bg).view(-1) if bg is not None else None
-        check(lib().hnr_composite_fwd(ptr(feats), ptr(valid), ptr(z), z_stride, ptr(dist), ptr(bgc), float(vsize_z), int(unit_mode), R, SR,
-                                      ptr(color), ptr(opacity), ptr(accT), ptr(bw), ptr(bgT), ptr(dist_out), stream()), "composite_fwd")
-        _count()
+        with _launch():
+            check(lib().hnr_composite_fwd(ptr(feats), ptr(valid), ptr(z), z_stride, ptr(dist), ptr(bgc), float(vsize_z), int(unit_mode), R, SR,
+                                          ptr(color), ptr(opacity), ptr(accT), ptr(bw), ptr(bgT), ptr(dist_out), stream()), "composite_fwd")
         ctx.save_for_backward(feats, valid, dist_out, accT, bgT, bgc if bgc is not None else torch.empty(0, device=dev))
         ctx.has_bg = bgc is not None
         ctx.mark_non_differentiable(dist_out)

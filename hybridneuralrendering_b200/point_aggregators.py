@@ -69,6 +69,36 @@ def _init_seq(s):
         nn.init.zeros_(mods[-1].bias)
 
 
+def _pyramid(x, ps):
+    outs = []
+    for i in range(3):
+        w0, b0, w1, b1 = ps[4 * i:4 * i + 4]
+        x = F.leaky_relu(F.conv2d(x, w0, b0, stride=2, padding=1), 0.01)
+        x = F.leaky_relu(F.conv2d(x, w1, b1, stride=1, padding=1), 0.01)
+        outs.append(x)
+    return outs
+
+
+class _ExactConvPyramid(torch.autograd.Function):
+    """the six pyramid convolutions (reference :598-630, :1059-1063) through cuDNN in exact fp32, forward
+    AND backward: cuDNN's default TF32 path (10-bit mantissa) would break the rtol 1e-4 bar, and a plain
+    `cudnn.flags` context around the forward would not cover the backward pass."""
+
+    @staticmethod
+    def forward(ctx, x, *params):
+        with torch.enable_grad(), torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            ps = [p.detach().requires_grad_(True) for p in params]
+            outs = _pyramid(x.detach(), ps)
+        ctx.ps, ctx.outs = ps, outs
+        return tuple(o.detach() for o in outs)
+
+    @staticmethod
+    def backward(ctx, *gs):
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            grads = torch.autograd.grad(ctx.outs, ctx.ps, [g.contiguous() for g in gs], allow_unused=True)
+        return (None, *grads)
+
+
 class PointAggregator(nn.Module):
     def __init__(self, opt):
         super().__init__()
@@ -128,10 +158,10 @@ class PointAggregator(nn.Module):
     def feature_pyramid(self, img_n: torch.Tensor):
         """img_n (1,V,H,W,3) -> NHWC levels [(V,H,W,3),(V,h1,w1,6),(V,h2,w2,12),(V,h3,w3,24)]"""
         img = img_n[0]
-        x = img.permute(0, 3, 1, 2)
-        s1 = self.aux_block_s1(x)
-        s2 = self.aux_block_s2(s1)
-        s3 = self.aux_block_s3(s2)
+        params = []
+        for blk in (self.aux_block_s1, self.aux_block_s2, self.aux_block_s3):
+            params += [blk[0].weight, blk[0].bias, blk[2].weight, blk[2].bias]
+        s1, s2, s3 = _ExactConvPyramid.apply(img.permute(0, 3, 1, 2), *params)
         return [img.contiguous()] + [t.permute(0, 2, 3, 1).contiguous() for t in (s1, s2, s3)]
 
     # ------------------------------------------------------------------ core
@@ -157,7 +187,8 @@ class PointAggregator(nn.Module):
         opt = self.opt
         xyz, xyz_pers, emb, color, dirs, conf = tables
         S, K = pidx.shape
-        weight, confc, valid = ops.NbrWeightsFn.apply(xyz, conf, pidx, mask, loc_w)
+        with ops.tag("gather"):
+            weight, confc, valid = ops.NbrWeightsFn.apply(xyz, conf, pidx, mask, loc_w)
         if vlist is None:
             vlist = torch.nonzero(valid, as_tuple=False).view(-1).to(torch.int32)        # sync (drop-in path only)
         Nv = vlist.shape[0]
@@ -165,36 +196,51 @@ class PointAggregator(nn.Module):
         if Nv == 0:
             return decoded, valid.bool(), weight, confc
         b1, b3 = self.block1, self.block3
-        X0, E = ops.NbrFeaturesFn.apply(emb, color, dirs, xyz, xyz_pers, pidx, mask, vlist, loc_w, loc_pers, raydirs, cam)
-        h = ops.linear([X0], b1[0].weight, b1[0].bias, ACT_LRELU)
-        h = ops.linear([h], b1[2].weight, b1[2].bias, ACT_LRELU)
-        h = ops.linear([h, E], b3[0].weight, b3[0].bias, ACT_LRELU)
-        h = ops.linear([h], b3[2].weight, b3[2].bias, ACT_LRELU)
-        sigma, X5 = ops.AlphaKSumFn.apply(h, confc, self.alpha_branch[0].weight, self.alpha_branch[0].bias, weight, vlist, raydirs, cam)
+        with ops.tag("gather"):
+            X0, E = ops.NbrFeaturesFn.apply(emb, color, dirs, xyz, xyz_pers, pidx, mask, vlist, loc_w, loc_pers, raydirs, cam)
+        with ops.tag("nbr_mlp"):
+            h = ops.linear([X0], b1[0].weight, b1[0].bias, ACT_LRELU)
+            h = ops.linear([h], b1[2].weight, b1[2].bias, ACT_LRELU)
+            h = ops.linear([h, E], b3[0].weight, b3[0].bias, ACT_LRELU)
+            h = ops.linear([h], b3[2].weight, b3[2].bias, ACT_LRELU)
+        with ops.tag("ksum"):
+            sigma, X5 = ops.AlphaKSumFn.apply(h, confc, self.alpha_branch[0].weight, self.alpha_branch[0].bias, weight, vlist, raydirs, cam)
         cf = self.color_feature_branch
-        g = ops.linear([X5], cf[0].weight, cf[0].bias, ACT_LRELU)
-        g = ops.linear([g], cf[2].weight, cf[2].bias, ACT_LRELU)
-        g = ops.linear([g], cf[4].weight, cf[4].bias, ACT_LRELU)
+        with ops.tag("sample_mlp"):
+            g = ops.linear([X5], cf[0].weight, cf[0].bias, ACT_LRELU)
+            g = ops.linear([g], cf[2].weight, cf[2].bias, ACT_LRELU)
+            g = ops.linear([g], cf[4].weight, cf[4].bias, ACT_LRELU)
         V = int(opt.use_nearest)
         if V > 0:
-            aux, ok = ops.ImageGatherFn.apply(levels[0], levels[1], levels[2], levels[3], xy, vlist)
+            with ops.tag("image_gather"):
+                aux, ok = ops.ImageGatherFn.apply(levels[0], levels[1], levels[2], levels[3], xy, vlist)
             dv = delta.reshape(V, S, 3).index_select(1, vlist.long()).reshape(V * Nv, 3)
             am = self.aux_merge_weight_block
-            t = ops.linear([aux.view(V * Nv, 45), g, dv], am[0].weight, am[0].bias, ACT_LRELU, mods=(0, Nv, 0), M=V * Nv)
-            t = ops.linear([t], am[2].weight, am[2].bias, ACT_LRELU)
-            t = ops.linear([t], am[4].weight, am[4].bias, ACT_LRELU)
-            sig = ops.linear([t], am[6].weight, am[6].bias, ACT_SIGMOID)
-            merged = ops.BlendFn.apply(aux, sig, ok, self._keep_mask(R, SR, vlist))
+            with ops.tag("sample_mlp"):
+                t = ops.linear([aux.view(V * Nv, 45), g, dv], am[0].weight, am[0].bias, ACT_LRELU, mods=(0, Nv, 0), M=V * Nv)
+                t = ops.linear([t], am[2].weight, am[2].bias, ACT_LRELU)
+                t = ops.linear([t], am[4].weight, am[4].bias, ACT_LRELU)
+                sig = ops.linear([t], am[6].weight, am[6].bias, ACT_SIGMOID)
+            with ops.tag("blend"):
+                merged = ops.BlendFn.apply(aux, sig, ok, self._keep_mask(R, SR, vlist))
         else:
             merged = torch.zeros((Nv, 45), device=pidx.device, dtype=torch.float32)
         gi, gv = g[:, :45], g[:, 45:]
         cm = self.color_mixup_block
-        m = ops.linear([gi, merged], cm[0].weight, cm[0].bias, ACT_LRELU)
-        m = ops.linear([m], cm[2].weight, cm[2].bias, ACT_LRELU)
-        m = ops.linear([m], cm[4].weight, cm[4].bias, ACT_NONE, res=gi)
-        rgb = ops.linear([m, gv], self.color_final_block[0].weight, self.color_final_block[0].bias, ACT_COLOR)
+        with ops.tag("sample_mlp"):
+            m = ops.linear([gi, merged], cm[0].weight, cm[0].bias, ACT_LRELU)
+            m = ops.linear([m], cm[2].weight, cm[2].bias, ACT_LRELU)
+            m = ops.linear([m], cm[4].weight, cm[4].bias, ACT_NONE, res=gi)
+            rgb = ops.linear([m, gv], self.color_final_block[0].weight, self.color_final_block[0].bias, ACT_COLOR)
         decoded = decoded.index_copy(0, vlist.long(), torch.cat([sigma, rgb], dim=-1))
+        self._last = (pidx, mask, vlist)
         return decoded, valid.bool(), weight, confc
+
+    def last_valid_neighbours(self) -> int:
+        """number of valid (sample, neighbour) pairs of the last call (profiling only; syncs)"""
+        pidx, mask, vlist = self._last
+        rows = (mask if mask is not None else (pidx >= 0)).index_select(0, vlist.long())
+        return int(rows.sum())
 
     # ------------------------------------------------------------------ drop-in forward (gathered tensors)
     def forward(self, sampled_color, sampled_Rw2c, sampled_dir, sampled_conf, sampled_embedding, sampled_xyz_pers, sampled_xyz,

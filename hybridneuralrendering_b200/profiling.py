@@ -1,0 +1,62 @@
+"""Live device timing of the hot-path kernels (CUDA events on the launching stream) and the roofline
+record bench.py publishes.  Algorithmic work per unit: SURVEY.md §8(d) / DESIGN.md."""
+from __future__ import annotations
+
+from typing import Dict
+
+import torch
+
+from . import ops
+from .renderer import render_rays
+
+FLOP_PER_NEIGHBOUR = 542_720            # 2*(284*256 + 256*256 + 263*256 + 256*256 + 256), SURVEY.md §8d
+
+
+def stage_times(net, frame, chunk_rays: int) -> Dict[str, float]:
+    """render one frame with per-launch events; returns {tag: milliseconds} plus '_units' counters"""
+    torch.cuda.synchronize()
+    ops.TIMERS = []
+    units = {"valid_neighbours": 0, "valid_samples": 0, "kept_rays": 0}
+    raydir = frame["raydir"]
+    R = raydir.shape[1]
+    static = {k: v for k, v in frame.items() if k not in ("raydir", "pixel_idx", "gt_image")}
+    try:
+        with torch.no_grad():
+            for r0 in range(0, R, chunk_rays):
+                net(raydir=raydir[:, r0:min(R, r0 + chunk_rays)], pixel_idx=None, **static)
+                ex = net.last_extras
+                units["valid_samples"] += ex.n_valid
+                units["kept_rays"] += ex.n_rays
+                units["valid_neighbours"] += net.aggregator.last_valid_neighbours() if ex.n_valid else 0
+        torch.cuda.synchronize()
+        out: Dict[str, float] = {}
+        launches: Dict[str, int] = {}
+        for tag, s, e in ops.TIMERS:
+            out[tag] = out.get(tag, 0.0) + s.elapsed_time(e)
+            launches[tag] = launches.get(tag, 0) + 1
+    finally:
+        ops.TIMERS = None
+    out["_units"] = units
+    out["_launches"] = launches
+    return out
+
+
+def dominant_kernel_roofline(net, frame, chunk_rays: int, peaks_and_kind) -> Dict:
+    """roofline record for the dominant kernel of the render step: the per-neighbour MLP.
+    achieved = 542,720 FLOP x valid neighbours of the frame / summed duration of its launches."""
+    peaks, kind = peaks_and_kind
+    t = stage_times(net, frame, chunk_rays)
+    units = t.pop("_units")
+    launches = t.pop("_launches")
+    total = sum(t.values())
+    ms = t.get("nbr_mlp", 0.0)
+    flops = FLOP_PER_NEIGHBOUR * units["valid_neighbours"]
+    achieved = flops / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+    # fp32-accurate tensor-core path = 3 TF32 MMAs per product -> peak = TF32 / 3; TF32 dense = bf16 / 2
+    # (MEASURED_PEAKS.json has no TF32 entry: "of derived")
+    peak = peaks["bf16_tflops_sustained"] / 2.0 / 3.0
+    return {"bound": "tensor", "kernel": "per-neighbour MLP (block1+block3, 4 dense layers)", "achieved": achieved, "peak": peak,
+            "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": None,
+            "peak_basis": f"bf16_tflops_sustained/2/3 of {kind} (3xTF32 fp32-equivalent)",
+            "launches": launches.get("nbr_mlp", 0), "kernel_ms_per_step": ms, "share_of_step": ms / total if total else None,
+            "units": units, "stage_ms": {k: round(v, 3) for k, v in sorted(t.items())}}

@@ -218,12 +218,12 @@ class lighting_fast_querier:
         ray_mask = torch.empty((R,), device=dev, dtype=torch.int8)
         ray_ids = torch.empty((R,), device=dev, dtype=torch.int32)
         vlist = torch.empty((R * SR,), device=dev, dtype=torch.int32)
-        check(lib().hnr_query(ptr(campos), ptr(camrot), ptr(raydir), ptr(ts), ts_stride, R, D, SR, K, G.g, ptr(G.cell_start),
+        with ops.tag("query"), ops._launch(10):
+          check(lib().hnr_query(ptr(campos), ptr(camrot), ptr(raydir), ptr(ts), ts_stride, R, D, SR, K, G.g, ptr(G.cell_start),
                               ptr(G.pts_sorted), ptr(G.occ_bits), ptr(sample_loc_full), ptr(b["pidx_full"]), ptr(b["nsamp"]),
                               ptr(b["nvalid"]), ptr(b["keep"]), ptr(b["ray_off"]), ptr(b["val_off"]), ptr(b["scratch"]), ptr(out_pidx),
                               ptr(out_loc_pers), ptr(out_loc_w), ptr(out_dirs), ptr(ray_mask), ptr(ray_ids), ptr(vlist), ptr(b["counts"]),
                               stream()), "query")
-        ops._count(10)
         b["counts_host"].copy_(b["counts"], non_blocking=True)
         torch.cuda.current_stream().synchronize()                  # the single readback of this call
         Rk, Nv = int(b["counts_host"][0]), int(b["counts_host"][1])

@@ -81,20 +81,41 @@ def point_attributes(rng: np.random.Generator, N: int, F: int = 32) -> Dict[str,
     )
 
 
-def _thin_cells(xyz: np.ndarray, cell: float, max_per_cell: int, origin: np.ndarray) -> np.ndarray:
-    """drop points so that no cell of edge `cell` holds more than max_per_cell (keeps the parity
-    configs off the reference's random-replacement path)."""
-    c = np.floor((xyz - origin) / np.float32(cell)).astype(np.int64)
-    c -= c.min(axis=0)
-    dims = c.max(axis=0) + 1
-    key = (c[:, 0] * dims[1] + c[:, 1]) * dims[2] + c[:, 2]
-    order = np.argsort(key, kind="stable")
-    ks = key[order]
-    start = np.r_[0, np.nonzero(np.diff(ks))[0] + 1]
-    rank = np.arange(len(ks)) - np.repeat(start, np.diff(np.r_[start, len(ks)]))
-    keep = np.zeros(len(ks), bool)
-    keep[order] = rank < max_per_cell
-    return xyz[keep]
+def _grid_origin(xyz: np.ndarray, cell: float, ranges, kernel: int = 3) -> np.ndarray:
+    """origin of the query grid for this cloud: bbox (clipped to `ranges`) minus cell*kernel/2, in
+    the f32 arithmetic of the reference's get_hyperparameters (query_point_indices_worldcoords.py:46-77)."""
+    mn = xyz.min(axis=0).astype(np.float32)
+    if ranges is not None:
+        mn = np.maximum(mn, np.asarray(ranges[:3], np.float32))
+    pad = (np.full(3, cell, np.float32) * np.asarray([kernel] * 3) / 2).astype(np.float32)
+    return (mn - pad).astype(np.float32)
+
+
+def _thin_cells(xyz: np.ndarray, cell: float, max_per_cell: int, ranges=None) -> np.ndarray:
+    """drop points so that no voxel of the query grid holds more than max_per_cell (keeps the parity
+    configs off the reference's random-replacement path).  The bbox-defining points
+    are kept so the grid origin does not move."""
+    for _ in range(4):
+        origin = _grid_origin(xyz, cell, ranges)
+        c = np.floor(((xyz - origin).astype(np.float32) / np.float32(cell)).astype(np.float32)).astype(np.int64)
+        c -= c.min(axis=0)
+        dims = c.max(axis=0) + 1
+        key = (c[:, 0] * dims[1] + c[:, 1]) * dims[2] + c[:, 2]
+        prio = np.ones(len(xyz), np.int8)
+        prio[np.r_[xyz.argmin(axis=0), xyz.argmax(axis=0)]] = 0        # extreme points first in their voxel
+        order = np.lexsort((np.arange(len(xyz)), prio, key))
+        ks = key[order]
+        start = np.r_[0, np.nonzero(np.diff(ks))[0] + 1]
+        rank = np.arange(len(ks)) - np.repeat(start, np.diff(np.r_[start, len(ks)]))
+        keep = np.zeros(len(ks), bool)
+        keep[order] = rank < max_per_cell
+        if keep.all():
+            break
+        xyz = xyz[keep]
+    # bbox-defining points to the front so that truncating the cloud keeps the grid origin
+    ext = np.unique(np.r_[xyz.argmin(axis=0), xyz.argmax(axis=0)])
+    rest = np.setdiff1d(np.arange(len(xyz)), ext, assume_unique=False)
+    return xyz[np.r_[ext, rest]]
 
 
 def lego_scene(N: int, seed: int = 0, vsize: float = 0.004, vscale: int = 2, P: int = 12) -> np.ndarray:
@@ -116,7 +137,7 @@ def lego_scene(N: int, seed: int = 0, vsize: float = 0.004, vscale: int = 2, P: 
     inside = np.all((xyz > lo) & (xyz < hi), axis=-1)
     xyz = xyz[inside]
     xyz = xyz[rng.permutation(len(xyz))]
-    xyz = _thin_cells(xyz, vsize * vscale, P, lo)
+    xyz = _thin_cells(xyz, vsize * vscale, P - 1, LEGO_BOX)
     if len(xyz) < N:
         raise RuntimeError(f"lego_scene produced {len(xyz)} < {N} points; lower N")
     return np.ascontiguousarray(xyz[:N])
@@ -150,7 +171,7 @@ def room_scene(N: int, seed: int = 0, size=(6.0, 5.0, 3.0), vsize: float = 0.008
         out.append(p)
     xyz = np.concatenate(out).astype(np.float32)
     xyz = xyz[rng.permutation(len(xyz))]
-    xyz = _thin_cells(xyz, vsize * vscale, P, xyz.min(axis=0))
+    xyz = _thin_cells(xyz, vsize * vscale, P - 1, None)
     if len(xyz) < N:
         raise RuntimeError(f"room_scene produced {len(xyz)} < {N} points; lower N")
     return np.ascontiguousarray(xyz[:N])

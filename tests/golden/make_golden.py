@@ -145,6 +145,7 @@ def blur_case():
         taps = rng.integers(2, 9)
         ii = rng.integers(0, 9, taps); jj = rng.integers(0, 9, taps)
         k[n, ii, jj] = rng.random(taps).astype(np.float32) + 0.1
+        k[n, 4, 4] = 0.5                       # centre tap as in the shipped line kernels: border normalisation never 0/0
         k[n] /= k[n].sum()
     # make the argmin non-trivial: gt of patch p := pred blurred with kernel (3p mod Nk) + small noise,
     # except the last patch whose gt is pred itself (identity candidate wins)

@@ -9,6 +9,9 @@ from oracle import render_oracle as ro
 pytestmark = pytest.mark.gpu
 
 RTOL = 1e-4   # north_star: renders / gradients within rtol 1e-4 in fp32
+# opacity = 1 - exp(-sigma*dist) is evaluated in fp32 by the reference too: its absolute error is one
+# ulp of 1.0 (6e-8) whatever the magnitude of the result, so tiny opacities carry an absolute tolerance
+OPACITY_ATOL = 2e-7
 
 
 def test_ray_march_golden_fwd_bwd():
@@ -17,9 +20,9 @@ def test_ray_march_golden_fwd_bwd():
     f = cuda(G["rm_feats"]).clone().requires_grad_(True)
     o = ray_march(cuda(G["rm_dist"]), cuda(G["rm_valid"]), f, radiance_render, alpha_blend, cuda(G["rm_bg"]))
     assert_close(o[0], G["rm_ray_color"], RTOL, 1e-6)
-    assert_close(o[2], G["rm_opacity"], RTOL, 1e-7)
+    assert_close(o[2], G["rm_opacity"], RTOL, OPACITY_ATOL)
     assert_close(o[3], G["rm_accT"], RTOL, 1e-12)
-    assert_close(o[4], G["rm_bw"], RTOL, 1e-9)
+    assert_close(o[4], G["rm_bw"], RTOL, OPACITY_ATOL)
     assert_close(o[5], G["rm_bgT"], RTOL, 1e-12)
     (o[0] * cuda(G["rm_G"])).sum().backward()
     assert_close(f.grad, G["rm_grad_feats"], RTOL, grad_atol(G["rm_grad_feats"], 1e-6))
@@ -43,7 +46,7 @@ def test_ray_march_random_vs_oracle_all_outputs(R, SR):
     fg = feats.cuda().clone().requires_grad_(True)
     og = ray_march(dist.cuda(), valid.cuda(), fg, radiance_render, alpha_blend, bg.cuda())
     for i in (0, 2, 3, 4, 5):
-        assert_close(og[i], oo[i], RTOL, 1e-9, f"output {i}")
+        assert_close(og[i], oo[i], RTOL, OPACITY_ATOL if i in (2, 4) else 1e-9, f"output {i}")
     (og[0] * gC.cuda()).sum().backward(retain_graph=True)
     assert_close(fg.grad, g1, RTOL, grad_atol(g1, 1e-5))
     fg.grad = None
