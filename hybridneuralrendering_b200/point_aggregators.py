@@ -126,7 +126,9 @@ class PointAggregator(nn.Module):
                   self.color_final_block):
             _init_seq(m)
         self.shading_patch_size = 1
-        self.mlp_engine = "simt"          # "simt" (exact fp32) | "tc" (tcgen05 3xTF32, forward/inference)
+        # per-neighbour MLP engine for no-grad forwards: "tc" = fused tcgen05 3xTF32 kernel (mlp_tc.cu),
+        # "simt" = exact-fp32 layer kernels.  Forwards that record a graph always use the layer kernels.
+        self.mlp_engine = "tc"
 
     @staticmethod
     def _check_supported(opt):
@@ -196,15 +198,25 @@ class PointAggregator(nn.Module):
         if Nv == 0:
             return decoded, valid.bool(), weight, confc
         b1, b3 = self.block1, self.block3
-        with ops.tag("gather"):
-            X0, E = ops.NbrFeaturesFn.apply(emb, color, dirs, xyz, xyz_pers, pidx, mask, vlist, loc_w, loc_pers, raydirs, cam)
-        with ops.tag("nbr_mlp"):
-            h = ops.linear([X0], b1[0].weight, b1[0].bias, ACT_LRELU)
-            h = ops.linear([h], b1[2].weight, b1[2].bias, ACT_LRELU)
-            h = ops.linear([h, E], b3[0].weight, b3[0].bias, ACT_LRELU)
-            h = ops.linear([h], b3[2].weight, b3[2].bias, ACT_LRELU)
-        with ops.tag("ksum"):
-            sigma, X5 = ops.AlphaKSumFn.apply(h, confc, self.alpha_branch[0].weight, self.alpha_branch[0].bias, weight, vlist, raydirs, cam)
+        use_tc = self.mlp_engine == "tc" and not torch.is_grad_enabled() and K == 8 and mask is None
+        if self.mlp_engine == "tc" and torch.is_grad_enabled():
+            use_tc = False            # training keeps the exact-fp32 layers (their backward needs the saved activations)
+        if use_tc:
+            from . import mlp_tc
+            wpack, bias = self._packed_weights()
+            with ops.tag("nbr_mlp"):
+                sigma, X5 = mlp_tc.forward(tables, pidx, vlist, loc_w, loc_pers, raydirs, cam, weight, confc, wpack, bias,
+                                           self.alpha_branch[0].weight, self.alpha_branch[0].bias)
+        else:
+            with ops.tag("gather"):
+                X0, E = ops.NbrFeaturesFn.apply(emb, color, dirs, xyz, xyz_pers, pidx, mask, vlist, loc_w, loc_pers, raydirs, cam)
+            with ops.tag("nbr_mlp"):
+                h = ops.linear([X0], b1[0].weight, b1[0].bias, ACT_LRELU)
+                h = ops.linear([h], b1[2].weight, b1[2].bias, ACT_LRELU)
+                h = ops.linear([h, E], b3[0].weight, b3[0].bias, ACT_LRELU)
+                h = ops.linear([h], b3[2].weight, b3[2].bias, ACT_LRELU)
+            with ops.tag("ksum"):
+                sigma, X5 = ops.AlphaKSumFn.apply(h, confc, self.alpha_branch[0].weight, self.alpha_branch[0].bias, weight, vlist, raydirs, cam)
         cf = self.color_feature_branch
         with ops.tag("sample_mlp"):
             g = ops.linear([X5], cf[0].weight, cf[0].bias, ACT_LRELU)
@@ -235,6 +247,17 @@ class PointAggregator(nn.Module):
         decoded = decoded.index_copy(0, vlist.long(), torch.cat([sigma, rgb], dim=-1))
         self._last = (pidx, mask, vlist)
         return decoded, valid.bool(), weight, confc
+
+    def _packed_weights(self):
+        """TF32 hi/lo images of block1/block3 for the tensor-core kernel, re-packed when a weight changes"""
+        ps = [self.block1[0].weight, self.block1[2].weight, self.block3[0].weight, self.block3[2].weight,
+              self.block1[0].bias, self.block1[2].bias, self.block3[0].bias, self.block3[2].bias]
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if getattr(self, "_pack_key", None) != key:
+            from . import mlp_tc
+            self._pack = mlp_tc.pack_mlp(self.block1, self.block3)
+            self._pack_key = key
+        return self._pack
 
     def last_valid_neighbours(self) -> int:
         """number of valid (sample, neighbour) pairs of the last call (profiling only; syncs)"""
