@@ -1,0 +1,263 @@
+// Dense layer on the 5th-gen tensor cores with fp32 accuracy (3xTF32), for the per-sample MLPs of the
+// aggregator: colour-feature branch 280->128->128->128, blend-weight net 176->64->64->64(->1) batched over
+// the V reference views, mix-up 90->45->45->45, colour head (reference layers:
+// models/aggregators/point_aggregators.py:556-683, used at :1028-1037, :1188-1217, :1285-1334).
+//
+//   Y[m, n] = act( sum_k concat(A0,A1,A2)[m,k] * W[n,k] + b[n] ) (+ res[m,n])
+//
+// Same machinery as mlp_tc.cu (tcgen05.mma kind::tf32 x3, TMEM accumulators, cp.async.bulk weight ring,
+// mbarrier pipelines) but one layer per launch with global-memory operands:
+//   * persistent CTA per SM over 128-row tiles; N padded to a multiple of 16 (<= 256);
+//   * 8 converter warps in two groups (alternating super-chunks of 4 K-chunks, 8 loads in flight per
+//     thread) read fp32 rows, split them into TF32 hi/lo and store the canonical UMMA operand layout;
+//   * the TMEM accumulator is double buffered (2 x N columns): 4 epilogue warps drain tile t (bias,
+//     activation, residual, store) while the MMA warp already accumulates tile t+1;
+//   * weights come pre-split / pre-tiled from the host (linear_tc.py), one bulk copy per K-chunk.
+#include "common.cuh"
+#include "hnr.h"
+#include "tc_common.cuh"
+
+namespace {
+using namespace tc;
+
+constexpr int TM = 128;
+constexpr int KC = 8;
+constexpr int NSW = 8;                       // weight ring depth
+constexpr int NSA = 8;                       // activation ring depth
+constexpr int A_PART = TM * KC * 4;          // 4096
+constexpr int A_STAGE = 2 * A_PART;          // hi + lo
+constexpr int W_STAGE_MAX = 2 * 256 * KC * 4;   // 16384
+constexpr int NCONV_WARPS = 8, NEPI_WARPS = 4;
+constexpr int WARP_MMA = NCONV_WARPS + NEPI_WARPS, WARP_TMA = WARP_MMA + 1;
+constexpr int NTHREADS = (WARP_TMA + 1) * 32;   // 448
+constexpr int SUPER = 4;                     // K-chunks per super-chunk
+
+constexpr int OFF_W = 0;
+constexpr int OFF_A = OFF_W + NSW * W_STAGE_MAX;        // 131072
+constexpr int OFF_BIAS = OFF_A + NSA * A_STAGE;         // +65536 = 196608
+constexpr int OFF_BAR = OFF_BIAS + 256 * 4;
+constexpr int SMEM_BYTES = OFF_BAR + 512;
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+constexpr uint32_t A_LBO = (TM / 8) * 128, SBO = 128;
+
+struct Src {
+    const float* p[3];
+    int ld[3];
+    int k[3];
+    int64_t mod[3];
+};
+
+struct LArgs {
+    Src A;
+    const uint8_t* wpack;
+    const float* bias;
+    const float* res;
+    float* Y;
+    int64_t M;
+    int ldres, ldy;
+    int K, Kp, N, Npad, act;
+};
+
+__device__ __forceinline__ float src_load(const Src& a, int64_t m, int k) {
+    int s = 0;
+    if (k >= a.k[0]) { k -= a.k[0]; s = 1; if (k >= a.k[1]) { k -= a.k[1]; s = 2; } }
+    if (a.mod[s] > 0) m %= a.mod[s];
+    return __ldg(a.p[s] + m * a.ld[s] + k);
+}
+
+// four consecutive K elements of row m starting at k0 (zero beyond K / M)
+__device__ __forceinline__ float4 load4(const LArgs& L, int64_t m, int k0) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (m >= L.M || k0 >= L.K) return v;
+    // fast path: the group lies inside one source and is 16-byte aligned
+    int s = 0, kk = k0;
+    if (kk >= L.A.k[0]) { kk -= L.A.k[0]; s = 1; if (kk >= L.A.k[1]) { kk -= L.A.k[1]; s = 2; } }
+    if (kk + 4 <= L.A.k[s]) {
+        int64_t mm = L.A.mod[s] > 0 ? m % L.A.mod[s] : m;
+        const float* p = L.A.p[s] + mm * L.A.ld[s] + kk;
+        if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) return __ldg(reinterpret_cast<const float4*>(p));
+        v.x = __ldg(p); v.y = __ldg(p + 1); v.z = __ldg(p + 2); v.w = __ldg(p + 3);
+        return v;
+    }
+    v.x = src_load(L.A, m, k0);
+    if (k0 + 1 < L.K) v.y = src_load(L.A, m, k0 + 1);
+    if (k0 + 2 < L.K) v.z = src_load(L.A, m, k0 + 2);
+    if (k0 + 3 < L.K) v.w = src_load(L.A, m, k0 + 3);
+    return v;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(LArgs L) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+    const uint32_t bar_fullW = smem_u32(bars), bar_emptyW = smem_u32(bars + NSW);
+    const uint32_t bar_fullA = smem_u32(bars + 2 * NSW), bar_emptyA = smem_u32(bars + 2 * NSW + NSA);
+    const uint32_t bar_accF = smem_u32(bars + 2 * NSW + 2 * NSA), bar_accE = bar_accF + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSW + 2 * NSA + 4);
+    float* bias_s = reinterpret_cast<float*>(smem + OFF_BIAS);
+
+    const int64_t ntiles = (L.M + TM - 1) / TM;
+    const int nchunk = L.Kp / KC;
+    const uint32_t w_part = (uint32_t)L.Npad * KC * 4, w_stage = 2 * w_part;
+    const uint32_t W_LBO = (uint32_t)(L.Npad / 8) * 128;
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < 2u * (uint32_t)L.Npad) tmem_cols <<= 1;
+
+    if (tid == 0) {
+        for (int s = 0; s < NSW; ++s) { mbar_init(bar_fullW + 8 * s, 1); mbar_init(bar_emptyW + 8 * s, 1); }
+        for (int s = 0; s < NSA; ++s) { mbar_init(bar_fullA + 8 * s, 4); mbar_init(bar_emptyA + 8 * s, 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(bar_accF + 8 * b, 1); mbar_init(bar_accE + 8 * b, NEPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == WARP_MMA) tmem_alloc(smem_u32(tmem_slot), tmem_cols);
+    for (int i = tid; i < 256; i += NTHREADS) bias_s[i] = (L.bias && i < L.N) ? L.bias[i] : 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == WARP_TMA) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+                for (int c = 0; c < nchunk; ++c, ++it) {
+                    const uint32_t s = it % NSW, ph = (it / NSW) & 1;
+                    mbar_wait(bar_emptyW + 8 * s, ph ^ 1);
+                    mbar_arrive_expect_tx(bar_fullW + 8 * s, w_stage);
+                    bulk_g2s(smem_u32(smem + OFF_W + s * W_STAGE_MAX), L.wpack + (size_t)c * w_stage, w_stage, bar_fullW + 8 * s);
+                }
+        }
+    } else if (warp == WARP_MMA) {
+        if (lane == 0) {
+            const uint32_t idesc = idesc_tf32(TM, L.Npad);
+            uint32_t it = 0, tcount = 0;
+            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+                const uint32_t b = tcount & 1, bph = (tcount >> 1) & 1;
+                mbar_wait(bar_accE + 8 * b, bph ^ 1);            // epilogue drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + b * (uint32_t)L.Npad;
+                for (int c = 0; c < nchunk; ++c, ++it) {
+                    const uint32_t sw = it % NSW, pw = (it / NSW) & 1, sa = it % NSA, pa = (it / NSA) & 1;
+                    mbar_wait(bar_fullW + 8 * sw, pw);
+                    mbar_wait(bar_fullA + 8 * sa, pa);
+                    tc_fence_after();
+                    const uint32_t ws = smem_u32(smem + OFF_W + sw * W_STAGE_MAX), as = smem_u32(smem + OFF_A + sa * A_STAGE);
+                    const uint64_t w_hi = umma_desc(ws, W_LBO, SBO), w_lo = umma_desc(ws + w_part, W_LBO, SBO);
+                    const uint64_t a_hi = umma_desc(as, A_LBO, SBO), a_lo = umma_desc(as + A_PART, A_LBO, SBO);
+                    tc_mma_tf32(d_tmem, a_hi, w_hi, idesc, c > 0 ? 1u : 0u);
+                    tc_mma_tf32(d_tmem, a_lo, w_hi, idesc, 1u);
+                    tc_mma_tf32(d_tmem, a_hi, w_lo, idesc, 1u);
+                    tc_commit(bar_emptyW + 8 * sw);
+                    tc_commit(bar_emptyA + 8 * sa);
+                }
+                tc_commit(bar_accF + 8 * b);
+            }
+        }
+    } else if (warp < NCONV_WARPS) {
+        // ---------------- converters: fp32 rows -> TF32 hi/lo operand chunks ----------------
+        const int grp = warp >> 2, r = (warp & 3) * 32 + lane;
+        uint32_t tile_it = 0;                                      // chunk counter at the start of the tile
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tile_it += nchunk) {
+            const int64_t m = tile * TM + r;
+            for (int c0 = grp * SUPER; c0 < nchunk; c0 += 2 * SUPER) {
+                float4 v[SUPER][2];
+#pragma unroll
+                for (int u = 0; u < SUPER; ++u) {
+                    if (c0 + u < nchunk) {
+                        v[u][0] = load4(L, m, (c0 + u) * KC);
+                        v[u][1] = load4(L, m, (c0 + u) * KC + 4);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < SUPER; ++u) {
+                    if (c0 + u < nchunk) {
+                        const uint32_t it = tile_it + c0 + u, s = it % NSA, ph = (it / NSA) & 1;
+                        mbar_wait(bar_emptyA + 8 * s, ph ^ 1);
+                        uint8_t* st = smem + OFF_A + s * A_STAGE;
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            float4 hi, lo;
+                            split4(v[u][h], hi, lo);
+                            *reinterpret_cast<float4*>(st + h * A_LBO + r * 16) = hi;
+                            *reinterpret_cast<float4*>(st + A_PART + h * A_LBO + r * 16) = lo;
+                        }
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_fullA + 8 * s);
+                    }
+                }
+            }
+        }
+    } else {
+        // ---------------- epilogue: TMEM -> bias / activation / residual -> global ----------------
+        const int q = warp & 3;                                    // TMEM lane quarter this warp may access
+        const int erow = q * 32 + lane;
+        uint32_t tcount = 0;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+            const uint32_t b = tcount & 1, bph = (tcount >> 1) & 1;
+            mbar_wait(bar_accF + 8 * b, bph);
+            tc_fence_after();
+            const int64_t m = tile * TM + erow;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + b * (uint32_t)L.Npad;
+            for (int n0 = 0; n0 < L.Npad; n0 += 16) {
+                float v[16];
+                tmem_ld16(taddr + n0, v);
+                if (m < L.M) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int n = n0 + i;
+                        if (n < L.N) {
+                            float y = apply_act(v[i] + bias_s[n], L.act);
+                            if (L.res) y += L.res[m * L.ldres + n];
+                            v[i] = y;
+                        }
+                    }
+                    float* o = L.Y + m * L.ldy + n0;
+                    if (n0 + 16 <= L.N && (L.ldy & 3) == 0 && (reinterpret_cast<uintptr_t>(L.Y) & 15) == 0) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(o)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (n0 + i < L.N) o[i] = v[i];
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_accE + 8 * b);
+        }
+    }
+    __syncthreads();
+    if (warp == WARP_MMA) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+}  // namespace
+
+extern "C" int64_t hnr_linear_tc_packed_bytes(int64_t Npad, int64_t Kp) { return (Kp / KC) * 2 * Npad * KC * 4; }
+
+// Y = act(concat(A) W^T + b) (+res) on tensor cores.  wpack: image of W zero-padded to (Npad, Kp), Npad % 16 == 0,
+// Npad <= 256, Kp % 8 == 0 (layout: linear_tc.py).  Same argument meaning as hnr_linear_fwd.
+extern "C" int hnr_linear_tc_fwd(const float* const* a_ptr, const int64_t* a_ld, const int64_t* a_k, const int64_t* a_mod, const void* wpack,
+                                 int64_t Npad, int64_t Kp, const float* bias, const float* res, int64_t ldres, float* Y, int64_t ldy,
+                                 int64_t M, int64_t N, int64_t K, int act, void* stream) {
+    if (M == 0) return HNR_OK;
+    HNR_CHECK_ARG(Npad % 16 == 0 && Npad >= 16 && Npad <= 256 && N <= Npad, "linear_tc_fwd: Npad must be a multiple of 16 in [16,256]");
+    HNR_CHECK_ARG(Kp % KC == 0 && K <= Kp && K > 0, "linear_tc_fwd: Kp must be a multiple of 8 and >= K");
+    HNR_CHECK_ARG(!(res && act != HNR_ACT_NONE), "linear_tc_fwd: residual only with act=none");
+    HNR_CHECK_ARG(a_k[0] + a_k[1] + a_k[2] == K, "linear_tc_fwd: concat widths must sum to K");
+    LArgs L{};
+    for (int i = 0; i < 3; ++i) { L.A.p[i] = a_ptr[i]; L.A.ld[i] = (int)a_ld[i]; L.A.k[i] = (int)a_k[i]; L.A.mod[i] = a_mod ? a_mod[i] : 0; }
+    L.wpack = (const uint8_t*)wpack; L.bias = bias; L.res = res; L.Y = Y; L.M = M; L.ldres = (int)ldres; L.ldy = (int)ldy;
+    L.K = (int)K; L.Kp = (int)Kp; L.N = (int)N; L.Npad = (int)Npad; L.act = act;
+    static bool configured = false;
+    if (!configured) {
+        HNR_CUDA(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        configured = true;
+    }
+    const int64_t ntiles = hnr_cdiv(M, TM);
+    const int grid = (int)(ntiles < HNR_NUM_SMS ? ntiles : HNR_NUM_SMS);
+    linear_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(L);
+    HNR_CHECK_LAUNCH("linear_tc_fwd");
+    return HNR_OK;
+}

@@ -23,8 +23,10 @@
 // :1002-1036 and models/helpers/networks.py:175-189 of the reference.
 #include "common.cuh"
 #include "hnr.h"
+#include "tc_common.cuh"
 
 namespace {
+using namespace tc;
 
 constexpr int TM = 128;                 // rows (neighbours) per tile
 constexpr int HID = 256;                // layer width == UMMA N
@@ -62,77 +64,6 @@ struct TcParams {
     int nlayer;
 };
 
-// ------------------------------------------------------------------------------------------------
-// PTX wrappers
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-                 "r"(bytes), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-    uint32_t* r = reinterpret_cast<uint32_t*>(v);
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void named_bar_workers() { asm volatile("bar.sync 1, %0;" ::"n"(NWORKER) : "memory"); }
-
-// UMMA shared-memory descriptor, canonical K-major layout without swizzle: core matrix = 8 rows x 16 B
-// (128 contiguous bytes); LBO = byte distance between core matrices along K, SBO = along M/N.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)(lbo >> 4) << 16;
-    d |= (uint64_t)(sbo >> 4) << 32;
-    d |= 1ull << 46;       // descriptor version (Blackwell)
-    return d;              // base_offset = 0, lbo_mode = 0, layout_type = SWIZZLE_NONE (0)
-}
 // instruction descriptor: D=f32, A=B=tf32, both K-major, M=128, N=256
 constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(HID >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 constexpr uint32_t A_LBO = (TM / 8) * 128, W_LBO = (HID / 8) * 128, SBO = 128;
@@ -299,7 +230,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_kernel(TcArgs A, TcParams 
                     o[1] = make_float4(ry - vy, rz - vz, rx * vx + ry * vy + rz * vz, 0.f);
                     wc_s[r] = live ? A.weight[s * A.K + k] * (A.confc ? A.confc[s * A.K + k] : 1.f) : 0.f;
                 }
-                named_bar_workers();
+                named_bar<NWORKER>();
             }
             for (int l = 0; l < nlayer; ++l) {
                 // ---- feed the layer: one (hi, lo) operand chunk per stage ----
@@ -406,7 +337,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_kernel(TcArgs A, TcParams 
                     if (last) araw_s[ehalf * TM + erow] = dot;
                 }
                 tc_fence_before();
-                named_bar_workers();           // every row of the new activation is in place / TMEM drained
+                named_bar<NWORKER>();           // every row of the new activation is in place / TMEM drained
             }
             if (!TEST) {
                 // ---- weighted K-sum over each sample's 8 neighbour rows + density head + view encoding ----
@@ -443,7 +374,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_kernel(TcArgs A, TcParams 
                         A.X5[v * X5_W + HID + 3 * NF_VIEW + q] = b;
                     }
                 }
-                named_bar_workers();           // act / wc / araw are reused by the next tile's gather
+                named_bar<NWORKER>();           // act / wc / araw are reused by the next tile's gather
             }
             (void)view;
         }

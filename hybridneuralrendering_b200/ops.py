@@ -84,6 +84,39 @@ def make_cam(campos: torch.Tensor, camrot: torch.Tensor, rw2c: Optional[torch.Te
 # --------------------------------------------------------------------------------------------
 # dense layer
 # --------------------------------------------------------------------------------------------
+# forward engine of ops.linear: "tc" = tcgen05 3xTF32 kernel (csrc/linear_tc.cu) for layers with >= 16 outputs,
+# "simt" = exact-fp32 FFMA kernel (csrc/linear_simt.cu).  Backward always uses the exact-fp32 kernels.
+LINEAR_ENGINE = "tc"
+_PACK_CACHE = {}
+
+
+def pack_linear(W: torch.Tensor):
+    """(N,K) fp32 -> (uint8 image, Npad, Kp): zero-pad to Npad % 16 == 0, Kp % 8 == 0, split into TF32 hi (13 low
+    mantissa bits cleared) and lo = w - hi, tile per 8-column chunk as [hi | lo], each part
+    [k half (2)][row group (Npad/8)][row (8)][4 floats] -- the canonical no-swizzle K-major UMMA layout."""
+    W = W.detach().float()
+    N, K = W.shape
+    Npad, Kp = (N + 15) // 16 * 16, (K + 7) // 8 * 8
+    Wp = torch.zeros((Npad, Kp), device=W.device, dtype=torch.float32)
+    Wp[:N, :K] = W
+    hi = (Wp.view(torch.int32) & -8192).view(torch.float32)
+    lo = Wp - hi
+    tile = lambda x: x.view(Npad // 8, 8, Kp // 8, 2, 4).permute(2, 3, 0, 1, 4)
+    img = torch.stack([tile(hi), tile(lo)], dim=1).contiguous().view(torch.uint8).reshape(-1)
+    assert img.numel() == lib().hnr_linear_tc_packed_bytes(Npad, Kp)
+    return img, Npad, Kp
+
+
+def _packed_linear(W: torch.Tensor):
+    key = (W.data_ptr(), tuple(W.shape))
+    ent = _PACK_CACHE.get(key)
+    if ent is None or ent[0] != W._version:
+        if len(_PACK_CACHE) > 256:
+            _PACK_CACHE.clear()
+        ent = (W._version, pack_linear(W))
+        _PACK_CACHE[key] = ent
+    return ent[1]
+
 class LinearFn(torch.autograd.Function):
     """y = act(concat(srcs) W^T + b [+ res]).  `mods[i] > 0`: source i has mods[i] rows reused by
     every block of mods[i] output rows."""
@@ -103,9 +136,16 @@ class LinearFn(torch.autograd.Function):
         modl = list(mods) + [0] * (3 - len(mods))
         resv = _rows2d(res) if res is not None else None
         bc = _f32c(b) if b is not None else None
-        with _launch():
-            check(lib().hnr_linear_fwd(ptr_array(padded), i64_array(lds), i64_array(ks), i64_array(modl), ptr(W), ptr(bc), ptr(resv),
-                                       resv.stride(0) if resv is not None else 0, ptr(Y), N, M, N, K, act, stream()), "linear_fwd")
+        if LINEAR_ENGINE == "tc" and N >= 16 and M >= 128:
+            wpack, Npad, Kp = _packed_linear(W)
+            with _launch():
+                check(lib().hnr_linear_tc_fwd(ptr_array(padded), i64_array(lds), i64_array(ks), i64_array(modl), ptr(wpack), Npad, Kp,
+                                              ptr(bc), ptr(resv), resv.stride(0) if resv is not None else 0, ptr(Y), N, M, N, K, act,
+                                              stream()), "linear_tc_fwd")
+        else:
+            with _launch():
+                check(lib().hnr_linear_fwd(ptr_array(padded), i64_array(lds), i64_array(ks), i64_array(modl), ptr(W), ptr(bc), ptr(resv),
+                                           resv.stride(0) if resv is not None else 0, ptr(Y), N, M, N, K, act, stream()), "linear_fwd")
         ctx.act, ctx.M, ctx.mods, ctx.nsrc, ctx.has_res, ctx.has_b = act, M, modl, len(srcs), res is not None, b is not None
         ctx.save_for_backward(W, Y, *srcs)
         return Y

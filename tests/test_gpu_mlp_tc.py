@@ -59,3 +59,41 @@ def test_fused_tc_path_matches_exact_fp32_path(R, SR, empty):
         dec_b, valid_b, w_b, cc_b = agg.forward_fused(*args, **kw)
     assert torch.equal(valid_a, valid_b)
     assert_close(dec_b, dec_a, 1e-4, 1e-6)
+
+
+@pytest.mark.parametrize("M,N,ks,act", [(128, 16, (8,), 0), (1000, 128, (280,), 1), (5000, 64, (45, 128, 3), 1), (777, 45, (45, 45), 1),
+                                         (130, 45, (45,), 0), (4096, 256, (256, 7), 1), (300, 128, (128,), 2)])
+def test_linear_tc_matches_fp64(M, N, ks, act):
+    """generic tensor-core layer (concat sources, padded N/K, bias, activation, residual) vs fp64 torch"""
+    from hybridneuralrendering_b200 import ops
+    rng = np.random.default_rng(M + N)
+    K = sum(ks)
+    srcs = [T(rng.standard_normal((M, k)).astype(np.float32)) for k in ks]
+    W, b = T((rng.standard_normal((N, K)) * 0.1).astype(np.float32)), T(rng.standard_normal(N).astype(np.float32))
+    res = T(rng.standard_normal((M, N)).astype(np.float32)) if act == 0 else None
+    y = torch.nn.functional.linear(torch.cat(srcs, 1).double(), W.double(), b.double())
+    y = [y, torch.nn.functional.leaky_relu(y, 0.01), torch.sigmoid(y)][act]
+    if res is not None:
+        y = y + res.double()
+    assert ops.LINEAR_ENGINE == "tc"
+    with torch.no_grad():
+        out = ops.linear([s.cuda() for s in srcs], W.cuda(), b.cuda(), act, res=res.cuda() if res is not None else None)
+    assert_close(out, y, 1e-5, 2e-5)
+
+
+def test_linear_tc_shared_row_block_and_slices():
+    from hybridneuralrendering_b200 import ops
+    rng = np.random.default_rng(0)
+    V, Nv = 4, 1000
+    g = T(rng.standard_normal((Nv, 128)).astype(np.float32))
+    a = T(rng.standard_normal((V * Nv, 45)).astype(np.float32))
+    d = T(rng.standard_normal((V * Nv, 3)).astype(np.float32))
+    W, b = T((rng.standard_normal((64, 176)) * 0.1).astype(np.float32)), T(rng.standard_normal(64).astype(np.float32))
+    ref = torch.nn.functional.leaky_relu(torch.nn.functional.linear(torch.cat([a, g.repeat(V, 1), d], 1).double(), W.double(), b.double()), 0.01)
+    with torch.no_grad():
+        y = ops.linear([a.cuda(), g.cuda(), d.cuda()], W.cuda(), b.cuda(), 1, mods=(0, Nv, 0), M=V * Nv)
+        gc = g.cuda()
+        W2 = T((rng.standard_normal((45, 90)) * 0.1).astype(np.float32)).cuda()
+        y2 = ops.linear([gc[:, :45], gc[:, 45:90]], W2, None, 0, res=gc[:, :45])
+    assert_close(y, ref, 1e-5, 2e-5)
+    assert_close(y2, g[:, :90].double() @ W2.cpu().double().t() + g[:, :45].double(), 1e-5, 2e-5)
