@@ -26,7 +26,7 @@ sys.path.insert(0, ROOT)
 H = W = 800
 N_POINTS = 1_000_000
 V = 4
-CHUNK = 32768
+CHUNK = None          # whole frame per query (one host readback per frame)
 WORKLOAD = "NeRF-synthetic lego-shaped full-frame render 800x800, synthetic 1M neural points (voxel query + aggregation + compositing)"
 CPU_SAMPLE_RAYS = 1024
 
@@ -256,7 +256,7 @@ def main():
     line = {"metric": "render Mpix/s", "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": t_res / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": H * W, "chunk_rays": CHUNK, "use_nearest": V, "SR": int(opt.SR), "K": int(opt.K),
+            "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": H * W, "chunk_rays": CHUNK or H * W, "valid_samples_per_pass": net.aggregator.max_valid_chunk, "use_nearest": V, "SR": int(opt.SR), "K": int(opt.K),
                        "l2": "flushed between steps (256 MB write)", "mlp_engine": net.aggregator.mlp_engine,
                        "parallelism": f"{world} independent frame(s), one per GPU"},
             "e2e": {"value": e2e, "unit": "Mpix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

@@ -8,8 +8,8 @@
 // Same machinery as mlp_tc.cu (tcgen05.mma kind::tf32 x3, TMEM accumulators, cp.async.bulk weight ring,
 // mbarrier pipelines) but one layer per launch with global-memory operands:
 //   * persistent CTA per SM over 128-row tiles; N padded to a multiple of 16 (<= 256);
-//   * 8 converter warps in two groups (alternating super-chunks of 4 K-chunks, 8 loads in flight per
-//     thread) read fp32 rows, split them into TF32 hi/lo and store the canonical UMMA operand layout;
+//   * 8 converter warps (thread = row x K-half) read fp32 rows one super-chunk (4 K-chunks) ahead, split them
+//     into TF32 hi/lo and store the canonical UMMA operand layout;
 //   * the TMEM accumulator is double buffered (2 x N columns): 4 epilogue warps drain tile t (bias,
 //     activation, residual, store) while the MMA warp already accumulates tile t+1;
 //   * weights come pre-split / pre-tiled from the host (linear_tc.py), one bulk copy per K-chunk.
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(LArgs L) {
 
     if (tid == 0) {
         for (int s = 0; s < NSW; ++s) { mbar_init(bar_fullW + 8 * s, 1); mbar_init(bar_emptyW + 8 * s, 1); }
-        for (int s = 0; s < NSA; ++s) { mbar_init(bar_fullA + 8 * s, 4); mbar_init(bar_emptyA + 8 * s, 1); }
+        for (int s = 0; s < NSA; ++s) { mbar_init(bar_fullA + 8 * s, NCONV_WARPS); mbar_init(bar_emptyA + 8 * s, 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(bar_accF + 8 * b, 1); mbar_init(bar_accE + 8 * b, NEPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -155,38 +155,45 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(LArgs L) {
         }
     } else if (warp < NCONV_WARPS) {
         // ---------------- converters: fp32 rows -> TF32 hi/lo operand chunks ----------------
-        const int grp = warp >> 2, r = (warp & 3) * 32 + lane;
-        uint32_t tile_it = 0;                                      // chunk counter at the start of the tile
-        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tile_it += nchunk) {
+        // thread = (row r, K half h); EVERY converter thread visits EVERY ring slot use in order (a waiter that
+        // skipped a phase of an mbarrier would alias its parity).  Global loads run one super-chunk (4 K-chunks)
+        // ahead of the conversion, also across tile boundaries.
+        const int r = tid & (TM - 1), h = tid >> 7;
+        const int nsc = (nchunk + SUPER - 1) / SUPER;
+        const int64_t my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+        const int64_t total = my_tiles * nsc;
+        auto load_super = [&](int64_t q, float4 (&dst)[SUPER]) {
+            const int64_t tile = blockIdx.x + (q / nsc) * gridDim.x;
+            const int c0 = (int)(q % nsc) * SUPER;
             const int64_t m = tile * TM + r;
-            for (int c0 = grp * SUPER; c0 < nchunk; c0 += 2 * SUPER) {
-                float4 v[SUPER][2];
 #pragma unroll
-                for (int u = 0; u < SUPER; ++u) {
-                    if (c0 + u < nchunk) {
-                        v[u][0] = load4(L, m, (c0 + u) * KC);
-                        v[u][1] = load4(L, m, (c0 + u) * KC + 4);
-                    }
-                }
+            for (int u = 0; u < SUPER; ++u)
+                dst[u] = (c0 + u < nchunk) ? load4(L, m, (c0 + u) * KC + h * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        float4 cur[SUPER], nxt[SUPER];
+        if (total > 0) load_super(0, cur);
+        uint32_t it = 0;
+        for (int64_t q = 0; q < total; ++q) {
+            if (q + 1 < total) load_super(q + 1, nxt);
+            const int c0 = (int)(q % nsc) * SUPER;
 #pragma unroll
-                for (int u = 0; u < SUPER; ++u) {
-                    if (c0 + u < nchunk) {
-                        const uint32_t it = tile_it + c0 + u, s = it % NSA, ph = (it / NSA) & 1;
-                        mbar_wait(bar_emptyA + 8 * s, ph ^ 1);
-                        uint8_t* st = smem + OFF_A + s * A_STAGE;
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            float4 hi, lo;
-                            split4(v[u][h], hi, lo);
-                            *reinterpret_cast<float4*>(st + h * A_LBO + r * 16) = hi;
-                            *reinterpret_cast<float4*>(st + A_PART + h * A_LBO + r * 16) = lo;
-                        }
-                        fence_proxy_async();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(bar_fullA + 8 * s);
-                    }
+            for (int u = 0; u < SUPER; ++u) {
+                if (c0 + u < nchunk) {
+                    const uint32_t s = it % NSA, ph = (it / NSA) & 1;
+                    ++it;
+                    mbar_wait(bar_emptyA + 8 * s, ph ^ 1);
+                    uint8_t* st = smem + OFF_A + s * A_STAGE;
+                    float4 hi, lo;
+                    split4(cur[u], hi, lo);
+                    *reinterpret_cast<float4*>(st + h * A_LBO + r * 16) = hi;
+                    *reinterpret_cast<float4*>(st + A_PART + h * A_LBO + r * 16) = lo;
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_fullA + 8 * s);
                 }
             }
+#pragma unroll
+            for (int u = 0; u < SUPER; ++u) cur[u] = nxt[u];
         }
     } else {
         // ---------------- epilogue: TMEM -> bias / activation / residual -> global ----------------

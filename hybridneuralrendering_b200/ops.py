@@ -86,8 +86,8 @@ def make_cam(campos: torch.Tensor, camrot: torch.Tensor, rw2c: Optional[torch.Te
 # --------------------------------------------------------------------------------------------
 # forward engine of ops.linear: "tc" = tcgen05 3xTF32 kernel (csrc/linear_tc.cu) for layers with >= 16 outputs,
 # "simt" = exact-fp32 FFMA kernel (csrc/linear_simt.cu).  Backward always uses the exact-fp32 kernels.
-LINEAR_ENGINE = "tc"
-_PACK_CACHE = {}
+import os as _os
+LINEAR_ENGINE = _os.environ.get("HNR_LINEAR_ENGINE", "tc")
 
 
 def pack_linear(W: torch.Tensor):
@@ -108,14 +108,17 @@ def pack_linear(W: torch.Tensor):
 
 
 def _packed_linear(W: torch.Tensor):
-    key = (W.data_ptr(), tuple(W.shape))
-    ent = _PACK_CACHE.get(key)
+    """packed image cached ON the weight tensor object (a cache keyed by data_ptr would hand a stale image to a
+    new tensor that the caching allocator placed at a recycled address)"""
+    ent = getattr(W, "_hnr_pack", None)
     if ent is None or ent[0] != W._version:
-        if len(_PACK_CACHE) > 256:
-            _PACK_CACHE.clear()
         ent = (W._version, pack_linear(W))
-        _PACK_CACHE[key] = ent
+        try:
+            W._hnr_pack = ent
+        except Exception:
+            pass
     return ent[1]
+
 
 class LinearFn(torch.autograd.Function):
     """y = act(concat(srcs) W^T + b [+ res]).  `mods[i] > 0`: source i has mods[i] rows reused by

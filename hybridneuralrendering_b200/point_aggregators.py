@@ -129,6 +129,7 @@ class PointAggregator(nn.Module):
         # per-neighbour MLP engine for no-grad forwards: "tc" = fused tcgen05 3xTF32 kernel (mlp_tc.cu),
         # "simt" = exact-fp32 layer kernels.  Forwards that record a graph always use the layer kernels.
         self.mlp_engine = "tc"
+        self.max_valid_chunk = 262144        # valid samples decoded per pass in no-grad mode (bounds activation memory)
 
     @staticmethod
     def _check_supported(opt):
@@ -186,7 +187,6 @@ class PointAggregator(nn.Module):
         """tables = (xyz (N,3), xyz_pers|None, emb (N,32), color (N,3), dir (N,3), conf (N,)).
         pidx (S,K) i32; mask (S,K) u8|None; loc_* / raydirs (S,3).  Returns decoded (S,4), valid (S) bool,
         weight (S,K), conf_coefficient (S,K)."""
-        opt = self.opt
         xyz, xyz_pers, emb, color, dirs, conf = tables
         S, K = pidx.shape
         with ops.tag("gather"):
@@ -195,12 +195,30 @@ class PointAggregator(nn.Module):
             vlist = torch.nonzero(valid, as_tuple=False).view(-1).to(torch.int32)        # sync (drop-in path only)
         Nv = vlist.shape[0]
         decoded = torch.zeros((S, 4), device=pidx.device, dtype=torch.float32)
+        self._last = (pidx, mask, vlist)
         if Nv == 0:
             return decoded, valid.bool(), weight, confc
+        args = (tables, pidx, mask, loc_pers, loc_w, raydirs, cam, R, SR, levels, xy, delta, weight, confc)
+        if torch.is_grad_enabled() or Nv <= self.max_valid_chunk:
+            decoded = decoded.index_copy(0, vlist.long(), self._decode(vlist, *args))
+        else:
+            # inference over many samples (full frames): bound the activation memory by walking the valid-sample
+            # list in slices; sizes are known on the host, so no synchronisation is involved
+            for v0 in range(0, Nv, self.max_valid_chunk):
+                part = vlist[v0:v0 + self.max_valid_chunk]
+                decoded.index_copy_(0, part.long(), self._decode(part, *args))
+        return decoded, valid.bool(), weight, confc
+
+    def _decode(self, vlist, tables, pidx, mask, loc_pers, loc_w, raydirs, cam, R, SR, levels, xy, delta, weight, confc):
+        """[sigma, rgb] (len(vlist),4) of the valid samples in `vlist`"""
+        opt = self.opt
+        xyz, xyz_pers, emb, color, dirs, conf = tables
+        S, K = pidx.shape
+        Nv = vlist.shape[0]
         b1, b3 = self.block1, self.block3
+        # per-neighbour MLP engine: the fused tensor-core kernel for no-grad forwards; forwards that record a graph use
+        # the layer kernels (their backward needs the saved activations)
         use_tc = self.mlp_engine == "tc" and not torch.is_grad_enabled() and K == 8 and mask is None
-        if self.mlp_engine == "tc" and torch.is_grad_enabled():
-            use_tc = False            # training keeps the exact-fp32 layers (their backward needs the saved activations)
         if use_tc:
             from . import mlp_tc
             wpack, bias = self._packed_weights()
@@ -244,9 +262,7 @@ class PointAggregator(nn.Module):
             m = ops.linear([m], cm[2].weight, cm[2].bias, ACT_LRELU)
             m = ops.linear([m], cm[4].weight, cm[4].bias, ACT_NONE, res=gi)
             rgb = ops.linear([m, gv], self.color_final_block[0].weight, self.color_final_block[0].bias, ACT_COLOR)
-        decoded = decoded.index_copy(0, vlist.long(), torch.cat([sigma, rgb], dim=-1))
-        self._last = (pidx, mask, vlist)
-        return decoded, valid.bool(), weight, confc
+        return torch.cat([sigma, rgb], dim=-1)
 
     def _packed_weights(self):
         """TF32 hi/lo images of block1/block3 for the tensor-core kernel, re-packed when a weight changes"""

@@ -17,17 +17,23 @@ def stage_times(net, frame, chunk_rays: int) -> Dict[str, float]:
     torch.cuda.synchronize()
     ops.TIMERS = []
     units = {"valid_neighbours": 0, "valid_samples": 0, "kept_rays": 0}
-    raydir = frame["raydir"]
-    R = raydir.shape[1]
-    static = {k: v for k, v in frame.items() if k not in ("raydir", "pixel_idx", "gt_image")}
+    from .renderer import render_rays
     try:
-        with torch.no_grad():
-            for r0 in range(0, R, chunk_rays):
-                net(raydir=raydir[:, r0:min(R, r0 + chunk_rays)], pixel_idx=None, **static)
-                ex = net.last_extras
-                units["valid_samples"] += ex.n_valid
-                units["kept_rays"] += ex.n_rays
-                units["valid_neighbours"] += net.aggregator.last_valid_neighbours() if ex.n_valid else 0
+        orig = net.forward
+
+        def counted(*a, **k):
+            o = orig(*a, **k)
+            ex = net.last_extras
+            units["valid_samples"] += ex.n_valid
+            units["kept_rays"] += ex.n_rays
+            units["valid_neighbours"] += net.aggregator.last_valid_neighbours() if ex.n_valid else 0
+            return o
+
+        net.forward = counted
+        try:
+            render_rays(net, frame, chunk_rays)
+        finally:
+            net.forward = orig
         torch.cuda.synchronize()
         out: Dict[str, float] = {}
         launches: Dict[str, int] = {}

@@ -12,9 +12,11 @@ from typing import Dict, Optional
 import torch
 
 
-def render_rays(net, frame: Dict[str, torch.Tensor], chunk_rays: int = 32768, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+def render_rays(net, frame: Dict[str, torch.Tensor], chunk_rays: Optional[int] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """frame: the reference's frame dict on the device (raydir (1,R,3), campos, camrotc2w, near, far,
-    nearest-view tensors...).  Returns colours (R,3) with bg colour for rays that hit nothing."""
+    nearest-view tensors...).  Returns colours (R,3) with bg colour for rays that hit nothing.
+    chunk_rays=None: as few ray chunks as the query's int32 index space allows (normally ONE per frame, i.e.
+    one host readback per frame; the aggregator bounds activation memory by itself)."""
     raydir = frame["raydir"]
     R = raydir.shape[1]
     dev = raydir.device
@@ -22,6 +24,11 @@ def render_rays(net, frame: Dict[str, torch.Tensor], chunk_rays: int = 32768, ou
     if out is None:
         out = torch.empty((R, 3), device=dev, dtype=torch.float32)
     out[:] = bg.reshape(1, 3).to(out) if bg is not None else 0.0
+    if chunk_rays is None:
+        opt = net.opt
+        cap = (2 ** 31 - 1) // (int(opt.SR) * int(opt.K))
+        n = -(-R // cap)
+        chunk_rays = -(-R // n)
     static = {k: v for k, v in frame.items() if k not in ("raydir", "pixel_idx", "gt_image")}
     with torch.no_grad():
         for r0 in range(0, R, chunk_rays):
