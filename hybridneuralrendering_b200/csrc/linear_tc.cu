@@ -52,6 +52,10 @@ struct LArgs {
     const uint8_t* wpack;
     const float* bias;
     const float* res;
+    const float* head_w;     // optional fused 1-output head: out_head[m] = head_act(sum_n y[m,n] head_w[n] + head_b[0])
+    const float* head_b;
+    float* out_head;
+    int head_act;
     float* Y;
     int64_t M;
     int ldres, ldy;
@@ -155,26 +159,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(LArgs L) {
         }
     } else if (warp < NCONV_WARPS) {
         // ---------------- converters: fp32 rows -> TF32 hi/lo operand chunks ----------------
-        // thread = (row r, K half h); EVERY converter thread visits EVERY ring slot use in order (a waiter that
-        // skipped a phase of an mbarrier would alias its parity).  Global loads run one super-chunk (4 K-chunks)
-        // ahead of the conversion, also across tile boundaries.
-        const int r = tid & (TM - 1), h = tid >> 7;
+        // A warp owns 16 rows.  One load instruction covers 4 rows x one 128 B super-chunk (4 K-chunks): lane =
+        // (row-in-4, 16 B piece), i.e. fully coalesced lines; DEPTH super-chunks are kept in flight per thread
+        // (statically indexed register buffers), also across tile boundaries.  EVERY converter thread visits EVERY
+        // ring slot use in order (a waiter that skipped a phase of an mbarrier would alias its parity).
+        const int piece = lane & 7, u_of = piece >> 1, h_of = piece & 1, rsub = lane >> 3;
         const int nsc = (nchunk + SUPER - 1) / SUPER;
         const int64_t my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
         const int64_t total = my_tiles * nsc;
-        auto load_super = [&](int64_t q, float4 (&dst)[SUPER]) {
+        constexpr int DEPTH = 3;
+        float4 buf[DEPTH][4];
+        auto load_super = [&](int64_t q, float4 (&dst)[4]) {
             const int64_t tile = blockIdx.x + (q / nsc) * gridDim.x;
-            const int c0 = (int)(q % nsc) * SUPER;
-            const int64_t m = tile * TM + r;
+            const int k0 = (int)(q % nsc) * SUPER * KC + piece * 4;
 #pragma unroll
-            for (int u = 0; u < SUPER; ++u)
-                dst[u] = (c0 + u < nchunk) ? load4(L, m, (c0 + u) * KC + h * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int jj = 0; jj < 4; ++jj) dst[jj] = load4(L, tile * TM + warp * 16 + jj * 4 + rsub, k0);
         };
-        float4 cur[SUPER], nxt[SUPER];
-        if (total > 0) load_super(0, cur);
         uint32_t it = 0;
-        for (int64_t q = 0; q < total; ++q) {
-            if (q + 1 < total) load_super(q + 1, nxt);
+        auto process = [&](int64_t q, const float4 (&src)[4]) {
             const int c0 = (int)(q % nsc) * SUPER;
 #pragma unroll
             for (int u = 0; u < SUPER; ++u) {
@@ -182,18 +184,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(LArgs L) {
                     const uint32_t s = it % NSA, ph = (it / NSA) & 1;
                     ++it;
                     mbar_wait(bar_emptyA + 8 * s, ph ^ 1);
-                    uint8_t* st = smem + OFF_A + s * A_STAGE;
-                    float4 hi, lo;
-                    split4(cur[u], hi, lo);
-                    *reinterpret_cast<float4*>(st + h * A_LBO + r * 16) = hi;
-                    *reinterpret_cast<float4*>(st + A_PART + h * A_LBO + r * 16) = lo;
+                    if (u_of == u) {
+                        uint8_t* st = smem + OFF_A + s * A_STAGE + h_of * A_LBO;
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            float4 hi, lo;
+                            split4(src[jj], hi, lo);
+                            const int row = warp * 16 + jj * 4 + rsub;
+                            *reinterpret_cast<float4*>(st + row * 16) = hi;
+                            *reinterpret_cast<float4*>(st + A_PART + row * 16) = lo;
+                        }
+                    }
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_fullA + 8 * s);
                 }
             }
+        };
 #pragma unroll
-            for (int u = 0; u < SUPER; ++u) cur[u] = nxt[u];
+        for (int d = 0; d < DEPTH; ++d)
+            if (d < total) load_super(d, buf[d]);
+        for (int64_t q = 0; q < total; q += DEPTH) {
+#pragma unroll
+            for (int d = 0; d < DEPTH; ++d) {
+                if (q + d < total) {
+                    process(q + d, buf[d]);
+                    if (q + d + DEPTH < total) load_super(q + d + DEPTH, buf[d]);
+                }
+            }
         }
     } else {
         // ---------------- epilogue: TMEM -> bias / activation / residual -> global ----------------
@@ -206,6 +224,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(LArgs L) {
             tc_fence_after();
             const int64_t m = tile * TM + erow;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + b * (uint32_t)L.Npad;
+            float dot = 0.f;
             for (int n0 = 0; n0 < L.Npad; n0 += 16) {
                 float v[16];
                 tmem_ld16(taddr + n0, v);
@@ -216,20 +235,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(LArgs L) {
                         if (n < L.N) {
                             float y = apply_act(v[i] + bias_s[n], L.act);
                             if (L.res) y += L.res[m * L.ldres + n];
+                            if (L.head_w) dot = fmaf(y, __ldg(L.head_w + n), dot);
                             v[i] = y;
                         }
                     }
-                    float* o = L.Y + m * L.ldy + n0;
-                    if (n0 + 16 <= L.N && (L.ldy & 3) == 0 && (reinterpret_cast<uintptr_t>(L.Y) & 15) == 0) {
+                    if (L.Y) {
+                        float* o = L.Y + m * L.ldy + n0;
+                        if (n0 + 16 <= L.N && (L.ldy & 3) == 0 && (reinterpret_cast<uintptr_t>(L.Y) & 15) == 0) {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(o)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                    } else {
+                            for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(o)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                        } else {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i)
-                            if (n0 + i < L.N) o[i] = v[i];
+                            for (int i = 0; i < 16; ++i)
+                                if (n0 + i < L.N) o[i] = v[i];
+                        }
                     }
                 }
             }
+            if (L.head_w && m < L.M) L.out_head[m] = apply_act(dot + L.head_b[0], L.head_act);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_accE + 8 * b);
@@ -243,11 +266,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(LArgs L) {
 
 extern "C" int64_t hnr_linear_tc_packed_bytes(int64_t Npad, int64_t Kp) { return (Kp / KC) * 2 * Npad * KC * 4; }
 
-// Y = act(concat(A) W^T + b) (+res) on tensor cores.  wpack: image of W zero-padded to (Npad, Kp), Npad % 16 == 0,
+// Y = act(concat(A) W^T + b) (+res) on tensor cores; optional fused single-output head applied to Y's rows in the
+// epilogue (out_head = head_act(Y . head_w + head_b)); Y may be NULL when only the head is wanted.  wpack: image of W zero-padded to (Npad, Kp), Npad % 16 == 0,
 // Npad <= 256, Kp % 8 == 0 (layout: linear_tc.py).  Same argument meaning as hnr_linear_fwd.
 extern "C" int hnr_linear_tc_fwd(const float* const* a_ptr, const int64_t* a_ld, const int64_t* a_k, const int64_t* a_mod, const void* wpack,
                                  int64_t Npad, int64_t Kp, const float* bias, const float* res, int64_t ldres, float* Y, int64_t ldy,
-                                 int64_t M, int64_t N, int64_t K, int act, void* stream) {
+                                 int64_t M, int64_t N, int64_t K, int act, const float* head_w, const float* head_b, int head_act,
+                                 float* out_head, void* stream) {
     if (M == 0) return HNR_OK;
     HNR_CHECK_ARG(Npad % 16 == 0 && Npad >= 16 && Npad <= 256 && N <= Npad, "linear_tc_fwd: Npad must be a multiple of 16 in [16,256]");
     HNR_CHECK_ARG(Kp % KC == 0 && K <= Kp && K > 0, "linear_tc_fwd: Kp must be a multiple of 8 and >= K");
@@ -255,6 +280,9 @@ extern "C" int hnr_linear_tc_fwd(const float* const* a_ptr, const int64_t* a_ld,
     HNR_CHECK_ARG(a_k[0] + a_k[1] + a_k[2] == K, "linear_tc_fwd: concat widths must sum to K");
     LArgs L{};
     for (int i = 0; i < 3; ++i) { L.A.p[i] = a_ptr[i]; L.A.ld[i] = (int)a_ld[i]; L.A.k[i] = (int)a_k[i]; L.A.mod[i] = a_mod ? a_mod[i] : 0; }
+    HNR_CHECK_ARG(Y || (head_w && out_head), "linear_tc_fwd: no output requested");
+    HNR_CHECK_ARG(!head_w || (head_b && out_head), "linear_tc_fwd: head needs head_b and out_head");
+    L.head_w = head_w; L.head_b = head_b; L.out_head = out_head; L.head_act = head_act;
     L.wpack = (const uint8_t*)wpack; L.bias = bias; L.res = res; L.Y = Y; L.M = M; L.ldres = (int)ldres; L.ldy = (int)ldy;
     L.K = (int)K; L.Kp = (int)Kp; L.N = (int)N; L.Npad = (int)Npad; L.act = act;
     static bool configured = false;

@@ -43,8 +43,8 @@ class tag:
 
 
 class _launch:
-    def __init__(self, n=1):
-        self.n = n
+    def __init__(self, n=1, name=None):
+        self.n, self.name = n, name
 
     def __enter__(self):
         _count(self.n)
@@ -56,7 +56,7 @@ class _launch:
     def __exit__(self, *a):
         if TIMERS is not None:
             self.e.record()
-            TIMERS.append((_TAG[-1], self.s, self.e))
+            TIMERS.append((_TAG[-1] if self.name is None else f"{_TAG[-1]}/{self.name}", self.s, self.e))
 
 
 def _f32c(t: torch.Tensor) -> torch.Tensor:
@@ -144,7 +144,7 @@ class LinearFn(torch.autograd.Function):
             with _launch():
                 check(lib().hnr_linear_tc_fwd(ptr_array(padded), i64_array(lds), i64_array(ks), i64_array(modl), ptr(wpack), Npad, Kp,
                                               ptr(bc), ptr(resv), resv.stride(0) if resv is not None else 0, ptr(Y), N, M, N, K, act,
-                                              stream()), "linear_tc_fwd")
+                                              None, None, 0, None, stream()), "linear_tc_fwd")
         else:
             with _launch():
                 check(lib().hnr_linear_fwd(ptr_array(padded), i64_array(lds), i64_array(ks), i64_array(modl), ptr(W), ptr(bc), ptr(resv),
@@ -167,10 +167,10 @@ class LinearFn(torch.autograd.Function):
         if any(need_src) and M > 0:
             outs = [torch.empty((M, ks[i]), device=W.device, dtype=torch.float32) if need_src[i] else None for i in range(ctx.nsrc)]
             outs_p = outs + [None] * (3 - ctx.nsrc)
-            check(lib().hnr_linear_bwd_data(ptr(dY), dY.stride(0), ptr(Y), Y.stride(0), ptr(W), ptr_array(outs_p),
-                                            i64_array([o.stride(0) if o is not None else 0 for o in outs_p]), i64_array(ks), M, N, K, act,
-                                            stream()), "linear_bwd_data")
-            _count()
+            with _launch(name="linear_bwd_data"):
+                check(lib().hnr_linear_bwd_data(ptr(dY), dY.stride(0), ptr(Y), Y.stride(0), ptr(W), ptr_array(outs_p),
+                                                i64_array([o.stride(0) if o is not None else 0 for o in outs_p]), i64_array(ks), M, N, K, act,
+                                                stream()), "linear_bwd_data")
             for i in range(ctx.nsrc):
                 if outs[i] is not None and ctx.mods[i] > 0:
                     outs[i] = outs[i].view(-1, ctx.mods[i], ks[i]).sum(dim=0)
@@ -182,12 +182,37 @@ class LinearFn(torch.autograd.Function):
             dW = torch.zeros_like(W)
             db = torch.zeros(N, device=W.device, dtype=torch.float32) if ctx.has_b else None
             if M > 0:
-                check(lib().hnr_linear_bwd_weight(ptr(dY), dY.stride(0), ptr(Y), Y.stride(0), ptr_array(padded), i64_array(lds),
-                                                  i64_array(ks), i64_array(ctx.mods), ptr(dW), ptr(db), M, N, K, act, stream()),
-                      "linear_bwd_weight")
-                _count()
+                with _launch(name="linear_bwd_weight"):
+                    check(lib().hnr_linear_bwd_weight(ptr(dY), dY.stride(0), ptr(Y), Y.stride(0), ptr_array(padded), i64_array(lds),
+                                                      i64_array(ks), i64_array(ctx.mods), ptr(dW), ptr(db), M, N, K, act, stream()),
+                          "linear_bwd_weight")
         d_res = dY if ctx.has_res else None
         return (dW, db, d_res, None, None, None, *d_srcs)
+
+
+def linear_head(srcs: Sequence[torch.Tensor], W, b, act: int, head_W, head_b, head_act: int, mods: Sequence[int] = (),
+                M: Optional[int] = None) -> torch.Tensor:
+    """no-grad fusion of a dense layer with a following 1-output layer: head_act(act(cat(srcs) W^T + b) head_W^T + head_b)
+    -> (M,1); the hidden layer's output never reaches memory (tensor-core epilogue).  Inference only."""
+    assert not torch.is_grad_enabled() and LINEAR_ENGINE == "tc"
+    srcs = [_rows2d(s) for s in srcs]
+    if M is None:
+        M = srcs[0].shape[0]
+    W = _f32c(W)
+    N, K = W.shape
+    ks = [s.shape[1] for s in srcs] + [0] * (3 - len(srcs))
+    assert sum(ks) == K and head_W.numel() == N
+    require_cuda(W, *srcs)
+    padded = list(srcs) + [None] * (3 - len(srcs))
+    lds = [s.stride(0) if s is not None else 0 for s in padded]
+    modl = list(mods) + [0] * (3 - len(mods))
+    out = torch.empty((M, 1), device=W.device, dtype=torch.float32)
+    wpack, Npad, Kp = _packed_linear(W)
+    hw, hb, bc = _f32c(head_W).view(-1), _f32c(head_b).view(-1), _f32c(b)
+    with _launch():
+        check(lib().hnr_linear_tc_fwd(ptr_array(padded), i64_array(lds), i64_array(ks), i64_array(modl), ptr(wpack), Npad, Kp, ptr(bc), None, 0,
+                                      None, N, M, N, K, act, ptr(hw), ptr(hb), head_act, ptr(out), stream()), "linear_tc_fwd(head)")
+    return out
 
 
 def linear(srcs: Sequence[torch.Tensor], W, b, act: int = ACT_NONE, res=None, mods: Sequence[int] = (), M: Optional[int] = None):
@@ -226,8 +251,8 @@ class NbrWeightsFn(torch.autograd.Function):
             S, K = pidx.shape
             g = _f32c(g_confc)
             d_conf = torch.zeros(ctx.conf_shape, device=pidx.device, dtype=torch.float32)
-            check(lib().hnr_conf_bwd(None, None, None, ptr(pidx), ptr(g), 0, S, K, ptr(d_conf), stream()), "conf_bwd")
-            _count()
+            with _launch(name="conf_bwd"):
+                check(lib().hnr_conf_bwd(None, None, None, ptr(pidx), ptr(g), 0, S, K, ptr(d_conf), stream()), "conf_bwd")
         return None, d_conf, None, None, None
 
 
@@ -256,10 +281,10 @@ class NbrFeaturesFn(torch.autograd.Function):
         d_col = torch.zeros(ctx.shapes[1], device=emb.device, dtype=torch.float32) if nc else None
         d_dir = torch.zeros(ctx.shapes[2], device=emb.device, dtype=torch.float32) if nd else None
         if ne or nc or nd:
-            check(lib().hnr_nbr_features_bwd(ptr(dX0), ptr(dE), ptr(emb), ptr(pidx), ptr(mask) if ctx.has_mask else None, ptr(vlist),
-                                             ptr(raydirs), ptr(ctx.cam), ctx.Nv, ctx.K, ptr(d_emb), ptr(d_col), ptr(d_dir), stream()),
-                  "nbr_features_bwd")
-            _count()
+            with _launch(name="nbr_features_bwd"):
+                check(lib().hnr_nbr_features_bwd(ptr(dX0), ptr(dE), ptr(emb), ptr(pidx), ptr(mask) if ctx.has_mask else None, ptr(vlist),
+                                                 ptr(raydirs), ptr(ctx.cam), ctx.Nv, ctx.K, ptr(d_emb), ptr(d_col), ptr(d_dir), stream()),
+                      "nbr_features_bwd")
         return d_emb, d_col, d_dir, None, None, None, None, None, None, None, None, None
 
 
@@ -290,9 +315,9 @@ class AlphaKSumFn(torch.autograd.Function):
         d_wc = torch.empty((Nv, K), device=H.device, dtype=torch.float32)
         d_wa = torch.zeros(HID, device=H.device, dtype=torch.float32)
         d_ba = torch.zeros(1, device=H.device, dtype=torch.float32)
-        check(lib().hnr_alpha_ksum_bwd(ptr(H), ptr(weight), ptr(confc), ptr(vlist), ptr(w_alpha), ptr(araw), ptr(d_sigma), ptr(dX5), Nv, K,
-                                       H.shape[1], ptr(dH), ptr(d_wc), ptr(d_wa), ptr(d_ba), stream()), "alpha_ksum_bwd")
-        _count()
+        with _launch(name="alpha_ksum_bwd"):
+            check(lib().hnr_alpha_ksum_bwd(ptr(H), ptr(weight), ptr(confc), ptr(vlist), ptr(w_alpha), ptr(araw), ptr(d_sigma), ptr(dX5), Nv, K,
+                                           H.shape[1], ptr(dH), ptr(d_wc), ptr(d_wa), ptr(d_ba), stream()), "alpha_ksum_bwd")
         d_confc = None
         if ctx.needs_input_grad[1]:
             vl = vlist.long()
@@ -344,9 +369,9 @@ class ImageGatherFn(torch.autograd.Function):
         V, S, Nv = ctx.dims
         grads = [None] + [torch.zeros(s, device=xy.device, dtype=torch.float32) for s in ctx.shapes[1:]]
         d_aux = _f32c(d_aux)
-        check(lib().hnr_image_gather_bwd(ptr_array(grads), i64_array(ctx.hw), ptr(xy), ptr(vlist), ptr(d_aux), V, S, Nv, stream()),
-              "image_gather_bwd")
-        _count()
+        with _launch(name="image_gather_bwd"):
+            check(lib().hnr_image_gather_bwd(ptr_array(grads), i64_array(ctx.hw), ptr(xy), ptr(vlist), ptr(d_aux), V, S, Nv, stream()),
+                  "image_gather_bwd")
         return None, grads[1], grads[2], grads[3], None, None
 
 
@@ -370,9 +395,9 @@ class BlendFn(torch.autograd.Function):
         V, Nv = aux.shape[0], aux.shape[1]
         d_aux = torch.empty_like(aux)
         d_sig = torch.empty_like(sig)
-        check(lib().hnr_blend_bwd(ptr(aux), ptr(sig), ptr(ok), ptr(keep) if ctx.has_keep else None, ptr(_f32c(d_merged)), V, Nv,
-                                  ptr(d_aux), ptr(d_sig), stream()), "blend_bwd")
-        _count()
+        with _launch(name="blend_bwd"):
+            check(lib().hnr_blend_bwd(ptr(aux), ptr(sig), ptr(ok), ptr(keep) if ctx.has_keep else None, ptr(_f32c(d_merged)), V, Nv,
+                                      ptr(d_aux), ptr(d_sig), stream()), "blend_bwd")
         return d_aux, d_sig, None, None
 
 
@@ -411,10 +436,10 @@ class CompositeFn(torch.autograd.Function):
         g_feats = torch.empty_like(feats)
         c = lambda t: _f32c(t) if t is not None else None
         gc = c(g_color) if g_color is not None else torch.zeros((R, 3), device=feats.device)
-        check(lib().hnr_composite_bwd(ptr(feats), ptr(valid), ptr(dist), ptr(accT), ptr(bgT), ptr(bg) if ctx.has_bg else None, ptr(gc),
-                                      ptr(c(g_opacity)), ptr(c(g_bgT)), ptr(c(g_bw)), ptr(c(g_accT)), R, SR, ptr(g_feats), stream()),
-              "composite_bwd")
-        _count()
+        with _launch(name="composite_bwd"):
+            check(lib().hnr_composite_bwd(ptr(feats), ptr(valid), ptr(dist), ptr(accT), ptr(bgT), ptr(bg) if ctx.has_bg else None, ptr(gc),
+                                          ptr(c(g_opacity)), ptr(c(g_bgT)), ptr(c(g_bw)), ptr(c(g_accT)), R, SR, ptr(g_feats), stream()),
+                  "composite_bwd")
         return g_feats, None, None, None, None, None, None, None
 
 
@@ -431,9 +456,9 @@ class BlurSelectFn(torch.autograd.Function):
         Nk, ks = kernels.shape[0], kernels.shape[1]
         out = torch.empty_like(pred)
         sel = torch.empty((patch_num * patch_num,), device=pred.device, dtype=torch.int32)
-        check(lib().hnr_blur_select_fwd(ptr(pred), ptr(gt), ptr(kernels), patch_num, patch_size, Nk, ks, ptr(out), ptr(sel), stream()),
-              "blur_select_fwd")
-        _count()
+        with _launch(name="blur_select_fwd"):
+            check(lib().hnr_blur_select_fwd(ptr(pred), ptr(gt), ptr(kernels), patch_num, patch_size, Nk, ks, ptr(out), ptr(sel), stream()),
+                  "blur_select_fwd")
         ctx.save_for_backward(kernels, sel)
         ctx.geom = (patch_num, patch_size, Nk, ks)
         ctx.mark_non_differentiable(sel)
@@ -445,6 +470,6 @@ class BlurSelectFn(torch.autograd.Function):
         pn, ps, Nk, ks = ctx.geom
         g_out = _f32c(g_out)
         g_pred = torch.empty_like(g_out)
-        check(lib().hnr_blur_select_bwd(ptr(g_out), ptr(kernels), ptr(sel), pn, ps, Nk, ks, ptr(g_pred), stream()), "blur_select_bwd")
-        _count()
+        with _launch(name="blur_select_bwd"):
+            check(lib().hnr_blur_select_bwd(ptr(g_out), ptr(kernels), ptr(sel), pn, ps, Nk, ks, ptr(g_pred), stream()), "blur_select_bwd")
         return g_pred, None, None, None, None

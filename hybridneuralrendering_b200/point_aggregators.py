@@ -249,8 +249,11 @@ class PointAggregator(nn.Module):
             with ops.tag("sample_mlp"):
                 t = ops.linear([aux.view(V * Nv, 45), g, dv], am[0].weight, am[0].bias, ACT_LRELU, mods=(0, Nv, 0), M=V * Nv)
                 t = ops.linear([t], am[2].weight, am[2].bias, ACT_LRELU)
-                t = ops.linear([t], am[4].weight, am[4].bias, ACT_LRELU)
-                sig = ops.linear([t], am[6].weight, am[6].bias, ACT_SIGMOID)
+                if not torch.is_grad_enabled() and ops.LINEAR_ENGINE == "tc" and V * Nv >= 128:
+                    sig = ops.linear_head([t], am[4].weight, am[4].bias, ACT_LRELU, am[6].weight, am[6].bias, ACT_SIGMOID)
+                else:
+                    t = ops.linear([t], am[4].weight, am[4].bias, ACT_LRELU)
+                    sig = ops.linear([t], am[6].weight, am[6].bias, ACT_SIGMOID)
             with ops.tag("blend"):
                 merged = ops.BlendFn.apply(aux, sig, ok, self._keep_mask(R, SR, vlist))
         else:

@@ -128,8 +128,9 @@ int hnr_linear_bwd_weight(const float* dY, int64_t lddy, const float* Y, int64_t
  * the host-packed TF32 hi/lo image of W zero-padded to (Npad % 16 == 0 <= 256, Kp % 8 == 0) (csrc/linear_tc.cu) */
 int64_t hnr_linear_tc_packed_bytes(int64_t Npad, int64_t Kp);
 int hnr_linear_tc_fwd(const float* const* a_ptr, const int64_t* a_ld, const int64_t* a_k, const int64_t* a_mod, const void* wpack,
-                      int64_t Npad, int64_t Kp, const float* bias, const float* res, int64_t ldres, float* Y, int64_t ldy, int64_t M,
-                      int64_t N, int64_t K, int act, void* stream);
+                      int64_t Npad, int64_t Kp, const float* bias, const float* res, int64_t ldres, float* Y /* may be NULL */,
+                      int64_t ldy, int64_t M, int64_t N, int64_t K, int act, const float* head_w /* N or NULL */,
+                      const float* head_b, int head_act, float* out_head /* M */, void* stream);
 
 /* Fused per-neighbour MLP on tcgen05 tensor cores (3xTF32, fp32 accuracy), inference path: gather from the
  * point tables + block1 + block3 + density head + weighted K-sum in one persistent kernel (csrc/mlp_tc.cu).
