@@ -59,6 +59,8 @@ _SIGS = {
     "hnr_mlp_tc_packed_bytes": (i64, [i64]),
     "hnr_mlp_tc_gemm_test": (C.c_int, [vp, i64, i64, vp, i64, vp, vp]),
     "hnr_mlp_tc_forward": (C.c_int, [vp] * 17 + [i64, i64, vp, vp, vp]),
+    "hnr_nbr_mlp_f16_packed_bytes": (i64, []),
+    "hnr_nbr_mlp_f16_forward": (C.c_int, [vp] * 17 + [C.POINTER(C.c_float), f32c, f32c, i64, i64, vp, vp, vp, vp]),
 }
 
 EXPORTED = sorted(_SIGS)

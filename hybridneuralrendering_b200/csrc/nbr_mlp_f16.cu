@@ -1,0 +1,537 @@
+// Fused per-neighbour MLP on the 5th-gen tensor cores, second generation (SURVEY.md §8a rows G1 + A1-A3).
+//
+//     x0(284) -> 256 -> 256 -> [+colour, dir-view, <dir,view>](263) -> 256 -> 256 -> density head, weighted K-sum
+//
+// One persistent CTA per SM walks tiles of 128 neighbour rows (16 shading samples x K=8).  What differs from the
+// first-generation kernel (mlp_tc.cu, 3xTF32):
+//   * fp32 accuracy from THREE FP16 MMAs per product ("3xFP16"): every operand v (pre-multiplied by a power-of-two
+//     scale so that hi and lo stay in fp16's normal range) is split into hi = fp16(v), lo = fp16(v - hi) and
+//     a*w ~= a_hi*w_hi + a_lo*w_hi + a_hi*w_lo is accumulated in fp32 in TMEM.  22 mantissa bits, like 3xTF32, but
+//     tcgen05.mma.kind::f16 runs at twice the TF32 rate and the operands take half the shared memory;
+//   * because hi+lo fp16 take exactly the 4 bytes of the fp32 value, the layer activations live in shared memory
+//     ALREADY in the canonical UMMA operand layout: the epilogue of layer l writes layer l+1's A operand in place
+//     and no conversion ring is needed for layers 1..3;
+//   * two TMEM accumulators (2 x 256 columns): the MMAs of layer l+1 start on the first K-chunks of the new
+//     activation while the epilogue of layer l is still draining the rest (per-32-column mbarriers), and the
+//     layer-0 MMAs of the NEXT tile run under the last epilogue + K-sum of the current tile;
+//   * warp roles: 4 epilogue warps (TMEM lane quarters), 4 generator warps (gather from the point tables, positional
+//     encodings, layer-0 operand chunks, one tile ahead), 1 MMA warp (one elected thread), 1 bulk-copy warp.
+//
+// The arithmetic restated is models/aggregators/point_aggregators.py:921-972, :1002-1036 and
+// models/helpers/networks.py:175-189 of the reference.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "hnr.h"
+#include "tc_common.cuh"
+
+namespace {
+using namespace tc;
+
+constexpr int TM = 128;                 // rows (neighbours) per tile == UMMA M
+constexpr int HID = 256;                // layer width == UMMA N
+constexpr int KC = 16;                  // K elements per chunk == one f16 MMA K-step (32 bytes per row)
+constexpr int NSW = 3;                  // weight ring stages
+constexpr int NSA = 3;                  // layer-0 operand ring stages
+constexpr int W_PART = HID * KC * 2;    // 8192 B: hi (or lo) weights of one chunk
+constexpr int W_STAGE = 2 * W_PART;     // 16384
+constexpr int A_PART = TM * KC * 2;     // 4096 B
+constexpr int A_STAGE = 2 * A_PART;     // 8192
+constexpr int ACT_PART = TM * HID * 2;  // 65536 B: hi (or lo) of a 128 x 256 activation
+constexpr int NLAYER = 4;
+constexpr int NC0 = 18, NC1 = 16, NC2 = 17, NC3 = 16;      // K chunks per layer (288, 256, 16 + 256, 256)
+constexpr int NCHUNK_TILE = NC0 + NC1 + NC2 + NC3;
+constexpr int FEAT = 32, NF_VIEW = 4, X5_W = 280;
+constexpr int NEPI = 128, NGEN = 128, NTHREADS = 320;
+
+// shared memory map (bytes)
+constexpr int OFF_W = 0;
+constexpr int OFF_A = OFF_W + NSW * W_STAGE;               // 49152
+constexpr int OFF_E = OFF_A + NSA * A_STAGE;               // 73728   block3 extras chunk, double buffered by tile parity
+constexpr int OFF_ACT = OFF_E + 2 * A_STAGE;               // 90112   hi | lo ; re-used as the fp32 staging of the K-sum
+constexpr int OFF_BIAS = OFF_ACT + 2 * ACT_PART;           // 221184  (4,256) fp32, pre-scaled
+constexpr int OFF_WALPHA = OFF_BIAS + NLAYER * HID * 4;    // 225280
+constexpr int OFF_WC = OFF_WALPHA + HID * 4;               // 226304  neighbour weight * conf, double buffered
+constexpr int OFF_BAR = OFF_WC + 2 * TM * 4;               // 227328
+constexpr int NBAR = 2 * NSW + 2 * NSA + 2 + 8 + 2 + 1 + 1;
+constexpr int SMEM_BYTES = OFF_BAR + NBAR * 8 + 16;
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+
+constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(HID >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);   // D=f32, A=B=f16, K-major
+constexpr uint32_t A_LBO = (TM / 8) * 128, W_LBO = (HID / 8) * 128, SBO = 128;
+
+struct F16Args {
+    const float *xyz, *xyz_pers, *emb, *color, *dir;
+    const int32_t *pidx, *vlist;
+    const float *loc_w, *loc_pers, *raydirs, *cam, *weight, *confc;
+    const uint8_t* wpack;          // 67 chunk images in consumption order
+    const float *bias, *walpha, *balpha;   // bias: (4,256), rows 0..2 pre-multiplied by the next layer's input scale
+    float *sigma, *X5, *dbg;
+    int64_t Nv;
+    float mul[NLAYER];             // accumulator -> (scaled) pre-activation factor per layer
+    float scale0, scale2;          // input scales of layer 0 (generated features) and layer 2 (extras chunk)
+};
+
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// tcgen05.ld without the wait; the matching wait names the registers as in/out operands so that no use of them
+// can be scheduled before it
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+                   "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]),
+                   "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]),
+                   "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+}
+
+template <int ID, int N>
+__device__ __forceinline__ void named_barrier() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(N) : "memory"); }
+
+__device__ __forceinline__ void rot3(const float* m, float x, float y, float z, float& ox, float& oy, float& oz) {
+    ox = x * m[0] + y * m[3] + z * m[6];
+    oy = x * m[1] + y * m[4] + z * m[7];
+    oz = x * m[2] + y * m[5] + z * m[8];
+}
+__device__ __forceinline__ float softplus_t(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+
+// 8 fp32 values -> 8 fp16 hi (one 16-byte core-matrix row) and 8 fp16 lo.  Values beyond fp16's range saturate.
+__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float a = fminf(fmaxf(v[2 * i], -65000.f), 65000.f), b = fminf(fmaxf(v[2 * i + 1], -65000.f), 65000.f);
+        const __half2 hh = __floats2half2_rn(a, b);
+        const float2 hf = __half22float2(hh);
+        const __half2 ll = __floats2half2_rn(a - hf.x, b - hf.y);
+        h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+        l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// store one 16-wide K chunk of row r (already scaled) into an operand stage: [hi: kb0 | kb1][lo: kb0 | kb1]
+__device__ __forceinline__ void store_chunk16(uint8_t* stage, int r, const float* v) {
+    uint4 hi, lo;
+    split8(v, hi, lo);
+    *reinterpret_cast<uint4*>(stage + r * 16) = hi;
+    *reinterpret_cast<uint4*>(stage + A_PART + r * 16) = lo;
+    split8(v + 8, hi, lo);
+    *reinterpret_cast<uint4*>(stage + A_LBO + r * 16) = hi;
+    *reinterpret_cast<uint4*>(stage + A_PART + A_LBO + r * 16) = lo;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) nbr_mlp_f16_kernel(F16Args A) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+    const uint32_t b0 = smem_u32(bars);
+    const uint32_t bar_wfull = b0, bar_wempty = b0 + 8 * NSW, bar_afull = bar_wempty + 8 * NSW, bar_aempty = bar_afull + 8 * NSA,
+                   bar_efull = bar_aempty + 8 * NSA, bar_actfull = bar_efull + 16, bar_accfull = bar_actfull + 64,
+                   bar_accempty0 = bar_accfull + 16, bar_tiledone = bar_accempty0 + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBAR);
+    float* bias_s = reinterpret_cast<float*>(smem + OFF_BIAS);
+    float* walpha_s = reinterpret_cast<float*>(smem + OFF_WALPHA);
+    float* wc_s = reinterpret_cast<float*>(smem + OFF_WC);
+
+    const int64_t total_rows = A.Nv * 8;
+    const int64_t ntiles = (total_rows + TM - 1) / TM;
+
+    if (tid == 0) {
+        for (int s = 0; s < NSW; ++s) { mbar_init(bar_wfull + 8 * s, 1); mbar_init(bar_wempty + 8 * s, 1); }
+        for (int s = 0; s < NSA; ++s) { mbar_init(bar_afull + 8 * s, 4); mbar_init(bar_aempty + 8 * s, 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(bar_efull + 8 * s, 4); mbar_init(bar_accfull + 8 * s, 1); }
+        for (int s = 0; s < 8; ++s) mbar_init(bar_actfull + 8 * s, 4);
+        mbar_init(bar_accempty0, 4);
+        mbar_init(bar_tiledone, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) tmem_alloc(smem_u32(tmem_slot), 512);
+    for (int i = tid; i < NLAYER * HID; i += NTHREADS) bias_s[i] = A.bias[i];
+    if (tid < HID) walpha_s[tid] = A.walpha[tid];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 9) {
+        // ================= bulk-copy producer: one 16 KB weight chunk image per stage =================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                for (int c = 0; c < NCHUNK_TILE; ++c, ++it) {
+                    const uint32_t s = it % NSW, ph = (it / NSW) & 1;
+                    mbar_wait(bar_wempty + 8 * s, ph ^ 1);
+                    mbar_arrive_expect_tx(bar_wfull + 8 * s, W_STAGE);
+                    bulk_g2s(smem_u32(smem + OFF_W + s * W_STAGE), A.wpack + (size_t)c * W_STAGE, W_STAGE, bar_wfull + 8 * s);
+                }
+            }
+        }
+    } else if (warp == 8) {
+        // ================= MMA issuer: one thread, 3 MMAs (3xFP16) per K chunk =================
+        if (lane == 0) {
+            uint32_t wit = 0, ait = 0, gen = 0, ti = 0;
+            const uint32_t act_hi = smem_u32(smem + OFF_ACT), act_lo = act_hi + ACT_PART;
+            auto issue = [&](uint32_t acc, uint32_t a_hi_addr, uint32_t a_lo_addr, bool first) {
+                const uint32_t s = wit % NSW, ph = (wit / NSW) & 1;
+                ++wit;
+                mbar_wait(bar_wfull + 8 * s, ph);
+                tc_fence_after();
+                const uint32_t w = smem_u32(smem + OFF_W + s * W_STAGE);
+                const uint64_t w_hi = umma_desc(w, W_LBO, SBO), w_lo = umma_desc(w + W_PART, W_LBO, SBO);
+                const uint64_t a_hi = umma_desc(a_hi_addr, A_LBO, SBO), a_lo = umma_desc(a_lo_addr, A_LBO, SBO);
+                tc_mma_f16(acc, a_hi, w_hi, IDESC, first ? 0u : 1u);
+                tc_mma_f16(acc, a_lo, w_hi, IDESC, 1u);
+                tc_mma_f16(acc, a_hi, w_lo, IDESC, 1u);
+                tc_commit(bar_wempty + 8 * s);
+            };
+            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
+                const uint32_t acc0 = tmem_base, acc1 = tmem_base + HID;
+                // ---- layer 0: operands from the generator ring (accumulator 0 was last read by epilogue 2 of the previous tile)
+                if (ti > 0) mbar_wait(bar_accempty0, (ti - 1) & 1);
+                for (int c = 0; c < NC0; ++c, ++ait) {
+                    const uint32_t s = ait % NSA, ph = (ait / NSA) & 1;
+                    mbar_wait(bar_afull + 8 * s, ph);
+                    const uint32_t a = smem_u32(smem + OFF_A + s * A_STAGE);
+                    issue(acc0, a, a + A_PART, c == 0);
+                    tc_commit(bar_aempty + 8 * s);
+                }
+                tc_commit(bar_accfull);
+                // ---- layer 1: operands = activation written by epilogue 0, released per 32 columns
+                for (int c = 0; c < NC1; ++c) {
+                    if ((c & 1) == 0) mbar_wait(bar_actfull + 8 * (c >> 1), gen & 1);
+                    issue(acc1, act_hi + c * 2 * A_LBO, act_lo + c * 2 * A_LBO, c == 0);
+                }
+                tc_commit(bar_accfull + 8);
+                ++gen;
+                // ---- layer 2: extras chunk first (ready since the gather), then the activation of epilogue 1
+                {
+                    const uint32_t p = ti & 1;
+                    mbar_wait(bar_efull + 8 * p, (ti >> 1) & 1);
+                    const uint32_t e = smem_u32(smem + OFF_E + p * A_STAGE);
+                    issue(acc0, e, e + A_PART, true);
+                }
+                for (int c = 0; c < NC1; ++c) {
+                    if ((c & 1) == 0) mbar_wait(bar_actfull + 8 * (c >> 1), gen & 1);
+                    issue(acc0, act_hi + c * 2 * A_LBO, act_lo + c * 2 * A_LBO, false);
+                }
+                tc_commit(bar_accfull);
+                ++gen;
+                // ---- layer 3
+                for (int c = 0; c < NC3; ++c) {
+                    if ((c & 1) == 0) mbar_wait(bar_actfull + 8 * (c >> 1), gen & 1);
+                    issue(acc1, act_hi + c * 2 * A_LBO, act_lo + c * 2 * A_LBO, c == 0);
+                }
+                tc_commit(bar_accfull + 8);
+                ++gen;
+            }
+        }
+    } else if (warp >= 4) {
+        // ================= generators: gather + layer-0 operand chunks, thread = row =================
+        const int r = tid - NEPI;
+        uint32_t ait = 0, ti = 0;
+        const float* rt = A.cam + 12;
+        // indices of the first tile
+        int64_t s_cur = 0, g_cur = 0;
+        bool live_cur = false;
+        auto load_idx = [&](int64_t tile, int64_t& s, int64_t& g, bool& live) {
+            const int64_t row = tile * TM + r;
+            live = tile < ntiles && row < total_rows;
+            const int64_t v = live ? (row >> 3) : 0;
+            s = A.vlist[v];
+            g = live ? max(A.pidx[s * 8 + (row & 7)], 0) : 0;
+        };
+        if ((int64_t)blockIdx.x < ntiles) load_idx(blockIdx.x, s_cur, g_cur, live_cur);
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
+            const int64_t row = tile * TM + r;
+            const int k = (int)(row & 7);
+            const int64_t s = s_cur, g = g_cur;
+            const bool live = live_cur;
+            // ---- issue every load of this row, then the index loads of the next tile ----
+            float4 e4[8];
+            const float4* ep = reinterpret_cast<const float4*>(A.emb + g * FEAT);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) e4[i] = __ldg(ep + i);
+            const float px = A.xyz[g * 3], py = A.xyz[g * 3 + 1], pz = A.xyz[g * 3 + 2];
+            const float dx = A.dir[g * 3], dy = A.dir[g * 3 + 1], dz = A.dir[g * 3 + 2];
+            const float c0 = A.color[g * 3], c1 = A.color[g * 3 + 1], c2 = A.color[g * 3 + 2];
+            const float lx = A.loc_w[s * 3], ly = A.loc_w[s * 3 + 1], lz = A.loc_w[s * 3 + 2];
+            const float sx = A.loc_pers[s * 3], sy = A.loc_pers[s * 3 + 1], sz = A.loc_pers[s * 3 + 2];
+            const float rx0 = A.raydirs[s * 3], ry0 = A.raydirs[s * 3 + 1], rz0 = A.raydirs[s * 3 + 2];
+            float wgt = live ? A.weight[s * 8 + k] : 0.f;
+            if (live && A.confc) wgt *= A.confc[s * 8 + k];
+            float qx, qy, qz;
+            if (A.xyz_pers) { qx = A.xyz_pers[g * 3]; qy = A.xyz_pers[g * 3 + 1]; qz = A.xyz_pers[g * 3 + 2]; }
+            load_idx(tile + gridDim.x, s_cur, g_cur, live_cur);
+            // ---- per-row geometry ----
+            float d[6];
+            rot3(rt, px - lx, py - ly, pz - lz, d[0], d[1], d[2]);
+            if (!A.xyz_pers) {
+                float cx, cy, cz;
+                rot3(A.cam + 3, px - A.cam[0], py - A.cam[1], pz - A.cam[2], cx, cy, cz);
+                qx = cx / cz; qy = cy / cz; qz = cz;
+            }
+            d[3] = qx * qz - sx * sz; d[4] = qy * qz - sy * sz; d[5] = qz - sz;
+            float vx, vy, vz, rx, ry, rz;
+            rot3(rt, rx0, ry0, rz0, vx, vy, vz);
+            rot3(rt, dx, dy, dz, rx, ry, rz);
+            // view-direction encoding of the sample (X5 columns 256..279): row k of a sample writes 3 of the 12 angles
+            if (live) {
+                float* xo = A.X5 + (row >> 3) * X5_W + HID;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const int q = k * 3 + j;
+                    if (q < 3 * NF_VIEW) {
+                        const int c = q / NF_VIEW, f = q - c * NF_VIEW;
+                        const float val = c == 0 ? vx : (c == 1 ? vy : vz);
+                        float a, b;
+                        sincosf(val * (float)(1 << f), &a, &b);
+                        xo[q] = a;
+                        xo[3 * NF_VIEW + q] = b;
+                    }
+                }
+            }
+            // ---- block3 extras chunk + row weight (buffers of tile parity p; last read by tile ti-2) ----
+            {
+                const uint32_t p = ti & 1;
+                if (ti >= 2) mbar_wait(bar_tiledone, ti & 1);
+                float ev[16];
+                ev[0] = c0; ev[1] = c1; ev[2] = c2; ev[3] = rx - vx; ev[4] = ry - vy; ev[5] = rz - vz; ev[6] = rx * vx + ry * vy + rz * vz;
+#pragma unroll
+                for (int i = 7; i < 16; ++i) ev[i] = 0.f;
+#pragma unroll
+                for (int i = 0; i < 7; ++i) ev[i] *= A.scale2;
+                store_chunk16(smem + OFF_E + p * A_STAGE, r, ev);
+                wc_s[p * TM + r] = wgt;
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_efull + 8 * p);
+            }
+            // ---- layer-0 operand chunks: every transcendental is evaluated BEFORE the first ring wait, so that once the
+            //      MMA warp starts freeing stages only doublings, scaling and the fp16 split remain on the critical path ----
+            const float* ef = reinterpret_cast<const float*>(e4);
+            const float sc0 = A.scale0;
+            float pe[64], sn[32], cs[32];
+#pragma unroll
+            for (int f = 0; f < 5; ++f) {                  // encoded distances: idx = f*12 + (sin|cos)*6 + component
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                    float a, b;
+                    sincosf(d[j] * (float)(1 << f), &a, &b);
+                    pe[f * 12 + j] = a * sc0;
+                    pe[f * 12 + 6 + j] = b * sc0;
+                }
+            }
+            pe[60] = pe[61] = pe[62] = pe[63] = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) sincosf(ef[i], &sn[i], &cs[i]);
+            auto put = [&](const float* v) {
+                const uint32_t st = ait % NSA, ph = (ait / NSA) & 1;
+                ++ait;
+                mbar_wait(bar_aempty + 8 * st, ph ^ 1);
+                store_chunk16(smem + OFF_A + st * A_STAGE, r, v);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_afull + 8 * st);
+            };
+            {   // raw embedding: 2 chunks
+                float v[16];
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = ef[c * 16 + i] * sc0;
+                    put(v);
+                }
+            }
+#pragma unroll
+            for (int cb = 0; cb < 4; ++cb) {   // sin/cos(2^f e) per block of 8 channels: chunk = [sin x 8 | cos x 8]
+                float v[16];
+#pragma unroll
+                for (int f = 0; f < 3; ++f) {
+                    if (f > 0) {               // next octave by angle doubling
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float a = sn[cb * 8 + i], b = cs[cb * 8 + i];
+                            sn[cb * 8 + i] = 2.f * a * b;
+                            cs[cb * 8 + i] = 1.f - 2.f * a * a;
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { v[i] = sn[cb * 8 + i] * sc0; v[8 + i] = cs[cb * 8 + i] * sc0; }
+                    put(v);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) put(pe + c * 16);
+        }
+    } else {
+        // ================= epilogue warps: thread = row = TMEM lane =================
+        const int r = tid;                                     // 0..127, warp w owns TMEM lanes 32w..32w+31
+        const uint32_t lane_base = (uint32_t)(32 * warp) << 16;
+        uint8_t* act_hi = smem + OFF_ACT;
+        float* stage = reinterpret_cast<float*>(smem + OFF_ACT);
+        uint32_t gen = 0, ti = 0;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
+            const int64_t row0 = tile * TM;
+#pragma unroll 1
+            for (int l = 0; l < NLAYER; ++l) {
+                const uint32_t b = l & 1;
+                mbar_wait(bar_accfull + 8 * b, (l >> 1) & 1);          // each accumulator completes twice per tile
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + lane_base + b * HID;
+                const float mul = A.mul[l];
+                const float* bl = bias_s + l * HID;
+                if (l < NLAYER - 1) {
+                    uint32_t va[32], vb[32];
+                    tmem_ld32_issue(taddr, va);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        uint32_t(&cur)[32] = (j & 1) ? vb : va;
+                        uint32_t(&nxt)[32] = (j & 1) ? va : vb;
+                        tmem_ld_wait(cur);
+                        if (j + 1 < 8) tmem_ld32_issue(taddr + (j + 1) * 32, nxt);
+                        float y[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const float t = fmaf(__uint_as_float(cur[i]), mul, bl[j * 32 + i]);
+                            y[i] = fmaxf(t, 0.01f * t);
+                        }
+                        if (A.dbg) {
+                            const int64_t row = row0 + r;
+                            if (row < total_rows) {
+                                float* o = A.dbg + ((int64_t)l * total_rows + row) * HID + j * 32;
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) o[i] = y[i];
+                            }
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            uint4 hi, lo;
+                            split8(y + q * 8, hi, lo);
+                            uint8_t* dst = act_hi + (j * 4 + q) * A_LBO + r * 16;
+                            *reinterpret_cast<uint4*>(dst) = hi;
+                            *reinterpret_cast<uint4*>(dst + ACT_PART) = lo;
+                        }
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_actfull + 8 * j);
+                    }
+                    ++gen;
+                    if (l == 2) {           // accumulator 0 drained: layer 0 of the next tile may overwrite it
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_accempty0);
+                    }
+                } else {
+                    // ---- last layer: density head, row weight, fp32 staging for the K-sum ----
+                    const uint32_t p = ti & 1;
+                    mbar_wait(bar_efull + 8 * p, (ti >> 1) & 1);       // makes the generator's wc_s of this tile visible
+                    const float wrow = wc_s[p * TM + r];
+                    float dot = 0.f;
+                    uint32_t va[32], vb[32];
+                    tmem_ld32_issue(taddr, va);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        uint32_t(&cur)[32] = (j & 1) ? vb : va;
+                        uint32_t(&nxt)[32] = (j & 1) ? va : vb;
+                        tmem_ld_wait(cur);
+                        if (j + 1 < 8) tmem_ld32_issue(taddr + (j + 1) * 32, nxt);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const int col = j * 32 + i;
+                            float t = fmaf(__uint_as_float(cur[i]), mul, bl[col]);
+                            t = fmaxf(t, 0.01f * t);
+                            if (A.dbg && row0 + r < total_rows) A.dbg[((int64_t)l * total_rows + row0 + r) * HID + col] = t;
+                            dot = fmaf(t, walpha_s[col], dot);
+                            // staging: element (col,row) at col*128 + ((row/4 + col) % 32)*4 + row%4 (conflict-free both ways)
+                            stage[col * TM + (((r >> 2) + col) & 31) * 4 + (r & 3)] = t * wrow;
+                        }
+                    }
+                    float sg = wrow * softplus_t(dot + A.balpha[0] - 1.f);
+                    sg += __shfl_xor_sync(0xffffffffu, sg, 1);
+                    sg += __shfl_xor_sync(0xffffffffu, sg, 2);
+                    sg += __shfl_xor_sync(0xffffffffu, sg, 4);
+                    const int64_t v = (row0 + r) >> 3;
+                    if ((r & 7) == 0 && v < A.Nv) A.sigma[v] = sg;
+                    tc_fence_before();
+                    named_barrier<1, NEPI>();
+                    // ---- weighted K-sum: thread = column (r and r+128), 16 samples ----
+                    const int64_t v0 = row0 >> 3;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int col = r + h * TM;
+                        const float* sc = stage + col * TM;
+#pragma unroll 4
+                        for (int si = 0; si < 16; ++si) {
+                            const float4 a = *reinterpret_cast<const float4*>(sc + ((2 * si + col) & 31) * 4);
+                            const float4 bq = *reinterpret_cast<const float4*>(sc + ((2 * si + 1 + col) & 31) * 4);
+                            const float sum = ((a.x + a.y) + (a.z + a.w)) + ((bq.x + bq.y) + (bq.z + bq.w));
+                            if (v0 + si < A.Nv) A.X5[(v0 + si) * X5_W + col] = sum;
+                        }
+                    }
+                    named_barrier<1, NEPI>();           // staging consumed: epilogue 0 of the next tile may write the activation
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_tiledone);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace
+
+// bytes of the packed weight image: 67 chunks x [hi 8 KB | lo 8 KB] in consumption order (host packer: mlp_tc.py)
+extern "C" int64_t hnr_nbr_mlp_f16_packed_bytes(void) { return (int64_t)NCHUNK_TILE * W_STAGE; }
+
+// Fused per-neighbour MLP + density head + weighted K-sum for Nv valid samples (K == 8), 3xFP16 on tcgen05.
+// mul[l]: accumulator -> pre-activation factor of layer l (includes the next layer's input scale for l < 3);
+// bias (4,256): rows 0..2 pre-multiplied by the next layer's input scale.  dbg (optional): (4, Nv*8, 256) activations.
+extern "C" int hnr_nbr_mlp_f16_forward(const float* xyz, const float* xyz_pers, const float* emb, const float* color, const float* dir,
+                                       const int32_t* pidx, const int32_t* vlist, const float* loc_w, const float* loc_pers,
+                                       const float* raydirs, const float* cam, const float* weight, const float* confc, const void* wpack,
+                                       const float* bias, const float* walpha, const float* balpha, const float* mul, float scale0,
+                                       float scale2, int64_t Nv, int64_t K, float* sigma, float* X5, float* dbg, void* stream) {
+    HNR_CHECK_ARG(K == 8, "nbr_mlp_f16_forward: K must be 8 (128-row tiles hold 16 whole samples)");
+    if (Nv == 0) return HNR_OK;
+    F16Args A{};
+    A.xyz = xyz; A.xyz_pers = xyz_pers; A.emb = emb; A.color = color; A.dir = dir; A.pidx = pidx; A.vlist = vlist;
+    A.loc_w = loc_w; A.loc_pers = loc_pers; A.raydirs = raydirs; A.cam = cam; A.weight = weight; A.confc = confc;
+    A.wpack = (const uint8_t*)wpack; A.bias = bias; A.walpha = walpha; A.balpha = balpha; A.sigma = sigma; A.X5 = X5; A.dbg = dbg;
+    A.Nv = Nv;
+    for (int l = 0; l < NLAYER; ++l) A.mul[l] = mul[l];
+    A.scale0 = scale0; A.scale2 = scale2;
+    static bool configured = false;
+    if (!configured) {
+        HNR_CUDA(cudaFuncSetAttribute(nbr_mlp_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        configured = true;
+    }
+    const int64_t ntiles = hnr_cdiv(Nv * 8, TM);
+    const int grid = (int)(ntiles < HNR_NUM_SMS ? ntiles : HNR_NUM_SMS);
+    nbr_mlp_f16_kernel<<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(A);
+    HNR_CHECK_LAUNCH("nbr_mlp_f16_forward");
+    return HNR_OK;
+}

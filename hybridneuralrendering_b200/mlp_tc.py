@@ -8,6 +8,7 @@ cp.async.bulk.  Layout of one 8 KB part: [k half (2)][row group (32)][row (8)][4
 """
 from __future__ import annotations
 
+import math
 from typing import List, Optional, Sequence
 
 import torch
@@ -100,3 +101,94 @@ def forward(tables, pidx, vlist, loc_w, loc_pers, raydirs, cam, weight, confc, w
                                        ptr(loc_pers), ptr(raydirs), ptr(cam), ptr(weight), ptr(confc), ptr(wpack), ptr(bias), ptr(wa),
                                        ptr(ba), Nv, K, ptr(sigma), ptr(X5), stream()), "mlp_tc_forward")
     return sigma, X5
+
+
+# =====================================================================================================
+# second generation: 3xFP16 (csrc/nbr_mlp_f16.cu)
+# =====================================================================================================
+KC16 = 16
+ACT_SCALE = 64.0          # power-of-two input scale of every layer: keeps hi AND lo of O(1e-3..1e3) activations in fp16's normal range
+
+
+def layer1_column_order_f16() -> List[int]:
+    """kernel K order of block1's 284 inputs for 16-wide chunks: [emb 32 | per 8-channel block and octave f:
+    sin x 8, cos x 8 | dist: f*12 + (sin|cos)*6 + j | 4 x pad] (reference order: see layer1_column_order)."""
+    cols = list(range(32))
+    for cblk in range(4):
+        for f in range(3):
+            for sc in range(2):
+                for i in range(8):
+                    cols.append(32 + ((cblk * 8 + i) * 3 + f) * 2 + sc)
+    for idx in range(64):
+        if idx < 60:
+            f, rem = divmod(idx, 12)
+            sc, j = divmod(rem, 6)
+            cols.append(224 + (j * 5 + f) * 2 + sc)
+        else:
+            cols.append(-1)
+    assert len(cols) == 288 and sorted(c for c in cols if c >= 0) == list(range(284))
+    return cols
+
+
+def split_f16(x: torch.Tensor):
+    hi = x.half()
+    lo = (x - hi.float()).half()
+    return hi, lo
+
+
+def pack_layer_f16(W: torch.Tensor, cols: Optional[Sequence[int]] = None):
+    """W (256, K) fp32 -> (uint8 image of Kp/16 chunks, weight scale).  The weights are multiplied by a power of two
+    that brings max|w| just below 2^14, split into fp16 hi / lo and tiled per 16-column chunk as [hi 8 KB | lo 8 KB],
+    each part [k block (2)][row group (32)][row (8)][8 halves] = canonical no-swizzle K-major UMMA core matrices."""
+    W = W.detach().float()
+    assert W.shape[0] == 256
+    if cols is None:
+        Kp = (W.shape[1] + KC16 - 1) // KC16 * KC16
+        cols = list(range(W.shape[1])) + [-1] * (Kp - W.shape[1])
+    Wp = _permute_pad(W, cols).contiguous()
+    Kp = Wp.shape[1]
+    assert Kp % KC16 == 0
+    wmax = float(Wp.abs().max())
+    sw = 2.0 ** math.floor(math.log2(16384.0 / wmax)) if wmax > 0 else 1.0
+    hi, lo = split_f16(Wp * sw)
+    tile = lambda x: x.view(32, 8, Kp // KC16, 2, 8).permute(2, 3, 0, 1, 4)          # (C, 2, 32, 8, 8)
+    img = torch.stack([tile(hi), tile(lo)], dim=1).contiguous()                        # (C, 2[hi|lo], 2, 32, 8, 8)
+    return img.view(torch.uint8).reshape(-1), sw
+
+
+def pack_mlp_f16(block1, block3, act_scale: float = ACT_SCALE):
+    """-> (wpack uint8, bias (4,256) pre-scaled, mul [4] floats, scale0, scale2) for hnr_nbr_mlp_f16_forward"""
+    l2 = list(range(256, 263)) + [-1] * 9 + list(range(256))        # extras chunk first, then the 256 hidden columns
+    layers = [(block1[0], layer1_column_order_f16()), (block1[2], None), (block3[0], l2), (block3[2], None)]
+    parts, sws = [], []
+    for lin, cols in layers:
+        img, sw = pack_layer_f16(lin.weight, cols)
+        parts.append(img)
+        sws.append(sw)
+    wpack = torch.cat(parts).contiguous()
+    assert wpack.numel() == lib().hnr_nbr_mlp_f16_packed_bytes()
+    s_in = [act_scale] * 4
+    mul = [s_in[l + 1] / (s_in[l] * sws[l]) for l in range(3)] + [1.0 / (s_in[3] * sws[3])]
+    bias = torch.stack([lin.bias.detach().float() * (s_in[l + 1] if l < 3 else 1.0) for l, (lin, _) in enumerate(layers)]).contiguous()
+    return wpack, bias, mul, s_in[0], s_in[2]
+
+
+def forward_f16(tables, pidx, vlist, loc_w, loc_pers, raydirs, cam, weight, confc, pack, w_alpha, b_alpha, debug: bool = False):
+    """fused gather + per-neighbour MLP + density head + weighted K-sum (inference), 3xFP16 tensor-core kernel.
+    Returns sigma (Nv,1), X5 (Nv,280) [, dbg (4, Nv*8, 256) unscaled-by-mul activations when debug]."""
+    import ctypes as C
+    xyz, xyz_pers, emb, color, dirs, _ = tables
+    wpack, bias, mul, s0, s2 = pack
+    Nv, K = vlist.shape[0], pidx.shape[1]
+    sigma = torch.empty((Nv, 1), device=pidx.device, dtype=torch.float32)
+    X5 = torch.empty((Nv, 280), device=pidx.device, dtype=torch.float32)
+    dbg = torch.zeros((4, Nv * K, 256), device=pidx.device, dtype=torch.float32) if debug else None
+    wa = w_alpha.detach().float().contiguous().view(-1)
+    ba = b_alpha.detach().float().contiguous().view(-1)
+    mul_c = (C.c_float * 4)(*mul)
+    with ops._launch():
+        check(lib().hnr_nbr_mlp_f16_forward(ptr(xyz), ptr(xyz_pers), ptr(emb), ptr(color), ptr(dirs), ptr(pidx), ptr(vlist), ptr(loc_w),
+                                            ptr(loc_pers), ptr(raydirs), ptr(cam), ptr(weight), ptr(confc), ptr(wpack), ptr(bias), ptr(wa),
+                                            ptr(ba), mul_c, float(s0), float(s2), Nv, K, ptr(sigma), ptr(X5), ptr(dbg), stream()),
+              "nbr_mlp_f16_forward")
+    return (sigma, X5, dbg) if debug else (sigma, X5)

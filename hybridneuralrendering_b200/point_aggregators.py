@@ -126,8 +126,9 @@ class PointAggregator(nn.Module):
                   self.color_final_block):
             _init_seq(m)
         self.shading_patch_size = 1
-        # per-neighbour MLP engine for no-grad forwards: "tc" = fused tcgen05 3xTF32 kernel (mlp_tc.cu),
-        # "simt" = exact-fp32 layer kernels.  Forwards that record a graph always use the layer kernels.
+        # per-neighbour MLP engine for no-grad forwards: "tc" = fused tcgen05 3xFP16 kernel (nbr_mlp_f16.cu), "tc_tf32" = the
+        # first-generation 3xTF32 kernel (mlp_tc.cu), "simt" = exact-fp32 layer kernels.  Forwards that record a graph
+        # always use the layer kernels.
         self.mlp_engine = "tc"
         self.max_valid_chunk = 262144        # valid samples decoded per pass in no-grad mode (bounds activation memory)
 
@@ -218,13 +219,17 @@ class PointAggregator(nn.Module):
         b1, b3 = self.block1, self.block3
         # per-neighbour MLP engine: the fused tensor-core kernel for no-grad forwards; forwards that record a graph use
         # the layer kernels (their backward needs the saved activations)
-        use_tc = self.mlp_engine == "tc" and not torch.is_grad_enabled() and K == 8 and mask is None
+        use_tc = self.mlp_engine in ("tc", "tc_tf32") and not torch.is_grad_enabled() and K == 8 and mask is None
         if use_tc:
             from . import mlp_tc
-            wpack, bias = self._packed_weights()
+            pack = self._packed_weights()
             with ops.tag("nbr_mlp"):
-                sigma, X5 = mlp_tc.forward(tables, pidx, vlist, loc_w, loc_pers, raydirs, cam, weight, confc, wpack, bias,
-                                           self.alpha_branch[0].weight, self.alpha_branch[0].bias)
+                if self.mlp_engine == "tc":
+                    sigma, X5 = mlp_tc.forward_f16(tables, pidx, vlist, loc_w, loc_pers, raydirs, cam, weight, confc, pack,
+                                                   self.alpha_branch[0].weight, self.alpha_branch[0].bias)
+                else:
+                    sigma, X5 = mlp_tc.forward(tables, pidx, vlist, loc_w, loc_pers, raydirs, cam, weight, confc, pack[0], pack[1],
+                                               self.alpha_branch[0].weight, self.alpha_branch[0].bias)
         else:
             with ops.tag("gather"):
                 X0, E = ops.NbrFeaturesFn.apply(emb, color, dirs, xyz, xyz_pers, pidx, mask, vlist, loc_w, loc_pers, raydirs, cam)
@@ -271,12 +276,12 @@ class PointAggregator(nn.Module):
         """TF32 hi/lo images of block1/block3 for the tensor-core kernel, re-packed when a weight changes"""
         ps = [self.block1[0].weight, self.block1[2].weight, self.block3[0].weight, self.block3[2].weight,
               self.block1[0].bias, self.block1[2].bias, self.block3[0].bias, self.block3[2].bias]
-        key = tuple((p.data_ptr(), p._version) for p in ps)
+        key = (self.mlp_engine,) + tuple((p.data_ptr(), p._version) for p in ps)
         if getattr(self, "_pack_key", None) != key:
             from . import mlp_tc
-            self._pack = mlp_tc.pack_mlp(self.block1, self.block3)
+            self._wpack_cache = (mlp_tc.pack_mlp_f16 if self.mlp_engine == "tc" else mlp_tc.pack_mlp)(self.block1, self.block3)
             self._pack_key = key
-        return self._pack
+        return self._wpack_cache
 
     def last_valid_neighbours(self) -> int:
         """number of valid (sample, neighbour) pairs of the last call (profiling only; syncs)"""

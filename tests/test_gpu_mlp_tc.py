@@ -97,3 +97,25 @@ def test_linear_tc_shared_row_block_and_slices():
         y2 = ops.linear([gc[:, :45], gc[:, 45:90]], W2, None, 0, res=gc[:, :45])
     assert_close(y, ref, 1e-5, 2e-5)
     assert_close(y2, g[:, :90].double() @ W2.cpu().double().t() + g[:, :45].double(), 1e-5, 2e-5)
+
+
+@pytest.mark.parametrize("R,SR,empty", [(3, 5, 0.0), (64, 24, 0.4), (300, 80, 0.2)])
+def test_f16_kernel_layers_match_fp64(R, SR, empty):
+    """every layer of the 3xFP16 fused kernel (debug taps) against fp64 torch on the same gathered features:
+    fp32-level accuracy (rtol 1e-5 of the layer's scale), heads and K-sum included"""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
+    from debug_nbr_f16 import layer_errors
+    errs = layer_errors(R=R, SR=SR, empty=empty, seed=R + SR)
+    for name, (e, scale) in zip(["layer0", "layer1", "layer2", "layer3", "sigma", "ksum", "viewpe"], errs):
+        assert e <= 1e-5 * scale + 1e-7, (name, e, scale)
+
+
+def test_f16_packing_roundtrip():
+    from hybridneuralrendering_b200 import mlp_tc
+    W = (torch.arange(256 * 32, dtype=torch.float32).view(256, 32).cuda() - 4000.0) / 7000.0
+    img, sw = mlp_tc.pack_layer_f16(W)
+    t = img.view(torch.float16).view(2, 2, 2, 32, 8, 8).float()                  # (chunk, hi|lo, k block, row group, row, 8)
+    rec = (t[:, 0] + t[:, 1]).permute(2, 3, 0, 1, 4).reshape(256, 32) / sw
+    assert float((rec - W).abs().max()) <= 2.0 ** -21 * float(W.abs().max())
+    assert sorted(c for c in mlp_tc.layer1_column_order_f16() if c >= 0) == list(range(284))
