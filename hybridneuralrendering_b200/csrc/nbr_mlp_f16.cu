@@ -14,8 +14,10 @@
 //   * two TMEM accumulators (2 x 256 columns): the MMAs of layer l+1 start on the first K-chunks of the new
 //     activation while the epilogue of layer l is still draining the rest (per-32-column mbarriers), and the
 //     layer-0 MMAs of the NEXT tile run under the last epilogue + K-sum of the current tile;
-//   * warp roles: 4 epilogue warps (TMEM lane quarters), 4 generator warps (gather from the point tables, positional
-//     encodings, layer-0 operand chunks, one tile ahead), 1 MMA warp (one elected thread), 1 bulk-copy warp.
+//   * warp roles (4 warpgroups, registers re-balanced with setmaxnreg): 2 x 4 epilogue warps (each TMEM lane quarter is
+//     served by two warps that take alternate 32-column blocks), 4 generator warps (gather from the point tables,
+//     positional encodings, layer-0 operand chunks, one tile ahead), 1 MMA warp (one elected thread), 1 bulk-copy warp;
+//     waiting warps back off with nanosleep so that their polling does not take issue slots from the working ones.
 //
 // The arithmetic restated is models/aggregators/point_aggregators.py:921-972, :1002-1036 and
 // models/helpers/networks.py:175-189 of the reference.
@@ -42,7 +44,7 @@ constexpr int NLAYER = 4;
 constexpr int NC0 = 18, NC1 = 16, NC2 = 17, NC3 = 16;      // K chunks per layer (288, 256, 16 + 256, 256)
 constexpr int NCHUNK_TILE = NC0 + NC1 + NC2 + NC3;
 constexpr int FEAT = 32, NF_VIEW = 4, X5_W = 280;
-constexpr int NEPI = 128, NGEN = 128, NTHREADS = 320;
+constexpr int NEPI = 256, NTHREADS = 512;      // warps 0-7 epilogue, 8-11 generators, 12 MMA, 13 bulk copy, 14-15 idle
 
 // shared memory map (bytes)
 constexpr int OFF_W = 0;
@@ -52,7 +54,8 @@ constexpr int OFF_ACT = OFF_E + 2 * A_STAGE;               // 90112   hi | lo ; 
 constexpr int OFF_BIAS = OFF_ACT + 2 * ACT_PART;           // 221184  (4,256) fp32, pre-scaled
 constexpr int OFF_WALPHA = OFF_BIAS + NLAYER * HID * 4;    // 225280
 constexpr int OFF_WC = OFF_WALPHA + HID * 4;               // 226304  neighbour weight * conf, double buffered
-constexpr int OFF_BAR = OFF_WC + 2 * TM * 4;               // 227328
+constexpr int OFF_ARAW = OFF_WC + 2 * TM * 4;              // 227328  density-head partial dot products of the two epilogue groups
+constexpr int OFF_BAR = OFF_ARAW + 2 * TM * 4;             // 228352
 constexpr int NBAR = 2 * NSW + 2 * NSA + 2 + 8 + 2 + 1 + 1;
 constexpr int SMEM_BYTES = OFF_BAR + NBAR * 8 + 16;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
@@ -115,21 +118,46 @@ __device__ __forceinline__ void rot3(const float* m, float x, float y, float z, 
 }
 __device__ __forceinline__ float softplus_t(float x) { return x > 20.f ? x : log1pf(expf(x)); }
 
-// 8 fp32 values -> 8 fp16 hi (one 16-byte core-matrix row) and 8 fp16 lo.  Values beyond fp16's range saturate.
+// two fp32 -> packed fp16x2 {lo half = a, hi half = b}, round to nearest, saturating at +-65504 (an activation beyond fp16's
+// range would otherwise become inf and poison the accumulator with inf - inf)
+__device__ __forceinline__ uint32_t pack_sat(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+// 8 fp32 values -> 8 fp16 hi (one 16-byte core-matrix row) and 8 fp16 lo = fp16(v - hi)
 __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
     uint32_t h[4], l[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const float a = fminf(fmaxf(v[2 * i], -65000.f), 65000.f), b = fminf(fmaxf(v[2 * i + 1], -65000.f), 65000.f);
-        const __half2 hh = __floats2half2_rn(a, b);
-        const float2 hf = __half22float2(hh);
-        const __half2 ll = __floats2half2_rn(a - hf.x, b - hf.y);
-        h[i] = *reinterpret_cast<const uint32_t*>(&hh);
-        l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+        const float a = v[2 * i], b = v[2 * i + 1];
+        h[i] = pack_sat(a, b);
+        const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&h[i]));
+        l[i] = pack_sat(a - hf.x, b - hf.y);
     }
     hi = make_uint4(h[0], h[1], h[2], h[3]);
     lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
+
+// mbarrier wait for warps that are ahead of the pipeline anyway: poll, then sleep between polls
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, unsigned ns) {
+    uint32_t done;
+    for (;;) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) break;
+        __nanosleep(ns);
+    }
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
 // store one 16-wide K chunk of row r (already scaled) into an operand stage: [hi: kb0 | kb1][lo: kb0 | kb1]
 __device__ __forceinline__ void store_chunk16(uint8_t* stage, int r, const float* v) {
@@ -142,6 +170,7 @@ __device__ __forceinline__ void store_chunk16(uint8_t* stage, int r, const float
     *reinterpret_cast<uint4*>(stage + A_PART + A_LBO + r * 16) = lo;
 }
 
+template <bool DBG>
 __global__ void __launch_bounds__(NTHREADS, 1) nbr_mlp_f16_kernel(F16Args A) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -154,6 +183,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nbr_mlp_f16_kernel(F16Args A) {
     float* bias_s = reinterpret_cast<float*>(smem + OFF_BIAS);
     float* walpha_s = reinterpret_cast<float*>(smem + OFF_WALPHA);
     float* wc_s = reinterpret_cast<float*>(smem + OFF_WC);
+    float* araw_s = reinterpret_cast<float*>(smem + OFF_ARAW);
 
     const int64_t total_rows = A.Nv * 8;
     const int64_t ntiles = (total_rows + TM - 1) / TM;
@@ -163,11 +193,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) nbr_mlp_f16_kernel(F16Args A) {
         for (int s = 0; s < NSA; ++s) { mbar_init(bar_afull + 8 * s, 4); mbar_init(bar_aempty + 8 * s, 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(bar_efull + 8 * s, 4); mbar_init(bar_accfull + 8 * s, 1); }
         for (int s = 0; s < 8; ++s) mbar_init(bar_actfull + 8 * s, 4);
-        mbar_init(bar_accempty0, 4);
-        mbar_init(bar_tiledone, 4);
+        mbar_init(bar_accempty0, 8);
+        mbar_init(bar_tiledone, 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 8) tmem_alloc(smem_u32(tmem_slot), 512);
+    if (warp == 12) tmem_alloc(smem_u32(tmem_slot), 512);
     for (int i = tid; i < NLAYER * HID; i += NTHREADS) bias_s[i] = A.bias[i];
     if (tid < HID) walpha_s[tid] = A.walpha[tid];
     tc_fence_before();
@@ -175,22 +205,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) nbr_mlp_f16_kernel(F16Args A) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 9) {
-        // ================= bulk-copy producer: one 16 KB weight chunk image per stage =================
-        if (lane == 0) {
+    if (warp >= 12) {
+        setmaxnreg_dec<40>();
+        if (warp == 13 && lane == 0) {
+            // ================= bulk-copy producer: one 16 KB weight chunk image per stage =================
             uint32_t it = 0;
             for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 for (int c = 0; c < NCHUNK_TILE; ++c, ++it) {
                     const uint32_t s = it % NSW, ph = (it / NSW) & 1;
-                    mbar_wait(bar_wempty + 8 * s, ph ^ 1);
+                    mbar_wait_relaxed(bar_wempty + 8 * s, ph ^ 1, 64);
                     mbar_arrive_expect_tx(bar_wfull + 8 * s, W_STAGE);
                     bulk_g2s(smem_u32(smem + OFF_W + s * W_STAGE), A.wpack + (size_t)c * W_STAGE, W_STAGE, bar_wfull + 8 * s);
                 }
             }
-        }
-    } else if (warp == 8) {
-        // ================= MMA issuer: one thread, 3 MMAs (3xFP16) per K chunk =================
-        if (lane == 0) {
+        } else if (warp == 12 && lane == 0) {
+            // ================= MMA issuer: one thread, 3 MMAs (3xFP16) per K chunk =================
             uint32_t wit = 0, ait = 0, gen = 0, ti = 0;
             const uint32_t act_hi = smem_u32(smem + OFF_ACT), act_lo = act_hi + ACT_PART;
             auto issue = [&](uint32_t acc, uint32_t a_hi_addr, uint32_t a_lo_addr, bool first) {
@@ -212,7 +241,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nbr_mlp_f16_kernel(F16Args A) {
                 if (ti > 0) mbar_wait(bar_accempty0, (ti - 1) & 1);
                 for (int c = 0; c < NC0; ++c, ++ait) {
                     const uint32_t s = ait % NSA, ph = (ait / NSA) & 1;
-                    mbar_wait(bar_afull + 8 * s, ph);
+                    mbar_wait_relaxed(bar_afull + 8 * s, ph, 20);
                     const uint32_t a = smem_u32(smem + OFF_A + s * A_STAGE);
                     issue(acc0, a, a + A_PART, c == 0);
                     tc_commit(bar_aempty + 8 * s);
@@ -220,7 +249,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nbr_mlp_f16_kernel(F16Args A) {
                 tc_commit(bar_accfull);
                 // ---- layer 1: operands = activation written by epilogue 0, released per 32 columns
                 for (int c = 0; c < NC1; ++c) {
-                    if ((c & 1) == 0) mbar_wait(bar_actfull + 8 * (c >> 1), gen & 1);
+                    if ((c & 1) == 0) mbar_wait_relaxed(bar_actfull + 8 * (c >> 1), gen & 1, 20);
                     issue(acc1, act_hi + c * 2 * A_LBO, act_lo + c * 2 * A_LBO, c == 0);
                 }
                 tc_commit(bar_accfull + 8);
@@ -233,26 +262,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) nbr_mlp_f16_kernel(F16Args A) {
                     issue(acc0, e, e + A_PART, true);
                 }
                 for (int c = 0; c < NC1; ++c) {
-                    if ((c & 1) == 0) mbar_wait(bar_actfull + 8 * (c >> 1), gen & 1);
+                    if ((c & 1) == 0) mbar_wait_relaxed(bar_actfull + 8 * (c >> 1), gen & 1, 20);
                     issue(acc0, act_hi + c * 2 * A_LBO, act_lo + c * 2 * A_LBO, false);
                 }
                 tc_commit(bar_accfull);
                 ++gen;
                 // ---- layer 3
                 for (int c = 0; c < NC3; ++c) {
-                    if ((c & 1) == 0) mbar_wait(bar_actfull + 8 * (c >> 1), gen & 1);
+                    if ((c & 1) == 0) mbar_wait_relaxed(bar_actfull + 8 * (c >> 1), gen & 1, 20);
                     issue(acc1, act_hi + c * 2 * A_LBO, act_lo + c * 2 * A_LBO, c == 0);
                 }
                 tc_commit(bar_accfull + 8);
                 ++gen;
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp >= 8) {
         // ================= generators: gather + layer-0 operand chunks, thread = row =================
+        setmaxnreg_inc<200>();
         const int r = tid - NEPI;
         uint32_t ait = 0, ti = 0;
         const float* rt = A.cam + 12;
-        // indices of the first tile
         int64_t s_cur = 0, g_cur = 0;
         bool live_cur = false;
         auto load_idx = [&](int64_t tile, int64_t& s, int64_t& g, bool& live) {
@@ -315,7 +344,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nbr_mlp_f16_kernel(F16Args A) {
             // ---- block3 extras chunk + row weight (buffers of tile parity p; last read by tile ti-2) ----
             {
                 const uint32_t p = ti & 1;
-                if (ti >= 2) mbar_wait(bar_tiledone, ti & 1);
+                if (ti >= 2) mbar_wait_relaxed(bar_tiledone, ti & 1, 128);
                 float ev[16];
                 ev[0] = c0; ev[1] = c1; ev[2] = c2; ev[3] = rx - vx; ev[4] = ry - vy; ev[5] = rz - vz; ev[6] = rx * vx + ry * vy + rz * vz;
 #pragma unroll
@@ -334,22 +363,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) nbr_mlp_f16_kernel(F16Args A) {
             const float sc0 = A.scale0;
             float pe[64], sn[32], cs[32];
 #pragma unroll
-            for (int f = 0; f < 5; ++f) {                  // encoded distances: idx = f*12 + (sin|cos)*6 + component
-#pragma unroll
-                for (int j = 0; j < 6; ++j) {
-                    float a, b;
-                    sincosf(d[j] * (float)(1 << f), &a, &b);
-                    pe[f * 12 + j] = a * sc0;
-                    pe[f * 12 + 6 + j] = b * sc0;
-                }
+            for (int j = 0; j < 6; ++j) {                  // encoded distances: idx = f*12 + (sin|cos)*6 + component
+                float a, b;                                // octaves 0 and 2 evaluated directly, 1, 3, 4 by angle doubling
+                sincosf(d[j], &a, &b);
+                pe[j] = a; pe[6 + j] = b;
+                pe[12 + j] = 2.f * a * b; pe[18 + j] = 1.f - 2.f * a * a;
+                sincosf(d[j] * 4.f, &a, &b);
+                pe[24 + j] = a; pe[30 + j] = b;
+                float a2 = 2.f * a * b, b2 = 1.f - 2.f * a * a;
+                pe[36 + j] = a2; pe[42 + j] = b2;
+                pe[48 + j] = 2.f * a2 * b2; pe[54 + j] = 1.f - 2.f * a2 * a2;
             }
+#pragma unroll
+            for (int i = 0; i < 60; ++i) pe[i] *= sc0;
             pe[60] = pe[61] = pe[62] = pe[63] = 0.f;
 #pragma unroll
             for (int i = 0; i < 32; ++i) sincosf(ef[i], &sn[i], &cs[i]);
             auto put = [&](const float* v) {
                 const uint32_t st = ait % NSA, ph = (ait / NSA) & 1;
                 ++ait;
-                mbar_wait(bar_aempty + 8 * st, ph ^ 1);
+                mbar_wait_relaxed(bar_aempty + 8 * st, ph ^ 1, 32);
                 store_chunk16(smem + OFF_A + st * A_STAGE, r, v);
                 fence_proxy_async();
                 __syncwarp();
@@ -386,38 +419,44 @@ __global__ void __launch_bounds__(NTHREADS, 1) nbr_mlp_f16_kernel(F16Args A) {
             for (int c = 0; c < 4; ++c) put(pe + c * 16);
         }
     } else {
-        // ================= epilogue warps: thread = row = TMEM lane =================
-        const int r = tid;                                     // 0..127, warp w owns TMEM lanes 32w..32w+31
-        const uint32_t lane_base = (uint32_t)(32 * warp) << 16;
+        // ================= epilogue warps: thread = (row = TMEM lane, group wg taking 32-column blocks wg, wg+2, ...) =================
+        setmaxnreg_inc<136>();
+        const int wg = warp >> 2;                              // 0 | 1
+        const int r = tid & (TM - 1);                          // warps w and w+4 own TMEM lanes 32(w&3)..+31
+        const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
         uint8_t* act_hi = smem + OFF_ACT;
         float* stage = reinterpret_cast<float*>(smem + OFF_ACT);
-        uint32_t gen = 0, ti = 0;
+        uint32_t ti = 0;
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
             const int64_t row0 = tile * TM;
 #pragma unroll 1
             for (int l = 0; l < NLAYER; ++l) {
                 const uint32_t b = l & 1;
-                mbar_wait(bar_accfull + 8 * b, (l >> 1) & 1);          // each accumulator completes twice per tile
+                mbar_wait_relaxed(bar_accfull + 8 * b, (l >> 1) & 1, 20);     // each accumulator completes twice per tile
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + lane_base + b * HID;
+                const uint32_t taddr = tmem_base + lane_base + b * HID + wg * 32;
                 const float mul = A.mul[l];
-                const float* bl = bias_s + l * HID;
+                const float4* bl4 = reinterpret_cast<const float4*>(bias_s + l * HID + wg * 32);
+                uint32_t va[32], vb[32];
+                tmem_ld32_issue(taddr, va);
                 if (l < NLAYER - 1) {
-                    uint32_t va[32], vb[32];
-                    tmem_ld32_issue(taddr, va);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        uint32_t(&cur)[32] = (j & 1) ? vb : va;
-                        uint32_t(&nxt)[32] = (j & 1) ? va : vb;
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int j = 2 * jj + wg;                     // column block
+                        uint32_t(&cur)[32] = (jj & 1) ? vb : va;
+                        uint32_t(&nxt)[32] = (jj & 1) ? va : vb;
                         tmem_ld_wait(cur);
-                        if (j + 1 < 8) tmem_ld32_issue(taddr + (j + 1) * 32, nxt);
+                        if (jj + 1 < 4) tmem_ld32_issue(taddr + (jj + 1) * 64, nxt);
                         float y[32];
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const float t = fmaf(__uint_as_float(cur[i]), mul, bl[j * 32 + i]);
-                            y[i] = fmaxf(t, 0.01f * t);
+                        for (int i4 = 0; i4 < 8; ++i4) {
+                            const float4 bb = bl4[jj * 16 + i4];
+                            const float t0 = fmaf(__uint_as_float(cur[4 * i4 + 0]), mul, bb.x), t1 = fmaf(__uint_as_float(cur[4 * i4 + 1]), mul, bb.y);
+                            const float t2 = fmaf(__uint_as_float(cur[4 * i4 + 2]), mul, bb.z), t3 = fmaf(__uint_as_float(cur[4 * i4 + 3]), mul, bb.w);
+                            y[4 * i4 + 0] = fmaxf(t0, 0.01f * t0); y[4 * i4 + 1] = fmaxf(t1, 0.01f * t1);
+                            y[4 * i4 + 2] = fmaxf(t2, 0.01f * t2); y[4 * i4 + 3] = fmaxf(t3, 0.01f * t3);
                         }
-                        if (A.dbg) {
+                        if (DBG) {
                             const int64_t row = row0 + r;
                             if (row < total_rows) {
                                 float* o = A.dbg + ((int64_t)l * total_rows + row) * HID + j * 32;
@@ -437,7 +476,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) nbr_mlp_f16_kernel(F16Args A) {
                         __syncwarp();
                         if (lane == 0) mbar_arrive(bar_actfull + 8 * j);
                     }
-                    ++gen;
                     if (l == 2) {           // accumulator 0 drained: layer 0 of the next tile may overwrite it
                         tc_fence_before();
                         __syncwarp();
@@ -446,52 +484,62 @@ __global__ void __launch_bounds__(NTHREADS, 1) nbr_mlp_f16_kernel(F16Args A) {
                 } else {
                     // ---- last layer: density head, row weight, fp32 staging for the K-sum ----
                     const uint32_t p = ti & 1;
-                    mbar_wait(bar_efull + 8 * p, (ti >> 1) & 1);       // makes the generator's wc_s of this tile visible
+                    mbar_wait_relaxed(bar_efull + 8 * p, (ti >> 1) & 1, 20);   // makes the generator's wc_s of this tile visible
                     const float wrow = wc_s[p * TM + r];
+                    const float4* wa4 = reinterpret_cast<const float4*>(walpha_s + wg * 32);
                     float dot = 0.f;
-                    uint32_t va[32], vb[32];
-                    tmem_ld32_issue(taddr, va);
+                    // staging: element (col,row) at col*128 + ((row/4) ^ (col%32))*4 + row%4  (conflict-free for the row-wise
+                    // writes here and for the column-wise float4 reads of the K-sum)
+                    float* srow = stage + (r & 3);
+                    const int rg = r >> 2;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        uint32_t(&cur)[32] = (j & 1) ? vb : va;
-                        uint32_t(&nxt)[32] = (j & 1) ? va : vb;
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int j = 2 * jj + wg;
+                        uint32_t(&cur)[32] = (jj & 1) ? vb : va;
+                        uint32_t(&nxt)[32] = (jj & 1) ? va : vb;
                         tmem_ld_wait(cur);
-                        if (j + 1 < 8) tmem_ld32_issue(taddr + (j + 1) * 32, nxt);
+                        if (jj + 1 < 4) tmem_ld32_issue(taddr + (jj + 1) * 64, nxt);
+                        float* sblk = srow + j * 32 * TM;
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const int col = j * 32 + i;
-                            float t = fmaf(__uint_as_float(cur[i]), mul, bl[col]);
-                            t = fmaxf(t, 0.01f * t);
-                            if (A.dbg && row0 + r < total_rows) A.dbg[((int64_t)l * total_rows + row0 + r) * HID + col] = t;
-                            dot = fmaf(t, walpha_s[col], dot);
-                            // staging: element (col,row) at col*128 + ((row/4 + col) % 32)*4 + row%4 (conflict-free both ways)
-                            stage[col * TM + (((r >> 2) + col) & 31) * 4 + (r & 3)] = t * wrow;
+                        for (int i4 = 0; i4 < 8; ++i4) {
+                            const float4 bb = bl4[jj * 16 + i4], ww = wa4[jj * 16 + i4];
+                            const float bv[4] = {bb.x, bb.y, bb.z, bb.w}, wv[4] = {ww.x, ww.y, ww.z, ww.w};
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const int i = 4 * i4 + u;
+                                float t = fmaf(__uint_as_float(cur[i]), mul, bv[u]);
+                                t = fmaxf(t, 0.01f * t);
+                                if (DBG && row0 + r < total_rows) A.dbg[((int64_t)l * total_rows + row0 + r) * HID + j * 32 + i] = t;
+                                dot = fmaf(t, wv[u], dot);
+                                sblk[i * TM + ((rg ^ i) << 2)] = t * wrow;
+                            }
                         }
                     }
-                    float sg = wrow * softplus_t(dot + A.balpha[0] - 1.f);
-                    sg += __shfl_xor_sync(0xffffffffu, sg, 1);
-                    sg += __shfl_xor_sync(0xffffffffu, sg, 2);
-                    sg += __shfl_xor_sync(0xffffffffu, sg, 4);
-                    const int64_t v = (row0 + r) >> 3;
-                    if ((r & 7) == 0 && v < A.Nv) A.sigma[v] = sg;
+                    araw_s[wg * TM + r] = dot;
                     tc_fence_before();
                     named_barrier<1, NEPI>();
-                    // ---- weighted K-sum: thread = column (r and r+128), 16 samples ----
-                    const int64_t v0 = row0 >> 3;
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int col = r + h * TM;
+                    if (wg == 0) {
+                        float sg = wrow * softplus_t(araw_s[r] + araw_s[TM + r] + A.balpha[0] - 1.f);
+                        sg += __shfl_xor_sync(0xffffffffu, sg, 1);
+                        sg += __shfl_xor_sync(0xffffffffu, sg, 2);
+                        sg += __shfl_xor_sync(0xffffffffu, sg, 4);
+                        const int64_t v = (row0 + r) >> 3;
+                        if ((r & 7) == 0 && v < A.Nv) A.sigma[v] = sg;
+                    }
+                    // ---- weighted K-sum: thread = column, 16 samples ----
+                    {
+                        const int64_t v0 = row0 >> 3;
+                        const int col = wg * TM + r, cl = col & 31;
                         const float* sc = stage + col * TM;
 #pragma unroll 4
                         for (int si = 0; si < 16; ++si) {
-                            const float4 a = *reinterpret_cast<const float4*>(sc + ((2 * si + col) & 31) * 4);
-                            const float4 bq = *reinterpret_cast<const float4*>(sc + ((2 * si + 1 + col) & 31) * 4);
+                            const float4 a = *reinterpret_cast<const float4*>(sc + (((2 * si) ^ cl) << 2));
+                            const float4 bq = *reinterpret_cast<const float4*>(sc + (((2 * si + 1) ^ cl) << 2));
                             const float sum = ((a.x + a.y) + (a.z + a.w)) + ((bq.x + bq.y) + (bq.z + bq.w));
                             if (v0 + si < A.Nv) A.X5[(v0 + si) * X5_W + col] = sum;
                         }
                     }
                     named_barrier<1, NEPI>();           // staging consumed: epilogue 0 of the next tile may write the activation
-                    __syncwarp();
                     if (lane == 0) mbar_arrive(bar_tiledone);
                 }
             }
@@ -499,7 +547,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nbr_mlp_f16_kernel(F16Args A) {
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) tmem_dealloc(tmem_base, 512);
+    if (warp == 12) tmem_dealloc(tmem_base, 512);
 }
 
 }  // namespace
@@ -526,12 +574,14 @@ extern "C" int hnr_nbr_mlp_f16_forward(const float* xyz, const float* xyz_pers, 
     A.scale0 = scale0; A.scale2 = scale2;
     static bool configured = false;
     if (!configured) {
-        HNR_CUDA(cudaFuncSetAttribute(nbr_mlp_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        HNR_CUDA(cudaFuncSetAttribute(nbr_mlp_f16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        HNR_CUDA(cudaFuncSetAttribute(nbr_mlp_f16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         configured = true;
     }
     const int64_t ntiles = hnr_cdiv(Nv * 8, TM);
     const int grid = (int)(ntiles < HNR_NUM_SMS ? ntiles : HNR_NUM_SMS);
-    nbr_mlp_f16_kernel<<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(A);
+    if (dbg) nbr_mlp_f16_kernel<true><<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(A);
+    else nbr_mlp_f16_kernel<false><<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(A);
     HNR_CHECK_LAUNCH("nbr_mlp_f16_forward");
     return HNR_OK;
 }
