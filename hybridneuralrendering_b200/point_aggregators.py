@@ -26,7 +26,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops
-from .ops import ACT_COLOR, ACT_LRELU, ACT_NONE, ACT_SIGMOID
+from .ops import ACT_COLOR, ACT_LRELU, ACT_NONE, ACT_SIGMOID, X5_W
 
 
 def drop_patch_rays(patch_size, patch_num, drop_ratio):
@@ -241,22 +241,34 @@ class PointAggregator(nn.Module):
             with ops.tag("ksum"):
                 sigma, X5 = ops.AlphaKSumFn.apply(h, confc, self.alpha_branch[0].weight, self.alpha_branch[0].bias, weight, vlist, raydirs, cam)
         cf = self.color_feature_branch
-        with ops.tag("sample_mlp"):
-            g = ops.linear([X5], cf[0].weight, cf[0].bias, ACT_LRELU)
-            g = ops.linear([g], cf[2].weight, cf[2].bias, ACT_LRELU)
-            g = ops.linear([g], cf[4].weight, cf[4].bias, ACT_LRELU)
         V = int(opt.use_nearest)
+        # per-sample MLPs: fused tensor-core chains (chain_f16.cu) for no-grad forwards, layer kernels otherwise
+        fused = self.mlp_engine == "tc" and not torch.is_grad_enabled()
+        if fused:
+            from . import chain
+            with ops.tag("sample_mlp"):
+                pc = chain.packed_chain(self, "cf", [cf[0], cf[2], cf[4]], [ACT_LRELU] * 3, X5_W)
+                g = chain.chain_forward(pc, [X5])[0]
+        else:
+            with ops.tag("sample_mlp"):
+                g = ops.linear([X5], cf[0].weight, cf[0].bias, ACT_LRELU)
+                g = ops.linear([g], cf[2].weight, cf[2].bias, ACT_LRELU)
+                g = ops.linear([g], cf[4].weight, cf[4].bias, ACT_LRELU)
         if V > 0:
             with ops.tag("image_gather"):
                 aux, ok = ops.ImageGatherFn.apply(levels[0], levels[1], levels[2], levels[3], xy, vlist)
             dv = delta.reshape(V, S, 3).index_select(1, vlist.long()).reshape(V * Nv, 3)
             am = self.aux_merge_weight_block
             with ops.tag("sample_mlp"):
-                t = ops.linear([aux.view(V * Nv, 45), g, dv], am[0].weight, am[0].bias, ACT_LRELU, mods=(0, Nv, 0), M=V * Nv)
-                t = ops.linear([t], am[2].weight, am[2].bias, ACT_LRELU)
-                if not torch.is_grad_enabled() and ops.LINEAR_ENGINE == "tc" and V * Nv >= 128:
-                    sig = ops.linear_head([t], am[4].weight, am[4].bias, ACT_LRELU, am[6].weight, am[6].bias, ACT_SIGMOID)
+                if fused:
+                    # kernel source order [g | aux | dview] (the 128-wide block first keeps its chunks 16-byte aligned)
+                    pc = chain.packed_chain(self, "am", [am[0], am[2], am[4]], [ACT_LRELU] * 3, 176,
+                                            cols0=list(range(45, 173)) + list(range(45)) + [173, 174, 175])
+                    sig = chain.chain_forward(pc, [g, aux.view(V * Nv, 45), dv], M=V * Nv, mods=(Nv, 0, 0), out=False,
+                                              head=(am[6].weight, am[6].bias, ACT_SIGMOID))[1]
                 else:
+                    t = ops.linear([aux.view(V * Nv, 45), g, dv], am[0].weight, am[0].bias, ACT_LRELU, mods=(0, Nv, 0), M=V * Nv)
+                    t = ops.linear([t], am[2].weight, am[2].bias, ACT_LRELU)
                     t = ops.linear([t], am[4].weight, am[4].bias, ACT_LRELU)
                     sig = ops.linear([t], am[6].weight, am[6].bias, ACT_SIGMOID)
             with ops.tag("blend"):
@@ -266,9 +278,13 @@ class PointAggregator(nn.Module):
         gi, gv = g[:, :45], g[:, 45:]
         cm = self.color_mixup_block
         with ops.tag("sample_mlp"):
-            m = ops.linear([gi, merged], cm[0].weight, cm[0].bias, ACT_LRELU)
-            m = ops.linear([m], cm[2].weight, cm[2].bias, ACT_LRELU)
-            m = ops.linear([m], cm[4].weight, cm[4].bias, ACT_NONE, res=gi)
+            if fused:
+                pc = chain.packed_chain(self, "cm", [cm[0], cm[2], cm[4]], [ACT_LRELU, ACT_LRELU, ACT_NONE], 90)
+                m = chain.chain_forward(pc, [gi, merged], res=gi)[0]
+            else:
+                m = ops.linear([gi, merged], cm[0].weight, cm[0].bias, ACT_LRELU)
+                m = ops.linear([m], cm[2].weight, cm[2].bias, ACT_LRELU)
+                m = ops.linear([m], cm[4].weight, cm[4].bias, ACT_NONE, res=gi)
             rgb = ops.linear([m, gv], self.color_final_block[0].weight, self.color_final_block[0].bias, ACT_COLOR)
         return torch.cat([sigma, rgb], dim=-1)
 

@@ -159,6 +159,19 @@ int hnr_nbr_mlp_f16_forward(const float* xyz, const float* xyz_pers, const float
                             float scale0, float scale2, int64_t Nv, int64_t K, float* sigma /* Nv */, float* X5 /* Nv,280 */,
                             float* dbg, void* stream);
 
+/* Fused chain of up to 4 dense layers (widths <= 128) on tcgen05, 3xFP16 split (csrc/chain_f16.cu): the per-sample MLPs
+ * color_feature_branch, aux_merge_weight_block (+ sigmoid head), color_mixup_block (+ residual) of
+ * point_aggregators.py:556-683 in one launch each, activations resident in shared memory between layers.
+ * src/src_ld/src_k/src_mod: up to 3 concatenated fp32 sources (as hnr_linear_fwd).  Per-layer arrays have nlayer
+ * entries: Kp (padded K), N, Np (N padded to 16), act, w_off (byte offset into wpack), mul, inv_next, Y (fp32 output of
+ * the layer or NULL), ldy.  wpack/bias/mul/inv_next are built by hybridneuralrendering_b200/chain.py. */
+int64_t hnr_chain_f16_chunk_bytes(int64_t Np);
+int hnr_chain_f16_forward(const float* const* src, const int64_t* src_ld, const int64_t* src_k, const int64_t* src_mod, float in_scale,
+                          int nlayer, const int64_t* Kp, const int64_t* N, const int64_t* Np, const int* act, const void* wpack,
+                          const int64_t* w_off, const float* bias /* 4,128 */, const float* mul, const float* inv_next,
+                          float* const* Y, const int64_t* ldy, const float* res, int64_t ldres, const float* head_w,
+                          const float* head_b, int head_act, float* head_out /* M */, int64_t M, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Compositing: neural_points_volumetric_model.py:331-339 + models/rendering/diff_ray_marching.py:508-557
  * ------------------------------------------------------------------------------------------- */

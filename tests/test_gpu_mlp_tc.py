@@ -119,3 +119,48 @@ def test_f16_packing_roundtrip():
     rec = (t[:, 0] + t[:, 1]).permute(2, 3, 0, 1, 4).reshape(256, 32) / sw
     assert float((rec - W).abs().max()) <= 2.0 ** -21 * float(W.abs().max())
     assert sorted(c for c in mlp_tc.layer1_column_order_f16() if c >= 0) == list(range(284))
+
+
+@pytest.mark.parametrize("M,ks,widths,acts,mods,res,head", [
+    (1000, (280,), (128, 128, 128), (1, 1, 1), None, False, False),            # colour-feature branch
+    (4 * 777, (128, 45, 3), (64, 64, 64), (1, 1, 1), (777, 0, 0), False, True),   # blend-weight net + sigmoid head, V=4
+    (5000, (45, 45), (45, 45, 45), (1, 1, 0), None, True, False),              # mix-up block + residual
+    (130, (16,), (16,), (0,), None, False, False),
+    (128 * 300 + 7, (128,), (128, 64), (1, 2), None, False, False),
+])
+def test_chain_f16_matches_fp64(M, ks, widths, acts, mods, res, head):
+    """fused tensor-core chains (3xFP16) vs fp64 torch: concat sources, row re-use, padded widths, residual, head"""
+    from hybridneuralrendering_b200 import chain
+    rng = np.random.default_rng(M)
+    K = sum(ks)
+    nrows = [mods[i] if mods and mods[i] else M for i in range(len(ks))]
+    srcs = [T(rng.standard_normal((nrows[i], k)).astype(np.float32)).cuda() for i, k in enumerate(ks)]
+    layers, kin = [], K
+    for w in widths:
+        lin = torch.nn.Linear(kin, w).cuda()
+        with torch.no_grad():
+            lin.weight.copy_(T((rng.standard_normal((w, kin)) * (1.5 / np.sqrt(kin))).astype(np.float32)))
+            lin.bias.copy_(T((rng.standard_normal(w) * 0.1).astype(np.float32)))
+        layers.append(lin)
+        kin = w
+    x = torch.cat([s.double() if s.shape[0] == M else s.double().repeat(M // s.shape[0], 1) for s in srcs], 1)
+    inner = []
+    for lin, a in zip(layers, acts):
+        x = torch.nn.functional.linear(x, lin.weight.double(), lin.bias.double())
+        x = [x, torch.nn.functional.leaky_relu(x, 0.01), torch.sigmoid(x)][a]
+        inner.append(x)
+    resv = srcs[0][:, :widths[-1]] if res else None
+    if res:
+        x = x + resv.double()
+    hw = hb = None
+    if head:
+        hw, hb = T((rng.standard_normal((1, widths[-1])) * 0.3).astype(np.float32)).cuda(), T(np.array([0.1], np.float32)).cuda()
+        href = torch.sigmoid(x @ hw.double().t() + hb.double())
+    pc = chain.PackedChain(layers, acts, K)
+    with torch.no_grad():
+        y, h, ys = chain.chain_forward(pc, srcs, M=M, mods=mods or (), res=resv, head=(hw, hb, 2) if head else None, keep_inner=True)
+    assert_close(y, x, 1e-5, 2e-5)
+    for a, b in zip(ys, inner[:-1]):
+        assert_close(a, b, 1e-5, 2e-5)
+    if head:
+        assert_close(h, href, 1e-5, 2e-5)
