@@ -61,6 +61,7 @@ _SIGS = {
     "hnr_mlp_tc_forward": (C.c_int, [vp] * 17 + [i64, i64, vp, vp, vp]),
     "hnr_nbr_mlp_f16_packed_bytes": (i64, []),
     "hnr_chain_f16_chunk_bytes": (i64, [i64]),
+    "hnr_chain_f16_set_trace": (None, [vp]),
     "hnr_chain_f16_forward": (C.c_int, [C.POINTER(vp), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), f32c, C.c_int, C.POINTER(i64),
                                         C.POINTER(i64), C.POINTER(i64), C.POINTER(C.c_int), vp, C.POINTER(i64), vp, C.POINTER(f32c),
                                         C.POINTER(f32c), C.POINTER(vp), C.POINTER(i64), vp, i64, vp, vp, C.c_int, vp, i64, vp]),

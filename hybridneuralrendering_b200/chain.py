@@ -120,6 +120,7 @@ def chain_forward(pc: PackedChain, srcs: Sequence[torch.Tensor], M: Optional[int
     if head is not None:
         hw, hb, hact = ops._f32c(head[0]).view(-1), ops._f32c(head[1]).view(-1), int(head[2])
         assert hw.numel() == pc.N[nl - 1]
+        hw = torch.nn.functional.pad(hw.detach(), (0, NMAX - hw.numel())).contiguous()      # the kernel reads whole 32-column blocks
         head_out = torch.empty((M, 1), device=dev, dtype=torch.float32)
     resv = ops._rows2d(res) if res is not None else None
     f4 = lambda v: (C.c_float * len(v))(*v)

@@ -8,7 +8,7 @@
 //   out = x_nlayer (+ residual)  and / or  head_act(x_nlayer . head_w + head_b)
 //
 // One launch runs the whole chain; the activations between layers never leave the SM:
-//   * a tile is 128 rows; two CTAs are resident per SM (256 threads, 2 x 128 TMEM columns each) so that one tile's
+//   * a tile is 128 rows; two CTAs are resident per SM (320 threads, 2 x 128 TMEM columns each) so that one tile's
 //     epilogue overlaps the other's MMAs across the serial layer dependency;
 //   * operands are split fp16 hi/lo (pre-multiplied by a power-of-two scale); a*w ~= a_hi*w_hi + a_lo*w_hi + a_hi*w_lo
 //     with three tcgen05.mma.kind::f16 into one fp32 TMEM accumulator (22 mantissa bits);
@@ -16,9 +16,11 @@
 //     no-swizzle K-major UMMA layout; layers >= 1: the epilogue of layer l writes layer l+1's A operand directly in
 //     that layout (hi+lo fp16 = the 4 bytes of the fp32 value) and releases it to the MMA warp per 32 columns;
 //   * weights come pre-split / pre-tiled from the host (chain.py), one cp.async.bulk per 16-wide K chunk;
-//   * warp roles: 4 epilogue warps (thread = row = TMEM lane), 2 generator warps, 1 MMA warp, 1 bulk-copy warp.
+//   * warp roles: 4 epilogue warps (thread = row = TMEM lane), 4 generator warps (thread = row, three K chunks of
+//     loads in flight: the chains are bound by reading their inputs), 1 MMA warp, 1 bulk-copy warp.
 // Optional fp32 copies of every layer's output (Y_l) make the same kernel usable as the forward of a training step.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "hnr.h"
@@ -31,20 +33,18 @@ constexpr int TM = 128;
 constexpr int NMAX = 128;               // widest layer == TMEM columns per accumulator
 constexpr int KC = 16;
 constexpr int MAXL = 4;
-constexpr int NSW = 2, NSA = 3;
+constexpr int NSW = 4, NSA = 2;
 constexpr int W_STAGE = 2 * NMAX * KC * 2;   // 8192
 constexpr int A_PART = TM * KC * 2;          // 4096
 constexpr int A_STAGE = 2 * A_PART;          // 8192
 constexpr int ACT_PART = TM * NMAX * 2;      // 32768
-constexpr int NTHREADS = 256;
-constexpr int NGEN = 64;
+constexpr int NTHREADS = 320;            // warps 0-3 epilogue, 4-7 generators, 8 MMA, 9 bulk copy
+constexpr int GEN_DEPTH = 3;             // K chunks a generator thread keeps in flight (registers)
 
 constexpr int OFF_W = 0;
-constexpr int OFF_A = OFF_W + NSW * W_STAGE;           // 16384
-constexpr int OFF_ACT = OFF_A + NSA * A_STAGE;         // 40960
-constexpr int OFF_BIAS = OFF_ACT + 2 * ACT_PART;       // 106496
-constexpr int OFF_HEAD = OFF_BIAS + MAXL * NMAX * 4;   // 108544
-constexpr int OFF_BAR = OFF_HEAD + NMAX * 4;           // 109056
+constexpr int OFF_A = OFF_W + NSW * W_STAGE;           // 32768
+constexpr int OFF_ACT = OFF_A + NSA * A_STAGE;         // 49152
+constexpr int OFF_BAR = OFF_ACT + 2 * ACT_PART;        // 114688 (bias / head weights are read through the read-only cache)
 constexpr int NBAR = 2 * NSW + 2 * NSA + 4 + 2 + 2;
 constexpr int SMEM_BYTES = OFF_BAR + NBAR * 8 + 16;
 static_assert(2 * (SMEM_BYTES + 1024) <= 227 * 1024, "two CTAs per SM");
@@ -71,6 +71,8 @@ struct ChainArgs {
     int head_act;
     float* head_out;
     int64_t M;
+    int wait_mode;
+    long long* trace;            // optional event trace of CTA 0 (bring-up / profiling): [count, (clock, id, a, b) ...]
 };
 
 __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
@@ -80,27 +82,6 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uin
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
-}
-__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
-                   "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]),
-                   "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]),
-                   "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
-                 :
-                 : "memory");
 }
 __device__ __forceinline__ uint32_t pack_sat(float a, float b) {
     uint32_t r;
@@ -119,33 +100,57 @@ __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
     hi = make_uint4(h[0], h[1], h[2], h[3]);
     lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
-__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, unsigned ns) {
+// wait policy experiment: mode 0 = plain polling, 1 = nanosleep between polls, 2 = try_wait with a suspend-time hint
+__device__ __forceinline__ void mbar_wait_mode(uint32_t bar, uint32_t parity, unsigned ns, int mode) {
     uint32_t done;
     for (;;) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
+        if (mode == 2) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(bar), "r"(parity), "r"(ns)
+                : "memory");
+        } else {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(bar), "r"(parity)
+                : "memory");
+        }
         if (done) break;
-        __nanosleep(ns);
+        if (mode == 1) __nanosleep(ns);
     }
 }
+#define mbar_wait_relaxed(bar, parity, ns) mbar_wait_mode(bar, parity, ns, A.wait_mode)
+// light-weight event trace of CTA 0 (profiling aid): each traced thread appends (clock64, tag) pairs to its own region
+constexpr int TRACE_CAP = 4096;
+#define TRACE_DECL(role) long long* tr__ = (A.trace && blockIdx.x == 0) ? A.trace + (role) * 2 * TRACE_CAP : nullptr; int trn__ = 0
+#define TRACE(id, a, b)                                                                          \
+    do {                                                                                         \
+        if (tr__ && trn__ < TRACE_CAP) {                                                         \
+            tr__[2 * trn__] = clock64();                                                         \
+            tr__[2 * trn__ + 1] = ((long long)(id) << 32) | ((long long)(a) << 16) | (long long)(b); \
+            ++trn__;                                                                             \
+        }                                                                                        \
+    } while (0)
+
 __host__ __device__ constexpr uint32_t idesc_f16(int N) {   // D=f32, A=B=f16, both K-major, M=128
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 }
 
-// 16 consecutive columns [c0, c0+16) of row m of the concatenated layer-0 input (zero beyond the last column)
-__device__ __forceinline__ void load_chunk(const ChainArgs& A, int64_t m, int c0, float (&v)[16]) {
+// 16 consecutive columns [c0, c0+16) of one row of the concatenated layer-0 input (zero beyond the last column);
+// rp[s] = pointer to the row's first element in source s
+__device__ __forceinline__ void load_chunk(const ChainArgs& A, const float* const (&rp)[3], int c0, float (&v)[16]) {
     int base = 0;
 #pragma unroll
     for (int s = 0; s < 3; ++s) {
         const int ks = A.k[s];
         if (ks > 0 && c0 >= base && c0 + 16 <= base + ks) {             // whole chunk inside source s
-            const int64_t row = A.mod[s] > 0 ? m % A.mod[s] : m;
-            const float* p = A.src[s] + row * A.ld[s] + (c0 - base);
+            const float* p = rp[s] + (c0 - base);
             if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -166,12 +171,7 @@ __device__ __forceinline__ void load_chunk(const ChainArgs& A, int64_t m, int c0
     for (int i = 0; i < 16; ++i) {
         const int c = c0 + i;
         float x = 0.f;
-        if (c < b3) {
-            const int s = c < b1 ? 0 : (c < b2 ? 1 : 2);
-            const int off = c - (s == 0 ? 0 : (s == 1 ? b1 : b2));
-            const int64_t row = A.mod[s] > 0 ? m % A.mod[s] : m;
-            x = __ldg(A.src[s] + row * A.ld[s] + off);
-        }
+        if (c < b3) x = c < b1 ? __ldg(rp[0] + c) : (c < b2 ? __ldg(rp[1] + (c - b1)) : __ldg(rp[2] + (c - b2)));
         v[i] = x;
     }
 }
@@ -184,54 +184,53 @@ __global__ void __launch_bounds__(NTHREADS, 2) chain_f16_kernel(const __grid_con
     const uint32_t bar_wfull = b0, bar_wempty = b0 + 8 * NSW, bar_afull = bar_wempty + 8 * NSW, bar_aempty = bar_afull + 8 * NSA,
                    bar_actfull = bar_aempty + 8 * NSA, bar_accfull = bar_actfull + 32, bar_accfree = bar_accfull + 16;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBAR);
-    float* bias_s = reinterpret_cast<float*>(smem + OFF_BIAS);
-    float* head_s = reinterpret_cast<float*>(smem + OFF_HEAD);
     const int64_t ntiles = (A.M + TM - 1) / TM;
     const int nl = A.nlayer;
 
     if (tid == 0) {
         for (int s = 0; s < NSW; ++s) { mbar_init(bar_wfull + 8 * s, 1); mbar_init(bar_wempty + 8 * s, 1); }
-        for (int s = 0; s < NSA; ++s) { mbar_init(bar_afull + 8 * s, 2); mbar_init(bar_aempty + 8 * s, 1); }
+        for (int s = 0; s < NSA; ++s) { mbar_init(bar_afull + 8 * s, 4); mbar_init(bar_aempty + 8 * s, 1); }
         for (int s = 0; s < 4; ++s) mbar_init(bar_actfull + 8 * s, 4);
         for (int s = 0; s < 2; ++s) { mbar_init(bar_accfull + 8 * s, 1); mbar_init(bar_accfree + 8 * s, 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 6) tmem_alloc(smem_u32(tmem_slot), 2 * NMAX);
-    for (int i = tid; i < MAXL * NMAX; i += NTHREADS) bias_s[i] = A.bias[i];
-    if (tid < NMAX) head_s[tid] = (A.head_w && tid < A.N[nl - 1]) ? A.head_w[tid] : 0.f;
+    if (warp == 8) tmem_alloc(smem_u32(tmem_slot), 2 * NMAX);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 7) {
-        // ================= bulk-copy producer: one weight chunk image (Np*64 bytes) per stage =================
+    if (warp == 9) {
+        // ================= bulk-copy producer: one stage = as many whole weight chunks (Np*64 bytes each) as fit in 8 KB =================
         if (lane == 0) {
             uint32_t it = 0;
             for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 for (int l = 0; l < nl; ++l) {
-                    const uint32_t bytes = (uint32_t)A.Np[l] * 64u;
+                    const uint32_t cbytes = (uint32_t)A.Np[l] * 64u;
+                    const int cps = W_STAGE / (int)cbytes;             // chunks per stage
                     const uint8_t* src = A.wpack + A.w_off[l];
                     const int nc = A.Kp[l] / KC;
-                    for (int c = 0; c < nc; ++c, ++it) {
+                    for (int c = 0; c < nc; c += cps, ++it) {
                         const uint32_t s = it % NSW, ph = (it / NSW) & 1;
-                        mbar_wait_relaxed(bar_wempty + 8 * s, ph ^ 1, 64);
+                        const uint32_t bytes = (uint32_t)min(cps, nc - c) * cbytes;
+                        mbar_wait_relaxed(bar_wempty + 8 * s, ph ^ 1, 32);
                         mbar_arrive_expect_tx(bar_wfull + 8 * s, bytes);
-                        bulk_g2s(smem_u32(smem + OFF_W + s * W_STAGE), src + (size_t)c * bytes, bytes, bar_wfull + 8 * s);
+                        bulk_g2s(smem_u32(smem + OFF_W + s * W_STAGE), src + (size_t)c * cbytes, bytes, bar_wfull + 8 * s);
                     }
                 }
             }
         }
-    } else if (warp == 6) {
+    } else if (warp == 8) {
         // ================= MMA issuer =================
         if (lane == 0) {
             uint32_t wit = 0, ait = 0, use[2] = {0, 0}, actcnt[4] = {0, 0, 0, 0};
+            TRACE_DECL(0);
             const uint32_t act_hi = smem_u32(smem + OFF_ACT), act_lo = act_hi + ACT_PART;
             for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 for (int l = 0; l < nl; ++l) {
                     const uint32_t b = l & 1, acc = tmem_base + b * NMAX;
                     const uint32_t np = (uint32_t)A.Np[l], idesc = idesc_f16((int)np), w_lbo = (np / 8) * 128, w_part = np * 32;
-                    const int nc = A.Kp[l] / KC;
+                    const int nc = A.Kp[l] / KC, cps = W_STAGE / (int)(np * 64u);
                     if (use[b] > 0) mbar_wait_relaxed(bar_accfree + 8 * b, (use[b] - 1) & 1, 20);   // previous reader of this accumulator done
                     ++use[b];
                     for (int c = 0; c < nc; ++c) {
@@ -251,75 +250,91 @@ __global__ void __launch_bounds__(NTHREADS, 2) chain_f16_kernel(const __grid_con
                             a_hi_addr = act_hi + c * 2 * A_LBO;
                             a_lo_addr = act_lo + c * 2 * A_LBO;
                         }
-                        const uint32_t s = wit % NSW, ph = (wit / NSW) & 1;
-                        ++wit;
-                        mbar_wait(bar_wfull + 8 * s, ph);
+                        TRACE(1, l, c);                                 // operand ready
+                        const int sub = c % cps;                       // chunk within the weight stage
+                        const uint32_t s = wit % NSW;
+                        if (sub == 0) {
+                            mbar_wait(bar_wfull + 8 * s, (wit / NSW) & 1);
+                        }
                         tc_fence_after();
-                        const uint32_t w = smem_u32(smem + OFF_W + s * W_STAGE);
+                        const uint32_t w = smem_u32(smem + OFF_W + s * W_STAGE) + (uint32_t)sub * (np * 64u);
                         const uint64_t w_hi = umma_desc(w, w_lbo, SBO), w_lo = umma_desc(w + w_part, w_lbo, SBO);
                         const uint64_t a_hi = umma_desc(a_hi_addr, A_LBO, SBO), a_lo = umma_desc(a_lo_addr, A_LBO, SBO);
                         tc_mma_f16(acc, a_hi, w_hi, idesc, c > 0 ? 1u : 0u);
                         tc_mma_f16(acc, a_lo, w_hi, idesc, 1u);
                         tc_mma_f16(acc, a_hi, w_lo, idesc, 1u);
-                        tc_commit(bar_wempty + 8 * s);
+                        if (sub == cps - 1 || c == nc - 1) {
+                            tc_commit(bar_wempty + 8 * s);
+                            ++wit;
+                        }
                         if (l == 0) tc_commit(bar_aempty + 8 * as);
+                        TRACE(2, l, c);                                 // MMAs issued
                     }
                     tc_commit(bar_accfull + 8 * b);
                 }
             }
         }
     } else if (warp >= 4) {
-        // ================= generators: fp32 source rows -> split fp16 operand chunks (thread = 2 rows) =================
-        const int g = tid - 128;                         // 0..63
+        // ================= generators: fp32 source rows -> split fp16 operand chunks (thread = row) =================
+        const int r = tid - 128;                         // 0..127
+        TRACE_DECL(1);
+        if (r != 0) tr__ = nullptr;
         const int nc0 = A.Kp[0] / KC;
         const float sc = A.in_scale;
         uint32_t ait = 0;
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const int64_t m0 = tile * TM + g, m1 = m0 + 64;
-            const bool ok0 = m0 < A.M, ok1 = m1 < A.M;
-            float va[16], vb[16], na[16], nb[16];
+            const int64_t m = tile * TM + r;
+            const bool ok = m < A.M;
+            const float* rp[3];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) { va[i] = vb[i] = 0.f; }
-            if (ok0) load_chunk(A, m0, 0, va);
-            if (ok1) load_chunk(A, m1, 0, vb);
-            for (int c = 0; c < nc0; ++c) {
+            for (int s = 0; s < 3; ++s) {
+                const int64_t rr = ok ? (A.mod[s] > 0 ? m % A.mod[s] : m) : 0;
+                rp[s] = A.src[s] + rr * A.ld[s];
+            }
+            float buf[GEN_DEPTH][16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) { na[i] = nb[i] = 0.f; }
-                if (c + 1 < nc0) {                       // next chunk's loads in flight while this one is converted
-                    if (ok0) load_chunk(A, m0, (c + 1) * KC, na);
-                    if (ok1) load_chunk(A, m1, (c + 1) * KC, nb);
+            for (int d = 0; d < GEN_DEPTH; ++d) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) buf[d][i] = 0.f;
+                if (ok && d < nc0) load_chunk(A, rp, d * KC, buf[d]);
+            }
+            for (int c = 0; c < nc0; c += GEN_DEPTH) {
+#pragma unroll
+                for (int d = 0; d < GEN_DEPTH; ++d) {
+                    if (c + d < nc0) {
+                        const uint32_t st = ait % NSA, ph = (ait / NSA) & 1;
+                        ++ait;
+                        float v[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = buf[d][i] * sc;
+                        if (ok && c + d + GEN_DEPTH < nc0) load_chunk(A, rp, (c + d + GEN_DEPTH) * KC, buf[d]);   // refill: stays in flight
+                        if (__float_as_int(v[0]) != 0x7fc12345) TRACE(10, c + d, 0);      // data arrived (forces the load)
+                        mbar_wait_relaxed(bar_aempty + 8 * st, ph ^ 1, 32);
+                        TRACE(11, c + d, 0);                                       // stage free
+                        uint8_t* stage = smem + OFF_A + st * A_STAGE;
+                        uint4 hi, lo;
+                        split8(v, hi, lo);
+                        *reinterpret_cast<uint4*>(stage + r * 16) = hi;
+                        *reinterpret_cast<uint4*>(stage + A_PART + r * 16) = lo;
+                        split8(v + 8, hi, lo);
+                        *reinterpret_cast<uint4*>(stage + A_LBO + r * 16) = hi;
+                        *reinterpret_cast<uint4*>(stage + A_PART + A_LBO + r * 16) = lo;
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_afull + 8 * st);
+                        TRACE(12, c + d, 0);                                       // delivered
+                    }
                 }
-                const uint32_t st = ait % NSA, ph = (ait / NSA) & 1;
-                ++ait;
-                mbar_wait_relaxed(bar_aempty + 8 * st, ph ^ 1, 32);
-                uint8_t* stage = smem + OFF_A + st * A_STAGE;
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    float* v = h ? vb : va;
-                    const int r = g + 64 * h;
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] *= sc;
-                    uint4 hi, lo;
-                    split8(v, hi, lo);
-                    *reinterpret_cast<uint4*>(stage + r * 16) = hi;
-                    *reinterpret_cast<uint4*>(stage + A_PART + r * 16) = lo;
-                    split8(v + 8, hi, lo);
-                    *reinterpret_cast<uint4*>(stage + A_LBO + r * 16) = hi;
-                    *reinterpret_cast<uint4*>(stage + A_PART + A_LBO + r * 16) = lo;
-                }
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_afull + 8 * st);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) { va[i] = na[i]; vb[i] = nb[i]; }
             }
         }
     } else {
-        // ================= epilogue warps: thread = row = TMEM lane =================
+        // ================= epilogue warps: thread = row = TMEM lane, 16 columns per step =================
         const int r = tid;
         const uint32_t lane_base = (uint32_t)(32 * warp) << 16;
         uint8_t* act_hi = smem + OFF_ACT;
         uint32_t use[2] = {0, 0};
+        TRACE_DECL(2);
+        if (r != 0) tr__ = nullptr;
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int64_t m = tile * TM + r;
             const bool live = m < A.M;
@@ -329,92 +344,83 @@ __global__ void __launch_bounds__(NTHREADS, 2) chain_f16_kernel(const __grid_con
                 mbar_wait_relaxed(bar_accfull + 8 * b, use[b] & 1, 20);
                 ++use[b];
                 tc_fence_after();
+                TRACE(20, l, 0);                                                    // accumulator complete
                 const uint32_t taddr = tmem_base + lane_base + b * NMAX;
                 const int np = A.Np[l], n = A.N[l], act = A.act[l];
-                const int nblk = (np + 31) >> 5;
                 const bool last = (l == nl - 1);
                 const float mul = A.mul[l], inv_next = A.inv_next[l];
-                const float* bl = bias_s + l * NMAX;
+                const float* bl = A.bias + l * NMAX;
                 float* yout = A.Y[l];
                 const int ldy = A.ldy[l];
+                const bool yvec = yout && (ldy & 3) == 0 && (reinterpret_cast<uintptr_t>(yout) & 15) == 0;
                 float dot = 0.f;
-                uint32_t va[32], vb[32];
-                tmem_ld32_issue(taddr, va);
+#pragma unroll 1
+                for (int c0 = 0; c0 < np; c0 += 16) {
+                    float y[16];
+                    tmem_ld16(taddr + c0, y);
+                    TRACE(21, l, c0);                                               // TMEM load done
+                    const float4* b4 = reinterpret_cast<const float4*>(bl + c0);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (j < nblk) {
-                        uint32_t(&cur)[32] = (j & 1) ? vb : va;
-                        uint32_t(&nxt)[32] = (j & 1) ? va : vb;
-                        tmem_ld_wait(cur);
-                        if (j + 1 < nblk) tmem_ld32_issue(taddr + (j + 1) * 32, nxt);
-                        float y[32];
-                        const float4* b4 = reinterpret_cast<const float4*>(bl + j * 32);
+                    for (int i4 = 0; i4 < 4; ++i4) {
+                        const float4 bb = __ldg(b4 + i4);
+                        y[4 * i4 + 0] = fmaf(y[4 * i4 + 0], mul, bb.x);
+                        y[4 * i4 + 1] = fmaf(y[4 * i4 + 1], mul, bb.y);
+                        y[4 * i4 + 2] = fmaf(y[4 * i4 + 2], mul, bb.z);
+                        y[4 * i4 + 3] = fmaf(y[4 * i4 + 3], mul, bb.w);
+                    }
+                    if (act == HNR_ACT_LRELU) {
 #pragma unroll
-                        for (int i4 = 0; i4 < 8; ++i4) {
-                            const float4 bb = b4[i4];
-                            y[4 * i4 + 0] = fmaf(__uint_as_float(cur[4 * i4 + 0]), mul, bb.x);
-                            y[4 * i4 + 1] = fmaf(__uint_as_float(cur[4 * i4 + 1]), mul, bb.y);
-                            y[4 * i4 + 2] = fmaf(__uint_as_float(cur[4 * i4 + 2]), mul, bb.z);
-                            y[4 * i4 + 3] = fmaf(__uint_as_float(cur[4 * i4 + 3]), mul, bb.w);
+                        for (int i = 0; i < 16; ++i) y[i] = fmaxf(y[i], 0.01f * y[i]);
+                    } else if (act != HNR_ACT_NONE) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) y[i] = apply_act(y[i], act);
+                    }
+                    if (last) {
+                        if (A.res && live) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                if (c0 + i < n) y[i] += __ldg(A.res + m * A.ldres + c0 + i);
                         }
-                        if (act == HNR_ACT_LRELU) {
+                        if (A.head_w) {
+                            const float4* h4 = reinterpret_cast<const float4*>(A.head_w + c0);      // zero padded to 128 by the host
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) y[i] = fmaxf(y[i], 0.01f * y[i]);
-                        } else if (act != HNR_ACT_NONE) {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) y[i] = apply_act(y[i], act);
-                        }
-                        if (np - j * 32 < 32) {                       // columns beyond Np were never written by the MMA
-#pragma unroll
-                            for (int i = 16; i < 32; ++i) y[i] = 0.f;
-                        }
-                        if (last) {
-                            if (A.res && live) {
-#pragma unroll
-                                for (int i = 0; i < 32; ++i)
-                                    if (j * 32 + i < n) y[i] += __ldg(A.res + m * A.ldres + j * 32 + i);
-                            }
-                            if (A.head_w) {
-                                const float4* h4 = reinterpret_cast<const float4*>(head_s + j * 32);
-#pragma unroll
-                                for (int i4 = 0; i4 < 8; ++i4) {
-                                    const float4 hh = h4[i4];
-                                    dot = fmaf(y[4 * i4 + 0], hh.x, dot); dot = fmaf(y[4 * i4 + 1], hh.y, dot);
-                                    dot = fmaf(y[4 * i4 + 2], hh.z, dot); dot = fmaf(y[4 * i4 + 3], hh.w, dot);
-                                }
+                            for (int i4 = 0; i4 < 4; ++i4) {
+                                const float4 hh = __ldg(h4 + i4);
+                                dot = fmaf(y[4 * i4 + 0], hh.x, dot); dot = fmaf(y[4 * i4 + 1], hh.y, dot);
+                                dot = fmaf(y[4 * i4 + 2], hh.z, dot); dot = fmaf(y[4 * i4 + 3], hh.w, dot);
                             }
                         }
-                        if (yout && live) {
-                            float* o = yout + m * ldy + j * 32;
-                            if ((ldy & 3) == 0 && (reinterpret_cast<uintptr_t>(yout) & 15) == 0 && j * 32 + 32 <= n) {
+                    }
+                    if (yout && live) {
+                        float* o = yout + m * ldy + c0;
+                        if (yvec && c0 + 16 <= n) {
 #pragma unroll
-                                for (int i4 = 0; i4 < 8; ++i4)
-                                    reinterpret_cast<float4*>(o)[i4] = make_float4(y[4 * i4] * inv_next, y[4 * i4 + 1] * inv_next,
-                                                                                   y[4 * i4 + 2] * inv_next, y[4 * i4 + 3] * inv_next);
-                            } else {
+                            for (int i4 = 0; i4 < 4; ++i4)
+                                reinterpret_cast<float4*>(o)[i4] = make_float4(y[4 * i4] * inv_next, y[4 * i4 + 1] * inv_next,
+                                                                               y[4 * i4 + 2] * inv_next, y[4 * i4 + 3] * inv_next);
+                        } else {
 #pragma unroll
-                                for (int i = 0; i < 32; ++i)
-                                    if (j * 32 + i < n) o[i] = y[i] * inv_next;
-                            }
+                            for (int i = 0; i < 16; ++i)
+                                if (c0 + i < n) o[i] = y[i] * inv_next;
                         }
-                        if (!last) {
-                            const int nkb = min(4, (np - j * 32) >> 3);       // 8-column k-blocks of this block that exist
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                if (q < nkb) {
-                                    uint4 hi, lo;
-                                    split8(y + q * 8, hi, lo);
-                                    uint8_t* dst = act_hi + (j * 4 + q) * A_LBO + r * 16;
-                                    *reinterpret_cast<uint4*>(dst) = hi;
-                                    *reinterpret_cast<uint4*>(dst + ACT_PART) = lo;
-                                }
-                            }
+                    }
+                    if (!last) {
+                        uint4 hi, lo;
+                        uint8_t* dst = act_hi + (c0 >> 3) * A_LBO + r * 16;
+                        split8(y, hi, lo);
+                        *reinterpret_cast<uint4*>(dst) = hi;
+                        *reinterpret_cast<uint4*>(dst + ACT_PART) = lo;
+                        split8(y + 8, hi, lo);
+                        *reinterpret_cast<uint4*>(dst + A_LBO) = hi;
+                        *reinterpret_cast<uint4*>(dst + A_LBO + ACT_PART) = lo;
+                        if ((c0 & 16) || c0 + 16 >= np) {            // a 32-column block (or the tail) is complete: release it to the MMA warp
                             fence_proxy_async();
                             __syncwarp();
-                            if (lane == 0) mbar_arrive(bar_actfull + 8 * j);
+                            if (lane == 0) mbar_arrive(bar_actfull + 8 * (c0 >> 5));
                         }
                     }
                 }
+                TRACE(22, l, 0);                                                    // epilogue of the layer done
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_accfree + 8 * b);
@@ -424,12 +430,16 @@ __global__ void __launch_bounds__(NTHREADS, 2) chain_f16_kernel(const __grid_con
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 6) tmem_dealloc(tmem_base, 2 * NMAX);
+    if (warp == 8) tmem_dealloc(tmem_base, 2 * NMAX);
 }
 
 }  // namespace
 
 extern "C" int64_t hnr_chain_f16_chunk_bytes(int64_t Np) { return Np * 64; }
+
+// profiling aid: device buffer (>= 1 + 4*8000 int64) that CTA 0 of the next launches fills with (clock, event, a, b); NULL = off
+static long long* g_chain_trace = nullptr;
+extern "C" void hnr_chain_f16_set_trace(void* buf) { g_chain_trace = (long long*)buf; }
 
 // Fused chain of up to 4 dense layers (widths <= 128) over M rows, 3xFP16 on tcgen05 (see the header of this file).
 // Arrays have nlayer entries.  Kp[0] = concat width padded to 16, Kp[l] = Np[l-1]; Np = N padded to 16.
@@ -461,6 +471,8 @@ extern "C" int hnr_chain_f16_forward(const float* const* src, const int64_t* src
     HNR_CHECK_ARG(!head_w || (head_b && head_out), "chain_f16_forward: head needs head_b and head_out");
     A.in_scale = in_scale; A.nlayer = nlayer; A.wpack = (const uint8_t*)wpack; A.bias = bias; A.res = res; A.ldres = (int)ldres;
     A.head_w = head_w; A.head_b = head_b; A.head_act = head_act; A.head_out = head_out; A.M = M;
+    { const char* e = getenv("HNR_WAIT_MODE"); A.wait_mode = e ? atoi(e) : 1; }
+    A.trace = g_chain_trace;
     static bool configured = false;
     if (!configured) {
         HNR_CUDA(cudaFuncSetAttribute(chain_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));

@@ -209,6 +209,39 @@ template <typename PP> bool cat_ok(PP p, const int64_t* ld, const int64_t* k, in
 
 }  // namespace
 
+// N <= 4 outputs (density / colour heads): a GEMM tile would waste 60 of its 64 columns.  One warp per row: the lanes
+// stride over the concatenated K (coalesced 128-byte reads), W lives in shared memory, warp-shuffle reduction.
+constexpr int SMALLN_MAXK = 512;
+__global__ void __launch_bounds__(256) linear_fwd_smalln_kernel(Cat3 A, const float* __restrict__ W, const float* __restrict__ bias,
+                                                                 const float* __restrict__ res, int ldres, float* __restrict__ Y, int ldy,
+                                                                 int64_t M, int N, int K, int act) {
+    __shared__ float Ws[4 * SMALLN_MAXK];
+    for (int i = threadIdx.x; i < N * K; i += blockDim.x) Ws[i] = W[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int b1 = A.k[0], b2 = A.k[0] + A.k[1];
+    for (int64_t m = warp0; m < M; m += nwarps) {
+        const float* r0 = A.p[0] + (A.mod[0] > 0 ? m % A.mod[0] : m) * A.ld[0];
+        const float* r1 = A.k[1] > 0 ? A.p[1] + (A.mod[1] > 0 ? m % A.mod[1] : m) * A.ld[1] : nullptr;
+        const float* r2 = A.k[2] > 0 ? A.p[2] + (A.mod[2] > 0 ? m % A.mod[2] : m) * A.ld[2] : nullptr;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int k = lane; k < K; k += 32) {
+            const float x = k < b1 ? r0[k] : (k < b2 ? r1[k - b1] : r2[k - b2]);
+#pragma unroll
+            for (int n = 0; n < 4; ++n)
+                if (n < N) acc[n] = fmaf(x, Ws[n * K + k], acc[n]);
+        }
+#pragma unroll
+        for (int n = 0; n < 4; ++n) acc[n] = warp_sum(acc[n]);
+        if (lane < N) {
+            float y = apply_act((lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3]) + (bias ? bias[lane] : 0.f), act);
+            if (res) y += res[m * ldres + lane];
+            Y[m * ldy + lane] = y;
+        }
+    }
+}
+
 extern "C" int hnr_linear_fwd(const float* const* a_ptr, const int64_t* a_ld, const int64_t* a_k, const int64_t* a_mod, const float* W, const float* bias,
                               const float* res, int64_t ldres, float* Y, int64_t ldy, int64_t M, int64_t N, int64_t K, int act,
                               void* stream) {
@@ -218,6 +251,13 @@ extern "C" int hnr_linear_fwd(const float* const* a_ptr, const int64_t* a_ld, co
     Cat3 A;
     for (int i = 0; i < 3; ++i) { A.p[i] = a_ptr[i]; A.ld[i] = (int)a_ld[i]; A.k[i] = (int)a_k[i]; A.mod[i] = a_mod ? a_mod[i] : 0; }
     HNR_CHECK_ARG(!(res && act != HNR_ACT_NONE), "linear_fwd: residual only with act=none");
+    if (N <= 4 && K <= SMALLN_MAXK) {
+        const int64_t blocks = hnr_cdiv(M, 8);
+        const int g = (int)(blocks < 16 * HNR_NUM_SMS ? blocks : 16 * HNR_NUM_SMS);
+        linear_fwd_smalln_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(A, W, bias, res, (int)ldres, Y, (int)ldy, M, (int)N, (int)K, act);
+        HNR_CHECK_LAUNCH("linear_fwd(small N)");
+        return HNR_OK;
+    }
     dim3 grid((unsigned)hnr_cdiv(M, BM), (unsigned)hnr_cdiv(N, BN));
     linear_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A, W, bias, res, (int)ldres, Y, (int)ldy, M, (int)N, (int)K, act);
     HNR_CHECK_LAUNCH("linear_fwd");

@@ -166,6 +166,9 @@ int hnr_nbr_mlp_f16_forward(const float* xyz, const float* xyz_pers, const float
  * entries: Kp (padded K), N, Np (N padded to 16), act, w_off (byte offset into wpack), mul, inv_next, Y (fp32 output of
  * the layer or NULL), ldy.  wpack/bias/mul/inv_next are built by hybridneuralrendering_b200/chain.py. */
 int64_t hnr_chain_f16_chunk_bytes(int64_t Np);
+/* profiling aid: CTA 0 of the following chain launches records (clock64, event, a, b) quadruples into buf
+ * (int64[3][4096][2]: per role MMA / generator / epilogue, pairs (clock, id<<32 | a<<16 | b)); NULL switches it off */
+void hnr_chain_f16_set_trace(void* buf);
 int hnr_chain_f16_forward(const float* const* src, const int64_t* src_ld, const int64_t* src_k, const int64_t* src_mod, float in_scale,
                           int nlayer, const int64_t* Kp, const int64_t* N, const int64_t* Np, const int* act, const void* wpack,
                           const int64_t* w_off, const float* bias /* 4,128 */, const float* mul, const float* inv_next,
