@@ -56,6 +56,8 @@ struct LArgs {
     const float* head_b;
     float* out_head;
     int head_act;
+    const float* gateY;      // backward-data mode: the A operand is dY * act'(gateY) (gateY = the layer's saved output)
+    int ldgate, gate_act;
     float* Y;
     int64_t M;
     int ldres, ldy;
@@ -70,7 +72,7 @@ __device__ __forceinline__ float src_load(const Src& a, int64_t m, int k) {
 }
 
 // four consecutive K elements of row m starting at k0 (zero beyond K / M)
-__device__ __forceinline__ float4 load4(const LArgs& L, int64_t m, int k0) {
+__device__ __forceinline__ float4 load4_raw(const LArgs& L, int64_t m, int k0) {
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (m >= L.M || k0 >= L.K) return v;
     // fast path: the group lies inside one source and is 16-byte aligned
@@ -87,6 +89,23 @@ __device__ __forceinline__ float4 load4(const LArgs& L, int64_t m, int k0) {
     if (k0 + 1 < L.K) v.y = src_load(L.A, m, k0 + 1);
     if (k0 + 2 < L.K) v.z = src_load(L.A, m, k0 + 2);
     if (k0 + 3 < L.K) v.w = src_load(L.A, m, k0 + 3);
+    return v;
+}
+__device__ __forceinline__ float4 load4(const LArgs& L, int64_t m, int k0) {
+    float4 v = load4_raw(L, m, k0);
+    if (L.gateY && m < L.M && k0 < L.K) {
+        const float* g = L.gateY + m * L.ldgate + k0;
+        if (k0 + 4 <= L.K && (reinterpret_cast<uintptr_t>(g) & 15) == 0) {
+            const float4 y = __ldg(reinterpret_cast<const float4*>(g));
+            v.x *= act_grad_from_out(y.x, L.gate_act); v.y *= act_grad_from_out(y.y, L.gate_act);
+            v.z *= act_grad_from_out(y.z, L.gate_act); v.w *= act_grad_from_out(y.w, L.gate_act);
+            return v;
+        }
+        v.x *= act_grad_from_out(__ldg(g), L.gate_act);
+        if (k0 + 1 < L.K) v.y *= act_grad_from_out(__ldg(g + 1), L.gate_act);
+        if (k0 + 2 < L.K) v.z *= act_grad_from_out(__ldg(g + 2), L.gate_act);
+        if (k0 + 3 < L.K) v.w *= act_grad_from_out(__ldg(g + 3), L.gate_act);
+    }
     return v;
 }
 
@@ -294,5 +313,32 @@ extern "C" int hnr_linear_tc_fwd(const float* const* a_ptr, const int64_t* a_ld,
     const int grid = (int)(ntiles < HNR_NUM_SMS ? ntiles : HNR_NUM_SMS);
     linear_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(L);
     HNR_CHECK_LAUNCH("linear_tc_fwd");
+    return HNR_OK;
+}
+
+// Backward w.r.t. the layer input on tensor cores: dX (M, K) = (dY * act'(Y)) (M, N) . W (N, K).
+// wpackT: image (hnr_linear_tc_packed_bytes(Kpad, Np)) of W^T zero-padded to (Kpad % 16 == 0 <= 256 output columns,
+// Np % 8 == 0 >= N reduction columns); a layer with more than 256 inputs is handled by the caller as two column
+// slices.  dX has row stride lddx; only its first Kout columns are written.
+extern "C" int hnr_linear_tc_bwd_data(const float* dY, int64_t lddy, const float* Y, int64_t ldy, int act, const void* wpackT,
+                                      int64_t Kpad, int64_t Np, float* dX, int64_t lddx, int64_t M, int64_t N, int64_t Kout,
+                                      void* stream) {
+    if (M == 0) return HNR_OK;
+    HNR_CHECK_ARG(Kpad % 16 == 0 && Kpad >= 16 && Kpad <= 256 && Kout <= Kpad, "linear_tc_bwd_data: at most 256 output columns per call");
+    HNR_CHECK_ARG(Np % KC == 0 && N <= Np && N > 0, "linear_tc_bwd_data: Np must be a multiple of 8 and >= N");
+    LArgs L{};
+    L.A.p[0] = dY; L.A.ld[0] = (int)lddy; L.A.k[0] = (int)N;
+    L.gateY = (act == HNR_ACT_NONE) ? nullptr : Y; L.ldgate = (int)ldy; L.gate_act = act;
+    L.wpack = (const uint8_t*)wpackT; L.Y = dX; L.M = M; L.ldy = (int)lddx;
+    L.K = (int)N; L.Kp = (int)Np; L.N = (int)Kout; L.Npad = (int)Kpad; L.act = HNR_ACT_NONE;
+    static bool configured = false;
+    if (!configured) {
+        HNR_CUDA(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        configured = true;
+    }
+    const int64_t ntiles = hnr_cdiv(M, TM);
+    const int grid = (int)(ntiles < HNR_NUM_SMS ? ntiles : HNR_NUM_SMS);
+    linear_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(L);
+    HNR_CHECK_LAUNCH("linear_tc_bwd_data");
     return HNR_OK;
 }

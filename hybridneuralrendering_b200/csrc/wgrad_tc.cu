@@ -1,0 +1,231 @@
+// Weight / bias gradient of a dense layer on the 5th-gen tensor cores (training path of SURVEY.md §8a rows A3-A4, I3, I5):
+//
+//     dZ = dY * act'(Y)                        (M x N)
+//     dW[n, k] += sum_m dZ[m, n] * X[m, k]     (N x K),     db[n] += sum_m dZ[m, n]
+//
+// i.e. a GEMM whose reduction runs over the M rows (hundreds of thousands) while the output is tiny.  Mapping:
+//   * UMMA "M" = 128 output rows n (one n-tile per blockIdx.y), UMMA "N" = the K input columns plus one column of
+//     ones that yields db for free (padded; two halves when wider than 256), UMMA "K" = 8 rows of m per step;
+//   * both operands are needed transposed (reduction index contiguous): 8 generator warps read 4(m) x 8(column)
+//     patches of dY / Y / X -- one element per lane, 32-byte row segments -- apply the activation derivative, split the
+//     value into TF32 hi/lo and write one 128-byte core matrix of the canonical K-major UMMA layout per patch
+//     (consecutive lanes -> consecutive words: conflict free);
+//   * fp32 accuracy from 3 TF32 MMAs per product (hi*hi + lo*hi + hi*lo) into one TMEM accumulator that stays resident
+//     for the CTA's whole share of the rows; the CTAs of a column split the rows and add their partial dW with
+//     red.global.add.f32 at the end;
+//   * mbarrier ring between the generator warps and the single MMA-issuing thread.
+// Replaces hnr_linear_bwd_weight (linear_simt.cu) in LinearFn.backward; same argument meaning.
+#include "common.cuh"
+#include "hnr.h"
+#include "tc_common.cuh"
+
+namespace {
+using namespace tc;
+
+constexpr int TN = 128;                 // n rows per CTA == UMMA M
+constexpr int KC = 8;                   // rows of m per MMA step (tf32 K)
+constexpr int NSTAGE = 3;
+constexpr int NGEN_WARPS = 8;
+constexpr int NTHREADS = (NGEN_WARPS + 1) * 32;
+constexpr int KW_MAX = 320;             // widest supported input (+1) after padding
+constexpr int A_PART = TN * KC * 4;     // 4096
+constexpr int B_PART_MAX = KW_MAX * KC * 4;   // 10240
+constexpr int STAGE_BYTES = 2 * A_PART + 2 * B_PART_MAX;   // 28672
+constexpr int OFF_BAR = NSTAGE * STAGE_BYTES;
+constexpr int SMEM_BYTES = OFF_BAR + 128;
+constexpr int SUPER = 4;                // K steps whose loads a generator warp keeps in flight together
+constexpr int MAX_TASKS = 14;           // core-matrix patches per warp per step: ceil((32 + 2*KW_MAX/8) / 8)
+static_assert((2 * TN / 8 + 2 * KW_MAX / 8 + NGEN_WARPS - 1) / NGEN_WARPS <= MAX_TASKS, "task bound");
+
+struct WArgs {
+    const float *dY, *Y;
+    int lddy, ldy, act;
+    const float* x[3];
+    int ld[3], k[3];
+    int64_t mod[3];
+    float *dW, *db;
+    int64_t M;
+    int N, K, KWp, half;        // KWp: padded width of [X | 1]; half = KWp when one MMA group, else KWp / 2
+};
+
+__device__ __forceinline__ float x_load(const WArgs& A, int64_t m, int k) {
+    int s = 0;
+    if (k >= A.k[0]) { k -= A.k[0]; s = 1; if (k >= A.k[1]) { k -= A.k[1]; s = 2; } }
+    if (A.mod[s] > 0) m %= A.mod[s];
+    return __ldg(A.x[s] + m * A.ld[s] + k);
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) wgrad_tc_kernel(const __grid_constant__ WArgs A) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t nsteps = (A.M + KC - 1) / KC, nsuper = (nsteps + SUPER - 1) / SUPER;
+    const int64_t my_super = (int64_t)blockIdx.x < nsuper ? (nsuper - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    if (my_super == 0) return;                                 // uniform for the CTA: nothing allocated yet
+    // K steps of this CTA: every super-step holds SUPER steps except the globally last one
+    const int64_t last_super = blockIdx.x + (my_super - 1) * gridDim.x;
+    const int64_t my_steps = (my_super - 1) * SUPER + (last_super == nsuper - 1 ? nsteps - last_super * SUPER : SUPER);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+    const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * NSTAGE, bar_acc = bar_empty + 8 * NSTAGE;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 1);
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < (uint32_t)A.KWp) tmem_cols <<= 1;
+    const int n0 = blockIdx.y * TN;
+    const uint32_t b_part = (uint32_t)A.KWp * KC * 4, B_LBO = (uint32_t)(A.KWp / 8) * 128;
+    constexpr uint32_t A_LBO = (TN / 8) * 128, SBO = 128;
+
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full + 8 * s, NGEN_WARPS); mbar_init(bar_empty + 8 * s, 1); }
+        mbar_init(bar_acc, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == NGEN_WARPS) tmem_alloc(smem_u32(tmem_slot), tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == NGEN_WARPS) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint32_t idesc = idesc_tf32(TN, A.half);
+            const int ngroup = A.KWp / A.half;                 // 1 or 2
+            for (int64_t it = 0; it < my_steps; ++it) {
+                const uint32_t s = (uint32_t)(it % NSTAGE), ph = (uint32_t)((it / NSTAGE) & 1);
+                mbar_wait(bar_full + 8 * s, ph);
+                tc_fence_after();
+                const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
+                const uint64_t a_hi = umma_desc(st, A_LBO, SBO), a_lo = umma_desc(st + A_PART, A_LBO, SBO);
+                for (int g = 0; g < ngroup; ++g) {
+                    const uint32_t boff = st + 2 * A_PART + (uint32_t)g * (uint32_t)(A.half / 8) * 128;
+                    const uint64_t b_hi = umma_desc(boff, B_LBO, SBO), b_lo = umma_desc(boff + b_part, B_LBO, SBO);
+                    const uint32_t d = tmem_base + (uint32_t)g * (uint32_t)A.half;
+                    tc_mma_tf32(d, a_hi, b_hi, idesc, it > 0 ? 1u : 0u);
+                    tc_mma_tf32(d, a_lo, b_hi, idesc, 1u);
+                    tc_mma_tf32(d, a_hi, b_lo, idesc, 1u);
+                }
+                tc_commit(bar_empty + 8 * s);
+            }
+            tc_commit(bar_acc);
+        }
+    } else {
+        // ================= generators: transposing loads -> TF32 hi/lo core matrices =================
+        const int j = lane >> 2, mi = lane & 3;                // patch element: column 8g + j, row 4h + mi
+        const int ntask_a = 2 * (TN / 8), ntask = ntask_a + 2 * (A.KWp / 8);
+        int64_t step = 0;
+        for (int64_t sit = 0; sit < my_super; ++sit) {
+            const int64_t ms = (blockIdx.x + sit * gridDim.x) * (int64_t)(SUPER * KC);
+            float val[SUPER][MAX_TASKS];
+            float gate[SUPER][2 * (TN / 8) / NGEN_WARPS];       // saved outputs of the A-side patches (tasks t < 4); used after all loads are issued
+#pragma unroll
+            for (int q = 0; q < SUPER; ++q) {
+#pragma unroll
+                for (int t = 0; t < MAX_TASKS; ++t) {
+                    const int task = warp + t * NGEN_WARPS;
+                    float v = 0.f;
+                    if (task < ntask) {
+                        const bool isa = task < ntask_a;
+                        const int tt = isa ? task : task - ntask_a;
+                        const int g = tt >> 1, h = tt & 1;
+                        const int64_t m = ms + q * KC + 4 * h + mi;
+                        const int col = 8 * g + j;
+                        if (m < A.M) {
+                            if (isa) {
+                                const int n = n0 + col;
+                                if (n < A.N) {
+                                    v = __ldg(A.dY + m * A.lddy + n);
+                                    if (t < 2 * (TN / 8) / NGEN_WARPS) gate[q][t] = A.act != HNR_ACT_NONE ? __ldg(A.Y + m * A.ldy + n) : 1.f;
+                                }
+                            } else {
+                                v = col < A.K ? x_load(A, m, col) : (col == A.K ? 1.f : 0.f);
+                            }
+                        }
+                    }
+                    val[q][t] = v;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < SUPER; ++q) {
+                if (ms + q * KC < A.M) {
+                    const uint32_t s = (uint32_t)(step % NSTAGE), ph = (uint32_t)((step / NSTAGE) & 1);
+                    ++step;
+                    mbar_wait(bar_empty + 8 * s, ph ^ 1);
+                    uint8_t* st = smem + s * STAGE_BYTES;
+#pragma unroll
+                    for (int t = 0; t < MAX_TASKS; ++t) {
+                        const int task = warp + t * NGEN_WARPS;
+                        if (task < ntask) {
+                            const bool isa = task < ntask_a;
+                            const int tt = isa ? task : task - ntask_a;
+                            const int g = tt >> 1, h = tt & 1;
+                            float v = val[q][t];
+                            if (t < 2 * (TN / 8) / NGEN_WARPS && A.act != HNR_ACT_NONE && v != 0.f) v *= act_grad_from_out(gate[q][t], A.act);
+                            const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u), lo = v - hi;
+                            uint8_t* base = isa ? st : st + 2 * A_PART;
+                            const uint32_t part = isa ? (uint32_t)A_PART : b_part, lbo = isa ? A_LBO : B_LBO;
+                            float* dst = reinterpret_cast<float*>(base + h * lbo + g * 128) + lane;
+                            *dst = hi;
+                            *reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(dst) + part) = lo;
+                        }
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_full + 8 * s);
+                }
+            }
+        }
+        // ================= epilogue (warps 0-3): TMEM partial -> red.global.add =================
+        if (warp < 4) {
+            mbar_wait(bar_acc, 0);
+            tc_fence_after();
+            const int n = n0 + 32 * warp + lane;
+            const uint32_t taddr = tmem_base + ((uint32_t)(32 * warp) << 16);
+            for (int c0 = 0; c0 < A.KWp; c0 += 16) {
+                float v[16];
+                tmem_ld16(taddr + c0, v);
+                if (n < A.N) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int c = c0 + i;
+                        if (c < A.K) atomicAdd(A.dW + (int64_t)n * A.K + c, v[i]);
+                        else if (c == A.K && A.db) atomicAdd(A.db + n, v[i]);
+                    }
+                }
+            }
+            tc_fence_before();
+        }
+    }
+    __syncthreads();
+    if (warp == NGEN_WARPS) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+}  // namespace
+
+// dW (N,K) += (dY * act'(Y))^T . concat(X), db (N) += column sums of dY * act'(Y); dW / db must be initialised by the
+// caller (normally zeros).  3xTF32 on tcgen05; K + 1 <= 320 after padding.  Same argument meaning as hnr_linear_bwd_weight.
+extern "C" int hnr_linear_tc_bwd_weight(const float* dY, int64_t lddy, const float* Y, int64_t ldy, const float* const* a_ptr,
+                                        const int64_t* a_ld, const int64_t* a_k, const int64_t* a_mod, float* dW, float* db, int64_t M,
+                                        int64_t N, int64_t K, int act, void* stream) {
+    if (M == 0) return HNR_OK;
+    HNR_CHECK_ARG(N > 0 && K > 0 && a_k[0] + a_k[1] + a_k[2] == K, "linear_tc_bwd_weight: concat widths must sum to K");
+    int64_t kw = (K + 1 + 15) / 16 * 16, half = kw;
+    if (kw > 256) { kw = (K + 1 + 31) / 32 * 32; half = kw / 2; }
+    HNR_CHECK_ARG(kw <= KW_MAX, "linear_tc_bwd_weight: layer input too wide (K + 1 must be <= 320)");
+    WArgs A{};
+    A.dY = dY; A.Y = Y; A.lddy = (int)lddy; A.ldy = (int)ldy; A.act = act;
+    for (int i = 0; i < 3; ++i) { A.x[i] = a_ptr[i]; A.ld[i] = (int)a_ld[i]; A.k[i] = (int)a_k[i]; A.mod[i] = a_mod ? a_mod[i] : 0; }
+    A.dW = dW; A.db = db; A.M = M; A.N = (int)N; A.K = (int)K; A.KWp = (int)kw; A.half = (int)half;
+    static bool configured = false;
+    if (!configured) {
+        HNR_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        configured = true;
+    }
+    const int ny = (int)hnr_cdiv(N, TN);
+    const int64_t nsteps = hnr_cdiv(M, KC);
+    const int64_t nsuper = hnr_cdiv(nsteps, SUPER);
+    int gx = HNR_NUM_SMS / ny;
+    if (gx < 1) gx = 1;
+    if (nsuper < gx) gx = (int)nsuper;
+    wgrad_tc_kernel<<<dim3((unsigned)gx, (unsigned)ny), NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(A);
+    HNR_CHECK_LAUNCH("linear_tc_bwd_weight");
+    return HNR_OK;
+}

@@ -120,6 +120,21 @@ def _packed_linear(W: torch.Tensor):
     return ent[1]
 
 
+def _packed_linear_T(W: torch.Tensor):
+    """images of W^T for the tensor-core data gradient, one per slice of <= 256 input columns: [(k0, (image, Kpad, Np))];
+    cached on the weight tensor like _packed_linear"""
+    ent = getattr(W, "_hnr_packT", None)
+    if ent is None or ent[0] != W._version:
+        K = W.shape[1]
+        packs = [(k0, pack_linear(W.detach()[:, k0:k0 + 256].t().contiguous())) for k0 in range(0, K, 256)]
+        ent = (W._version, packs)
+        try:
+            W._hnr_packT = ent
+        except Exception:
+            pass
+    return ent[1]
+
+
 class LinearFn(torch.autograd.Function):
     """y = act(concat(srcs) W^T + b [+ res]).  `mods[i] > 0`: source i has mods[i] rows reused by
     every block of mods[i] output rows."""
@@ -141,7 +156,7 @@ class LinearFn(torch.autograd.Function):
         bc = _f32c(b) if b is not None else None
         if LINEAR_ENGINE == "tc" and N >= 16 and M >= 128:
             wpack, Npad, Kp = _packed_linear(W)
-            with _launch():
+            with _launch(name=f"linear_tc_fwd[{M}x{N}x{K}]" if TIMERS is not None else None):
                 check(lib().hnr_linear_tc_fwd(ptr_array(padded), i64_array(lds), i64_array(ks), i64_array(modl), ptr(wpack), Npad, Kp,
                                               ptr(bc), ptr(resv), resv.stride(0) if resv is not None else 0, ptr(Y), N, M, N, K, act,
                                               None, None, 0, None, stream()), "linear_tc_fwd")
@@ -164,16 +179,29 @@ class LinearFn(torch.autograd.Function):
         lds = [s.stride(0) if s is not None else 0 for s in padded]
         need_src = [ctx.needs_input_grad[6 + i] for i in range(ctx.nsrc)]
         d_srcs: List[Optional[torch.Tensor]] = [None] * ctx.nsrc
+        use_tc = LINEAR_ENGINE == "tc" and M >= 128 and N >= 16
         if any(need_src) and M > 0:
-            outs = [torch.empty((M, ks[i]), device=W.device, dtype=torch.float32) if need_src[i] else None for i in range(ctx.nsrc)]
-            outs_p = outs + [None] * (3 - ctx.nsrc)
-            with _launch(name="linear_bwd_data"):
-                check(lib().hnr_linear_bwd_data(ptr(dY), dY.stride(0), ptr(Y), Y.stride(0), ptr(W), ptr_array(outs_p),
-                                                i64_array([o.stride(0) if o is not None else 0 for o in outs_p]), i64_array(ks), M, N, K, act,
-                                                stream()), "linear_bwd_data")
+            if use_tc:
+                # tensor-core data gradient: dX = (dY * act'(Y)) . W in column slices of <= 256, then views per source
+                dX = torch.empty((M, K), device=W.device, dtype=torch.float32)
+                for k0, (wpackT, Kpad, Np) in _packed_linear_T(W):
+                    with _launch(name=f"linear_tc_bwd_data[{M}x{N}x{K}]" if TIMERS is not None else None):
+                        check(lib().hnr_linear_tc_bwd_data(ptr(dY), dY.stride(0), ptr(Y), Y.stride(0), act, ptr(wpackT), Kpad, Np,
+                                                           ptr(dX[:, k0:]), K, M, N, min(256, K - k0), stream()), "linear_tc_bwd_data")
+                outs, off = [], 0
+                for i in range(ctx.nsrc):
+                    outs.append(dX[:, off:off + ks[i]] if need_src[i] else None)
+                    off += ks[i]
+            else:
+                outs = [torch.empty((M, ks[i]), device=W.device, dtype=torch.float32) if need_src[i] else None for i in range(ctx.nsrc)]
+                outs_p = outs + [None] * (3 - ctx.nsrc)
+                with _launch(name="linear_bwd_data"):
+                    check(lib().hnr_linear_bwd_data(ptr(dY), dY.stride(0), ptr(Y), Y.stride(0), ptr(W), ptr_array(outs_p),
+                                                    i64_array([o.stride(0) if o is not None else 0 for o in outs_p]), i64_array(ks), M, N, K, act,
+                                                    stream()), "linear_bwd_data")
             for i in range(ctx.nsrc):
                 if outs[i] is not None and ctx.mods[i] > 0:
-                    outs[i] = outs[i].view(-1, ctx.mods[i], ks[i]).sum(dim=0)
+                    outs[i] = outs[i].reshape(-1, ctx.mods[i], ks[i]).sum(dim=0)
                 d_srcs[i] = outs[i]
         elif any(need_src):
             d_srcs = [torch.zeros_like(s) if n else None for s, n in zip(srcs, need_src)]
@@ -182,10 +210,16 @@ class LinearFn(torch.autograd.Function):
             dW = torch.zeros_like(W)
             db = torch.zeros(N, device=W.device, dtype=torch.float32) if ctx.has_b else None
             if M > 0:
-                with _launch(name="linear_bwd_weight"):
-                    check(lib().hnr_linear_bwd_weight(ptr(dY), dY.stride(0), ptr(Y), Y.stride(0), ptr_array(padded), i64_array(lds),
-                                                      i64_array(ks), i64_array(ctx.mods), ptr(dW), ptr(db), M, N, K, act, stream()),
-                          "linear_bwd_weight")
+                if use_tc and (K + 1 + 31) // 32 * 32 <= 320:
+                    with _launch(name=f"linear_tc_bwd_weight[{M}x{N}x{K}]" if TIMERS is not None else None):
+                        check(lib().hnr_linear_tc_bwd_weight(ptr(dY), dY.stride(0), ptr(Y), Y.stride(0), ptr_array(padded), i64_array(lds),
+                                                             i64_array(ks), i64_array(ctx.mods), ptr(dW), ptr(db), M, N, K, act, stream()),
+                              "linear_tc_bwd_weight")
+                else:
+                    with _launch(name="linear_bwd_weight"):
+                        check(lib().hnr_linear_bwd_weight(ptr(dY), dY.stride(0), ptr(Y), Y.stride(0), ptr_array(padded), i64_array(lds),
+                                                          i64_array(ks), i64_array(ctx.mods), ptr(dW), ptr(db), M, N, K, act, stream()),
+                              "linear_bwd_weight")
         d_res = dY if ctx.has_res else None
         return (dW, db, d_res, None, None, None, *d_srcs)
 

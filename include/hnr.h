@@ -132,6 +132,17 @@ int hnr_linear_tc_fwd(const float* const* a_ptr, const int64_t* a_ld, const int6
                       int64_t ldy, int64_t M, int64_t N, int64_t K, int act, const float* head_w /* N or NULL */,
                       const float* head_b, int head_act, float* out_head /* M */, void* stream);
 
+/* Tensor-core backward of a dense layer (training path), 3xTF32:
+ *   hnr_linear_tc_bwd_data:   dX (M, Kout <= 256 columns per call) = (dY * act'(Y)) (M,N) . W (N, K-slice); wpackT = image of
+ *                             the transposed weight slice (csrc/linear_tc.cu; replaces hnr_linear_bwd_data)
+ *   hnr_linear_tc_bwd_weight: dW (N,K) += (dY * act'(Y))^T . concat(X), db += column sums; reduction over the M rows with the
+ *                             accumulator resident in TMEM (csrc/wgrad_tc.cu; replaces hnr_linear_bwd_weight) */
+int hnr_linear_tc_bwd_data(const float* dY, int64_t lddy, const float* Y, int64_t ldy, int act, const void* wpackT, int64_t Kpad,
+                           int64_t Np, float* dX, int64_t lddx, int64_t M, int64_t N, int64_t Kout, void* stream);
+int hnr_linear_tc_bwd_weight(const float* dY, int64_t lddy, const float* Y, int64_t ldy, const float* const* a_ptr, const int64_t* a_ld,
+                             const int64_t* a_k, const int64_t* a_mod, float* dW, float* db, int64_t M, int64_t N, int64_t K, int act,
+                             void* stream);
+
 /* Fused per-neighbour MLP on tcgen05 tensor cores (3xTF32, fp32 accuracy), inference path: gather from the
  * point tables + block1 + block3 + density head + weighted K-sum in one persistent kernel (csrc/mlp_tc.cu).
  * Same arithmetic as hnr_nbr_features + 4 x hnr_linear_fwd + hnr_alpha_ksum_fwd

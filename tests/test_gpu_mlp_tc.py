@@ -164,3 +164,37 @@ def test_chain_f16_matches_fp64(M, ks, widths, acts, mods, res, head):
         assert_close(a, b, 1e-5, 2e-5)
     if head:
         assert_close(h, href, 1e-5, 2e-5)
+
+
+@pytest.mark.parametrize("M,N,ks,act,mods", [
+    (1000, 256, (284,), 1, None),            # block1[0]: two 256-column slices of the data gradient, two MMA groups in wgrad
+    (4096, 256, (256, 7), 1, None),          # block3[0]
+    (3 * 500, 64, (45, 128, 3), 1, (0, 500, 0)),   # blend-weight net input layer, rows of source 1 shared by 3 views
+    (777, 45, (45, 45), 0, None),            # mix-up output layer (no activation)
+    (129, 128, (280,), 1, None),
+    (20000, 16, (64,), 2, None),
+])
+def test_linear_tc_backward_matches_fp64(M, N, ks, act, mods):
+    """tensor-core data / weight / bias gradients of a dense layer (3xTF32) vs fp64 autograd"""
+    from hybridneuralrendering_b200 import ops
+    rng = np.random.default_rng(M + N)
+    K = sum(ks)
+    nrows = [mods[i] if mods and mods[i] else M for i in range(len(ks))]
+    srcs = [T(rng.standard_normal((nrows[i], k)).astype(np.float32)).cuda().requires_grad_(True) for i, k in enumerate(ks)]
+    W = T((rng.standard_normal((N, K)) * 0.1).astype(np.float32)).cuda().requires_grad_(True)
+    b = T(rng.standard_normal(N).astype(np.float32)).cuda().requires_grad_(True)
+    gy = T(rng.standard_normal((M, N)).astype(np.float32)).cuda()
+    assert ops.LINEAR_ENGINE == "tc"
+    sd = [s.detach().double().requires_grad_(True) for s in srcs]
+    Wd, bd = W.detach().double().requires_grad_(True), b.detach().double().requires_grad_(True)
+    x = torch.cat([s if s.shape[0] == M else s.repeat(M // s.shape[0], 1) for s in sd], 1)
+    yd = torch.nn.functional.linear(x, Wd, bd)
+    if act == 1:       # LeakyReLU' jumps at 0: a pre-activation within rounding noise of 0 may take either slope in fp32
+        gy = gy * (yd.detach().abs() > 1e-4).float()
+    yd = [yd, torch.nn.functional.leaky_relu(yd, 0.01), torch.sigmoid(yd)][act]
+    yd.backward(gy.double())
+    y = ops.linear(srcs, W, b, act, mods=mods or ())
+    y.backward(gy)
+    assert_close(y, yd, 1e-5, 2e-5)
+    for a, r in zip(srcs + [W, b], sd + [Wd, bd]):
+        assert_close(a.grad, r.grad, 1e-4, 1e-5 * float(r.grad.abs().max()))
