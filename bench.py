@@ -179,6 +179,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="product")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step half of the metric")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -257,10 +258,25 @@ def main():
             "ms_per_step": t_res / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": H * W, "chunk_rays": CHUNK or H * W, "valid_samples_per_pass": net.aggregator.max_valid_chunk, "use_nearest": V, "SR": int(opt.SR), "K": int(opt.K),
-                       "l2": "flushed between steps (256 MB write)", "mlp_engine": net.aggregator.mlp_engine,
+                       "l2": "flushed between steps (256 MB write)", "mlp_engine": "tc (3xFP16 tcgen05 fused kernels)",
                        "parallelism": f"{world} independent frame(s), one per GPU"},
             "e2e": {"value": e2e, "unit": "Mpix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "clocks": clk.summary(), "roofline": roof}
+    # second half of BASELINE.json's metric: train rays/s (fwd+bwd) on configs[2]; under torchrun every rank trains on its own
+    # 4096-ray batch and the gradients are all-reduced over NCCL (weak scaling), time = max over ranks
+    if not args.no_train:
+        from hybridneuralrendering_b200.benchmarks import train_step_benchmark
+        del net, resident, flush
+        torch.cuda.empty_cache()
+        tr = train_step_benchmark(dev, steps=max(3, args.steps), warmup=max(3, args.warmup), world=world, rank=rank, stage_split=(world == 1))
+        tt = torch.tensor([tr["ms_fwd_bwd"]], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        tr["ms_fwd_bwd"] = float(tt.item())
+        tr["value"] = world * tr["rays"] / (tr["ms_fwd_bwd"] * 1e-3)
+        tr["n_gpus"] = world
+        tr["gradient_allreduce"] = "NCCL SUM, dense point gradients + coalesced MLP bucket" if world > 1 else "none (1 GPU)"
+        line["train"] = tr
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         q_np, n_sample = sample_query(xyz, att, fr, P, dev)
         cores = os.cpu_count() or 1

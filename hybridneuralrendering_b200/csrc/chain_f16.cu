@@ -221,18 +221,23 @@ __global__ void __launch_bounds__(NTHREADS, 2) chain_f16_kernel(const __grid_con
             }
         }
     } else if (warp == 8) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
+        // ================= MMA issuer: the whole warp walks the schedule (warp-uniform control flow), one elected lane issues =================
+        {
             uint32_t wit = 0, ait = 0, use[2] = {0, 0}, actcnt[4] = {0, 0, 0, 0};
             TRACE_DECL(0);
+            if (lane != 0) tr__ = nullptr;
             const uint32_t act_hi = smem_u32(smem + OFF_ACT), act_lo = act_hi + ACT_PART;
+            const uint32_t w_base = smem_u32(smem + OFF_W), a_base = smem_u32(smem + OFF_A);
+            const uint64_t dA = umma_desc(0, A_LBO, SBO);
             for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 for (int l = 0; l < nl; ++l) {
                     const uint32_t b = l & 1, acc = tmem_base + b * NMAX;
                     const uint32_t np = (uint32_t)A.Np[l], idesc = idesc_f16((int)np), w_lbo = (np / 8) * 128, w_part = np * 32;
+                    const uint64_t dW = umma_desc(0, w_lbo, SBO);
                     const int nc = A.Kp[l] / KC, cps = W_STAGE / (int)(np * 64u);
                     if (use[b] > 0) mbar_wait_relaxed(bar_accfree + 8 * b, (use[b] - 1) & 1, 20);   // previous reader of this accumulator done
                     ++use[b];
+                    int sub = 0;
                     for (int c = 0; c < nc; ++c) {
                         uint32_t a_hi_addr, a_lo_addr, as = 0;
                         if (l == 0) {
@@ -240,7 +245,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) chain_f16_kernel(const __grid_con
                             const uint32_t ph = (ait / NSA) & 1;
                             ++ait;
                             mbar_wait_relaxed(bar_afull + 8 * as, ph, 20);
-                            a_hi_addr = smem_u32(smem + OFF_A + as * A_STAGE);
+                            a_hi_addr = a_base + as * A_STAGE;
                             a_lo_addr = a_hi_addr + A_PART;
                         } else {
                             if ((c & 1) == 0) {
@@ -251,26 +256,25 @@ __global__ void __launch_bounds__(NTHREADS, 2) chain_f16_kernel(const __grid_con
                             a_lo_addr = act_lo + c * 2 * A_LBO;
                         }
                         TRACE(1, l, c);                                 // operand ready
-                        const int sub = c % cps;                       // chunk within the weight stage
                         const uint32_t s = wit % NSW;
-                        if (sub == 0) {
-                            mbar_wait(bar_wfull + 8 * s, (wit / NSW) & 1);
-                        }
+                        if (sub == 0) mbar_wait(bar_wfull + 8 * s, (wit / NSW) & 1);
                         tc_fence_after();
-                        const uint32_t w = smem_u32(smem + OFF_W + s * W_STAGE) + (uint32_t)sub * (np * 64u);
-                        const uint64_t w_hi = umma_desc(w, w_lbo, SBO), w_lo = umma_desc(w + w_part, w_lbo, SBO);
-                        const uint64_t a_hi = umma_desc(a_hi_addr, A_LBO, SBO), a_lo = umma_desc(a_lo_addr, A_LBO, SBO);
-                        tc_mma_f16(acc, a_hi, w_hi, idesc, c > 0 ? 1u : 0u);
-                        tc_mma_f16(acc, a_lo, w_hi, idesc, 1u);
-                        tc_mma_f16(acc, a_hi, w_lo, idesc, 1u);
-                        if (sub == cps - 1 || c == nc - 1) {
-                            tc_commit(bar_wempty + 8 * s);
-                            ++wit;
+                        const bool release_w = (sub == cps - 1 || c == nc - 1);
+                        if (elect_one()) {
+                            const uint32_t w = w_base + s * W_STAGE + (uint32_t)sub * (np * 64u);
+                            const uint64_t w_hi = dW | (uint64_t)((w & 0x3FFFFu) >> 4), w_lo = dW | (uint64_t)(((w + w_part) & 0x3FFFFu) >> 4);
+                            const uint64_t a_hi = dA | (uint64_t)((a_hi_addr & 0x3FFFFu) >> 4), a_lo = dA | (uint64_t)((a_lo_addr & 0x3FFFFu) >> 4);
+                            tc_mma_f16(acc, a_hi, w_hi, idesc, c > 0 ? 1u : 0u);
+                            tc_mma_f16(acc, a_lo, w_hi, idesc, 1u);
+                            tc_mma_f16(acc, a_hi, w_lo, idesc, 1u);
+                            if (release_w) tc_commit(bar_wempty + 8 * s);
+                            if (l == 0) tc_commit(bar_aempty + 8 * as);
+                            if (c == nc - 1) tc_commit(bar_accfull + 8 * b);
                         }
-                        if (l == 0) tc_commit(bar_aempty + 8 * as);
+                        __syncwarp();
+                        if (release_w) { ++wit; sub = 0; } else { ++sub; }
                         TRACE(2, l, c);                                 // MMAs issued
                     }
-                    tc_commit(bar_accfull + 8 * b);
                 }
             }
         }

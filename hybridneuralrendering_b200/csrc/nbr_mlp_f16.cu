@@ -218,22 +218,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) nbr_mlp_f16_kernel(F16Args A) {
                     bulk_g2s(smem_u32(smem + OFF_W + s * W_STAGE), A.wpack + (size_t)c * W_STAGE, W_STAGE, bar_wfull + 8 * s);
                 }
             }
-        } else if (warp == 12 && lane == 0) {
-            // ================= MMA issuer: one thread, 3 MMAs (3xFP16) per K chunk =================
+        } else if (warp == 12) {
+            // ================= MMA issuer: the whole warp walks the schedule (warp-uniform), one elected lane issues
+            //                   3 MMAs (3xFP16) per K chunk =================
             uint32_t wit = 0, ait = 0, gen = 0, ti = 0;
             const uint32_t act_hi = smem_u32(smem + OFF_ACT), act_lo = act_hi + ACT_PART;
-            auto issue = [&](uint32_t acc, uint32_t a_hi_addr, uint32_t a_lo_addr, bool first) {
+            const uint32_t w_base = smem_u32(smem + OFF_W), a_base = smem_u32(smem + OFF_A), e_base = smem_u32(smem + OFF_E);
+            // descriptor = constant high word | (address >> 4) in the low 14 bits | LBO field
+            const uint64_t dW = umma_desc(0, W_LBO, SBO), dA = umma_desc(0, A_LBO, SBO);
+            auto issue = [&](uint32_t acc, uint32_t a_hi_addr, uint32_t a_lo_addr, bool first, uint32_t extra_commit) {
                 const uint32_t s = wit % NSW, ph = (wit / NSW) & 1;
                 ++wit;
                 mbar_wait(bar_wfull + 8 * s, ph);
                 tc_fence_after();
-                const uint32_t w = smem_u32(smem + OFF_W + s * W_STAGE);
-                const uint64_t w_hi = umma_desc(w, W_LBO, SBO), w_lo = umma_desc(w + W_PART, W_LBO, SBO);
-                const uint64_t a_hi = umma_desc(a_hi_addr, A_LBO, SBO), a_lo = umma_desc(a_lo_addr, A_LBO, SBO);
-                tc_mma_f16(acc, a_hi, w_hi, IDESC, first ? 0u : 1u);
-                tc_mma_f16(acc, a_lo, w_hi, IDESC, 1u);
-                tc_mma_f16(acc, a_hi, w_lo, IDESC, 1u);
-                tc_commit(bar_wempty + 8 * s);
+                if (elect_one()) {
+                    const uint32_t w = w_base + s * W_STAGE;
+                    const uint64_t w_hi = dW | (uint64_t)((w & 0x3FFFFu) >> 4), w_lo = dW | (uint64_t)(((w + W_PART) & 0x3FFFFu) >> 4);
+                    const uint64_t a_hi = dA | (uint64_t)((a_hi_addr & 0x3FFFFu) >> 4), a_lo = dA | (uint64_t)((a_lo_addr & 0x3FFFFu) >> 4);
+                    tc_mma_f16(acc, a_hi, w_hi, IDESC, first ? 0u : 1u);
+                    tc_mma_f16(acc, a_lo, w_hi, IDESC, 1u);
+                    tc_mma_f16(acc, a_hi, w_lo, IDESC, 1u);
+                    tc_commit(bar_wempty + 8 * s);
+                    if (extra_commit) tc_commit(extra_commit);
+                }
+                __syncwarp();
             };
             for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
                 const uint32_t acc0 = tmem_base, acc1 = tmem_base + HID;
@@ -242,37 +250,40 @@ __global__ void __launch_bounds__(NTHREADS, 1) nbr_mlp_f16_kernel(F16Args A) {
                 for (int c = 0; c < NC0; ++c, ++ait) {
                     const uint32_t s = ait % NSA, ph = (ait / NSA) & 1;
                     mbar_wait_relaxed(bar_afull + 8 * s, ph, 20);
-                    const uint32_t a = smem_u32(smem + OFF_A + s * A_STAGE);
-                    issue(acc0, a, a + A_PART, c == 0);
-                    tc_commit(bar_aempty + 8 * s);
+                    const uint32_t a = a_base + s * A_STAGE;
+                    issue(acc0, a, a + A_PART, c == 0, bar_aempty + 8 * s);
                 }
-                tc_commit(bar_accfull);
+                if (elect_one()) tc_commit(bar_accfull);
+                __syncwarp();
                 // ---- layer 1: operands = activation written by epilogue 0, released per 32 columns
                 for (int c = 0; c < NC1; ++c) {
                     if ((c & 1) == 0) mbar_wait_relaxed(bar_actfull + 8 * (c >> 1), gen & 1, 20);
-                    issue(acc1, act_hi + c * 2 * A_LBO, act_lo + c * 2 * A_LBO, c == 0);
+                    issue(acc1, act_hi + c * 2 * A_LBO, act_lo + c * 2 * A_LBO, c == 0, 0);
                 }
-                tc_commit(bar_accfull + 8);
+                if (elect_one()) tc_commit(bar_accfull + 8);
+                __syncwarp();
                 ++gen;
                 // ---- layer 2: extras chunk first (ready since the gather), then the activation of epilogue 1
                 {
                     const uint32_t p = ti & 1;
                     mbar_wait(bar_efull + 8 * p, (ti >> 1) & 1);
-                    const uint32_t e = smem_u32(smem + OFF_E + p * A_STAGE);
-                    issue(acc0, e, e + A_PART, true);
+                    const uint32_t e = e_base + p * A_STAGE;
+                    issue(acc0, e, e + A_PART, true, 0);
                 }
                 for (int c = 0; c < NC1; ++c) {
                     if ((c & 1) == 0) mbar_wait_relaxed(bar_actfull + 8 * (c >> 1), gen & 1, 20);
-                    issue(acc0, act_hi + c * 2 * A_LBO, act_lo + c * 2 * A_LBO, false);
+                    issue(acc0, act_hi + c * 2 * A_LBO, act_lo + c * 2 * A_LBO, false, 0);
                 }
-                tc_commit(bar_accfull);
+                if (elect_one()) tc_commit(bar_accfull);
+                __syncwarp();
                 ++gen;
                 // ---- layer 3
                 for (int c = 0; c < NC3; ++c) {
                     if ((c & 1) == 0) mbar_wait_relaxed(bar_actfull + 8 * (c >> 1), gen & 1, 20);
-                    issue(acc1, act_hi + c * 2 * A_LBO, act_lo + c * 2 * A_LBO, c == 0);
+                    issue(acc1, act_hi + c * 2 * A_LBO, act_lo + c * 2 * A_LBO, c == 0, 0);
                 }
-                tc_commit(bar_accfull + 8);
+                if (elect_one()) tc_commit(bar_accfull + 8);
+                __syncwarp();
                 ++gen;
             }
         }

@@ -107,4 +107,16 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint
     return d;              // base_offset = 0, lbo_mode = 0, layout_type = SWIZZLE_NONE (0)
 }
 
+// one elected lane of a fully converged warp (warp-uniform control flow around it lets the compiler keep the tcgen05
+// operands in uniform registers instead of wrapping every instruction in a per-lane loop)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 }  // namespace tc

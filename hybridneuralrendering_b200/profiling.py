@@ -10,6 +10,7 @@ from . import ops
 from .renderer import render_rays
 
 FLOP_PER_NEIGHBOUR = 542_720            # 2*(284*256 + 256*256 + 263*256 + 256*256 + 256), SURVEY.md §8d
+DRAM_BYTES_PER_LAUNCH_NCU = 337_902_848  # measured, see profiles/r1_nbr_mlp_f16_ncu.md (86.1 MB read + 251.8 MB written)
 
 
 def stage_times(net, frame, chunk_rays: int) -> Dict[str, float]:
@@ -58,11 +59,22 @@ def dominant_kernel_roofline(net, frame, chunk_rays: int, peaks_and_kind) -> Dic
     ms = t.get("nbr_mlp", 0.0)
     flops = FLOP_PER_NEIGHBOUR * units["valid_neighbours"]
     achieved = flops / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
-    # fp32-accurate tensor-core path = 3 TF32 MMAs per product -> peak = TF32 / 3; TF32 dense = bf16 / 2
-    # (MEASURED_PEAKS.json has no TF32 entry: "of derived")
-    peak = peaks["bf16_tflops_sustained"] / 2.0 / 3.0
-    return {"bound": "tensor", "kernel": "per-neighbour MLP (block1+block3, 4 dense layers)", "achieved": achieved, "peak": peak,
-            "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": None,
-            "peak_basis": f"bf16_tflops_sustained/2/3 of {kind} (3xTF32 fp32-equivalent)",
-            "launches": launches.get("nbr_mlp", 0), "kernel_ms_per_step": ms, "share_of_step": ms / total if total else None,
+    # fp32-accurate tensor-core path = 3 FP16 MMAs per product (csrc/nbr_mlp_f16.cu) -> peak = dense fp16/bf16 tensor
+    # throughput / 3.  MEASURED_PEAKS.json: cuBLAS bf16 (same tcgen05 kind::f16 rate); the kernel is timed inside a long
+    # step, so the sustained figure applies.
+    engine = getattr(net.aggregator, "mlp_engine", "tc")
+    if engine == "tc":
+        peak = peaks["bf16_tflops_sustained"] / 3.0
+        basis = f"bf16_tflops_sustained/3 of {kind} (3xFP16 split, fp32-equivalent FLOPs)"
+    else:
+        peak = peaks["bf16_tflops_sustained"] / 2.0 / 3.0
+        basis = f"bf16_tflops_sustained/2/3 of {kind} (3xTF32, TF32 dense = bf16/2 derived)"
+    nl = launches.get("nbr_mlp", 0)
+    return {"bound": "tensor", "kernel": "nbr_mlp_f16_kernel: fused per-neighbour MLP (gather + block1 + block3 + density head + K-sum)",
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+            "traffic": DRAM_BYTES_PER_LAUNCH_NCU, "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch of 262,144 valid "
+            "samples, ncu --set full (profiles/r1_nbr_mlp_f16_ncu.md); algorithmic HBM bytes per launch = 168 B x neighbours in + 1124 B x samples out",
+            "algorithmic_flop_per_launch": FLOP_PER_NEIGHBOUR * units["valid_neighbours"] / nl if nl else None,
+            "peak_basis": basis, "launches": nl, "kernel_ms_per_step": ms, "kernel_ms_per_launch": ms / nl if nl else None,
+            "share_of_step": ms / total if total else None,
             "units": units, "stage_ms": {k: round(v, 3) for k, v in sorted(t.items())}}
