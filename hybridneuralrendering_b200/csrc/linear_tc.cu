@@ -151,8 +151,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(LArgs L) {
                 }
         }
     } else if (warp == WARP_MMA) {
-        if (lane == 0) {
+        // the whole warp walks the schedule (warp-uniform control flow keeps the tcgen05 operands in uniform registers);
+        // one elected lane issues
+        {
             const uint32_t idesc = idesc_tf32(TM, L.Npad);
+            const uint64_t dW = umma_desc(0, W_LBO, SBO), dA = umma_desc(0, A_LBO, SBO);
+            const uint32_t w_base = smem_u32(smem + OFF_W), a_base = smem_u32(smem + OFF_A);
             uint32_t it = 0, tcount = 0;
             for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
                 const uint32_t b = tcount & 1, bph = (tcount >> 1) & 1;
@@ -164,16 +168,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(LArgs L) {
                     mbar_wait(bar_fullW + 8 * sw, pw);
                     mbar_wait(bar_fullA + 8 * sa, pa);
                     tc_fence_after();
-                    const uint32_t ws = smem_u32(smem + OFF_W + sw * W_STAGE_MAX), as = smem_u32(smem + OFF_A + sa * A_STAGE);
-                    const uint64_t w_hi = umma_desc(ws, W_LBO, SBO), w_lo = umma_desc(ws + w_part, W_LBO, SBO);
-                    const uint64_t a_hi = umma_desc(as, A_LBO, SBO), a_lo = umma_desc(as + A_PART, A_LBO, SBO);
-                    tc_mma_tf32(d_tmem, a_hi, w_hi, idesc, c > 0 ? 1u : 0u);
-                    tc_mma_tf32(d_tmem, a_lo, w_hi, idesc, 1u);
-                    tc_mma_tf32(d_tmem, a_hi, w_lo, idesc, 1u);
-                    tc_commit(bar_emptyW + 8 * sw);
-                    tc_commit(bar_emptyA + 8 * sa);
+                    if (elect_one()) {
+                        const uint32_t ws = w_base + sw * W_STAGE_MAX, as = a_base + sa * A_STAGE;
+                        const uint64_t w_hi = dW | (uint64_t)((ws & 0x3FFFFu) >> 4), w_lo = dW | (uint64_t)(((ws + w_part) & 0x3FFFFu) >> 4);
+                        const uint64_t a_hi = dA | (uint64_t)((as & 0x3FFFFu) >> 4), a_lo = dA | (uint64_t)(((as + A_PART) & 0x3FFFFu) >> 4);
+                        tc_mma_tf32(d_tmem, a_hi, w_hi, idesc, c > 0 ? 1u : 0u);
+                        tc_mma_tf32(d_tmem, a_lo, w_hi, idesc, 1u);
+                        tc_mma_tf32(d_tmem, a_hi, w_lo, idesc, 1u);
+                        tc_commit(bar_emptyW + 8 * sw);
+                        tc_commit(bar_emptyA + 8 * sa);
+                        if (c == nchunk - 1) tc_commit(bar_accF + 8 * b);
+                    }
+                    __syncwarp();
                 }
-                tc_commit(bar_accF + 8 * b);
             }
         }
     } else if (warp < NCONV_WARPS) {

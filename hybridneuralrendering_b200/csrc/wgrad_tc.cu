@@ -85,27 +85,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_tc_kernel(const __grid_cons
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == NGEN_WARPS) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
+        // ================= MMA issuer: warp-uniform schedule, one elected lane issues =================
+        {
             const uint32_t idesc = idesc_tf32(TN, A.half);
             const int ngroup = A.KWp / A.half;                 // 1 or 2
+            const uint64_t dA = umma_desc(0, A_LBO, SBO), dB = umma_desc(0, B_LBO, SBO);
+            const uint32_t s_base = smem_u32(smem);
             for (int64_t it = 0; it < my_steps; ++it) {
                 const uint32_t s = (uint32_t)(it % NSTAGE), ph = (uint32_t)((it / NSTAGE) & 1);
                 mbar_wait(bar_full + 8 * s, ph);
                 tc_fence_after();
-                const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
-                const uint64_t a_hi = umma_desc(st, A_LBO, SBO), a_lo = umma_desc(st + A_PART, A_LBO, SBO);
-                for (int g = 0; g < ngroup; ++g) {
-                    const uint32_t boff = st + 2 * A_PART + (uint32_t)g * (uint32_t)(A.half / 8) * 128;
-                    const uint64_t b_hi = umma_desc(boff, B_LBO, SBO), b_lo = umma_desc(boff + b_part, B_LBO, SBO);
-                    const uint32_t d = tmem_base + (uint32_t)g * (uint32_t)A.half;
-                    tc_mma_tf32(d, a_hi, b_hi, idesc, it > 0 ? 1u : 0u);
-                    tc_mma_tf32(d, a_lo, b_hi, idesc, 1u);
-                    tc_mma_tf32(d, a_hi, b_lo, idesc, 1u);
+                if (elect_one()) {
+                    const uint32_t st = s_base + s * STAGE_BYTES;
+                    const uint64_t a_hi = dA | (uint64_t)((st & 0x3FFFFu) >> 4), a_lo = dA | (uint64_t)(((st + A_PART) & 0x3FFFFu) >> 4);
+                    for (int g = 0; g < ngroup; ++g) {
+                        const uint32_t boff = st + 2 * A_PART + (uint32_t)g * (uint32_t)(A.half / 8) * 128;
+                        const uint64_t b_hi = dB | (uint64_t)((boff & 0x3FFFFu) >> 4), b_lo = dB | (uint64_t)(((boff + b_part) & 0x3FFFFu) >> 4);
+                        const uint32_t d = tmem_base + (uint32_t)g * (uint32_t)A.half;
+                        tc_mma_tf32(d, a_hi, b_hi, idesc, it > 0 ? 1u : 0u);
+                        tc_mma_tf32(d, a_lo, b_hi, idesc, 1u);
+                        tc_mma_tf32(d, a_hi, b_lo, idesc, 1u);
+                    }
+                    tc_commit(bar_empty + 8 * s);
+                    if (it == my_steps - 1) tc_commit(bar_acc);
                 }
-                tc_commit(bar_empty + 8 * s);
+                __syncwarp();
             }
-            tc_commit(bar_acc);
         }
     } else {
         // ================= generators: transposing loads -> TF32 hi/lo core matrices =================

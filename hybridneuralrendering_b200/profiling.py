@@ -10,7 +10,7 @@ from . import ops
 from .renderer import render_rays
 
 FLOP_PER_NEIGHBOUR = 542_720            # 2*(284*256 + 256*256 + 263*256 + 256*256 + 256), SURVEY.md §8d
-DRAM_BYTES_PER_LAUNCH_NCU = 337_902_848  # measured, see profiles/r1_nbr_mlp_f16_ncu.md (86.1 MB read + 251.8 MB written)
+DRAM_BYTES_PER_LAUNCH_NCU = 330_913_792  # measured, see profiles/r1_nbr_mlp_f16_ncu.md (85.5 MB read + 245.4 MB written)
 
 
 def stage_times(net, frame, chunk_rays: int) -> Dict[str, float]:
