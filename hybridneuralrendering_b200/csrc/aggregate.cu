@@ -390,6 +390,69 @@ image_gather_kernel(hnr_pyramid_t P, const float* __restrict__ xy, const int32_t
     }
 }
 
+// Forward lookup, vectorised: 16 lanes per (view, sample) pair, two pairs per warp.  A lane owns one 16-byte (level 3, level 2)
+// or 8-byte (level 1) channel group of one pyramid level -- the NHWC layout makes the channels of a tap contiguous -- and
+// evaluates the 4-tap bilinear interpolation with the same expression per channel as the scalar kernel above:
+//   sub-lane 0..5 : level 3 (24 ch) float4 q        -> aux[21 + 4q ..]
+//   sub-lane 6..8 : level 2 (12 ch) float4 q-6      -> aux[ 9 + 4(q-6) ..]
+//   sub-lane 9..11: level 1 ( 6 ch) float2 q-9      -> aux[ 3 + 2(q-9) ..]
+//   sub-lane 12   : level 0 rgb (nearest pixel), validity flag
+__global__ void __launch_bounds__(256)
+image_gather_fwd_v2_kernel(hnr_pyramid_t P, const float* __restrict__ xy, const int32_t* __restrict__ vlist, int V, int64_t S, int64_t Nv,
+                           float* __restrict__ aux, float* __restrict__ ok) {
+    const int q = threadIdx.x & 15;
+    const int64_t pair = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    if (pair >= (int64_t)V * Nv || q > 12) return;
+    const int v = (int)(pair / Nv);
+    const int64_t n = pair - (int64_t)v * Nv;
+    const int64_t s = vlist[n];
+    const float2 f = *reinterpret_cast<const float2*>(xy + ((int64_t)v * S + s) * 2);
+    const int px = (int)f.x, py = (int)f.y;                  // truncation toward zero, as .to(torch.int32)
+    const int H = P.h[0], W = P.w[0];
+    const bool inb = !(px < 0 || px >= W || py < 0 || py >= H);
+    const bool zero = !inb || (px == 0 && py == 0);          // pixel (0,0) is the zeroed "invalid" slot
+    float* o = aux + pair * AUX_C;
+    if (q == 12) {
+        ok[pair] = inb ? 1.f : 0.f;
+        float r = 0.f, g = 0.f, b = 0.f;
+        if (!zero) {
+            const float* p0 = P.lvl[0] + (((int64_t)v * H + py) * W + px) * 3;
+            r = p0[0]; g = p0[1]; b = p0[2];
+        }
+        o[0] = r; o[1] = g; o[2] = b;
+        return;
+    }
+    const int l = q < 6 ? 3 : (q < 9 ? 2 : 1);
+    const int grp = q < 6 ? q : (q < 9 ? q - 6 : q - 9);     // float4 (levels 3, 2) or float2 (level 1) index inside the pixel
+    const int ch0 = l == 3 ? 21 + 4 * grp : (l == 2 ? 9 + 4 * grp : 3 + 2 * grp);
+    float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
+    if (!zero) {
+        int y0, y1, x0, x1; float ly0, ly1, lx0, lx1;
+        const int hl = l == 3 ? P.h[3] : (l == 2 ? P.h[2] : P.h[1]), wl = l == 3 ? P.w[3] : (l == 2 ? P.w[2] : P.w[1]);
+        const int C = l == 3 ? 24 : (l == 2 ? 12 : 6);
+        const float* lv = l == 3 ? P.lvl[3] : (l == 2 ? P.lvl[2] : P.lvl[1]);
+        bilin_setup(py, hl, H, y0, y1, ly0, ly1);
+        bilin_setup(px, wl, W, x0, x1, lx0, lx1);
+        const float* b = lv + (int64_t)v * hl * wl * C;
+        const int o00 = (y0 * wl + x0) * C, o01 = (y0 * wl + x1) * C, o10 = (y1 * wl + x0) * C, o11 = (y1 * wl + x1) * C;
+        if (l == 1) {
+            const float2 a = *reinterpret_cast<const float2*>(b + o00 + 2 * grp), bq = *reinterpret_cast<const float2*>(b + o01 + 2 * grp);
+            const float2 c = *reinterpret_cast<const float2*>(b + o10 + 2 * grp), d = *reinterpret_cast<const float2*>(b + o11 + 2 * grp);
+            r0 = ly0 * (lx0 * a.x + lx1 * bq.x) + ly1 * (lx0 * c.x + lx1 * d.x);
+            r1 = ly0 * (lx0 * a.y + lx1 * bq.y) + ly1 * (lx0 * c.y + lx1 * d.y);
+        } else {
+            const float4 a = *reinterpret_cast<const float4*>(b + o00 + 4 * grp), bq = *reinterpret_cast<const float4*>(b + o01 + 4 * grp);
+            const float4 c = *reinterpret_cast<const float4*>(b + o10 + 4 * grp), d = *reinterpret_cast<const float4*>(b + o11 + 4 * grp);
+            r0 = ly0 * (lx0 * a.x + lx1 * bq.x) + ly1 * (lx0 * c.x + lx1 * d.x);
+            r1 = ly0 * (lx0 * a.y + lx1 * bq.y) + ly1 * (lx0 * c.y + lx1 * d.y);
+            r2 = ly0 * (lx0 * a.z + lx1 * bq.z) + ly1 * (lx0 * c.z + lx1 * d.z);
+            r3 = ly0 * (lx0 * a.w + lx1 * bq.w) + ly1 * (lx0 * c.w + lx1 * d.w);
+        }
+    }
+    o[ch0] = r0; o[ch0 + 1] = r1;
+    if (l != 1) { o[ch0 + 2] = r2; o[ch0 + 3] = r3; }
+}
+
 // ------------------------------------------------------------------ I3: learned multi-view blend
 // thread per (sample, channel): merged = keep * sum_v aux_v w_v / (sum_v w_v + 1e-6), w_v = sig_v * ok_v
 __global__ void blend_fwd_kernel(const float* __restrict__ aux, const float* __restrict__ sig, const float* __restrict__ ok,
@@ -548,7 +611,15 @@ extern "C" int hnr_image_gather_fwd(const float* const* levels, const int64_t* l
     if (V * Nv == 0) return HNR_OK;
     hnr_pyramid_t P;
     fill_pyramid(P, levels, nullptr, level_hw);
-    image_gather_kernel<false><<<warp_blocks(V * Nv), 256, 0, (cudaStream_t)stream>>>(P, xy, vlist, (int)V, S, Nv, aux, ok, nullptr);
+    // vector path: needs the channel groups 16-byte (levels 2, 3) / 8-byte (level 1) aligned, i.e. base pointers from the allocator
+    // and the standard 6 / 12 / 24 channel pyramid, and 32-bit tap offsets inside one view
+    const bool vec_ok = P.c[1] == 6 && P.c[2] == 12 && P.c[3] == 24 && (reinterpret_cast<uintptr_t>(levels[1]) & 7) == 0 &&
+                        (reinterpret_cast<uintptr_t>(levels[2]) & 15) == 0 && (reinterpret_cast<uintptr_t>(levels[3]) & 15) == 0 &&
+                        (reinterpret_cast<uintptr_t>(xy) & 7) == 0 && (int64_t)P.h[1] * P.w[1] * 24 < (1ll << 31);
+    if (vec_ok)
+        image_gather_fwd_v2_kernel<<<(unsigned)hnr_cdiv(V * Nv * 16, 256), 256, 0, (cudaStream_t)stream>>>(P, xy, vlist, (int)V, S, Nv, aux, ok);
+    else
+        image_gather_kernel<false><<<warp_blocks(V * Nv), 256, 0, (cudaStream_t)stream>>>(P, xy, vlist, (int)V, S, Nv, aux, ok, nullptr);
     HNR_CHECK_LAUNCH("image_gather_fwd");
     return HNR_OK;
 }
