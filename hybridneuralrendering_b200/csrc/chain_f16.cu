@@ -20,6 +20,7 @@
 //     loads in flight: the chains are bound by reading their inputs), 1 MMA warp, 1 bulk-copy warp.
 // Optional fp32 copies of every layer's output (Y_l) make the same kernel usable as the forward of a training step.
 #include <cuda_fp16.h>
+#include <limits.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -33,16 +34,15 @@ constexpr int TM = 128;
 constexpr int NMAX = 128;               // widest layer == TMEM columns per accumulator
 constexpr int KC = 16;
 constexpr int MAXL = 4;
-constexpr int NSW = 4, NSA = 2;
+constexpr int NSW = 2, NSA = 4;           // weight stages (8 KB, several chunks each when narrow) / layer-0 operand stages (pairs)
 constexpr int W_STAGE = 2 * NMAX * KC * 2;   // 8192
 constexpr int A_PART = TM * KC * 2;          // 4096
 constexpr int A_STAGE = 2 * A_PART;          // 8192
 constexpr int ACT_PART = TM * NMAX * 2;      // 32768
 constexpr int NTHREADS = 320;            // warps 0-3 epilogue, 4-7 generators, 8 MMA, 9 bulk copy
-constexpr int GEN_DEPTH = 3;             // K chunks a generator thread keeps in flight (registers)
 
 constexpr int OFF_W = 0;
-constexpr int OFF_A = OFF_W + NSW * W_STAGE;           // 32768
+constexpr int OFF_A = OFF_W + NSW * W_STAGE;           // 16384
 constexpr int OFF_ACT = OFF_A + NSA * A_STAGE;         // 49152
 constexpr int OFF_BAR = OFF_ACT + 2 * ACT_PART;        // 114688 (bias / head weights are read through the read-only cache)
 constexpr int NBAR = 2 * NSW + 2 * NSA + 4 + 2 + 2;
@@ -140,40 +140,6 @@ constexpr int TRACE_CAP = 4096;
 
 __host__ __device__ constexpr uint32_t idesc_f16(int N) {   // D=f32, A=B=f16, both K-major, M=128
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
-}
-
-// 16 consecutive columns [c0, c0+16) of one row of the concatenated layer-0 input (zero beyond the last column);
-// rp[s] = pointer to the row's first element in source s
-__device__ __forceinline__ void load_chunk(const ChainArgs& A, const float* const (&rp)[3], int c0, float (&v)[16]) {
-    int base = 0;
-#pragma unroll
-    for (int s = 0; s < 3; ++s) {
-        const int ks = A.k[s];
-        if (ks > 0 && c0 >= base && c0 + 16 <= base + ks) {             // whole chunk inside source s
-            const float* p = rp[s] + (c0 - base);
-            if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float4 q = __ldg(reinterpret_cast<const float4*>(p) + i);
-                    v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = __ldg(p + i);
-            }
-            return;
-        }
-        base += ks;
-    }
-    // chunk straddles sources (or the zero padding): per-column lookup
-    const int b1 = A.k[0], b2 = A.k[0] + A.k[1], b3 = b2 + A.k[2];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const int c = c0 + i;
-        float x = 0.f;
-        if (c < b3) x = c < b1 ? __ldg(rp[0] + c) : (c < b2 ? __ldg(rp[1] + (c - b1)) : __ldg(rp[2] + (c - b2)));
-        v[i] = x;
-    }
 }
 
 __global__ void __launch_bounds__(NTHREADS, 2) chain_f16_kernel(const __grid_constant__ ChainArgs A) {
@@ -279,56 +245,107 @@ __global__ void __launch_bounds__(NTHREADS, 2) chain_f16_kernel(const __grid_con
             }
         }
     } else if (warp >= 4) {
-        // ================= generators: fp32 source rows -> split fp16 operand chunks (thread = row) =================
-        const int r = tid - 128;                         // 0..127
+        // ================= generators: fp32 source rows -> split fp16 operand chunks =================
         TRACE_DECL(1);
-        if (r != 0) tr__ = nullptr;
-        const int nc0 = A.Kp[0] / KC;
+        if (tid != 128) tr__ = nullptr;
+        // Line-coalesced loads: a step covers a PAIR of K chunks = 32 columns = 128 bytes of every row.  lane = (row-in-4,
+        // 16-byte piece), so one load instruction reads 4 rows x one full 128-byte line; a warp owns 32 rows (8 instructions).
+        // Each lane converts its own 4 columns and stores 8-byte hi / lo pieces straight into the two operand stages.
+        const int nc0 = A.Kp[0] / KC, npair = (nc0 + 1) / 2;
         const float sc = A.in_scale;
+        const int gw = warp - 4, rsub = lane >> 3, piece = lane & 7;
+        const int ktot = A.k[0] + A.k[1] + A.k[2], b1 = A.k[0], b2 = A.k[0] + A.k[1];
         uint32_t ait = 0;
+        // the row offsets of this lane's 8 rows are cached per (tile, source), so a step's loads cost one address each
+        int cur_src = -1;
+        int64_t cur_tile = -1;
+        const float* sbase_p = nullptr;
+        int rowoff[8];                                   // element offset of the row relative to the tile's first row in the cached source; INT_MIN = row beyond M
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const int64_t m = tile * TM + r;
-            const bool ok = m < A.M;
-            const float* rp[3];
+            const int64_t m0 = tile * TM;
+            for (int p = 0; p < npair; ++p) {
+                const int col0 = 32 * p + 4 * piece;
+                const bool have1 = 2 * p + 1 < nc0;      // second chunk of the pair exists
+                const bool mine = piece < 4 || have1;
+                int s_ = 0, k_ = col0;
+                if (k_ >= b1) { k_ -= b1; s_ = 1; if (col0 >= b2) { k_ = col0 - b2; s_ = 2; } }
+                const int ks_ = s_ == 0 ? A.k[0] : (s_ == 1 ? A.k[1] : A.k[2]);
+                const bool whole = col0 + 4 <= ktot && k_ + 4 <= ks_;
+                float4 v[8];
 #pragma unroll
-            for (int s = 0; s < 3; ++s) {
-                const int64_t rr = ok ? (A.mod[s] > 0 ? m % A.mod[s] : m) : 0;
-                rp[s] = A.src[s] + rr * A.ld[s];
-            }
-            float buf[GEN_DEPTH][16];
+                for (int i = 0; i < 8; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (mine && whole) {
+                    const int sld = s_ == 0 ? A.ld[0] : (s_ == 1 ? A.ld[1] : A.ld[2]);
+                    if (s_ != cur_src || tile != cur_tile) {
+                        const int64_t smod = s_ == 0 ? A.mod[0] : (s_ == 1 ? A.mod[1] : A.mod[2]);
+                        const int64_t first = smod > 0 ? m0 % smod : m0;          // source row of the tile's first row
+                        sbase_p = (s_ == 0 ? A.src[0] : (s_ == 1 ? A.src[1] : A.src[2])) + first * sld;
 #pragma unroll
-            for (int d = 0; d < GEN_DEPTH; ++d) {
+                        for (int i = 0; i < 8; ++i) {
+                            const int r = 32 * gw + 4 * i + rsub;
+                            int64_t rr = first + r;
+                            if (smod > 0 && rr >= smod) rr %= smod;
+                            rowoff[i] = (m0 + r < A.M) ? (int)((rr - first) * sld) : INT_MIN;
+                        }
+                        cur_src = s_; cur_tile = tile;
+                    }
+                    const float* cb = sbase_p + k_;
+                    const bool vec = ((reinterpret_cast<uintptr_t>(cb) & 15) == 0) && ((sld & 3) == 0);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) buf[d][i] = 0.f;
-                if (ok && d < nc0) load_chunk(A, rp, d * KC, buf[d]);
-            }
-            for (int c = 0; c < nc0; c += GEN_DEPTH) {
+                    for (int i = 0; i < 8; ++i) {
+                        if (rowoff[i] != INT_MIN) {
+                            const float* qd = cb + rowoff[i];
+                            if (vec) v[i] = __ldg(reinterpret_cast<const float4*>(qd));
+                            else v[i] = make_float4(__ldg(qd), __ldg(qd + 1), __ldg(qd + 2), __ldg(qd + 3));
+                        }
+                    }
+                } else if (mine) {
 #pragma unroll
-                for (int d = 0; d < GEN_DEPTH; ++d) {
-                    if (c + d < nc0) {
-                        const uint32_t st = ait % NSA, ph = (ait / NSA) & 1;
-                        ++ait;
-                        float v[16];
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = 32 * gw + 4 * i + rsub;
+                        if (m0 + r < A.M) {
+                            float e[4];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = buf[d][i] * sc;
-                        if (ok && c + d + GEN_DEPTH < nc0) load_chunk(A, rp, (c + d + GEN_DEPTH) * KC, buf[d]);   // refill: stays in flight
-                        if (__float_as_int(v[0]) != 0x7fc12345) TRACE(10, c + d, 0);      // data arrived (forces the load)
-                        mbar_wait_relaxed(bar_aempty + 8 * st, ph ^ 1, 32);
-                        TRACE(11, c + d, 0);                                       // stage free
-                        uint8_t* stage = smem + OFF_A + st * A_STAGE;
-                        uint4 hi, lo;
-                        split8(v, hi, lo);
-                        *reinterpret_cast<uint4*>(stage + r * 16) = hi;
-                        *reinterpret_cast<uint4*>(stage + A_PART + r * 16) = lo;
-                        split8(v + 8, hi, lo);
-                        *reinterpret_cast<uint4*>(stage + A_LBO + r * 16) = hi;
-                        *reinterpret_cast<uint4*>(stage + A_PART + A_LBO + r * 16) = lo;
-                        fence_proxy_async();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(bar_afull + 8 * st);
-                        TRACE(12, c + d, 0);                                       // delivered
+                            for (int u = 0; u < 4; ++u) {            // straddles two sources or the zero padding: per element
+                                const int c = col0 + u;
+                                e[u] = 0.f;
+                                if (c < ktot) {
+                                    const int su = c < b1 ? 0 : (c < b2 ? 1 : 2);
+                                    const int ku = c - (su == 0 ? 0 : (su == 1 ? b1 : b2));
+                                    const int64_t rr = A.mod[su] > 0 ? (m0 + r) % A.mod[su] : m0 + r;
+                                    e[u] = __ldg(A.src[su] + rr * A.ld[su] + ku);
+                                }
+                            }
+                            v[i] = make_float4(e[0], e[1], e[2], e[3]);
+                        }
                     }
                 }
+                TRACE(10, p, 0);
+                const uint32_t st0 = ait % NSA, ph0 = (ait / NSA) & 1, st1 = (ait + 1) % NSA, ph1 = ((ait + 1) / NSA) & 1;
+                ait += have1 ? 2 : 1;
+                mbar_wait_relaxed(bar_aempty + 8 * st0, ph0 ^ 1, 32);
+                if (have1) mbar_wait_relaxed(bar_aempty + 8 * st1, ph1 ^ 1, 32);
+                TRACE(11, p, 0);
+                if (mine) {
+                    uint8_t* stage = smem + OFF_A + (piece < 4 ? st0 : st1) * A_STAGE + ((piece >> 1) & 1) * A_LBO + (piece & 1) * 8;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = 32 * gw + 4 * i + rsub;
+                        const float a = v[i].x * sc, b = v[i].y * sc, c = v[i].z * sc, d = v[i].w * sc;
+                        const uint32_t h0 = pack_sat(a, b), h1 = pack_sat(c, d);
+                        const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&h0)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&h1));
+                        const uint32_t l0 = pack_sat(a - f0.x, b - f0.y), l1 = pack_sat(c - f1.x, d - f1.y);
+                        *reinterpret_cast<uint2*>(stage + r * 16) = make_uint2(h0, h1);
+                        *reinterpret_cast<uint2*>(stage + A_PART + r * 16) = make_uint2(l0, l1);
+                    }
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(bar_afull + 8 * st0);
+                    if (have1) mbar_arrive(bar_afull + 8 * st1);
+                }
+                TRACE(12, p, 0);
             }
         }
     } else {
@@ -357,6 +374,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) chain_f16_kernel(const __grid_con
                 float* yout = A.Y[l];
                 const int ldy = A.ldy[l];
                 const bool yvec = yout && (ldy & 3) == 0 && (reinterpret_cast<uintptr_t>(yout) & 15) == 0;
+                // last layer with dense, 32-column-multiple rows: stage the fp32 tile in the (now free) activation buffer and
+                // store it with whole-row coalesced writes instead of one 64-byte piece per thread
+                const bool staged = last && yvec && ldy == n && (n & 31) == 0;
+                float4* stg = reinterpret_cast<float4*>(smem + OFF_ACT);
                 float dot = 0.f;
 #pragma unroll 1
                 for (int c0 = 0; c0 < np; c0 += 16) {
@@ -395,7 +416,11 @@ __global__ void __launch_bounds__(NTHREADS, 2) chain_f16_kernel(const __grid_con
                             }
                         }
                     }
-                    if (yout && live) {
+                    if (staged) {
+#pragma unroll
+                        for (int i4 = 0; i4 < 4; ++i4)      // 16-byte granule g of row r lives at r*(n/4) + (g ^ (r & 7)): conflict-free both ways
+                            stg[r * (n >> 2) + (((c0 >> 2) + i4) ^ (r & 7))] = make_float4(y[4 * i4], y[4 * i4 + 1], y[4 * i4 + 2], y[4 * i4 + 3]);
+                    } else if (yout && live) {
                         float* o = yout + m * ldy + c0;
                         if (yvec && c0 + 16 <= n) {
 #pragma unroll
@@ -423,6 +448,16 @@ __global__ void __launch_bounds__(NTHREADS, 2) chain_f16_kernel(const __grid_con
                             if (lane == 0) mbar_arrive(bar_actfull + 8 * (c0 >> 5));
                         }
                     }
+                }
+                if (staged) {
+                    asm volatile("bar.sync 1, 128;" ::: "memory");                // all four epilogue warps have staged their rows
+                    const int gpr = n >> 2;                                        // granules per row (multiple of 8)
+                    for (int idx = tid; idx < TM * gpr; idx += 128) {
+                        const int row = idx / gpr, g = idx - row * gpr;
+                        const int64_t mm = tile * TM + row;
+                        if (mm < A.M) reinterpret_cast<float4*>(yout + mm * ldy)[g] = stg[row * gpr + (g ^ (row & 7))];
+                    }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");                // staging consumed before the next tile's epilogue writes the activation
                 }
                 TRACE(22, l, 0);                                                    // epilogue of the layer done
                 tc_fence_before();
