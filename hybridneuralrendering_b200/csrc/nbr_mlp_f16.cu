@@ -69,7 +69,8 @@ struct F16Args {
     const float *loc_w, *loc_pers, *raydirs, *cam, *weight, *confc;
     const uint8_t* wpack;          // 67 chunk images in consumption order
     const float *bias, *walpha, *balpha;   // bias: (4,256), rows 0..2 pre-multiplied by the next layer's input scale
-    float *sigma, *X5, *dbg;
+    float *sigma, *X5, *dbg, *araw;     // dbg: optional (4, Nv*8, 256) activations of every layer (training / tests); araw: (Nv*8) density pre-activation
+    float inv_act;                      // 1 / input scale of layers 1..3 (the saved activations are unscaled)
     int64_t Nv;
     float mul[NLAYER];             // accumulator -> (scaled) pre-activation factor per layer
     float scale0, scale2;          // input scales of layer 0 (generated features) and layer 2 (extras chunk)
@@ -470,9 +471,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) nbr_mlp_f16_kernel(F16Args A) {
                         if (DBG) {
                             const int64_t row = row0 + r;
                             if (row < total_rows) {
-                                float* o = A.dbg + ((int64_t)l * total_rows + row) * HID + j * 32;
+                                float4* o = reinterpret_cast<float4*>(A.dbg + ((int64_t)l * total_rows + row) * HID + j * 32);
+                                const float ia = A.inv_act;
 #pragma unroll
-                                for (int i = 0; i < 32; ++i) o[i] = y[i];
+                                for (int i = 0; i < 8; ++i) o[i] = make_float4(y[4 * i] * ia, y[4 * i + 1] * ia, y[4 * i + 2] * ia, y[4 * i + 3] * ia);
                             }
                         }
 #pragma unroll
@@ -515,22 +517,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) nbr_mlp_f16_kernel(F16Args A) {
                         for (int i4 = 0; i4 < 8; ++i4) {
                             const float4 bb = bl4[jj * 16 + i4], ww = wa4[jj * 16 + i4];
                             const float bv[4] = {bb.x, bb.y, bb.z, bb.w}, wv[4] = {ww.x, ww.y, ww.z, ww.w};
+                            float tsave[4];
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
                                 const int i = 4 * i4 + u;
                                 float t = fmaf(__uint_as_float(cur[i]), mul, bv[u]);
                                 t = fmaxf(t, 0.01f * t);
-                                if (DBG && row0 + r < total_rows) A.dbg[((int64_t)l * total_rows + row0 + r) * HID + j * 32 + i] = t;
+                                if (DBG) tsave[u] = t;
                                 dot = fmaf(t, wv[u], dot);
                                 sblk[i * TM + ((rg ^ i) << 2)] = t * wrow;
                             }
+                            if (DBG && row0 + r < total_rows)
+                                reinterpret_cast<float4*>(A.dbg + ((int64_t)l * total_rows + row0 + r) * HID + j * 32)[i4] =
+                                    make_float4(tsave[0], tsave[1], tsave[2], tsave[3]);
                         }
                     }
                     araw_s[wg * TM + r] = dot;
                     tc_fence_before();
                     named_barrier<1, NEPI>();
                     if (wg == 0) {
-                        float sg = wrow * softplus_t(araw_s[r] + araw_s[TM + r] + A.balpha[0] - 1.f);
+                        const float raw = araw_s[r] + araw_s[TM + r] + A.balpha[0];
+                        if (DBG && A.araw && row0 + r < total_rows) A.araw[row0 + r] = raw;
+                        float sg = wrow * softplus_t(raw - 1.f);
                         sg += __shfl_xor_sync(0xffffffffu, sg, 1);
                         sg += __shfl_xor_sync(0xffffffffu, sg, 2);
                         sg += __shfl_xor_sync(0xffffffffu, sg, 4);
@@ -568,12 +576,15 @@ extern "C" int64_t hnr_nbr_mlp_f16_packed_bytes(void) { return (int64_t)NCHUNK_T
 
 // Fused per-neighbour MLP + density head + weighted K-sum for Nv valid samples (K == 8), 3xFP16 on tcgen05.
 // mul[l]: accumulator -> pre-activation factor of layer l (includes the next layer's input scale for l < 3);
-// bias (4,256): rows 0..2 pre-multiplied by the next layer's input scale.  dbg (optional): (4, Nv*8, 256) activations.
+// bias (4,256): rows 0..2 pre-multiplied by the next layer's input scale; inv_act = 1 / that scale.  dbg (optional):
+// (4, Nv*8, 256) unscaled activations of the four layers, araw (optional, with dbg): (Nv*8) density pre-activations --
+// the training forward saves them for the backward pass.
 extern "C" int hnr_nbr_mlp_f16_forward(const float* xyz, const float* xyz_pers, const float* emb, const float* color, const float* dir,
                                        const int32_t* pidx, const int32_t* vlist, const float* loc_w, const float* loc_pers,
                                        const float* raydirs, const float* cam, const float* weight, const float* confc, const void* wpack,
                                        const float* bias, const float* walpha, const float* balpha, const float* mul, float scale0,
-                                       float scale2, int64_t Nv, int64_t K, float* sigma, float* X5, float* dbg, void* stream) {
+                                       float scale2, float inv_act, int64_t Nv, int64_t K, float* sigma, float* X5, float* dbg, float* araw,
+                                       void* stream) {
     HNR_CHECK_ARG(K == 8, "nbr_mlp_f16_forward: K must be 8 (128-row tiles hold 16 whole samples)");
     if (Nv == 0) return HNR_OK;
     F16Args A{};
@@ -582,7 +593,7 @@ extern "C" int hnr_nbr_mlp_f16_forward(const float* xyz, const float* xyz_pers, 
     A.wpack = (const uint8_t*)wpack; A.bias = bias; A.walpha = walpha; A.balpha = balpha; A.sigma = sigma; A.X5 = X5; A.dbg = dbg;
     A.Nv = Nv;
     for (int l = 0; l < NLAYER; ++l) A.mul[l] = mul[l];
-    A.scale0 = scale0; A.scale2 = scale2;
+    A.scale0 = scale0; A.scale2 = scale2; A.inv_act = inv_act; A.araw = araw;
     static bool configured = false;
     if (!configured) {
         HNR_CUDA(cudaFuncSetAttribute(nbr_mlp_f16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));

@@ -136,7 +136,7 @@ def split_f16(x: torch.Tensor):
     return hi, lo
 
 
-def pack_layer_f16(W: torch.Tensor, cols: Optional[Sequence[int]] = None):
+def pack_layer_f16(W: torch.Tensor, cols: Optional[Sequence[int]] = None, weight_scale: Optional[float] = None):
     """W (256, K) fp32 -> (uint8 image of Kp/16 chunks, weight scale).  The weights are multiplied by a power of two
     that brings max|w| just below 2^14, split into fp16 hi / lo and tiled per 16-column chunk as [hi 8 KB | lo 8 KB],
     each part [k block (2)][row group (32)][row (8)][8 halves] = canonical no-swizzle K-major UMMA core matrices."""
@@ -148,21 +148,27 @@ def pack_layer_f16(W: torch.Tensor, cols: Optional[Sequence[int]] = None):
     Wp = _permute_pad(W, cols).contiguous()
     Kp = Wp.shape[1]
     assert Kp % KC16 == 0
-    wmax = float(Wp.abs().max())
-    sw = 2.0 ** math.floor(math.log2(16384.0 / wmax)) if wmax > 0 else 1.0
+    if weight_scale is None:
+        wmax = float(Wp.abs().max())                      # host read-back: fine for inference (packed once per weight version)
+        sw = 2.0 ** math.floor(math.log2(16384.0 / wmax)) if wmax > 0 else 1.0
+    else:
+        sw = float(weight_scale)                          # training re-packs every step: a fixed scale avoids the synchronisation
     hi, lo = split_f16(Wp * sw)
     tile = lambda x: x.view(32, 8, Kp // KC16, 2, 8).permute(2, 3, 0, 1, 4)          # (C, 2, 32, 8, 8)
     img = torch.stack([tile(hi), tile(lo)], dim=1).contiguous()                        # (C, 2[hi|lo], 2, 32, 8, 8)
     return img.view(torch.uint8).reshape(-1), sw
 
 
-def pack_mlp_f16(block1, block3, act_scale: float = ACT_SCALE):
+TRAIN_WEIGHT_SCALE = 1024.0     # fixed power-of-two weight scale of graph-recording forwards: full hi/lo precision for 1e-4 <= |w| < 63
+
+
+def pack_mlp_f16(block1, block3, act_scale: float = ACT_SCALE, weight_scale: Optional[float] = None):
     """-> (wpack uint8, bias (4,256) pre-scaled, mul [4] floats, scale0, scale2) for hnr_nbr_mlp_f16_forward"""
     l2 = list(range(256, 263)) + [-1] * 9 + list(range(256))        # extras chunk first, then the 256 hidden columns
     layers = [(block1[0], layer1_column_order_f16()), (block1[2], None), (block3[0], l2), (block3[2], None)]
     parts, sws = [], []
     for lin, cols in layers:
-        img, sw = pack_layer_f16(lin.weight, cols)
+        img, sw = pack_layer_f16(lin.weight, cols, weight_scale)
         parts.append(img)
         sws.append(sw)
     wpack = torch.cat(parts).contiguous()
@@ -174,21 +180,23 @@ def pack_mlp_f16(block1, block3, act_scale: float = ACT_SCALE):
 
 
 def forward_f16(tables, pidx, vlist, loc_w, loc_pers, raydirs, cam, weight, confc, pack, w_alpha, b_alpha, debug: bool = False):
-    """fused gather + per-neighbour MLP + density head + weighted K-sum (inference), 3xFP16 tensor-core kernel.
-    Returns sigma (Nv,1), X5 (Nv,280) [, dbg (4, Nv*8, 256) unscaled-by-mul activations when debug]."""
+    """fused gather + per-neighbour MLP + density head + weighted K-sum, 3xFP16 tensor-core kernel.
+    Returns sigma (Nv,1), X5 (Nv,280) [, acts (4, Nv*8, 256) activations of the four layers, araw (Nv*8) density
+    pre-activations when debug -- what the training forward saves for the backward pass]."""
     import ctypes as C
     xyz, xyz_pers, emb, color, dirs, _ = tables
     wpack, bias, mul, s0, s2 = pack
     Nv, K = vlist.shape[0], pidx.shape[1]
     sigma = torch.empty((Nv, 1), device=pidx.device, dtype=torch.float32)
     X5 = torch.empty((Nv, 280), device=pidx.device, dtype=torch.float32)
-    dbg = torch.zeros((4, Nv * K, 256), device=pidx.device, dtype=torch.float32) if debug else None
+    dbg = torch.empty((4, Nv * K, 256), device=pidx.device, dtype=torch.float32) if debug else None
+    araw = torch.empty((Nv * K,), device=pidx.device, dtype=torch.float32) if debug else None
     wa = w_alpha.detach().float().contiguous().view(-1)
     ba = b_alpha.detach().float().contiguous().view(-1)
     mul_c = (C.c_float * 4)(*mul)
     with ops._launch():
         check(lib().hnr_nbr_mlp_f16_forward(ptr(xyz), ptr(xyz_pers), ptr(emb), ptr(color), ptr(dirs), ptr(pidx), ptr(vlist), ptr(loc_w),
                                             ptr(loc_pers), ptr(raydirs), ptr(cam), ptr(weight), ptr(confc), ptr(wpack), ptr(bias), ptr(wa),
-                                            ptr(ba), mul_c, float(s0), float(s2), Nv, K, ptr(sigma), ptr(X5), ptr(dbg), stream()),
-              "nbr_mlp_f16_forward")
-    return (sigma, X5, dbg) if debug else (sigma, X5)
+                                            ptr(ba), mul_c, float(s0), float(s2), 1.0 / ACT_SCALE, Nv, K, ptr(sigma), ptr(X5), ptr(dbg),
+                                            ptr(araw), stream()), "nbr_mlp_f16_forward")
+    return (sigma, X5, dbg, araw) if debug else (sigma, X5)

@@ -171,57 +171,70 @@ class LinearFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dY):
         W, Y, *srcs = ctx.saved_tensors
-        dY = _rows2d(dY)
-        N, K = W.shape
-        M, act = ctx.M, ctx.act
-        ks = [s.shape[1] for s in srcs] + [0] * (3 - len(srcs))
-        padded = list(srcs) + [None] * (3 - len(srcs))
-        lds = [s.stride(0) if s is not None else 0 for s in padded]
         need_src = [ctx.needs_input_grad[6 + i] for i in range(ctx.nsrc)]
-        d_srcs: List[Optional[torch.Tensor]] = [None] * ctx.nsrc
-        use_tc = LINEAR_ENGINE == "tc" and M >= 128 and N >= 16
-        if any(need_src) and M > 0:
-            if use_tc:
-                # tensor-core data gradient: dX = (dY * act'(Y)) . W in column slices of <= 256, then views per source
-                dX = torch.empty((M, K), device=W.device, dtype=torch.float32)
-                for k0, (wpackT, Kpad, Np) in _packed_linear_T(W):
-                    with _launch(name=f"linear_tc_bwd_data[{M}x{N}x{K}]" if TIMERS is not None else None):
-                        check(lib().hnr_linear_tc_bwd_data(ptr(dY), dY.stride(0), ptr(Y), Y.stride(0), act, ptr(wpackT), Kpad, Np,
-                                                           ptr(dX[:, k0:]), K, M, N, min(256, K - k0), stream()), "linear_tc_bwd_data")
-                outs, off = [], 0
-                for i in range(ctx.nsrc):
-                    outs.append(dX[:, off:off + ks[i]] if need_src[i] else None)
-                    off += ks[i]
-            else:
-                outs = [torch.empty((M, ks[i]), device=W.device, dtype=torch.float32) if need_src[i] else None for i in range(ctx.nsrc)]
-                outs_p = outs + [None] * (3 - ctx.nsrc)
-                with _launch(name="linear_bwd_data"):
-                    check(lib().hnr_linear_bwd_data(ptr(dY), dY.stride(0), ptr(Y), Y.stride(0), ptr(W), ptr_array(outs_p),
-                                                    i64_array([o.stride(0) if o is not None else 0 for o in outs_p]), i64_array(ks), M, N, K, act,
-                                                    stream()), "linear_bwd_data")
-            for i in range(ctx.nsrc):
-                if outs[i] is not None and ctx.mods[i] > 0:
-                    outs[i] = outs[i].reshape(-1, ctx.mods[i], ks[i]).sum(dim=0)
-                d_srcs[i] = outs[i]
-        elif any(need_src):
-            d_srcs = [torch.zeros_like(s) if n else None for s, n in zip(srcs, need_src)]
-        dW = db = None
-        if ctx.needs_input_grad[0] or (ctx.has_b and ctx.needs_input_grad[1]):
-            dW = torch.zeros_like(W)
-            db = torch.zeros(N, device=W.device, dtype=torch.float32) if ctx.has_b else None
-            if M > 0:
-                if use_tc and (K + 1 + 31) // 32 * 32 <= 320:
-                    with _launch(name=f"linear_tc_bwd_weight[{M}x{N}x{K}]" if TIMERS is not None else None):
-                        check(lib().hnr_linear_tc_bwd_weight(ptr(dY), dY.stride(0), ptr(Y), Y.stride(0), ptr_array(padded), i64_array(lds),
-                                                             i64_array(ks), i64_array(ctx.mods), ptr(dW), ptr(db), M, N, K, act, stream()),
-                              "linear_tc_bwd_weight")
-                else:
-                    with _launch(name="linear_bwd_weight"):
-                        check(lib().hnr_linear_bwd_weight(ptr(dY), dY.stride(0), ptr(Y), Y.stride(0), ptr_array(padded), i64_array(lds),
-                                                          i64_array(ks), i64_array(ctx.mods), ptr(dW), ptr(db), M, N, K, act, stream()),
-                              "linear_bwd_weight")
+        need_w = ctx.needs_input_grad[0] or (ctx.has_b and ctx.needs_input_grad[1])
+        d_srcs, dW, db = linear_backward(W, Y, srcs, ctx.mods, dY, ctx.act, need_src, need_w, ctx.has_b, M=ctx.M)
         d_res = dY if ctx.has_res else None
         return (dW, db, d_res, None, None, None, *d_srcs)
+
+
+def linear_backward(W, Y, srcs, mods, dY, act: int, need_src, need_w: bool = True, has_b: bool = True, M: Optional[int] = None):
+    """gradients of y = act(concat(srcs) W^T + b) given dY and the saved output Y: ([d_src_i | None], dW | None, db | None).
+    Tensor-core kernels (3xTF32: gated data gradient, TMEM-resident weight gradient) for layers with >= 16 outputs and
+    >= 128 rows, exact-fp32 SIMT kernels otherwise."""
+    srcs = [_rows2d(s) for s in srcs]
+    nsrc = len(srcs)
+    dY, Y = _rows2d(dY), _rows2d(Y)
+    N, K = W.shape
+    if M is None:
+        M = dY.shape[0]
+    mods = list(mods) + [0] * (3 - len(mods))
+    ks = [s.shape[1] for s in srcs] + [0] * (3 - nsrc)
+    padded = list(srcs) + [None] * (3 - nsrc)
+    lds = [s.stride(0) if s is not None else 0 for s in padded]
+    d_srcs: List[Optional[torch.Tensor]] = [None] * nsrc
+    use_tc = LINEAR_ENGINE == "tc" and M >= 128 and N >= 16
+    if any(need_src) and M > 0:
+        if use_tc:
+            # tensor-core data gradient: dX = (dY * act'(Y)) . W in column slices of <= 256, then views per source
+            dX = torch.empty((M, K), device=W.device, dtype=torch.float32)
+            for k0, (wpackT, Kpad, Np) in _packed_linear_T(W):
+                with _launch(name=f"linear_tc_bwd_data[{M}x{N}x{K}]" if TIMERS is not None else None):
+                    check(lib().hnr_linear_tc_bwd_data(ptr(dY), dY.stride(0), ptr(Y), Y.stride(0), act, ptr(wpackT), Kpad, Np,
+                                                       ptr(dX[:, k0:]), K, M, N, min(256, K - k0), stream()), "linear_tc_bwd_data")
+            outs, off = [], 0
+            for i in range(nsrc):
+                outs.append(dX[:, off:off + ks[i]] if need_src[i] else None)
+                off += ks[i]
+        else:
+            outs = [torch.empty((M, ks[i]), device=W.device, dtype=torch.float32) if need_src[i] else None for i in range(nsrc)]
+            outs_p = outs + [None] * (3 - nsrc)
+            with _launch(name="linear_bwd_data"):
+                check(lib().hnr_linear_bwd_data(ptr(dY), dY.stride(0), ptr(Y), Y.stride(0), ptr(W), ptr_array(outs_p),
+                                                i64_array([o.stride(0) if o is not None else 0 for o in outs_p]), i64_array(ks), M, N, K, act,
+                                                stream()), "linear_bwd_data")
+        for i in range(nsrc):
+            if outs[i] is not None and mods[i] > 0:
+                outs[i] = outs[i].reshape(-1, mods[i], ks[i]).sum(dim=0)
+            d_srcs[i] = outs[i]
+    elif any(need_src):
+        d_srcs = [torch.zeros_like(s) if n else None for s, n in zip(srcs, need_src)]
+    dW = db = None
+    if need_w:
+        dW = torch.zeros_like(W)
+        db = torch.zeros(N, device=W.device, dtype=torch.float32) if has_b else None
+        if M > 0:
+            if use_tc and (K + 1 + 31) // 32 * 32 <= 320:
+                with _launch(name=f"linear_tc_bwd_weight[{M}x{N}x{K}]" if TIMERS is not None else None):
+                    check(lib().hnr_linear_tc_bwd_weight(ptr(dY), dY.stride(0), ptr(Y), Y.stride(0), ptr_array(padded), i64_array(lds),
+                                                         i64_array(ks), i64_array(mods), ptr(dW), ptr(db), M, N, K, act, stream()),
+                          "linear_tc_bwd_weight")
+            else:
+                with _launch(name="linear_bwd_weight"):
+                    check(lib().hnr_linear_bwd_weight(ptr(dY), dY.stride(0), ptr(Y), Y.stride(0), ptr_array(padded), i64_array(lds),
+                                                      i64_array(ks), i64_array(mods), ptr(dW), ptr(db), M, N, K, act, stream()),
+                          "linear_bwd_weight")
+    return d_srcs, dW, db
 
 
 def linear_head(srcs: Sequence[torch.Tensor], W, b, act: int, head_W, head_b, head_act: int, mods: Sequence[int] = (),
@@ -358,6 +371,63 @@ class AlphaKSumFn(torch.autograd.Function):
             d_confc = torch.zeros_like(confc)
             d_confc.index_copy_(0, vl, d_wc * weight.index_select(0, vl))
         return dH, d_confc, d_wa.view(ctx.wshape), d_ba.view(ctx.bshape), None, None, None, None
+
+
+class NbrMlpFusedFn(torch.autograd.Function):
+    """Training forward of the whole per-neighbour stage (gather, encodings, block1, block3, density head, weighted K-sum)
+    through the fused tensor-core kernel (csrc/nbr_mlp_f16.cu) with the four layers' activations saved for the backward
+    pass; the backward runs layer by layer on the tensor-core gradient kernels.  Same arithmetic and the same gradients as
+    NbrFeaturesFn -> 4 x LinearFn -> AlphaKSumFn.  -> sigma (Nv,1), X5 (Nv,280)."""
+
+    @staticmethod
+    def forward(ctx, emb, color, dirs, confc, W1, b1, W2, b2, W3, b3, W4, b4, w_alpha, b_alpha, aux):
+        from . import mlp_tc
+        xyz, xyz_pers, pidx, vlist, loc_w, loc_pers, raydirs, cam, weight, pack = aux
+        Nv, K = vlist.shape[0], pidx.shape[1]
+        X0 = torch.empty((Nv * K, X0_W), device=emb.device, dtype=torch.float32)
+        E = torch.empty((Nv * K, E_W), device=emb.device, dtype=torch.float32)
+        with _launch():
+            check(lib().hnr_nbr_features(ptr(xyz), ptr(xyz_pers), ptr(emb), ptr(color), ptr(dirs), ptr(pidx), ptr(vlist), ptr(loc_w),
+                                         ptr(loc_pers), ptr(raydirs), ptr(cam), Nv, K, emb.shape[-1], ptr(X0), ptr(E), stream()), "nbr_features")
+        confc_c = _f32c(confc)
+        sigma, X5, H, araw = mlp_tc.forward_f16((xyz, xyz_pers, emb, color, dirs, None), pidx, vlist, loc_w, loc_pers, raydirs, cam, weight,
+                                                confc_c, pack, w_alpha, b_alpha, debug=True)
+        ctx.save_for_backward(emb, confc_c, W1, W2, W3, W4, _f32c(w_alpha).view(-1), X0, E, H, araw, pidx, vlist, raydirs, weight)
+        ctx.cam, ctx.Nv, ctx.K = cam, Nv, K
+        ctx.shapes = (emb.shape, color.shape, dirs.shape, w_alpha.shape, b_alpha.shape)
+        return sigma, X5
+
+    @staticmethod
+    def backward(ctx, d_sigma, dX5):
+        emb, confc, W1, W2, W3, W4, w_alpha, X0, E, H, araw, pidx, vlist, raydirs, weight = ctx.saved_tensors
+        Nv, K = ctx.Nv, ctx.K
+        d_sigma, dX5 = _f32c(d_sigma), _f32c(dX5)
+        dH4 = torch.empty_like(H[3])
+        d_wc = torch.empty((Nv, K), device=H.device, dtype=torch.float32)
+        d_wa = torch.zeros(HID, device=H.device, dtype=torch.float32)
+        d_ba = torch.zeros(1, device=H.device, dtype=torch.float32)
+        with _launch(name="alpha_ksum_bwd"):
+            check(lib().hnr_alpha_ksum_bwd(ptr(H[3]), ptr(weight), ptr(confc), ptr(vlist), ptr(w_alpha), ptr(araw), ptr(d_sigma), ptr(dX5), Nv, K,
+                                           HID, ptr(dH4), ptr(d_wc), ptr(d_wa), ptr(d_ba), stream()), "alpha_ksum_bwd")
+        d_confc = None
+        if ctx.needs_input_grad[3]:
+            vl = vlist.long()
+            d_confc = torch.zeros_like(confc)
+            d_confc.index_copy_(0, vl, d_wc * weight.index_select(0, vl))
+        (dH3,), dW4, db4 = linear_backward(W4, H[3], [H[2]], (), dH4, ACT_LRELU, [True])
+        (dH2, dE), dW3, db3 = linear_backward(W3, H[2], [H[1], E], (), dH3, ACT_LRELU, [True, True])
+        (dH1,), dW2, db2 = linear_backward(W2, H[1], [H[0]], (), dH2, ACT_LRELU, [True])
+        (dX0,), dW1, db1 = linear_backward(W1, H[0], [X0], (), dH1, ACT_LRELU, [True])
+        ne, nc, nd = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        d_emb = torch.zeros(ctx.shapes[0], device=emb.device, dtype=torch.float32) if ne else None
+        d_col = torch.zeros(ctx.shapes[1], device=emb.device, dtype=torch.float32) if nc else None
+        d_dir = torch.zeros(ctx.shapes[2], device=emb.device, dtype=torch.float32) if nd else None
+        if ne or nc or nd:
+            dX0c, dEc = _f32c(dX0), _f32c(dE)
+            with _launch(name="nbr_features_bwd"):
+                check(lib().hnr_nbr_features_bwd(ptr(dX0c), ptr(dEc), ptr(emb), ptr(pidx), None, ptr(vlist), ptr(raydirs), ptr(ctx.cam), Nv, K,
+                                                 ptr(d_emb), ptr(d_col), ptr(d_dir), stream()), "nbr_features_bwd")
+        return (d_emb, d_col, d_dir, d_confc, dW1, db1, dW2, db2, dW3, db3, dW4, db4, d_wa.view(ctx.shapes[3]), d_ba.view(ctx.shapes[4]), None)
 
 
 # --------------------------------------------------------------------------------------------

@@ -131,6 +131,7 @@ class PointAggregator(nn.Module):
         # always use the layer kernels.
         self.mlp_engine = "tc"
         self.max_valid_chunk = 262144        # valid samples decoded per pass in no-grad mode (bounds activation memory)
+        self.fused_train_forward = True      # graph-recording forwards of the per-neighbour stage also use the fused kernel
 
     @staticmethod
     def _check_supported(opt):
@@ -230,6 +231,13 @@ class PointAggregator(nn.Module):
                 else:
                     sigma, X5 = mlp_tc.forward(tables, pidx, vlist, loc_w, loc_pers, raydirs, cam, weight, confc, pack[0], pack[1],
                                                self.alpha_branch[0].weight, self.alpha_branch[0].bias)
+        elif self.mlp_engine == "tc" and torch.is_grad_enabled() and K == 8 and mask is None and self.fused_train_forward:
+            # training: the same fused kernel, with the four layers' activations saved for the tensor-core backward
+            with ops.tag("nbr_mlp"):
+                sigma, X5 = ops.NbrMlpFusedFn.apply(emb, color, dirs, confc, b1[0].weight, b1[0].bias, b1[2].weight, b1[2].bias,
+                                                    b3[0].weight, b3[0].bias, b3[2].weight, b3[2].bias, self.alpha_branch[0].weight,
+                                                    self.alpha_branch[0].bias,
+                                                    (xyz, xyz_pers, pidx, vlist, loc_w, loc_pers, raydirs, cam, weight, self._packed_weights()))
         else:
             with ops.tag("gather"):
                 X0, E = ops.NbrFeaturesFn.apply(emb, color, dirs, xyz, xyz_pers, pidx, mask, vlist, loc_w, loc_pers, raydirs, cam)
@@ -292,10 +300,15 @@ class PointAggregator(nn.Module):
         """TF32 hi/lo images of block1/block3 for the tensor-core kernel, re-packed when a weight changes"""
         ps = [self.block1[0].weight, self.block1[2].weight, self.block3[0].weight, self.block3[2].weight,
               self.block1[0].bias, self.block1[2].bias, self.block3[0].bias, self.block3[2].bias]
-        key = (self.mlp_engine,) + tuple((p.data_ptr(), p._version) for p in ps)
+        train = torch.is_grad_enabled()
+        key = (self.mlp_engine, train) + tuple((p.data_ptr(), p._version) for p in ps)
         if getattr(self, "_pack_key", None) != key:
             from . import mlp_tc
-            self._wpack_cache = (mlp_tc.pack_mlp_f16 if self.mlp_engine == "tc" else mlp_tc.pack_mlp)(self.block1, self.block3)
+            if self.mlp_engine == "tc":
+                # graph-recording forwards re-pack after every optimiser step: fixed weight scale, no host read-back
+                self._wpack_cache = mlp_tc.pack_mlp_f16(self.block1, self.block3, weight_scale=mlp_tc.TRAIN_WEIGHT_SCALE if train else None)
+            else:
+                self._wpack_cache = mlp_tc.pack_mlp(self.block1, self.block3)
             self._pack_key = key
         return self._wpack_cache
 

@@ -161,14 +161,15 @@ int hnr_mlp_tc_forward(const float* xyz, const float* xyz_pers, const float* emb
  * accumulators so that epilogue l overlaps the MMAs of layer l+1 (csrc/nbr_mlp_f16.cu).  wpack: 67 chunk images in
  * consumption order; bias (4,256) with rows 0..2 pre-multiplied by the next layer's input scale; mul[4]: accumulator ->
  * pre-activation factors; scale0/scale2: input scales of the generated features / the block3 extras (all built by
- * hybridneuralrendering_b200/mlp_tc.py: pack_mlp_f16).  dbg: optional (4, Nv*8, 256) per-layer activations, else NULL. */
+ * hybridneuralrendering_b200/mlp_tc.py: pack_mlp_f16).  dbg: optional (4, Nv*8, 256) per-layer activations (saved by the
+ * training forward for the backward pass, and the taps of the parity test), else NULL. */
 int64_t hnr_nbr_mlp_f16_packed_bytes(void);
 int hnr_nbr_mlp_f16_forward(const float* xyz, const float* xyz_pers, const float* emb, const float* color, const float* dir,
                             const int32_t* pidx, const int32_t* vlist, const float* loc_w, const float* loc_pers,
                             const float* raydirs, const float* cam, const float* weight, const float* confc, const void* wpack,
                             const float* bias, const float* walpha, const float* balpha, const float* mul /* host, 4 */,
-                            float scale0, float scale2, int64_t Nv, int64_t K, float* sigma /* Nv */, float* X5 /* Nv,280 */,
-                            float* dbg, void* stream);
+                            float scale0, float scale2, float inv_act, int64_t Nv, int64_t K, float* sigma /* Nv */,
+                            float* X5 /* Nv,280 */, float* dbg, float* araw /* Nv*8, with dbg */, void* stream);
 
 /* Fused chain of up to 4 dense layers (widths <= 128) on tcgen05, 3xFP16 split (csrc/chain_f16.cu): the per-sample MLPs
  * color_feature_branch, aux_merge_weight_block (+ sigmoid head), color_mixup_block (+ residual) of

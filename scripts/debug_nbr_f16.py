@@ -33,7 +33,7 @@ def layer_errors(R=64, SR=24, empty=0.4, seed=3, N=4000):
         vlist = torch.nonzero(valid).view(-1).to(torch.int32)
         X0, E = ops.NbrFeaturesFn.apply(emb, color, dirs, xyz, None, pidx, None, vlist, loc_w, loc_pers, raydirs, cam)
         pack = mlp_tc.pack_mlp_f16(agg.block1, agg.block3)
-        sigma, X5, dbg = mlp_tc.forward_f16(tables, pidx, vlist, loc_w, loc_pers, raydirs, cam, weight, confc, pack,
+        sigma, X5, dbg, araw_k = mlp_tc.forward_f16(tables, pidx, vlist, loc_w, loc_pers, raydirs, cam, weight, confc, pack,
                                             agg.alpha_branch[0].weight, agg.alpha_branch[0].bias, debug=True)
         torch.cuda.synchronize()
         f = lambda lin, x: torch.nn.functional.leaky_relu(torch.nn.functional.linear(x, lin.weight.double(), lin.bias.double()), 0.01)
@@ -44,7 +44,7 @@ def layer_errors(R=64, SR=24, empty=0.4, seed=3, N=4000):
         refs = [h1, h2, h3, h4]
         errs = []
         for l in range(4):
-            got = dbg[l].double() / (mlp_tc.ACT_SCALE if l < 3 else 1.0)
+            got = dbg[l].double()
             errs.append((float((got - refs[l]).abs().max()), float(refs[l].abs().max())))
         # heads
         Nv = vlist.shape[0]
@@ -57,11 +57,12 @@ def layer_errors(R=64, SR=24, empty=0.4, seed=3, N=4000):
         # view encoding columns against the exact path
         _, X5_ref = ops.AlphaKSumFn.apply(h4.float(), confc, agg.alpha_branch[0].weight, agg.alpha_branch[0].bias, weight, vlist, raydirs, cam)
         errs.append((float((X5[:, 256:] - X5_ref[:, 256:]).abs().max()), 1.0))
+        errs.append((float((araw_k.double().view(Nv, 8) - araw).abs().max()), float(araw.abs().max())))
     return errs
 
 
 if __name__ == "__main__":
-    names = ["layer0", "layer1", "layer2", "layer3", "sigma", "ksum", "viewpe"]
+    names = ["layer0", "layer1", "layer2", "layer3", "sigma", "ksum", "viewpe", "araw"]
     for cfg in [dict(R=3, SR=5, empty=0.0), dict(R=64, SR=24, empty=0.4), dict(R=300, SR=80, empty=0.2)]:
         errs = layer_errors(**cfg)
         print(cfg, " ".join(f"{n}: {e:.2e}/{s:.2e}" for n, (e, s) in zip(names, errs)), flush=True)

@@ -107,7 +107,7 @@ def test_f16_kernel_layers_match_fp64(R, SR, empty):
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
     from debug_nbr_f16 import layer_errors
     errs = layer_errors(R=R, SR=SR, empty=empty, seed=R + SR)
-    for name, (e, scale) in zip(["layer0", "layer1", "layer2", "layer3", "sigma", "ksum", "viewpe"], errs):
+    for name, (e, scale) in zip(["layer0", "layer1", "layer2", "layer3", "sigma", "ksum", "viewpe", "araw"], errs):
         assert e <= 1e-5 * scale + 1e-7, (name, e, scale)
 
 
