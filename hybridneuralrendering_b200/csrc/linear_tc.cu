@@ -27,9 +27,9 @@ constexpr int NSA = 8;                       // activation ring depth
 constexpr int A_PART = TM * KC * 4;          // 4096
 constexpr int A_STAGE = 2 * A_PART;          // hi + lo
 constexpr int W_STAGE_MAX = 2 * 256 * KC * 4;   // 16384
-constexpr int NCONV_WARPS = 8, NEPI_WARPS = 4;
+constexpr int NCONV_WARPS = 8, NEPI_WARPS = 8;   // two epilogue warps per TMEM lane quarter, alternating 16-column steps
 constexpr int WARP_MMA = NCONV_WARPS + NEPI_WARPS, WARP_TMA = WARP_MMA + 1;
-constexpr int NTHREADS = (WARP_TMA + 1) * 32;   // 448
+constexpr int NTHREADS = (WARP_TMA + 1) * 32;   // 576
 constexpr int SUPER = 4;                     // K-chunks per super-chunk
 
 constexpr int OFF_W = 0;
@@ -202,30 +202,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(LArgs L) {
             for (int jj = 0; jj < 4; ++jj) dst[jj] = load4(L, tile * TM + warp * 16 + jj * 4 + rsub, k0);
         };
         uint32_t it = 0;
+        // a super-chunk fills up to SUPER ring slots at once: wait for all of them, let EVERY lane store its own 16-byte piece
+        // (lane's chunk = u_of), then one proxy fence and one arrive per slot
         auto process = [&](int64_t q, const float4 (&src)[4]) {
             const int c0 = (int)(q % nsc) * SUPER;
+            const int nvalid = min(SUPER, nchunk - c0);
 #pragma unroll
             for (int u = 0; u < SUPER; ++u) {
-                if (c0 + u < nchunk) {
-                    const uint32_t s = it % NSA, ph = (it / NSA) & 1;
-                    ++it;
+                if (u < nvalid) {
+                    const uint32_t s = (it + u) % NSA, ph = ((it + u) / NSA) & 1;
                     mbar_wait(bar_emptyA + 8 * s, ph ^ 1);
-                    if (u_of == u) {
-                        uint8_t* st = smem + OFF_A + s * A_STAGE + h_of * A_LBO;
-#pragma unroll
-                        for (int jj = 0; jj < 4; ++jj) {
-                            float4 hi, lo;
-                            split4(src[jj], hi, lo);
-                            const int row = warp * 16 + jj * 4 + rsub;
-                            *reinterpret_cast<float4*>(st + row * 16) = hi;
-                            *reinterpret_cast<float4*>(st + A_PART + row * 16) = lo;
-                        }
-                    }
-                    fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_fullA + 8 * s);
                 }
             }
+            if (u_of < nvalid) {
+                uint8_t* st = smem + OFF_A + ((it + u_of) % NSA) * A_STAGE + h_of * A_LBO;
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    float4 hi, lo;
+                    split4(src[jj], hi, lo);
+                    const int row = warp * 16 + jj * 4 + rsub;
+                    *reinterpret_cast<float4*>(st + row * 16) = hi;
+                    *reinterpret_cast<float4*>(st + A_PART + row * 16) = lo;
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane < nvalid) mbar_arrive(bar_fullA + 8 * ((it + lane) % NSA));
+            it += nvalid;
         };
 #pragma unroll
         for (int d = 0; d < DEPTH; ++d)
@@ -241,8 +244,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(LArgs L) {
         }
     } else {
         // ---------------- epilogue: TMEM -> bias / activation / residual -> global ----------------
-        const int q = warp & 3;                                    // TMEM lane quarter this warp may access
+        // Two warps serve each TMEM lane quarter and take alternate 16-column steps (with a fused head one warp takes all
+        // steps of its rows: the dot product needs the whole row).  The common case -- full 16-column step, vector store,
+        // LeakyReLU or no activation, no residual / head -- runs without per-element branches.
+        const int ew = warp - NCONV_WARPS;
+        const int q = ew & 3, half = ew >> 2;                      // TMEM lane quarter, step parity
         const int erow = q * 32 + lane;
+        const bool solo = L.head_w != nullptr;                     // head: half 0 does every step, half 1 only signals
+        const bool vec_ok = L.Y && (L.ldy & 3) == 0 && (reinterpret_cast<uintptr_t>(L.Y) & 15) == 0;
+        const bool simple = !L.res && !L.head_w && (L.act == HNR_ACT_LRELU || L.act == HNR_ACT_NONE);
+        const float slope = L.act == HNR_ACT_LRELU ? 0.01f : 1.f;
         uint32_t tcount = 0;
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
             const uint32_t b = tcount & 1, bph = (tcount >> 1) & 1;
@@ -251,34 +262,49 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(LArgs L) {
             const int64_t m = tile * TM + erow;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + b * (uint32_t)L.Npad;
             float dot = 0.f;
-            for (int n0 = 0; n0 < L.Npad; n0 += 16) {
-                float v[16];
-                tmem_ld16(taddr + n0, v);
-                if (m < L.M) {
+            if (!(solo && half == 1)) {
+                const int step0 = solo ? 0 : half, dstep = solo ? 1 : 2;
+                for (int st = step0; st * 16 < L.Npad; st += dstep) {
+                    const int n0 = st * 16;
+                    float v[16];
+                    tmem_ld16(taddr + n0, v);
+                    if (m < L.M) {
+                        if (simple && vec_ok && n0 + 16 <= L.N) {
+                            const float4* b4 = reinterpret_cast<const float4*>(bias_s + n0);
+                            float4* o = reinterpret_cast<float4*>(L.Y + m * L.ldy + n0);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int n = n0 + i;
-                        if (n < L.N) {
-                            float y = apply_act(v[i] + bias_s[n], L.act);
-                            if (L.res) y += L.res[m * L.ldres + n];
-                            if (L.head_w) dot = fmaf(y, __ldg(L.head_w + n), dot);
-                            v[i] = y;
-                        }
-                    }
-                    if (L.Y) {
-                        float* o = L.Y + m * L.ldy + n0;
-                        if (n0 + 16 <= L.N && (L.ldy & 3) == 0 && (reinterpret_cast<uintptr_t>(L.Y) & 15) == 0) {
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(o)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                            for (int i = 0; i < 4; ++i) {
+                                const float4 bb = b4[i];
+                                const float t0 = v[4 * i] + bb.x, t1 = v[4 * i + 1] + bb.y, t2 = v[4 * i + 2] + bb.z, t3 = v[4 * i + 3] + bb.w;
+                                o[i] = make_float4(fmaxf(t0, slope * t0), fmaxf(t1, slope * t1), fmaxf(t2, slope * t2), fmaxf(t3, slope * t3));
+                            }
                         } else {
 #pragma unroll
-                            for (int i = 0; i < 16; ++i)
-                                if (n0 + i < L.N) o[i] = v[i];
+                            for (int i = 0; i < 16; ++i) {
+                                const int n = n0 + i;
+                                if (n < L.N) {
+                                    float y = apply_act(v[i] + bias_s[n], L.act);
+                                    if (L.res) y += L.res[m * L.ldres + n];
+                                    if (L.head_w) dot = fmaf(y, __ldg(L.head_w + n), dot);
+                                    v[i] = y;
+                                }
+                            }
+                            if (L.Y) {
+                                float* o = L.Y + m * L.ldy + n0;
+                                if (n0 + 16 <= L.N && vec_ok) {
+#pragma unroll
+                                    for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(o)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                                } else {
+#pragma unroll
+                                    for (int i = 0; i < 16; ++i)
+                                        if (n0 + i < L.N) o[i] = v[i];
+                                }
+                            }
                         }
                     }
                 }
+                if (L.head_w && m < L.M) L.out_head[m] = apply_act(dot + L.head_b[0], L.head_act);
             }
-            if (L.head_w && m < L.M) L.out_head[m] = apply_act(dot + L.head_b[0], L.head_act);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_accE + 8 * b);
