@@ -48,13 +48,7 @@ struct WArgs {
     int N, K, KWp, half;        // KWp: padded width of [X | 1]; half = KWp when one MMA group, else KWp / 2
 };
 
-__device__ __forceinline__ float x_load(const WArgs& A, int64_t m, int k) {
-    int s = 0;
-    if (k >= A.k[0]) { k -= A.k[0]; s = 1; if (k >= A.k[1]) { k -= A.k[1]; s = 2; } }
-    if (A.mod[s] > 0) m %= A.mod[s];
-    return __ldg(A.x[s] + m * A.ld[s] + k);
-}
-
+template <bool HAS_MOD>
 __global__ void __launch_bounds__(NTHREADS, 1) wgrad_tc_kernel(const __grid_constant__ WArgs A) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -114,38 +108,70 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_tc_kernel(const __grid_cons
         }
     } else {
         // ================= generators: transposing loads -> TF32 hi/lo core matrices =================
+        // task = warp + 8t.  Tasks t < NA are A-side (dY) patches, the rest B-side (X | 1).  Both task counts are even, so the
+        // K-half of a patch is h = warp & 1 and its 8-column group g = (warp >> 1) + 4t (A) / (warp >> 1) + 4(t - NA) (B).
+        // Everything that depends only on the patch -- column pointer, row stride, destination -- is resolved once; a step
+        // costs one address + one load per patch, then one split + two stores.
         const int j = lane >> 2, mi = lane & 3;                // patch element: column 8g + j, row 4h + mi
+        constexpr int NA = 2 * (TN / 8) / NGEN_WARPS;
         const int ntask_a = 2 * (TN / 8), ntask = ntask_a + 2 * (A.KWp / 8);
+        const int h = warp & 1, crow = 4 * h + mi;
+        const float* cptr[MAX_TASKS];                          // column base (row 0); nullptr = constant column
+        const float* gptr[NA];                                 // saved-output column for the activation derivative
+        int cld[MAX_TASKS];                                    // row stride
+        int csrc[MAX_TASKS];                                   // source index (row re-use modulus lookup), HAS_MOD only
+        uint32_t ones_mask = 0;                                // bit t: the patch column is the column of ones (-> db)
+        const uint32_t dbase_a = (uint32_t)h * A_LBO + (uint32_t)(warp >> 1) * 128u + (uint32_t)lane * 4u;
+        const uint32_t dbase_b = 2u * A_PART + (uint32_t)h * B_LBO + (uint32_t)(warp >> 1) * 128u + (uint32_t)lane * 4u;
+#pragma unroll
+        for (int t = 0; t < MAX_TASKS; ++t) {
+            cptr[t] = nullptr; cld[t] = 0; csrc[t] = 0;
+            if (t < NA) gptr[t] = nullptr;
+            if (warp + t * NGEN_WARPS < ntask) {
+                const int col = 8 * ((warp >> 1) + 4 * (t < NA ? t : t - NA)) + j;
+                if (t < NA) {
+                    const int n = n0 + col;
+                    if (n < A.N) {
+                        cptr[t] = A.dY + n; cld[t] = A.lddy;
+                        if (A.act != HNR_ACT_NONE) gptr[t] = A.Y + n;
+                    }
+                } else if (col < A.K) {
+                    int s_ = 0, k = col;
+                    if (k >= A.k[0]) { k -= A.k[0]; s_ = 1; if (k >= A.k[1]) { k -= A.k[1]; s_ = 2; } }
+                    cptr[t] = A.x[s_] + k; cld[t] = A.ld[s_]; csrc[t] = s_;
+                } else if (col == A.K) {
+                    ones_mask |= 1u << t;
+                }
+            }
+        }
         int64_t step = 0;
         for (int64_t sit = 0; sit < my_super; ++sit) {
             const int64_t ms = (blockIdx.x + sit * gridDim.x) * (int64_t)(SUPER * KC);
             float val[SUPER][MAX_TASKS];
-            float gate[SUPER][2 * (TN / 8) / NGEN_WARPS];       // saved outputs of the A-side patches (tasks t < 4); used after all loads are issued
+            float gate[SUPER][NA];
 #pragma unroll
             for (int q = 0; q < SUPER; ++q) {
+                const int64_t m = ms + q * KC + crow;
+                const bool inr = m < A.M;
+                int64_t mm[3] = {m, m, m};
+                if (HAS_MOD) {
+#pragma unroll
+                    for (int s_ = 0; s_ < 3; ++s_)
+                        if (A.mod[s_] > 0) mm[s_] = m % A.mod[s_];
+                }
 #pragma unroll
                 for (int t = 0; t < MAX_TASKS; ++t) {
-                    const int task = warp + t * NGEN_WARPS;
                     float v = 0.f;
-                    if (task < ntask) {
-                        const bool isa = task < ntask_a;
-                        const int tt = isa ? task : task - ntask_a;
-                        const int g = tt >> 1, h = tt & 1;
-                        const int64_t m = ms + q * KC + 4 * h + mi;
-                        const int col = 8 * g + j;
-                        if (m < A.M) {
-                            if (isa) {
-                                const int n = n0 + col;
-                                if (n < A.N) {
-                                    v = __ldg(A.dY + m * A.lddy + n);
-                                    if (t < 2 * (TN / 8) / NGEN_WARPS) gate[q][t] = A.act != HNR_ACT_NONE ? __ldg(A.Y + m * A.ldy + n) : 1.f;
-                                }
-                            } else {
-                                v = col < A.K ? x_load(A, m, col) : (col == A.K ? 1.f : 0.f);
-                            }
+                    if (inr) {
+                        if (cptr[t]) {
+                            const int64_t row = (HAS_MOD && t >= NA) ? (csrc[t] == 0 ? mm[0] : (csrc[t] == 1 ? mm[1] : mm[2])) : m;
+                            v = __ldg(cptr[t] + row * cld[t]);
+                        } else if ((ones_mask >> t) & 1u) {
+                            v = 1.f;
                         }
                     }
                     val[q][t] = v;
+                    if (t < NA) gate[q][t] = (inr && gptr[t]) ? __ldg(gptr[t] + m * A.ldy) : 1.f;
                 }
             }
 #pragma unroll
@@ -157,19 +183,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_tc_kernel(const __grid_cons
                     uint8_t* st = smem + s * STAGE_BYTES;
 #pragma unroll
                     for (int t = 0; t < MAX_TASKS; ++t) {
-                        const int task = warp + t * NGEN_WARPS;
-                        if (task < ntask) {
-                            const bool isa = task < ntask_a;
-                            const int tt = isa ? task : task - ntask_a;
-                            const int g = tt >> 1, h = tt & 1;
+                        if (warp + t * NGEN_WARPS < ntask) {
                             float v = val[q][t];
-                            if (t < 2 * (TN / 8) / NGEN_WARPS && A.act != HNR_ACT_NONE && v != 0.f) v *= act_grad_from_out(gate[q][t], A.act);
+                            if (t < NA && gptr[t]) v *= act_grad_from_out(gate[q][t], A.act);
                             const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u), lo = v - hi;
-                            uint8_t* base = isa ? st : st + 2 * A_PART;
-                            const uint32_t part = isa ? (uint32_t)A_PART : b_part, lbo = isa ? A_LBO : B_LBO;
-                            float* dst = reinterpret_cast<float*>(base + h * lbo + g * 128) + lane;
-                            *dst = hi;
-                            *reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(dst) + part) = lo;
+                            const uint32_t off = t < NA ? dbase_a + (uint32_t)t * 512u : dbase_b + (uint32_t)(t - NA) * 512u;
+                            *reinterpret_cast<float*>(st + off) = hi;
+                            *reinterpret_cast<float*>(st + off + (t < NA ? (uint32_t)A_PART : b_part)) = lo;
                         }
                     }
                     fence_proxy_async();
@@ -221,16 +241,19 @@ extern "C" int hnr_linear_tc_bwd_weight(const float* dY, int64_t lddy, const flo
     A.dW = dW; A.db = db; A.M = M; A.N = (int)N; A.K = (int)K; A.KWp = (int)kw; A.half = (int)half;
     static bool configured = false;
     if (!configured) {
-        HNR_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        HNR_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        HNR_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         configured = true;
     }
+    const bool has_mod = A.mod[0] > 0 || A.mod[1] > 0 || A.mod[2] > 0;
     const int ny = (int)hnr_cdiv(N, TN);
     const int64_t nsteps = hnr_cdiv(M, KC);
     const int64_t nsuper = hnr_cdiv(nsteps, SUPER);
     int gx = HNR_NUM_SMS / ny;
     if (gx < 1) gx = 1;
     if (nsuper < gx) gx = (int)nsuper;
-    wgrad_tc_kernel<<<dim3((unsigned)gx, (unsigned)ny), NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(A);
+    if (has_mod) wgrad_tc_kernel<true><<<dim3((unsigned)gx, (unsigned)ny), NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(A);
+    else wgrad_tc_kernel<false><<<dim3((unsigned)gx, (unsigned)ny), NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(A);
     HNR_CHECK_LAUNCH("linear_tc_bwd_weight");
     return HNR_OK;
 }
