@@ -40,21 +40,47 @@ def peaks():
 
 
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region (NVML every 20 ms; nvidia-smi as a fallback)."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
         self.index, self.rows, self.stop = index, [], False
         self.t = threading.Thread(target=self.run, daemon=True)
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        except Exception:
+            self.nvml = None
+
+    def sample_nvml(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM)
+        r = n.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") else \
+            n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        g = lambda name, alt: getattr(n, name, getattr(n, alt, 0))
+        bits = [g("nvmlClocksEventReasonHwSlowdown", "nvmlClocksThrottleReasonHwSlowdown"),
+                g("nvmlClocksEventReasonHwThermalSlowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"),
+                g("nvmlClocksEventReasonSwThermalSlowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"),
+                g("nvmlClocksEventReasonSwPowerCap", "nvmlClocksThrottleReasonSwPowerCap")]
+        return [str(sm), str(mx)] + ["Active" if (b and (r & b)) else "Not Active" for b in bits]
 
     def run(self):
         while not self.stop:
             try:
+                if self.nvml is not None:
+                    self.rows.append(self.sample_nvml())
+                    time.sleep(0.02)
+                    continue
                 o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
                                    capture_output=True, text=True, timeout=5).stdout.strip()
                 if o:
                     self.rows.append([x.strip() for x in o.split(",")])
             except Exception:
-                pass
+                self.nvml = None
             time.sleep(0.2)
 
     def __enter__(self):
@@ -175,7 +201,7 @@ def sample_query(xyz, att, fr, P, dev):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="product")
     ap.add_argument("--no-cpu-baseline", action="store_true")

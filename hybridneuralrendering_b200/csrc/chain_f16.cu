@@ -71,7 +71,6 @@ struct ChainArgs {
     int head_act;
     float* head_out;
     int64_t M;
-    int wait_mode;
     long long* trace;            // optional event trace of CTA 0 (bring-up / profiling): [count, (clock, id, a, b) ...]
 };
 
@@ -100,32 +99,22 @@ __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
     hi = make_uint4(h[0], h[1], h[2], h[3]);
     lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
-// wait policy experiment: mode 0 = plain polling, 1 = nanosleep between polls, 2 = try_wait with a suspend-time hint
-__device__ __forceinline__ void mbar_wait_mode(uint32_t bar, uint32_t parity, unsigned ns, int mode) {
+// mbarrier wait for warps that are ahead of the pipeline anyway: poll, then sleep between polls (polling, sleeping and
+// try_wait with a suspend-time hint were measured to perform identically here; sleeping leaves the issue slots to the others)
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, unsigned ns) {
     uint32_t done;
     for (;;) {
-        if (mode == 2) {
-            asm volatile(
-                "{\n\t.reg .pred p;\n\t"
-                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-                "selp.u32 %0, 1, 0, p;\n\t}"
-                : "=r"(done)
-                : "r"(bar), "r"(parity), "r"(ns)
-                : "memory");
-        } else {
-            asm volatile(
-                "{\n\t.reg .pred p;\n\t"
-                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                "selp.u32 %0, 1, 0, p;\n\t}"
-                : "=r"(done)
-                : "r"(bar), "r"(parity)
-                : "memory");
-        }
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
         if (done) break;
-        if (mode == 1) __nanosleep(ns);
+        __nanosleep(ns);
     }
 }
-#define mbar_wait_relaxed(bar, parity, ns) mbar_wait_mode(bar, parity, ns, A.wait_mode)
 // light-weight event trace of CTA 0 (profiling aid): each traced thread appends (clock64, tag) pairs to its own region
 constexpr int TRACE_CAP = 4096;
 #define TRACE_DECL(role) long long* tr__ = (A.trace && blockIdx.x == 0) ? A.trace + (role) * 2 * TRACE_CAP : nullptr; int trn__ = 0
@@ -510,7 +499,6 @@ extern "C" int hnr_chain_f16_forward(const float* const* src, const int64_t* src
     HNR_CHECK_ARG(!head_w || (head_b && head_out), "chain_f16_forward: head needs head_b and head_out");
     A.in_scale = in_scale; A.nlayer = nlayer; A.wpack = (const uint8_t*)wpack; A.bias = bias; A.res = res; A.ldres = (int)ldres;
     A.head_w = head_w; A.head_b = head_b; A.head_act = head_act; A.head_out = head_out; A.M = M;
-    { const char* e = getenv("HNR_WAIT_MODE"); A.wait_mode = e ? atoi(e) : 1; }
     A.trace = g_chain_trace;
     static bool configured = false;
     if (!configured) {

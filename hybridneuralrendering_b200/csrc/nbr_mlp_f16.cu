@@ -117,6 +117,10 @@ __device__ __forceinline__ void rot3(const float* m, float x, float y, float z, 
     oy = x * m[1] + y * m[4] + z * m[7];
     oz = x * m[2] + y * m[5] + z * m[8];
 }
+// sin/cos of small arguments (|x| of a few radians: embedding channels, scaled distances, view directions) on the MUFU
+// pipe: absolute error ~5e-7, two orders of magnitude below what rtol 1e-4 on the rendered output needs, at a fifth
+// of the instructions of the full-range routine
+__device__ __forceinline__ void sincos_fast(float x, float* s, float* c) { __sincosf(x, s, c); }
 __device__ __forceinline__ float softplus_t(float x) { return x > 20.f ? x : log1pf(expf(x)); }
 
 // two fp32 -> packed fp16x2 {lo half = a, hi half = b}, round to nearest, saturating at +-65504 (an activation beyond fp16's
@@ -377,10 +381,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) nbr_mlp_f16_kernel(F16Args A) {
 #pragma unroll
             for (int j = 0; j < 6; ++j) {                  // encoded distances: idx = f*12 + (sin|cos)*6 + component
                 float a, b;                                // octaves 0 and 2 evaluated directly, 1, 3, 4 by angle doubling
-                sincosf(d[j], &a, &b);
+                sincos_fast(d[j], &a, &b);
                 pe[j] = a; pe[6 + j] = b;
                 pe[12 + j] = 2.f * a * b; pe[18 + j] = 1.f - 2.f * a * a;
-                sincosf(d[j] * 4.f, &a, &b);
+                sincos_fast(d[j] * 4.f, &a, &b);
                 pe[24 + j] = a; pe[30 + j] = b;
                 float a2 = 2.f * a * b, b2 = 1.f - 2.f * a * a;
                 pe[36 + j] = a2; pe[42 + j] = b2;
@@ -390,7 +394,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nbr_mlp_f16_kernel(F16Args A) {
             for (int i = 0; i < 60; ++i) pe[i] *= sc0;
             pe[60] = pe[61] = pe[62] = pe[63] = 0.f;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) sincosf(ef[i], &sn[i], &cs[i]);
+            for (int i = 0; i < 32; ++i) sincos_fast(ef[i], &sn[i], &cs[i]);
             auto put = [&](const float* v) {
                 const uint32_t st = ait % NSA, ph = (ait / NSA) & 1;
                 ++ait;
