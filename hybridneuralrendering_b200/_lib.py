@@ -67,8 +67,8 @@ _SIGS = {
     "hnr_chain_f16_set_trace": (None, [vp]),
     "hnr_chain_f16_forward": (C.c_int, [C.POINTER(vp), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), f32c, C.c_int, C.POINTER(i64),
                                         C.POINTER(i64), C.POINTER(i64), C.POINTER(C.c_int), vp, C.POINTER(i64), vp, C.POINTER(f32c),
-                                        C.POINTER(f32c), C.POINTER(vp), C.POINTER(i64), vp, i64, vp, vp, C.c_int, vp, i64, vp]),
-    "hnr_nbr_mlp_f16_forward": (C.c_int, [vp] * 17 + [C.POINTER(C.c_float), f32c, f32c, f32c, i64, i64, vp, vp, vp, vp, vp]),
+                                        C.POINTER(f32c), C.POINTER(vp), C.POINTER(i64), vp, i64, vp, vp, C.c_int, vp, i64, vp, vp]),
+    "hnr_nbr_mlp_f16_forward": (C.c_int, [vp] * 17 + [C.POINTER(C.c_float), f32c, f32c, f32c, i64, i64, vp, vp, vp, vp, vp, vp]),
 }
 
 EXPORTED = sorted(_SIGS)

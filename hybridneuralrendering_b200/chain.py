@@ -130,6 +130,7 @@ def chain_forward(pc: PackedChain, srcs: Sequence[torch.Tensor], M: Optional[int
                                           i64_array(pc.Kp), i64_array(pc.N), i64_array(pc.Np), i4(pc.acts), ptr(pc.wpack),
                                           i64_array(pc.w_off), ptr(pc.bias), f4(pc.mul), f4(pc.inv_next), ptr_array(Ys),
                                           i64_array([y.stride(0) if y is not None else 0 for y in Ys]), ptr(resv),
-                                          resv.stride(0) if resv is not None else 0, ptr(hw), ptr(hb), hact, ptr(head_out), M, stream()),
+                                          resv.stride(0) if resv is not None else 0, ptr(hw), ptr(hb), hact, ptr(head_out), M,
+                                          ptr(ops.status_word(dev)), stream()),
               "chain_f16_forward")
     return Ys[nl - 1], head_out, Ys[:-1]

@@ -71,6 +71,7 @@ struct ChainArgs {
     int head_act;
     float* head_out;
     int64_t M;
+    int32_t* status;             // optional: bit 1 is set when a scaled value left fp16's range and was saturated
     long long* trace;            // optional event trace of CTA 0 (bring-up / profiling): [count, (clock, id, a, b) ...]
 };
 
@@ -321,6 +322,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) chain_f16_kernel(const __grid_con
                     for (int i = 0; i < 8; ++i) {
                         const int r = 32 * gw + 4 * i + rsub;
                         const float a = v[i].x * sc, b = v[i].y * sc, c = v[i].z * sc, d = v[i].w * sc;
+                        if (fmaxf(fmaxf(fabsf(a), fabsf(b)), fmaxf(fabsf(c), fabsf(d))) > 65000.f && A.status) atomicOr(A.status, 2);
                         const uint32_t h0 = pack_sat(a, b), h1 = pack_sat(c, d);
                         const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&h0)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&h1));
                         const uint32_t l0 = pack_sat(a - f0.x, b - f0.y), l1 = pack_sat(c - f1.x, d - f1.y);
@@ -423,6 +425,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) chain_f16_kernel(const __grid_con
                         }
                     }
                     if (!last) {
+                        float am = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) am = fmaxf(am, fabsf(y[i]));
+                        if (am > 65000.f && A.status) atomicOr(A.status, 2);
                         uint4 hi, lo;
                         uint8_t* dst = act_hi + (c0 >> 3) * A_LBO + r * 16;
                         split8(y, hi, lo);
@@ -477,7 +483,7 @@ extern "C" int hnr_chain_f16_forward(const float* const* src, const int64_t* src
                                      float in_scale, int nlayer, const int64_t* Kp, const int64_t* N, const int64_t* Np, const int* act,
                                      const void* wpack, const int64_t* w_off, const float* bias, const float* mul, const float* inv_next,
                                      float* const* Y, const int64_t* ldy, const float* res, int64_t ldres, const float* head_w,
-                                     const float* head_b, int head_act, float* head_out, int64_t M, void* stream) {
+                                     const float* head_b, int head_act, float* head_out, int64_t M, int32_t* status, void* stream) {
     HNR_CHECK_ARG(nlayer >= 1 && nlayer <= MAXL, "chain_f16_forward: 1..4 layers");
     if (M == 0) return HNR_OK;
     ChainArgs A{};
@@ -500,6 +506,7 @@ extern "C" int hnr_chain_f16_forward(const float* const* src, const int64_t* src
     A.in_scale = in_scale; A.nlayer = nlayer; A.wpack = (const uint8_t*)wpack; A.bias = bias; A.res = res; A.ldres = (int)ldres;
     A.head_w = head_w; A.head_b = head_b; A.head_act = head_act; A.head_out = head_out; A.M = M;
     A.trace = g_chain_trace;
+    A.status = status;
     static bool configured = false;
     if (!configured) {
         HNR_CUDA(cudaFuncSetAttribute(chain_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));

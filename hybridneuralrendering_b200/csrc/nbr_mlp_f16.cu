@@ -71,6 +71,7 @@ struct F16Args {
     const float *bias, *walpha, *balpha;   // bias: (4,256), rows 0..2 pre-multiplied by the next layer's input scale
     float *sigma, *X5, *dbg, *araw;     // dbg: optional (4, Nv*8, 256) activations of every layer (training / tests); araw: (Nv*8) density pre-activation
     float inv_act;                      // 1 / input scale of layers 1..3 (the saved activations are unscaled)
+    int32_t* status;                    // optional: bit 0 is set when a scaled activation left fp16's range and was saturated
     int64_t Nv;
     float mul[NLAYER];             // accumulator -> (scaled) pre-activation factor per layer
     float scale0, scale2;          // input scales of layer 0 (generated features) and layer 2 (extras chunk)
@@ -455,6 +456,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nbr_mlp_f16_kernel(F16Args A) {
                 const float4* bl4 = reinterpret_cast<const float4*>(bias_s + l * HID + wg * 32);
                 uint32_t va[32], vb[32];
                 tmem_ld32_issue(taddr, va);
+                float amax = 0.f;                                      // largest scaled pre-activation magnitude of this thread's blocks
                 if (l < NLAYER - 1) {
 #pragma unroll
                     for (int jj = 0; jj < 4; ++jj) {
@@ -471,6 +473,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nbr_mlp_f16_kernel(F16Args A) {
                             const float t2 = fmaf(__uint_as_float(cur[4 * i4 + 2]), mul, bb.z), t3 = fmaf(__uint_as_float(cur[4 * i4 + 3]), mul, bb.w);
                             y[4 * i4 + 0] = fmaxf(t0, 0.01f * t0); y[4 * i4 + 1] = fmaxf(t1, 0.01f * t1);
                             y[4 * i4 + 2] = fmaxf(t2, 0.01f * t2); y[4 * i4 + 3] = fmaxf(t3, 0.01f * t3);
+                            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(t0), fabsf(t1)), fmaxf(fabsf(t2), fabsf(t3))));
                         }
                         if (DBG) {
                             const int64_t row = row0 + r;
@@ -493,6 +496,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nbr_mlp_f16_kernel(F16Args A) {
                         __syncwarp();
                         if (lane == 0) mbar_arrive(bar_actfull + 8 * j);
                     }
+                    if (amax > 65000.f && A.status) atomicOr(A.status, 1);      // the saturating pack clipped a value: results are not fp32-exact
                     if (l == 2) {           // accumulator 0 drained: layer 0 of the next tile may overwrite it
                         tc_fence_before();
                         __syncwarp();
@@ -588,7 +592,7 @@ extern "C" int hnr_nbr_mlp_f16_forward(const float* xyz, const float* xyz_pers, 
                                        const float* raydirs, const float* cam, const float* weight, const float* confc, const void* wpack,
                                        const float* bias, const float* walpha, const float* balpha, const float* mul, float scale0,
                                        float scale2, float inv_act, int64_t Nv, int64_t K, float* sigma, float* X5, float* dbg, float* araw,
-                                       void* stream) {
+                                       int32_t* status, void* stream) {
     HNR_CHECK_ARG(K == 8, "nbr_mlp_f16_forward: K must be 8 (128-row tiles hold 16 whole samples)");
     if (Nv == 0) return HNR_OK;
     F16Args A{};
@@ -597,7 +601,7 @@ extern "C" int hnr_nbr_mlp_f16_forward(const float* xyz, const float* xyz_pers, 
     A.wpack = (const uint8_t*)wpack; A.bias = bias; A.walpha = walpha; A.balpha = balpha; A.sigma = sigma; A.X5 = X5; A.dbg = dbg;
     A.Nv = Nv;
     for (int l = 0; l < NLAYER; ++l) A.mul[l] = mul[l];
-    A.scale0 = scale0; A.scale2 = scale2; A.inv_act = inv_act; A.araw = araw;
+    A.scale0 = scale0; A.scale2 = scale2; A.inv_act = inv_act; A.araw = araw; A.status = status;
     static bool configured = false;
     if (!configured) {
         HNR_CUDA(cudaFuncSetAttribute(nbr_mlp_f16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));

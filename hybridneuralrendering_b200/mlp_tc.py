@@ -198,5 +198,5 @@ def forward_f16(tables, pidx, vlist, loc_w, loc_pers, raydirs, cam, weight, conf
         check(lib().hnr_nbr_mlp_f16_forward(ptr(xyz), ptr(xyz_pers), ptr(emb), ptr(color), ptr(dirs), ptr(pidx), ptr(vlist), ptr(loc_w),
                                             ptr(loc_pers), ptr(raydirs), ptr(cam), ptr(weight), ptr(confc), ptr(wpack), ptr(bias), ptr(wa),
                                             ptr(ba), mul_c, float(s0), float(s2), 1.0 / ACT_SCALE, Nv, K, ptr(sigma), ptr(X5), ptr(dbg),
-                                            ptr(araw), stream()), "nbr_mlp_f16_forward")
+                                            ptr(araw), ptr(ops.status_word(pidx.device)), stream()), "nbr_mlp_f16_forward")
     return (sigma, X5, dbg, araw) if debug else (sigma, X5)

@@ -24,6 +24,37 @@ def _count(n: int = 1):
     LAUNCHES += n
 
 
+# Range guard of the split-fp16 tensor-core kernels: they saturate instead of overflowing and set a bit in this device word;
+# the host looks at it at its next natural synchronisation point (the query's count read-back) and raises.
+_STATUS = {}
+
+
+def status_word(dev) -> torch.Tensor:
+    key = torch.device(dev).index or 0
+    if key not in _STATUS:
+        _STATUS[key] = (torch.zeros(1, dtype=torch.int32, device=dev), torch.zeros(1, dtype=torch.int32).pin_memory())
+    return _STATUS[key][0]
+
+
+def status_fetch_async(dev) -> None:
+    """queue the copy of the status word to pinned host memory (call BEFORE a stream synchronisation)"""
+    key = torch.device(dev).index or 0
+    if key in _STATUS:
+        _STATUS[key][1].copy_(_STATUS[key][0], non_blocking=True)
+
+
+def status_check(dev) -> None:
+    """after the synchronisation: raise if a tensor-core kernel had to saturate a value"""
+    key = torch.device(dev).index or 0
+    if key in _STATUS and int(_STATUS[key][1][0]) != 0:
+        bits = int(_STATUS[key][1][0])
+        _STATUS[key][0].zero_()
+        _STATUS[key][1].zero_()
+        raise RuntimeError(f"hybridneuralrendering_b200: a split-fp16 tensor-core kernel saturated an activation (status {bits}: "
+                           "1 = per-neighbour MLP, 2 = per-sample chain); hidden activations beyond +-1000 do not fit the fp16 "
+                           "split -- set aggregator.mlp_engine = 'tc_tf32' (3xTF32, fp32 exponent range) for this model")
+
+
 # optional per-launch device timing (CUDA events on the launching stream); used by profiling.py / bench.py
 TIMERS = None          # None = off, else a list of (tag, start_event, end_event)
 _TAG = ["untagged"]

@@ -225,7 +225,9 @@ class lighting_fast_querier:
                               ptr(out_loc_pers), ptr(out_loc_w), ptr(out_dirs), ptr(ray_mask), ptr(ray_ids), ptr(vlist), ptr(b["counts"]),
                               stream()), "query")
         b["counts_host"].copy_(b["counts"], non_blocking=True)
+        ops.status_fetch_async(dev)                                # range guard of the previous frame's tensor-core kernels rides along
         torch.cuda.current_stream().synchronize()                  # the single readback of this call
+        ops.status_check(dev)
         Rk, Nv = int(b["counts_host"][0]), int(b["counts_host"][1])
         self.last = QueryExtras(vlist=vlist[:Nv], ray_ids=ray_ids[:Rk], n_rays=Rk, n_valid=Nv)
         self.count += 1

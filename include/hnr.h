@@ -169,7 +169,8 @@ int hnr_nbr_mlp_f16_forward(const float* xyz, const float* xyz_pers, const float
                             const float* raydirs, const float* cam, const float* weight, const float* confc, const void* wpack,
                             const float* bias, const float* walpha, const float* balpha, const float* mul /* host, 4 */,
                             float scale0, float scale2, float inv_act, int64_t Nv, int64_t K, float* sigma /* Nv */,
-                            float* X5 /* Nv,280 */, float* dbg, float* araw /* Nv*8, with dbg */, void* stream);
+                            float* X5 /* Nv,280 */, float* dbg, float* araw /* Nv*8, with dbg */,
+                            int32_t* status /* optional device word: |= 1 when an activation saturated fp16 */, void* stream);
 
 /* Fused chain of up to 4 dense layers (widths <= 128) on tcgen05, 3xFP16 split (csrc/chain_f16.cu): the per-sample MLPs
  * color_feature_branch, aux_merge_weight_block (+ sigmoid head), color_mixup_block (+ residual) of
@@ -185,7 +186,8 @@ int hnr_chain_f16_forward(const float* const* src, const int64_t* src_ld, const 
                           int nlayer, const int64_t* Kp, const int64_t* N, const int64_t* Np, const int* act, const void* wpack,
                           const int64_t* w_off, const float* bias /* 4,128 */, const float* mul, const float* inv_next,
                           float* const* Y, const int64_t* ldy, const float* res, int64_t ldres, const float* head_w,
-                          const float* head_b, int head_act, float* head_out /* M */, int64_t M, void* stream);
+                          const float* head_b, int head_act, float* head_out /* M */, int64_t M,
+                          int32_t* status /* optional device word: |= 2 when a value saturated fp16 */, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Compositing: neural_points_volumetric_model.py:331-339 + models/rendering/diff_ray_marching.py:508-557

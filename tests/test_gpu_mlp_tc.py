@@ -198,3 +198,23 @@ def test_linear_tc_backward_matches_fp64(M, N, ks, act, mods):
     assert_close(y, yd, 1e-5, 2e-5)
     for a, r in zip(srcs + [W, b], sd + [Wd, bd]):
         assert_close(a.grad, r.grad, 1e-4, 1e-5 * float(r.grad.abs().max()))
+
+
+def test_fp16_split_range_guard_raises_instead_of_diverging_silently():
+    """values that do not fit the scaled fp16 split are saturated by the kernels AND reported: the host raises at its next
+    synchronisation point instead of returning numbers that silently differ from the fp32 reference"""
+    from hybridneuralrendering_b200 import chain, ops
+    dev = torch.device("cuda")
+    lin = [torch.nn.Linear(32, 32).cuda(), torch.nn.Linear(32, 16).cuda()]
+    pc = chain.PackedChain(lin, [1, 0], 32)
+    x = torch.randn(256, 32, device=dev)
+    with torch.no_grad():
+        chain.chain_forward(pc, [x])
+        ops.status_fetch_async(dev); torch.cuda.synchronize()
+        ops.status_check(dev)                                        # in range: silent
+        chain.chain_forward(pc, [x * 1e6])
+        ops.status_fetch_async(dev); torch.cuda.synchronize()
+        with pytest.raises(RuntimeError, match="saturated"):
+            ops.status_check(dev)
+        ops.status_fetch_async(dev); torch.cuda.synchronize()
+        ops.status_check(dev)                                        # the flag is cleared once reported
