@@ -45,7 +45,8 @@ def train_step_benchmark(dev, steps: int = 5, warmup: int = 3, world: int = 1, p
     R = frame["raydir"].shape[1]
     params = [p for p in net.parameters() if p.requires_grad]
     opt_net = torch.optim.Adam([p for n, p in net.named_parameters() if p.requires_grad and not n.startswith("neural_points.")], lr=5e-4)
-    opt_pts = torch.optim.Adam([p for n, p in net.named_parameters() if p.requires_grad and n.startswith("neural_points.")], lr=2e-3)
+    from .optim import FusedAdam
+    opt_pts = FusedAdam([p for n, p in net.named_parameters() if p.requires_grad and n.startswith("neural_points.")], lr=2e-3)
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
 
     def fwd_bwd():

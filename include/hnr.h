@@ -209,6 +209,14 @@ int hnr_blur_select_fwd(const float* pred /* S*S,3 */, const float* gt, const fl
 int hnr_blur_select_bwd(const float* g_out, const float* kernels, const int32_t* select, int64_t patch_num, int64_t patch_size,
                         int64_t num_kernels, int64_t kernel_size, float* g_pred, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Fused dense Adam step for the neural-point tables (reference: one torch.optim.Adam over the point
+ * parameters, models/mvs_points_volumetric_model.py:94-104).  Same arithmetic as torch.optim.Adam (amsgrad off);
+ * step = 1-based count after this update.  One read of p,g,m,v and one write of p,m,v per element.
+ * ------------------------------------------------------------------------------------------- */
+int hnr_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                  float weight_decay, int64_t step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
