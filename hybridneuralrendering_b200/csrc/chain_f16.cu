@@ -25,6 +25,7 @@
 
 #include "common.cuh"
 #include "hnr.h"
+#define TRACE_SRC A.trace
 #include "tc_common.cuh"
 
 namespace {
@@ -116,18 +117,6 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity,
         __nanosleep(ns);
     }
 }
-// light-weight event trace of CTA 0 (profiling aid): each traced thread appends (clock64, tag) pairs to its own region
-constexpr int TRACE_CAP = 4096;
-#define TRACE_DECL(role) long long* tr__ = (A.trace && blockIdx.x == 0) ? A.trace + (role) * 2 * TRACE_CAP : nullptr; int trn__ = 0
-#define TRACE(id, a, b)                                                                          \
-    do {                                                                                         \
-        if (tr__ && trn__ < TRACE_CAP) {                                                         \
-            tr__[2 * trn__] = clock64();                                                         \
-            tr__[2 * trn__ + 1] = ((long long)(id) << 32) | ((long long)(a) << 16) | (long long)(b); \
-            ++trn__;                                                                             \
-        }                                                                                        \
-    } while (0)
-
 __host__ __device__ constexpr uint32_t idesc_f16(int N) {   // D=f32, A=B=f16, both K-major, M=128
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 }
@@ -471,9 +460,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) chain_f16_kernel(const __grid_con
 
 extern "C" int64_t hnr_chain_f16_chunk_bytes(int64_t Np) { return Np * 64; }
 
-// profiling aid: device buffer (>= 1 + 4*8000 int64) that CTA 0 of the next launches fills with (clock, event, a, b); NULL = off
-static long long* g_chain_trace = nullptr;
-extern "C" void hnr_chain_f16_set_trace(void* buf) { g_chain_trace = (long long*)buf; }
+// profiling aid (see tc_common.cuh TRACE): device buffer that CTA 0 of the following tensor-core launches fills; NULL = off
+static long long* g_trace = nullptr;
+extern "C" void hnr_chain_f16_set_trace(void* buf) { g_trace = (long long*)buf; }
+long long* hnr_trace_ptr() { return g_trace; }
 
 // Fused chain of up to 4 dense layers (widths <= 128) over M rows, 3xFP16 on tcgen05 (see the header of this file).
 // Arrays have nlayer entries.  Kp[0] = concat width padded to 16, Kp[l] = Np[l-1]; Np = N padded to 16.
@@ -505,7 +495,7 @@ extern "C" int hnr_chain_f16_forward(const float* const* src, const int64_t* src
     HNR_CHECK_ARG(!head_w || (head_b && head_out), "chain_f16_forward: head needs head_b and head_out");
     A.in_scale = in_scale; A.nlayer = nlayer; A.wpack = (const uint8_t*)wpack; A.bias = bias; A.res = res; A.ldres = (int)ldres;
     A.head_w = head_w; A.head_b = head_b; A.head_act = head_act; A.head_out = head_out; A.M = M;
-    A.trace = g_chain_trace;
+    A.trace = g_trace;
     A.status = status;
     static bool configured = false;
     if (!configured) {

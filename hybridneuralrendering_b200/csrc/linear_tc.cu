@@ -13,8 +13,11 @@
 //   * the TMEM accumulator is double buffered (2 x N columns): 4 epilogue warps drain tile t (bias,
 //     activation, residual, store) while the MMA warp already accumulates tile t+1;
 //   * weights come pre-split / pre-tiled from the host (linear_tc.py), one bulk copy per K-chunk.
+#include <limits.h>
+
 #include "common.cuh"
 #include "hnr.h"
+#define TRACE_SRC L.trace
 #include "tc_common.cuh"
 
 namespace {
@@ -59,6 +62,7 @@ struct LArgs {
     const float* gateY;      // backward-data mode: the A operand is dY * act'(gateY) (gateY = the layer's saved output)
     int ldgate, gate_act;
     float* Y;
+    long long* trace;        // profiling aid (tc_common.cuh TRACE)
     int64_t M;
     int ldres, ldy;
     int K, Kp, N, Npad, act;
@@ -158,15 +162,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(LArgs L) {
             const uint64_t dW = umma_desc(0, W_LBO, SBO), dA = umma_desc(0, A_LBO, SBO);
             const uint32_t w_base = smem_u32(smem + OFF_W), a_base = smem_u32(smem + OFF_A);
             uint32_t it = 0, tcount = 0;
+            TRACE_DECL(0);
+            if (lane != 0) tr__ = nullptr;
             for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
                 const uint32_t b = tcount & 1, bph = (tcount >> 1) & 1;
                 mbar_wait(bar_accE + 8 * b, bph ^ 1);            // epilogue drained this accumulator
+                TRACE(3, tcount, 0);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + b * (uint32_t)L.Npad;
                 for (int c = 0; c < nchunk; ++c, ++it) {
                     const uint32_t sw = it % NSW, pw = (it / NSW) & 1, sa = it % NSA, pa = (it / NSA) & 1;
                     mbar_wait(bar_fullW + 8 * sw, pw);
+                    TRACE(4, c, 0);
                     mbar_wait(bar_fullA + 8 * sa, pa);
+                    TRACE(1, c, 0);
                     tc_fence_after();
                     if (elect_one()) {
                         const uint32_t ws = w_base + sw * W_STAGE_MAX, as = a_base + sa * A_STAGE;
@@ -195,18 +204,75 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(LArgs L) {
         const int64_t total = my_tiles * nsc;
         constexpr int DEPTH = 3;
         float4 buf[DEPTH][4];
+        // The address arithmetic of a super-chunk is resolved once per (tile, source): the 4 row offsets of this lane are
+        // cached, so the common case costs one add + one 16-byte load per row (the generic load4 path -- source lookup,
+        // re-use modulus, alignment tests per element group -- measured 3.5 k cycles per super-chunk and paced the kernel).
+        int cs_src = -1;
+        int64_t cs_tile = -1;
+        const float* cs_base = nullptr;
+        const float* cs_gate = nullptr;
+        int cs_off[4], cs_goff[4];                      // element offsets of the 4 rows (INT_MIN = beyond M)
+        bool cs_vec = false;
         auto load_super = [&](int64_t q, float4 (&dst)[4]) {
             const int64_t tile = blockIdx.x + (q / nsc) * gridDim.x;
             const int k0 = (int)(q % nsc) * SUPER * KC + piece * 4;
+            int s_ = 0, kk = k0;
+            if (kk >= L.A.k[0]) { kk -= L.A.k[0]; s_ = 1; if (kk >= L.A.k[1]) { kk -= L.A.k[1]; s_ = 2; } }
+            const int ks_ = s_ == 0 ? L.A.k[0] : (s_ == 1 ? L.A.k[1] : L.A.k[2]);
+            if (k0 + 4 <= L.K && kk + 4 <= ks_) {
+                if (s_ != cs_src || tile != cs_tile) {
+                    const float* sp = s_ == 0 ? L.A.p[0] : (s_ == 1 ? L.A.p[1] : L.A.p[2]);
+                    const int sld = s_ == 0 ? L.A.ld[0] : (s_ == 1 ? L.A.ld[1] : L.A.ld[2]);
+                    const int64_t smod = s_ == 0 ? L.A.mod[0] : (s_ == 1 ? L.A.mod[1] : L.A.mod[2]);
+                    const int64_t m0 = tile * TM, first = smod > 0 ? m0 % smod : m0;
+                    cs_base = sp + first * sld;
+                    cs_gate = L.gateY ? L.gateY + m0 * L.ldgate : nullptr;
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) dst[jj] = load4(L, tile * TM + warp * 16 + jj * 4 + rsub, k0);
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int r = warp * 16 + jj * 4 + rsub;
+                        int64_t rr = first + r;
+                        if (smod > 0 && rr >= smod) rr %= smod;
+                        cs_off[jj] = (m0 + r < L.M) ? (int)((rr - first) * sld) : INT_MIN;
+                        cs_goff[jj] = r * L.ldgate;
+                    }
+                    cs_vec = ((sld & 3) == 0) && (!L.gateY || (L.ldgate & 3) == 0);
+                    cs_src = s_; cs_tile = tile;
+                }
+                const float* cb = cs_base + kk;
+                const float* gb = cs_gate ? cs_gate + k0 : nullptr;
+                const bool vec = cs_vec && ((reinterpret_cast<uintptr_t>(cb) & 15) == 0) && (!gb || (reinterpret_cast<uintptr_t>(gb) & 15) == 0);
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (cs_off[jj] != INT_MIN) {
+                        const float* qd = cb + cs_off[jj];
+                        if (vec) v = __ldg(reinterpret_cast<const float4*>(qd));
+                        else v = make_float4(__ldg(qd), __ldg(qd + 1), __ldg(qd + 2), __ldg(qd + 3));
+                        if (gb) {
+                            const float* gq = gb + cs_goff[jj];
+                            float4 y;
+                            if (vec) y = __ldg(reinterpret_cast<const float4*>(gq));
+                            else y = make_float4(__ldg(gq), __ldg(gq + 1), __ldg(gq + 2), __ldg(gq + 3));
+                            v.x *= act_grad_from_out(y.x, L.gate_act); v.y *= act_grad_from_out(y.y, L.gate_act);
+                            v.z *= act_grad_from_out(y.z, L.gate_act); v.w *= act_grad_from_out(y.w, L.gate_act);
+                        }
+                    }
+                    dst[jj] = v;
+                }
+            } else {
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) dst[jj] = load4(L, tile * TM + warp * 16 + jj * 4 + rsub, k0);     // straddling / padded group
+            }
         };
         uint32_t it = 0;
+        TRACE_DECL(1);
+        if (tid != 0) tr__ = nullptr;
         // a super-chunk fills up to SUPER ring slots at once: wait for all of them, let EVERY lane store its own 16-byte piece
         // (lane's chunk = u_of), then one proxy fence and one arrive per slot
         auto process = [&](int64_t q, const float4 (&src)[4]) {
             const int c0 = (int)(q % nsc) * SUPER;
             const int nvalid = min(SUPER, nchunk - c0);
+            TRACE(10, c0, 0);
 #pragma unroll
             for (int u = 0; u < SUPER; ++u) {
                 if (u < nvalid) {
@@ -214,6 +280,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(LArgs L) {
                     mbar_wait(bar_emptyA + 8 * s, ph ^ 1);
                 }
             }
+            TRACE(11, c0, 0);
             if (u_of < nvalid) {
                 uint8_t* st = smem + OFF_A + ((it + u_of) % NSA) * A_STAGE + h_of * A_LBO;
 #pragma unroll
@@ -229,6 +296,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(LArgs L) {
             __syncwarp();
             if (lane < nvalid) mbar_arrive(bar_fullA + 8 * ((it + lane) % NSA));
             it += nvalid;
+            TRACE(12, c0, 0);
         };
 #pragma unroll
         for (int d = 0; d < DEPTH; ++d)
@@ -255,10 +323,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(LArgs L) {
         const bool simple = !L.res && !L.head_w && (L.act == HNR_ACT_LRELU || L.act == HNR_ACT_NONE);
         const float slope = L.act == HNR_ACT_LRELU ? 0.01f : 1.f;
         uint32_t tcount = 0;
+        TRACE_DECL(2);
+        if (ew != 0 || lane != 0) tr__ = nullptr;
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
             const uint32_t b = tcount & 1, bph = (tcount >> 1) & 1;
             mbar_wait(bar_accF + 8 * b, bph);
             tc_fence_after();
+            TRACE(20, tcount, 0);
             const int64_t m = tile * TM + erow;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + b * (uint32_t)L.Npad;
             float dot = 0.f;
@@ -305,6 +376,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(LArgs L) {
                 }
                 if (L.head_w && m < L.M) L.out_head[m] = apply_act(dot + L.head_b[0], L.head_act);
             }
+            TRACE(22, tcount, 0);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_accE + 8 * b);
@@ -337,6 +409,7 @@ extern "C" int hnr_linear_tc_fwd(const float* const* a_ptr, const int64_t* a_ld,
     L.head_w = head_w; L.head_b = head_b; L.out_head = out_head; L.head_act = head_act;
     L.wpack = (const uint8_t*)wpack; L.bias = bias; L.res = res; L.Y = Y; L.M = M; L.ldres = (int)ldres; L.ldy = (int)ldy;
     L.K = (int)K; L.Kp = (int)Kp; L.N = (int)N; L.Npad = (int)Npad; L.act = act;
+    L.trace = hnr_trace_ptr();
     static bool configured = false;
     if (!configured) {
         HNR_CUDA(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -364,6 +437,7 @@ extern "C" int hnr_linear_tc_bwd_data(const float* dY, int64_t lddy, const float
     L.gateY = (act == HNR_ACT_NONE) ? nullptr : Y; L.ldgate = (int)ldy; L.gate_act = act;
     L.wpack = (const uint8_t*)wpackT; L.Y = dX; L.M = M; L.ldy = (int)lddx;
     L.K = (int)N; L.Kp = (int)Np; L.N = (int)Kout; L.Npad = (int)Kpad; L.act = HNR_ACT_NONE;
+    L.trace = hnr_trace_ptr();
     static bool configured = false;
     if (!configured) {
         HNR_CUDA(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));

@@ -23,6 +23,7 @@
 // :1002-1036 and models/helpers/networks.py:175-189 of the reference.
 #include "common.cuh"
 #include "hnr.h"
+#define TRACE_SRC ((long long*)nullptr)
 #include "tc_common.cuh"
 
 namespace {

@@ -25,6 +25,7 @@
 
 #include "common.cuh"
 #include "hnr.h"
+#define TRACE_SRC ((long long*)nullptr)
 #include "tc_common.cuh"
 
 namespace {

@@ -3,6 +3,21 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+long long* hnr_trace_ptr();      // chain_f16.cu: trace buffer set through hnr_chain_f16_set_trace (NULL = off)
+
+// light-weight event trace of CTA 0 (profiling aid): each traced thread appends (clock64, tag) pairs to its own region
+constexpr int TRACE_CAP = 4096;
+#define TRACE_DECL(role) long long* tr__ = (TRACE_SRC && blockIdx.x == 0) ? TRACE_SRC + (role) * 2 * TRACE_CAP : nullptr; int trn__ = 0
+#define TRACE(id, a, b)                                                                          \
+    do {                                                                                         \
+        if (tr__ && trn__ < TRACE_CAP) {                                                         \
+            tr__[2 * trn__] = clock64();                                                         \
+            tr__[2 * trn__ + 1] = ((long long)(id) << 32) | ((long long)(a) << 16) | (long long)(b); \
+            ++trn__;                                                                             \
+        }                                                                                        \
+    } while (0)
+
+
 namespace tc {
 
 // ------------------------------------------------------------------------------------------------

@@ -17,6 +17,7 @@
 // Replaces hnr_linear_bwd_weight (linear_simt.cu) in LinearFn.backward; same argument meaning.
 #include "common.cuh"
 #include "hnr.h"
+#define TRACE_SRC ((long long*)nullptr)
 #include "tc_common.cuh"
 
 namespace {

@@ -228,11 +228,12 @@ def linear_backward(W, Y, srcs, mods, dY, act: int, need_src, need_w: bool = Tru
     if any(need_src) and M > 0:
         if use_tc:
             # tensor-core data gradient: dX = (dY * act'(Y)) . W in column slices of <= 256, then views per source
-            dX = torch.empty((M, K), device=W.device, dtype=torch.float32)
+            ldx = (K + 3) // 4 * 4                      # 16-byte aligned rows: the consumers of the column views load float4
+            dX = torch.empty((M, ldx), device=W.device, dtype=torch.float32)
             for k0, (wpackT, Kpad, Np) in _packed_linear_T(W):
                 with _launch(name=f"linear_tc_bwd_data[{M}x{N}x{K}]" if TIMERS is not None else None):
                     check(lib().hnr_linear_tc_bwd_data(ptr(dY), dY.stride(0), ptr(Y), Y.stride(0), act, ptr(wpackT), Kpad, Np,
-                                                       ptr(dX[:, k0:]), K, M, N, min(256, K - k0), stream()), "linear_tc_bwd_data")
+                                                       ptr(dX[:, k0:]), ldx, M, N, min(256, K - k0), stream()), "linear_tc_bwd_data")
             outs, off = [], 0
             for i in range(nsrc):
                 outs.append(dX[:, off:off + ks[i]] if need_src[i] else None)
