@@ -11,12 +11,22 @@ M, N, K = 602192, 256, 256
 x = torch.randn(M, K, device="cuda")
 W = torch.randn(N, K, device="cuda") * 0.06
 b = torch.zeros(N, device="cuda")
-with torch.no_grad():
-    ops.linear([x], W, b, 1); torch.cuda.synchronize()
-    buf = torch.zeros(3 * 2 * 4096, dtype=torch.int64, device="cuda")
-    lib().hnr_chain_f16_set_trace(ptr(buf))
-    ops.linear([x], W, b, 1); torch.cuda.synchronize()
-    lib().hnr_chain_f16_set_trace(None)
+mode = sys.argv[2] if len(sys.argv) > 2 else "fwd"
+buf = torch.zeros(3 * 2 * 4096, dtype=torch.int64, device="cuda")
+if mode == "fwd":
+    with torch.no_grad():
+        ops.linear([x], W, b, 1); torch.cuda.synchronize()
+        lib().hnr_chain_f16_set_trace(ptr(buf))
+        ops.linear([x], W, b, 1); torch.cuda.synchronize()
+        lib().hnr_chain_f16_set_trace(None)
+else:                                   # data gradient only (gated A operand)
+    with torch.no_grad():
+        y = ops.linear([x], W, b, 1)
+        gy = torch.randn_like(y)
+        ops.linear_backward(W, y, [x], (), gy, 1, [True], need_w=False); torch.cuda.synchronize()
+        lib().hnr_chain_f16_set_trace(ptr(buf))
+        ops.linear_backward(W, y, [x], (), gy, 1, [True], need_w=False); torch.cuda.synchronize()
+        lib().hnr_chain_f16_set_trace(None)
 t = buf.cpu().numpy().reshape(3, 4096, 2)
 ev = []
 for role in range(3):
