@@ -303,6 +303,10 @@ def main():
         tr["n_gpus"] = world
         tr["gradient_allreduce"] = "NCCL SUM, dense point gradients + coalesced MLP bucket" if world > 1 else "none (1 GPU)"
         line["train"] = tr
+        if world == 1:
+            from hybridneuralrendering_b200.benchmarks import blur_train_step_benchmark
+            torch.cuda.empty_cache()
+            line["train_blur"] = blur_train_step_benchmark(dev, steps=3, warmup=3)      # BASELINE configs[3]
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         q_np, n_sample = sample_query(xyz, att, fr, P, dev)
         cores = os.cpu_count() or 1

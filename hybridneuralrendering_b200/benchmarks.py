@@ -96,3 +96,54 @@ def train_step_benchmark(dev, steps: int = 5, warmup: int = 3, world: int = 1, p
             "rays": R, "kept_rays": int(ex.n_rays), "valid_samples": int(ex.n_valid), "valid_neighbours": agg.last_valid_neighbours(),
             "points": points, "views": views, "loss": float(loss.detach()), "launches_per_step": launches // steps,
             "stage_ms": {k: round(v, 3) for k, v in sorted(stages.items())}, "config": TRAIN_WORKLOAD}
+
+
+BLUR_WORKLOAD = "full model with blur handling: 32x32 patch rays (4x4 dilated patches of 8x8) + pre-defined degradation-kernel convolution, fwd+bwd"
+
+
+def blur_train_step_benchmark(dev, steps: int = 5, warmup: int = 3, points: int = 2_000_000, views: int = 8) -> Dict:
+    """BASELINE.json configs[3]: as the training step, but 1,024 rays on a 4x4 grid of 8x8 patches, the output filled back to
+    the patch raster and passed through the blur module (36 pre-defined 9x9 kernels + identity, per-patch best match,
+    models/base_rendering_model.py:677-786) before the loss; forward + backward through blur and render."""
+    from . import NeuralPoints, NeuralPointsRayMarching, PointAggregator, make_opt
+    from . import synthetic as syn
+    from .blur import blur_select, predefined_blur_kernels
+    from .neural_points_volumetric_model import fill_invalid
+    opt = make_opt("scannet", use_nearest=views, SR=24, is_train=True, drop_ratio=0.5, dilation_setup="4_8_1_8", max_o=1_000_000)
+    xyz = syn.room_scene(points, 0)
+    att = syn.point_attributes(np.random.default_rng(0), len(xyz))
+    fr = syn.room_frame(H=480, W=640, V=views, patch_num=4, patch_size=8, seed=0)
+    c = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    pts = NeuralPoints(32, len(xyz), opt, dev)
+    pts.set_points(c(xyz), c(att["emb"])[None], points_color=c(att["color"])[None], points_dir=c(att["dir"])[None],
+                   points_conf=c(att["conf"])[None], parameter=True)
+    torch.manual_seed(0)
+    net = NeuralPointsRayMarching(aggregator=PointAggregator(opt).to(dev), neural_points=pts, opt=opt).to(dev)
+    net.near_far = (0.1, 8.0)
+    frame = {k: (c(v) if isinstance(v, np.ndarray) and v.dtype.kind == "f" else v) for k, v in fr.items()}
+    kernels = c(predefined_blur_kernels(3))[None]
+    R = fr["raydir"].shape[1]
+    params = [p for p in net.parameters() if p.requires_grad]
+
+    def fwd_bwd():
+        for p in params:
+            p.grad = None
+        out = net(**frame)
+        full = fill_invalid(out, frame["bg_color"], net.last_extras.ray_ids)
+        blurred, _ = blur_select(full["coarse_raycolor"], frame["gt_image"], kernels, 4, 8)
+        loss = torch.nn.functional.mse_loss(blurred, frame["gt_image"])
+        loss.backward()
+        return loss
+
+    for _ in range(warmup):
+        fwd_bwd()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    torch.cuda.synchronize()
+    for s, e in ev:
+        s.record()
+        loss = fwd_bwd()
+        e.record()
+    torch.cuda.synchronize()
+    ms = sum(s.elapsed_time(e) for s, e in ev) / steps
+    return {"metric": "train rays/s (fwd+bwd, with blur module)", "value": R / (ms * 1e-3), "unit": "rays/s", "ms_fwd_bwd": ms, "rays": R,
+            "valid_samples": int(net.last_extras.n_valid), "loss": float(loss.detach()), "config": BLUR_WORKLOAD}
