@@ -40,9 +40,9 @@ _SIGS = {
     "hnr_alpha_ksum_bwd": (C.c_int, [vp] * 8 + [i64, i64, i64, vp, vp, vp, vp, vp]),
     "hnr_conf_bwd": (C.c_int, [vp] * 5 + [i64, i64, i64, vp, vp]),
     "hnr_project_views": (C.c_int, [vp] * 5 + [i64, i64, vp, vp, vp]),
-    "hnr_image_gather_fwd": (C.c_int, [C.POINTER(vp), C.POINTER(i64), vp, vp, i64, i64, i64, vp, vp, vp]),
+    "hnr_image_gather_fwd": (C.c_int, [C.POINTER(vp), C.POINTER(i64), vp, vp, i64, i64, i64, vp, vp, i64, vp, vp]),
     "hnr_image_gather_bwd": (C.c_int, [C.POINTER(vp), C.POINTER(i64), vp, vp, vp, i64, i64, i64, vp]),
-    "hnr_blend_fwd": (C.c_int, [vp, vp, vp, vp, i64, i64, vp, vp]),
+    "hnr_blend_fwd": (C.c_int, [vp, vp, vp, vp, i64, i64, i64, vp, i64, vp]),
     "hnr_blend_bwd": (C.c_int, [vp, vp, vp, vp, vp, i64, i64, vp, vp, vp]),
     "hnr_linear_fwd": (C.c_int, [C.POINTER(vp), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), vp, vp, vp, i64, vp, i64, i64, i64,
                                  i64, C.c_int, vp]),

@@ -54,11 +54,13 @@ class PackedChain:
         Kp = [_pad16(k_in)]
         imgs, sws, Nps, Ns = [], [], [], []
         for l, lin in enumerate(layers):
-            assert lin.weight.shape[1] == (k_in if l == 0 else Ns[-1])
+            assert (lin.weight.shape[1] == k_in or (l == 0 and cols0 is not None)) if l == 0 else lin.weight.shape[1] == Ns[-1]
             W = lin.weight
             if l == 0 and cols0 is not None:
-                assert sorted(cols0) == list(range(k_in))
-                W = W.detach().index_select(1, torch.tensor(list(cols0), device=W.device))
+                # cols0[k'] = reference input column presented at kernel column k' (-1 = padding column with zero weight)
+                assert sorted(c for c in cols0 if c >= 0) == list(range(W.shape[1])) and len(cols0) == k_in
+                idx = torch.tensor([max(c, 0) for c in cols0], device=W.device)
+                W = W.detach().index_select(1, idx) * torch.tensor([1.0 if c >= 0 else 0.0 for c in cols0], device=W.device)
             img, sw, Np = pack_chain_layer(W, Kp[l])
             imgs.append(img); sws.append(sw); Nps.append(Np); Ns.append(lin.weight.shape[0])
             Kp.append(Np)

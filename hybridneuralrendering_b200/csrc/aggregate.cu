@@ -399,7 +399,7 @@ image_gather_kernel(hnr_pyramid_t P, const float* __restrict__ xy, const int32_t
 //   sub-lane 12   : level 0 rgb (nearest pixel), validity flag
 __global__ void __launch_bounds__(256)
 image_gather_fwd_v2_kernel(hnr_pyramid_t P, const float* __restrict__ xy, const int32_t* __restrict__ vlist, int V, int64_t S, int64_t Nv,
-                           float* __restrict__ aux, float* __restrict__ ok) {
+                           float* __restrict__ aux, float* __restrict__ ok, int aux_ld, const float* __restrict__ delta) {
     const int q = threadIdx.x & 15;
     const int64_t pair = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
     if (pair >= (int64_t)V * Nv || q > 12) return;
@@ -411,9 +411,13 @@ image_gather_fwd_v2_kernel(hnr_pyramid_t P, const float* __restrict__ xy, const 
     const int H = P.h[0], W = P.w[0];
     const bool inb = !(px < 0 || px >= W || py < 0 || py >= H);
     const bool zero = !inb || (px == 0 && py == 0);          // pixel (0,0) is the zeroed "invalid" slot
-    float* o = aux + pair * AUX_C;
+    float* o = aux + pair * aux_ld;
     if (q == 12) {
         ok[pair] = inb ? 1.f : 0.f;
+        if (delta) {                                         // 48-wide rows: the view-direction difference rides in columns 45..47
+            const float* dp = delta + ((int64_t)v * S + s) * 3;
+            o[AUX_C] = dp[0]; o[AUX_C + 1] = dp[1]; o[AUX_C + 2] = dp[2];
+        }
         float r = 0.f, g = 0.f, b = 0.f;
         if (!zero) {
             const float* p0 = P.lvl[0] + (((int64_t)v * H + py) * W + px) * 3;
@@ -456,15 +460,16 @@ image_gather_fwd_v2_kernel(hnr_pyramid_t P, const float* __restrict__ xy, const 
 // ------------------------------------------------------------------ I3: learned multi-view blend
 // thread per (sample, channel): merged = keep * sum_v aux_v w_v / (sum_v w_v + 1e-6), w_v = sig_v * ok_v
 __global__ void blend_fwd_kernel(const float* __restrict__ aux, const float* __restrict__ sig, const float* __restrict__ ok,
-                                 const uint8_t* __restrict__ keep, int V, int64_t Nv, float* __restrict__ merged) {
+                                 const uint8_t* __restrict__ keep, int V, int64_t Nv, int aux_ld, float* __restrict__ merged, int merged_ld) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= Nv * AUX_C) return;
-    int64_t n = i / AUX_C;
-    int c = (int)(i - n * AUX_C);
+    if (i >= Nv * merged_ld) return;
+    int64_t n = i / merged_ld;
+    int c = (int)(i - n * merged_ld);
+    if (c >= AUX_C) { merged[i] = 0.f; return; }             // padding columns of a 48-wide row
     float num = 0.f, den = 0.f;
     for (int v = 0; v < V; ++v) {
         float w = sig[(int64_t)v * Nv + n] * ok[(int64_t)v * Nv + n];
-        num += aux[((int64_t)v * Nv + n) * AUX_C + c] * w;
+        num += aux[((int64_t)v * Nv + n) * aux_ld + c] * w;
         den += w;
     }
     float m = num / (den + 1e-6f);
@@ -607,8 +612,10 @@ static int fill_pyramid(hnr_pyramid_t& P, const float* const* lvl, float* const*
 }
 
 extern "C" int hnr_image_gather_fwd(const float* const* levels, const int64_t* level_hw, const float* xy, const int32_t* vlist,
-                                    int64_t V, int64_t S, int64_t Nv, float* aux, float* ok, void* stream) {
+                                    int64_t V, int64_t S, int64_t Nv, float* aux, float* ok, int64_t aux_ld, const float* delta,
+                                    void* stream) {
     if (V * Nv == 0) return HNR_OK;
+    HNR_CHECK_ARG(aux_ld >= AUX_C && (!delta || aux_ld >= AUX_C + 3), "image_gather_fwd: aux_ld must be >= 45 (>= 48 with delta)");
     hnr_pyramid_t P;
     fill_pyramid(P, levels, nullptr, level_hw);
     // vector path: needs the channel groups 16-byte (levels 2, 3) / 8-byte (level 1) aligned, i.e. base pointers from the allocator
@@ -617,9 +624,12 @@ extern "C" int hnr_image_gather_fwd(const float* const* levels, const int64_t* l
                         (reinterpret_cast<uintptr_t>(levels[2]) & 15) == 0 && (reinterpret_cast<uintptr_t>(levels[3]) & 15) == 0 &&
                         (reinterpret_cast<uintptr_t>(xy) & 7) == 0 && (int64_t)P.h[1] * P.w[1] * 24 < (1ll << 31);
     if (vec_ok)
-        image_gather_fwd_v2_kernel<<<(unsigned)hnr_cdiv(V * Nv * 16, 256), 256, 0, (cudaStream_t)stream>>>(P, xy, vlist, (int)V, S, Nv, aux, ok);
-    else
+        image_gather_fwd_v2_kernel<<<(unsigned)hnr_cdiv(V * Nv * 16, 256), 256, 0, (cudaStream_t)stream>>>(P, xy, vlist, (int)V, S, Nv, aux, ok,
+                                                                                                           (int)aux_ld, delta);
+    else {
+        HNR_CHECK_ARG(aux_ld == AUX_C && !delta, "image_gather_fwd: padded rows need the vector path (standard 6/12/24-channel pyramid)");
         image_gather_kernel<false><<<warp_blocks(V * Nv), 256, 0, (cudaStream_t)stream>>>(P, xy, vlist, (int)V, S, Nv, aux, ok, nullptr);
+    }
     HNR_CHECK_LAUNCH("image_gather_fwd");
     return HNR_OK;
 }
@@ -635,9 +645,11 @@ extern "C" int hnr_image_gather_bwd(float* const* level_grads, const int64_t* le
 }
 
 extern "C" int hnr_blend_fwd(const float* aux, const float* sig, const float* ok, const uint8_t* keep, int64_t V, int64_t Nv,
-                             float* merged, void* stream) {
+                             int64_t aux_ld, float* merged, int64_t merged_ld, void* stream) {
     if (Nv == 0) return HNR_OK;
-    blend_fwd_kernel<<<(unsigned)hnr_cdiv(Nv * AUX_C, 256), 256, 0, (cudaStream_t)stream>>>(aux, sig, ok, keep, (int)V, Nv, merged);
+    HNR_CHECK_ARG(aux_ld >= AUX_C && merged_ld >= AUX_C, "blend_fwd: row strides must be >= 45");
+    blend_fwd_kernel<<<(unsigned)hnr_cdiv(Nv * merged_ld, 256), 256, 0, (cudaStream_t)stream>>>(aux, sig, ok, keep, (int)V, Nv, (int)aux_ld, merged,
+                                                                                             (int)merged_ld);
     HNR_CHECK_LAUNCH("blend_fwd");
     return HNR_OK;
 }

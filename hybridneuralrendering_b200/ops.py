@@ -492,8 +492,8 @@ class ImageGatherFn(torch.autograd.Function):
         aux = torch.empty((V, Nv, AUX_C), device=xy.device, dtype=torch.float32)
         ok = torch.empty((V, Nv), device=xy.device, dtype=torch.float32)
         with _launch():
-            check(lib().hnr_image_gather_fwd(ptr_array(lv), i64_array(hw), ptr(xy), ptr(vlist), V, S, Nv, ptr(aux), ptr(ok), stream()),
-                  "image_gather_fwd")
+            check(lib().hnr_image_gather_fwd(ptr_array(lv), i64_array(hw), ptr(xy), ptr(vlist), V, S, Nv, ptr(aux), ptr(ok), AUX_C, None,
+                                             stream()), "image_gather_fwd")
         ctx.hw, ctx.shapes, ctx.dims = hw, [l.shape for l in lv], (V, S, Nv)
         ctx.save_for_backward(xy, vlist)
         ctx.mark_non_differentiable(ok)
@@ -511,6 +511,35 @@ class ImageGatherFn(torch.autograd.Function):
         return None, grads[1], grads[2], grads[3], None, None
 
 
+AUX_LD = 48        # 16-byte aligned row stride of the no-grad image-branch tensors: [aux 45 | dview 3] and [merged 45 | 0 0 0]
+
+
+def image_gather_padded(levels, xy, vlist, delta):
+    """no-grad lookup into 48-wide rows with the view-direction difference in columns 45..47: the blend-weight net reads
+    [aux | dview] as one aligned block.  -> aux48 (V,Nv,48), ok (V,Nv)"""
+    lv = [_f32c(l) for l in levels]
+    V, S, Nv = xy.shape[0], xy.shape[1], vlist.shape[0]
+    hw = []
+    for l in lv:
+        hw += [l.shape[1], l.shape[2]]
+    aux = torch.empty((V, Nv, AUX_LD), device=xy.device, dtype=torch.float32)
+    ok = torch.empty((V, Nv), device=xy.device, dtype=torch.float32)
+    d = _f32c(delta.reshape(V, S, 3))
+    with _launch():
+        check(lib().hnr_image_gather_fwd(ptr_array(lv), i64_array(hw), ptr(xy), ptr(vlist), V, S, Nv, ptr(aux), ptr(ok), AUX_LD, ptr(d),
+                                         stream()), "image_gather_fwd")
+    return aux, ok
+
+
+def blend_padded(aux48, sig, ok, keep):
+    """no-grad blend of 48-wide aux rows -> merged (Nv,48) with zero padding"""
+    V, Nv = aux48.shape[0], aux48.shape[1]
+    merged = torch.empty((Nv, AUX_LD), device=aux48.device, dtype=torch.float32)
+    with _launch():
+        check(lib().hnr_blend_fwd(ptr(aux48), ptr(_f32c(sig)), ptr(ok), ptr(keep), V, Nv, AUX_LD, ptr(merged), AUX_LD, stream()), "blend_fwd")
+    return merged
+
+
 class BlendFn(torch.autograd.Function):
     """aux (V,Nv,45), sig (V*Nv,1), ok (V,Nv), keep (Nv) u8|None -> merged (Nv,45)."""
 
@@ -520,7 +549,7 @@ class BlendFn(torch.autograd.Function):
         V, Nv = aux.shape[0], aux.shape[1]
         merged = torch.empty((Nv, AUX_C), device=aux.device, dtype=torch.float32)
         with _launch():
-            check(lib().hnr_blend_fwd(ptr(aux), ptr(sig), ptr(ok), ptr(keep), V, Nv, ptr(merged), stream()), "blend_fwd")
+            check(lib().hnr_blend_fwd(ptr(aux), ptr(sig), ptr(ok), ptr(keep), V, Nv, AUX_C, ptr(merged), AUX_C, stream()), "blend_fwd")
         ctx.save_for_backward(aux, sig, ok, keep if keep is not None else torch.empty(0, device=aux.device))
         ctx.has_keep = keep is not None
         return merged

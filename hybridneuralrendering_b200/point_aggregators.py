@@ -262,33 +262,41 @@ class PointAggregator(nn.Module):
                 g = ops.linear([X5], cf[0].weight, cf[0].bias, ACT_LRELU)
                 g = ops.linear([g], cf[2].weight, cf[2].bias, ACT_LRELU)
                 g = ops.linear([g], cf[4].weight, cf[4].bias, ACT_LRELU)
-        if V > 0:
+        if V > 0 and fused:
+            # inference: 48-wide rows ([aux 45 | dview 3], [merged 45 | 0 0 0]) keep every chain input 16-byte aligned
+            with ops.tag("image_gather"):
+                aux48, ok = ops.image_gather_padded(levels, xy, vlist, delta)
+            am = self.aux_merge_weight_block
+            with ops.tag("sample_mlp"):
+                # kernel source order [g | aux | dview]
+                pc = chain.packed_chain(self, "am", [am[0], am[2], am[4]], [ACT_LRELU] * 3, 176,
+                                        cols0=list(range(45, 173)) + list(range(45)) + [173, 174, 175])
+                sig = chain.chain_forward(pc, [g, aux48.view(V * Nv, ops.AUX_LD)], M=V * Nv, mods=(Nv, 0), out=False,
+                                          head=(am[6].weight, am[6].bias, ACT_SIGMOID))[1]
+            with ops.tag("blend"):
+                merged = ops.blend_padded(aux48, sig, ok, self._keep_mask(R, SR, vlist))
+        elif V > 0:
             with ops.tag("image_gather"):
                 aux, ok = ops.ImageGatherFn.apply(levels[0], levels[1], levels[2], levels[3], xy, vlist)
             dv = delta.reshape(V, S, 3).index_select(1, vlist.long()).reshape(V * Nv, 3)
             am = self.aux_merge_weight_block
             with ops.tag("sample_mlp"):
-                if fused:
-                    # kernel source order [g | aux | dview] (the 128-wide block first keeps its chunks 16-byte aligned)
-                    pc = chain.packed_chain(self, "am", [am[0], am[2], am[4]], [ACT_LRELU] * 3, 176,
-                                            cols0=list(range(45, 173)) + list(range(45)) + [173, 174, 175])
-                    sig = chain.chain_forward(pc, [g, aux.view(V * Nv, 45), dv], M=V * Nv, mods=(Nv, 0, 0), out=False,
-                                              head=(am[6].weight, am[6].bias, ACT_SIGMOID))[1]
-                else:
-                    t = ops.linear([aux.view(V * Nv, 45), g, dv], am[0].weight, am[0].bias, ACT_LRELU, mods=(0, Nv, 0), M=V * Nv)
-                    t = ops.linear([t], am[2].weight, am[2].bias, ACT_LRELU)
-                    t = ops.linear([t], am[4].weight, am[4].bias, ACT_LRELU)
-                    sig = ops.linear([t], am[6].weight, am[6].bias, ACT_SIGMOID)
+                t = ops.linear([aux.view(V * Nv, 45), g, dv], am[0].weight, am[0].bias, ACT_LRELU, mods=(0, Nv, 0), M=V * Nv)
+                t = ops.linear([t], am[2].weight, am[2].bias, ACT_LRELU)
+                t = ops.linear([t], am[4].weight, am[4].bias, ACT_LRELU)
+                sig = ops.linear([t], am[6].weight, am[6].bias, ACT_SIGMOID)
             with ops.tag("blend"):
                 merged = ops.BlendFn.apply(aux, sig, ok, self._keep_mask(R, SR, vlist))
         else:
-            merged = torch.zeros((Nv, 45), device=pidx.device, dtype=torch.float32)
+            merged = torch.zeros((Nv, ops.AUX_LD if fused else 45), device=pidx.device, dtype=torch.float32)
         gi, gv = g[:, :45], g[:, 45:]
         cm = self.color_mixup_block
         with ops.tag("sample_mlp"):
             if fused:
-                pc = chain.packed_chain(self, "cm", [cm[0], cm[2], cm[4]], [ACT_LRELU, ACT_LRELU, ACT_NONE], 90)
-                m = chain.chain_forward(pc, [gi, merged], res=gi)[0]
+                # sources g[:, :48] and merged (48 wide): the three padding columns of each meet zero weights
+                pc = chain.packed_chain(self, "cm", [cm[0], cm[2], cm[4]], [ACT_LRELU, ACT_LRELU, ACT_NONE], 96,
+                                        cols0=list(range(45)) + [-1] * 3 + list(range(45, 90)) + [-1] * 3)
+                m = chain.chain_forward(pc, [g[:, :ops.AUX_LD], merged], res=gi)[0]
             else:
                 m = ops.linear([gi, merged], cm[0].weight, cm[0].bias, ACT_LRELU)
                 m = ops.linear([m], cm[2].weight, cm[2].bias, ACT_LRELU)

@@ -102,12 +102,14 @@ int hnr_project_views(const float* loc_w, const float* w2c /* V,4,4 */, const fl
 /* pyramid lookup == F.interpolate(bilinear) to full res, zero pixel (0,0), truncated nearest pixel
  * (:1064-1096, :1193); levels are NHWC: (V,H,W,3),(V,h1,w1,6),(V,h2,w2,12),(V,h3,w3,24) */
 int hnr_image_gather_fwd(const float* const* levels, const int64_t* level_hw /* 8 */, const float* xy, const int32_t* vlist,
-                         int64_t V, int64_t S, int64_t Nv, float* aux /* V,Nv,45 */, float* ok /* V,Nv */, void* stream);
+                         int64_t V, int64_t S, int64_t Nv, float* aux /* V,Nv,aux_ld */, float* ok /* V,Nv */,
+                         int64_t aux_ld /* 45, or 48 = 16-byte aligned rows */, const float* delta /* V,S,3 or NULL: copied into columns
+                         45..47 of a 48-wide row (the blend-weight net's input [aux | dview] in one aligned block) */, void* stream);
 int hnr_image_gather_bwd(float* const* level_grads, const int64_t* level_hw, const float* xy, const int32_t* vlist, const float* d_aux,
                          int64_t V, int64_t S, int64_t Nv, void* stream);
 /* multi-view blend (:1199-1217) + train-time drop (:1222-1237) */
-int hnr_blend_fwd(const float* aux, const float* sig, const float* ok, const uint8_t* keep, int64_t V, int64_t Nv, float* merged,
-                  void* stream);
+int hnr_blend_fwd(const float* aux, const float* sig, const float* ok, const uint8_t* keep, int64_t V, int64_t Nv, int64_t aux_ld,
+                  float* merged, int64_t merged_ld /* 45, or 48 with zero padding */, void* stream);
 int hnr_blend_bwd(const float* aux, const float* sig, const float* ok, const uint8_t* keep, const float* d_merged, int64_t V,
                   int64_t Nv, float* d_aux, float* d_sig, void* stream);
 

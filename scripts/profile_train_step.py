@@ -1,0 +1,23 @@
+#!/usr/bin/env python
+"""torch.profiler view of one training step (configs[2]): which CUDA kernels -- ours and torch's -- take the time."""
+import os, sys
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from hybridneuralrendering_b200.benchmarks import build_train_case
+from hybridneuralrendering_b200.renderer import training_loss
+
+dev = torch.device("cuda:0")
+net, frame = build_train_case(dev)
+params = [p for p in net.parameters() if p.requires_grad]
+def step():
+    for p in params: p.grad = None
+    out = net(**frame)
+    loss = training_loss(out, frame["gt_image"])
+    loss.backward()
+for _ in range(3): step()
+torch.cuda.synchronize()
+from torch.profiler import profile, ProfilerActivity
+with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+    step(); torch.cuda.synchronize()
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=28, max_name_column_width=70))
