@@ -153,6 +153,8 @@ def pack_layer_f16(W: torch.Tensor, cols: Optional[Sequence[int]] = None, weight
         sw = 2.0 ** math.floor(math.log2(16384.0 / wmax)) if wmax > 0 else 1.0
     else:
         sw = float(weight_scale)                          # training re-packs every step: a fixed scale avoids the synchronisation
+        # ... and the range check rides on the device status word (reported at the host's next synchronisation point)
+        ops.status_word(W.device).bitwise_or_((Wp.abs().max() * sw > 60000.0).to(torch.int32) * 4)
     hi, lo = split_f16(Wp * sw)
     tile = lambda x: x.view(32, 8, Kp // KC16, 2, 8).permute(2, 3, 0, 1, 4)          # (C, 2, 32, 8, 8)
     img = torch.stack([tile(hi), tile(lo)], dim=1).contiguous()                        # (C, 2[hi|lo], 2, 32, 8, 8)
