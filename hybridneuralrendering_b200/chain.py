@@ -25,15 +25,34 @@ def _pad16(n: int) -> int:
     return (n + 15) // 16 * 16
 
 
-def pack_chain_layer(W: torch.Tensor, Kp: int):
+_IDX_CACHE = {}
+
+
+def _cols_index(cols0, device):
+    """(index tensor, 0/1 mask tensor) for a column order, cached per device: creating them from Python lists is a blocking
+    host-to-device copy, which must not happen on every training step"""
+    key = (str(device), tuple(cols0))
+    ent = _IDX_CACHE.get(key)
+    if ent is None:
+        idx = torch.tensor([max(c, 0) for c in cols0], device=device)
+        mask = torch.tensor([1.0 if c >= 0 else 0.0 for c in cols0], device=device)
+        ent = _IDX_CACHE[key] = (idx, mask)
+    return ent
+
+
+def pack_chain_layer(W: torch.Tensor, Kp: int, weight_scale: Optional[float] = None):
     W = W.detach().float()
     N, K = W.shape
     Np = _pad16(N)
     assert Np <= NMAX and K <= Kp and Kp % 16 == 0
     Wp = torch.zeros((Np, Kp), device=W.device, dtype=torch.float32)
     Wp[:N, :K] = W
-    wmax = float(Wp.abs().max())
-    sw = 2.0 ** math.floor(math.log2(16384.0 / wmax)) if wmax > 0 else 1.0
+    if weight_scale is None:
+        wmax = float(Wp.abs().max())                      # host read-back: inference packs once per weight version
+        sw = 2.0 ** math.floor(math.log2(16384.0 / wmax)) if wmax > 0 else 1.0
+    else:                                                 # training re-packs every step: fixed scale, range check on the status word
+        sw = float(weight_scale)
+        ops.status_word(W.device).bitwise_or_((Wp.abs().max() * sw > 60000.0).to(torch.int32) * 4)
     Ws = Wp * sw
     hi = Ws.half()
     lo = (Ws - hi.float()).half()
@@ -47,7 +66,7 @@ class PackedChain:
     """packed weights + scale bookkeeping of a chain; rebuilt when any weight / bias changes"""
 
     def __init__(self, layers: Sequence[torch.nn.Linear], acts: Sequence[int], k_in: int, act_scale: float = ACT_SCALE,
-                 cols0: Optional[Sequence[int]] = None):
+                 cols0: Optional[Sequence[int]] = None, weight_scale: Optional[float] = None):
         """cols0: order in which the kernel's concatenated sources present the first layer's input columns"""
         assert 1 <= len(layers) <= 4 and len(acts) == len(layers)
         self.nlayer = len(layers)
@@ -59,9 +78,9 @@ class PackedChain:
             if l == 0 and cols0 is not None:
                 # cols0[k'] = reference input column presented at kernel column k' (-1 = padding column with zero weight)
                 assert sorted(c for c in cols0 if c >= 0) == list(range(W.shape[1])) and len(cols0) == k_in
-                idx = torch.tensor([max(c, 0) for c in cols0], device=W.device)
-                W = W.detach().index_select(1, idx) * torch.tensor([1.0 if c >= 0 else 0.0 for c in cols0], device=W.device)
-            img, sw, Np = pack_chain_layer(W, Kp[l])
+                idx, mask = _cols_index(cols0, W.device)
+                W = W.detach().index_select(1, idx) * mask
+            img, sw, Np = pack_chain_layer(W, Kp[l], weight_scale)
             imgs.append(img); sws.append(sw); Nps.append(Np); Ns.append(lin.weight.shape[0])
             Kp.append(Np)
         self.Kp, self.N, self.Np, self.acts = Kp[:-1], Ns, Nps, list(acts)
@@ -84,13 +103,16 @@ class PackedChain:
         self.bias = bias.contiguous()
 
 
-def packed_chain(owner, name: str, layers, acts, k_in: int, cols0=None) -> PackedChain:
+TRAIN_WEIGHT_SCALE = 1024.0
+
+
+def packed_chain(owner, name: str, layers, acts, k_in: int, cols0=None, weight_scale=None) -> PackedChain:
     """cache on `owner` (a module) keyed by the parameters' versions"""
     key = tuple((p.data_ptr(), p._version) for lin in layers for p in (lin.weight, lin.bias) if p is not None)
     cache = owner.__dict__.setdefault("_chain_cache", {})
     ent = cache.get(name)
     if ent is None or ent[0] != key:
-        ent = (key, PackedChain(layers, acts, k_in, cols0=cols0))
+        ent = (key, PackedChain(layers, acts, k_in, cols0=cols0, weight_scale=weight_scale))
         cache[name] = ent
     return ent[1]
 
@@ -136,3 +158,102 @@ def chain_forward(pc: PackedChain, srcs: Sequence[torch.Tensor], M: Optional[int
                                           ptr(ops.status_word(dev)), stream()),
               "chain_f16_forward")
     return Ys[nl - 1], head_out, Ys[:-1]
+
+
+class ChainFn(torch.autograd.Function):
+    """Graph-recording forward of a fused chain: one chain_f16 launch with every layer's output kept, backward layer by
+    layer on the tensor-core gradient kernels (ops.linear_backward).  Same arithmetic and gradients as the equivalent
+    sequence of ops.linear calls.  apply(pc, layers_params..., ) is wrapped by chain_train()."""
+
+    @staticmethod
+    def forward(ctx, pc, acts, mods, M, has_res, head_act, nlayer, nsrc, cols0, *tensors):
+        # tensors = [W_0, b_0, ..., W_{n-1}, b_{n-1}] + ([head_W, head_b] if head_act >= 0) + srcs + ([res] if has_res)
+        k = 2 * nlayer
+        Ws, bs = list(tensors[0:k:2]), list(tensors[1:k:2])
+        head = None
+        if head_act >= 0:
+            head = (tensors[k], tensors[k + 1], head_act)
+            k += 2
+        srcs = list(tensors[k:k + nsrc])
+        res = tensors[k + nsrc] if has_res else None
+        y, h, inner = chain_forward(pc, srcs, M=M, mods=mods, out=True, res=res, head=head, keep_inner=True)
+        ctx.cfg = (acts, mods, M, has_res, head_act, nlayer, nsrc, cols0)
+        ctx.save_for_backward(*Ws, *([head[0]] if head else []), *srcs, *inner, y, *([h] if head else []), *([res] if has_res else []))
+        if head is not None:
+            ctx.mark_non_differentiable(y)
+            return y, h
+        return y, y.new_empty(0)
+
+    @staticmethod
+    def backward(ctx, dY, dH):
+        acts, mods, M, has_res, head_act, nlayer, nsrc, cols0 = ctx.cfg
+        sv = list(ctx.saved_tensors)
+        Ws = sv[:nlayer]; p = nlayer
+        head_W = None
+        if head_act >= 0:
+            head_W = sv[p]; p += 1
+        srcs = sv[p:p + nsrc]; p += nsrc
+        inner = sv[p:p + nlayer - 1]; p += nlayer - 1
+        y = sv[p]; p += 1
+        h = sv[p] if head_act >= 0 else None
+        p += 1 if head_act >= 0 else 0
+        res = sv[p] if has_res else None
+        Ys = inner + [y]
+        g_head = [None, None]
+        if head_act >= 0:
+            # head: h = act(y_last . w + b); its input is y_last AFTER the residual (none in that configuration)
+            (dY_from_head,), dWh, dbh = ops.linear_backward(head_W, h, [y], (), dH, head_act, [True])
+            g_head = [dWh, dbh]
+            dcur = dY_from_head
+        else:
+            dcur = dY
+        d_res = dcur if has_res else None
+        gW = [None] * nlayer
+        gb = [None] * nlayer
+        d_srcs = [None] * nsrc
+        for l in reversed(range(nlayer)):
+            ins = srcs if l == 0 else [Ys[l - 1]]
+            need = [ctx.needs_input_grad[9 + 2 * nlayer + (2 if head_act >= 0 else 0) + i] for i in range(nsrc)] if l == 0 else [True]
+            Wl = Ws[l]
+            if l == 0 and cols0 is not None:         # the kernel's source order is a column permutation of the reference weight
+                idx = _cols_index(cols0, Wl.device)[0]
+                Wl = Wl.index_select(1, idx)
+            d_in, gW[l], gb[l] = ops.linear_backward(Wl, Ys[l], ins, mods if l == 0 else (), dcur, acts[l], need, M=M)
+            if l == 0 and cols0 is not None and gW[l] is not None:
+                gW[l] = torch.zeros_like(gW[l]).index_copy_(1, idx, gW[l])
+            if l == 0:
+                d_srcs = d_in
+            else:
+                dcur = d_in[0]
+        grads = []
+        for l in range(nlayer):
+            grads += [gW[l], gb[l]]
+        if head_act >= 0:
+            grads += g_head
+        grads += list(d_srcs)
+        if has_res:
+            grads.append(d_res)
+        return (None,) * 9 + tuple(grads)
+
+
+def chain_train(pc: PackedChain, layers, acts, srcs, M=None, mods=(), res=None, head=None, cols0=None):
+    """autograd-aware fused chain.  layers: the nn.Linear modules (their parameters receive gradients); head = (nn.Linear, act) or
+    None.  Returns (y_last, head_out | None).  NOTE: with a residual the last activation must be 'none' (as in the mix-up block):
+    the saved output then includes the residual, which the identity derivative never reads."""
+    srcs = [ops._rows2d(s) for s in srcs]
+    if M is None:
+        M = srcs[0].shape[0]
+    assert res is None or acts[-1] == ops.ACT_NONE
+    tensors = []
+    for lin in layers:
+        tensors += [lin.weight, lin.bias]
+    head_act = -1
+    if head is not None:
+        tensors += [head[0].weight, head[0].bias]
+        head_act = int(head[1])
+    tensors += srcs
+    if res is not None:
+        tensors.append(res)
+    y, h = ChainFn.apply(pc, tuple(acts), tuple(mods), M, res is not None, head_act, len(layers), len(srcs),
+                         tuple(cols0) if cols0 is not None else None, *tensors)
+    return y, (h if head is not None else None)

@@ -257,7 +257,15 @@ class PointAggregator(nn.Module):
             with ops.tag("sample_mlp"):
                 pc = chain.packed_chain(self, "cf", [cf[0], cf[2], cf[4]], [ACT_LRELU] * 3, X5_W)
                 g = chain.chain_forward(pc, [X5])[0]
-        else:
+        # graph-recording forwards: the same chain kernel with every layer's output kept for the tensor-core backward
+        fused_t = self.mlp_engine == "tc" and torch.is_grad_enabled() and self.fused_train_forward and Nv >= 128
+        if fused_t:
+            from . import chain
+            TS = chain.TRAIN_WEIGHT_SCALE
+            with ops.tag("sample_mlp"):
+                pc = chain.packed_chain(self, "cf_t", [cf[0], cf[2], cf[4]], [ACT_LRELU] * 3, X5_W, weight_scale=TS)
+                g = chain.chain_train(pc, [cf[0], cf[2], cf[4]], [ACT_LRELU] * 3, [X5])[0]
+        elif not fused:
             with ops.tag("sample_mlp"):
                 g = ops.linear([X5], cf[0].weight, cf[0].bias, ACT_LRELU)
                 g = ops.linear([g], cf[2].weight, cf[2].bias, ACT_LRELU)
@@ -281,10 +289,16 @@ class PointAggregator(nn.Module):
             dv = delta.reshape(V, S, 3).index_select(1, vlist.long()).reshape(V * Nv, 3)
             am = self.aux_merge_weight_block
             with ops.tag("sample_mlp"):
-                t = ops.linear([aux.view(V * Nv, 45), g, dv], am[0].weight, am[0].bias, ACT_LRELU, mods=(0, Nv, 0), M=V * Nv)
-                t = ops.linear([t], am[2].weight, am[2].bias, ACT_LRELU)
-                t = ops.linear([t], am[4].weight, am[4].bias, ACT_LRELU)
-                sig = ops.linear([t], am[6].weight, am[6].bias, ACT_SIGMOID)
+                if fused_t:
+                    c0 = list(range(45, 173)) + list(range(45)) + [173, 174, 175]        # kernel source order [g | aux | dview]
+                    pc = chain.packed_chain(self, "am_t", [am[0], am[2], am[4]], [ACT_LRELU] * 3, 176, cols0=c0, weight_scale=TS)
+                    sig = chain.chain_train(pc, [am[0], am[2], am[4]], [ACT_LRELU] * 3, [g, aux.view(V * Nv, 45), dv], M=V * Nv,
+                                            mods=(Nv, 0, 0), head=(am[6], ACT_SIGMOID), cols0=c0)[1]
+                else:
+                    t = ops.linear([aux.view(V * Nv, 45), g, dv], am[0].weight, am[0].bias, ACT_LRELU, mods=(0, Nv, 0), M=V * Nv)
+                    t = ops.linear([t], am[2].weight, am[2].bias, ACT_LRELU)
+                    t = ops.linear([t], am[4].weight, am[4].bias, ACT_LRELU)
+                    sig = ops.linear([t], am[6].weight, am[6].bias, ACT_SIGMOID)
             with ops.tag("blend"):
                 merged = ops.BlendFn.apply(aux, sig, ok, self._keep_mask(R, SR, vlist))
         else:
@@ -297,6 +311,9 @@ class PointAggregator(nn.Module):
                 pc = chain.packed_chain(self, "cm", [cm[0], cm[2], cm[4]], [ACT_LRELU, ACT_LRELU, ACT_NONE], 96,
                                         cols0=list(range(45)) + [-1] * 3 + list(range(45, 90)) + [-1] * 3)
                 m = chain.chain_forward(pc, [g[:, :ops.AUX_LD], merged], res=gi)[0]
+            elif fused_t:
+                pc = chain.packed_chain(self, "cm_t", [cm[0], cm[2], cm[4]], [ACT_LRELU, ACT_LRELU, ACT_NONE], 90, weight_scale=TS)
+                m = chain.chain_train(pc, [cm[0], cm[2], cm[4]], [ACT_LRELU, ACT_LRELU, ACT_NONE], [gi, merged], res=gi)[0]
             else:
                 m = ops.linear([gi, merged], cm[0].weight, cm[0].bias, ACT_LRELU)
                 m = ops.linear([m], cm[2].weight, cm[2].bias, ACT_LRELU)
