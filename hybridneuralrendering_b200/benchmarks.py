@@ -20,7 +20,7 @@ def build_train_case(dev, points: int = 2_000_000, views: int = 8, seed: int = 0
                    max_o=1_000_000)       # >= occupied voxels of the 2M-point room (generator must respect max_o)
     xyz = syn.room_scene(points, 0)                        # the point cloud is replicated: same on every rank
     att = syn.point_attributes(np.random.default_rng(0), len(xyz))
-    fr = syn.room_frame(H=480, W=640, V=views, patch_num=8, patch_size=8, seed=seed)    # every rank draws its own ray batch
+    fr = syn.room_frame(H=480, W=640, V=views, patch_num=8, patch_size=8, seed=seed)
     c = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     pts = NeuralPoints(32, len(xyz), opt, dev)
     pts.set_points(c(xyz), c(att["emb"])[None], points_color=c(att["color"])[None], points_dir=c(att["dir"])[None],
@@ -40,7 +40,9 @@ def train_step_benchmark(dev, steps: int = 5, warmup: int = 3, world: int = 1, p
     import torch.distributed as dist
     from . import parallel
     from .renderer import training_loss
-    net, frame = build_train_case(dev, points, views, seed=rank)
+    # weak scaling: every rank gets the SAME amount of work (the same 4096-ray batch; gradients are still all-reduced), so that the
+    # max-over-ranks time measures the collective and not the spread of valid-sample counts between different batches
+    net, frame = build_train_case(dev, points, views, seed=0)
     agg = net.aggregator
     R = frame["raydir"].shape[1]
     params = [p for p in net.parameters() if p.requires_grad]
