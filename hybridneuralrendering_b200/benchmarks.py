@@ -51,6 +51,8 @@ def train_step_benchmark(dev, steps: int = 5, warmup: int = 3, world: int = 1, p
     opt_pts = FusedAdam([p for n, p in net.named_parameters() if p.requires_grad and n.startswith("neural_points.")], lr=2e-3)
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
 
+    ar = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+
     def fwd_bwd():
         for p in params:
             p.grad = None
@@ -59,8 +61,9 @@ def train_step_benchmark(dev, steps: int = 5, warmup: int = 3, world: int = 1, p
         with ops.tag("backward"):
             loss.backward()
         if world > 1:
-            with ops.tag("allreduce"):
-                parallel.allreduce_gradients(params, (out["ray_mask"] > 0).sum())
+            ar[0].record()
+            parallel.allreduce_gradients(params, (out["ray_mask"] > 0).sum())
+            ar[1].record()
         return out, loss
 
     for _ in range(warmup):
@@ -94,6 +97,9 @@ def train_step_benchmark(dev, steps: int = 5, warmup: int = 3, world: int = 1, p
             stages[tag] = stages.get(tag, 0.0) + s.elapsed_time(e)
         ops.TIMERS = None
     ex = net.last_extras
+    if world > 1:
+        torch.cuda.synchronize()
+        stages["allreduce (NCCL + scaling, device time of the last step)"] = ar[0].elapsed_time(ar[1])
     return {"metric": "train rays/s (fwd+bwd)", "value": R / (t_fb * 1e-3), "unit": "rays/s", "ms_fwd_bwd": t_fb, "ms_adam": t_opt,
             "rays": R, "kept_rays": int(ex.n_rays), "valid_samples": int(ex.n_valid), "valid_neighbours": agg.last_valid_neighbours(),
             "points": points, "views": views, "loss": float(loss.detach()), "launches_per_step": launches // steps,
