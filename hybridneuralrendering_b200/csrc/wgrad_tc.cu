@@ -17,7 +17,7 @@
 // Replaces hnr_linear_bwd_weight (linear_simt.cu) in LinearFn.backward; same argument meaning.
 #include "common.cuh"
 #include "hnr.h"
-#define TRACE_SRC ((long long*)nullptr)
+#define TRACE_SRC A.trace
 #include "tc_common.cuh"
 
 namespace {
@@ -45,6 +45,7 @@ struct WArgs {
     int ld[3], k[3];
     int64_t mod[3];
     float *dW, *db;
+    long long* trace;           // profiling aid (tc_common.cuh TRACE)
     int64_t M;
     int N, K, KWp, half;        // KWp: padded width of [X | 1]; half = KWp when one MMA group, else KWp / 2
 };
@@ -86,9 +87,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_tc_kernel(const __grid_cons
             const int ngroup = A.KWp / A.half;                 // 1 or 2
             const uint64_t dA = umma_desc(0, A_LBO, SBO), dB = umma_desc(0, B_LBO, SBO);
             const uint32_t s_base = smem_u32(smem);
+            TRACE_DECL(0);
+            if (lane != 0 || blockIdx.y != 0) tr__ = nullptr;
             for (int64_t it = 0; it < my_steps; ++it) {
                 const uint32_t s = (uint32_t)(it % NSTAGE), ph = (uint32_t)((it / NSTAGE) & 1);
                 mbar_wait(bar_full + 8 * s, ph);
+                TRACE(1, it & 0xffff, 0);
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t st = s_base + s * STAGE_BYTES;
@@ -146,35 +150,52 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_tc_kernel(const __grid_cons
             }
         }
         int64_t step = 0;
+        TRACE_DECL(1);
+        if (tid != 0 || blockIdx.y != 0) tr__ = nullptr;
         for (int64_t sit = 0; sit < my_super; ++sit) {
+            TRACE(10, sit & 0xffff, 0);
             const int64_t ms = (blockIdx.x + sit * gridDim.x) * (int64_t)(SUPER * KC);
             float val[SUPER][MAX_TASKS];
             float gate[SUPER][NA];
+            const bool full = ms + SUPER * KC <= A.M;         // every row of the super-step exists: no per-row tests
 #pragma unroll
             for (int q = 0; q < SUPER; ++q) {
                 const int64_t m = ms + q * KC + crow;
-                const bool inr = m < A.M;
-                int64_t mm[3] = {m, m, m};
-                if (HAS_MOD) {
+                if (full && !HAS_MOD && m < (1ll << 31)) {
+                    // fast path (trace-guided: the generic path spent ~75 cycles per load on 64-bit index arithmetic and row tests):
+                    // one 32-bit multiply + one wide add per load
+                    const uint32_t m32 = (uint32_t)m;
 #pragma unroll
-                    for (int s_ = 0; s_ < 3; ++s_)
-                        if (A.mod[s_] > 0) mm[s_] = m % A.mod[s_];
-                }
-#pragma unroll
-                for (int t = 0; t < MAX_TASKS; ++t) {
-                    float v = 0.f;
-                    if (inr) {
-                        if (cptr[t]) {
-                            const int64_t row = (HAS_MOD && t >= NA) ? (csrc[t] == 0 ? mm[0] : (csrc[t] == 1 ? mm[1] : mm[2])) : m;
-                            v = __ldg(cptr[t] + row * cld[t]);
-                        } else if ((ones_mask >> t) & 1u) {
-                            v = 1.f;
-                        }
+                    for (int t = 0; t < MAX_TASKS; ++t) {
+                        val[q][t] = cptr[t] ? __ldg(cptr[t] + (size_t)m32 * (uint32_t)cld[t]) : (((ones_mask >> t) & 1u) ? 1.f : 0.f);
+                        if (t < NA) gate[q][t] = gptr[t] ? __ldg(gptr[t] + (size_t)m32 * (uint32_t)A.ldy) : 1.f;
                     }
-                    val[q][t] = v;
-                    if (t < NA) gate[q][t] = (inr && gptr[t]) ? __ldg(gptr[t] + m * A.ldy) : 1.f;
+                } else {
+                    const bool inr = m < A.M;
+                    int64_t mm[3] = {m, m, m};
+                    if (HAS_MOD) {
+#pragma unroll
+                        for (int s_ = 0; s_ < 3; ++s_)
+                            if (A.mod[s_] > 0) mm[s_] = m % A.mod[s_];
+                    }
+#pragma unroll
+                    for (int t = 0; t < MAX_TASKS; ++t) {
+                        float v = 0.f;
+                        if (inr) {
+                            if (cptr[t]) {
+                                const int64_t row = (HAS_MOD && t >= NA) ? (csrc[t] == 0 ? mm[0] : (csrc[t] == 1 ? mm[1] : mm[2])) : m;
+                                v = __ldg(cptr[t] + row * cld[t]);
+                            } else if ((ones_mask >> t) & 1u) {
+                                v = 1.f;
+                            }
+                        }
+                        val[q][t] = v;
+                        if (t < NA) gate[q][t] = (inr && gptr[t]) ? __ldg(gptr[t] + m * A.ldy) : 1.f;
+                    }
                 }
             }
+            TRACE(11, sit & 0xffff, 0);
+            const bool lrelu = A.act == HNR_ACT_LRELU;
 #pragma unroll
             for (int q = 0; q < SUPER; ++q) {
                 if (ms + q * KC < A.M) {
@@ -186,7 +207,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_tc_kernel(const __grid_cons
                     for (int t = 0; t < MAX_TASKS; ++t) {
                         if (warp + t * NGEN_WARPS < ntask) {
                             float v = val[q][t];
-                            if (t < NA && gptr[t]) v *= act_grad_from_out(gate[q][t], A.act);
+                            if (t < NA && gptr[t]) v *= lrelu ? (gate[q][t] > 0.f ? 1.f : 0.01f) : act_grad_from_out(gate[q][t], A.act);
                             const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u), lo = v - hi;
                             const uint32_t off = t < NA ? dbase_a + (uint32_t)t * 512u : dbase_b + (uint32_t)(t - NA) * 512u;
                             *reinterpret_cast<float*>(st + off) = hi;
@@ -196,6 +217,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_tc_kernel(const __grid_cons
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_full + 8 * s);
+                    TRACE(12, sit & 0xffff, q);
                 }
             }
         }
@@ -239,6 +261,7 @@ extern "C" int hnr_linear_tc_bwd_weight(const float* dY, int64_t lddy, const flo
     WArgs A{};
     A.dY = dY; A.Y = Y; A.lddy = (int)lddy; A.ldy = (int)ldy; A.act = act;
     for (int i = 0; i < 3; ++i) { A.x[i] = a_ptr[i]; A.ld[i] = (int)a_ld[i]; A.k[i] = (int)a_k[i]; A.mod[i] = a_mod ? a_mod[i] : 0; }
+    A.trace = hnr_trace_ptr();
     A.dW = dW; A.db = db; A.M = M; A.N = (int)N; A.K = (int)K; A.KWp = (int)kw; A.half = (int)half;
     static bool configured = false;
     if (!configured) {

@@ -19,6 +19,14 @@ if mode == "fwd":
         lib().hnr_chain_f16_set_trace(ptr(buf))
         ops.linear([x], W, b, 1); torch.cuda.synchronize()
         lib().hnr_chain_f16_set_trace(None)
+elif mode == "wgrad":
+    with torch.no_grad():
+        y = ops.linear([x], W, b, 1)
+        gy = torch.randn_like(y)
+        ops.linear_backward(W, y, [x], (), gy, 1, [False], need_w=True); torch.cuda.synchronize()
+        lib().hnr_chain_f16_set_trace(ptr(buf))
+        ops.linear_backward(W, y, [x], (), gy, 1, [False], need_w=True); torch.cuda.synchronize()
+        lib().hnr_chain_f16_set_trace(None)
 else:                                   # data gradient only (gated A operand)
     with torch.no_grad():
         y = ops.linear([x], W, b, 1)
@@ -36,5 +44,7 @@ for role in range(3):
 ev.sort()
 t0 = ev[0][0]
 names = {1: "mma.A", 3: "mma.acc", 4: "mma.W", 10: "cv.start", 11: "cv.free", 12: "cv.deliv", 20: "epi.acc", 22: "epi.done"}
+if mode == "wgrad":
+    names = {1: "mma.step", 10: "gen.super", 11: "gen.loaded", 12: "gen.deliv"}
 for e in ev[:int(sys.argv[1]) if len(sys.argv) > 1 else 300]:
     print(f"{e[0] - t0:8d} {'  ' * e[1]}{names.get(e[2], e[2]):9s} {e[3]:4d}")
