@@ -253,8 +253,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(LArgs L) {
                             float4 y;
                             if (vec) y = __ldg(reinterpret_cast<const float4*>(gq));
                             else y = make_float4(__ldg(gq), __ldg(gq + 1), __ldg(gq + 2), __ldg(gq + 3));
-                            v.x *= act_grad_from_out(y.x, L.gate_act); v.y *= act_grad_from_out(y.y, L.gate_act);
-                            v.z *= act_grad_from_out(y.z, L.gate_act); v.w *= act_grad_from_out(y.w, L.gate_act);
+                            if (L.gate_act == HNR_ACT_LRELU) {           // the common case without the generic switch
+                                v.x *= y.x > 0.f ? 1.f : 0.01f; v.y *= y.y > 0.f ? 1.f : 0.01f;
+                                v.z *= y.z > 0.f ? 1.f : 0.01f; v.w *= y.w > 0.f ? 1.f : 0.01f;
+                            } else {
+                                v.x *= act_grad_from_out(y.x, L.gate_act); v.y *= act_grad_from_out(y.y, L.gate_act);
+                                v.z *= act_grad_from_out(y.z, L.gate_act); v.w *= act_grad_from_out(y.w, L.gate_act);
+                            }
                         }
                     }
                     dst[jj] = v;
