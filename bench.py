@@ -28,7 +28,8 @@ N_POINTS = 1_000_000
 V = 4
 CHUNK = None          # whole frame per query (one host readback per frame)
 WORKLOAD = "NeRF-synthetic lego-shaped full-frame render 800x800, synthetic 1M neural points (voxel query + aggregation + compositing)"
-CPU_SAMPLE_RAYS = 1024
+CPU_SAMPLE_RAYS = 12288      # 96 x 128 window at the image centre: ~10 s of host work per pass
+CPU_CHUNK_RAYS = 1024         # walked in chunks (the reference's own frame driver renders chunk by chunk, train_ft.py:282-351)
 
 
 def peaks():
@@ -134,9 +135,14 @@ def cpu_reference_sample(P, xyz, att, fr, opt, q_np, n_threads):
     from oracle import render_oracle as ro
     torch.set_num_threads(n_threads)
     cfg = ro.AggCfg(use_nearest=V)
+    n = int(q_np["sample_pidx"].shape[1])
+    pts = dict(xyz=xyz, **att)
+    out = None
     t0 = time.perf_counter()
     with torch.no_grad():
-        out = po.render_from_query(P, cfg, dict(xyz=xyz, **att), q_np, fr, float(opt.vsize[2]))
+        for r0 in range(0, n, CPU_CHUNK_RAYS):
+            qc = {k: q_np[k][:, r0:r0 + CPU_CHUNK_RAYS] for k in ("sample_pidx", "sample_loc", "sample_loc_w", "sample_ray_dirs")}
+            out = po.render_from_query(P, cfg, pts, qc, fr, float(opt.vsize[2]))
     dt = time.perf_counter() - t0
     return out, dt
 
@@ -176,7 +182,7 @@ def sample_query(xyz, att, fr, P, dev):
     """query tensors (numpy) for a bounded sample of rays around the image centre.  The reference has no
     CPU query (its query is CUDA only), so the sample's neighbour lists come from the product query on the
     GPU when one is present, else from the numpy oracle on a smaller sample."""
-    yy, xx = np.meshgrid(np.arange(H // 2 - 16, H // 2 + 16), np.arange(W // 2 - 16, W // 2 + 16), indexing="ij")
+    yy, xx = np.meshgrid(np.arange(H // 2 - 48, H // 2 + 48), np.arange(W // 2 - 64, W // 2 + 64), indexing="ij")
     ids = (yy * W + xx).reshape(-1)[:CPU_SAMPLE_RAYS]
     sub = dict(fr, raydir=fr["raydir"][:, ids])
     opt = make_opt_lego()
@@ -307,6 +313,7 @@ def main():
             from hybridneuralrendering_b200.benchmarks import blur_train_step_benchmark
             torch.cuda.empty_cache()
             line["train_blur"] = blur_train_step_benchmark(dev, steps=3, warmup=3)      # BASELINE configs[3]
+            line["train_blur_learnable"] = blur_train_step_benchmark(dev, steps=3, warmup=3, learnable=True)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         q_np, n_sample = sample_query(xyz, att, fr, P, dev)
         cores = os.cpu_count() or 1

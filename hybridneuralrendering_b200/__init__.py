@@ -6,7 +6,7 @@ C ABI, include/hnr.h).  No CPU / PyTorch fallback: the kernels are the only impl
 from .options import make_opt  # noqa: F401
 
 __all__ = ["make_opt", "lighting_fast_querier", "NeuralPoints", "PointAggregator", "NeuralPointsRayMarching", "ray_march",
-           "blur_update_output", "fill_invalid"]
+           "blur_update_output", "learnable_blur_update_output", "fill_invalid"]
 
 
 def __getattr__(name):
@@ -24,6 +24,8 @@ def __getattr__(name):
         from .diff_ray_marching import ray_march as v
     elif name == "blur_update_output":
         from .blur import blur_update_output as v
+    elif name == "learnable_blur_update_output":
+        from .blur import learnable_blur_update_output as v
     else:
         raise AttributeError(name)
     return v

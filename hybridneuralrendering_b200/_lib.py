@@ -53,6 +53,10 @@ _SIGS = {
     "hnr_composite_bwd": (C.c_int, [vp] * 11 + [i64, i64, vp, vp]),
     "hnr_blur_select_fwd": (C.c_int, [vp, vp, vp, i64, i64, i64, i64, vp, vp, vp]),
     "hnr_blur_select_bwd": (C.c_int, [vp, vp, vp, i64, i64, i64, i64, vp, vp]),
+    "hnr_blur_gray_fwd": (C.c_int, [vp, vp, i64, i64, vp, vp]),
+    "hnr_blur_gray_bwd": (C.c_int, [vp, i64, i64, vp, vp]),
+    "hnr_blur_learn_fwd": (C.c_int, [vp, vp, i64, i64, i64, i64, C.c_int, C.c_int, C.c_int, vp, vp]),
+    "hnr_blur_learn_bwd": (C.c_int, [vp, vp, i64, vp, i64, i64, i64, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
     "hnr_linear_tc_packed_bytes": (i64, [i64, i64]),
     "hnr_linear_tc_fwd": (C.c_int, [C.POINTER(vp), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), vp, i64, i64, vp, vp, i64, vp, i64, i64,
                                     i64, i64, C.c_int, vp, vp, C.c_int, vp, vp]),

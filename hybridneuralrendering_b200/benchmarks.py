@@ -109,15 +109,16 @@ def train_step_benchmark(dev, steps: int = 5, warmup: int = 3, world: int = 1, p
 BLUR_WORKLOAD = "full model with blur handling: 32x32 patch rays (4x4 dilated patches of 8x8) + pre-defined degradation-kernel convolution, fwd+bwd"
 
 
-def blur_train_step_benchmark(dev, steps: int = 5, warmup: int = 3, points: int = 2_000_000, views: int = 8) -> Dict:
+def blur_train_step_benchmark(dev, steps: int = 5, warmup: int = 3, points: int = 2_000_000, views: int = 8, learnable: bool = False) -> Dict:
     """BASELINE.json configs[3]: as the training step, but 1,024 rays on a 4x4 grid of 8x8 patches, the output filled back to
     the patch raster and passed through the blur module (36 pre-defined 9x9 kernels + identity, per-patch best match,
     models/base_rendering_model.py:677-786) before the loss; forward + backward through blur and render."""
     from . import NeuralPoints, NeuralPointsRayMarching, PointAggregator, make_opt
     from . import synthetic as syn
-    from .blur import blur_select, predefined_blur_kernels
+    from .blur import blur_select, learnable_blur, predefined_blur_kernels
     from .neural_points_volumetric_model import fill_invalid
-    opt = make_opt("scannet", use_nearest=views, SR=24, is_train=True, drop_ratio=0.5, dilation_setup="4_8_1_8", max_o=1_000_000)
+    opt = make_opt("scannet", use_nearest=views, SR=24, is_train=True, drop_ratio=0.5, dilation_setup="4_8_1_8", max_o=1_000_000,
+                   learnable_blur_kernel=int(learnable), boundary_mode=1)
     xyz = syn.room_scene(points, 0)
     att = syn.point_attributes(np.random.default_rng(0), len(xyz))
     fr = syn.room_frame(H=480, W=640, V=views, patch_num=4, patch_size=8, seed=0)
@@ -138,7 +139,10 @@ def blur_train_step_benchmark(dev, steps: int = 5, warmup: int = 3, points: int 
             p.grad = None
         out = net(**frame)
         full = fill_invalid(out, frame["bg_color"], net.last_extras.ray_ids)
-        blurred, _ = blur_select(full["coarse_raycolor"], frame["gt_image"], kernels, 4, 8)
+        if learnable:
+            blurred, _ = learnable_blur(full["coarse_raycolor"], frame["gt_image"], out["blur_predictor"], 4, 8, 9, 4, 0, 1)
+        else:
+            blurred, _ = blur_select(full["coarse_raycolor"], frame["gt_image"], kernels, 4, 8)
         loss = torch.nn.functional.mse_loss(blurred, frame["gt_image"])
         loss.backward()
         return loss
@@ -154,4 +158,5 @@ def blur_train_step_benchmark(dev, steps: int = 5, warmup: int = 3, points: int 
     torch.cuda.synchronize()
     ms = sum(s.elapsed_time(e) for s, e in ev) / steps
     return {"metric": "train rays/s (fwd+bwd, with blur module)", "value": R / (ms * 1e-3), "unit": "rays/s", "ms_fwd_bwd": ms, "rays": R,
-            "valid_samples": int(net.last_extras.n_valid), "loss": float(loss.detach()), "config": BLUR_WORKLOAD}
+            "valid_samples": int(net.last_extras.n_valid), "loss": float(loss.detach()),
+            "config": BLUR_WORKLOAD.replace("pre-defined degradation-kernel convolution", "learnable per-patch blur kernel") if learnable else BLUR_WORKLOAD}

@@ -1,6 +1,6 @@
 """Blur-handling module -- host-side mirror of BaseRenderingModel.blur_update_output
-(models/base_rendering_model.py:677-786) plus the pre-defined kernel bank the dataset builds
-(data/scannet_ft_dataset.py:184-242)."""
+(models/base_rendering_model.py:677-786) and learnable_blur_update_output (:827-1020), plus the pre-defined
+kernel bank the dataset builds (data/scannet_ft_dataset.py:184-242)."""
 from __future__ import annotations
 
 import math
@@ -26,6 +26,50 @@ def blur_update_output(model, faster_version=True):
         raise NotImplementedError
     out, _ = blur_select(model.output["coarse_raycolor"], model.gt_image, model.blur_kernels.to(model.output["coarse_raycolor"].device),
                          int(model.dilation_PatchNum), int(model.dilation_PatchSize))
+    model.output["coarse_raycolor"] = out
+
+
+def blur_predictor_forward(blur_predictor, feat: torch.Tensor) -> torch.Tensor:
+    """learn_blur_kernel_block (point_aggregators.py:715-749: Linear 2*ps^2 ->128->128->128-> ks^2[+1], LeakyReLU, final Sigmoid)
+    through the dense-layer kernels; feat (N, 2*ps^2)."""
+    if isinstance(blur_predictor, (list, tuple)):
+        raise NotImplementedError("learnable_blur_kernel_conv=1 (conv stem before the predictor MLP) is not selected by any shipped "
+                                  "script and is not implemented; there is no fallback path")
+    lins = [m for m in blur_predictor if isinstance(m, torch.nn.Linear)]
+    x = feat
+    for i, l in enumerate(lins):
+        x = ops.linear([x], l.weight, l.bias, ops.ACT_SIGMOID if i == len(lins) - 1 else ops.ACT_LRELU)
+    return x
+
+
+def learnable_blur(coarse_raycolor, gt_image, blur_predictor, patch_num: int, patch_size: int, kernel_size: int = 9, kernel_mode: int = 4,
+                   kernel_norm: int = 0, boundary_mode: int = 0):
+    """coarse_raycolor, gt_image (1,S*S,3) on the S x S patch raster -> (new coarse_raycolor (1,S*S,3), raw predictor output
+    (N, ks^2 [+1]))."""
+    if kernel_mode not in (0, 4) or kernel_norm not in (0, 1) or boundary_mode not in (0, 1, 2):
+        raise NotImplementedError(f"learnable blur: mode {kernel_mode} / norm {kernel_norm} / boundary {boundary_mode}")
+    pred = coarse_raycolor.reshape(-1, 3)
+    feat = ops.BlurGrayFn.apply(pred, gt_image.reshape(-1, 3), int(patch_num), int(patch_size))
+    raw = blur_predictor_forward(blur_predictor, feat)
+    out = ops.BlurLearnFn.apply(pred, raw, int(patch_num), int(patch_size), int(kernel_size), int(kernel_norm), int(kernel_mode),
+                                int(boundary_mode))
+    return out.view(1, -1, 3), raw
+
+
+def learnable_blur_update_output(model, blur_predictor, visualize=False, faster_version=True):
+    """drop-in body for BaseRenderingModel.learnable_blur_update_output (models/base_rendering_model.py:827-1020): reads
+    model.output["coarse_raycolor"], model.gt_image, model.dilation_PatchNum/Size and model.opt.{learnable_blur_kernel_size,
+    learnable_blur_kernel_mode, learnable_blur_kernel_norm, learnable_blur_kernel_conv, boundary_mode}; replaces
+    model.output["coarse_raycolor"]."""
+    if not faster_version or int(model.dilation_PatchNum) <= 0:
+        raise NotImplementedError
+    opt = model.opt
+    if getattr(opt, "learnable_blur_kernel_conv", 0):
+        raise NotImplementedError("learnable_blur_kernel_conv=1 is not implemented (no shipped script selects it)")
+    out, _ = learnable_blur(model.output["coarse_raycolor"], model.gt_image.to(model.output["coarse_raycolor"].device), blur_predictor,
+                            int(model.dilation_PatchNum), int(model.dilation_PatchSize), int(getattr(opt, "learnable_blur_kernel_size", 9)),
+                            int(getattr(opt, "learnable_blur_kernel_mode", 4)), int(getattr(opt, "learnable_blur_kernel_norm", 0)),
+                            int(getattr(opt, "boundary_mode", 0)))
     model.output["coarse_raycolor"] = out
 
 

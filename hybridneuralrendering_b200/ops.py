@@ -639,3 +639,57 @@ class BlurSelectFn(torch.autograd.Function):
         with _launch(name="blur_select_bwd"):
             check(lib().hnr_blur_select_bwd(ptr(g_out), ptr(kernels), ptr(sel), pn, ps, Nk, ks, ptr(g_pred), stream()), "blur_select_bwd")
         return g_pred, None, None, None, None
+
+
+class BlurGrayFn(torch.autograd.Function):
+    """pred, gt (S*S,3) on the patch raster -> predictor input rows (N, 2*ps*ps) = [mean_c gt | mean_c pred]
+    (base_rendering_model.py:887-889); gradient to pred only."""
+
+    @staticmethod
+    def forward(ctx, pred, gt, patch_num: int, patch_size: int):
+        pred, gt = _f32c(pred), _f32c(gt)
+        require_cuda(pred, gt)
+        feat = torch.empty((patch_num * patch_num, 2 * patch_size * patch_size), device=pred.device, dtype=torch.float32)
+        with _launch(name="blur_gray_fwd"):
+            check(lib().hnr_blur_gray_fwd(ptr(pred), ptr(gt), patch_num, patch_size, ptr(feat), stream()), "blur_gray_fwd")
+        ctx.geom = (patch_num, patch_size, tuple(pred.shape))
+        return feat
+
+    @staticmethod
+    def backward(ctx, g_feat):
+        pn, ps, shape = ctx.geom
+        g_feat = _f32c(g_feat)
+        g_pred = torch.empty(shape, device=g_feat.device, dtype=torch.float32)
+        with _launch(name="blur_gray_bwd"):
+            check(lib().hnr_blur_gray_bwd(ptr(g_feat), pn, ps, ptr(g_pred), stream()), "blur_gray_bwd")
+        return g_pred, None, None, None
+
+
+class BlurLearnFn(torch.autograd.Function):
+    """pred (S*S,3) on the patch raster, raw (N, ks*ks [+1]) predictor outputs -> blurred pred (S*S,3)
+    (base_rendering_model.py:893-1005); gradients to pred and raw."""
+
+    @staticmethod
+    def forward(ctx, pred, raw, patch_num: int, patch_size: int, kernel_size: int, norm_mode: int, mix_mode: int, boundary_mode: int):
+        pred, raw = _f32c(pred), _f32c(raw)
+        require_cuda(pred, raw)
+        assert raw.dim() == 2 and raw.shape[0] == patch_num * patch_num
+        out = torch.empty_like(pred)
+        with _launch(name="blur_learn_fwd"):
+            check(lib().hnr_blur_learn_fwd(ptr(pred), ptr(raw), raw.shape[1], patch_num, patch_size, kernel_size, norm_mode, mix_mode,
+                                           boundary_mode, ptr(out), stream()), "blur_learn_fwd")
+        ctx.save_for_backward(pred, raw)
+        ctx.geom = (patch_num, patch_size, kernel_size, norm_mode, mix_mode, boundary_mode)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        pred, raw = ctx.saved_tensors
+        pn, ps, ks, nm, mm, bm = ctx.geom
+        g_out = _f32c(g_out)
+        g_pred = torch.empty_like(pred)
+        g_raw = torch.zeros_like(raw)
+        with _launch(name="blur_learn_bwd"):
+            check(lib().hnr_blur_learn_bwd(ptr(pred), ptr(raw), raw.shape[1], ptr(g_out), pn, ps, ks, nm, mm, bm, ptr(g_pred), ptr(g_raw),
+                                           stream()), "blur_learn_bwd")
+        return g_pred, g_raw, None, None, None, None, None, None

@@ -121,6 +121,16 @@ class PointAggregator(nn.Module):
         self.color_mixup_block = _mlp([2 * aux_c, aux_c, aux_c, aux_c], act_last=False)
         self.color_final_block = nn.Sequential(nn.Linear(H // 2, 3))
         self.learn_blur_kernel_block = None
+        if getattr(opt, "learnable_blur_kernel", 0):
+            # blur-kernel predictor (reference :715-749): [gray gt patch | gray rendered patch] -> ks^2 taps (+1 combine weight)
+            if getattr(opt, "learnable_blur_kernel_conv", 0):
+                raise NotImplementedError("learnable_blur_kernel_conv=1 is not implemented (no shipped script selects it)")
+            kk = int(getattr(opt, "learnable_blur_kernel_size", 9)) ** 2
+            if int(getattr(opt, "learnable_blur_kernel_mode", 4)) in (2, 4):
+                kk += 1
+            self.learn_blur_kernel_block = _mlp([2 * int(getattr(opt, "learnable_blur_patch_size", 8)) ** 2, 128, 128, 128, kk],
+                                                act_last=False, final=nn.Sigmoid())
+            _init_seq(self.learn_blur_kernel_block)
         for m in (self.block1, self.block3, self.alpha_branch, self.color_branch, self.color_feature_branch,
                   self.aux_merge_weight_block, self.aux_block_s1, self.aux_block_s2, self.aux_block_s3, self.color_mixup_block,
                   self.color_final_block):
@@ -142,7 +152,7 @@ class PointAggregator(nn.Module):
                    mixup_mode="partial", learn_residuals=1, apply_pnt_mask=1, agg_weight_norm=1)
         bad = {k: getattr(opt, k, v) for k, v in req.items() if getattr(opt, k, v) != v}
         off = [k for k in ("tradition_attention", "refine_blend", "dynamic_weight", "add_idx", "separate_color_decoder",
-                           "large_color_final_block", "use_2D_CNN", "disable_viewdirs", "disable_color_feature", "learnable_blur_kernel",
+                           "large_color_final_block", "use_2D_CNN", "disable_viewdirs", "disable_color_feature", "learnable_blur_kernel_conv",
                            "downweight_blurry_feats", "dist_xyz_deno") if getattr(opt, k, 0)]
         if bad or off:
             raise NotImplementedError(f"PointAggregator: unsupported options {bad} / enabled flags {off}; only the shipped "

@@ -212,6 +212,21 @@ int hnr_blur_select_bwd(const float* g_out, const float* kernels, const int32_t*
                         int64_t num_kernels, int64_t kernel_size, float* g_pred, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Learnable blur-kernel branch: models/base_rendering_model.py:827-1020.
+ *   hnr_blur_gray_*   predictor input rows feat (N, 2*ps*ps) = [mean_c gt | mean_c pred] per patch (:883-889)
+ *   hnr_blur_learn_*  raw (N, ld_raw >= ks*ks [+1]) = the predictor's sigmoid outputs; kernel normalisation norm_mode 0 (/sum) or
+ *                     1 (softmax) (:895-899); mix_mode 0, or 4 = predicted weight * kernel + (1-weight) * identity, renormalised
+ *                     (:904-909); per-patch ks x ks zero-padded cross-correlation with boundary_mode 0 (/ (mask+1e-10)),
+ *                     1 (+ (1-mask) * input) or 2 (as 1 with the mask detached from the kernel gradient) (:915-923)
+ * ------------------------------------------------------------------------------------------- */
+int hnr_blur_gray_fwd(const float* pred /* S*S,3 */, const float* gt, int64_t patch_num, int64_t patch_size, float* feat, void* stream);
+int hnr_blur_gray_bwd(const float* g_feat, int64_t patch_num, int64_t patch_size, float* g_pred, void* stream);
+int hnr_blur_learn_fwd(const float* pred, const float* raw, int64_t ld_raw, int64_t patch_num, int64_t patch_size, int64_t kernel_size,
+                       int norm_mode, int mix_mode, int boundary_mode, float* out, void* stream);
+int hnr_blur_learn_bwd(const float* pred, const float* raw, int64_t ld_raw, const float* g_out, int64_t patch_num, int64_t patch_size,
+                       int64_t kernel_size, int norm_mode, int mix_mode, int boundary_mode, float* g_pred, float* g_raw, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Fused dense Adam step for the neural-point tables (reference: one torch.optim.Adam over the point
  * parameters, models/mvs_points_volumetric_model.py:94-104).  Same arithmetic as torch.optim.Adam (amsgrad off);
  * step = 1-based count after this update.  One read of p,g,m,v and one write of p,m,v per element.

@@ -316,6 +316,67 @@ def blur_select(pred: torch.Tensor, gt: torch.Tensor, kernels: torch.Tensor, pat
 
 
 # ----------------------------------------------------------------------------------------------
+# N3: learnable blur-kernel branch
+# ----------------------------------------------------------------------------------------------
+def learnable_blur(pred: torch.Tensor, gt: torch.Tensor, weights, patch_num: int, patch_size: int, kernel_size: int = 9,
+                   kernel_mode: int = 4, kernel_norm: int = 0, boundary_mode: int = 0):
+    """pred, gt (1,S*S,3) on the patch raster; weights = [(W,b)] * 4 of learn_blur_kernel_block (point_aggregators.py:715-749).
+    Returns (new_pred (1,S*S,3), raw predictor output (N, ks^2 [+1])).  base_rendering_model.py:827-1020 with
+    learnable_blur_kernel_conv=0."""
+    S, N, KK = patch_num * patch_size, patch_num * patch_num, kernel_size * kernel_size
+
+    def to_patches(x):
+        x = x.reshape(S, S, 3).permute(2, 0, 1).reshape(3, patch_num, patch_size, patch_num, patch_size)
+        return x.permute(1, 3, 0, 2, 4).reshape(N, 3, patch_size, patch_size)
+
+    xp, gp = to_patches(pred), to_patches(gt)
+    x = torch.cat([gp.mean(dim=1).reshape(N, -1), xp.mean(dim=1).reshape(N, -1)], dim=-1)          # :887-889
+    for i, (W, b) in enumerate(weights):
+        x = F.linear(x, W, b)
+        x = torch.sigmoid(x) if i == len(weights) - 1 else F.leaky_relu(x, 0.01)
+    raw = x
+    if kernel_norm == 0:                                                                             # :895-899
+        k = raw[:, :KK].view(N, 1, kernel_size, kernel_size)
+        k = k / k.sum(dim=(2, 3), keepdim=True)
+    else:
+        k = F.softmax(raw[:, :KK], dim=-1).view(N, 1, kernel_size, kernel_size)
+    if kernel_mode == 4:                                                                             # :904-909
+        wc = raw[:, -1][:, None, None, None]
+        ident = torch.zeros_like(k)
+        ident[:, :, kernel_size // 2, kernel_size // 2] = 1.0
+        k = wc * k + (1 - wc) * ident
+        k = k / k.sum(dim=(2, 3), keepdim=True)
+    elif kernel_mode != 0:
+        raise NotImplementedError
+    xin = xp.permute(1, 0, 2, 3)                                                                     # (3,N,p,p): groups = patches
+    pad = kernel_size // 2
+    if boundary_mode == 0:                                                                           # :915-923
+        m = F.conv2d(torch.ones_like(xin), k, padding=pad, groups=N)
+        y = F.conv2d(xin, k, padding=pad, groups=N) / (m + 1e-10)
+    elif boundary_mode in (1, 2):
+        m = F.conv2d(torch.ones_like(xin), k if boundary_mode == 1 else k.detach(), padding=pad, groups=N)
+        y = F.conv2d(xin, k, padding=pad, groups=N) + (1 - m) * xin
+    else:
+        raise NotImplementedError
+    best = y.permute(1, 0, 2, 3)                                                                     # (N,3,p,p)
+    img = best.reshape(patch_num, patch_num, 3, patch_size, patch_size).permute(2, 0, 3, 1, 4).reshape(3, S, S)
+    return img.permute(1, 2, 0).reshape(1, S * S, 3), raw
+
+
+def blur_predictor_params(seed: int, patch_size: int = 8, kernel_size: int = 9, kernel_mode: int = 4):
+    """seeded weights [(W,b)]*4 of learn_blur_kernel_block (numpy PCG64; larger than init_seq's so the predicted taps are far
+    from uniform).  Used by tests/golden/make_golden.py and by the tests, so the fixtures store only reference OUTPUTS."""
+    rng = np.random.default_rng(seed)
+    sizes = [2 * patch_size * patch_size, 128, 128, 128, kernel_size * kernel_size + (1 if kernel_mode in (2, 4) else 0)]
+    out = []
+    for i in range(4):
+        W = (rng.standard_normal((sizes[i + 1], sizes[i])) * (2.5 / np.sqrt(sizes[i]))).astype(np.float32)
+        b = (rng.standard_normal((sizes[i + 1],)) * 0.5).astype(np.float32)
+        out.append((torch.from_numpy(W), torch.from_numpy(b)))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
 # weights
 # ----------------------------------------------------------------------------------------------
 LAYER_SHAPES = {

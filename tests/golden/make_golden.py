@@ -180,10 +180,55 @@ def blur_case():
     print("blur ok")
 
 
+def learnable_blur_case():
+    """learnable_blur_update_output (base_rendering_model.py:827-1020) called unbound on a namespace, with the predictor MLP
+    built by the reference's own PointAggregator(opt.learnable_blur_kernel=1) (point_aggregators.py:715-749).  One file, four
+    option sets: the shipped one (mode 4, /sum, boundary 1) and the other norm / mode / boundary branches."""
+    import types
+    BaseRenderingModel = ref_import.import_with_stubs("models.base_rendering_model").BaseRenderingModel
+    rng = np.random.default_rng(21)
+    PN, PS, KS = 3, 8, 9
+    S = PN * PS
+    pred0 = rng.random((1, S * S, 3), dtype=np.float32)
+    gt = T(rng.random((1, S * S, 3), dtype=np.float32))
+    G = T(rng.standard_normal((1, S * S, 3)).astype(np.float32))
+    res = dict(pred=pred0, gt=gt.numpy(), G=G.numpy(), meta=np.array([PN, PS, KS]))
+    cases = [(4, 0, 1), (4, 0, 0), (0, 1, 2), (4, 1, 2)]            # (kernel_mode, kernel_norm, boundary_mode)
+    res["cases"] = np.array(cases)
+    for ci, (mode, norm, bmode) in enumerate(cases):
+        opt = ref_import.shipped_opt(is_train=True, learnable_blur_kernel=1, learnable_blur_kernel_size=KS, learnable_blur_patch_size=PS,
+                                     learnable_blur_kernel_mode=mode, learnable_blur_kernel_norm=norm, learnable_blur_kernel_conv=0,
+                                     boundary_mode=bmode)
+        agg = ref_import.aggregator(opt)
+        blk = agg.learn_blur_kernel_block
+        lins = [m for m in blk if isinstance(m, torch.nn.Linear)]
+        with torch.no_grad():
+            for m, (W, b) in zip(lins, ro.blur_predictor_params(100 + ci, PS, KS, mode)):
+                m.weight.copy_(W)
+                m.bias.copy_(b)
+        pred = T(pred0.copy()).requires_grad_(True)
+        ns = types.SimpleNamespace(dilation_PatchNum=PN, dilation_PatchSize=PS, gt_image=gt, output={"coarse_raycolor": pred},
+                                   xv_patches=[], yv_patches=[], opt=opt)
+        BaseRenderingModel.learnable_blur_update_output(ns, blk)
+        out = ns.output["coarse_raycolor"]
+        (out * G).sum().backward()
+        res[f"c{ci}_out"] = out.detach().numpy()
+        res[f"c{ci}_grad_pred"] = pred.grad.numpy().copy()
+        for li, m in enumerate([m for m in blk if isinstance(m, torch.nn.Linear)]):
+            res[f"c{ci}_gW{li}"] = m.weight.grad.numpy().copy()
+            res[f"c{ci}_gb{li}"] = m.bias.grad.numpy().copy()
+    np.savez_compressed(os.path.join(OUT, "blur_learn.npz"), **res)
+    print("learnable blur ok")
+
+
 if __name__ == "__main__":
+    if "--only-learnable-blur" in sys.argv:
+        learnable_blur_case()
+        sys.exit(0)
     torch.set_num_threads(4)
     agg_case("agg_eval", R=12, SR=5, V=2, H=20, W=24, is_train=False, drop_ratio=0.0, dilation_setup="7_8_1_8", seed=1, with_grad=False)
     agg_case("agg_train", R=16, SR=6, V=3, H=24, W=20, is_train=True, drop_ratio=0.5, dilation_setup="2_2_1_8", seed=2, with_grad=True)
     misc_cases()
     projection_case()
     blur_case()
+    learnable_blur_case()

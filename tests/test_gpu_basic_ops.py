@@ -102,6 +102,64 @@ def test_blur_module_method_dropin_shipped_shape():
     assert_close(m.output["coarse_raycolor"], ref, RTOL, 1e-6)
 
 
+def _blur_predictor(params):
+    """learn_blur_kernel_block with the given [(W,b)]*4, built by the product's own aggregator so the state_dict names are the
+    checkpoint's (learn_blur_kernel_block.{0,2,4,6})."""
+    from hybridneuralrendering_b200 import PointAggregator, make_opt
+    KK1, K0 = params[-1][0].shape[0], params[0][0].shape[1]
+    ks = int(np.sqrt(KK1))
+    agg = PointAggregator(make_opt(is_train=True, learnable_blur_kernel=1, learnable_blur_kernel_size=ks,
+                                   learnable_blur_patch_size=int(np.sqrt(K0 // 2)), learnable_blur_kernel_mode=4 if KK1 > ks * ks else 0)).cuda()
+    sd = {}
+    for li, (W, b) in enumerate(params):
+        sd[f"learn_blur_kernel_block.{2 * li}.weight"], sd[f"learn_blur_kernel_block.{2 * li}.bias"] = W, b
+    missing = agg.load_state_dict(sd, strict=False)
+    assert not missing.unexpected_keys
+    return agg.learn_blur_kernel_block
+
+
+def test_learnable_blur_golden_fwd_bwd():
+    """N3: learnable_blur_update_output through the drop-in method body vs outputs and gradients of the unmodified
+    reference (tests/golden/blur_learn.npz), every norm / mode / boundary branch of the fixture."""
+    import types
+    from hybridneuralrendering_b200.blur import learnable_blur_update_output
+    G = load_golden("blur_learn")
+    PN, PS, KS = [int(v) for v in G["meta"]]
+    for ci, (mode, norm, bmode) in enumerate(G["cases"].tolist()):
+        blk = _blur_predictor(ro.blur_predictor_params(100 + ci, PS, KS, mode))
+        pred = cuda(G["pred"]).clone().requires_grad_(True)
+        opt = types.SimpleNamespace(learnable_blur_kernel_size=KS, learnable_blur_kernel_mode=mode, learnable_blur_kernel_norm=norm,
+                                    learnable_blur_kernel_conv=0, boundary_mode=bmode)
+        m = types.SimpleNamespace(output={"coarse_raycolor": pred}, gt_image=cuda(G["gt"]), dilation_PatchNum=PN, dilation_PatchSize=PS, opt=opt)
+        learnable_blur_update_output(m, blk)
+        out = m.output["coarse_raycolor"]
+        assert_close(out, G[f"c{ci}_out"], RTOL, 1e-6, f"case {ci} out")
+        (out * cuda(G["G"])).sum().backward()
+        assert_close(pred.grad, G[f"c{ci}_grad_pred"], RTOL, grad_atol(G[f"c{ci}_grad_pred"]), f"case {ci} d pred")
+        for li in range(4):
+            lin = blk[2 * li]
+            assert_close(lin.weight.grad, G[f"c{ci}_gW{li}"], RTOL, grad_atol(G[f"c{ci}_gW{li}"]), f"case {ci} dW{li}")
+            assert_close(lin.bias.grad, G[f"c{ci}_gb{li}"], RTOL, grad_atol(G[f"c{ci}_gb{li}"]), f"case {ci} db{li}")
+
+
+def test_learnable_blur_shipped_shape_vs_oracle():
+    """7x7 patches of 8x8, 9x9 predicted kernels, mode 4 / boundary 1 (the *_learnable.sh configuration) vs the oracle, plus the
+    identity property: a combine weight of 0 (last predictor bias -> -inf) leaves the rendered colours unchanged."""
+    from hybridneuralrendering_b200.blur import learnable_blur
+    rng = np.random.default_rng(5)
+    PN, PS, KS = 7, 8, 9
+    P = ro.blur_predictor_params(7, PS, KS, 4)
+    pred, gt = T(rng.random((1, (PN * PS) ** 2, 3), dtype=np.float32)), T(rng.random((1, (PN * PS) ** 2, 3), dtype=np.float32))
+    ref, raw_ref = ro.learnable_blur(pred, gt, P, PN, PS, KS, 4, 0, 1)
+    out, raw = learnable_blur(pred.cuda(), gt.cuda(), _blur_predictor(P), PN, PS, KS, 4, 0, 1)
+    assert_close(raw, raw_ref, RTOL, 1e-6)
+    assert_close(out, ref, RTOL, 1e-6)
+    P[-1][1][-1] = -1e4                          # sigmoid -> 0: kernel = identity
+    out, raw = learnable_blur(pred.cuda(), gt.cuda(), _blur_predictor(P), PN, PS, KS, 4, 0, 1)
+    assert float(raw[:, -1].abs().max()) == 0.0
+    assert_close(out, pred, 1e-6, 1e-7)
+
+
 @pytest.mark.parametrize("M,N,ks,act", [(1, 1, (5,), 0), (130, 256, (284,), 1), (257, 256, (256, 7), 1), (300, 64, (45, 128, 3), 1),
                                          (77, 1, (64,), 2), (64, 3, (45, 83), 3), (1000, 45, (45,), 0), (0, 8, (4,), 1)])
 def test_linear_fwd_bwd_vs_torch(M, N, ks, act):

@@ -118,3 +118,22 @@ def test_blur_matches_reference():
     (out * T(G["G"])).sum().backward()
     np.testing.assert_allclose(pred.grad.numpy(), G["grad_pred"], rtol=1e-5, atol=1e-7)
     assert len(set(sel.tolist())) > 1, "fixture should exercise more than one candidate"
+
+
+def test_learnable_blur_matches_reference():
+    """N3: oracle restatement of learnable_blur_update_output vs the unmodified reference, all option branches of the fixture
+    (outputs, gradient w.r.t. the rendered colours and every predictor weight)."""
+    G = _load("blur_learn")
+    PN, PS, KS = [int(v) for v in G["meta"]]
+    for ci, (mode, norm, bmode) in enumerate(G["cases"].tolist()):
+        W = [(w.clone().requires_grad_(True), b.clone().requires_grad_(True)) for w, b in ro.blur_predictor_params(100 + ci, PS, KS, mode)]
+        pred = T(G["pred"]).clone().requires_grad_(True)
+        out, raw = ro.learnable_blur(pred, T(G["gt"]), W, PN, PS, KS, mode, norm, bmode)
+        np.testing.assert_allclose(out.detach().numpy(), G[f"c{ci}_out"], rtol=1e-5, atol=1e-6)
+        (out * T(G["G"])).sum().backward()
+        ref = G[f"c{ci}_grad_pred"]
+        np.testing.assert_allclose(pred.grad.numpy(), ref, rtol=1e-4, atol=1e-5 * np.abs(ref).max())
+        for li, (w, b) in enumerate(W):
+            for got, key in ((w.grad, f"c{ci}_gW{li}"), (b.grad, f"c{ci}_gb{li}")):
+                np.testing.assert_allclose(got.numpy(), G[key], rtol=1e-4, atol=1e-4 * np.abs(G[key]).max() + 1e-12)
+        assert raw.std() > 0.05, "fixture should predict non-uniform kernels"
