@@ -47,6 +47,7 @@ _SIGS = {
     "hnr_linear_fwd": (C.c_int, [C.POINTER(vp), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), vp, vp, vp, i64, vp, i64, i64, i64,
                                  i64, C.c_int, vp]),
     "hnr_linear_bwd_data": (C.c_int, [vp, i64, vp, i64, vp, C.POINTER(vp), C.POINTER(i64), C.POINTER(i64), i64, i64, i64, C.c_int, vp]),
+    "hnr_linear_bwd_data_narrow": (C.c_int, [vp, i64, vp, i64, C.c_int, vp, i64, i64, i64, vp, i64, i64, i64, vp]),
     "hnr_linear_bwd_weight": (C.c_int, [vp, i64, vp, i64, C.POINTER(vp), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), vp, vp, i64,
                                         i64, i64, C.c_int, vp]),
     "hnr_composite_fwd": (C.c_int, [vp, vp, vp, C.c_int, vp, vp, f32c, C.c_int, i64, i64, vp, vp, vp, vp, vp, vp, vp]),

@@ -221,6 +221,7 @@ alpha_ksum_fwd_kernel(const float* __restrict__ H, const float* __restrict__ wei
 }
 
 // grid-stride over samples so the dense-weight gradient is accumulated in registers first
+template <int KT>      // KT > 0: compile-time neighbour count (the K-loop unrolls and its 2*K row loads are issued up front)
 __global__ void __launch_bounds__(256)
 alpha_ksum_bwd_kernel(const float* __restrict__ H, const float* __restrict__ weight, const float* __restrict__ confc,
                       const int32_t* __restrict__ vlist, const float* __restrict__ w_alpha, const float* __restrict__ alpha_raw,
@@ -238,11 +239,13 @@ alpha_ksum_bwd_kernel(const float* __restrict__ H, const float* __restrict__ wei
         const float ds = d_sigma[v];
         const float4* g4 = reinterpret_cast<const float4*>(dX5 + v * X5_W) + lane * 2;
         const float4 g0 = g4[0], g1 = g4[1];
-        for (int k = 0; k < K; ++k) {
-            const int64_t row = v * K + k;
+        const int KK = KT > 0 ? KT : K;
+#pragma unroll
+        for (int k = 0; k < KK; ++k) {
+            const int64_t row = v * KK + k;
             const float4* h4 = reinterpret_cast<const float4*>(H + row * HID) + lane * 2;
             float4 h0 = h4[0], h1 = h4[1];
-            float wc = weight[s * K + k] * (confc ? confc[s * K + k] : 1.f);
+            float wc = weight[s * KK + k] * (confc ? confc[s * KK + k] : 1.f);
             float raw = alpha_raw[row] - 1.f;
             float sp = softplus_t(raw);
             float sgm = 1.f / (1.f + expf(-raw));
@@ -260,10 +263,21 @@ alpha_ksum_bwd_kernel(const float* __restrict__ H, const float* __restrict__ wei
             gb += draw;
         }
     }
-    float* o = d_walpha + lane * 8;
-    atomicAdd(o + 0, gw0.x); atomicAdd(o + 1, gw0.y); atomicAdd(o + 2, gw0.z); atomicAdd(o + 3, gw0.w);
-    atomicAdd(o + 4, gw1.x); atomicAdd(o + 5, gw1.y); atomicAdd(o + 6, gw1.z); atomicAdd(o + 7, gw1.w);
-    if (lane == 0) atomicAdd(d_balpha, gb);
+    // CTA-level reduction first: one global atomic per channel per CTA instead of one per warp (the 256 addresses are shared
+    // by every warp of the grid)
+    __shared__ float red[8][HID + 1];
+    {
+        float* o = &red[threadIdx.x >> 5][lane * 8];
+        o[0] = gw0.x; o[1] = gw0.y; o[2] = gw0.z; o[3] = gw0.w; o[4] = gw1.x; o[5] = gw1.y; o[6] = gw1.z; o[7] = gw1.w;
+        if (lane == 0) red[threadIdx.x >> 5][HID] = gb;
+    }
+    __syncthreads();
+    const int nw = blockDim.x >> 5;
+    for (int c = threadIdx.x; c <= HID; c += blockDim.x) {
+        float t = 0.f;
+        for (int w = 0; w < nw; ++w) t += red[w][c];
+        atomicAdd(c < HID ? d_walpha + c : d_balpha, t);
+    }
 }
 
 // gradient of the per-point confidence: through wc = w_hat * clampST(conf) (identity gradient) for
@@ -283,9 +297,14 @@ __global__ void conf_bwd_kernel(const float* __restrict__ d_wc, const float* __r
 __global__ void conf_up_bwd_kernel(const float* __restrict__ d_confc, const int32_t* __restrict__ pidx, int64_t n,
                                    float* __restrict__ d_conf) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float g = d_confc[i];
-    if (g != 0.f) atomicAdd(&d_conf[max(pidx[i], 0)], g);
+    const bool in = i < n;
+    const float g = in ? d_confc[i] : 0.f;
+    const int p = in ? pidx[i] : 0;
+    // masked slots (pidx < 0) all alias point 0: one atomic per warp instead of one per slot (hundreds of thousands of
+    // same-address atomics serialise)
+    const float gm = warp_sum(p < 0 ? g : 0.f);
+    if ((threadIdx.x & 31) == 0 && gm != 0.f) atomicAdd(&d_conf[0], gm);
+    if (p >= 0 && g != 0.f) atomicAdd(&d_conf[p], g);
 }
 
 // ------------------------------------------------------------------ P1: projection into the reference views
@@ -571,8 +590,12 @@ extern "C" int hnr_alpha_ksum_bwd(const float* H, const float* weight, const flo
     if (Nv == 0) return HNR_OK;
     int64_t blocks = hnr_cdiv(Nv * 32, 256);
     if (blocks > 8 * HNR_NUM_SMS) blocks = 8 * HNR_NUM_SMS;
-    alpha_ksum_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(H, weight, confc, vlist, w_alpha, alpha_raw, d_sigma, dX5,
-                                                                             Nv, (int)K, dH, d_wc, d_walpha, d_balpha);
+    if (K == 8)
+        alpha_ksum_bwd_kernel<8><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(H, weight, confc, vlist, w_alpha, alpha_raw, d_sigma, dX5,
+                                                                                    Nv, (int)K, dH, d_wc, d_walpha, d_balpha);
+    else
+        alpha_ksum_bwd_kernel<0><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(H, weight, confc, vlist, w_alpha, alpha_raw, d_sigma, dX5,
+                                                                                    Nv, (int)K, dH, d_wc, d_walpha, d_balpha);
     HNR_CHECK_LAUNCH("alpha_ksum_bwd");
     return HNR_OK;
 }

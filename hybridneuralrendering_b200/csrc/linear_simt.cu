@@ -242,6 +242,123 @@ __global__ void __launch_bounds__(256) linear_fwd_smalln_kernel(Cat3 A, const fl
     }
 }
 
+// Weight gradient of the same heads (N <= 4 outputs, K <= 128 inputs): dW[n,k] += sum_m dPre[m,n] A[m,k], db[n] += sum_m dPre[m,n].
+// One warp per row, lanes stride over K (coalesced), per-warp register accumulators over a grid-stride row loop, one shared-memory
+// reduction per CTA, then one global atomic per (n,k) per CTA.  HBM-bound: reads M x K once (the 64x64 GEMM tile of
+// linear_bwd_weight_kernel wastes 60 of 64 output rows: 514 us for the 64->1 blend-weight head at M = 602k, trace of round 1).
+constexpr int SMALLN_BWD_MAXK = 128;
+__global__ void __launch_bounds__(256) linear_bwd_weight_smalln_kernel(const float* __restrict__ dY, int lddy, const float* __restrict__ Y,
+                                                                        int ldy, Cat3 A, float* __restrict__ dW, float* __restrict__ db,
+                                                                        int64_t M, int N, int K, int act) {
+    __shared__ float sW[4 * SMALLN_BWD_MAXK + 4];
+    for (int i = threadIdx.x; i < 4 * SMALLN_BWD_MAXK + 4; i += blockDim.x) sW[i] = 0.f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int b1 = A.k[0], b2 = A.k[0] + A.k[1];
+    float acc[4][4] = {};
+    float bs[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int64_t m = warp0; m < M; m += nwarps) {
+        float dp = 0.f;
+        if (lane < N) {
+            dp = dY[m * lddy + lane];
+            if (act != HNR_ACT_NONE) dp *= act_grad_from_out(Y[m * ldy + lane], act);
+        }
+        float d[4];
+#pragma unroll
+        for (int n = 0; n < 4; ++n) d[n] = __shfl_sync(0xffffffffu, dp, n);
+        const float* r0 = A.p[0] + (A.mod[0] > 0 ? m % A.mod[0] : m) * A.ld[0];
+        const float* r1 = A.k[1] > 0 ? A.p[1] + (A.mod[1] > 0 ? m % A.mod[1] : m) * A.ld[1] : nullptr;
+        const float* r2 = A.k[2] > 0 ? A.p[2] + (A.mod[2] > 0 ? m % A.mod[2] : m) * A.ld[2] : nullptr;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = lane + 32 * j;
+            if (k < K) {
+                const float x = k < b1 ? r0[k] : (k < b2 ? r1[k - b1] : r2[k - b2]);
+#pragma unroll
+                for (int n = 0; n < 4; ++n) acc[n][j] = fmaf(d[n], x, acc[n][j]);
+            }
+        }
+#pragma unroll
+        for (int n = 0; n < 4; ++n) bs[n] += d[n];
+    }
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+        if (n >= N) break;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = lane + 32 * j;
+            if (k < K) atomicAdd(&sW[n * SMALLN_BWD_MAXK + k], acc[n][j]);
+        }
+        if (lane == 0) atomicAdd(&sW[4 * SMALLN_BWD_MAXK + n], bs[n]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < N * K; i += blockDim.x) atomicAdd(&dW[i], sW[(i / K) * SMALLN_BWD_MAXK + (i % K)]);
+    if (db && threadIdx.x < N) atomicAdd(&db[threadIdx.x], sW[4 * SMALLN_BWD_MAXK + threadIdx.x]);
+}
+
+// Data gradient of a NARROW column slice of a wide layer: dA[m, 0..KN) = sum_n dPre[m,n] W[n, k0 + 0..KN), KN <= 8 output columns,
+// N = 128*NV reduction columns (NV <= 2).  Used for the 7 extra inputs of block3's first layer (colour, dir - view, <dir,view>;
+// point_aggregators.py:1002-1010): the tensor-core slice kernel spends a full pass (1.3 ms at M = 562k) on them because its cost is
+// reading and converting dY, not the MMAs.  Warp per row, the W slice lives in registers, float4 row loads, butterfly reduction:
+// HBM-bound, one read of dY and Y.
+template <int NV>
+__global__ void __launch_bounds__(256) linear_bwd_data_narrow_kernel(const float* __restrict__ dY, int lddy, const float* __restrict__ Y,
+                                                                      int ldy, int act, const float* __restrict__ W, int ldw, int k0, int KN,
+                                                                      float* __restrict__ dA, int ldda, int64_t M) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    // lane owns reduction columns n = 128*v + 4*lane + c  (v < NV, c < 4): conflict-free float4 row loads
+    float w[8][NV * 4];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int v = 0; v < NV; ++v)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) w[k][v * 4 + c] = k < KN ? W[(int64_t)(128 * v + 4 * lane + c) * ldw + k0 + k] : 0.f;
+    for (int64_t m = warp0; m < M; m += nwarps) {
+        float g[NV * 4];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            const float4 d4 = *reinterpret_cast<const float4*>(dY + m * lddy + 128 * v + 4 * lane);
+            g[v * 4 + 0] = d4.x; g[v * 4 + 1] = d4.y; g[v * 4 + 2] = d4.z; g[v * 4 + 3] = d4.w;
+            if (act != HNR_ACT_NONE) {
+                const float4 y4 = *reinterpret_cast<const float4*>(Y + m * ldy + 128 * v + 4 * lane);
+                g[v * 4 + 0] *= act_grad_from_out(y4.x, act); g[v * 4 + 1] *= act_grad_from_out(y4.y, act);
+                g[v * 4 + 2] *= act_grad_from_out(y4.z, act); g[v * 4 + 3] *= act_grad_from_out(y4.w, act);
+            }
+        }
+        float out = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float a = 0.f;
+#pragma unroll
+            for (int i = 0; i < NV * 4; ++i) a = fmaf(g[i], w[k][i], a);
+            a = warp_sum(a);
+            if (lane == k) out = a;
+        }
+        if (lane < KN) dA[m * ldda + lane] = out;
+    }
+}
+
+extern "C" int hnr_linear_bwd_data_narrow(const float* dY, int64_t lddy, const float* Y, int64_t ldy, int act, const float* W, int64_t ldw,
+                                          int64_t k0, int64_t kn, float* dA, int64_t ldda, int64_t M, int64_t N, void* stream) {
+    if (M == 0) return HNR_OK;
+    HNR_CHECK_ARG(kn > 0 && kn <= 8 && (N == 128 || N == 256), "linear_bwd_data_narrow: 1..8 output columns, 128 or 256 reduction columns");
+    HNR_CHECK_ARG(lddy % 4 == 0 && ldy % 4 == 0 && ((uintptr_t)dY & 15) == 0 && ((uintptr_t)Y & 15) == 0,
+                  "linear_bwd_data_narrow: dY / Y rows must be 16-byte aligned");
+    const int64_t blocks = hnr_cdiv(M, 8);
+    const int g = (int)(blocks < 8 * HNR_NUM_SMS ? blocks : 8 * HNR_NUM_SMS);
+    if (N == 256)
+        linear_bwd_data_narrow_kernel<2><<<g, 256, 0, (cudaStream_t)stream>>>(dY, (int)lddy, Y, (int)ldy, act, W, (int)ldw, (int)k0, (int)kn, dA,
+                                                                             (int)ldda, M);
+    else
+        linear_bwd_data_narrow_kernel<1><<<g, 256, 0, (cudaStream_t)stream>>>(dY, (int)lddy, Y, (int)ldy, act, W, (int)ldw, (int)k0, (int)kn, dA,
+                                                                             (int)ldda, M);
+    HNR_CHECK_LAUNCH("linear_bwd_data_narrow");
+    return HNR_OK;
+}
+
 extern "C" int hnr_linear_fwd(const float* const* a_ptr, const int64_t* a_ld, const int64_t* a_k, const int64_t* a_mod, const float* W, const float* bias,
                               const float* res, int64_t ldres, float* Y, int64_t ldy, int64_t M, int64_t N, int64_t K, int act,
                               void* stream) {
@@ -285,6 +402,13 @@ extern "C" int hnr_linear_bwd_weight(const float* dY, int64_t lddy, const float*
     HNR_CHECK_ARG(cat_ok(a_ptr, a_ld, a_k, K), "linear_bwd_weight: concat widths must sum to K");
     Cat3 A;
     for (int i = 0; i < 3; ++i) { A.p[i] = a_ptr[i]; A.ld[i] = (int)a_ld[i]; A.k[i] = (int)a_k[i]; A.mod[i] = a_mod ? a_mod[i] : 0; }
+    if (N <= 4 && K <= SMALLN_BWD_MAXK) {
+        const int64_t blocks = hnr_cdiv(M, 64);                     // >= 8 rows per warp before the CTA-level reduction
+        const int g = (int)(blocks < 4 * HNR_NUM_SMS ? (blocks < 1 ? 1 : blocks) : 4 * HNR_NUM_SMS);
+        linear_bwd_weight_smalln_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(dY, (int)lddy, Y, (int)ldy, A, dW, db, M, (int)N, (int)K, act);
+        HNR_CHECK_LAUNCH("linear_bwd_weight(small N)");
+        return HNR_OK;
+    }
     const int64_t tiles = hnr_cdiv(N, BM) * hnr_cdiv(K, BN);
     int64_t splits = (4 * HNR_NUM_SMS + tiles - 1) / tiles;          // aim at >= 4 CTAs per SM
     int64_t max_splits = hnr_cdiv(M, 256);

@@ -69,6 +69,7 @@ class NeuralPointsRayMarching(nn.Module):
         output["coarse_point_opacity"] = opacity
         output["coarse_is_background"] = background_transmission
         output["ray_mask"] = ray_mask_tensor
+        output["ray_ids"] = None if extras is None else extras.ray_ids       # (R'',) ids of the kept rays (extra key, not in the reference's dict)
         if weight is not None:
             output["weight"] = weight.detach()
             output["blend_weight"] = blend_weight.detach()

@@ -14,6 +14,7 @@ from ._lib import check, i64_array, lib, ptr, ptr_array, require_cuda, stream
 
 ACT_NONE, ACT_LRELU, ACT_SIGMOID, ACT_COLOR = 0, 1, 2, 3
 X0_W, E_W, HID, X5_W, AUX_C = 284, 7, 256, 280, 45
+X0_GRAD_W = 224      # leading columns of the layer-0 input that carry a gradient: [emb 32 | sin/cos(2^j emb) 192]
 
 # counts kernels launched through the C ABI (bench.py reports it as gpu_launches)
 LAUNCHES = 0
@@ -210,10 +211,13 @@ class LinearFn(torch.autograd.Function):
         return (dW, db, d_res, None, None, None, *d_srcs)
 
 
-def linear_backward(W, Y, srcs, mods, dY, act: int, need_src, need_w: bool = True, has_b: bool = True, M: Optional[int] = None):
+def linear_backward(W, Y, srcs, mods, dY, act: int, need_src, need_w: bool = True, has_b: bool = True, M: Optional[int] = None,
+                    k_need: Optional[int] = None):
     """gradients of y = act(concat(srcs) W^T + b) given dY and the saved output Y: ([d_src_i | None], dW | None, db | None).
     Tensor-core kernels (3xTF32: gated data gradient, TMEM-resident weight gradient) for layers with >= 16 outputs and
-    >= 128 rows, exact-fp32 SIMT kernels otherwise."""
+    >= 128 rows, exact-fp32 SIMT kernels otherwise.  `k_need`: only the first k_need input columns of the data gradient are
+    consumed by the caller (the rest of the returned buffer is left unwritten) -- a column slice nobody reads costs a full pass
+    over dY."""
     srcs = [_rows2d(s) for s in srcs]
     nsrc = len(srcs)
     dY, Y = _rows2d(dY), _rows2d(Y)
@@ -231,10 +235,22 @@ def linear_backward(W, Y, srcs, mods, dY, act: int, need_src, need_w: bool = Tru
             # tensor-core data gradient: dX = (dY * act'(Y)) . W in column slices of <= 256, then views per source
             ldx = (K + 3) // 4 * 4                      # 16-byte aligned rows: the consumers of the column views load float4
             dX = torch.empty((M, ldx), device=W.device, dtype=torch.float32)
+            kn = K if k_need is None else min(K, int(k_need))
+            Wc = _f32c(W)
+            narrow_ok = N in (128, 256) and dY.stride(0) % 4 == 0 and Y.stride(0) % 4 == 0 and dY.data_ptr() % 16 == 0 and Y.data_ptr() % 16 == 0
             for k0, (wpackT, Kpad, Np) in _packed_linear_T(W):
+                if k0 >= kn:
+                    continue
+                kout = min(256, kn - k0)
+                if kout <= 8 and narrow_ok:
+                    # a slice of a few columns (the 7 extra inputs of block3): HBM-bound SIMT kernel, one read of dY / Y
+                    with _launch(name=f"linear_bwd_data_narrow[{M}x{N}x{kout}]" if TIMERS is not None else None):
+                        check(lib().hnr_linear_bwd_data_narrow(ptr(dY), dY.stride(0), ptr(Y), Y.stride(0), act, ptr(Wc), Wc.stride(0), k0, kout,
+                                                               ptr(dX[:, k0:]), ldx, M, N, stream()), "linear_bwd_data_narrow")
+                    continue
                 with _launch(name=f"linear_tc_bwd_data[{M}x{N}x{K}]" if TIMERS is not None else None):
                     check(lib().hnr_linear_tc_bwd_data(ptr(dY), dY.stride(0), ptr(Y), Y.stride(0), act, ptr(wpackT), Kpad, Np,
-                                                       ptr(dX[:, k0:]), ldx, M, N, min(256, K - k0), stream()), "linear_tc_bwd_data")
+                                                       ptr(dX[:, k0:]), ldx, M, N, kout, stream()), "linear_tc_bwd_data")
             outs, off = [], 0
             for i in range(nsrc):
                 outs.append(dX[:, off:off + ks[i]] if need_src[i] else None)
@@ -450,7 +466,9 @@ class NbrMlpFusedFn(torch.autograd.Function):
         (dH3,), dW4, db4 = linear_backward(W4, H[3], [H[2]], (), dH4, ACT_LRELU, [True])
         (dH2, dE), dW3, db3 = linear_backward(W3, H[2], [H[1], E], (), dH3, ACT_LRELU, [True, True])
         (dH1,), dW2, db2 = linear_backward(W2, H[1], [H[0]], (), dH2, ACT_LRELU, [True])
-        (dX0,), dW1, db1 = linear_backward(W1, H[0], [X0], (), dH1, ACT_LRELU, [True])
+        # of layer 0's 284 inputs only [emb 32 | PE(emb) 192] carry a gradient (the 60 distance encodings depend on positions,
+        # xyz_grad = 0; nbr_features_bwd reads columns < 224 only): one 224-column slice instead of 256 + 28
+        (dX0,), dW1, db1 = linear_backward(W1, H[0], [X0], (), dH1, ACT_LRELU, [True], k_need=X0_GRAD_W)
         ne, nc, nd = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
         d_emb = torch.zeros(ctx.shapes[0], device=emb.device, dtype=torch.float32) if ne else None
         d_col = torch.zeros(ctx.shapes[1], device=emb.device, dtype=torch.float32) if nc else None

@@ -187,13 +187,20 @@ class PointAggregator(nn.Module):
             return None
         if not (opt.ray_points and opt.drop_patch and opt.drop_disturb_range == 0):
             raise NotImplementedError("only the deterministic patch drop (ray_points=1, drop_patch=1, drop_disturb_range=0) is implemented")
-        toks = opt.dilation_setup.split('_')
-        pos = drop_patch_rays(int(toks[1]), int(toks[0]), opt.drop_ratio)
-        if len(pos) and pos.max() >= R:
-            raise IndexError(f"index {int(pos.max())} is out of bounds for axis 0 with size {R}")   # what numpy raises in the reference
-        dropped = torch.zeros(R, dtype=torch.bool, device=vlist.device)
-        dropped[torch.from_numpy(pos).to(vlist.device)] = True
-        return (~dropped[(vlist.long() // SR)]).to(torch.uint8).contiguous()
+        # the dropped-ray flags depend on the options only: built once per (R, setup, ratio, device).  Uploading them every step is
+        # a pageable host-to-device copy, i.e. a host stall until the whole forward so far has executed (1.8 ms in the step trace)
+        key = (R, opt.dilation_setup, float(opt.drop_ratio), str(vlist.device))
+        cache = self.__dict__.setdefault("_keep_cache", {})
+        keep_ray = cache.get(key)
+        if keep_ray is None:
+            toks = opt.dilation_setup.split('_')
+            pos = drop_patch_rays(int(toks[1]), int(toks[0]), opt.drop_ratio)
+            if len(pos) and pos.max() >= R:
+                raise IndexError(f"index {int(pos.max())} is out of bounds for axis 0 with size {R}")   # what numpy raises in the reference
+            flags = np.ones(R, dtype=np.uint8)
+            flags[pos] = 0
+            keep_ray = cache[key] = torch.from_numpy(flags).to(vlist.device)
+        return keep_ray.index_select(0, vlist.long() // SR).contiguous()
 
     def _run(self, tables, pidx, mask, loc_pers, loc_w, raydirs, cam, R, SR, levels, xy, delta, vlist=None):
         """tables = (xyz (N,3), xyz_pers|None, emb (N,32), color (N,3), dir (N,3), conf (N,)).
@@ -415,7 +422,7 @@ class PointAggregator(nn.Module):
         levels = xy = delta = None
         if opt.use_nearest > 0:
             levels = self.feature_pyramid(img_n)
-            w2c = torch.linalg.inv(c2w_n.reshape(-1, 4, 4).float())
+            w2c = torch.linalg.inv_ex(c2w_n.reshape(-1, 4, 4).float())[0]        # inv() reads its info flag back (host sync)
             xy, delta = ops.project_views(loc_w, w2c, intrinsic_n.reshape(3, 3), campos.reshape(-1)[:3], campos_n.reshape(-1, 3))
         decoded, valid, weight, confc = self._run(tables, sample_pidx.reshape(S, K), None, sample_loc.reshape(S, 3), loc_w,
                                                   sample_ray_dirs.reshape(S, 3), cam, R, SR, levels, xy, delta,

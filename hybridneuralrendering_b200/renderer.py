@@ -44,8 +44,10 @@ def training_loss(output: Dict[str, torch.Tensor], gt_image: torch.Tensor, zero_
     """MSE on ray-masked colours (+1e-6) scaled by frame_weight, plus the zero-one regulariser on
     conf_coefficient (reference models/base_rendering_model.py:1114-1118, :1198-1240).
     `output` is the un-filled output of NeuralPointsRayMarching (R'' kept rays)."""
-    mask = output["ray_mask"][0] > 0
-    gt = gt_image[:, mask]
+    if output.get("ray_ids") is not None:
+        gt = gt_image.index_select(1, output["ray_ids"].long())       # kept-ray list from the query: no nonzero(), no host sync
+    else:
+        gt = gt_image[:, output["ray_mask"][0] > 0]
     loss = (torch.nn.functional.mse_loss(output["coarse_raycolor"], gt) + 1e-6) * frame_weight
     if "conf_coefficient" in output and zero_one_weight > 0:
         v = output["conf_coefficient"].clamp(1e-3, 1 - 1e-3)

@@ -125,6 +125,10 @@ int hnr_linear_bwd_data(const float* dY, int64_t lddy, const float* Y, int64_t l
 int hnr_linear_bwd_weight(const float* dY, int64_t lddy, const float* Y, int64_t ldy, const float* const* a_ptr, const int64_t* a_ld,
                           const int64_t* a_k, const int64_t* a_mod, float* dW, float* db, int64_t M, int64_t N, int64_t K, int act,
                           void* stream);
+/* data gradient of a narrow column slice [k0, k0+kn), kn <= 8, of a layer with N = 128 or 256 outputs: dA (M, kn) =
+ * (dY * act'(Y)) (M,N) . W[:, k0:k0+kn]; W (N, ldw) row-major.  HBM-bound (one read of dY and Y); dY / Y rows 16-byte aligned. */
+int hnr_linear_bwd_data_narrow(const float* dY, int64_t lddy, const float* Y, int64_t ldy, int act, const float* W, int64_t ldw,
+                               int64_t k0, int64_t kn, float* dA, int64_t ldda, int64_t M, int64_t N, void* stream);
 
 /* one dense layer on tcgen05 tensor cores (3xTF32, fp32 accuracy): same semantics as hnr_linear_fwd; wpack is
  * the host-packed TF32 hi/lo image of W zero-padded to (Npad % 16 == 0 <= 256, Kp % 8 == 0) (csrc/linear_tc.cu) */

@@ -161,7 +161,9 @@ def test_learnable_blur_shipped_shape_vs_oracle():
 
 
 @pytest.mark.parametrize("M,N,ks,act", [(1, 1, (5,), 0), (130, 256, (284,), 1), (257, 256, (256, 7), 1), (300, 64, (45, 128, 3), 1),
-                                         (77, 1, (64,), 2), (64, 3, (45, 83), 3), (1000, 45, (45,), 0), (0, 8, (4,), 1)])
+                                         (77, 1, (64,), 2), (64, 3, (45, 83), 3), (1000, 45, (45,), 0), (0, 8, (4,), 1),
+                                         # heads at training sizes: small-N weight-gradient kernel with its grid-stride row loop
+                                         (40003, 1, (64,), 2), (30011, 3, (45, 83), 3), (5000, 4, (100, 20, 8), 1)])
 def test_linear_fwd_bwd_vs_torch(M, N, ks, act):
     from hybridneuralrendering_b200 import ops
     rng = np.random.default_rng(M + N)
@@ -217,6 +219,24 @@ def test_linear_strided_sources_and_shared_block():
     W2 = T((rng.standard_normal((3, 128)) * 0.1).astype(np.float32)).cuda()
     y2 = ops.linear([gi, gv], W2, None, 0)
     assert_close(y2, g.double() @ W2.cpu().double().t(), 1e-5, 1e-5)
+
+
+def test_linear_backward_needed_columns_and_narrow_slice():
+    """data gradient restricted to the leading columns the caller consumes (layer 0 of the per-neighbour MLP: 224 of 284) and the
+    narrow-slice kernel (block3's 7 extra inputs) vs fp64"""
+    from hybridneuralrendering_b200 import ops
+    rng = np.random.default_rng(3)
+    M, N = 3000, 256
+    for K, k_need in ((284, 224), (263, None)):
+        X = T(rng.standard_normal((M, K)).astype(np.float32))
+        W = T((rng.standard_normal((N, K)) * 0.1).astype(np.float32))
+        Y = torch.nn.functional.leaky_relu(X.double() @ W.double().t(), 0.01)
+        dY = T(rng.standard_normal((M, N)).astype(np.float32))
+        ref = (dY.double() * torch.where(Y > 0, 1.0, 0.01)) @ W.double()
+        (dX,), dW, db = ops.linear_backward(W.cuda(), Y.float().cuda(), [X.cuda()], (), dY.cuda(), ops.ACT_LRELU, [True], k_need=k_need)
+        kk = k_need or K
+        assert_close(dX[:, :kk], ref[:, :kk], 1e-4, grad_atol(ref, 1e-5))
+        assert_close(dW, (dY.double() * torch.where(Y > 0, 1.0, 0.01)).t() @ X.double(), 1e-4, 1e-3)
 
 
 def test_fused_adam_matches_torch_adam_dense_semantics():
