@@ -247,6 +247,7 @@ __global__ void __launch_bounds__(256) linear_fwd_smalln_kernel(Cat3 A, const fl
 // reduction per CTA, then one global atomic per (n,k) per CTA.  HBM-bound: reads M x K once (the 64x64 GEMM tile of
 // linear_bwd_weight_kernel wastes 60 of 64 output rows: 514 us for the 64->1 blend-weight head at M = 602k, trace of round 1).
 constexpr int SMALLN_BWD_MAXK = 128;
+constexpr int SMALLN_ROWS = 4;      // rows per warp iteration: their loads are issued together (a row is only K <= 128 floats)
 __global__ void __launch_bounds__(256) linear_bwd_weight_smalln_kernel(const float* __restrict__ dY, int lddy, const float* __restrict__ Y,
                                                                         int ldy, Cat3 A, float* __restrict__ dW, float* __restrict__ db,
                                                                         int64_t M, int N, int K, int act) {
@@ -258,29 +259,36 @@ __global__ void __launch_bounds__(256) linear_bwd_weight_smalln_kernel(const flo
     const int b1 = A.k[0], b2 = A.k[0] + A.k[1];
     float acc[4][4] = {};
     float bs[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int64_t m = warp0; m < M; m += nwarps) {
-        float dp = 0.f;
-        if (lane < N) {
-            dp = dY[m * lddy + lane];
-            if (act != HNR_ACT_NONE) dp *= act_grad_from_out(Y[m * ldy + lane], act);
-        }
-        float d[4];
+    for (int64_t mb = warp0 * SMALLN_ROWS; mb < M; mb += nwarps * SMALLN_ROWS) {
+        float dp[SMALLN_ROWS], x[SMALLN_ROWS][4];
 #pragma unroll
-        for (int n = 0; n < 4; ++n) d[n] = __shfl_sync(0xffffffffu, dp, n);
-        const float* r0 = A.p[0] + (A.mod[0] > 0 ? m % A.mod[0] : m) * A.ld[0];
-        const float* r1 = A.k[1] > 0 ? A.p[1] + (A.mod[1] > 0 ? m % A.mod[1] : m) * A.ld[1] : nullptr;
-        const float* r2 = A.k[2] > 0 ? A.p[2] + (A.mod[2] > 0 ? m % A.mod[2] : m) * A.ld[2] : nullptr;
+        for (int r = 0; r < SMALLN_ROWS; ++r) {
+            const int64_t m = mb + r;
+            dp[r] = 0.f;
+            if (m < M && lane < N) {
+                dp[r] = dY[m * lddy + lane];
+                if (act != HNR_ACT_NONE) dp[r] *= act_grad_from_out(Y[m * ldy + lane], act);
+            }
+            const int64_t mc = m < M ? m : M - 1;       // clamped row: loads stay in bounds, dp = 0 removes its contribution
+            const float* r0 = A.p[0] + (A.mod[0] > 0 ? mc % A.mod[0] : mc) * A.ld[0];
+            const float* r1 = A.k[1] > 0 ? A.p[1] + (A.mod[1] > 0 ? mc % A.mod[1] : mc) * A.ld[1] : nullptr;
+            const float* r2 = A.k[2] > 0 ? A.p[2] + (A.mod[2] > 0 ? mc % A.mod[2] : mc) * A.ld[2] : nullptr;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int k = lane + 32 * j;
-            if (k < K) {
-                const float x = k < b1 ? r0[k] : (k < b2 ? r1[k - b1] : r2[k - b2]);
-#pragma unroll
-                for (int n = 0; n < 4; ++n) acc[n][j] = fmaf(d[n], x, acc[n][j]);
+            for (int j = 0; j < 4; ++j) {
+                const int k = lane + 32 * j;
+                x[r][j] = k < K ? (k < b1 ? r0[k] : (k < b2 ? r1[k - b1] : r2[k - b2])) : 0.f;
             }
         }
 #pragma unroll
-        for (int n = 0; n < 4; ++n) bs[n] += d[n];
+        for (int r = 0; r < SMALLN_ROWS; ++r) {
+#pragma unroll
+            for (int n = 0; n < 4; ++n) {
+                const float d = __shfl_sync(0xffffffffu, dp[r], n);
+                bs[n] += d;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[n][j] = fmaf(d, x[r][j], acc[n][j]);
+            }
+        }
     }
 #pragma unroll
     for (int n = 0; n < 4; ++n) {
@@ -303,29 +311,32 @@ __global__ void __launch_bounds__(256) linear_bwd_weight_smalln_kernel(const flo
 // reading and converting dY, not the MMAs.  Warp per row, the W slice lives in registers, float4 row loads, butterfly reduction:
 // HBM-bound, one read of dY and Y.
 template <int NV>
-__global__ void __launch_bounds__(256) linear_bwd_data_narrow_kernel(const float* __restrict__ dY, int lddy, const float* __restrict__ Y,
+__global__ void __launch_bounds__(256, 4) linear_bwd_data_narrow_kernel(const float* __restrict__ dY, int lddy, const float* __restrict__ Y,
                                                                       int ldy, int act, const float* __restrict__ W, int ldw, int k0, int KN,
                                                                       float* __restrict__ dA, int ldda, int64_t M) {
+    // lane owns reduction columns n = 128*v + 4*lane + c  (v < NV, c < 4): conflict-free float4 loads of the rows and of the W slice
+    __shared__ float4 sw[8][NV][32];
+    for (int i = threadIdx.x; i < 8 * NV * 32; i += blockDim.x) {
+        const int k = i / (NV * 32), v = (i / 32) % NV, l = i % 32;
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < KN) {
+            const float* wp = W + (int64_t)(128 * v + 4 * l) * ldw + k0 + k;
+            t = make_float4(wp[0], wp[ldw], wp[2 * (int64_t)ldw], wp[3 * (int64_t)ldw]);
+        }
+        sw[k][v][l] = t;
+    }
+    __syncthreads();
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    // lane owns reduction columns n = 128*v + 4*lane + c  (v < NV, c < 4): conflict-free float4 row loads
-    float w[8][NV * 4];
-#pragma unroll
-    for (int k = 0; k < 8; ++k)
-#pragma unroll
-        for (int v = 0; v < NV; ++v)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) w[k][v * 4 + c] = k < KN ? W[(int64_t)(128 * v + 4 * lane + c) * ldw + k0 + k] : 0.f;
     for (int64_t m = warp0; m < M; m += nwarps) {
-        float g[NV * 4];
+        float4 g[NV];
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
-            const float4 d4 = *reinterpret_cast<const float4*>(dY + m * lddy + 128 * v + 4 * lane);
-            g[v * 4 + 0] = d4.x; g[v * 4 + 1] = d4.y; g[v * 4 + 2] = d4.z; g[v * 4 + 3] = d4.w;
+            g[v] = *reinterpret_cast<const float4*>(dY + m * lddy + 128 * v + 4 * lane);
             if (act != HNR_ACT_NONE) {
                 const float4 y4 = *reinterpret_cast<const float4*>(Y + m * ldy + 128 * v + 4 * lane);
-                g[v * 4 + 0] *= act_grad_from_out(y4.x, act); g[v * 4 + 1] *= act_grad_from_out(y4.y, act);
-                g[v * 4 + 2] *= act_grad_from_out(y4.z, act); g[v * 4 + 3] *= act_grad_from_out(y4.w, act);
+                g[v].x *= act_grad_from_out(y4.x, act); g[v].y *= act_grad_from_out(y4.y, act);
+                g[v].z *= act_grad_from_out(y4.z, act); g[v].w *= act_grad_from_out(y4.w, act);
             }
         }
         float out = 0.f;
@@ -333,7 +344,10 @@ __global__ void __launch_bounds__(256) linear_bwd_data_narrow_kernel(const float
         for (int k = 0; k < 8; ++k) {
             float a = 0.f;
 #pragma unroll
-            for (int i = 0; i < NV * 4; ++i) a = fmaf(g[i], w[k][i], a);
+            for (int v = 0; v < NV; ++v) {
+                const float4 w4 = sw[k][v][lane];
+                a = fmaf(g[v].x, w4.x, a); a = fmaf(g[v].y, w4.y, a); a = fmaf(g[v].z, w4.z, a); a = fmaf(g[v].w, w4.w, a);
+            }
             a = warp_sum(a);
             if (lane == k) out = a;
         }
@@ -403,8 +417,8 @@ extern "C" int hnr_linear_bwd_weight(const float* dY, int64_t lddy, const float*
     Cat3 A;
     for (int i = 0; i < 3; ++i) { A.p[i] = a_ptr[i]; A.ld[i] = (int)a_ld[i]; A.k[i] = (int)a_k[i]; A.mod[i] = a_mod ? a_mod[i] : 0; }
     if (N <= 4 && K <= SMALLN_BWD_MAXK) {
-        const int64_t blocks = hnr_cdiv(M, 64);                     // >= 8 rows per warp before the CTA-level reduction
-        const int g = (int)(blocks < 4 * HNR_NUM_SMS ? (blocks < 1 ? 1 : blocks) : 4 * HNR_NUM_SMS);
+        const int64_t blocks = hnr_cdiv(M, 8 * 2 * SMALLN_ROWS);    // >= 2 iterations per warp before the CTA-level reduction
+        const int g = (int)(blocks < 6 * HNR_NUM_SMS ? (blocks < 1 ? 1 : blocks) : 6 * HNR_NUM_SMS);
         linear_bwd_weight_smalln_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(dY, (int)lddy, Y, (int)ldy, A, dW, db, M, (int)N, (int)K, act);
         HNR_CHECK_LAUNCH("linear_bwd_weight(small N)");
         return HNR_OK;

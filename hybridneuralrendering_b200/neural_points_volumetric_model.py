@@ -45,15 +45,19 @@ class NeuralPointsRayMarching(nn.Module):
         nf = self.near_far
         inputs = {"pixel_idx": pixel_idx, "camrotc2w": camrotc2w, "campos": campos, "near": near, "far": far, "h": h, "w": w,
                   "intrinsic": intrinsic, "raydir": raydir}
-        sample_pidx, sample_loc, sample_loc_w, sample_ray_dirs, ray_mask_tensor, vsize, extras = self.neural_points.query(
-            inputs, near=None if nf is None else nf[0], far=None if nf is None else nf[1])
         if getattr(opt, "dynamic_nearest", 0):
             opt.use_nearest = c2w_nearest.shape[1]
         V = int(opt.use_nearest)
+        # everything that does not depend on the query is issued BEFORE it: the query ends with the one device->host read-back of a
+        # forward, and whatever the host still has to launch after that read-back runs with the GPU idle
+        self.aggregator.prepack()
+        views = self.aggregator.prepare_views(images_nearest, c2w_nearest[0, :V]) if V > 0 else None
+        sample_pidx, sample_loc, sample_loc_w, sample_ray_dirs, ray_mask_tensor, vsize, extras = self.neural_points.query(
+            inputs, near=None if nf is None else nf[0], far=None if nf is None else nf[1])
         decoded, ray_valid, weight, conf_coefficient = self.aggregator.forward_fused(
             self.neural_points, sample_pidx, sample_loc, sample_loc_w, sample_ray_dirs, campos, camrotc2w, extras=extras,
             img_n=images_nearest, c2w_n=None if V == 0 else c2w_nearest[0, :V], intrinsic_n=None if V == 0 else intrinsic_nearest[0],
-            campos_n=None if V == 0 else campos_nearest[0, :V])
+            campos_n=None if V == 0 else campos_nearest[0, :V], views=views)
         output["blur_predictor"] = self.aggregator.learn_blur_kernel_block if getattr(opt, "is_train", False) else None
         keep_w = not ((opt.sparse_loss_weight <= 0) and ("conf_coefficient" not in opt.zero_one_loss_items) and opt.prob == 0)
         if not keep_w:

@@ -307,7 +307,7 @@ class PointAggregator(nn.Module):
             am = self.aux_merge_weight_block
             with ops.tag("sample_mlp"):
                 if fused_t:
-                    c0 = list(range(45, 173)) + list(range(45)) + [173, 174, 175]        # kernel source order [g | aux | dview]
+                    c0 = self._AM_COLS0                                                  # kernel source order [g | aux | dview]
                     pc = chain.packed_chain(self, "am_t", [am[0], am[2], am[4]], [ACT_LRELU] * 3, 176, cols0=c0, weight_scale=TS)
                     sig = chain.chain_train(pc, [am[0], am[2], am[4]], [ACT_LRELU] * 3, [g, aux.view(V * Nv, 45), dv], M=V * Nv,
                                             mods=(Nv, 0, 0), head=(am[6], ACT_SIGMOID), cols0=c0)[1]
@@ -337,6 +337,31 @@ class PointAggregator(nn.Module):
                 m = ops.linear([m], cm[4].weight, cm[4].bias, ACT_NONE, res=gi)
             rgb = ops.linear([m, gv], self.color_final_block[0].weight, self.color_final_block[0].bias, ACT_COLOR)
         return torch.cat([sigma, rgb], dim=-1)
+
+    _AM_COLS0 = list(range(45, 173)) + list(range(45)) + [173, 174, 175]        # blend-weight net, kernel source order [g | aux | dview]
+
+    def prepack(self):
+        """Re-pack the tensor-core weight images of a graph-recording forward NOW (they are cached by parameter version, so the
+        forward then finds them ready).  The conductor calls this BEFORE the query: the ~150 small packing launches that follow
+        every optimiser step are then issued while the GPU still executes the previous step's backward, instead of after the
+        query's read-back, where the GPU idles until the host has caught up."""
+        if not (torch.is_grad_enabled() and self.mlp_engine == "tc" and self.fused_train_forward and int(self.opt.K) == 8):
+            return
+        from . import chain
+        TS = chain.TRAIN_WEIGHT_SCALE
+        self._packed_weights()
+        cf, am, cm = self.color_feature_branch, self.aux_merge_weight_block, self.color_mixup_block
+        chain.packed_chain(self, "cf_t", [cf[0], cf[2], cf[4]], [ACT_LRELU] * 3, X5_W, weight_scale=TS)
+        if int(self.opt.use_nearest) > 0:
+            chain.packed_chain(self, "am_t", [am[0], am[2], am[4]], [ACT_LRELU] * 3, 176, cols0=self._AM_COLS0, weight_scale=TS)
+        chain.packed_chain(self, "cm_t", [cm[0], cm[2], cm[4]], [ACT_LRELU, ACT_LRELU, ACT_NONE], 90, weight_scale=TS)
+
+    def prepare_views(self, img_n, c2w_n):
+        """query-independent part of the image branch (feature pyramid I1, world->camera matrices of the reference views),
+        so that the conductor can issue it before the query's read-back.  -> (levels, w2c)"""
+        levels = self.feature_pyramid(img_n)
+        w2c = torch.linalg.inv_ex(c2w_n.reshape(-1, 4, 4).float())[0]        # inv() reads its info flag back (host sync)
+        return levels, w2c
 
     def _packed_weights(self):
         """TF32 hi/lo images of block1/block3 for the tensor-core kernel, re-packed when a weight changes"""
@@ -405,7 +430,7 @@ class PointAggregator(nn.Module):
 
     # ------------------------------------------------------------------ fused forward (point tables + indices)
     def forward_fused(self, points, sample_pidx, sample_loc, sample_loc_w, sample_ray_dirs, campos, camrotc2w, extras=None, img_n=None,
-                      c2w_n=None, intrinsic_n=None, campos_n=None):
+                      c2w_n=None, intrinsic_n=None, campos_n=None, views=None):
         """points: NeuralPoints.  sample_* as returned by NeuralPoints.query.  Projection into the
         reference views (P1) runs in-kernel.  Returns decoded (1,R,SR,4), ray_valid, weight, conf_coefficient."""
         opt = self.opt
@@ -421,8 +446,7 @@ class PointAggregator(nn.Module):
         loc_w = sample_loc_w.reshape(S, 3)
         levels = xy = delta = None
         if opt.use_nearest > 0:
-            levels = self.feature_pyramid(img_n)
-            w2c = torch.linalg.inv_ex(c2w_n.reshape(-1, 4, 4).float())[0]        # inv() reads its info flag back (host sync)
+            levels, w2c = views if views is not None else self.prepare_views(img_n, c2w_n)
             xy, delta = ops.project_views(loc_w, w2c, intrinsic_n.reshape(3, 3), campos.reshape(-1)[:3], campos_n.reshape(-1, 3))
         decoded, valid, weight, confc = self._run(tables, sample_pidx.reshape(S, K), None, sample_loc.reshape(S, 3), loc_w,
                                                   sample_ray_dirs.reshape(S, 3), cam, R, SR, levels, xy, delta,
