@@ -285,6 +285,8 @@ def main():
     # roofline of the dominant kernel: the per-neighbour MLP (4 dense layers, 542,720 FLOP per neighbour row)
     from hybridneuralrendering_b200 import profiling
     roof = profiling.dominant_kernel_roofline(net, resident, CHUNK, peaks())
+    # whole-step roofline as SURVEY.md 8(d) defines it (sum over stages of max(bytes/HBM, FLOPs/tensor peak) / measured time)
+    roof["step"] = profiling.step_roofline(roof["units"], V, H * W, int(opt.z_depth_dim), int(opt.SR), H, W, t_res / args.steps * 1e3, peaks()[0])
 
     line = {"metric": "render Mpix/s", "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": t_res / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -307,6 +309,8 @@ def main():
         tr["ms_fwd_bwd"] = float(tt.item())
         tr["value"] = world * tr["rays"] / (tr["ms_fwd_bwd"] * 1e-3)
         tr["n_gpus"] = world
+        tr["roofline"] = profiling.step_roofline(tr, tr["views"], tr["rays"], 400, 24, 480, 640, tr["ms_fwd_bwd"], peaks()[0], train=True,
+                                                 points=tr["points"])
         tr["gradient_allreduce"] = "NCCL SUM, dense point gradients + coalesced MLP bucket" if world > 1 else "none (1 GPU)"
         line["train"] = tr
         if world == 1:

@@ -212,6 +212,7 @@ template <typename PP> bool cat_ok(PP p, const int64_t* ld, const int64_t* k, in
 // N <= 4 outputs (density / colour heads): a GEMM tile would waste 60 of its 64 columns.  One warp per row: the lanes
 // stride over the concatenated K (coalesced 128-byte reads), W lives in shared memory, warp-shuffle reduction.
 constexpr int SMALLN_MAXK = 512;
+constexpr int FWD_ROWS = 4;
 __global__ void __launch_bounds__(256) linear_fwd_smalln_kernel(Cat3 A, const float* __restrict__ W, const float* __restrict__ bias,
                                                                  const float* __restrict__ res, int ldres, float* __restrict__ Y, int ldy,
                                                                  int64_t M, int N, int K, int act) {
@@ -221,23 +222,40 @@ __global__ void __launch_bounds__(256) linear_fwd_smalln_kernel(Cat3 A, const fl
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int b1 = A.k[0], b2 = A.k[0] + A.k[1];
-    for (int64_t m = warp0; m < M; m += nwarps) {
-        const float* r0 = A.p[0] + (A.mod[0] > 0 ? m % A.mod[0] : m) * A.ld[0];
-        const float* r1 = A.k[1] > 0 ? A.p[1] + (A.mod[1] > 0 ? m % A.mod[1] : m) * A.ld[1] : nullptr;
-        const float* r2 = A.k[2] > 0 ? A.p[2] + (A.mod[2] > 0 ? m % A.mod[2] : m) * A.ld[2] : nullptr;
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    // FWD_ROWS rows per warp iteration: their loads are independent and issued together (a row is only K floats, i.e. a handful of
+    // 128-byte lines per lane pass -- one row at a time leaves the warp waiting on 4 loads); per-row arithmetic order is unchanged
+    for (int64_t mb = warp0 * FWD_ROWS; mb < M; mb += nwarps * FWD_ROWS) {
+        const float *r0[FWD_ROWS], *r1[FWD_ROWS], *r2[FWD_ROWS];
+#pragma unroll
+        for (int r = 0; r < FWD_ROWS; ++r) {
+            const int64_t m = mb + r < M ? mb + r : M - 1;      // clamped: loads stay in bounds, the row is not stored
+            r0[r] = A.p[0] + (A.mod[0] > 0 ? m % A.mod[0] : m) * A.ld[0];
+            r1[r] = A.k[1] > 0 ? A.p[1] + (A.mod[1] > 0 ? m % A.mod[1] : m) * A.ld[1] : nullptr;
+            r2[r] = A.k[2] > 0 ? A.p[2] + (A.mod[2] > 0 ? m % A.mod[2] : m) * A.ld[2] : nullptr;
+        }
+        float acc[FWD_ROWS][4] = {};
         for (int k = lane; k < K; k += 32) {
-            const float x = k < b1 ? r0[k] : (k < b2 ? r1[k - b1] : r2[k - b2]);
+            float x[FWD_ROWS];
+#pragma unroll
+            for (int r = 0; r < FWD_ROWS; ++r) x[r] = k < b1 ? r0[r][k] : (k < b2 ? r1[r][k - b1] : r2[r][k - b2]);
 #pragma unroll
             for (int n = 0; n < 4; ++n)
-                if (n < N) acc[n] = fmaf(x, Ws[n * K + k], acc[n]);
+                if (n < N) {
+                    const float w = Ws[n * K + k];
+#pragma unroll
+                    for (int r = 0; r < FWD_ROWS; ++r) acc[r][n] = fmaf(x[r], w, acc[r][n]);
+                }
         }
 #pragma unroll
-        for (int n = 0; n < 4; ++n) acc[n] = warp_sum(acc[n]);
-        if (lane < N) {
-            float y = apply_act((lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3]) + (bias ? bias[lane] : 0.f), act);
-            if (res) y += res[m * ldres + lane];
-            Y[m * ldy + lane] = y;
+        for (int r = 0; r < FWD_ROWS; ++r) {
+#pragma unroll
+            for (int n = 0; n < 4; ++n) acc[r][n] = warp_sum(acc[r][n]);
+            const int64_t m = mb + r;
+            if (m < M && lane < N) {
+                float y = apply_act((lane == 0 ? acc[r][0] : lane == 1 ? acc[r][1] : lane == 2 ? acc[r][2] : acc[r][3]) + (bias ? bias[lane] : 0.f), act);
+                if (res) y += res[m * ldres + lane];
+                Y[m * ldy + lane] = y;
+            }
         }
     }
 }
@@ -383,7 +401,7 @@ extern "C" int hnr_linear_fwd(const float* const* a_ptr, const int64_t* a_ld, co
     for (int i = 0; i < 3; ++i) { A.p[i] = a_ptr[i]; A.ld[i] = (int)a_ld[i]; A.k[i] = (int)a_k[i]; A.mod[i] = a_mod ? a_mod[i] : 0; }
     HNR_CHECK_ARG(!(res && act != HNR_ACT_NONE), "linear_fwd: residual only with act=none");
     if (N <= 4 && K <= SMALLN_MAXK) {
-        const int64_t blocks = hnr_cdiv(M, 8);
+        const int64_t blocks = hnr_cdiv(M, 8 * FWD_ROWS);
         const int g = (int)(blocks < 16 * HNR_NUM_SMS ? blocks : 16 * HNR_NUM_SMS);
         linear_fwd_smalln_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(A, W, bias, res, (int)ldres, Y, (int)ldy, M, (int)N, (int)K, act);
         HNR_CHECK_LAUNCH("linear_fwd(small N)");

@@ -23,6 +23,7 @@
 // cell = (int)floorf((p - origin) / cell) with IEEE division; d2 = fma(z,z, fma(x,x, y*y)) as in the
 // sm_100a SASS of the reference source (oracle/build_ref_query_cubin.py); position = campos +
 // (dir * t) with separate rounding (two torch ops in the reference).
+#include <stdlib.h>
 #include "common.cuh"
 
 #include "hnr.h"
@@ -259,36 +260,74 @@ __device__ __forceinline__ unsigned long long shfl_up_u64(unsigned long long v, 
     return __shfl_up_sync(0xffffffffu, v, d);
 }
 
+// merge one batch of up to 32 candidate keys (one per lane, KEY_EMPTY = none) into the sorted top-K held by lanes 0..K-1
+__device__ __forceinline__ void knn_merge(unsigned long long key, int K, int lane, unsigned long long& topk, int& kid) {
+    unsigned cand = __ballot_sync(0xffffffffu, key != KEY_EMPTY);
+    kid += __popc(cand);
+    unsigned long long kth = shfl_u64(topk, K - 1);
+    unsigned m = __ballot_sync(0xffffffffu, key < kth);
+    while (m) {
+        int src = __ffs(m) - 1;
+        m &= m - 1;
+        unsigned long long x = shfl_u64(key, src);
+        kth = shfl_u64(topk, K - 1);
+        if (x < kth) {                         // warp-uniform
+            unsigned long long prev = shfl_up_u64(topk, 1);
+            if (lane == 0) prev = 0ull;
+            topk = (x < prev) ? prev : ((x < topk) ? x : topk);
+        }
+    }
+}
+
+__device__ __forceinline__ unsigned long long knn_key(const float4 p, float sx, float sy, float sz, float r2) {
+    float vx = __fsub_rn(p.x, sx), vy = __fsub_rn(p.y, sy), vz = __fsub_rn(p.z, sz);
+    float d2 = __fmaf_rn(vz, vz, __fmaf_rn(vx, vx, __fmul_rn(vy, vy)));
+    if (r2 == 0.f || d2 <= r2) return ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)__float_as_int(p.w);
+    return KEY_EMPTY;
+}
+
 // process up to 32 candidates of one voxel (lane j < n owns candidate j)
 __device__ __forceinline__ void knn_visit(const float4* __restrict__ pts, int start, int n, float sx, float sy, float sz, float r2,
                                           int K, int lane, unsigned long long& topk, int& kid) {
     for (int b0 = 0; b0 < n; b0 += 32) {
         unsigned long long key = KEY_EMPTY;
-        if (b0 + lane < n) {
-            float4 p = pts[start + b0 + lane];
-            float vx = __fsub_rn(p.x, sx), vy = __fsub_rn(p.y, sy), vz = __fsub_rn(p.z, sz);
-            float d2 = __fmaf_rn(vz, vz, __fmaf_rn(vx, vx, __fmul_rn(vy, vy)));
-            if (r2 == 0.f || d2 <= r2)
-                key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)__float_as_int(p.w);
-        }
-        unsigned cand = __ballot_sync(0xffffffffu, key != KEY_EMPTY);
-        kid += __popc(cand);
-        unsigned long long kth = shfl_u64(topk, K - 1);
-        unsigned m = __ballot_sync(0xffffffffu, key < kth);
-        while (m) {
-            int src = __ffs(m) - 1;
-            m &= m - 1;
-            unsigned long long x = shfl_u64(key, src);
-            kth = shfl_u64(topk, K - 1);
-            if (x < kth) {                         // warp-uniform
-                unsigned long long prev = shfl_up_u64(topk, 1);
-                if (lane == 0) prev = 0ull;
-                topk = (x < prev) ? prev : ((x < topk) ? x : topk);
-            }
-        }
+        if (b0 + lane < n) key = knn_key(pts[start + b0 + lane], sx, sy, sz, r2);
+        knn_merge(key, K, lane, topk, kid);
     }
 }
 
+// The points of up to 32 voxels (lane c holds voxel c's start / count) walked in FULL 32-lane batches: candidate j of the
+// concatenated list belongs to the first voxel whose inclusive count prefix exceeds j (binary search over the lanes with
+// shuffles).  A voxel holds <= P (12..26) points, so the per-voxel walk of knn_visit leaves 20..60 % of the lanes idle and
+// pays one dependent L2 round trip per non-empty voxel; here a sample costs ceil(candidates / 32) round trips.  The result is
+// the same: the top-K is the set of the K smallest (d2, id) keys, ids are unique, and the candidate count `kid` is only
+// looked at after a whole shell.
+__device__ __forceinline__ void knn_visit_cells(const float4* __restrict__ pts, int start, int n, float sx, float sy, float sz, float r2,
+                                                int K, int lane, unsigned long long& topk, int& kid) {
+    int incl = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    const int excl = incl - n;
+    for (int b0 = 0; b0 < total; b0 += 32) {
+        const int j = b0 + lane;
+        int lo = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+            int v = __shfl_sync(0xffffffffu, incl, lo + step - 1);
+            if (v <= j) lo += step;
+        }
+        const int st = __shfl_sync(0xffffffffu, start, lo), ex = __shfl_sync(0xffffffffu, excl, lo);
+        unsigned long long key = KEY_EMPTY;
+        if (j < total) key = knn_key(pts[st + (j - ex)], sx, sy, sz, r2);
+        knn_merge(key, K, lane, topk, kid);
+    }
+}
+
+template <bool BATCHED>
 __global__ void __launch_bounds__(128)
 knn_kernel(const float* __restrict__ sample_loc, const int32_t* __restrict__ nsamp, int64_t R, int SR, int K, hnr_grid_t g,
            const int32_t* __restrict__ cell_start, const float4* __restrict__ pts_sorted, int32_t* __restrict__ pidx,
@@ -322,12 +361,16 @@ knn_kernel(const float* __restrict__ sample_loc, const int32_t* __restrict__ nsa
                         n = min(cell_start[l + 1] - start, g.P);
                     }
                 }
-                unsigned nonempty = __ballot_sync(0xffffffffu, n > 0);
-                while (nonempty) {
-                    int src = __ffs(nonempty) - 1;
-                    nonempty &= nonempty - 1;
-                    int st = __shfl_sync(0xffffffffu, start, src), nn = __shfl_sync(0xffffffffu, n, src);
-                    knn_visit(pts_sorted, st, nn, sx, sy, sz, g.radius2, K, lane, topk, kid);
+                if (BATCHED) {
+                    knn_visit_cells(pts_sorted, start, n, sx, sy, sz, g.radius2, K, lane, topk, kid);
+                } else {
+                    unsigned nonempty = __ballot_sync(0xffffffffu, n > 0);
+                    while (nonempty) {
+                        int src = __ffs(nonempty) - 1;
+                        nonempty &= nonempty - 1;
+                        int st = __shfl_sync(0xffffffffu, start, src), nn = __shfl_sync(0xffffffffu, n, src);
+                        knn_visit(pts_sorted, st, nn, sx, sy, sz, g.radius2, K, lane, topk, kid);
+                    }
                 }
             }
             if (kid >= K) break;
@@ -469,8 +512,13 @@ extern "C" int hnr_query(const float* campos, const float* camrot, const float* 
     if (R == 0) { HNR_CUDA(cudaMemsetAsync(counts_out, 0, 2 * sizeof(int32_t), st)); return HNR_OK; }
     ray_select_kernel<<<(unsigned)hnr_cdiv(R * 32, 256), 256, 0, st>>>(campos, raydir, ts, ts_stride, R, (int)D, (int)SR, *g, occ_bits,
                                                                       sample_loc_full, nsamp);
-    knn_kernel<<<(unsigned)R, 128, 0, st>>>(sample_loc_full, nsamp, R, (int)SR, (int)K, *g, cell_start, (const float4*)pts_sorted,
-                                            pidx_full, nvalid);
+    static const bool knn_per_voxel = getenv("HNR_KNN_PER_VOXEL") != nullptr;      // A/B switch: the first-generation voxel-by-voxel walk
+    if (knn_per_voxel)
+        knn_kernel<false><<<(unsigned)R, 128, 0, st>>>(sample_loc_full, nsamp, R, (int)SR, (int)K, *g, cell_start, (const float4*)pts_sorted,
+                                                       pidx_full, nvalid);
+    else
+        knn_kernel<true><<<(unsigned)R, 128, 0, st>>>(sample_loc_full, nsamp, R, (int)SR, (int)K, *g, cell_start, (const float4*)pts_sorted,
+                                                      pidx_full, nvalid);
     ray_flags_kernel<<<(unsigned)hnr_cdiv(R, 256), 256, 0, st>>>(nvalid, R, keep);
     launch_scan(keep, ray_off, R, scan_scratch, st);
     launch_scan(nvalid, val_off, R, scan_scratch, st);

@@ -78,3 +78,45 @@ def dominant_kernel_roofline(net, frame, chunk_rays: int, peaks_and_kind) -> Dic
             "peak_basis": basis, "launches": nl, "kernel_ms_per_step": ms, "kernel_ms_per_launch": ms / nl if nl else None,
             "share_of_step": ms / total if total else None,
             "units": units, "stage_ms": {k: round(v, 3) for k, v in sorted(t.items())}}
+
+
+def step_roofline(units: Dict[str, int], views: int, rays: int, depth_samples: int, SR: int, height: int, width: int, measured_ms: float,
+                  peaks: Dict[str, float], train: bool = False, points: int = 0) -> Dict:
+    """Roofline time of a whole step as SURVEY.md 8(d) defines it: sum over the stages of max(algorithmic bytes / HBM peak,
+    algorithmic FLOPs / tensor peak); `frac` = that / the measured CUDA-event time of the step.
+
+    Bytes and FLOPs per unit are the table of SURVEY.md 8(d) (compulsory traffic only).  Counts: M = valid neighbour rows,
+    Nv = valid samples, R'' = kept rays (all measured on this run's inputs).  The candidate-point term `16*Cand` of the neighbour
+    search is not counted by the product and is left out, which only LOWERS the roofline time (conservative fraction).
+    Tensor peaks: the fp32-accurate forward runs 3 FP16 MMAs per product (peak = bf16_tflops_sustained / 3), the backward 3 TF32
+    MMAs (TF32 dense = bf16 / 2 -> / 6).  train=True adds the backward rows (FLOPs x2, gather recompute + scatter-add RMW,
+    image-gather scatter, compositing backward, pyramid dgrad/wgrad) and the dense zero-filled point-gradient tables (39*N floats)."""
+    M, Nv, Rk = int(units["valid_neighbours"]), int(units["valid_samples"]), int(units["kept_rays"])
+    V = int(views)
+    hbm = float(peaks["hbm_gbs"]) * 1e9
+    t_fwd = float(peaks["bf16_tflops_sustained"]) / 3.0 * 1e12
+    t_bwd = float(peaks["bf16_tflops_sustained"]) / 6.0 * 1e12
+    nbr_flop = FLOP_PER_NEIGHBOUR * M
+    smp_flop = (154_184 + 39_040 * V) * Nv
+    st = {   # stage: (bytes, fwd flops, bwd flops)
+        "query (ray generation, occupancy mask, sample selection, neighbour search)":
+            (24 * rays + 4 * rays * depth_samples + 16 * Rk * SR + 124 * Nv, 0, 0),
+        "gather + weights": (168 * M + 24 * Nv + 16 * Nv + ((16 * Nv + 168 * M + 2 * 156 * M) if train else 0), 0, 0),
+        "per-neighbour MLP": (0, nbr_flop, 2 * nbr_flop if train else 0),
+        "per-sample MLPs": (0, smp_flop, 2 * smp_flop if train else 0),
+        "image gather": (200 * V * Nv + (2 * 180 * V * Nv if train else 0), 0, 0),
+        "feature pyramid (cuDNN)": ((12 + 10.5) * V * height * width * (3 if train else 1), 0, 0),
+        "compositing": ((21 + 8) * Rk * SR + 16 * Rk + (((21 + 8) * Rk * SR + 32 * Rk + 16 * Rk * SR) if train else 0), 0, 0),
+    }
+    if train and points:
+        st["dense point-gradient tables (zero fill)"] = (39 * 4 * points, 0, 0)
+    rows, total = {}, 0.0
+    for k, (b, f, g) in st.items():
+        ms = max(b / hbm, f / t_fwd + g / t_bwd) * 1e3
+        rows[k] = {"bytes": int(b), "flop": int(f + g), "roofline_ms": round(ms, 4), "bound": "tensor" if f else "hbm"}
+        total += ms
+    return {"definition": "sum over stages of max(bytes / HBM peak, FLOPs / tensor peak) / measured step time (SURVEY.md 8d)",
+            "roofline_ms": total, "measured_ms": measured_ms, "frac": total / measured_ms if measured_ms else None,
+            "hbm_peak_gbs": peaks["hbm_gbs"], "tensor_peak_fwd_tflops": t_fwd / 1e12, "tensor_peak_bwd_tflops": t_bwd / 1e12,
+            "tensor_share_of_roofline": sum(r["roofline_ms"] for r in rows.values() if r["bound"] == "tensor") / total if total else None,
+            "stages": rows}

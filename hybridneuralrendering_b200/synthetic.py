@@ -236,6 +236,20 @@ def room_frame(H: int = 480, W: int = 640, V: int = 8, patch_num: int = 8, patch
     )
 
 
+def frame_scene(seed: int = 31, F: int = 14, H: int = 40, W: int = 56, step: int = 5):
+    """inputs of the frame-producer golden: random uint8 frames, room-like poses, frame numbers 0,5,10,...; every 4th frame is a
+    test frame (not in train_id_list).  Deterministic, regenerated by the tests (only reference OUTPUTS are stored)."""
+    rng = np.random.default_rng(seed)
+    images = rng.integers(0, 256, (F, H, W, 3), dtype=np.uint8)
+    vids = [step * i for i in range(F)]
+    c2w = np.stack([look_at(np.array([2.0 + 0.05 * t, 2.0 + 0.03 * t, 1.4]), np.array([5.4, 2.75 + 0.2 * t, 1.0])) for t in range(F)]).astype(np.float32)
+    s = W / 640.0
+    K = intrinsic_matrix(577.87 * s, 577.87 * s, W / 2.0 - 0.37, H / 2.0 + 0.21).astype(np.float32)
+    train_ids = [v for i, v in enumerate(vids) if i % 4 != 3]
+    test_ids = [v for i, v in enumerate(vids) if i % 4 == 3]
+    return images, c2w, vids, K, train_ids, test_ids
+
+
 # ----------------------------------------------------------------------------------------------
 # config 1: gathered inputs with precomputed (random) neighbours
 # ----------------------------------------------------------------------------------------------

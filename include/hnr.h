@@ -238,6 +238,23 @@ int hnr_blur_learn_bwd(const float* pred, const float* raw, int64_t ld_raw, cons
 int hnr_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                   float weight_decay, int64_t step, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Frame-dict producer on the device: the per-item arithmetic of ScannetFtDataset.__getitem__
+ * (data/scannet_ft_dataset.py:736-976) once the frames are decoded; the frames stay resident in HBM as uint8 (F,H,W,3).
+ *   hnr_frame_rays   pixel grid + get_dtu_raydir (data/data_utils.py:57-71) + gt_image_full[py, px] lookup (:945-957).
+ *                    patches = int32 (patch_num^2, 3) rows {x0, y0, dilation} in patch order (i, j) of the 'dilated' sampler
+ *                    (:917-940; 'patch' mode = one patch with dilation 1, :887-892); NULL = full frame inside `margin`
+ *                    (:941-944).  intrinsic = 9 floats row-major, c2w = 16 floats row-major, both DEVICE pointers.
+ *                    Outputs: pixel_idx (n,2), raydir (n,3), gt_image (n,3) or NULL; n = (patch_num*patch_size)^2 or
+ *                    (width-2*margin)*(height-2*margin).  frame_u8 = the item's own frame (H,W,3), only read for gt_image.
+ *   hnr_frame_views  images_nearest (n_views, frame_bytes) fp32 = bank[view_ids[v]] / 255 (T.ToTensor, :743, :823-826);
+ *                    frame_bytes = H*W*3.
+ * ------------------------------------------------------------------------------------------- */
+int hnr_frame_rays(const int32_t* patches, int64_t patch_num, int64_t patch_size, int64_t width, int64_t height, int64_t margin,
+                   const float* intrinsic, const float* c2w, int dir_norm, const uint8_t* frame_u8, float* pixel_idx, float* raydir,
+                   float* gt_image, void* stream);
+int hnr_frame_views(const uint8_t* bank, const int32_t* view_ids, int64_t n_views, int64_t frame_bytes, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,6 +20,8 @@ sys.path.insert(0, ROOT)
 
 from oracle import ref_import, render_oracle as ro          # noqa: E402
 from hybridneuralrendering_b200 import synthetic as syn      # noqa: E402
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from frame_cases import FRAME_CASES                          # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))
 T = torch.from_numpy
@@ -221,7 +223,59 @@ def learnable_blur_case():
     print("learnable blur ok")
 
 
+def frame_case():
+    """ScannetFtDataset.__getitem__ (data/scannet_ft_dataset.py:736-976), the UNMODIFIED method, called unbound on a namespace that
+    carries the attributes it reads, over a temporary scene directory (lossless PNG payload under the .jpg names the method
+    opens -- PIL detects the format from the content; LANCZOS resize to the same size is the identity)."""
+    import random
+    import tempfile
+    import types
+    from PIL import Image
+    from torchvision import transforms
+    mod = ref_import.import_with_stubs("data.scannet_ft_dataset")
+    images, c2w, vids, K, train_ids, test_ids = syn.frame_scene()
+    F, H, W = images.shape[:3]
+    res = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        os.makedirs(os.path.join(tmp, "scene", "exported", "color"))
+        os.makedirs(os.path.join(tmp, "scene", "exported", "pose"))
+        for i, v in enumerate(vids):
+            with open(os.path.join(tmp, "scene", "exported", "color", f"{v}.jpg"), "wb") as f:
+                Image.fromarray(images[i]).save(f, format="PNG")
+            np.savetxt(os.path.join(tmp, "scene", "exported", "pose", f"{v}.txt"), c2w[i].astype(np.float64), fmt="%.18e")
+        for name, split, idx, over, seed, bg in FRAME_CASES:
+            o = dict(use_frame_weight=0, weight_exp=1.0, dynamic_nearest=0, select_high_quality=0, downweight_blurry_feats=0,
+                     random_sample_size=32, dilation_setup="8_8_1_8")
+            o.update(over)
+            opt = types.SimpleNamespace(**o)
+            ns = types.SimpleNamespace(id_list=train_ids if split == "train" else test_ids, train_id_list=train_ids, data_dir=tmp, scan="scene",
+                                       img_wh=(W, H), transform=transforms.ToTensor(), intrinsic=K.copy(), opt=opt, split=split,
+                                       train_weight_list=None, total_num_image=vids[-1] + 1, step=5, near_far=[0.1, 8.0],
+                                       bg_color=bg, blur_kernels=np.zeros((1, 9, 9), np.float32))
+            random.seed(seed)
+            np.random.seed(seed)
+            item = mod.ScannetFtDataset.__getitem__(ns, idx)
+            for k in ("pixel_idx", "raydir", "gt_image", "images_nearest", "c2w_nearest", "campos_nearest", "camrotc2w_nearest",
+                      "vid_angle_nearest", "c2w", "campos", "camrotc2w", "middle", "near", "far", "bg_color", "intrinsic"):
+                v = item[k]
+                res[f"{name}_{k}"] = v.numpy() if torch.is_tensor(v) else np.asarray(v)
+            res[f"{name}_meta"] = np.array([item["vid"], item["h"], item["w"], opt.use_nearest])
+            res[f"{name}_after"] = np.array([random.random(), np.random.rand()])     # both streams must be left in the same state
+            # images_nearest is large: keep which frames were chosen (exact match against the scene) instead of the pixels
+            chosen = []
+            for img in res.pop(f"{name}_images_nearest"):
+                hit = [i for i in range(F) if np.array_equal(img, images[i].astype(np.float32) / np.float32(255))]
+                assert len(hit) == 1, hit
+                chosen.append(vids[hit[0]])
+            res[f"{name}_vid_nearest"] = np.array(chosen)
+    np.savez_compressed(os.path.join(OUT, "frame.npz"), **res)
+    print("frame ok", {n: res[f"{n}_vid_nearest"].tolist() for n, *_ in FRAME_CASES})
+
+
 if __name__ == "__main__":
+    if "--only-frame" in sys.argv:
+        frame_case()
+        sys.exit(0)
     if "--only-learnable-blur" in sys.argv:
         learnable_blur_case()
         sys.exit(0)
@@ -232,3 +286,4 @@ if __name__ == "__main__":
     projection_case()
     blur_case()
     learnable_blur_case()
+    frame_case()

@@ -103,3 +103,82 @@ def test_query_oracle_layered_rule_small():
         assert set(canon.tolist()) <= set(range(1, 6)) and (canon >= 0).sum() == 4      # never looks at the far shell
         slots8, canon8, _ = qo.layered_knn(xyz, g, base, 8, [3, 3, 3])
         assert set(range(1, 8)) == set(canon8[canon8 >= 0].tolist())                    # K=8 > 5: walks layer 1 too
+
+
+def test_frame_producer_host_logic_matches_reference_golden():
+    """N4 host side of the PRODUCT (no GPU needed): nearest-view choice and the patch draws reproduce the unmodified reference's
+    choices for the seeded golden cases; both RNG streams are consumed in the reference's order."""
+    import random
+    from frame_cases import FRAME_CASES
+    from hybridneuralrendering_b200 import frame_producer as fp
+    from hybridneuralrendering_b200 import synthetic as syn
+    G = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "frame.npz")))
+    images, c2w, vids, K, train_ids, test_ids = syn.frame_scene()
+    H, W = images.shape[1:3]
+    for name, split, idx, over, seed, bg in FRAME_CASES:
+        random.seed(seed)
+        np.random.seed(seed)
+        vid = (train_ids if split == "train" else test_ids)[idx]
+        V = over["use_nearest"]
+        if over.get("dynamic_nearest"):
+            V = int(np.random.randint(2, 8)) if split == "train" else 4
+        vn = fp.select_nearest_views(train_ids, vid, V, over["find_nearest_mode"], split)
+        assert vn.tolist() == G[f"{name}_vid_nearest"].tolist(), name
+        pix = G[f"{name}_pixel_idx"]
+        m = over["edge_filter"]
+        if over["random_sample"] == "dilated":
+            st = over["dilation_setup"].split("_")
+            PN, PS = int(st[0]), int(st[1])
+            p = fp.draw_dilated_patches(W, H, m, PN, PS, np.arange(float(st[2]), float(st[3]) + 1))
+            for i in range(PN):
+                for j in range(PN):
+                    blk = pix[i * PS:(i + 1) * PS, j * PS:(j + 1) * PS]
+                    x0, y0, d = p[i * PN + j]
+                    assert (blk[0, 0] == (x0, y0)).all() and (blk[1, 1] == (x0 + d, y0 + d)).all(), (name, i, j)
+
+
+def test_frame_producer_item_host_path_with_stubbed_device_ops(monkeypatch):
+    """runs FrameProducer.item on the CPU with the two device entry points replaced by recorders (the real kernels are covered by
+    tests/test_gpu_frame_producer.py): key set, shapes, the patch table handed to the kernel and the RNG state after the item."""
+    import random
+    from frame_cases import FRAME_CASES
+    from hybridneuralrendering_b200 import frame_producer as fp
+    from hybridneuralrendering_b200 import synthetic as syn
+    G = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "frame.npz")))
+    images, c2w, vids, K, train_ids, test_ids = syn.frame_scene()
+    H, W = images.shape[1:3]
+    seen = {}
+
+    def fake_rays(patches, PN, PS, width, height, margin, intrinsic, c2w_, dir_norm, frame_u8):
+        seen.update(patches=None if patches is None else patches.numpy().copy(), PN=PN, PS=PS, margin=margin, dir_norm=dir_norm)
+        rows, cols = (height - 2 * margin, width - 2 * margin) if patches is None else (PN * PS, PN * PS)
+        return torch.zeros(rows, cols, 2), torch.zeros(rows * cols, 3), torch.zeros(rows * cols, 3)
+
+    monkeypatch.setattr(fp, "frame_rays", fake_rays)
+    monkeypatch.setattr(fp, "frame_views", lambda bank, ids: bank[ids.long()].float() / 255.0)
+    for name, split, idx, over, seed, bg in FRAME_CASES:
+        bank = fp.FrameBank(images, c2w, vids, K, "cpu")
+        prod = fp.FrameProducer(bank, train_ids if split == "train" else test_ids, train_ids, fp.default_opt(**over), split=split,
+                                bg_color=bg, blur_kernels=np.zeros((1, 9, 9), np.float32), total_num_image=vids[-1] + 1)
+        random.seed(seed)
+        np.random.seed(seed)
+        it = prod.item(idx)
+        np.testing.assert_array_equal(np.array([random.random(), np.random.rand()]), G[f"{name}_after"], err_msg=name)
+        assert it["vid_nearest"].tolist() == G[f"{name}_vid_nearest"].tolist()
+        V = len(it["vid_nearest"])
+        assert it["images_nearest"].shape == (1, V, H, W, 3) and it["c2w_nearest"].shape == (1, V, 4, 4)
+        assert it["campos_nearest"].shape == (1, V, 3) and it["campos"].shape == (1, 3) and it["camrotc2w"].shape == (1, 3, 3)
+        np.testing.assert_array_equal(it["c2w_nearest"][0].numpy(), G[f"{name}_c2w_nearest"])
+        np.testing.assert_array_equal(it["bg_color"][0].numpy(), G[f"{name}_bg_color"])
+        pix = G[f"{name}_pixel_idx"]
+        assert seen["margin"] == over["edge_filter"] and seen["dir_norm"] == (over["dir_norm"] > 0)
+        if seen["patches"] is None:
+            assert it["pixel_idx"].shape[1:3] == pix.shape[:2]
+        else:
+            PN, PS = seen["PN"], seen["PS"]
+            assert PN * PS == pix.shape[0]
+            for p, (x0, y0, d) in enumerate(seen["patches"]):
+                blk = pix[(p // PN) * PS:(p // PN + 1) * PS, (p % PN) * PS:(p % PN + 1) * PS]
+                xs, ys = np.meshgrid(x0 + d * np.arange(PS), y0 + d * np.arange(PS))
+                np.testing.assert_array_equal(blk[..., 0], xs)
+                np.testing.assert_array_equal(blk[..., 1], ys)

@@ -137,3 +137,32 @@ def test_learnable_blur_matches_reference():
             for got, key in ((w.grad, f"c{ci}_gW{li}"), (b.grad, f"c{ci}_gb{li}")):
                 np.testing.assert_allclose(got.numpy(), G[key], rtol=1e-4, atol=1e-4 * np.abs(G[key]).max() + 1e-12)
         assert raw.std() > 0.05, "fixture should predict non-uniform kernels"
+
+
+def _frame_oracle_item(name, split, idx, over, seed, bg):
+    import random
+    from oracle import frame_oracle as fo
+    images, c2w, vids, K, train_ids, test_ids = syn.frame_scene()
+    random.seed(seed)
+    np.random.seed(seed)
+    it = fo.frame_item(images, c2w, vids, K, train_ids if split == "train" else test_ids, train_ids, idx, split=split, bg_color=bg,
+                       total_num_image=vids[-1] + 1, **over)
+    return it, np.array([random.random(), np.random.rand()])
+
+
+def test_frame_producer_matches_reference():
+    """N4: oracle restatement of ScannetFtDataset.__getitem__ vs the unmodified method (tests/golden/frame.npz): chosen views,
+    pixel grid, ground-truth lookup and camera entries exact; ray directions to 1 ulp-ish (BLAS vs numpy summation order);
+    both RNG streams end in the same state."""
+    from frame_cases import FRAME_CASES
+    G = _load("frame")
+    for name, split, idx, over, seed, bg in FRAME_CASES:
+        it, after = _frame_oracle_item(name, split, idx, over, seed, bg)
+        assert it["vid_nearest"].tolist() == G[f"{name}_vid_nearest"].tolist(), name
+        assert [it["vid"], it["h"], it["w"]] == G[f"{name}_meta"][:3].tolist()
+        for k in ("pixel_idx", "gt_image", "c2w_nearest", "campos_nearest", "camrotc2w_nearest", "c2w", "campos", "camrotc2w", "bg_color"):
+            np.testing.assert_array_equal(np.asarray(it[k], np.float32), G[f"{name}_{k}"].astype(np.float32), err_msg=f"{name}:{k}")
+        np.testing.assert_allclose(it["raydir"], G[f"{name}_raydir"], rtol=0, atol=3e-7, err_msg=name)
+        np.testing.assert_allclose(it["vid_angle_nearest"], G[f"{name}_vid_angle_nearest"], rtol=1e-12)
+        np.testing.assert_allclose(it["middle"], G[f"{name}_middle"].reshape(()), rtol=1e-6)
+        np.testing.assert_array_equal(after, G[f"{name}_after"])
