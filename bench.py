@@ -28,7 +28,7 @@ N_POINTS = 1_000_000
 V = 4
 CHUNK = None          # whole frame per query (one host readback per frame)
 WORKLOAD = "NeRF-synthetic lego-shaped full-frame render 800x800, synthetic 1M neural points (voxel query + aggregation + compositing)"
-CPU_SAMPLE_RAYS = 12288      # 96 x 128 window at the image centre: ~10 s of host work per pass
+CPU_SAMPLE_RAYS = 20480      # 160 x 128 window at the image centre: ~12 s of host work per pass on 16 threads
 CPU_CHUNK_RAYS = 1024         # walked in chunks (the reference's own frame driver renders chunk by chunk, train_ft.py:282-351)
 
 
@@ -182,7 +182,7 @@ def sample_query(xyz, att, fr, P, dev):
     """query tensors (numpy) for a bounded sample of rays around the image centre.  The reference has no
     CPU query (its query is CUDA only), so the sample's neighbour lists come from the product query on the
     GPU when one is present, else from the numpy oracle on a smaller sample."""
-    yy, xx = np.meshgrid(np.arange(H // 2 - 48, H // 2 + 48), np.arange(W // 2 - 64, W // 2 + 64), indexing="ij")
+    yy, xx = np.meshgrid(np.arange(H // 2 - 80, H // 2 + 80), np.arange(W // 2 - 64, W // 2 + 64), indexing="ij")
     ids = (yy * W + xx).reshape(-1)[:CPU_SAMPLE_RAYS]
     sub = dict(fr, raydir=fr["raydir"][:, ids])
     opt = make_opt_lego()
