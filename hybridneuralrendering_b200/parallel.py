@@ -31,14 +31,35 @@ def shard_patches(n_rays: int, rays_per_patch: int, rank: int, world: int) -> Tu
     return p0 * rays_per_patch, p1 * rays_per_patch
 
 
+def shard_patch_rows(patch_num: int, patch_size: int, rank: int, world: int) -> Tuple[int, int]:
+    """[begin, end) ray range of `rank` for a training frame whose rays are the raster of a (patch_num*patch_size)^2 pixel grid
+    (data/scannet_ft_dataset.py:917-945): whole ROWS of patches, i.e. multiples of patch_size * S consecutive rays, so that
+    every 8x8 patch stays on one rank (a contiguous 64-ray range of the raster is one pixel row of 8 different patches)."""
+    S = patch_num * patch_size
+    r0, r1 = shard_patches(patch_num * patch_size * S, patch_size * S, rank, world)
+    return r0, r1
+
+
 def shard_frame(frame: Dict[str, torch.Tensor], rank: int, world: int, rays_per_patch: int = 64) -> Dict[str, torch.Tensor]:
-    """slice the per-ray entries of a frame dict; everything else is replicated"""
+    """slice the per-ray entries of a frame dict; everything else is replicated.
+    Frames that carry the dilated-patch layout (`dilation_PatchNum`, `dilation_PatchSize`) are cut along whole patch rows
+    (`shard_patch_rows`); other frames (full-frame rendering) in contiguous multiples of `rays_per_patch` rays."""
     R = frame["raydir"].shape[1]
-    b, e = shard_patches(R, rays_per_patch, rank, world)
+    PN, PS = frame.get("dilation_PatchNum"), frame.get("dilation_PatchSize")
+    if PN is not None and PS is not None and (int(PN) * int(PS)) ** 2 == R:
+        b, e = shard_patch_rows(int(PN), int(PS), rank, world)
+    else:
+        b, e = shard_patches(R, rays_per_patch, rank, world)
     out = dict(frame)
-    for k in ("raydir", "gt_image", "pixel_idx"):
+    for k in ("raydir", "gt_image"):
         if k in frame and frame[k] is not None and frame[k].dim() >= 2 and frame[k].shape[1] == R:
             out[k] = frame[k][:, b:e].contiguous()
+    pix = frame.get("pixel_idx")
+    if pix is not None and torch.is_tensor(pix):
+        if pix.dim() == 3 and pix.shape[1] == R:                       # (1,R,2)
+            out["pixel_idx"] = pix[:, b:e].contiguous()
+        elif pix.dim() == 4 and pix.shape[1] * pix.shape[2] == R:      # (1,S_h,S_w,2) as the dataset / FrameProducer hand it over
+            out["pixel_idx"] = pix.reshape(pix.shape[0], R, 2)[:, b:e].contiguous()
     return out
 
 

@@ -88,3 +88,26 @@ def test_shard_frame_slices_only_ray_entries():
              "campos": torch.zeros(1, 3), "images_nearest": torch.zeros(1, 2, 4, 4, 3)}
     s = parallel.shard_frame(frame, 1, 2)
     assert s["raydir"].shape == (1, 128, 3) and s["gt_image"].shape == (1, 128, 3) and s["images_nearest"].shape == (1, 2, 4, 4, 3)
+
+
+def test_shard_frame_keeps_patches_whole():
+    """training frames (dilated patch layout): every rank gets whole rows of patches of the raster, for any world size"""
+    PN, PS = 8, 8
+    S = PN * PS
+    R = S * S
+    patch_of_ray = ((torch.arange(S)[:, None] // PS) * PN + torch.arange(S)[None, :] // PS).reshape(-1)      # raster -> patch id
+    frame = {"raydir": torch.arange(R, dtype=torch.float32)[None, :, None].expand(1, R, 3), "gt_image": torch.zeros(1, R, 3),
+             "pixel_idx": torch.zeros(1, S, S, 2), "dilation_PatchNum": np.array([PN]), "dilation_PatchSize": np.array([PS])}
+    for world in (1, 2, 3, 4, 8):
+        seen = []
+        owners = {}
+        for rank in range(world):
+            sh = parallel.shard_frame(frame, rank, world)
+            ids = sh["raydir"][0, :, 0].long()
+            assert sh["pixel_idx"].shape == (1, len(ids), 2) and sh["gt_image"].shape == (1, len(ids), 3)
+            assert len(ids) % (PS * S) == 0 and torch.equal(ids, torch.arange(int(ids[0]), int(ids[0]) + len(ids)))
+            for pch in patch_of_ray[ids].unique().tolist():
+                assert owners.setdefault(pch, rank) == rank, "a patch is split between ranks"
+            assert (torch.bincount(patch_of_ray[ids], minlength=PN * PN)[patch_of_ray[ids].unique()] == PS * PS).all()
+            seen.append(ids)
+        assert torch.equal(torch.cat(seen), torch.arange(R))
