@@ -383,6 +383,135 @@ knn_kernel(const float* __restrict__ sample_loc, const int32_t* __restrict__ nsa
     if (threadIdx.x == 0) nvalid[ray] = s_valid;
 }
 
+// ---- third generation (NOT the default yet: selected with HNR_KNN_V3=1, to be A/B-ed and promoted in round 2) ----
+// The batched kernel above is instruction-issue bound (profiles/r1_knn_batched_ncu.md: IPC 3.2 of 4, ~800 warp instructions
+// per sample).  Two of its biggest items are removed here:
+//   * shell sizes are compile-time for the shipped kernel_size = 3 (shell 0 = the sample's own voxel, shell 1 = the 26
+//     surrounding voxels): the voxel offsets `ci / side^2`, `(ci / side) % side`, `ci % side` become constant divisions;
+//   * a batch with many candidates below the current K-th key (always the first batches of a sample, whose top-K is still empty)
+//     is merged by sorting: bitonic sort of the 32 keys, C[lane] = min(top[lane], batch[31 - lane]) -- the 32 smallest of the
+//     union as a bitonic sequence -- and one bitonic merge; ~150 instructions instead of ~16 per serial insertion.
+// Same result by construction: the top-K is the set of the K smallest unique (d2, id) keys in ascending order.
+__device__ __forceinline__ unsigned long long u64_min(unsigned long long a, unsigned long long b) { return a < b ? a : b; }
+__device__ __forceinline__ unsigned long long u64_max(unsigned long long a, unsigned long long b) { return a < b ? b : a; }
+
+__device__ __forceinline__ void knn_merge_v3(unsigned long long key, int K, int lane, unsigned long long& topk, int& kid) {
+    const unsigned cand = __ballot_sync(0xffffffffu, key != KEY_EMPTY);
+    kid += __popc(cand);
+    unsigned long long kth = shfl_u64(topk, K - 1);
+    unsigned m = __ballot_sync(0xffffffffu, key < kth);
+    if (__popc(m) > 8) {
+        // sort the batch ascending over the lanes
+        unsigned long long v = key;
+#pragma unroll
+        for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                const unsigned long long p = __shfl_xor_sync(0xffffffffu, v, j);
+                const bool up = (lane & k) == 0, lower = (lane & j) == 0;
+                v = (lower == up) ? u64_min(v, p) : u64_max(v, p);
+            }
+        }
+        // the 32 smallest of (top, batch) as a bitonic sequence, then sorted; lanes >= K may keep further keys: harmless, they are
+        // never written out and never smaller than lane K-1
+        const unsigned long long rev = shfl_u64(v, 31 - lane);
+        v = u64_min(topk, rev);
+#pragma unroll
+        for (int j = 16; j > 0; j >>= 1) {
+            const unsigned long long p = __shfl_xor_sync(0xffffffffu, v, j);
+            v = (lane & j) == 0 ? u64_min(v, p) : u64_max(v, p);
+        }
+        topk = v;
+        return;
+    }
+    while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        const unsigned long long x = shfl_u64(key, src);
+        kth = shfl_u64(topk, K - 1);
+        if (x < kth) {                         // warp-uniform
+            unsigned long long prev = shfl_up_u64(topk, 1);
+            if (lane == 0) prev = 0ull;
+            topk = (x < prev) ? prev : ((x < topk) ? x : topk);
+        }
+    }
+}
+
+// walk the concatenated candidate list of up to 32 voxels (see knn_visit_cells) with the sorting merge
+__device__ __forceinline__ void knn_visit_cells_v3(const float4* __restrict__ pts, int start, int n, float sx, float sy, float sz, float r2,
+                                                   int K, int lane, unsigned long long& topk, int& kid) {
+    int incl = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    const int excl = incl - n;
+    for (int b0 = 0; b0 < total; b0 += 32) {
+        const int j = b0 + lane;
+        int lo = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+            const int v = __shfl_sync(0xffffffffu, incl, lo + step - 1);
+            if (v <= j) lo += step;
+        }
+        const int st = __shfl_sync(0xffffffffu, start, lo), ex = __shfl_sync(0xffffffffu, excl, lo);
+        unsigned long long key = KEY_EMPTY;
+        if (j < total) key = knn_key(pts[st + (j - ex)], sx, sy, sz, r2);
+        knn_merge_v3(key, K, lane, topk, kid);
+    }
+}
+
+// one shell with a compile-time edge (SIDE = 2 * layer + 1 <= 3: at most 27 voxels = one lane group)
+template <int SIDE>
+__device__ __forceinline__ void knn_shell_v3(const hnr_grid_t& g, const int32_t* __restrict__ cell_start, const float4* __restrict__ pts,
+                                             int fx, int fy, int fz, float sx, float sy, float sz, int K, int lane,
+                                             unsigned long long& topk, int& kid) {
+    constexpr int LAYER = SIDE / 2, NCELL = SIDE * SIDE * SIDE;
+    static_assert(NCELL <= 32, "one voxel per lane");
+    int start = 0, n = 0;
+    if (lane < NCELL) {
+        const int ox = lane / (SIDE * SIDE) - LAYER, oy = (lane / SIDE) % SIDE - LAYER, oz = lane % SIDE - LAYER;
+        const int cx = fx + ox, cy = fy + oy, cz = fz + oz;
+        const bool shell = max(abs(ox), max(abs(oy), abs(oz))) == LAYER;
+        if (shell && cx >= 0 && cx < g.dims[0] && cy >= 0 && cy < g.dims[1] && cz >= 0 && cz < g.dims[2]) {
+            const int64_t l = cell_lin(g, cx, cy, cz);
+            start = cell_start[l];
+            n = min(cell_start[l + 1] - start, g.P);
+        }
+    }
+    knn_visit_cells_v3(pts, start, n, sx, sy, sz, g.radius2, K, lane, topk, kid);
+}
+
+__global__ void __launch_bounds__(128)
+knn_kernel_v3(const float* __restrict__ sample_loc, const int32_t* __restrict__ nsamp, int64_t R, int SR, int K, hnr_grid_t g,
+              const int32_t* __restrict__ cell_start, const float4* __restrict__ pts_sorted, int32_t* __restrict__ pidx,
+              int32_t* __restrict__ nvalid) {
+    const int64_t ray = blockIdx.x;
+    const int ns = nsamp[ray];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __shared__ int s_valid;
+    if (threadIdx.x == 0) s_valid = 0;
+    __syncthreads();
+    int my_valid = 0;
+    for (int s = w; s < ns; s += nw) {
+        const float* lp = sample_loc + (ray * SR + s) * 3;
+        const float sx = lp[0], sy = lp[1], sz = lp[2];
+        int fx, fy, fz;
+        cell_coord(g, sx, sy, sz, fx, fy, fz);
+        unsigned long long topk = KEY_EMPTY;      // lanes 0..K-1: ascending (d2, id) keys
+        int kid = 0;
+        knn_shell_v3<1>(g, cell_start, pts_sorted, fx, fy, fz, sx, sy, sz, K, lane, topk, kid);
+        if (kid < K && g.layers > 1) knn_shell_v3<3>(g, cell_start, pts_sorted, fx, fy, fz, sx, sy, sz, K, lane, topk, kid);
+        if (lane < K) pidx[(ray * SR + s) * K + lane] = (topk == KEY_EMPTY) ? -1 : (int32_t)(topk & 0xffffffffull);
+        if (lane == 0 && topk != KEY_EMPTY) my_valid++;
+    }
+    if (lane == 0 && my_valid) atomicAdd(&s_valid, my_valid);
+    __syncthreads();
+    if (threadIdx.x == 0) nvalid[ray] = s_valid;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Q7: ray compaction + perspective coordinates + valid-sample list
 // ------------------------------------------------------------------------------------------------
@@ -513,7 +642,11 @@ extern "C" int hnr_query(const float* campos, const float* camrot, const float* 
     ray_select_kernel<<<(unsigned)hnr_cdiv(R * 32, 256), 256, 0, st>>>(campos, raydir, ts, ts_stride, R, (int)D, (int)SR, *g, occ_bits,
                                                                       sample_loc_full, nsamp);
     static const bool knn_per_voxel = getenv("HNR_KNN_PER_VOXEL") != nullptr;      // A/B switch: the first-generation voxel-by-voxel walk
-    if (knn_per_voxel)
+    static const bool knn_v3 = getenv("HNR_KNN_V3") != nullptr;                    // third generation, not promoted yet (<= 2 shells only)
+    if (knn_v3 && g->layers <= 2)
+        knn_kernel_v3<<<(unsigned)R, 128, 0, st>>>(sample_loc_full, nsamp, R, (int)SR, (int)K, *g, cell_start, (const float4*)pts_sorted,
+                                                   pidx_full, nvalid);
+    else if (knn_per_voxel)
         knn_kernel<false><<<(unsigned)R, 128, 0, st>>>(sample_loc_full, nsamp, R, (int)SR, (int)K, *g, cell_start, (const float4*)pts_sorted,
                                                        pidx_full, nvalid);
     else
