@@ -182,3 +182,25 @@ def test_frame_producer_item_host_path_with_stubbed_device_ops(monkeypatch):
                 xs, ys = np.meshgrid(x0 + d * np.arange(PS), y0 + d * np.arange(PS))
                 np.testing.assert_array_equal(blk[..., 0], xs)
                 np.testing.assert_array_equal(blk[..., 1], ys)
+
+
+def test_step_roofline_formula():
+    """roofline time = sum over stages of max(bytes / HBM peak, FLOPs / tensor peak).  Hand-checked numbers for the
+    configs[1] frame of round 1 (28.2 M neighbour rows, 3.95 M valid samples, 163,570 kept rays)."""
+    from hybridneuralrendering_b200 import profiling
+    pk = {"hbm_gbs": 6553.3, "bf16_tflops_sustained": 1370.7}
+    u = {"valid_neighbours": 28233702, "valid_samples": 3945903, "kept_rays": 163570}
+    r = profiling.step_roofline(u, 4, 640000, 400, 80, 800, 800, 72.9, pk)
+    nbr = 542720 * 28233702 / (1370.7e12 / 3) * 1e3
+    smp = (154184 + 4 * 39040) * 3945903 / (1370.7e12 / 3) * 1e3
+    assert abs(r["stages"]["per-neighbour MLP"]["roofline_ms"] - nbr) < 1e-3 and abs(nbr - 33.537) < 0.01
+    assert abs(r["stages"]["per-sample MLPs"]["roofline_ms"] - smp) < 1e-3
+    gather = (168 * 28233702 + 40 * 3945903) / 6553.3e9 * 1e3
+    assert abs(r["stages"]["gather + weights"]["roofline_ms"] - gather) < 1e-3
+    assert abs(r["roofline_ms"] - sum(s["roofline_ms"] for s in r["stages"].values())) < 1e-2
+    assert abs(r["frac"] - r["roofline_ms"] / 72.9) < 1e-9 and 0.5 < r["frac"] < 0.53
+    t = profiling.step_roofline({"valid_neighbours": 562096, "valid_samples": 75272, "kept_rays": 4096}, 8, 4096, 400, 24, 480, 640, 25.9, pk,
+                                train=True, points=2_000_000)
+    fwd, bwd = 542720 * 562096 / (1370.7e12 / 3), 2 * 542720 * 562096 / (1370.7e12 / 6)
+    assert abs(t["stages"]["per-neighbour MLP"]["roofline_ms"] - (fwd + bwd) * 1e3) < 1e-3
+    assert "dense point-gradient tables (zero fill)" in t["stages"] and 0.14 < t["frac"] < 0.16
