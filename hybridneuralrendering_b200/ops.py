@@ -5,6 +5,7 @@ fallback.  torch is used for allocation, streams and the autograd tape only.
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -211,6 +212,12 @@ class LinearFn(torch.autograd.Function):
         return (dW, db, d_res, None, None, None, *d_srcs)
 
 
+# narrowest layer whose backward runs on the tensor-core kernels.  The 64-wide blend-weight net spends 3.6 ms per training step there for
+# ~0.5 ms of traffic: HNR_TC_BWD_MIN_N=65 sends it to the exact-fp32 SIMT kernels instead -- an A/B switch for round 2,
+# the default (16) is the measured and validated configuration.
+TC_BWD_MIN_N = int(os.environ.get("HNR_TC_BWD_MIN_N", "16"))
+
+
 def linear_backward(W, Y, srcs, mods, dY, act: int, need_src, need_w: bool = True, has_b: bool = True, M: Optional[int] = None,
                     k_need: Optional[int] = None):
     """gradients of y = act(concat(srcs) W^T + b) given dY and the saved output Y: ([d_src_i | None], dW | None, db | None).
@@ -229,7 +236,7 @@ def linear_backward(W, Y, srcs, mods, dY, act: int, need_src, need_w: bool = Tru
     padded = list(srcs) + [None] * (3 - nsrc)
     lds = [s.stride(0) if s is not None else 0 for s in padded]
     d_srcs: List[Optional[torch.Tensor]] = [None] * nsrc
-    use_tc = LINEAR_ENGINE == "tc" and M >= 128 and N >= 16
+    use_tc = LINEAR_ENGINE == "tc" and M >= 128 and N >= TC_BWD_MIN_N
     if any(need_src) and M > 0:
         if use_tc:
             # tensor-core data gradient: dX = (dY * act'(Y)) . W in column slices of <= 256, then views per source
