@@ -21,7 +21,7 @@ sys.path.insert(0, ROOT)
 from oracle import ref_import, render_oracle as ro          # noqa: E402
 from hybridneuralrendering_b200 import synthetic as syn      # noqa: E402
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from frame_cases import FRAME_CASES                          # noqa: E402
+from frame_cases import FRAME_CASES, FRAME_CASES_CPU        # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))
 T = torch.from_numpy
@@ -243,7 +243,7 @@ def frame_case():
             with open(os.path.join(tmp, "scene", "exported", "color", f"{v}.jpg"), "wb") as f:
                 Image.fromarray(images[i]).save(f, format="PNG")
             np.savetxt(os.path.join(tmp, "scene", "exported", "pose", f"{v}.txt"), c2w[i].astype(np.float64), fmt="%.18e")
-        for name, split, idx, over, seed, bg in FRAME_CASES:
+        for name, split, idx, over, seed, bg in FRAME_CASES + FRAME_CASES_CPU:
             o = dict(use_frame_weight=0, weight_exp=1.0, dynamic_nearest=0, select_high_quality=0, downweight_blurry_feats=0,
                      random_sample_size=32, dilation_setup="8_8_1_8")
             o.update(over)
@@ -263,13 +263,19 @@ def frame_case():
             res[f"{name}_after"] = np.array([random.random(), np.random.rand()])     # both streams must be left in the same state
             # images_nearest is large: keep which frames were chosen (exact match against the scene) instead of the pixels
             chosen = []
-            for img in res.pop(f"{name}_images_nearest"):
+            imgs_n = res.pop(f"{name}_images_nearest")
+            res[f"{name}_images_nearest_absmax"] = np.float32(np.abs(imgs_n).max())
+            if opt.use_nearest <= 0:                                                    # zeroed placeholder frame (:849-851)
+                assert imgs_n.shape[0] == 1 and not imgs_n.any()
+                res[f"{name}_vid_nearest"] = np.array([0])
+                continue
+            for img in imgs_n:
                 hit = [i for i in range(F) if np.array_equal(img, images[i].astype(np.float32) / np.float32(255))]
                 assert len(hit) == 1, hit
                 chosen.append(vids[hit[0]])
             res[f"{name}_vid_nearest"] = np.array(chosen)
     np.savez_compressed(os.path.join(OUT, "frame.npz"), **res)
-    print("frame ok", {n: res[f"{n}_vid_nearest"].tolist() for n, *_ in FRAME_CASES})
+    print("frame ok", {n: res[f"{n}_vid_nearest"].tolist() for n, *_ in FRAME_CASES + FRAME_CASES_CPU})
 
 
 if __name__ == "__main__":

@@ -109,13 +109,13 @@ def test_frame_producer_host_logic_matches_reference_golden():
     """N4 host side of the PRODUCT (no GPU needed): nearest-view choice and the patch draws reproduce the unmodified reference's
     choices for the seeded golden cases; both RNG streams are consumed in the reference's order."""
     import random
-    from frame_cases import FRAME_CASES
+    from frame_cases import FRAME_CASES, FRAME_CASES_CPU
     from hybridneuralrendering_b200 import frame_producer as fp
     from hybridneuralrendering_b200 import synthetic as syn
     G = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "frame.npz")))
     images, c2w, vids, K, train_ids, test_ids = syn.frame_scene()
     H, W = images.shape[1:3]
-    for name, split, idx, over, seed, bg in FRAME_CASES:
+    for name, split, idx, over, seed, bg in FRAME_CASES + FRAME_CASES_CPU:
         random.seed(seed)
         np.random.seed(seed)
         vid = (train_ids if split == "train" else test_ids)[idx]
@@ -141,7 +141,7 @@ def test_frame_producer_item_host_path_with_stubbed_device_ops(monkeypatch):
     """runs FrameProducer.item on the CPU with the two device entry points replaced by recorders (the real kernels are covered by
     tests/test_gpu_frame_producer.py): key set, shapes, the patch table handed to the kernel and the RNG state after the item."""
     import random
-    from frame_cases import FRAME_CASES
+    from frame_cases import FRAME_CASES, FRAME_CASES_CPU
     from hybridneuralrendering_b200 import frame_producer as fp
     from hybridneuralrendering_b200 import synthetic as syn
     G = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "frame.npz")))
@@ -156,7 +156,7 @@ def test_frame_producer_item_host_path_with_stubbed_device_ops(monkeypatch):
 
     monkeypatch.setattr(fp, "frame_rays", fake_rays)
     monkeypatch.setattr(fp, "frame_views", lambda bank, ids: bank[ids.long()].float() / 255.0)
-    for name, split, idx, over, seed, bg in FRAME_CASES:
+    for name, split, idx, over, seed, bg in FRAME_CASES + FRAME_CASES_CPU:
         bank = fp.FrameBank(images, c2w, vids, K, "cpu")
         prod = fp.FrameProducer(bank, train_ids if split == "train" else test_ids, train_ids, fp.default_opt(**over), split=split,
                                 bg_color=bg, blur_kernels=np.zeros((1, 9, 9), np.float32), total_num_image=vids[-1] + 1)
@@ -167,6 +167,7 @@ def test_frame_producer_item_host_path_with_stubbed_device_ops(monkeypatch):
         assert it["vid_nearest"].tolist() == G[f"{name}_vid_nearest"].tolist()
         V = len(it["vid_nearest"])
         assert it["images_nearest"].shape == (1, V, H, W, 3) and it["c2w_nearest"].shape == (1, V, 4, 4)
+        assert np.float32(it["images_nearest"].abs().max()) == G[f"{name}_images_nearest_absmax"]
         assert it["campos_nearest"].shape == (1, V, 3) and it["campos"].shape == (1, 3) and it["camrotc2w"].shape == (1, 3, 3)
         np.testing.assert_array_equal(it["c2w_nearest"][0].numpy(), G[f"{name}_c2w_nearest"])
         np.testing.assert_array_equal(it["bg_color"][0].numpy(), G[f"{name}_bg_color"])

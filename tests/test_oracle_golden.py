@@ -154,10 +154,11 @@ def test_frame_producer_matches_reference():
     """N4: oracle restatement of ScannetFtDataset.__getitem__ vs the unmodified method (tests/golden/frame.npz): chosen views,
     pixel grid, ground-truth lookup and camera entries exact; ray directions to 1 ulp-ish (BLAS vs numpy summation order);
     both RNG streams end in the same state."""
-    from frame_cases import FRAME_CASES
+    from frame_cases import FRAME_CASES, FRAME_CASES_CPU
     G = _load("frame")
-    for name, split, idx, over, seed, bg in FRAME_CASES:
+    for name, split, idx, over, seed, bg in FRAME_CASES + FRAME_CASES_CPU:
         it, after = _frame_oracle_item(name, split, idx, over, seed, bg)
+        assert np.float32(np.abs(it["images_nearest"]).max()) == G[f"{name}_images_nearest_absmax"]
         assert it["vid_nearest"].tolist() == G[f"{name}_vid_nearest"].tolist(), name
         assert [it["vid"], it["h"], it["w"]] == G[f"{name}_meta"][:3].tolist()
         for k in ("pixel_idx", "gt_image", "c2w_nearest", "campos_nearest", "camrotc2w_nearest", "c2w", "campos", "camrotc2w", "bg_color"):
