@@ -18,6 +18,7 @@ raises instead of silently computing something different.
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import numpy as np
@@ -140,7 +141,8 @@ class PointAggregator(nn.Module):
         # first-generation 3xTF32 kernel (mlp_tc.cu), "simt" = exact-fp32 layer kernels.  Forwards that record a graph
         # always use the layer kernels.
         self.mlp_engine = "tc"
-        self.max_valid_chunk = 262144        # valid samples decoded per pass in no-grad mode (bounds activation memory)
+        # valid samples decoded per pass in no-grad mode (bounds activation memory); HNR_MAX_VALID_CHUNK = A/B override
+        self.max_valid_chunk = int(os.environ.get("HNR_MAX_VALID_CHUNK", "262144"))
         self.fused_train_forward = True      # graph-recording forwards of the per-neighbour stage also use the fused kernel
 
     @staticmethod
