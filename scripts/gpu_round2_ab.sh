@@ -13,6 +13,7 @@ HNR_MAX_VALID_CHUNK=524288 timeout 100 python bench.py --steps 5 --warmup 3 --no
 HNR_MAX_VALID_CHUNK=131072 timeout 100 python bench.py --steps 5 --warmup 3 --no-train --no-cpu-baseline > gpurun_out/ab_render_chunk128k.json 2>/dev/null
 timeout 100 python scripts/train_step_bench.py --steps 5 --warmup 3 --json gpurun_out/ab_train_default.json > /dev/null 2>&1
 HNR_TC_BWD_MIN_N=65 timeout 100 python scripts/train_step_bench.py --steps 5 --warmup 3 --json gpurun_out/ab_train_bwd_simt.json > /dev/null 2>&1
+timeout 60 python scripts/measure_tf32_peak.py --json gpurun_out/tf32_peak.json
 python - <<'P'
 import glob, json
 for f in sorted(glob.glob("gpurun_out/ab_render_*.json")):
