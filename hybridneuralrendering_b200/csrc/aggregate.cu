@@ -15,6 +15,7 @@
 #include "common.cuh"
 
 #include "hnr.h"
+#include "img_common.cuh"
 
 namespace {
 
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(256)
 nbr_features_bwd_kernel(const float* __restrict__ dX0, const float* __restrict__ dE, const float* __restrict__ emb,
                         const int32_t* __restrict__ pidx, const uint8_t* __restrict__ mask, const int32_t* __restrict__ vlist,
                         const float* __restrict__ raydirs, const float* __restrict__ cam, int64_t rows, int K, float* __restrict__ d_emb,
-                        float* __restrict__ d_color, float* __restrict__ d_dir) {
+                        float* __restrict__ d_color, float* __restrict__ d_dir, int ldx) {
     const int lane = threadIdx.x & 31;
     const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (row >= rows) return;
@@ -150,7 +151,7 @@ nbr_features_bwd_kernel(const float* __restrict__ dX0, const float* __restrict__
     const int64_t s = vlist[v];
     if (slot_masked(pidx, mask, s * K + k)) return;     // masked rows carry exactly zero gradient
     const int64_t g = pidx[s * K + k];
-    const float* dx = dX0 + row * X0_W;
+    const float* dx = dX0 + row * ldx;
     if (d_emb) {
         float e = emb[g * F_EMB + lane];
         float acc = dx[lane];
@@ -269,6 +270,83 @@ alpha_ksum_bwd_kernel(const float* __restrict__ H, const float* __restrict__ wei
     {
         float* o = &red[threadIdx.x >> 5][lane * 8];
         o[0] = gw0.x; o[1] = gw0.y; o[2] = gw0.z; o[3] = gw0.w; o[4] = gw1.x; o[5] = gw1.y; o[6] = gw1.z; o[7] = gw1.w;
+        if (lane == 0) red[threadIdx.x >> 5][HID] = gb;
+    }
+    __syncthreads();
+    const int nw = blockDim.x >> 5;
+    for (int c = threadIdx.x; c <= HID; c += blockDim.x) {
+        float t = 0.f;
+        for (int w = 0; w < nw; ++w) t += red[w][c];
+        atomicAdd(c < HID ? d_walpha + c : d_balpha, t);
+    }
+}
+
+// Same backward for the fused training path: the saved layer-3 output is read from its split image (img_common.cuh; lane = one
+// 8-column group = one 16-byte piece per plane) and the result is written as the GATED gradient dZ_3 = dH * act'(H) in the
+// same format -- the first operand of the fused data-gradient chain (nbr_bwd_f16.cu) and of the weight-gradient kernel.
+__global__ void __launch_bounds__(256)
+alpha_ksum_bwd_img_kernel(const uint8_t* __restrict__ himg, const float* __restrict__ weight, const float* __restrict__ confc,
+                          const int32_t* __restrict__ vlist, const float* __restrict__ w_alpha, const float* __restrict__ alpha_raw,
+                          const float* __restrict__ d_sigma, const float* __restrict__ dX5, int64_t Nv, uint8_t* __restrict__ dzimg,
+                          float* __restrict__ d_wc, float* __restrict__ d_walpha, float* __restrict__ d_balpha) {
+    constexpr int KK = 8;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const float4* wa4 = reinterpret_cast<const float4*>(w_alpha) + lane * 2;
+    const float4 wa0 = wa4[0], wa1 = wa4[1];
+    const float wa[8] = {wa0.x, wa0.y, wa0.z, wa0.w, wa1.x, wa1.y, wa1.z, wa1.w};
+    float gw[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) gw[i] = 0.f;
+    float gb = 0.f;
+    for (int64_t v = warp0; v < Nv; v += nwarps) {
+        const int64_t s = vlist[v];
+        const float ds = d_sigma[v];
+        const float4* g4 = reinterpret_cast<const float4*>(dX5 + v * X5_W) + lane * 2;
+        const float4 g0 = g4[0], g1 = g4[1];
+        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        uint4 hh[KK], hl[KK];
+#pragma unroll
+        for (int k = 0; k < KK; ++k) {
+            const uint8_t* p = himg + img::piece_off(v * KK + k, lane, HID);
+            hh[k] = __ldg(reinterpret_cast<const uint4*>(p));
+            hl[k] = __ldg(reinterpret_cast<const uint4*>(p + img::plane_bytes(HID)));
+        }
+#pragma unroll
+        for (int k = 0; k < KK; ++k) {
+            const int64_t row = v * KK + k;
+            float h[8];
+            img::join8_bf16(hh[k], hl[k], h);
+            const float wc = weight[s * KK + k] * (confc ? confc[s * KK + k] : 1.f);
+            const float raw = alpha_raw[row] - 1.f;
+            const float sp = softplus_t(raw);
+            const float sgm = 1.f / (1.f + expf(-raw));
+            const float draw = wc * ds * sgm;
+            float hd = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) hd = fmaf(h[i], g[i], hd);
+            hd = warp_sum(hd);
+            if (lane == 0) d_wc[row] = sp * ds + hd;
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                o[i] = (wc * g[i] + draw * wa[i]) * (h[i] > 0.f ? 1.f : 0.01f);
+                gw[i] = fmaf(draw, h[i], gw[i]);
+            }
+            gb += draw;
+            uint4 hi, lo;
+            img::split8_bf16(o, hi, lo);
+            uint8_t* q = dzimg + img::piece_off(row, lane, HID);
+            *reinterpret_cast<uint4*>(q) = hi;
+            *reinterpret_cast<uint4*>(q + img::plane_bytes(HID)) = lo;
+        }
+    }
+    __shared__ float red[8][HID + 1];
+    {
+        float* o = &red[threadIdx.x >> 5][lane * 8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = gw[i];
         if (lane == 0) red[threadIdx.x >> 5][HID] = gb;
     }
     __syncthreads();
@@ -567,8 +645,21 @@ extern "C" int hnr_nbr_features_bwd(const float* dX0, const float* dE, const flo
     HNR_CHECK_ARG(Nv >= 0 && K > 0, "nbr_features_bwd: bad shape");
     if (Nv == 0) return HNR_OK;
     nbr_features_bwd_kernel<<<warp_blocks(Nv * K), 256, 0, (cudaStream_t)stream>>>(dX0, dE, emb, pidx, mask, vlist, raydirs, cam,
-                                                                                  Nv * K, (int)K, d_emb, d_color, d_dir);
+                                                                                  Nv * K, (int)K, d_emb, d_color, d_dir, X0_W);
     HNR_CHECK_LAUNCH("nbr_features_bwd");
+    return HNR_OK;
+}
+
+// same with an explicit row stride of dX0 (>= 224: only [emb 32 | PE(emb) 192] are read) -- the fused data-gradient chain
+// (hnr_nbr_bwd_f16) produces exactly those 224 columns
+extern "C" int hnr_nbr_features_bwd_ld(const float* dX0, int64_t ldx, const float* dE, const float* emb, const int32_t* pidx,
+                                       const uint8_t* mask, const int32_t* vlist, const float* raydirs, const float* cam, int64_t Nv,
+                                       int64_t K, float* d_emb, float* d_color, float* d_dir, void* stream) {
+    HNR_CHECK_ARG(Nv >= 0 && K > 0 && ldx >= F_EMB + 2 * NF_FEAT * F_EMB, "nbr_features_bwd_ld: bad shape");
+    if (Nv == 0) return HNR_OK;
+    nbr_features_bwd_kernel<<<warp_blocks(Nv * K), 256, 0, (cudaStream_t)stream>>>(dX0, dE, emb, pidx, mask, vlist, raydirs, cam,
+                                                                                  Nv * K, (int)K, d_emb, d_color, d_dir, (int)ldx);
+    HNR_CHECK_LAUNCH("nbr_features_bwd_ld");
     return HNR_OK;
 }
 
@@ -597,6 +688,22 @@ extern "C" int hnr_alpha_ksum_bwd(const float* H, const float* weight, const flo
         alpha_ksum_bwd_kernel<0><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(H, weight, confc, vlist, w_alpha, alpha_raw, d_sigma, dX5,
                                                                                     Nv, (int)K, dH, d_wc, d_walpha, d_balpha);
     HNR_CHECK_LAUNCH("alpha_ksum_bwd");
+    return HNR_OK;
+}
+
+// Backward of the density head + weighted K-sum for the fused training path (K == 8): like hnr_alpha_ksum_bwd, but the saved
+// layer-3 output comes as a split image (h3img) and the result is the gated gradient dZ_3 = dH * LeakyReLU'(H_3) as a split
+// image (dz3img; rows beyond Nv*8 are left to the consumer, hnr_nbr_bwd_f16 zeroes them).
+extern "C" int hnr_alpha_ksum_bwd_img(const void* h3img, const float* weight, const float* confc, const int32_t* vlist, const float* w_alpha,
+                                      const float* alpha_raw, const float* d_sigma, const float* dX5, int64_t Nv, int64_t K, void* dz3img,
+                                      float* d_wc, float* d_walpha, float* d_balpha, void* stream) {
+    HNR_CHECK_ARG(K == 8, "alpha_ksum_bwd_img: K must be 8");
+    if (Nv == 0) return HNR_OK;
+    int64_t blocks = hnr_cdiv(Nv, 8);
+    if (blocks > 4 * HNR_NUM_SMS) blocks = 4 * HNR_NUM_SMS;
+    alpha_ksum_bwd_img_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const uint8_t*)h3img, weight, confc, vlist, w_alpha, alpha_raw,
+                                                                                 d_sigma, dX5, Nv, (uint8_t*)dz3img, d_wc, d_walpha, d_balpha);
+    HNR_CHECK_LAUNCH("alpha_ksum_bwd_img");
     return HNR_OK;
 }
 

@@ -27,6 +27,7 @@
 #include "hnr.h"
 #define TRACE_SRC ((long long*)nullptr)
 #include "tc_common.cuh"
+#include "img_common.cuh"
 
 namespace {
 using namespace tc;
@@ -70,7 +71,12 @@ struct F16Args {
     const float *loc_w, *loc_pers, *raydirs, *cam, *weight, *confc;
     const uint8_t* wpack;          // 67 chunk images in consumption order
     const float *bias, *walpha, *balpha;   // bias: (4,256), rows 0..2 pre-multiplied by the next layer's input scale
-    float *sigma, *X5, *dbg, *araw;     // dbg: optional (4, Nv*8, 256) activations of every layer (training / tests); araw: (Nv*8) density pre-activation
+    float *sigma, *X5, *dbg, *araw;     // dbg: optional (4, Nv*8, 256) activations of every layer (tests); araw: (Nv*8) density pre-activation
+    // training forward (MODE 2): split images (img_common.cuh) of the layer-0 input in kernel column order (288 wide), the
+    // block3 extras chunk (16 wide) and the four layers' outputs (256 wide), rows padded to the tile -- the operands of the
+    // fused backward kernels (nbr_bwd_f16.cu, wgrad_img.cu)
+    uint8_t *x0img, *eimg, *himg[NLAYER];
+    float inv_scale0, inv_scale2;
     float inv_act;                      // 1 / input scale of layers 1..3 (the saved activations are unscaled)
     int32_t* status;                    // optional: bit 0 is set when a scaled activation left fp16's range and was saturated
     int64_t Nv;
@@ -177,8 +183,25 @@ __device__ __forceinline__ void store_chunk16(uint8_t* stage, int r, const float
     *reinterpret_cast<uint4*>(stage + A_PART + A_LBO + r * 16) = lo;
 }
 
-template <bool DBG>
+// one 16-wide chunk of row `row` (values pre-multiplied by 1/inv) -> column groups 2c, 2c+1 of a split image with C columns
+__device__ __forceinline__ void store_chunk16_img(uint8_t* image, int C, int64_t row, int chunk, const float* v, float inv) {
+    float u[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) u[i] = v[i] * inv;
+    uint8_t* p = image + img::piece_off(row, 2 * chunk, C);
+    uint4 hi, lo;
+    img::split8_bf16(u, hi, lo);
+    *reinterpret_cast<uint4*>(p) = hi;
+    *reinterpret_cast<uint4*>(p + img::plane_bytes(C)) = lo;
+    img::split8_bf16(u + 8, hi, lo);
+    *reinterpret_cast<uint4*>(p + 512) = hi;
+    *reinterpret_cast<uint4*>(p + 512 + img::plane_bytes(C)) = lo;
+}
+
+// MODE 0: inference; 1: fp32 copies of every layer's output (tests); 2: training forward, split images saved for the backward
+template <int MODE>
 __global__ void __launch_bounds__(NTHREADS, 1) nbr_mlp_f16_kernel(F16Args A) {
+    constexpr bool DBG = MODE == 1;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -370,6 +393,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nbr_mlp_f16_kernel(F16Args A) {
 #pragma unroll
                 for (int i = 0; i < 7; ++i) ev[i] *= A.scale2;
                 store_chunk16(smem + OFF_E + p * A_STAGE, r, ev);
+                if (MODE == 2) store_chunk16_img(A.eimg, 16, row, 0, ev, A.inv_scale2);
                 wc_s[p * TM + r] = wgt;
                 fence_proxy_async();
                 __syncwarp();
@@ -397,7 +421,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) nbr_mlp_f16_kernel(F16Args A) {
             pe[60] = pe[61] = pe[62] = pe[63] = 0.f;
 #pragma unroll
             for (int i = 0; i < 32; ++i) sincos_fast(ef[i], &sn[i], &cs[i]);
+            int chunk_no = 0;
             auto put = [&](const float* v) {
+                if (MODE == 2) store_chunk16_img(A.x0img, NC0 * KC, row, chunk_no, v, A.inv_scale0);
+                ++chunk_no;
                 const uint32_t st = ait % NSA, ph = (ait / NSA) & 1;
                 ++ait;
                 mbar_wait_relaxed(bar_aempty + 8 * st, ph ^ 1, 32);
@@ -492,6 +519,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) nbr_mlp_f16_kernel(F16Args A) {
                             uint8_t* dst = act_hi + (j * 4 + q) * A_LBO + r * 16;
                             *reinterpret_cast<uint4*>(dst) = hi;
                             *reinterpret_cast<uint4*>(dst + ACT_PART) = lo;
+                            if (MODE == 2) {            // unscaled output as bf16 hi/lo: operand of the backward kernels
+                                float u[8];
+                                const float ia = A.inv_act;
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) u[i] = y[q * 8 + i] * ia;
+                                img::split8_bf16(u, hi, lo);
+                                uint8_t* gp = A.himg[l] + img::piece_off(row0 + r, j * 4 + q, HID);
+                                *reinterpret_cast<uint4*>(gp) = hi;
+                                *reinterpret_cast<uint4*>(gp + img::plane_bytes(HID)) = lo;
+                            }
                         }
                         fence_proxy_async();
                         __syncwarp();
@@ -533,6 +570,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nbr_mlp_f16_kernel(F16Args A) {
                                 float t = fmaf(__uint_as_float(cur[i]), mul, bv[u]);
                                 t = fmaxf(t, 0.01f * t);
                                 if (DBG) tsave[u] = t;
+                                if (MODE == 2) cur[i] = __float_as_uint(t);      // kept for the image store below
                                 dot = fmaf(t, wv[u], dot);
                                 sblk[i * TM + ((rg ^ i) << 2)] = t * wrow;
                             }
@@ -540,13 +578,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) nbr_mlp_f16_kernel(F16Args A) {
                                 reinterpret_cast<float4*>(A.dbg + ((int64_t)l * total_rows + row0 + r) * HID + j * 32)[i4] =
                                     make_float4(tsave[0], tsave[1], tsave[2], tsave[3]);
                         }
+                        if (MODE == 2) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                float u8[8];
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) u8[i] = __uint_as_float(cur[q * 8 + i]);
+                                uint4 hi, lo;
+                                img::split8_bf16(u8, hi, lo);
+                                uint8_t* gp = A.himg[l] + img::piece_off(row0 + r, j * 4 + q, HID);
+                                *reinterpret_cast<uint4*>(gp) = hi;
+                                *reinterpret_cast<uint4*>(gp + img::plane_bytes(HID)) = lo;
+                            }
+                        }
                     }
                     araw_s[wg * TM + r] = dot;
                     tc_fence_before();
                     named_barrier<1, NEPI>();
                     if (wg == 0) {
                         const float raw = araw_s[r] + araw_s[TM + r] + A.balpha[0];
-                        if (DBG && A.araw && row0 + r < total_rows) A.araw[row0 + r] = raw;
+                        if (MODE != 0 && A.araw && row0 + r < total_rows) A.araw[row0 + r] = raw;
                         float sg = wrow * softplus_t(raw - 1.f);
                         sg += __shfl_xor_sync(0xffffffffu, sg, 1);
                         sg += __shfl_xor_sync(0xffffffffu, sg, 2);
@@ -588,6 +639,23 @@ extern "C" int64_t hnr_nbr_mlp_f16_packed_bytes(void) { return (int64_t)NCHUNK_T
 // bias (4,256): rows 0..2 pre-multiplied by the next layer's input scale; inv_act = 1 / that scale.  dbg (optional):
 // (4, Nv*8, 256) unscaled activations of the four layers, araw (optional, with dbg): (Nv*8) density pre-activations --
 // the training forward saves them for the backward pass.
+static int nbr_mlp_f16_launch(F16Args& A, int mode, void* stream) {
+    static bool configured = false;
+    if (!configured) {
+        HNR_CUDA(cudaFuncSetAttribute(nbr_mlp_f16_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        HNR_CUDA(cudaFuncSetAttribute(nbr_mlp_f16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        HNR_CUDA(cudaFuncSetAttribute(nbr_mlp_f16_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        configured = true;
+    }
+    const int64_t ntiles = hnr_cdiv(A.Nv * 8, TM);
+    const int grid = (int)(ntiles < HNR_NUM_SMS ? ntiles : HNR_NUM_SMS);
+    if (mode == 2) nbr_mlp_f16_kernel<2><<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(A);
+    else if (mode == 1) nbr_mlp_f16_kernel<1><<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(A);
+    else nbr_mlp_f16_kernel<0><<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(A);
+    HNR_CHECK_LAUNCH("nbr_mlp_f16_forward");
+    return HNR_OK;
+}
+
 extern "C" int hnr_nbr_mlp_f16_forward(const float* xyz, const float* xyz_pers, const float* emb, const float* color, const float* dir,
                                        const int32_t* pidx, const int32_t* vlist, const float* loc_w, const float* loc_pers,
                                        const float* raydirs, const float* cam, const float* weight, const float* confc, const void* wpack,
@@ -603,16 +671,32 @@ extern "C" int hnr_nbr_mlp_f16_forward(const float* xyz, const float* xyz_pers, 
     A.Nv = Nv;
     for (int l = 0; l < NLAYER; ++l) A.mul[l] = mul[l];
     A.scale0 = scale0; A.scale2 = scale2; A.inv_act = inv_act; A.araw = araw; A.status = status;
-    static bool configured = false;
-    if (!configured) {
-        HNR_CUDA(cudaFuncSetAttribute(nbr_mlp_f16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        HNR_CUDA(cudaFuncSetAttribute(nbr_mlp_f16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        configured = true;
-    }
-    const int64_t ntiles = hnr_cdiv(Nv * 8, TM);
-    const int grid = (int)(ntiles < HNR_NUM_SMS ? ntiles : HNR_NUM_SMS);
-    if (dbg) nbr_mlp_f16_kernel<true><<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(A);
-    else nbr_mlp_f16_kernel<false><<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(A);
-    HNR_CHECK_LAUNCH("nbr_mlp_f16_forward");
-    return HNR_OK;
+    return nbr_mlp_f16_launch(A, dbg ? 1 : 0, stream);
+}
+
+// Training forward: same arithmetic, and everything the fused backward needs is saved as split images (img_common.cuh; every
+// image has ceil(Nv*8 / 128) * 128 rows): x0img 288 columns (layer-0 input in kernel column order), eimg 16 columns (block3
+// extras [colour 3, dir - view 3, <dir, view>, 9 x 0]), himg[0..3] 256 columns (outputs of the four layers); araw (Nv*8) density
+// pre-activations.  Consumers: hnr_alpha_ksum_bwd_img, hnr_nbr_bwd_f16, hnr_wgrad_img.
+extern "C" int hnr_nbr_mlp_f16_forward_train(const float* xyz, const float* xyz_pers, const float* emb, const float* color, const float* dir,
+                                             const int32_t* pidx, const int32_t* vlist, const float* loc_w, const float* loc_pers,
+                                             const float* raydirs, const float* cam, const float* weight, const float* confc,
+                                             const void* wpack, const float* bias, const float* walpha, const float* balpha, const float* mul,
+                                             float scale0, float scale2, float inv_act, int64_t Nv, int64_t K, float* sigma, float* X5,
+                                             void* x0img, void* eimg, void* h0img, void* h1img, void* h2img, void* h3img, float* araw,
+                                             int32_t* status, void* stream) {
+    HNR_CHECK_ARG(K == 8, "nbr_mlp_f16_forward_train: K must be 8 (128-row tiles hold 16 whole samples)");
+    HNR_CHECK_ARG(x0img && eimg && h0img && h1img && h2img && h3img && araw, "nbr_mlp_f16_forward_train: every image is required");
+    if (Nv == 0) return HNR_OK;
+    F16Args A{};
+    A.xyz = xyz; A.xyz_pers = xyz_pers; A.emb = emb; A.color = color; A.dir = dir; A.pidx = pidx; A.vlist = vlist;
+    A.loc_w = loc_w; A.loc_pers = loc_pers; A.raydirs = raydirs; A.cam = cam; A.weight = weight; A.confc = confc;
+    A.wpack = (const uint8_t*)wpack; A.bias = bias; A.walpha = walpha; A.balpha = balpha; A.sigma = sigma; A.X5 = X5; A.dbg = nullptr;
+    A.Nv = Nv;
+    for (int l = 0; l < NLAYER; ++l) A.mul[l] = mul[l];
+    A.scale0 = scale0; A.scale2 = scale2; A.inv_act = inv_act; A.araw = araw; A.status = status;
+    A.x0img = (uint8_t*)x0img; A.eimg = (uint8_t*)eimg;
+    A.himg[0] = (uint8_t*)h0img; A.himg[1] = (uint8_t*)h1img; A.himg[2] = (uint8_t*)h2img; A.himg[3] = (uint8_t*)h3img;
+    A.inv_scale0 = 1.f / scale0; A.inv_scale2 = 1.f / scale2;
+    return nbr_mlp_f16_launch(A, 2, stream);
 }

@@ -202,3 +202,87 @@ def forward_f16(tables, pidx, vlist, loc_w, loc_pers, raydirs, cam, weight, conf
                                             ptr(ba), mul_c, float(s0), float(s2), 1.0 / ACT_SCALE, Nv, K, ptr(sigma), ptr(X5), ptr(dbg),
                                             ptr(araw), ptr(ops.status_word(pidx.device)), stream()), "nbr_mlp_f16_forward")
     return (sigma, X5, dbg, araw) if debug else (sigma, X5)
+
+
+# =====================================================================================================
+# fused training path (csrc/nbr_bwd_f16.cu, csrc/wgrad_img.cu): split images + W^T images
+# =====================================================================================================
+X0_IMG_W, E_IMG_W = 288, 16
+X0_GRAD_W = 224           # leading reference columns of the layer-0 input that carry a gradient: [emb 32 | sin/cos(2^j emb) 192]
+
+
+def rows_padded(rows: int) -> int:
+    return (rows + 127) // 128 * 128
+
+
+def image_empty(rows: int, cols: int, device) -> torch.Tensor:
+    """uninitialised split image (csrc/img_common.cuh) of `rows` x `cols` values: 4 bytes per element, rows padded to 128"""
+    return torch.empty(rows_padded(rows) * cols * 4, device=device, dtype=torch.uint8)
+
+
+def image_to_dense(imgt: torch.Tensor, rows: int, cols: int) -> torch.Tensor:
+    """split image -> (rows, cols) fp32 (hi + lo); tests / debugging only"""
+    rp = rows_padded(rows)
+    v = imgt.view(torch.bfloat16).view(rp // 32, 2, cols // 8, 32, 8).float()
+    return (v[:, 0] + v[:, 1]).permute(0, 2, 1, 3).reshape(rp, cols)[:rows]
+
+
+def dense_to_image(x: torch.Tensor) -> torch.Tensor:
+    """(rows, cols % 16 == 0) fp32 -> split image with zero padding rows; tests / debugging only"""
+    rows, cols = x.shape
+    rp = rows_padded(rows)
+    xp = torch.zeros((rp, cols), device=x.device, dtype=torch.float32)
+    xp[:rows] = x
+    hi = xp.bfloat16()
+    lo = (xp - hi.float()).bfloat16()
+    t = lambda a: a.view(rp // 32, 32, cols // 8, 8).permute(0, 2, 1, 3)
+    return torch.stack([t(hi), t(lo)], dim=1).contiguous().view(torch.uint8).reshape(-1)
+
+
+def _pack_wT_bf16(W: torch.Tensor) -> torch.Tensor:
+    """W (256 outputs n, K <= 256 input columns k) -> 16 chunk images of the B operand of dX = dZ . W: rows = k (zero padded to
+    256), reduction index n in 16-wide chunks, bf16 hi | lo, canonical no-swizzle K-major UMMA core matrices"""
+    W = W.detach().float()
+    assert W.shape[0] == 256 and W.shape[1] <= 256
+    B = torch.zeros((256, 256), device=W.device, dtype=torch.float32)
+    B[:W.shape[1]] = W.t()
+    hi = B.bfloat16()
+    lo = (B - hi.float()).bfloat16()
+    tile = lambda x: x.view(32, 8, 16, 2, 8).permute(2, 3, 0, 1, 4)                  # (chunk, k block, row group, row, 8)
+    return torch.stack([tile(hi), tile(lo)], dim=1).contiguous().view(torch.uint8).reshape(-1)
+
+
+def pack_mlp_bwd(block1, block3) -> torch.Tensor:
+    """W^T images of the data-gradient chain in consumption order: W4, W3[:, :256], W2, W1[:, :224] (reference column order)"""
+    parts = [_pack_wT_bf16(block3[2].weight), _pack_wT_bf16(block3[0].weight[:, :256]), _pack_wT_bf16(block1[2].weight),
+             _pack_wT_bf16(block1[0].weight[:, :X0_GRAD_W])]
+    out = torch.cat(parts).contiguous()
+    assert out.numel() == lib().hnr_nbr_bwd_f16_packed_bytes()
+    return out
+
+
+def forward_f16_train(tables, pidx, vlist, loc_w, loc_pers, raydirs, cam, weight, confc, pack, w_alpha, b_alpha):
+    """training forward of the fused per-neighbour stage.  Returns sigma (Nv,1), X5 (Nv,280), images dict {x0, e, h0..h3}, araw."""
+    import ctypes as C
+    xyz, xyz_pers, emb, color, dirs, _ = tables
+    wpack, bias, mul, s0, s2 = pack
+    Nv, K = vlist.shape[0], pidx.shape[1]
+    dev = pidx.device
+    rows = Nv * K
+    sigma = torch.empty((Nv, 1), device=dev, dtype=torch.float32)
+    X5 = torch.empty((Nv, 280), device=dev, dtype=torch.float32)
+    imgs = {"x0": image_empty(rows, X0_IMG_W, dev), "e": image_empty(rows, E_IMG_W, dev)}
+    for l in range(4):
+        imgs[f"h{l}"] = image_empty(rows, 256, dev)
+    araw = torch.empty((rows,), device=dev, dtype=torch.float32)
+    wa = w_alpha.detach().float().contiguous().view(-1)
+    ba = b_alpha.detach().float().contiguous().view(-1)
+    mul_c = (C.c_float * 4)(*mul)
+    with ops._launch():
+        check(lib().hnr_nbr_mlp_f16_forward_train(ptr(xyz), ptr(xyz_pers), ptr(emb), ptr(color), ptr(dirs), ptr(pidx), ptr(vlist), ptr(loc_w),
+                                                  ptr(loc_pers), ptr(raydirs), ptr(cam), ptr(weight), ptr(confc), ptr(wpack), ptr(bias),
+                                                  ptr(wa), ptr(ba), mul_c, float(s0), float(s2), 1.0 / ACT_SCALE, Nv, K, ptr(sigma), ptr(X5),
+                                                  ptr(imgs["x0"]), ptr(imgs["e"]), ptr(imgs["h0"]), ptr(imgs["h1"]), ptr(imgs["h2"]),
+                                                  ptr(imgs["h3"]), ptr(araw), ptr(ops.status_word(dev)), stream()),
+              "nbr_mlp_f16_forward_train")
+    return sigma, X5, imgs, araw

@@ -488,6 +488,95 @@ class NbrMlpFusedFn(torch.autograd.Function):
         return (d_emb, d_col, d_dir, d_confc, dW1, db1, dW2, db2, dW3, db3, dW4, db4, d_wa.view(ctx.shapes[3]), d_ba.view(ctx.shapes[4]), None)
 
 
+class NbrMlpTrainFn(torch.autograd.Function):
+    """Fully fused training path of the per-neighbour stage (round 2).  Forward: nbr_mlp_f16 in save mode -- the layer-0 input,
+    the block3 extras and the four layers' outputs go to HBM as split bf16 images (csrc/img_common.cuh).  Backward: three
+    launches instead of 4 x (data gradient + weight gradient): density-head / K-sum backward writing the gated gradient image
+    dZ_3, the fused data-gradient chain (csrc/nbr_bwd_f16.cu: dZ_3 -> dZ_2 -> dZ_1 -> dZ_0 -> dX0, gradient tile resident on the
+    SM), and ONE weight-gradient launch for all four layers that bulk-copies the images as MN-major UMMA operands
+    (csrc/wgrad_img.cu).  Same gradients as NbrMlpFusedFn (autograd over point_aggregators.py:921-1026 of the reference).
+    -> sigma (Nv,1), X5 (Nv,280)."""
+
+    @staticmethod
+    def forward(ctx, emb, color, dirs, confc, W1, b1, W2, b2, W3, b3, W4, b4, w_alpha, b_alpha, aux):
+        from . import mlp_tc
+        xyz, xyz_pers, pidx, vlist, loc_w, loc_pers, raydirs, cam, weight, pack, packT = aux
+        Nv, K = vlist.shape[0], pidx.shape[1]
+        confc_c = _f32c(confc)
+        sigma, X5, imgs, araw = mlp_tc.forward_f16_train((xyz, xyz_pers, emb, color, dirs, None), pidx, vlist, loc_w, loc_pers, raydirs, cam,
+                                                         weight, confc_c, pack, w_alpha, b_alpha)
+        ctx.save_for_backward(emb, confc_c, W3, _f32c(w_alpha).view(-1), araw, pidx, vlist, raydirs, weight, packT, imgs["x0"], imgs["e"],
+                              imgs["h0"], imgs["h1"], imgs["h2"], imgs["h3"])
+        ctx.cam, ctx.Nv, ctx.K = cam, Nv, K
+        ctx.shapes = (emb.shape, color.shape, dirs.shape, w_alpha.shape, b_alpha.shape)
+        return sigma, X5
+
+    @staticmethod
+    def backward(ctx, d_sigma, dX5):
+        from . import mlp_tc
+        emb, confc, W3, w_alpha, araw, pidx, vlist, raydirs, weight, packT, x0img, eimg, h0, h1, h2, h3 = ctx.saved_tensors
+        Nv, K = ctx.Nv, ctx.K
+        rows = Nv * K
+        dev = emb.device
+        d_sigma, dX5 = _f32c(d_sigma), _f32c(dX5)
+        dz = [mlp_tc.image_empty(rows, HID, dev) for _ in range(4)]                 # dZ_0 .. dZ_3
+        d_wc = torch.empty((Nv, K), device=dev, dtype=torch.float32)
+        small = torch.zeros(HID + 1 + 4 * HID * WG_LDO, device=dev, dtype=torch.float32)   # one fill: d_walpha | d_balpha | 4 x (256, 320)
+        d_wa, d_ba, gw = small[:HID], small[HID:HID + 1], small[HID + 1:].view(4, HID, WG_LDO)
+        with _launch(name="alpha_ksum_bwd"):
+            check(lib().hnr_alpha_ksum_bwd_img(ptr(h3), ptr(weight), ptr(confc), ptr(vlist), ptr(w_alpha), ptr(araw), ptr(d_sigma), ptr(dX5),
+                                               Nv, K, ptr(dz[3]), ptr(d_wc), ptr(d_wa), ptr(d_ba), stream()), "alpha_ksum_bwd_img")
+        d_confc = None
+        if ctx.needs_input_grad[3]:
+            vl = vlist.long()
+            d_confc = torch.zeros_like(confc)
+            d_confc.index_copy_(0, vl, d_wc * weight.index_select(0, vl))
+        dX0 = torch.empty((rows, X0_GRAD_W), device=dev, dtype=torch.float32)
+        with _launch(name="nbr_bwd_chain"):
+            check(lib().hnr_nbr_bwd_f16(ptr(dz[3]), ptr(h2), ptr(h1), ptr(h0), ptr(dz[2]), ptr(dz[1]), ptr(dz[0]), ptr(dX0), X0_GRAD_W,
+                                        X0_GRAD_W, ptr(packT), rows, stream()), "nbr_bwd_f16")
+        dE = torch.empty((rows, E_W), device=dev, dtype=torch.float32)
+        W3c = _f32c(W3)
+        with _launch(name="dz_extras_bwd"):
+            check(lib().hnr_dz_extras_bwd(ptr(dz[2]), ptr(W3c), W3c.stride(0), HID, rows, ptr(dE), stream()), "dz_extras_bwd")
+        with _launch(name="wgrad_img"):
+            check(lib().hnr_wgrad_img(4, ptr_array(dz), ptr_array([x0img, h0, h1, h2]), ptr_array([None, None, eimg, None]),
+                                      i64_array([mlp_tc.X0_IMG_W, HID, HID, HID]), i64_array([0, 0, mlp_tc.E_IMG_W, 0]),
+                                      ptr_array([gw[0], gw[1], gw[2], gw[3]]), i64_array([WG_LDO] * 4), mlp_tc.rows_padded(rows), stream()),
+                  "wgrad_img")
+        idx, mask = _x0_cols(dev)
+        dW1 = torch.zeros((HID, X0_W), device=dev, dtype=torch.float32).index_copy_(1, idx, gw[0][:, :mlp_tc.X0_IMG_W][:, mask])
+        db1 = gw[0][:, mlp_tc.X0_IMG_W]
+        dW2, db2 = gw[1][:, :HID], gw[1][:, HID]
+        dW3 = torch.cat([gw[2][:, :HID], gw[2][:, HID:HID + E_W]], dim=1)
+        db3 = gw[2][:, HID + mlp_tc.E_IMG_W]
+        dW4, db4 = gw[3][:, :HID], gw[3][:, HID]
+        ne, nc, nd = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        d_emb = torch.zeros(ctx.shapes[0], device=dev, dtype=torch.float32) if ne else None
+        d_col = torch.zeros(ctx.shapes[1], device=dev, dtype=torch.float32) if nc else None
+        d_dir = torch.zeros(ctx.shapes[2], device=dev, dtype=torch.float32) if nd else None
+        if ne or nc or nd:
+            with _launch(name="nbr_features_bwd"):
+                check(lib().hnr_nbr_features_bwd_ld(ptr(dX0), X0_GRAD_W, ptr(dE), ptr(emb), ptr(pidx), None, ptr(vlist), ptr(raydirs),
+                                                    ptr(ctx.cam), Nv, K, ptr(d_emb), ptr(d_col), ptr(d_dir), stream()), "nbr_features_bwd_ld")
+        return (d_emb, d_col, d_dir, d_confc, dW1, db1, dW2, db2, dW3, db3, dW4, db4, d_wa.view(ctx.shapes[3]), d_ba.view(ctx.shapes[4]), None)
+
+
+WG_LDO = 320          # row stride of the weight-gradient scratch of hnr_wgrad_img (>= 288 + 16 + 1)
+_X0_COLS = {}
+
+
+def _x0_cols(dev):
+    """(reference column of every real kernel-order column of the layer-0 input, mask of the real columns), cached per device"""
+    key = str(dev)
+    if key not in _X0_COLS:
+        from . import mlp_tc
+        cols = mlp_tc.layer1_column_order_f16()
+        _X0_COLS[key] = (torch.tensor([c for c in cols if c >= 0], device=dev, dtype=torch.long),
+                         torch.tensor([c >= 0 for c in cols], device=dev, dtype=torch.bool))
+    return _X0_COLS[key]
+
+
 # --------------------------------------------------------------------------------------------
 # image branch
 # --------------------------------------------------------------------------------------------

@@ -144,6 +144,9 @@ class PointAggregator(nn.Module):
         # valid samples decoded per pass in no-grad mode (bounds activation memory); HNR_MAX_VALID_CHUNK = A/B override
         self.max_valid_chunk = int(os.environ.get("HNR_MAX_VALID_CHUNK", "262144"))
         self.fused_train_forward = True      # graph-recording forwards of the per-neighbour stage also use the fused kernel
+        # backward of the per-neighbour stage: fused data-gradient chain + one image-fed weight-gradient launch (nbr_bwd_f16.cu,
+        # wgrad_img.cu); False = layer-by-layer tensor-core kernels (kept as the cross-check of the fused path in the tests)
+        self.fused_backward = os.environ.get("HNR_FUSED_BWD", "1") != "0"
 
     @staticmethod
     def _check_supported(opt):
@@ -253,10 +256,17 @@ class PointAggregator(nn.Module):
         elif self.mlp_engine == "tc" and torch.is_grad_enabled() and K == 8 and mask is None and self.fused_train_forward:
             # training: the same fused kernel, with the four layers' activations saved for the tensor-core backward
             with ops.tag("nbr_mlp"):
-                sigma, X5 = ops.NbrMlpFusedFn.apply(emb, color, dirs, confc, b1[0].weight, b1[0].bias, b1[2].weight, b1[2].bias,
-                                                    b3[0].weight, b3[0].bias, b3[2].weight, b3[2].bias, self.alpha_branch[0].weight,
-                                                    self.alpha_branch[0].bias,
-                                                    (xyz, xyz_pers, pidx, vlist, loc_w, loc_pers, raydirs, cam, weight, self._packed_weights()))
+                if self.fused_backward:
+                    sigma, X5 = ops.NbrMlpTrainFn.apply(emb, color, dirs, confc, b1[0].weight, b1[0].bias, b1[2].weight, b1[2].bias,
+                                                        b3[0].weight, b3[0].bias, b3[2].weight, b3[2].bias, self.alpha_branch[0].weight,
+                                                        self.alpha_branch[0].bias,
+                                                        (xyz, xyz_pers, pidx, vlist, loc_w, loc_pers, raydirs, cam, weight,
+                                                         self._packed_weights(), self._packed_weights_bwd()))
+                else:
+                    sigma, X5 = ops.NbrMlpFusedFn.apply(emb, color, dirs, confc, b1[0].weight, b1[0].bias, b1[2].weight, b1[2].bias,
+                                                        b3[0].weight, b3[0].bias, b3[2].weight, b3[2].bias, self.alpha_branch[0].weight,
+                                                        self.alpha_branch[0].bias,
+                                                        (xyz, xyz_pers, pidx, vlist, loc_w, loc_pers, raydirs, cam, weight, self._packed_weights()))
         else:
             with ops.tag("gather"):
                 X0, E = ops.NbrFeaturesFn.apply(emb, color, dirs, xyz, xyz_pers, pidx, mask, vlist, loc_w, loc_pers, raydirs, cam)
@@ -352,6 +362,8 @@ class PointAggregator(nn.Module):
         from . import chain
         TS = chain.TRAIN_WEIGHT_SCALE
         self._packed_weights()
+        if self.fused_backward:
+            self._packed_weights_bwd()
         cf, am, cm = self.color_feature_branch, self.aux_merge_weight_block, self.color_mixup_block
         chain.packed_chain(self, "cf_t", [cf[0], cf[2], cf[4]], [ACT_LRELU] * 3, X5_W, weight_scale=TS)
         if int(self.opt.use_nearest) > 0:
@@ -380,6 +392,16 @@ class PointAggregator(nn.Module):
                 self._wpack_cache = mlp_tc.pack_mlp(self.block1, self.block3)
             self._pack_key = key
         return self._wpack_cache
+
+    def _packed_weights_bwd(self):
+        """bf16 hi/lo images of W^T for the fused data-gradient chain, re-packed when a weight changes"""
+        ps = [self.block1[0].weight, self.block1[2].weight, self.block3[0].weight, self.block3[2].weight]
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if getattr(self, "_packT_key", None) != key:
+            from . import mlp_tc
+            self._wpackT_cache = mlp_tc.pack_mlp_bwd(self.block1, self.block3)
+            self._packT_key = key
+        return self._wpackT_cache
 
     def last_valid_neighbours(self) -> int:
         """number of valid (sample, neighbour) pairs of the last call (profiling only; syncs)"""

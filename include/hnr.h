@@ -178,6 +178,42 @@ int hnr_nbr_mlp_f16_forward(const float* xyz, const float* xyz_pers, const float
                             float* X5 /* Nv,280 */, float* dbg, float* araw /* Nv*8, with dbg */,
                             int32_t* status /* optional device word: |= 1 when an activation saturated fp16 */, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Fused TRAINING path of the per-neighbour MLP (round 2).  The reference's backward is autograd over
+ * models/aggregators/point_aggregators.py:921-972, :1002-1026; here three kernels replace the 4 x (data gradient + weight
+ * gradient) layer launches.  Everything that crosses HBM between them is a "split image" (csrc/img_common.cuh): bf16 hi | lo
+ * planes per 32-row slab, which is simultaneously the canonical MN-major UMMA operand of the weight gradient and a
+ * thread-per-row coalesced format.  All images have ceil(Nv*8 / 128) * 128 rows.
+ * ------------------------------------------------------------------------------------------- */
+/* forward that saves its operands: x0img 288 columns (layer-0 input, kernel column order = mlp_tc.layer1_column_order_f16),
+ * eimg 16 columns (block3 extras), h0..h3img 256 columns (layer outputs), araw (Nv*8) density pre-activations. */
+int hnr_nbr_mlp_f16_forward_train(const float* xyz, const float* xyz_pers, const float* emb, const float* color, const float* dir,
+                                  const int32_t* pidx, const int32_t* vlist, const float* loc_w, const float* loc_pers,
+                                  const float* raydirs, const float* cam, const float* weight, const float* confc, const void* wpack,
+                                  const float* bias, const float* walpha, const float* balpha, const float* mul /* host, 4 */,
+                                  float scale0, float scale2, float inv_act, int64_t Nv, int64_t K, float* sigma, float* X5,
+                                  void* x0img, void* eimg, void* h0img, void* h1img, void* h2img, void* h3img, float* araw,
+                                  int32_t* status, void* stream);
+/* backward of the density head + weighted K-sum (:1002-1036) from / to images: reads h3img, writes dz3img = dH * act'(H_3) */
+int hnr_alpha_ksum_bwd_img(const void* h3img, const float* weight, const float* confc, const int32_t* vlist, const float* w_alpha,
+                           const float* alpha_raw, const float* d_sigma, const float* dX5, int64_t Nv, int64_t K, void* dz3img,
+                           float* d_wc, float* d_walpha, float* d_balpha, void* stream);
+/* fused data-gradient chain dZ_3 -> dZ_2 -> dZ_1 -> dZ_0 -> dX0 (csrc/nbr_bwd_f16.cu; 3 x bf16 split on tcgen05, gradient
+ * tile resident in shared memory / TMEM across the four layers).  wpackT: hnr_nbr_bwd_f16_packed_bytes() bytes built by
+ * mlp_tc.pack_mlp_bwd.  dX0 (rows, ldx): the first nx0 input-gradient columns of layer 0. */
+int64_t hnr_nbr_bwd_f16_packed_bytes(void);
+int hnr_nbr_bwd_f16(const void* dz3, const void* h2, const void* h1, const void* h0, void* dz2, void* dz1, void* dz0, float* dX0,
+                    int64_t ldx, int64_t nx0, const void* wpackT, int64_t rows, void* stream);
+/* dE (rows,7) = dZ (image) . W[:, k0:k0+7]: gradient of block3's extra inputs */
+int hnr_dz_extras_bwd(const void* dz, const float* W, int64_t ldw, int64_t k0, int64_t rows, float* dE, void* stream);
+/* weight + bias gradients of up to 4 layers in ONE launch, operands bulk-copied from the images as MN-major UMMA tiles
+ * (csrc/wgrad_img.cu).  Job i: out[i] (256, ldo[i]) += [dZ^T X | dZ^T E | dZ^T 1]. */
+int hnr_wgrad_img(int njob, const void* const* a, const void* const* b, const void* const* e, const int64_t* cb, const int64_t* ce,
+                  float* const* out, const int64_t* ldo, int64_t rows_pad, void* stream);
+int hnr_nbr_features_bwd_ld(const float* dX0, int64_t ldx, const float* dE, const float* emb, const int32_t* pidx, const uint8_t* mask,
+                            const int32_t* vlist, const float* raydirs, const float* cam, int64_t Nv, int64_t K, float* d_emb,
+                            float* d_color, float* d_dir, void* stream);
+
 /* Fused chain of up to 4 dense layers (widths <= 128) on tcgen05, 3xFP16 split (csrc/chain_f16.cu): the per-sample MLPs
  * color_feature_branch, aux_merge_weight_block (+ sigmoid head), color_mixup_block (+ residual) of
  * point_aggregators.py:556-683 in one launch each, activations resident in shared memory between layers.

@@ -1,0 +1,192 @@
+"""Fused training backward of the per-neighbour MLP (csrc/nbr_bwd_f16.cu, csrc/wgrad_img.cu, the image variants of the forward and of
+the density-head backward): every kernel against fp64 on the same inputs, then the whole path against the layer-by-layer
+tensor-core backward and (in test_gpu_e2e / test_gpu_aggregator) against the oracle and the reference's golden gradients.
+Tolerance: 1e-4 x the tensor's max magnitude (north_star: gradients within rtol 1e-4), written at each assert."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from hybridneuralrendering_b200 import make_opt, mlp_tc, ops  # noqa: E402
+from hybridneuralrendering_b200 import synthetic as syn  # noqa: E402
+from hybridneuralrendering_b200._lib import check, i64_array, lib, ptr, ptr_array, stream  # noqa: E402
+from oracle import render_oracle as ro  # noqa: E402
+
+from helpers import cuda, grad_atol  # noqa: E402
+
+TOL = 1e-4
+
+
+def _rel_max(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-300))
+
+
+def test_image_roundtrip_and_precision():
+    """split image <-> dense: layout round trip and the 16-bit mantissa of hi + lo"""
+    g = torch.Generator().manual_seed(0)
+    x = (torch.randn(1000, 48, generator=g) * torch.logspace(-6, 3, 48)[None]).cuda()
+    im = mlp_tc.dense_to_image(x)
+    assert im.numel() == mlp_tc.rows_padded(1000) * 48 * 4
+    y = mlp_tc.image_to_dense(im, 1000, 48)
+    assert float(((x - y).abs() / x.abs().clamp_min(1e-30)).max()) < 2.0 ** -15
+
+
+@pytest.mark.parametrize("rows", [1000, 128 * 300 + 17])
+def test_wgrad_img_matches_fp64(rows):
+    """dW = dZ^T [X | E], db = column sums of dZ, for 4 jobs of the shipped shapes in one launch (MN-major UMMA operands)"""
+    g = torch.Generator().manual_seed(rows)
+    dev = torch.device("cuda")
+    shapes = [(288, 0), (256, 0), (256, 16), (256, 0)]
+    dz, xs, es = [], [], []
+    for cb, ce in shapes:
+        # rows spanning several orders of magnitude, like real gradients
+        dz.append((torch.randn(rows, 256, generator=g) * torch.logspace(-5, 0, rows)[:, None]).to(dev))
+        xs.append(torch.randn(rows, cb, generator=g).to(dev))
+        es.append(torch.randn(rows, ce, generator=g).to(dev) if ce else None)
+    a = [mlp_tc.dense_to_image(t) for t in dz]
+    b = [mlp_tc.dense_to_image(t) for t in xs]
+    e = [mlp_tc.dense_to_image(t) if t is not None else None for t in es]
+    out = torch.zeros((4, 256, 320), device=dev)
+    check(lib().hnr_wgrad_img(4, ptr_array(a), ptr_array(b), ptr_array(e), i64_array([s[0] for s in shapes]), i64_array([s[1] for s in shapes]),
+                              ptr_array([out[i] for i in range(4)]), i64_array([320] * 4), mlp_tc.rows_padded(rows), stream()), "wgrad_img")
+    torch.cuda.synchronize()
+    for i, (cb, ce) in enumerate(shapes):
+        ref = dz[i].double().t() @ xs[i].double()
+        assert _rel_max(out[i][:, :cb], ref) < TOL, (i, "dW", _rel_max(out[i][:, :cb], ref))
+        if ce:
+            refe = dz[i].double().t() @ es[i].double()
+            assert _rel_max(out[i][:, cb:cb + ce], refe) < TOL, (i, "dW extras")
+        refb = dz[i].double().sum(0)
+        assert _rel_max(out[i][:, cb + ce], refb) < TOL, (i, "db", _rel_max(out[i][:, cb + ce], refb))
+
+
+@pytest.mark.parametrize("rows", [128 * 3 + 40, 128 * 148 * 2 + 77])
+def test_nbr_bwd_chain_matches_fp64(rows):
+    """dZ_3 -> dZ_2 -> dZ_1 -> dZ_0 -> dX0 through the fused kernel vs the same chain in fp64 (per layer)"""
+    g = torch.Generator().manual_seed(7)
+    dev = torch.device("cuda")
+    dz3 = (torch.randn(rows, 256, generator=g) * torch.logspace(-4, 0, rows)[:, None]).to(dev)
+    H = [torch.randn(rows, 256, generator=g).to(dev) for _ in range(3)]            # H_0, H_1, H_2 (only the signs matter)
+    W4, W3, W2 = [(torch.randn(256, 256, generator=g) / 16).to(dev) for _ in range(3)]
+    W1 = (torch.randn(256, 284, generator=g) / 16).to(dev)
+    W3f = torch.cat([W3, torch.randn(256, 7, generator=g).to(dev) / 16], dim=1)
+
+    class L:            # minimal stand-ins for nn.Linear
+        def __init__(self, w):
+            self.weight = w
+    packT = mlp_tc.pack_mlp_bwd([L(W1), None, L(W2)], [L(W3f), None, L(W4)])
+    # poison the padding rows of the dZ_3 image: the kernel must zero them (the weight-gradient kernel reads whole slabs)
+    rp = mlp_tc.rows_padded(rows)
+    im3 = mlp_tc.dense_to_image(torch.cat([dz3, torch.full((rp - rows, 256), 1e20, device=dev)]))
+    hims = [mlp_tc.dense_to_image(h) for h in H]
+    outs = [mlp_tc.image_empty(rows, 256, dev) for _ in range(3)]
+    dX0 = torch.full((rows, 224), float("nan"), device=dev)
+    check(lib().hnr_nbr_bwd_f16(ptr(im3), ptr(hims[2]), ptr(hims[1]), ptr(hims[0]), ptr(outs[2]), ptr(outs[1]), ptr(outs[0]), ptr(dX0), 224, 224,
+                                ptr(packT), rows, stream()), "nbr_bwd_f16")
+    dE = torch.empty((rows, 7), device=dev)
+    check(lib().hnr_dz_extras_bwd(ptr(outs[2]), ptr(W3f), 263, 256, rows, ptr(dE), stream()), "dz_extras_bwd")
+    torch.cuda.synchronize()
+    gate = lambda h: torch.where(mlp_tc.image_to_dense(mlp_tc.dense_to_image(h), rows, 256) > 0, 1.0, 0.01).double()
+    r2 = (dz3.double() @ W4.double()) * gate(H[2])
+    r1 = (r2 @ W3.double()) * gate(H[1])
+    r0 = (r1 @ W2.double()) * gate(H[0])
+    rx = r0 @ W1.double()[:, :224]
+    for name, got, ref in (("dZ_2", mlp_tc.image_to_dense(outs[2], rows, 256), r2), ("dZ_1", mlp_tc.image_to_dense(outs[1], rows, 256), r1),
+                           ("dZ_0", mlp_tc.image_to_dense(outs[0], rows, 256), r0), ("dX0", dX0, rx),
+                           ("dE", dE, r2 @ W3f.double()[:, 256:])):
+        assert torch.isfinite(got).all(), name
+        # per-row scale: rows span 4 orders of magnitude
+        err = (got.double() - ref).abs().amax(1) / ref.abs().amax(1).clamp_min(1e-300)
+        assert float(err.max()) < TOL, (name, float(err.max()))
+    if rp > rows:       # padding rows of every image are zero after the kernel
+        for im in [im3] + outs:
+            v = im.view(torch.bfloat16).view(rp // 32, 2, 32, 32, 8).float()
+            tail = (v[:, 0] + v[:, 1]).permute(0, 2, 1, 3).reshape(rp, 256)[rows:]
+            assert float(tail.abs().max()) == 0.0
+
+
+def _build(opt, xyz, att, P):
+    from hybridneuralrendering_b200 import NeuralPoints, NeuralPointsRayMarching, PointAggregator
+    pts = NeuralPoints(32, len(xyz), opt, torch.device("cuda"))
+    pts.set_points(cuda(xyz), cuda(att["emb"])[None], points_color=cuda(att["color"])[None], points_dir=cuda(att["dir"])[None],
+                   points_conf=cuda(att["conf"])[None], parameter=True)
+    agg = PointAggregator(opt).cuda()
+    agg.load_state_dict(P, strict=False)
+    return NeuralPointsRayMarching(aggregator=agg, neural_points=pts, opt=opt).cuda()
+
+
+def test_train_forward_images_match_debug_taps():
+    """the images the training forward saves are the bf16 hi+lo split of the activations the debug taps report"""
+    opt = make_opt("scannet", use_nearest=2, SR=24, is_train=True, drop_ratio=0.0, dilation_setup="4_4_1_8")
+    xyz = syn.room_scene(30000, 9)
+    att = syn.point_attributes(np.random.default_rng(9), len(xyz))
+    fr = syn.room_frame(H=48, W=64, V=2, patch_num=4, patch_size=4, seed=5)
+    net = _build(opt, xyz, att, ro.random_params(10))
+    agg, pts = net.aggregator, net.neural_points
+    frame = {k: (cuda(v) if isinstance(v, np.ndarray) and v.dtype.kind == "f" else v) for k, v in fr.items()}
+    with torch.no_grad():
+        inputs = {"raydir": frame["raydir"], "campos": frame["campos"], "camrotc2w": frame["camrotc2w"], "near": frame["near"], "far": frame["far"]}
+        pidx, loc, loc_w, dirs, _, _, ex = pts.query(inputs)
+        S, K = pidx.shape[1] * pidx.shape[2], pidx.shape[3]
+        tables = (pts.xyz, None, pts.points_embeding[0], pts.points_color[0], pts.points_dir[0], pts.points_conf.reshape(-1))
+        cam = ops.make_cam(frame["campos"], frame["camrotc2w"], pts.Rw2c)
+        weight, confc, _ = ops.NbrWeightsFn.apply(pts.xyz, tables[5], pidx.reshape(S, K), None, loc_w.reshape(S, 3))
+        with torch.enable_grad():
+            pack = agg._packed_weights()          # training scales
+        args = (tables, pidx.reshape(S, K), ex.vlist, loc_w.reshape(S, 3), loc.reshape(S, 3), dirs.reshape(S, 3), cam, weight, confc, pack,
+                agg.alpha_branch[0].weight, agg.alpha_branch[0].bias)
+        s1, x1, dbg, araw1 = mlp_tc.forward_f16(*args, debug=True)
+        s2, x2, imgs, araw2 = mlp_tc.forward_f16_train(*args)
+        X0 = torch.empty((ex.vlist.shape[0] * K, 284), device="cuda")
+        E = torch.empty((ex.vlist.shape[0] * K, 7), device="cuda")
+        check(lib().hnr_nbr_features(ptr(pts.xyz), None, ptr(tables[2]), ptr(tables[3]), ptr(tables[4]), ptr(pidx.reshape(S, K)), ptr(ex.vlist),
+                                     ptr(loc_w.reshape(S, 3)), ptr(loc.reshape(S, 3)), ptr(dirs.reshape(S, 3)), ptr(cam), ex.vlist.shape[0], K, 32,
+                                     ptr(X0), ptr(E), stream()), "nbr_features")
+    rows = ex.vlist.shape[0] * K
+    assert rows > 1000
+    assert torch.equal(s1, s2) and torch.equal(x1, x2) and torch.equal(araw1, araw2)
+    for l in range(4):
+        got = mlp_tc.image_to_dense(imgs[f"h{l}"], rows, 256)
+        assert float((got - dbg[l]).abs().max()) <= 2.0 ** -15 * float(dbg[l].abs().max()), l
+        assert torch.equal(got > 0, dbg[l].bfloat16().float() > 0)          # the gate the backward reads
+    cols = mlp_tc.layer1_column_order_f16()
+    gx = mlp_tc.image_to_dense(imgs["x0"], rows, 288)
+    real = torch.tensor([c for c in cols if c >= 0], device="cuda")
+    keep = torch.tensor([c >= 0 for c in cols], device="cuda")
+    # the fused kernel evaluates sin / cos on the MUFU pipe (abs error ~5e-7): compare at 1e-5
+    assert float((gx[:, keep] - X0.index_select(1, real)).abs().max()) < 1e-5 + 2.0 ** -15
+    assert float(gx[:, ~keep].abs().max()) == 0.0
+    ge = mlp_tc.image_to_dense(imgs["e"], rows, 16)
+    assert float((ge[:, :7] - E).abs().max()) <= 2.0 ** -15 * float(E.abs().max()) and float(ge[:, 7:].abs().max()) == 0.0
+
+
+def test_fused_backward_equals_layered_backward():
+    """whole training step: fused backward (image path) vs the layer-by-layer tensor-core backward (3xTF32) on the same forward
+    kernel -- every parameter and point gradient within 1e-4 x max magnitude"""
+    opt = make_opt("scannet", use_nearest=2, SR=24, is_train=True, drop_ratio=0.5, dilation_setup="4_4_1_8")
+    xyz = syn.room_scene(30000, 9)
+    att = syn.point_attributes(np.random.default_rng(9), len(xyz))
+    fr = syn.room_frame(H=48, W=64, V=2, patch_num=4, patch_size=4, seed=5)
+    P = ro.random_params(10)
+    res = []
+    for fused in (True, False):
+        net = _build(opt, xyz, att, P)
+        net.aggregator.fused_backward = fused
+        torch.manual_seed(3)
+        frame = {k: (cuda(v) if isinstance(v, np.ndarray) and v.dtype.kind == "f" else v) for k, v in fr.items()}
+        out = net(**frame)
+        gt = cuda(fr["gt_image"])[:, out["ray_mask"][0] > 0]
+        v = out["conf_coefficient"].clamp(1e-3, 1 - 1e-3)
+        loss = torch.nn.functional.mse_loss(out["coarse_raycolor"], gt) + 1e-4 * torch.mean(torch.log(v) + torch.log(1 - v))
+        loss.backward()
+        res.append((out["coarse_raycolor"].detach(), {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}))
+    (ca, ga), (cb, gb) = res
+    assert torch.equal(ca, cb)                  # same forward kernel, same arithmetic
+    assert set(ga) == set(gb) and len(ga) > 40
+    for k in ga:
+        a, b = ga[k].double(), gb[k].double()
+        assert float((a - b).abs().max()) <= TOL * float(b.abs().max()) + 1e-30, (k, float((a - b).abs().max()), float(b.abs().max()))
