@@ -34,7 +34,7 @@ def build_train_case(dev, points: int = 2_000_000, views: int = 8, seed: int = 0
 
 
 def train_step_benchmark(dev, steps: int = 5, warmup: int = 3, world: int = 1, points: int = 2_000_000, views: int = 8,
-                         rank: int = 0, stage_split: bool = True) -> Dict:
+                         rank: int = 0, stage_split: bool = True, prefetch: bool = True) -> Dict:
     """fwd + loss + bwd (+ gradient all-reduce over NCCL when world > 1) timed with CUDA events; Adam timed separately.
     Returns a dict; 'value' is THIS rank's rays/s -- the caller aggregates over ranks with the max-over-ranks time."""
     import torch.distributed as dist
@@ -58,6 +58,8 @@ def train_step_benchmark(dev, steps: int = 5, warmup: int = 3, world: int = 1, p
             p.grad = None
         out = net(**frame)
         loss = training_loss(out, frame["gt_image"])
+        if prefetch:
+            net.prefetch_query(**frame)       # the NEXT step's voxel query (one query per step, software-pipelined one step ahead)
         with ops.tag("backward"):
             loss.backward()
         if world > 1:

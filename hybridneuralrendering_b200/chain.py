@@ -40,6 +40,16 @@ def _cols_index(cols0, device):
     return ent
 
 
+def _cols_real(cols0, device):
+    """(reference column, kernel column) index tensors of the real (non-padding) columns of a column order, cached per device"""
+    key = (str(device), tuple(cols0), "real")
+    ent = _IDX_CACHE.get(key)
+    if ent is None:
+        ent = _IDX_CACHE[key] = (torch.tensor([c for c in cols0 if c >= 0], device=device, dtype=torch.long),
+                                 torch.tensor([k for k, c in enumerate(cols0) if c >= 0], device=device, dtype=torch.long))
+    return ent
+
+
 def pack_chain_layer(W: torch.Tensor, Kp: int, weight_scale: Optional[float] = None):
     W = W.detach().float()
     N, K = W.shape
@@ -118,7 +128,7 @@ def packed_chain(owner, name: str, layers, acts, k_in: int, cols0=None, weight_s
 
 
 def chain_forward(pc: PackedChain, srcs: Sequence[torch.Tensor], M: Optional[int] = None, mods: Sequence[int] = (),
-                  out: bool = True, res: Optional[torch.Tensor] = None, head=None, keep_inner: bool = False):
+                  out: bool = True, res: Optional[torch.Tensor] = None, head=None, keep_inner: bool = False, save_images: bool = False):
     """run the chain over M rows.  srcs: 2-D fp32 tensors with unit inner stride (row stride free); concat widths must sum to
     the first layer's K.  head = (weight (1,N) , bias (1,), act) fuses a 1-output layer on the last output.
     Returns (Y_last or None, head_out or None, [inner Y_l] if keep_inner)."""
@@ -149,6 +159,20 @@ def chain_forward(pc: PackedChain, srcs: Sequence[torch.Tensor], M: Optional[int
     resv = ops._rows2d(res) if res is not None else None
     f4 = lambda v: (C.c_float * len(v))(*v)
     i4 = lambda v: (C.c_int * len(v))(*[int(x) for x in v])
+    if save_images:
+        # training forward: the concatenated input and the inner outputs go to HBM as split images (csrc/img_common.cuh)
+        from . import mlp_tc
+        x0img = mlp_tc.image_empty(M, pc.Kp[0], dev)
+        himg = [mlp_tc.image_empty(M, pc.Np[l], dev) for l in range(nl - 1)]
+        with ops._launch():
+            check(lib().hnr_chain_f16_forward_train(ptr_array(padded), i64_array(lds), i64_array(ks), i64_array(modl), float(pc.in_scale), nl,
+                                                    i64_array(pc.Kp), i64_array(pc.N), i64_array(pc.Np), i4(pc.acts), ptr(pc.wpack),
+                                                    i64_array(pc.w_off), ptr(pc.bias), f4(pc.mul), f4(pc.inv_next), ptr_array(Ys),
+                                                    i64_array([y.stride(0) if y is not None else 0 for y in Ys]), ptr(resv),
+                                                    resv.stride(0) if resv is not None else 0, ptr(hw), ptr(hb), hact, ptr(head_out), M,
+                                                    ptr(ops.status_word(dev)), ptr(x0img), ptr_array(himg + [None] * (4 - len(himg))), stream()),
+                  "chain_f16_forward_train")
+        return Ys[nl - 1], head_out, (x0img, himg)
     with ops._launch():
         check(lib().hnr_chain_f16_forward(ptr_array(padded), i64_array(lds), i64_array(ks), i64_array(modl), float(pc.in_scale), nl,
                                           i64_array(pc.Kp), i64_array(pc.N), i64_array(pc.Np), i4(pc.acts), ptr(pc.wpack),
@@ -160,13 +184,117 @@ def chain_forward(pc: PackedChain, srcs: Sequence[torch.Tensor], M: Optional[int
     return Ys[nl - 1], head_out, Ys[:-1]
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# fused backward (csrc/chain_bwd_f16.cu + csrc/wgrad_img.cu)
+# ------------------------------------------------------------------------------------------------------------------
+FUSED_BWD = __import__("os").environ.get("HNR_FUSED_BWD", "1") != "0"
+
+
+def _pack_wT_chunks(B: torch.Tensor) -> torch.Tensor:
+    """B (rows % 8 == 0, red % 16 == 0) fp32 = the B operand of a data-gradient MMA (rows = input columns k, reduction = output
+    units n) -> red/16 chunk images [hi | lo], each part [k block (2)][row group][row (8)][8 bf16] (canonical K-major UMMA)"""
+    rows, red = B.shape
+    hi = B.bfloat16()
+    lo = (B - hi.float()).bfloat16()
+    tile = lambda x: x.view(rows // 8, 8, red // 16, 2, 8).permute(2, 3, 0, 1, 4)
+    return torch.stack([tile(hi), tile(lo)], dim=1).contiguous().view(torch.uint8).reshape(-1)
+
+
+class PackedChainBwd:
+    """W^T images of a chain for hnr_chain_bwd_f16: layer l's operand has rows = Np[l-1] (l > 0) or NX (l = 0, the first NX
+    kernel-order input columns) and the reduction over Np[l] output units."""
+
+    def __init__(self, layers, pc: PackedChain, NX: int, cols0=None):
+        dev = layers[0].weight.device
+        self.NX = NX
+        imgs, offs, o = [], [], 0
+        for l, lin in enumerate(layers):
+            W = lin.weight.detach().float()                        # (N_l, K_l)
+            if l == 0 and cols0 is not None:
+                idx, mask = _cols_index(cols0, dev)
+                W = W.index_select(1, idx) * mask                    # kernel source order
+            rows = NX if l == 0 else pc.Np[l - 1]
+            B = torch.zeros((rows, pc.Np[l]), device=dev, dtype=torch.float32)
+            kk = min(rows, W.shape[1])
+            B[:kk, :W.shape[0]] = W.t()[:kk]
+            img = _pack_wT_chunks(B)
+            imgs.append(img)
+            offs.append(o)
+            o += img.numel()
+        self.w_off = offs
+        self.wpack = torch.cat(imgs).contiguous()
+
+
+def packed_chain_bwd(owner, name: str, layers, pc: PackedChain, NX: int, cols0=None) -> PackedChainBwd:
+    key = (NX,) + tuple((lin.weight.data_ptr(), lin.weight._version) for lin in layers)
+    cache = owner.__dict__.setdefault("_chain_bwd_cache", {})
+    ent = cache.get(name)
+    if ent is None or ent[0] != key:
+        ent = (key, PackedChainBwd(layers, pc, NX, cols0))
+        cache[name] = ent
+    return ent[1]
+
+
+WG_LDO = 320
+
+
+def chain_backward_fused(pc: PackedChain, pb: PackedChainBwd, Ws, images, y_top: torch.Tensor, dY: torch.Tensor, M: int, acts, ks, mods,
+                         need_src, cols0):
+    """data gradients (one fused launch) + weight / bias gradients (one image-fed launch) of a chain.
+    Returns ([d_src_i | None], [dW_l], [db_l])."""
+    from . import mlp_tc
+    x0img, himg = images
+    nl = pc.nlayer
+    dev = dY.device
+    dY, y_top = ops._rows2d(dY), ops._rows2d(y_top)
+    NX = pb.NX
+    ktot = sum(ks)
+    ldx = max(NX, (ktot + 3) // 4 * 4)
+    dX = torch.empty((M, ldx), device=dev, dtype=torch.float32)
+    if ldx > NX:
+        dX[:, NX:].zero_()
+    dz = [mlp_tc.image_empty(M, pc.Np[l], dev) for l in range(nl)]
+    act_top = int(acts[nl - 1])
+    with ops._launch(name="chain_bwd"):
+        check(lib().hnr_chain_bwd_f16(nl, i64_array(pc.Np), i64_array(pc.N), NX, act_top, ptr(dY), dY.stride(0), ptr(y_top), y_top.stride(0),
+                                      ptr_array(himg + [None] * (4 - len(himg))), ptr_array(dz + [None] * (4 - nl)), ptr(pb.wpack),
+                                      i64_array(pb.w_off), ptr(dX), ldx, M, stream()), "chain_bwd_f16")
+    gw = torch.zeros((nl, NMAX, WG_LDO), device=dev, dtype=torch.float32)
+    rp = mlp_tc.rows_padded(M)
+    with ops._launch(name="wgrad_img"):
+        check(lib().hnr_wgrad_img_jobs(nl, ptr_array(dz), i64_array(pc.Np), ptr_array([x0img] + himg), None, i64_array([pc.Kp[0]] + pc.Np[:-1]),
+                                       i64_array([0] * nl), ptr_array([gw[l] for l in range(nl)]), i64_array([WG_LDO] * nl),
+                                       i64_array([rp] * nl), stream()), "wgrad_img_jobs")
+    dWs, dbs = [], []
+    for l in range(nl):
+        N, K = Ws[l].shape
+        cb = pc.Kp[0] if l == 0 else pc.Np[l - 1]
+        if l == 0 and cols0 is not None:
+            ref_idx, kern_idx = _cols_real(cols0, dev)                    # no boolean-mask indexing: that would synchronise with the device
+            dW = torch.zeros((N, K), device=dev, dtype=torch.float32).index_copy_(1, ref_idx, gw[0][:N].index_select(1, kern_idx))
+        else:
+            dW = gw[l][:N, :K].contiguous()
+        dWs.append(dW)
+        dbs.append(gw[l][:N, cb].contiguous())
+    d_srcs, off = [], 0
+    for i, k in enumerate(ks):
+        g = None
+        if need_src[i]:
+            g = dX[:, off:off + k]
+            if mods[i] > 0:
+                g = g.reshape(-1, mods[i], k).sum(dim=0)
+        d_srcs.append(g)
+        off += k
+    return d_srcs, dWs, dbs
+
+
 class ChainFn(torch.autograd.Function):
     """Graph-recording forward of a fused chain: one chain_f16 launch with every layer's output kept, backward layer by
     layer on the tensor-core gradient kernels (ops.linear_backward).  Same arithmetic and gradients as the equivalent
     sequence of ops.linear calls.  apply(pc, layers_params..., ) is wrapped by chain_train()."""
 
     @staticmethod
-    def forward(ctx, pc, acts, mods, M, has_res, head_act, nlayer, nsrc, cols0, *tensors):
+    def forward(ctx, pc, acts, mods, M, has_res, head_act, nlayer, nsrc, cols0, pb, *tensors):
         # tensors = [W_0, b_0, ..., W_{n-1}, b_{n-1}] + ([head_W, head_b] if head_act >= 0) + srcs + ([res] if has_res)
         k = 2 * nlayer
         Ws, bs = list(tensors[0:k:2]), list(tensors[1:k:2])
@@ -176,6 +304,18 @@ class ChainFn(torch.autograd.Function):
             k += 2
         srcs = list(tensors[k:k + nsrc])
         res = tensors[k + nsrc] if has_res else None
+        fused = FUSED_BWD and pb is not None
+        ctx.fused = fused
+        if fused:
+            y, h, images = chain_forward(pc, srcs, M=M, mods=mods, out=True, res=res, head=head, save_images=True)
+            ctx.cfg = (acts, mods, M, has_res, head_act, nlayer, nsrc, cols0)
+            ctx.pc, ctx.pb, ctx.ks = pc, pb, [s_.shape[1] for s_ in srcs]
+            ctx.nimg = len(images[1])
+            ctx.save_for_backward(*Ws, *([head[0]] if head else []), images[0], *images[1], y, *([h] if head else []))
+            if head is not None:
+                ctx.mark_non_differentiable(y)
+                return y, h
+            return y, y.new_empty(0)
         y, h, inner = chain_forward(pc, srcs, M=M, mods=mods, out=True, res=res, head=head, keep_inner=True)
         ctx.cfg = (acts, mods, M, has_res, head_act, nlayer, nsrc, cols0)
         ctx.save_for_backward(*Ws, *([head[0]] if head else []), *srcs, *inner, y, *([h] if head else []), *([res] if has_res else []))
@@ -188,6 +328,8 @@ class ChainFn(torch.autograd.Function):
     def backward(ctx, dY, dH):
         acts, mods, M, has_res, head_act, nlayer, nsrc, cols0 = ctx.cfg
         sv = list(ctx.saved_tensors)
+        if ctx.fused:
+            return ChainFn._backward_fused(ctx, sv, dY, dH)
         Ws = sv[:nlayer]; p = nlayer
         head_W = None
         if head_act >= 0:
@@ -213,7 +355,7 @@ class ChainFn(torch.autograd.Function):
         d_srcs = [None] * nsrc
         for l in reversed(range(nlayer)):
             ins = srcs if l == 0 else [Ys[l - 1]]
-            need = [ctx.needs_input_grad[9 + 2 * nlayer + (2 if head_act >= 0 else 0) + i] for i in range(nsrc)] if l == 0 else [True]
+            need = [ctx.needs_input_grad[10 + 2 * nlayer + (2 if head_act >= 0 else 0) + i] for i in range(nsrc)] if l == 0 else [True]
             Wl = Ws[l]
             if l == 0 and cols0 is not None:         # the kernel's source order is a column permutation of the reference weight
                 idx = _cols_index(cols0, Wl.device)[0]
@@ -233,10 +375,41 @@ class ChainFn(torch.autograd.Function):
         grads += list(d_srcs)
         if has_res:
             grads.append(d_res)
-        return (None,) * 9 + tuple(grads)
+        return (None,) * 10 + tuple(grads)
+
+    @staticmethod
+    def _backward_fused(ctx, sv, dY, dH):
+        acts, mods, M, has_res, head_act, nlayer, nsrc, cols0 = ctx.cfg
+        Ws = sv[:nlayer]; p = nlayer
+        head_W = None
+        if head_act >= 0:
+            head_W = sv[p]; p += 1
+        x0img = sv[p]; p += 1
+        himg = list(sv[p:p + ctx.nimg]); p += ctx.nimg
+        y = sv[p]; p += 1
+        h = sv[p] if head_act >= 0 else None
+        g_head = [None, None]
+        if head_act >= 0:
+            (dcur,), dWh, dbh = ops.linear_backward(head_W, h, [y], (), dH, head_act, [True])
+            g_head = [dWh, dbh]
+        else:
+            dcur = dY
+        d_res = dcur if has_res else None
+        need = [ctx.needs_input_grad[10 + 2 * nlayer + (2 if head_act >= 0 else 0) + i] for i in range(nsrc)]
+        modl = list(mods) + [0] * (nsrc - len(mods))
+        d_srcs, gW, gb = chain_backward_fused(ctx.pc, ctx.pb, Ws, (x0img, himg), y, dcur, M, acts, ctx.ks, modl, need, cols0)
+        grads = []
+        for l in range(nlayer):
+            grads += [gW[l], gb[l]]
+        if head_act >= 0:
+            grads += g_head
+        grads += list(d_srcs)
+        if has_res:
+            grads.append(d_res)
+        return (None,) * 10 + tuple(grads)
 
 
-def chain_train(pc: PackedChain, layers, acts, srcs, M=None, mods=(), res=None, head=None, cols0=None):
+def chain_train(pc: PackedChain, layers, acts, srcs, M=None, mods=(), res=None, head=None, cols0=None, pb: Optional[PackedChainBwd] = None):
     """autograd-aware fused chain.  layers: the nn.Linear modules (their parameters receive gradients); head = (nn.Linear, act) or
     None.  Returns (y_last, head_out | None).  NOTE: with a residual the last activation must be 'none' (as in the mix-up block):
     the saved output then includes the residual, which the identity derivative never reads."""
@@ -255,5 +428,5 @@ def chain_train(pc: PackedChain, layers, acts, srcs, M=None, mods=(), res=None, 
     if res is not None:
         tensors.append(res)
     y, h = ChainFn.apply(pc, tuple(acts), tuple(mods), M, res is not None, head_act, len(layers), len(srcs),
-                         tuple(cols0) if cols0 is not None else None, *tensors)
+                         tuple(cols0) if cols0 is not None else None, pb, *tensors)
     return y, (h if head is not None else None)

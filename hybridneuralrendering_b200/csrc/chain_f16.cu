@@ -27,6 +27,7 @@
 #include "hnr.h"
 #define TRACE_SRC A.trace
 #include "tc_common.cuh"
+#include "img_common.cuh"
 
 namespace {
 using namespace tc;
@@ -73,6 +74,10 @@ struct ChainArgs {
     float* head_out;
     int64_t M;
     int32_t* status;             // optional: bit 1 is set when a scaled value left fp16's range and was saturated
+    // training forward: split images (img_common.cuh) of the concatenated input (Kp[0] columns, kernel source order) and of the
+    // inner layers' outputs (Np[l] columns), rows padded to the tile -- operands of chain_bwd_f16.cu / wgrad_img.cu.  NULL = off
+    uint8_t* x0img;
+    uint8_t* himg[MAXL];
     long long* trace;            // optional event trace of CTA 0 (bring-up / profiling): [count, (clock, id, a, b) ...]
 };
 
@@ -299,6 +304,18 @@ __global__ void __launch_bounds__(NTHREADS, 2) chain_f16_kernel(const __grid_con
                         }
                     }
                 }
+                if (A.x0img && mine) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int64_t m = m0 + 32 * gw + 4 * i + rsub;
+                        const uint32_t h0 = img::pack_bf16(v[i].x, v[i].y), h1 = img::pack_bf16(v[i].z, v[i].w);
+                        const uint32_t l0 = img::pack_bf16(v[i].x - img::bf16_lo_f(h0), v[i].y - img::bf16_hi_f(h0));
+                        const uint32_t l1 = img::pack_bf16(v[i].z - img::bf16_lo_f(h1), v[i].w - img::bf16_hi_f(h1));
+                        uint8_t* gp = A.x0img + img::piece_off(m, col0 >> 3, A.Kp[0]) + (col0 & 7) * 2;
+                        *reinterpret_cast<uint2*>(gp) = make_uint2(h0, h1);
+                        *reinterpret_cast<uint2*>(gp + img::plane_bytes(A.Kp[0])) = make_uint2(l0, l1);
+                    }
+                }
                 TRACE(10, p, 0);
                 const uint32_t st0 = ait % NSA, ph0 = (ait / NSA) & 1, st1 = (ait + 1) % NSA, ph1 = ((ait + 1) / NSA) & 1;
                 ait += have1 ? 2 : 1;
@@ -413,6 +430,19 @@ __global__ void __launch_bounds__(NTHREADS, 2) chain_f16_kernel(const __grid_con
                                 if (c0 + i < n) o[i] = y[i] * inv_next;
                         }
                     }
+                    if (!last && A.himg[l]) {
+                        float u[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) u[i] = y[i] * inv_next;
+                        uint4 hi, lo;
+                        uint8_t* gp = A.himg[l] + img::piece_off(m, c0 >> 3, np);
+                        img::split8_bf16(u, hi, lo);
+                        *reinterpret_cast<uint4*>(gp) = hi;
+                        *reinterpret_cast<uint4*>(gp + img::plane_bytes(np)) = lo;
+                        img::split8_bf16(u + 8, hi, lo);
+                        *reinterpret_cast<uint4*>(gp + 512) = hi;
+                        *reinterpret_cast<uint4*>(gp + 512 + img::plane_bytes(np)) = lo;
+                    }
                     if (!last) {
                         float am = 0.f;
 #pragma unroll
@@ -466,14 +496,16 @@ extern "C" void hnr_chain_f16_set_trace(void* buf) { g_trace = (long long*)buf; 
 long long* hnr_trace_ptr() { return g_trace; }
 
 // Fused chain of up to 4 dense layers (widths <= 128) over M rows, 3xFP16 on tcgen05 (see the header of this file).
+// (hnr_chain_f16_forward / hnr_chain_f16_forward_train below share this launcher.)
 // Arrays have nlayer entries.  Kp[0] = concat width padded to 16, Kp[l] = Np[l-1]; Np = N padded to 16.
 // wpack / bias / mul / inv_next: built by hybridneuralrendering_b200/chain.py.  Y[l] may be NULL (inner layers) --
 // at least one of Y[nlayer-1] and head_out must be given.
-extern "C" int hnr_chain_f16_forward(const float* const* src, const int64_t* src_ld, const int64_t* src_k, const int64_t* src_mod,
-                                     float in_scale, int nlayer, const int64_t* Kp, const int64_t* N, const int64_t* Np, const int* act,
-                                     const void* wpack, const int64_t* w_off, const float* bias, const float* mul, const float* inv_next,
-                                     float* const* Y, const int64_t* ldy, const float* res, int64_t ldres, const float* head_w,
-                                     const float* head_b, int head_act, float* head_out, int64_t M, int32_t* status, void* stream) {
+static int chain_f16_launch(const float* const* src, const int64_t* src_ld, const int64_t* src_k, const int64_t* src_mod,
+                            float in_scale, int nlayer, const int64_t* Kp, const int64_t* N, const int64_t* Np, const int* act,
+                            const void* wpack, const int64_t* w_off, const float* bias, const float* mul, const float* inv_next,
+                            float* const* Y, const int64_t* ldy, const float* res, int64_t ldres, const float* head_w,
+                            const float* head_b, int head_act, float* head_out, int64_t M, int32_t* status, void* x0img,
+                            void* const* himg, void* stream) {
     HNR_CHECK_ARG(nlayer >= 1 && nlayer <= MAXL, "chain_f16_forward: 1..4 layers");
     if (M == 0) return HNR_OK;
     ChainArgs A{};
@@ -497,6 +529,8 @@ extern "C" int hnr_chain_f16_forward(const float* const* src, const int64_t* src
     A.head_w = head_w; A.head_b = head_b; A.head_act = head_act; A.head_out = head_out; A.M = M;
     A.trace = g_trace;
     A.status = status;
+    A.x0img = (uint8_t*)x0img;
+    for (int l = 0; l < nlayer; ++l) A.himg[l] = (himg && l < nlayer - 1) ? (uint8_t*)himg[l] : nullptr;
     static bool configured = false;
     if (!configured) {
         HNR_CUDA(cudaFuncSetAttribute(chain_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -507,4 +541,26 @@ extern "C" int hnr_chain_f16_forward(const float* const* src, const int64_t* src
     chain_f16_kernel<<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(A);
     HNR_CHECK_LAUNCH("chain_f16_forward");
     return HNR_OK;
+}
+
+extern "C" int hnr_chain_f16_forward(const float* const* src, const int64_t* src_ld, const int64_t* src_k, const int64_t* src_mod,
+                                     float in_scale, int nlayer, const int64_t* Kp, const int64_t* N, const int64_t* Np, const int* act,
+                                     const void* wpack, const int64_t* w_off, const float* bias, const float* mul, const float* inv_next,
+                                     float* const* Y, const int64_t* ldy, const float* res, int64_t ldres, const float* head_w,
+                                     const float* head_b, int head_act, float* head_out, int64_t M, int32_t* status, void* stream) {
+    return chain_f16_launch(src, src_ld, src_k, src_mod, in_scale, nlayer, Kp, N, Np, act, wpack, w_off, bias, mul, inv_next, Y, ldy, res, ldres,
+                            head_w, head_b, head_act, head_out, M, status, nullptr, nullptr, stream);
+}
+
+// Training forward of a chain: same arithmetic; additionally saves the concatenated input (x0img: Kp[0] columns, kernel source
+// order) and the outputs of the inner layers (himg[l], l < nlayer-1: Np[l] columns) as split images with ceil(M/128)*128 rows.
+extern "C" int hnr_chain_f16_forward_train(const float* const* src, const int64_t* src_ld, const int64_t* src_k, const int64_t* src_mod,
+                                           float in_scale, int nlayer, const int64_t* Kp, const int64_t* N, const int64_t* Np, const int* act,
+                                           const void* wpack, const int64_t* w_off, const float* bias, const float* mul, const float* inv_next,
+                                           float* const* Y, const int64_t* ldy, const float* res, int64_t ldres, const float* head_w,
+                                           const float* head_b, int head_act, float* head_out, int64_t M, int32_t* status, void* x0img,
+                                           void* const* himg, void* stream) {
+    HNR_CHECK_ARG(x0img && himg, "chain_f16_forward_train: images required");
+    return chain_f16_launch(src, src_ld, src_k, src_mod, in_scale, nlayer, Kp, N, Np, act, wpack, w_off, bias, mul, inv_next, Y, ldy, res, ldres,
+                            head_w, head_b, head_act, head_out, M, status, x0img, himg, stream);
 }

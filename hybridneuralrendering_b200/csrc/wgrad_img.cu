@@ -39,17 +39,18 @@ constexpr int NTHREADS = 192;                   // warp 0 bulk copy, warp 1 MMA,
 constexpr uint32_t MN_SBO = 512, MN_LBO = 128;
 
 struct WJob {
-    const uint8_t* a;      // dZ image, 256 columns
+    const uint8_t* a;      // dZ image, ca columns (the layer's padded output width)
     const uint8_t* b;      // X image, cb columns
     const uint8_t* e;      // optional extra image, ce columns (NULL: none)
-    float* out;            // (256, ldo) fp32, += : columns [0, cb) dW vs X, [cb, cb+ce) dW vs extra, column cb+ce = db
-    int cb, ce, ldo;
-    int cta_begin;         // first CTA of this job (even); the job owns CTAs [cta_begin, next job's cta_begin)
+    float* out;            // (ca, ldo) fp32, += : columns [0, cb) dW vs X, [cb, cb+ce) dW vs extra, column cb+ce = db
+    int ca, cb, ce, ldo;
+    int nhalf;             // ceil(ca / 128): 128-row blocks of the output, one per CTA of a group
+    int cta_begin;         // first CTA of this job; the job owns CTAs [cta_begin, next job's cta_begin), a multiple of nhalf
+    int64_t nslab;         // 32-row slabs of this job's images
 };
 struct WArgs {
     WJob job[MAXJOB];
     int njob, ncta;
-    int64_t nslab;
     uint32_t lbo, sbo;     // descriptor strides (bring-up switch HNR_WG_SWAP exchanges them)
 };
 
@@ -76,13 +77,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_img_kernel(const __grid_con
         if (q < A.njob && (int)blockIdx.x >= A.job[q].cta_begin) ji = q;
     const WJob& J = A.job[ji];
     const int cta_end = ji + 1 < A.njob ? A.job[ji + 1].cta_begin : A.ncta;
-    const int npair = (cta_end - J.cta_begin) / 2;
+    const int npair = (cta_end - J.cta_begin) / J.nhalf;
     const int local = (int)blockIdx.x - J.cta_begin;
-    const int half = local & 1, cls = local >> 1;
-    const int64_t my_slabs = cls < A.nslab ? (A.nslab - cls + npair - 1) / npair : 0;
+    const int half = local % J.nhalf, cls = local / J.nhalf;
+    const int64_t my_slabs = cls < J.nslab ? (J.nslab - cls + npair - 1) / npair : 0;
     if (my_slabs == 0) return;                                  // uniform: nothing allocated yet
     const int ct = J.cb + J.ce;                                 // operand columns; the ones block follows
     const uint32_t b_plane = (uint32_t)ct / 8 * 512;
+    const int hw = min(128, J.ca - 128 * half);                 // output rows (= dZ columns) of this CTA
+    const uint32_t a_plane = (uint32_t)hw / 8 * 512;            // bytes of one A plane actually loaded (<= 8192)
 
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
     const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * NSTAGE, bar_acc = bar_empty + 8 * NSTAGE;
@@ -93,6 +96,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_img_kernel(const __grid_con
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < 256; i += NTHREADS) reinterpret_cast<uint32_t*>(smem + OFF_ONES)[i] = 0x3F803F80u;     // bf16 1.0 pairs
+    if (hw < 128) {
+        // a layer narrower than the 128-row MMA: the column groups the copies never touch read as zeros
+        for (int s = 0; s < NSTAGE; ++s)
+            for (int part = 0; part < 2; ++part)
+                for (uint32_t o = a_plane + tid * 16; o < 8192; o += NTHREADS * 16)
+                    *reinterpret_cast<uint4*>(smem + s * STAGE_BYTES + part * 8192 + o) = make_uint4(0u, 0u, 0u, 0u);
+    }
     fence_proxy_async();
     if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
     tc_fence_before();
@@ -103,7 +113,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_img_kernel(const __grid_con
     if (warp == 0) {
         if (lane == 0) {
             // ================= bulk-copy producer =================
-            const uint32_t stage_tx = A_BYTES + 2 * b_plane;
+            const uint32_t stage_tx = 2 * a_plane + 2 * b_plane;
             for (int64_t it = 0; it < my_slabs; ++it) {
                 const int64_t slab = cls + it * npair;
                 const uint32_t s = (uint32_t)(it % NSTAGE), ph = (uint32_t)((it / NSTAGE) & 1);
@@ -111,9 +121,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_img_kernel(const __grid_con
                 const uint32_t full = bar_full + 8 * s;
                 mbar_arrive_expect_tx(full, stage_tx);
                 const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
-                const uint8_t* ap = J.a + slab * img::slab_bytes(256) + (int64_t)half * 8192;
-                bulk_g2s(st, ap, 8192, full);                                           // A hi: 16 column groups of my half
-                bulk_g2s(st + 8192, ap + img::plane_bytes(256), 8192, full);            // A lo
+                const uint8_t* ap = J.a + slab * img::slab_bytes(J.ca) + (int64_t)half * 8192;
+                bulk_g2s(st, ap, a_plane, full);                                        // A hi: the column groups of my half
+                bulk_g2s(st + 8192, ap + img::plane_bytes(J.ca), a_plane, full);        // A lo
                 const uint8_t* bp = J.b + slab * img::slab_bytes(J.cb);
                 const uint32_t bmain = (uint32_t)J.cb / 8 * 512;
                 bulk_g2s(st + A_BYTES, bp, bmain, full);                                // B hi
@@ -171,11 +181,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_img_kernel(const __grid_con
         tc_fence_after();
         const int q = warp & 3;                                     // TMEM lane quarter this warp may read
         const int n = half * 128 + q * 32 + lane;
+        const bool live = q * 32 + lane < hw;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
         float* o = J.out + (int64_t)n * J.ldo;
         for (int c0 = 0; c0 < ct + 16; c0 += 16) {
             float v[16];
             tmem_ld16(taddr + c0, v);
+            if (!live) continue;
             if (c0 < ct) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) atomicAdd(o + c0 + i, v[i]);
@@ -191,37 +203,49 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_img_kernel(const __grid_con
 
 }  // namespace
 
-// Weight + bias gradients of up to 4 layers in one launch.  Per job i: a[i] = split image of dZ (rows_pad x 256), b[i] = split
-// image of the layer input (rows_pad x cb[i], cb % 16 == 0, <= 288), e[i] = optional extra input image (ce[i] columns, 0 or 16),
-// out[i] = (256, ldo[i]) fp32 accumulated into (zero it first): columns [0, cb+ce) = dW in operand-column order, column
-// cb+ce = db.  rows_pad % 128 == 0; padding rows of the dZ images must be zero.  share[i] > 0: relative cost used to split the SMs.
-extern "C" int hnr_wgrad_img(int njob, const void* const* a, const void* const* b, const void* const* e, const int64_t* cb,
-                             const int64_t* ce, float* const* out, const int64_t* ldo, int64_t rows_pad, void* stream) {
+// Weight + bias gradients of up to 4 layers in one launch.  Per job i: a[i] = split image of dZ (ca[i] columns = the layer's
+// padded output width, multiple of 16, <= 256), b[i] = split image of the layer input (cb[i] columns, multiple of 16, <= 288),
+// e[i] = optional extra input image (ce[i] columns, 0 or 16), out[i] = (ca[i], ldo[i]) fp32 accumulated into (zero it first):
+// columns [0, cb+ce) = dW in operand-column order, column cb+ce = db.  rows_pad[i] % 128 == 0 rows per image; padding rows of
+// the dZ images must be zero and those of the input images finite.
+extern "C" int hnr_wgrad_img_jobs(int njob, const void* const* a, const int64_t* ca, const void* const* b, const void* const* e,
+                                  const int64_t* cb, const int64_t* ce, float* const* out, const int64_t* ldo, const int64_t* rows_pad,
+                                  void* stream) {
     HNR_CHECK_ARG(njob >= 1 && njob <= MAXJOB, "wgrad_img: 1..4 jobs");
-    HNR_CHECK_ARG(rows_pad % 128 == 0, "wgrad_img: rows_pad must be a multiple of 128");
-    if (rows_pad == 0) return HNR_OK;
     WArgs A{};
     A.njob = njob;
-    A.nslab = rows_pad / img::SLAB;
-    // CTA pairs per job proportional to the bytes a slab costs (A half + all of B)
-    int64_t cost[MAXJOB], total = 0;
+    // CTA groups per job proportional to the bytes the job streams
+    double cost[MAXJOB], total = 0;
+    int nhalf[MAXJOB];
     for (int i = 0; i < njob; ++i) {
-        HNR_CHECK_ARG(cb[i] > 0 && cb[i] % 16 == 0 && (ce[i] == 0 || ce[i] == 16) && cb[i] + ce[i] <= B_MAX_COLS - 0 && cb[i] + ce[i] + 16 <= 512,
-                      "wgrad_img: operand widths");
+        HNR_CHECK_ARG(rows_pad[i] % 128 == 0, "wgrad_img: rows_pad must be a multiple of 128");
+        HNR_CHECK_ARG(ca[i] >= 16 && ca[i] % 16 == 0 && ca[i] <= 256, "wgrad_img: dZ width");
+        HNR_CHECK_ARG(cb[i] > 0 && cb[i] % 16 == 0 && (ce[i] == 0 || ce[i] == 16) && cb[i] + ce[i] <= B_MAX_COLS, "wgrad_img: operand widths");
         HNR_CHECK_ARG(ldo[i] >= cb[i] + ce[i] + 1, "wgrad_img: ldo too small");
-        cost[i] = 128 + cb[i] + ce[i];
+        nhalf[i] = (int)((ca[i] + 127) / 128);
+        cost[i] = (double)rows_pad[i] * (double)(ca[i] + nhalf[i] * (cb[i] + ce[i]));
         total += cost[i];
     }
-    const int pairs_total = HNR_NUM_SMS / 2;
-    int pairs[MAXJOB], used = 0;
-    for (int i = 0; i < njob; ++i) { pairs[i] = (int)(pairs_total * cost[i] / total); if (pairs[i] < 1) pairs[i] = 1; used += pairs[i]; }
-    for (int i = 0; used < pairs_total; i = (i + 1) % njob) { ++pairs[i]; ++used; }
+    if (total == 0) return HNR_OK;
+    int groups[MAXJOB], used = 0;
+    for (int i = 0; i < njob; ++i) {
+        int g = (int)((double)HNR_NUM_SMS * cost[i] / total / nhalf[i]);
+        const int64_t nslab = rows_pad[i] / img::SLAB;
+        if (g < 1) g = 1;
+        if (g > nslab) g = (int)(nslab > 0 ? nslab : 1);
+        groups[i] = g;
+        used += g * nhalf[i];
+    }
+    for (int guard = 0; used > HNR_NUM_SMS && guard < 1000; ++guard)            // rounding up the small jobs may overshoot
+        for (int i = 0; i < njob && used > HNR_NUM_SMS; ++i)
+            if (groups[i] > 1) { --groups[i]; used -= nhalf[i]; }
     int cta = 0;
     for (int i = 0; i < njob; ++i) {
         WJob& J = A.job[i];
         J.a = (const uint8_t*)a[i]; J.b = (const uint8_t*)b[i]; J.e = (e && ce[i]) ? (const uint8_t*)e[i] : nullptr;
-        J.cb = (int)cb[i]; J.ce = J.e ? (int)ce[i] : 0; J.out = out[i]; J.ldo = (int)ldo[i]; J.cta_begin = cta;
-        cta += 2 * pairs[i];
+        J.ca = (int)ca[i]; J.cb = (int)cb[i]; J.ce = J.e ? (int)ce[i] : 0; J.out = out[i]; J.ldo = (int)ldo[i]; J.cta_begin = cta;
+        J.nhalf = nhalf[i]; J.nslab = rows_pad[i] / img::SLAB;
+        cta += groups[i] * nhalf[i];
     }
     A.ncta = cta;
     const char* sw = getenv("HNR_WG_SWAP");
@@ -236,4 +260,13 @@ extern "C" int hnr_wgrad_img(int njob, const void* const* a, const void* const* 
     wgrad_img_kernel<<<cta, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(A);
     HNR_CHECK_LAUNCH("wgrad_img");
     return HNR_OK;
+}
+
+// the per-neighbour MLP's form: every dZ image 256 columns wide, one row count
+extern "C" int hnr_wgrad_img(int njob, const void* const* a, const void* const* b, const void* const* e, const int64_t* cb,
+                             const int64_t* ce, float* const* out, const int64_t* ldo, int64_t rows_pad, void* stream) {
+    HNR_CHECK_ARG(njob >= 1 && njob <= MAXJOB, "wgrad_img: 1..4 jobs");
+    int64_t ca[MAXJOB], rp[MAXJOB];
+    for (int i = 0; i < njob; ++i) { ca[i] = 256; rp[i] = rows_pad; }
+    return hnr_wgrad_img_jobs(njob, a, ca, b, e, cb, ce, out, ldo, rp, stream);
 }

@@ -42,11 +42,17 @@ def layer1_column_order() -> List[int]:
     return cols
 
 
+_PERM_CACHE = {}
+
+
 def _permute_pad(W: torch.Tensor, cols: Sequence[int]) -> torch.Tensor:
-    idx = torch.tensor([c if c >= 0 else 0 for c in cols], device=W.device, dtype=torch.long)
-    out = W.index_select(1, idx)
-    pad = torch.tensor([c < 0 for c in cols], device=W.device)
-    return out.masked_fill(pad[None, :], 0.0)
+    key = (str(W.device), tuple(cols))
+    ent = _PERM_CACHE.get(key)
+    if ent is None:         # built once per column order and device: creating a tensor from a Python list is a blocking host-to-device copy
+        ent = _PERM_CACHE[key] = (torch.tensor([c if c >= 0 else 0 for c in cols], device=W.device, dtype=torch.long),
+                                  torch.tensor([c < 0 for c in cols], device=W.device))
+    idx, pad = ent
+    return W.index_select(1, idx).masked_fill(pad[None, :], 0.0)
 
 
 def pack_layer(W: torch.Tensor, cols: Optional[Sequence[int]] = None) -> torch.Tensor:

@@ -148,14 +148,32 @@ class NeuralPoints(nn.Module):
         avoid a device->host read of inputs["near"/"far"] (the reference reads them every call, :707).
         Returns (sample_pidx (1,R'',SR,K) i32, sample_loc (pers), sample_loc_w, sample_ray_dirs,
         ray_mask (1,R) i8, vsize, extras)."""
-        if near is None:
-            near = float(torch.min(inputs["near"]).item())
-        if far is None:
-            far = float(torch.max(inputs["far"]).item())
+        key = self._query_key(inputs, near, far)
+        pend = getattr(self, "_pending", None)
+        self._pending = None
         q = self.querier
-        out = q.query_points(inputs.get("pixel_idx"), None, self.xyz[None, ...], None, inputs.get("h"), inputs.get("w"),
-                             inputs.get("intrinsic"), near, far, inputs["raydir"], inputs["campos"], inputs["camrotc2w"], ts=ts)
+        if ts is None and pend is not None and pend[0] == key and pend[1]["G"] is q._ensure_grid(self.xyz[None, ...]):
+            out = q.query_finish(pend[1])                      # launched earlier by prefetch(): the read-back is already there
+        else:
+            if near is None:
+                near = float(torch.min(inputs["near"]).item())
+            if far is None:
+                far = float(torch.max(inputs["far"]).item())
+            out = q.query_points(inputs.get("pixel_idx"), None, self.xyz[None, ...], None, inputs.get("h"), inputs.get("w"),
+                                 inputs.get("intrinsic"), near, far, inputs["raydir"], inputs["campos"], inputs["camrotc2w"], ts=ts)
         return out[0], out[1], out[2], out[3], out[4], out[5], q.last
+
+    @staticmethod
+    def _query_key(inputs, near, far):
+        t = lambda x: (x.data_ptr(), tuple(x.shape), x._version)
+        return (t(inputs["raydir"]), t(inputs["campos"]), t(inputs["camrotc2w"]), near, far)
+
+    def prefetch(self, inputs: Dict, near: float, far: float) -> None:
+        """launch the voxel query of a FUTURE forward now (kernels + asynchronous read-back, no host wait).  The next query() with
+        the same ray / camera tensors and the same point set picks the result up; anything else discards it.  The query does not
+        depend on trainable state (xyz_grad = 0), so a training loop can issue it one step ahead."""
+        self._pending = (self._query_key(inputs, near, far),
+                         self.querier.query_launch(self.xyz[None, ...], near, far, inputs["raydir"], inputs["campos"], inputs["camrotc2w"]))
 
     def forward(self, inputs):
         """(:702-733) returns the reference's 14-tuple with materialised neighbour gathers."""

@@ -83,6 +83,14 @@ class NeuralPointsRayMarching(nn.Module):
         self.last_extras = extras
         return output
 
+    def prefetch_query(self, campos=None, raydir=None, camrotc2w=None, **kargs) -> None:
+        """Software pipelining for training loops: enqueue the voxel query of the NEXT frame (pass its frame dict) before the
+        current frame's backward pass is issued.  Needs `near_far` to be set (no device read of near / far).  The next forward()
+        with the same tensors consumes the result without a host wait; the reference has no counterpart (its query blocks)."""
+        if self.near_far is None:
+            raise RuntimeError("prefetch_query needs net.near_far = (near, far) as python floats")
+        self.neural_points.prefetch({"raydir": raydir, "campos": campos, "camrotc2w": camrotc2w}, self.near_far[0], self.near_far[1])
+
     def _probe_outputs(self, output, weight, conf_coefficient, sample_pidx, sample_loc_w):
         """the eight extra tensors point growing reads when opt.prob == 1 (:394-425); plain tensor ops
         on our kernels' outputs -- not a hot path (runs every prob_freq=10000 iterations)."""

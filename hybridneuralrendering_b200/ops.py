@@ -544,8 +544,8 @@ class NbrMlpTrainFn(torch.autograd.Function):
                                       i64_array([mlp_tc.X0_IMG_W, HID, HID, HID]), i64_array([0, 0, mlp_tc.E_IMG_W, 0]),
                                       ptr_array([gw[0], gw[1], gw[2], gw[3]]), i64_array([WG_LDO] * 4), mlp_tc.rows_padded(rows), stream()),
                   "wgrad_img")
-        idx, mask = _x0_cols(dev)
-        dW1 = torch.zeros((HID, X0_W), device=dev, dtype=torch.float32).index_copy_(1, idx, gw[0][:, :mlp_tc.X0_IMG_W][:, mask])
+        ref_idx, kern_idx = _x0_cols(dev)
+        dW1 = torch.zeros((HID, X0_W), device=dev, dtype=torch.float32).index_copy_(1, ref_idx, gw[0].index_select(1, kern_idx))
         db1 = gw[0][:, mlp_tc.X0_IMG_W]
         dW2, db2 = gw[1][:, :HID], gw[1][:, HID]
         dW3 = torch.cat([gw[2][:, :HID], gw[2][:, HID:HID + E_W]], dim=1)
@@ -559,7 +559,7 @@ class NbrMlpTrainFn(torch.autograd.Function):
             with _launch(name="nbr_features_bwd"):
                 check(lib().hnr_nbr_features_bwd_ld(ptr(dX0), X0_GRAD_W, ptr(dE), ptr(emb), ptr(pidx), None, ptr(vlist), ptr(raydirs),
                                                     ptr(ctx.cam), Nv, K, ptr(d_emb), ptr(d_col), ptr(d_dir), stream()), "nbr_features_bwd_ld")
-        return (d_emb, d_col, d_dir, d_confc, dW1, db1, dW2, db2, dW3, db3, dW4, db4, d_wa.view(ctx.shapes[3]), d_ba.view(ctx.shapes[4]), None)
+        return (d_emb, d_col, d_dir, d_confc, dW1, db1, dW2, db2, dW3, db3, dW4, db4, d_wa.clone().view(ctx.shapes[3]), d_ba.clone().view(ctx.shapes[4]), None)
 
 
 WG_LDO = 320          # row stride of the weight-gradient scratch of hnr_wgrad_img (>= 288 + 16 + 1)
@@ -567,13 +567,14 @@ _X0_COLS = {}
 
 
 def _x0_cols(dev):
-    """(reference column of every real kernel-order column of the layer-0 input, mask of the real columns), cached per device"""
+    """(reference column, kernel-order column) of every real column of the layer-0 input, cached per device (index tensors, not a
+    boolean mask: mask indexing reads its count back from the device, i.e. a host synchronisation in the middle of backward)"""
     key = str(dev)
     if key not in _X0_COLS:
         from . import mlp_tc
         cols = mlp_tc.layer1_column_order_f16()
         _X0_COLS[key] = (torch.tensor([c for c in cols if c >= 0], device=dev, dtype=torch.long),
-                         torch.tensor([c >= 0 for c in cols], device=dev, dtype=torch.bool))
+                         torch.tensor([k for k, c in enumerate(cols) if c >= 0], device=dev, dtype=torch.long))
     return _X0_COLS[key]
 
 

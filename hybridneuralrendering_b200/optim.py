@@ -41,4 +41,6 @@ class FusedAdam(torch.optim.Optimizer):
                     check(lib().hnr_adam_step(ptr(p), ptr(g), ptr(st["exp_avg"]), ptr(st["exp_avg_sq"]), p.numel(), float(group["lr"]),
                                               float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]), int(st["step"]),
                                               stream()), "adam_step")
+                # the kernel writes through the raw pointer: tell autograd / the version-keyed caches (voxel grid, packed weights)
+                torch.autograd.graph.increment_version(p)
         return loss

@@ -121,14 +121,18 @@ def allreduce_gradients(params: Iterable[torch.nn.Parameter], n_local_valid: tor
 
 
 def train_step(net, frame_shard: Dict[str, torch.Tensor], optimizers: Sequence[torch.optim.Optimizer], group=None,
-               zero_one_weight: float = 1e-4):
+               zero_one_weight: float = 1e-4, next_frame_shard: Optional[Dict[str, torch.Tensor]] = None):
     """one data-parallel training step on this rank's ray shard: forward (fused hot path), loss, backward,
-    gradient all-reduce with global-mean normalisation, optimiser steps.  Returns (loss, n_global_valid)."""
+    gradient all-reduce with global-mean normalisation, optimiser steps.  Returns (loss, n_global_valid).
+    `next_frame_shard`: the shard of the NEXT step, if known -- its voxel query is enqueued before this step's backward pass
+    so that the next forward does not stall at the query's read-back (NeuralPointsRayMarching.prefetch_query)."""
     from .renderer import training_loss
     for o in optimizers:
         o.zero_grad(set_to_none=True)
     out = net(**frame_shard)
     n_local = (out["ray_mask"] > 0).sum()
+    if next_frame_shard is not None and getattr(net, "near_far", None) is not None:
+        net.prefetch_query(**next_frame_shard)
     if out["coarse_raycolor"].shape[1] > 0:
         loss = training_loss(out, frame_shard["gt_image"], zero_one_weight)
         loss.backward()

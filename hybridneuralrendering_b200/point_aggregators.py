@@ -255,18 +255,19 @@ class PointAggregator(nn.Module):
                                                self.alpha_branch[0].weight, self.alpha_branch[0].bias)
         elif self.mlp_engine == "tc" and torch.is_grad_enabled() and K == 8 and mask is None and self.fused_train_forward:
             # training: the same fused kernel, with the four layers' activations saved for the tensor-core backward
+            tp = self._train_packs()
             with ops.tag("nbr_mlp"):
                 if self.fused_backward:
                     sigma, X5 = ops.NbrMlpTrainFn.apply(emb, color, dirs, confc, b1[0].weight, b1[0].bias, b1[2].weight, b1[2].bias,
                                                         b3[0].weight, b3[0].bias, b3[2].weight, b3[2].bias, self.alpha_branch[0].weight,
                                                         self.alpha_branch[0].bias,
                                                         (xyz, xyz_pers, pidx, vlist, loc_w, loc_pers, raydirs, cam, weight,
-                                                         self._packed_weights(), self._packed_weights_bwd()))
+                                                         tp.nbr_pack, tp.nbr_packT))
                 else:
                     sigma, X5 = ops.NbrMlpFusedFn.apply(emb, color, dirs, confc, b1[0].weight, b1[0].bias, b1[2].weight, b1[2].bias,
                                                         b3[0].weight, b3[0].bias, b3[2].weight, b3[2].bias, self.alpha_branch[0].weight,
                                                         self.alpha_branch[0].bias,
-                                                        (xyz, xyz_pers, pidx, vlist, loc_w, loc_pers, raydirs, cam, weight, self._packed_weights()))
+                                                        (xyz, xyz_pers, pidx, vlist, loc_w, loc_pers, raydirs, cam, weight, tp.nbr_pack))
         else:
             with ops.tag("gather"):
                 X0, E = ops.NbrFeaturesFn.apply(emb, color, dirs, xyz, xyz_pers, pidx, mask, vlist, loc_w, loc_pers, raydirs, cam)
@@ -290,10 +291,10 @@ class PointAggregator(nn.Module):
         fused_t = self.mlp_engine == "tc" and torch.is_grad_enabled() and self.fused_train_forward and Nv >= 128
         if fused_t:
             from . import chain
-            TS = chain.TRAIN_WEIGHT_SCALE
+            tp = self._train_packs()
             with ops.tag("sample_mlp"):
-                pc = chain.packed_chain(self, "cf_t", [cf[0], cf[2], cf[4]], [ACT_LRELU] * 3, X5_W, weight_scale=TS)
-                g = chain.chain_train(pc, [cf[0], cf[2], cf[4]], [ACT_LRELU] * 3, [X5])[0]
+                # dX5: only the 256 K-sum columns carry a gradient (the last 24 are the view-direction encoding)
+                g = chain.chain_train(tp.pc["cf"], [cf[0], cf[2], cf[4]], [ACT_LRELU] * 3, [X5], pb=tp.pb["cf"])[0]
         elif not fused:
             with ops.tag("sample_mlp"):
                 g = ops.linear([X5], cf[0].weight, cf[0].bias, ACT_LRELU)
@@ -320,9 +321,8 @@ class PointAggregator(nn.Module):
             with ops.tag("sample_mlp"):
                 if fused_t:
                     c0 = self._AM_COLS0                                                  # kernel source order [g | aux | dview]
-                    pc = chain.packed_chain(self, "am_t", [am[0], am[2], am[4]], [ACT_LRELU] * 3, 176, cols0=c0, weight_scale=TS)
-                    sig = chain.chain_train(pc, [am[0], am[2], am[4]], [ACT_LRELU] * 3, [g, aux.view(V * Nv, 45), dv], M=V * Nv,
-                                            mods=(Nv, 0, 0), head=(am[6], ACT_SIGMOID), cols0=c0)[1]
+                    sig = chain.chain_train(tp.pc["am"], [am[0], am[2], am[4]], [ACT_LRELU] * 3, [g, aux.view(V * Nv, 45), dv], M=V * Nv,
+                                            mods=(Nv, 0, 0), head=(am[6], ACT_SIGMOID), cols0=c0, pb=tp.pb["am"])[1]
                 else:
                     t = ops.linear([aux.view(V * Nv, 45), g, dv], am[0].weight, am[0].bias, ACT_LRELU, mods=(0, Nv, 0), M=V * Nv)
                     t = ops.linear([t], am[2].weight, am[2].bias, ACT_LRELU)
@@ -341,8 +341,7 @@ class PointAggregator(nn.Module):
                                         cols0=list(range(45)) + [-1] * 3 + list(range(45, 90)) + [-1] * 3)
                 m = chain.chain_forward(pc, [g[:, :ops.AUX_LD], merged], res=gi)[0]
             elif fused_t:
-                pc = chain.packed_chain(self, "cm_t", [cm[0], cm[2], cm[4]], [ACT_LRELU, ACT_LRELU, ACT_NONE], 90, weight_scale=TS)
-                m = chain.chain_train(pc, [cm[0], cm[2], cm[4]], [ACT_LRELU, ACT_LRELU, ACT_NONE], [gi, merged], res=gi)[0]
+                m = chain.chain_train(tp.pc["cm"], [cm[0], cm[2], cm[4]], [ACT_LRELU, ACT_LRELU, ACT_NONE], [gi, merged], res=gi, pb=tp.pb["cm"])[0]
             else:
                 m = ops.linear([gi, merged], cm[0].weight, cm[0].bias, ACT_LRELU)
                 m = ops.linear([m], cm[2].weight, cm[2].bias, ACT_LRELU)
@@ -353,22 +352,21 @@ class PointAggregator(nn.Module):
     _AM_COLS0 = list(range(45, 173)) + list(range(45)) + [173, 174, 175]        # blend-weight net, kernel source order [g | aux | dview]
 
     def prepack(self):
-        """Re-pack the tensor-core weight images of a graph-recording forward NOW (they are cached by parameter version, so the
-        forward then finds them ready).  The conductor calls this BEFORE the query: the ~150 small packing launches that follow
-        every optimiser step are then issued while the GPU still executes the previous step's backward, instead of after the
-        query's read-back, where the GPU idles until the host has caught up."""
-        if not (torch.is_grad_enabled() and self.mlp_engine == "tc" and self.fused_train_forward and int(self.opt.K) == 8):
-            return
-        from . import chain
-        TS = chain.TRAIN_WEIGHT_SCALE
-        self._packed_weights()
-        if self.fused_backward:
-            self._packed_weights_bwd()
-        cf, am, cm = self.color_feature_branch, self.aux_merge_weight_block, self.color_mixup_block
-        chain.packed_chain(self, "cf_t", [cf[0], cf[2], cf[4]], [ACT_LRELU] * 3, X5_W, weight_scale=TS)
-        if int(self.opt.use_nearest) > 0:
-            chain.packed_chain(self, "am_t", [am[0], am[2], am[4]], [ACT_LRELU] * 3, 176, cols0=self._AM_COLS0, weight_scale=TS)
-        chain.packed_chain(self, "cm_t", [cm[0], cm[2], cm[4]], [ACT_LRELU, ACT_LRELU, ACT_NONE], 90, weight_scale=TS)
+        """Bring the tensor-core weight images of a graph-recording forward up to date NOW (one launch, packer.TrainPacker).  The
+        conductor calls this BEFORE the query so that the launch is issued while the GPU still executes the previous step."""
+        if torch.is_grad_enabled() and self.mlp_engine == "tc" and self.fused_train_forward and int(self.opt.K) == 8:
+            self._train_packs()
+
+    def _train_packs(self):
+        """packs of the training forward / backward (built once with the tensor-op packers, then refreshed by ONE kernel launch
+        whenever a parameter version changed)"""
+        from .packer import TrainPacker
+        tp = getattr(self, "_tp", None)
+        if tp is None or not tp.current(self, self.fused_backward):
+            tp = self._tp = TrainPacker(self, self.fused_backward)
+        else:
+            tp.refresh()
+        return tp
 
     def prepare_views(self, img_n, c2w_n):
         """query-independent part of the image branch (feature pyramid I1, world->camera matrices of the reference views),

@@ -184,7 +184,7 @@ class lighting_fast_querier:
                 pidx_full=torch.empty((R, SR, K), **i32), nsamp=torch.empty(R, **i32), nvalid=torch.empty(R, **i32),
                 keep=torch.empty(R, **i32), ray_off=torch.empty(R + 1, **i32), val_off=torch.empty(R + 1, **i32),
                 scratch=torch.empty(int(lib().hnr_scan_scratch_elems(R)) + 1, **i32), counts=torch.empty(2, **i32),
-                counts_host=torch.empty(2, dtype=torch.int32).pin_memory(),
+                counts_host=[torch.empty(2, dtype=torch.int32).pin_memory() for _ in range(2)],
             )
             self._bufs = {key: b}          # keep only the latest shape
         return b
@@ -193,6 +193,14 @@ class lighting_fast_querier:
                      near_depth, far_depth, ray_dirs_tensor, cam_pos_tensor, cam_rot_tensor, ts: Optional[torch.Tensor] = None):
         """Same arguments as the reference (:80); `ts` optionally overrides the candidate parameters
         (tests feed the oracle and this kernel the same floats)."""
+        return self.query_finish(self.query_launch(point_xyz_w_tensor, near_depth, far_depth, ray_dirs_tensor, cam_pos_tensor, cam_rot_tensor, ts))
+
+    def query_launch(self, point_xyz_w_tensor, near_depth, far_depth, ray_dirs_tensor, cam_pos_tensor, cam_rot_tensor,
+                     ts: Optional[torch.Tensor] = None) -> dict:
+        """first half of query_points: enqueue the query kernels and the read-back of the two output counts, WITHOUT waiting for
+        them.  A training loop launches the query of the NEXT frame before it issues the current frame's backward pass
+        (NeuralPointsRayMarching.prefetch_query): the read-back has long completed when the next forward asks for it, so the host
+        never idles the GPU at the query's synchronisation point."""
         opt = self.opt
         near, far = float(np.asarray(near_depth).item()), float(np.asarray(far_depth).item())
         G = self._ensure_grid(point_xyz_w_tensor)
@@ -224,12 +232,23 @@ class lighting_fast_querier:
                               ptr(b["nvalid"]), ptr(b["keep"]), ptr(b["ray_off"]), ptr(b["val_off"]), ptr(b["scratch"]), ptr(out_pidx),
                               ptr(out_loc_pers), ptr(out_loc_w), ptr(out_dirs), ptr(ray_mask), ptr(ray_ids), ptr(vlist), ptr(b["counts"]),
                               stream()), "query")
-        b["counts_host"].copy_(b["counts"], non_blocking=True)
+        # two pinned read-back slots alternate: a prefetched query may still be pending when the next one is launched
+        self._slot = 1 - getattr(self, "_slot", 0)
+        host = b["counts_host"][self._slot]
+        host.copy_(b["counts"], non_blocking=True)
         ops.status_fetch_async(dev)                                # range guard of the previous frame's tensor-core kernels rides along
-        torch.cuda.current_stream().synchronize()                  # the single readback of this call
-        ops.status_check(dev)
-        Rk, Nv = int(b["counts_host"][0]), int(b["counts_host"][1])
-        self.last = QueryExtras(vlist=vlist[:Nv], ray_ids=ray_ids[:Rk], n_rays=Rk, n_valid=Nv)
+        ev = torch.cuda.Event()
+        ev.record()
+        return dict(event=ev, host=host, G=G, dev=dev, out=(out_pidx, out_loc_pers, out_loc_w, out_dirs, ray_mask), vlist=vlist, ray_ids=ray_ids)
+
+    def query_finish(self, p: dict):
+        """second half of query_points: wait for the read-back (the single host synchronisation of a query) and cut the outputs"""
+        p["event"].synchronize()
+        ops.status_check(p["dev"])
+        Rk, Nv = int(p["host"][0]), int(p["host"][1])
+        out_pidx, out_loc_pers, out_loc_w, out_dirs, ray_mask = p["out"]
+        G = p["G"]
+        self.last = QueryExtras(vlist=p["vlist"][:Nv], ray_ids=p["ray_ids"][:Rk], n_rays=Rk, n_valid=Nv)
         self.count += 1
         return (out_pidx[:Rk][None], out_loc_pers[:Rk][None], out_loc_w[:Rk][None], out_dirs[:Rk][None], ray_mask[None],
                 G.vsize_np, G.ranges_np)

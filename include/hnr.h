@@ -210,6 +210,29 @@ int hnr_dz_extras_bwd(const void* dz, const float* W, int64_t ldw, int64_t k0, i
  * (csrc/wgrad_img.cu).  Job i: out[i] (256, ldo[i]) += [dZ^T X | dZ^T E | dZ^T 1]. */
 int hnr_wgrad_img(int njob, const void* const* a, const void* const* b, const void* const* e, const int64_t* cb, const int64_t* ce,
                   float* const* out, const int64_t* ldo, int64_t rows_pad, void* stream);
+/* generic form: per-job dZ width ca[i] (the layer's padded output width, <= 256) and row count rows_pad[i] */
+int hnr_wgrad_img_jobs(int njob, const void* const* a, const int64_t* ca, const void* const* b, const void* const* e, const int64_t* cb,
+                       const int64_t* ce, float* const* out, const int64_t* ldo, const int64_t* rows_pad, void* stream);
+/* Fused training path of the per-sample chains (color_feature_branch, aux_merge_weight_block, color_mixup_block;
+ * point_aggregators.py:1028-1037, :1188-1217, :1285-1334).  hnr_chain_f16_forward_train = hnr_chain_f16_forward that also saves
+ * the concatenated input (x0img, Kp[0] columns) and the inner outputs (himg[l], Np[l] columns) as split images;
+ * hnr_chain_bwd_f16 (csrc/chain_bwd_f16.cu) = fused data-gradient chain: dZ_top = dY * act'(Ytop), dZ_{l-1} = (dZ_l W_l) *
+ * act'(H_{l-1}), dX = dZ_0 W_0[:, :NX]; every dZ_l is also written as a split image for hnr_wgrad_img_jobs. */
+int hnr_chain_f16_forward_train(const float* const* src, const int64_t* src_ld, const int64_t* src_k, const int64_t* src_mod,
+                                float in_scale, int nlayer, const int64_t* Kp, const int64_t* N, const int64_t* Np, const int* act,
+                                const void* wpack, const int64_t* w_off, const float* bias, const float* mul, const float* inv_next,
+                                float* const* Y, const int64_t* ldy, const float* res, int64_t ldres, const float* head_w,
+                                const float* head_b, int head_act, float* head_out, int64_t M, int32_t* status, void* x0img,
+                                void* const* himg, void* stream);
+int hnr_chain_bwd_f16(int nlayer, const int64_t* Np, const int64_t* N, int64_t NX, int act_top, const float* dY, int64_t lddy,
+                      const float* Ytop, int64_t ldyt, const void* const* gimg, void* const* dzimg, const void* wpackT,
+                      const int64_t* w_off, float* dX, int64_t ldx, int64_t M, void* stream);
+/* One-launch re-packing of every weight image of the training step (csrc/pack.cu): device-resident job tables built by
+ * hybridneuralrendering_b200/packer.py (struct layouts there and in pack.cu; sizes exported for the consistency check). */
+int64_t hnr_pack_job_bytes(void);
+int64_t hnr_bias_job_bytes(void);
+int hnr_pack_weights(const void* jobs, int64_t njobs, int64_t total_pieces, const void* bias_jobs, int64_t nbias, int32_t* status,
+                     void* stream);
 int hnr_nbr_features_bwd_ld(const float* dX0, int64_t ldx, const float* dE, const float* emb, const int32_t* pidx, const uint8_t* mask,
                             const int32_t* vlist, const float* raydirs, const float* cam, int64_t Nv, int64_t K, float* d_emb,
                             float* d_color, float* d_dir, void* stream);

@@ -21,11 +21,12 @@ def main():
     ap.add_argument("--points", type=int, default=2_000_000)
     ap.add_argument("--views", type=int, default=8)
     ap.add_argument("--json", default=None)
+    ap.add_argument("--no-prefetch", action="store_true", help="do not launch the next step's voxel query ahead (A/B of the software pipelining)")
     args = ap.parse_args()
     from hybridneuralrendering_b200.benchmarks import train_step_benchmark
     dev = torch.device("cuda:0")
     torch.cuda.set_device(dev)
-    line = train_step_benchmark(dev, args.steps, args.warmup, points=args.points, views=args.views)
+    line = train_step_benchmark(dev, args.steps, args.warmup, points=args.points, views=args.views, prefetch=not args.no_prefetch)
     print(json.dumps(line))
     if args.json:
         with open(args.json, "w") as f:

@@ -190,3 +190,111 @@ def test_fused_backward_equals_layered_backward():
     for k in ga:
         a, b = ga[k].double(), gb[k].double()
         assert float((a - b).abs().max()) <= TOL * float(b.abs().max()) + 1e-30, (k, float((a - b).abs().max()), float(b.abs().max()))
+
+
+@pytest.mark.parametrize("M,ks,widths,acts,mods,res,head,cols0,nx", [
+    (1000, (280,), (128, 128, 128), (1, 1, 1), None, False, False, None, 256),                 # colour-feature branch (dX5: 256 columns)
+    (4 * 777, (128, 45, 3), (64, 64, 64), (1, 1, 1), (777, 0, 0), False, True, "am", 176),   # blend-weight net + sigmoid head, V = 4
+    (5000, (45, 45), (45, 45, 45), (1, 1, 0), None, True, False, None, 96),                   # mix-up block + residual
+    (128 * 150 + 7, (128,), (128, 64), (1, 1), None, False, False, None, 128),
+])
+def test_chain_train_fused_backward_matches_fp64(M, ks, widths, acts, mods, res, head, cols0, nx):
+    """ChainFn with the fused backward (chain_bwd_f16 + wgrad_img) vs fp64 autograd: source, weight and bias gradients"""
+    from hybridneuralrendering_b200 import chain
+    T = torch.from_numpy
+    rng = np.random.default_rng(M)
+    K = sum(ks)
+    nrows = [mods[i] if mods and mods[i] else M for i in range(len(ks))]
+    srcs = [T(rng.standard_normal((nrows[i], k)).astype(np.float32)).cuda().requires_grad_(True) for i, k in enumerate(ks)]
+    layers, kin = [], K
+    for w in widths:
+        lin = torch.nn.Linear(kin, w).cuda()
+        with torch.no_grad():
+            lin.weight.copy_(T((rng.standard_normal((w, kin)) * (1.5 / np.sqrt(kin))).astype(np.float32)))
+            lin.bias.copy_(T((rng.standard_normal(w) * 0.1).astype(np.float32)))
+        layers.append(lin)
+        kin = w
+    hl = None
+    if head:
+        hl = torch.nn.Linear(widths[-1], 1).cuda()
+    # kernel source order of the blend-weight net: the reference concatenates [aux 45 | g 128 | dview 3], the kernel reads [g | aux | dview]
+    c0 = None
+    order = list(range(len(ks)))
+    if cols0 == "am":
+        c0 = list(range(45, 173)) + list(range(45)) + [173, 174, 175]
+        order = [1, 0, 2]                                            # reference concat order of the kernel's sources
+    # ---- fp64 reference
+    sd = [s.detach().double().requires_grad_(True) for s in srcs]
+    Wd = [(l.weight.detach().double().requires_grad_(True), l.bias.detach().double().requires_grad_(True)) for l in layers]
+    full = lambda s: s if s.shape[0] == M else s.repeat(M // s.shape[0], 1)
+    x = torch.cat([full(sd[i]) for i in order], 1)
+    pre = []
+    for (W, b), a in zip(Wd, acts):
+        x = torch.nn.functional.linear(x, W, b)
+        pre.append(x)
+        x = [x, torch.nn.functional.leaky_relu(x, 0.01), torch.sigmoid(x)][a]
+    if res:
+        x = x + sd[0][:, :widths[-1]]
+    gy = T(rng.standard_normal((M, widths[-1])).astype(np.float32)).cuda()
+    # LeakyReLU' jumps at 0: drop the upstream gradient of rows with a pre-activation within rounding noise of 0 anywhere
+    safe = torch.ones(M, dtype=torch.bool, device="cuda")
+    for p_, a in zip(pre, acts):
+        if a == 1:
+            safe &= (p_.detach().abs() > 1e-4).all(dim=1)
+    if head:
+        hd = (hl.weight.detach().double().requires_grad_(True), hl.bias.detach().double().requires_grad_(True))
+        out = torch.sigmoid(torch.nn.functional.linear(x, *hd))
+        gh = T(rng.standard_normal((M, 1)).astype(np.float32)).cuda() * safe[:, None].float()
+        out.backward(gh.double())
+    else:
+        gy = gy * safe[:, None].float()
+        x.backward(gy.double())
+    # ---- product
+    owner = torch.nn.Module()
+    with torch.enable_grad():
+        pc = chain.PackedChain(layers, acts, K, cols0=c0, weight_scale=chain.TRAIN_WEIGHT_SCALE)
+        pb = chain.PackedChainBwd(layers, pc, nx, cols0=c0)
+        y, h = chain.chain_train(pc, layers, list(acts), srcs, M=M, mods=mods or (), res=srcs[0][:, :widths[-1]] if res else None,
+                                 head=(hl, 2) if head else None, cols0=c0, pb=pb)
+        (h if head else y).backward(gh if head else gy)
+    tol = lambda r: 1e-4 * float(r.abs().max())
+    for i, (a, r) in enumerate(zip(srcs, sd)):
+        if r.grad is None:
+            continue
+        if cols0 == "am" and i == 2:
+            continue                                 # the view-direction difference carries no gradient in the model (column 176+ not computed)
+        ncol = a.grad.shape[1]
+        got, ref = a.grad.double(), r.grad
+        if M == 1000 and ncol == 280:                # only the first 256 columns of dX5 are computed
+            got, ref = got[:, :256], ref[:, :256]
+        assert float((got - ref).abs().max()) <= tol(ref), ("src", i, float((got - ref).abs().max()), tol(ref))
+    for l, (lin, (W, b)) in enumerate(zip(layers, Wd)):
+        assert float((lin.weight.grad.double() - W.grad).abs().max()) <= tol(W.grad), ("W", l)
+        assert float((lin.bias.grad.double() - b.grad).abs().max()) <= tol(b.grad), ("b", l)
+
+
+def test_one_launch_repack_equals_tensor_op_packers():
+    """packer.TrainPacker: after the weights change, ONE kernel launch must reproduce bit for bit what the tensor-op packers
+    (mlp_tc.pack_mlp_f16 / pack_mlp_bwd, chain.PackedChain / PackedChainBwd) build from scratch"""
+    from hybridneuralrendering_b200 import PointAggregator, chain
+    from hybridneuralrendering_b200.packer import TrainPacker
+    torch.manual_seed(1)
+    agg = PointAggregator(make_opt("scannet", use_nearest=4, is_train=True)).cuda()
+    with torch.enable_grad():
+        tp = TrainPacker(agg, True)
+        assert tp.current(agg, True)
+        before = tp.nbr_pack[0].clone()
+        with torch.no_grad():
+            for p in agg.parameters():
+                p.add_(torch.randn_like(p) * 0.05)               # an "optimiser step" (bumps the versions)
+        tp.refresh()
+        ref = TrainPacker(agg, True)                             # fresh build with the tensor-op packers
+    assert not torch.equal(before, tp.nbr_pack[0])
+    assert torch.equal(tp.nbr_pack[0], ref.nbr_pack[0]) and torch.equal(tp.nbr_pack[1], ref.nbr_pack[1])
+    assert torch.equal(tp.nbr_packT, ref.nbr_packT)
+    for k in tp.pc:
+        assert torch.equal(tp.pc[k].wpack, ref.pc[k].wpack), k
+        assert torch.equal(tp.pc[k].bias, ref.pc[k].bias), k
+        assert torch.equal(tp.pb[k].wpack, ref.pb[k].wpack), k
+    torch.cuda.synchronize()
+    assert int(ops.status_word(torch.device("cuda"))[0]) == 0
