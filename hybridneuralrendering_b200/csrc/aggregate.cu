@@ -372,17 +372,28 @@ __global__ void conf_bwd_kernel(const float* __restrict__ d_wc, const float* __r
     if (w == 0.f) return;
     atomicAdd(&d_conf[max(pidx[s * K + k], 0)], d_wc[i] * w);
 }
-__global__ void conf_up_bwd_kernel(const float* __restrict__ d_confc, const int32_t* __restrict__ pidx, int64_t n,
-                                   float* __restrict__ d_conf) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool in = i < n;
-    const float g = in ? d_confc[i] : 0.f;
-    const int p = in ? pidx[i] : 0;
-    // masked slots (pidx < 0) all alias point 0: one atomic per warp instead of one per slot (hundreds of thousands of
-    // same-address atomics serialise)
-    const float gm = warp_sum(p < 0 ? g : 0.f);
-    if ((threadIdx.x & 31) == 0 && gm != 0.f) atomicAdd(&d_conf[0], gm);
-    if (p >= 0 && g != 0.f) atomicAdd(&d_conf[p], g);
+__global__ void __launch_bounds__(256) conf_up_bwd_kernel(const float* __restrict__ d_confc, const int32_t* __restrict__ pidx, int64_t n,
+                                                          float* __restrict__ d_conf) {
+    // masked slots (pidx < 0) all alias point 0 (clamp(pidx, 0), neural_points.py:711): hundreds of thousands of terms for ONE address.
+    // They are summed in double per thread (grid-stride) and per block, one atomic per block: neither serialised same-address
+    // atomics nor the fp32 rounding of a 300k-term running sum (7e-4 relative at the shipped shapes)
+    double gm = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float g = d_confc[i];
+        const int p = pidx[i];
+        if (p < 0) gm += (double)g;
+        else if (g != 0.f) atomicAdd(&d_conf[p], g);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) gm += __shfl_xor_sync(0xffffffffu, gm, o);
+    __shared__ double red[8];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = gm;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        if (t != 0.0) atomicAdd(&d_conf[0], (float)t);
+    }
 }
 
 // ------------------------------------------------------------------ P1: projection into the reference views
@@ -714,7 +725,9 @@ extern "C" int hnr_conf_bwd(const float* d_wc, const float* weight, const int32_
         HNR_CHECK_LAUNCH("conf_bwd");
     }
     if (S > 0 && d_confc) {
-        conf_up_bwd_kernel<<<(unsigned)hnr_cdiv(S * K, 256), 256, 0, (cudaStream_t)stream>>>(d_confc, pidx, S * K, d_conf);
+        int64_t nb = hnr_cdiv(S * K, 256 * 8);
+        if (nb > 2 * HNR_NUM_SMS) nb = 2 * HNR_NUM_SMS;
+        conf_up_bwd_kernel<<<(unsigned)(nb < 1 ? 1 : nb), 256, 0, (cudaStream_t)stream>>>(d_confc, pidx, S * K, d_conf);
         HNR_CHECK_LAUNCH("conf_up_bwd");
     }
     return HNR_OK;

@@ -144,3 +144,73 @@ def test_image_gather_equals_interpolate_then_lookup():
     aux, ok = ops.ImageGatherFn.apply(levels[0], levels[1], levels[2], levels[3], cuda(xy), vlist)
     np.testing.assert_array_equal(ok.cpu().numpy(), (~bad).astype(np.float32))
     assert_close(aux, ref, 1e-5, 1e-6)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# shipped shapes: goldens of the unmodified reference at SR 80 / V 4 (eval) and SR 24 / V 8 / 7_8_1_8 / drop 0.5 (training, with
+# the misaligned out-of-range patch drop of SURVEY B.16), thousands of valid samples, point tables as leaves
+# ---------------------------------------------------------------------------------------------------------------------
+def _tables_case(G):
+    R, SR, V, H, W, is_train, seed, N = [int(x) for x in G["meta"]]
+    d = syn.render_stage_inputs(seed=seed, N=N, R=R, SR=SR, K=8, V=V, H=H, W=W, empty_frac=float(G["empty_frac"]))
+    return d, syn.gather_neighbours(d), (R, SR, V, H, W, bool(is_train), seed)
+
+
+def _run_dropin_tables(agg, d, g, grad):
+    tab = {k: cuda(d[k]).clone().requires_grad_(grad) for k in ("emb", "color", "dir", "conf")}
+    idx = cuda(np.maximum(d["sample_pidx"], 0)).long()
+    out = agg(tab["color"][idx], torch.eye(3).cuda(), tab["dir"][idx], tab["conf"][idx], tab["emb"][idx], cuda(g["sampled_xyz_pers"]),
+              cuda(g["sampled_xyz"]), cuda(g["sample_pnt_mask"]), cuda(d["sample_loc"]), cuda(d["sample_loc_w"]), cuda(d["sample_ray_dirs"]),
+              d["vsize"], 0, img_n=cuda(d["images_nearest"]), sample_loc_i_n=cuda(d["sample_loc_i_n"]), delta_viewdir_n=cuda(d["delta_viewdir_n"]))
+    return out, tab
+
+
+def test_dropin_forward_matches_reference_golden_shipped_eval_shape():
+    from hybridneuralrendering_b200.diff_ray_marching import ray_march_from_depth
+    G = load_golden("agg_eval_sr80")
+    d, g, (R, SR, V, H, W, is_train, seed) = _tables_case(G)
+    assert (SR, V) == (80, 4) and int(G["ray_valid"].sum()) >= 2000
+    agg = build_aggregator(ro.random_params(seed + 100), use_nearest=V, is_train=False)
+    with torch.no_grad():
+        (decoded, valid, w, cc), _ = _run_dropin_tables(agg, d, g, False)
+        color, opacity, *_ = ray_march_from_depth(cuda(d["sample_loc"]), valid, decoded, float(d["vsize"][2]), 1, torch.ones(1, 3).cuda())
+    np.testing.assert_array_equal(valid.cpu().numpy(), G["ray_valid"])
+    assert_close(decoded, G["decoded"], RTOL, 1e-6)
+    assert_close(color, G["ray_color"], RTOL, 1e-6)
+    assert_close(opacity, G["opacity"], RTOL, 2e-7)
+
+
+def test_dropin_train_step_matches_reference_golden_shipped_train_shape():
+    from hybridneuralrendering_b200.diff_ray_marching import ray_march_from_depth
+    G = load_golden("agg_train_sr24")
+    d, g, (R, SR, V, H, W, is_train, seed) = _tables_case(G)
+    assert (SR, V, str(G["dilation_setup"])) == (24, 8, "7_8_1_8") and int(G["ray_valid"].sum()) >= 2000
+    agg = build_aggregator(ro.random_params(seed + 100), use_nearest=V, is_train=True, drop_ratio=float(G["drop_ratio"]),
+                           dilation_setup=str(G["dilation_setup"]))
+    (decoded, valid, w, cc, _), tab = _run_dropin_tables(agg, d, g, True)
+    assert_close(decoded, G["decoded"], RTOL, 1e-6)
+    color, opacity, *_ = ray_march_from_depth(cuda(d["sample_loc"]), valid, decoded, float(d["vsize"][2]), 1, torch.ones(1, 3).cuda())
+    assert_close(color, G["ray_color"], RTOL, 1e-6)
+    v = cc.clamp(1e-3, 1 - 1e-3)
+    # rays with a hidden unit on a LeakyReLU kink in the reference's forward are masked out of the colour loss (make_golden._fragile_rays)
+    keep = cuda(G["keep"])
+    loss = torch.nn.functional.mse_loss(color * keep, cuda(G["gt"]) * keep) + 1e-4 * torch.mean(torch.log(v) + torch.log(1 - v))
+    assert_close(loss, G["loss"], 1e-5, 0)
+    loss.backward()
+    for k, t in tab.items():
+        ref, got = G["gradT_" + k], t.grad
+        if k == "conf":
+            # conf[0] receives the regulariser's gradient of all ~310k MASKED slots (they alias point 0, neural_points.py:711); the
+            # reference adds them one by one in fp32 and lands 8.5e-4 away from the fp64 value (-4.33799e-4; product: 1e-4 away)
+            assert abs(float(got[0]) - float(ref[0])) <= 2e-3 * abs(float(ref[0]))
+            ref, got = ref[1:], got[1:]
+        assert_close(got, ref, RTOL, grad_atol(ref), k)
+    n = 0
+    for k, p in agg.named_parameters():
+        key = "gradP_" + k
+        if key not in G:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+            continue
+        assert_close(p.grad, G[key], RTOL, grad_atol(G[key]), k)          # rtol 1e-4 + 1e-4 x max magnitude (north_star)
+        n += 1
+    assert n >= 40
