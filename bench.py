@@ -2,12 +2,17 @@
 """bench.py -- headline benchmark of the per-ray sample pipeline (contract: task prompt ④).
 
     python bench.py --gpus N --steps K --warmup W            # product arm (one rank per GPU under torchrun for N>1)
-    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port), rank 0 only
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own training step on the host cores, rank 0 only
 
-N=1 workload = BASELINE.json configs[1]: NeRF-synthetic lego-shaped full-frame render 800x800,
-synthetic 1M neural points (voxel query + aggregation + compositing).  metric: render Mpix/s.
-One step = one full frame.  N>1: frames are independent units -> each rank renders its own frame
-(weak scaling, no data-path collective); value = frames of all ranks / max-over-ranks time.
+Headline (the half of BASELINE.json's metric that north_star sets its targets on): **train rays/s (fwd+bwd)** on configs[2] --
+ScanNet scene0241_01-shaped hybrid training step, 640x480 frames, 4096-ray batch (8x8 dilated patches of 8x8), 8 reference-view
+feature maps, 2M neural points.  One step = forward + loss + backward (+ NCCL gradient all-reduce for N > 1) + Adam of the network
+and of the point tables.  N > 1 is data parallel exactly as north_star describes it: the point cloud, grid, weights are replicated,
+every rank trains on its OWN 4096-ray raster (weak scaling), the gradients of the MLPs and of the dense point tables (39 floats x
+2M points = 312 MB) are all-reduced over NCCL, overlapped with the next forward's query / pyramid / packing.
+Also reported in the same JSON line: `render` (configs[1]: 800x800 full-frame render, Mpix/s, N = 1), `train_blur*` (configs[3]),
+`large_scene` (configs[4]: 8M points, 1296x968 frames, 1.25 GB of point gradients per all-reduce; every N), `cpu_baseline` and
+`reference_gpu` (the unmodified reference's training step on the host cores / on the same B200).
 """
 import argparse
 import json
@@ -27,17 +32,21 @@ H = W = 800
 N_POINTS = 1_000_000
 V = 4
 CHUNK = None          # whole frame per query (one host readback per frame)
-WORKLOAD = "NeRF-synthetic lego-shaped full-frame render 800x800, synthetic 1M neural points (voxel query + aggregation + compositing)"
-CPU_SAMPLE_RAYS = 20480      # 160 x 128 window at the image centre: ~12 s of host work per pass on 16 threads
-CPU_CHUNK_RAYS = 1024         # walked in chunks (the reference's own frame driver renders chunk by chunk, train_ft.py:282-351)
+RENDER_WORKLOAD = "NeRF-synthetic lego-shaped full-frame render 800x800, synthetic 1M neural points (voxel query + aggregation + compositing)"
+FLOP_NBR_FWD = 542_720                                   # per valid neighbour row, SURVEY.md 8d
+FLOP_NBR_DGRAD = 2 * (3 * 256 * 256 + 256 * 224)         # dZ_3 -> dZ_2 -> dZ_1 -> dZ_0 -> dX0 (224 needed input columns)
+BYTES_WGRAD_ROW = 4 * (4 * 256 + 288 + 256 + 272 + 256)  # every dZ / input image read once, 4 bytes per element
 
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    d, kind = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
     if os.path.exists(p):
-        d = json.load(open(p))
-        return d, "measured"
-    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+        d, kind = json.load(open(p)), "measured"
+    t = os.path.join(ROOT, "profiles", "r2_tf32_peak.json")            # scripts/measure_tf32_peak.py on this pool's B200
+    if os.path.exists(t):
+        d = dict(d, **{k: v for k, v in json.load(open(t)).items() if k.startswith("tf32_")})
+    return d, kind
 
 
 class ClockSampler:
@@ -98,147 +107,108 @@ class ClockSampler:
         sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows if len(r) > 2 + i)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].replace(".", "").isdigit() else None,
+        # median over the samples taken under load (idle samples between steps sit at the idle clock)
+        hot = [x for x in sm if x >= 0.6 * max(sm)] if sm else []
+        return {"sm_mhz": hot[len(hot) // 2] if hot else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].replace(".", "").isdigit() else None,
                 "reasons": reasons, "samples": len(self.rows)}
 
 
-def build_scene(seed):
+# ======================================================================================================================
+# reference arm / cpu_baseline / reference_gpu: the reference's own training step (oracle/reference_pipeline.py)
+# ======================================================================================================================
+def train_scene(views=8, points=2_000_000):
+    from hybridneuralrendering_b200 import make_opt
     from hybridneuralrendering_b200 import synthetic as syn
-    xyz = syn.lego_scene(N_POINTS, seed)
-    att = syn.point_attributes(np.random.default_rng(seed), len(xyz))
-    fr = syn.lego_frame(H=H, W=W, V=V, seed=seed)
-    return xyz, att, fr
+    from hybridneuralrendering_b200.synthetic import point_attributes
+    opt = make_opt("scannet", use_nearest=views, SR=24, is_train=True, drop_ratio=0.5, dilation_setup="8_8_1_8", max_o=1_000_000)
+    xyz = syn.room_scene(points, 0)
+    att = point_attributes(np.random.default_rng(0), len(xyz))
+    fr = syn.room_frame(H=480, W=640, V=views, patch_num=8, patch_size=8, seed=0)
+    return opt, xyz, att, fr
 
 
-def build_net(xyz, att, dev, P):
-    from hybridneuralrendering_b200 import NeuralPoints, NeuralPointsRayMarching, PointAggregator, make_opt
-    opt = make_opt("lego", use_nearest=V, is_train=False)
-    c = lambda a: torch.from_numpy(a).to(dev)
-    pts = NeuralPoints(32, len(xyz), opt, dev)
-    pts.set_points(c(xyz), c(att["emb"])[None], points_color=c(att["color"])[None], points_dir=c(att["dir"])[None],
-                   points_conf=c(att["conf"])[None], parameter=True)
-    agg = PointAggregator(opt).to(dev)
-    agg.load_state_dict(P, strict=False)
-    net = NeuralPointsRayMarching(aggregator=agg, neural_points=pts, opt=opt).to(dev)
-    net.near_far = (2.0, 6.0)
-    return net, opt
+def reference_step_times(device: str, rays: int, repeats: int, warmup: int):
+    """times the reference's training step on the first `rays` rays (whole 8x8 patches) of the headline's 4096-ray raster.
+    -> dict(rays/s over fwd+bwd of aggregation+compositing, with the query reported next to it)"""
+    from oracle import reference_pipeline as rp
+    from oracle import render_oracle as ro
+    opt, xyz, att, fr = train_scene()
+    # whole patch ROWS of the raster: the first `rays` rays of the (64 x 64)-pixel patch raster
+    ids = np.arange(min(rays, fr["raydir"].shape[1]))
+    # the reference's patch drop indexes the raster of the WHOLE batch (point_aggregators.py:1222-1237): on a sub-sample of the rays
+    # its positions fall outside the compacted ray array, so the sample runs without the drop (the dropped rays cost the same)
+    st = rp.ReferenceStep(xyz, att, fr, opt, ro.random_params(0), device, ray_ids=ids, drop_ratio=0.0)
+    tq = st.query()
+    f, b = [], []
+    for i in range(warmup + repeats):
+        tf, tb, kept, loss = st.fwd_bwd()
+        if i >= warmup:
+            f.append(tf); b.append(tb)
+    tf, tb = float(np.mean(f)), float(np.mean(b))
+    return {"rays": int(len(ids)), "kept_rays": kept, "s_fwd": tf, "s_bwd": tb, "s_query": tq, "value": len(ids) / (tf + tb), "value_with_query": len(ids) / (tf + tb + tq),
+            "kind": rp.kind(), "query": st.query_kind, "loss": loss}
 
 
+def run_reference(args, rank):
+    """--impl reference: the reference's own implementation of the path on the box's host cores, all threads, the headline's
+    metric / unit / workload; each step = fwd+bwd of a bounded sample of the 4096-ray batch."""
+    if rank != 0:
+        return
+    from hybridneuralrendering_b200.benchmarks import TRAIN_WORKLOAD
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    rays = 1024 if cores >= 8 else 512            # ~2-3 s of host work per step: the K+W run ends within a few minutes
+    r = reference_step_times("cpu", rays, args.steps, args.warmup)
+    sample = (f"first {r['rays']} rays (16 whole patches of the 4096-ray raster, {r['kept_rays']} hit the scene) per step: PointAggregator.forward + ray_dist "
+              f"+ ray_march + loss + backward ({r['kind']}: {'unmodified reference classes' if r['kind'] == 'reference' else 'oracle port'}), torch {torch.__version__} "
+              f"CPU fp32, {cores} threads; fwd {r['s_fwd']:.2f} s + bwd {r['s_bwd']:.2f} s per step; the voxel query is not in the metric "
+              f"(the reference has no CPU query; {r['query']} took {r['s_query']:.2f} s incl. its per-call grid build)")
+    line = {"impl": "reference", "metric": "train rays/s (fwd+bwd)", "value": r["value"], "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": (r["s_fwd"] + r["s_bwd"]) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": {"workload": TRAIN_WORKLOAD, "sample": sample},
+            "cpu_baseline": {"value": r["value"], "unit": "rays/s", "cores": cores, "kind": r["kind"], "sample": sample},
+            "e2e": {"value": r["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ======================================================================================================================
+# configs[1]: full-frame render (N = 1 only; frames are independent units, no collective)
+# ======================================================================================================================
 FRAME_KEYS = ("campos", "camrotc2w", "raydir", "near", "far", "intrinsic", "bg_color", "images_nearest", "c2w_nearest", "campos_nearest",
               "intrinsic_nearest")
 
 
-def cpu_reference_sample(P, xyz, att, fr, opt, q_np, n_threads):
-    """the reference's CPU path for aggregation + compositing (oracle port of PointAggregator.forward,
-    the ray_dist prologue and ray_march), timed on a bounded sample of the frame's kept rays."""
-    from oracle import pipeline_oracle as po
-    from oracle import render_oracle as ro
-    torch.set_num_threads(n_threads)
-    cfg = ro.AggCfg(use_nearest=V)
-    n = int(q_np["sample_pidx"].shape[1])
-    pts = dict(xyz=xyz, **att)
-    out = None
-    t0 = time.perf_counter()
-    with torch.no_grad():
-        for r0 in range(0, n, CPU_CHUNK_RAYS):
-            qc = {k: q_np[k][:, r0:r0 + CPU_CHUNK_RAYS] for k in ("sample_pidx", "sample_loc", "sample_loc_w", "sample_ray_dirs")}
-            out = po.render_from_query(P, cfg, pts, qc, fr, float(opt.vsize[2]))
-    dt = time.perf_counter() - t0
-    return out, dt
-
-
-def run_reference(args, rank):
-    """--impl reference: the reference's own CPU implementation of the path (oracle port; the Python
-    reference cannot travel to the GPU box), all host threads, bounded sample per step."""
-    if rank != 0:
-        return
-    from oracle import render_oracle as ro
-    dev = torch.device("cuda:0") if torch.cuda.is_available() else None
-    xyz, att, fr = build_scene(0)
-    P = ro.random_params(0)
-    cores = os.cpu_count() or 1
-    q_np, n_sample = sample_query(xyz, att, fr, P, dev)
-    times = []
-    for i in range(args.warmup + args.steps):
-        _, dt = cpu_reference_sample(P, xyz, att, fr, make_opt_lego(), q_np, cores)
-        if i >= args.warmup:
-            times.append(dt)
-    t = float(np.mean(times))
-    val = n_sample / t / 1e6
-    line = {"impl": "reference", "metric": "render Mpix/s", "value": val, "unit": "Mpix/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": WORKLOAD, "sample": f"{n_sample} kept rays of the frame (aggregation+compositing on CPU; query results precomputed)"},
-            "cpu_baseline": {"value": val, "unit": "Mpix/s", "cores": cores, "kind": "port", "sample": f"{n_sample} kept rays, torch {torch.__version__} CPU fp32"},
-            "e2e": {"value": val, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line))
-
-
-def make_opt_lego():
-    from hybridneuralrendering_b200 import make_opt
-    return make_opt("lego", use_nearest=V, is_train=False)
-
-
-def sample_query(xyz, att, fr, P, dev):
-    """query tensors (numpy) for a bounded sample of rays around the image centre.  The reference has no
-    CPU query (its query is CUDA only), so the sample's neighbour lists come from the product query on the
-    GPU when one is present, else from the numpy oracle on a smaller sample."""
-    yy, xx = np.meshgrid(np.arange(H // 2 - 80, H // 2 + 80), np.arange(W // 2 - 64, W // 2 + 64), indexing="ij")
-    ids = (yy * W + xx).reshape(-1)[:CPU_SAMPLE_RAYS]
-    sub = dict(fr, raydir=fr["raydir"][:, ids])
-    opt = make_opt_lego()
-    if dev is not None:
-        net, _ = build_net(xyz, att, dev, P)
-        c = lambda a: torch.from_numpy(a).to(dev)
-        inputs = {"raydir": c(sub["raydir"]), "campos": c(fr["campos"]), "camrotc2w": c(fr["camrotc2w"])}
-        pidx, loc, loc_w, dirs, mask, _, _ = net.neural_points.query(inputs, near=2.0, far=6.0)
-        q = dict(sample_pidx=pidx.cpu().numpy(), sample_loc=loc.cpu().numpy(), sample_loc_w=loc_w.cpu().numpy(), sample_ray_dirs=dirs.cpu().numpy())
-        del net
-        torch.cuda.empty_cache()
-    else:
-        from oracle import query_oracle as qo
-        ids = ids[:64]
-        sub = dict(fr, raydir=fr["raydir"][:, ids])
-        ts = qo.candidate_ts(int(opt.z_depth_dim), 2.0, 6.0)[0, 0]
-        q = qo.query(xyz, fr["campos"], fr["camrotc2w"], sub["raydir"], ts, vsize=opt.vsize, vscale=opt.vscale, kernel_size=opt.kernel_size,
-                     query_size=opt.query_size, ranges=opt.ranges, radius_limit_scale=opt.radius_limit_scale, SR=opt.SR, K=opt.K, P=opt.P)
-    return q, int(q["sample_pidx"].shape[1])
-
-
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="product")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-train", action="store_true", help="skip the training-step half of the metric")
-    args = ap.parse_args()
-    rank = int(os.environ.get("RANK", 0))
-    world = int(os.environ.get("WORLD_SIZE", 1))
-    local = int(os.environ.get("LOCAL_RANK", 0))
-    if args.impl == "reference":
-        run_reference(args, rank)
-        return
-    import torch.distributed as dist
-    from hybridneuralrendering_b200 import ops
+def render_benchmark(dev, steps, warmup, pk):
+    from hybridneuralrendering_b200 import NeuralPoints, NeuralPointsRayMarching, PointAggregator, make_opt, ops, profiling
+    from hybridneuralrendering_b200 import synthetic as syn
     from hybridneuralrendering_b200.renderer import render_rays
-    from oracle import render_oracle as ro          # only for the seeded weights + the cpu_baseline leg
-
-    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback of the product path)"
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    xyz, att, fr = build_scene(rank)               # every rank renders its own view of its own replica
-    P = ro.random_params(0)
-    net, opt = build_net(xyz, att, dev, P)
+    xyz = syn.lego_scene(N_POINTS, 0)
+    att = syn.point_attributes(np.random.default_rng(0), len(xyz))
+    fr = syn.lego_frame(H=H, W=W, V=V, seed=0)
+    opt = make_opt("lego", use_nearest=V, is_train=False)
+    c = lambda a: torch.from_numpy(a).to(dev)
+    pts = NeuralPoints(32, len(xyz), opt, dev)
+    t0 = time.perf_counter()
+    pts.set_points(c(xyz), c(att["emb"])[None], points_color=c(att["color"])[None], points_dir=c(att["dir"])[None],
+                   points_conf=c(att["conf"])[None], parameter=True)
+    torch.manual_seed(0)
+    agg = PointAggregator(opt).to(dev)
+    agg.load_state_dict(syn.random_aggregator_params(0), strict=False)
+    net = NeuralPointsRayMarching(aggregator=agg, neural_points=pts, opt=opt).to(dev)
+    net.near_far = (2.0, 6.0)
     host = {k: torch.from_numpy(np.ascontiguousarray(fr[k])).pin_memory() for k in FRAME_KEYS}
     resident = {k: v.to(dev) for k, v in host.items()}
     img = torch.empty((H * W, 3), device=dev)
     img_host = torch.empty((H * W, 3)).pin_memory()
-    h2d = sum(v.numel() * v.element_size() for v in host.values())
-    d2h = img_host.numel() * 4
-    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)        # > 126 MB L2
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+    # grid build: once per point set (amortised, not in the Mpix/s), reported separately (SURVEY 8d)
+    torch.cuda.synchronize()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    pts.querier._ensure_grid(pts.xyz[None, ...])
+    g1.record()
+    torch.cuda.synchronize()
+    grid_ms = g0.elapsed_time(g1)
 
     def step_resident():
         render_rays(net, resident, CHUNK, out=img)
@@ -248,82 +218,164 @@ def main():
         render_rays(net, f, CHUNK, out=img)
         img_host.copy_(img, non_blocking=True)
 
-    def barrier():
+    def timed(fn, n):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
         torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    def timed(fn, steps):
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        barrier()
         for s, e in ev:
             flush.zero_()
             s.record()
             fn()
             e.record()
-        barrier()
-        ms = sum(s.elapsed_time(e) for s, e in ev)
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()) / 1e3
+        torch.cuda.synchronize()
+        return sum(s.elapsed_time(e) for s, e in ev) / 1e3
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step_resident()
     ops.LAUNCHES = 0
-    with ClockSampler(local) as clk:
-        t_res = timed(step_resident, args.steps)
+    t_res = timed(step_resident, steps)
     launches = ops.LAUNCHES
-    for _ in range(max(1, args.warmup // 2)):
-        step_e2e()
-    t_e2e = timed(step_e2e, args.steps)
+    step_e2e()
+    t_e2e = timed(step_e2e, steps)
     mpix = H * W / 1e6
-    value = world * args.steps * mpix / t_res
-    e2e = world * args.steps * mpix / t_e2e
+    roof = profiling.dominant_kernel_roofline(net, resident, CHUNK, pk)
+    roof["step"] = profiling.step_roofline(roof["units"], V, H * W, int(opt.z_depth_dim), int(opt.SR), H, W, t_res / steps * 1e3, pk[0])
+    return {"metric": "render Mpix/s", "value": steps * mpix / t_res, "unit": "Mpix/s", "ms_per_frame": t_res / steps * 1e3,
+            "e2e": {"value": steps * mpix / t_e2e, "unit": "Mpix/s", "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in host.values()),
+                    "d2h_bytes_per_step": img_host.numel() * 4},
+            "grid_build_ms": grid_ms, "grid_build_note": "occupancy-grid build of the 1M points, once per point-set change (the reference rebuilds per forward)",
+            "gpu_launches": launches, "roofline": roof,
+            "config": {"workload": RENDER_WORKLOAD, "rays_per_step": H * W, "chunk_rays": CHUNK or H * W, "valid_samples_per_pass": agg.max_valid_chunk,
+                       "use_nearest": V, "SR": int(opt.SR), "K": int(opt.K), "l2": "flushed between frames (256 MB write)"}}
 
-    # roofline of the dominant kernel: the per-neighbour MLP (4 dense layers, 542,720 FLOP per neighbour row)
-    from hybridneuralrendering_b200 import profiling
-    roof = profiling.dominant_kernel_roofline(net, resident, CHUNK, peaks())
-    # whole-step roofline as SURVEY.md 8(d) defines it (sum over stages of max(bytes/HBM, FLOPs/tensor peak) / measured time)
-    roof["step"] = profiling.step_roofline(roof["units"], V, H * W, int(opt.z_depth_dim), int(opt.SR), H, W, t_res / args.steps * 1e3, peaks()[0])
 
-    line = {"metric": "render Mpix/s", "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": t_res / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": H * W, "chunk_rays": CHUNK or H * W, "valid_samples_per_pass": net.aggregator.max_valid_chunk, "use_nearest": V, "SR": int(opt.SR), "K": int(opt.K),
-                       "l2": "flushed between steps (256 MB write)", "mlp_engine": "tc (3xFP16 tcgen05 fused kernels)",
-                       "parallelism": f"{world} independent frame(s), one per GPU"},
-            "e2e": {"value": e2e, "unit": "Mpix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": launches, "clocks": clk.summary(), "roofline": roof}
-    # second half of BASELINE.json's metric: train rays/s (fwd+bwd) on configs[2]; under torchrun every rank trains on its own
-    # 4096-ray batch and the gradients are all-reduced over NCCL (weak scaling), time = max over ranks
-    if not args.no_train:
-        from hybridneuralrendering_b200.benchmarks import train_step_benchmark
-        del net, resident, flush
+def train_kernel_rooflines(tr, pk):
+    """roofline records of the three big kernels of the fused training path from the per-launch CUDA events of one step"""
+    peaks_d, kind = pk
+    M, rows = tr["valid_neighbours"], tr["valid_samples"] * 8
+    rows_pad = (rows + 127) // 128 * 128
+    tens = peaks_d["bf16_tflops_sustained"] / 3.0
+    st = tr["stage_ms"]
+    out = []
+
+    def rec(name, tag, bound, work, peak, unit, note):
+        ms = st.get(tag)
+        if not ms:
+            return
+        ach = work / (ms * 1e-3) / (1e12 if bound == "tensor" else 1e9)
+        out.append({"kernel": name, "bound": bound, "ms": ms, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak, "work_per_launch": work, "note": note})
+
+    rec("nbr_mlp_f16_kernel<2> (fused per-neighbour forward, training mode: saves its operands as split images)", "nbr_mlp", "tensor",
+        FLOP_NBR_FWD * M, tens, "TFLOP/s", "542,720 FLOP x valid neighbours; peak = bf16_tflops_sustained/3 (3 f16 MMAs per fp32-accurate product)")
+    rec("nbr_bwd_f16_kernel (fused data-gradient chain dZ_3 -> dX0)", "backward/nbr_bwd_chain", "tensor", FLOP_NBR_DGRAD * M, tens, "TFLOP/s",
+        "2*(3*256*256 + 256*224) FLOP x valid neighbours; peak = bf16_tflops_sustained/3 (3 bf16 MMAs per product)")
+    ws = st.get("backward/wgrad_img")
+    if ws:
+        # three wgrad_img launches per step (per-neighbour MLP + three chains); the per-neighbour one dominates: attribute by bytes
+        v, nv = tr["views"], tr["valid_samples"]
+        chain_bytes = 4 * (nv * (3 * 128 + 288 + 128 + 128) + v * nv * (3 * 64 + 176 + 64 + 64) + nv * (3 * 48 + 96 + 48 + 48))
+        work = BYTES_WGRAD_ROW * rows_pad + chain_bytes
+        ach = work / (ws * 1e-3) / 1e9
+        out.append({"kernel": "wgrad_img_kernel (all weight/bias gradients from MN-major slab images, 4 launches per step)", "bound": "hbm", "ms": ws,
+                    "achieved": ach, "peak": peaks_d["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks_d["hbm_gbs"], "work_per_launch": work,
+                    "note": "every dZ / input image read once (4 B per element); the two 128-row halves of a layer re-read the input image through L2"})
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="product")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-render", action="store_true", help="skip the configs[1] full-frame render (N = 1)")
+    ap.add_argument("--no-large", action="store_true", help="skip configs[4] (8M points)")
+    ap.add_argument("--no-extras", action="store_true", help="skip configs[3] (blur) and the reference_gpu leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    import torch.distributed as dist
+    from hybridneuralrendering_b200 import benchmarks, profiling
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback of the product path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    pk = peaks()
+    steps, warmup = max(3, args.steps), max(3, args.warmup)
+
+    # ---------------------------------------------------------------- headline: configs[2] training step
+    with ClockSampler(local) as clk:
+        tr = benchmarks.train_step_benchmark(dev, steps=steps, warmup=warmup, world=world, rank=rank, stage_split=(world == 1))
+    roofs = train_kernel_rooflines(tr, pk) if world == 1 else []
+    top = max(roofs, key=lambda r: r["ms"]) if roofs else None
+    # whole-step roofline (SURVEY 8d) against fwd+bwd time: backward on the f16 pipe like the forward (3 bf16 MMAs per product)
+    step_roof = profiling.step_roofline(tr, tr["views"], tr["rays_per_step_per_gpu"], 400, 24, 480, 640, tr["ms_fwd_bwd"], pk[0], train=True,
+                                        points=tr["points"])
+    line = {"metric": "train rays/s (fwd+bwd)", "value": tr["value"], "unit": "rays/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": tr["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": benchmarks.TRAIN_WORKLOAD, "rays_per_step_per_gpu": tr["rays_per_step_per_gpu"], "points": tr["points"], "views": tr["views"],
+                       "SR": 24, "K": 8, "step": tr["step"], "l2": "flushed between steps (256 MB write)",
+                       "query": "the next step's voxel query is launched one step ahead (one query per step, software-pipelined)",
+                       "mlp_engine": "3xFP16 tcgen05 fused forward, 3xBF16 tcgen05 fused backward (split images)",
+                       "parallelism": (f"dp{world}: point cloud / grid / weights replicated, every rank its own 4096-ray raster, NCCL SUM all-reduce of the MLP bucket "
+                                       "(1.8 MB) and of the dense point-gradient tables (312 MB) overlapped with the next forward's query / pyramid / packing")
+                       if world > 1 else "1 GPU"},
+            "e2e": tr.get("e2e"), "gpu_launches": tr["launches_per_step"] * steps, "clocks": clk.summary(),
+            "train": {k: tr[k] for k in ("ms_per_step", "ms_fwd_bwd", "kept_rays", "valid_samples", "valid_neighbours", "loss", "launches_per_step", "stage_ms")}}
+    if top is not None:
+        line["roofline"] = {"bound": top["bound"], "achieved": top["achieved"], "peak": top["peak"], "unit": top["unit"], "frac": top["frac"],
+                            "traffic": None, "kernel": top["kernel"], "kernel_ms": top["ms"], "note": top["note"],
+                            "peak_source": f"MEASURED_PEAKS.json ({pk[1]}), sustained figures (kernels timed inside a long step)",
+                            "kernels": roofs, "step": step_roof}
+    else:
+        line["roofline"] = {"bound": "tensor", "achieved": None, "peak": None, "unit": "TFLOP/s", "frac": None, "traffic": None,
+                            "note": "per-kernel events are taken at N = 1 only", "step": step_roof}
+    torch.cuda.empty_cache()
+
+    # ---------------------------------------------------------------- configs[4]: 8M points (every N; the 1.25 GB all-reduce)
+    if not args.no_large:
+        lg = benchmarks.train_step_benchmark(dev, steps=min(steps, 10), warmup=3, world=world, rank=rank, stage_split=False, points=8_000_000,
+                                             size=(12.0, 10.0, 3.0), H=968, W=1296, max_o=4_000_000, e2e=False, workload=benchmarks.LARGE_WORKLOAD)
+        line["large_scene"] = {k: lg[k] for k in ("metric", "value", "unit", "ms_per_step", "ms_fwd_bwd", "rays_per_step_per_gpu", "points", "views", "kept_rays",
+                                                  "valid_samples", "step", "config")}
+        line["large_scene"]["n_gpus"] = world
+        line["large_scene"]["allreduce_bytes"] = 39 * 4 * lg["points"] if world > 1 else 0
         torch.cuda.empty_cache()
-        tr = train_step_benchmark(dev, steps=max(3, args.steps), warmup=max(3, args.warmup), world=world, rank=rank, stage_split=(world == 1))
-        tt = torch.tensor([tr["ms_fwd_bwd"]], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        tr["ms_fwd_bwd"] = float(tt.item())
-        tr["value"] = world * tr["rays"] / (tr["ms_fwd_bwd"] * 1e-3)
-        tr["n_gpus"] = world
-        tr["roofline"] = profiling.step_roofline(tr, tr["views"], tr["rays"], 400, 24, 480, 640, tr["ms_fwd_bwd"], peaks()[0], train=True,
-                                                 points=tr["points"])
-        tr["gradient_allreduce"] = "NCCL SUM, dense point gradients + coalesced MLP bucket" if world > 1 else "none (1 GPU)"
-        line["train"] = tr
-        if world == 1:
-            from hybridneuralrendering_b200.benchmarks import blur_train_step_benchmark
+
+    if world == 1:
+        if not args.no_render:
+            line["render"] = render_benchmark(dev, steps, warmup, pk)
             torch.cuda.empty_cache()
-            line["train_blur"] = blur_train_step_benchmark(dev, steps=3, warmup=3)      # BASELINE configs[3]
-            line["train_blur_learnable"] = blur_train_step_benchmark(dev, steps=3, warmup=3, learnable=True)
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        q_np, n_sample = sample_query(xyz, att, fr, P, dev)
-        cores = os.cpu_count() or 1
-        _, dt = cpu_reference_sample(P, xyz, att, fr, opt, q_np, cores)
-        line["cpu_baseline"] = {"value": n_sample / dt / 1e6, "unit": "Mpix/s", "cores": cores, "kind": "port",
-                                "sample": f"{n_sample} kept rays of the same frame, aggregation+compositing (reference's torch CPU path restated), {dt:.1f} s"}
+        if not args.no_extras:
+            line["train_blur"] = benchmarks.blur_train_step_benchmark(dev, steps=3, warmup=3)      # BASELINE configs[3]
+            line["train_blur_learnable"] = benchmarks.blur_train_step_benchmark(dev, steps=3, warmup=3, learnable=True)   # SURVEY 8f N3
+            torch.cuda.empty_cache()
+            try:
+                r = reference_step_times("cuda", 4096, 3, 2)
+                line["reference_gpu"] = {"value": r["value_with_query"], "unit": "rays/s", "value_without_query": r["value"], "kind": r["kind"], "rays": r["rays"],
+                                         "s_query": r["s_query"], "s_fwd": r["s_fwd"], "s_bwd": r["s_bwd"],
+                                         "what": f"the reference's own GPU path on this B200, same 4096-ray batch: {r['query']} (grid rebuilt per call) + "
+                                                 "PointAggregator / ray_march (ATen, cuBLAS fp32) fwd + bwd; no optimiser step"}
+            except Exception as e:      # the comparator must never break the product line
+                line["reference_gpu"] = {"unavailable": repr(e)[:300]}
+            torch.cuda.empty_cache()
+        if not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            try:
+                r = reference_step_times("cpu", 2048 if cores >= 8 else 512, 1, 1)
+                line["cpu_baseline"] = {"value": r["value"], "unit": "rays/s", "cores": cores, "kind": r["kind"],
+                                        "sample": (f"first {r['rays']} rays (whole patches) of the same 4096-ray batch, fwd {r['s_fwd']:.1f} s + bwd {r['s_bwd']:.1f} s of "
+                                                   f"PointAggregator.forward + ray_dist + ray_march + loss + backward, torch {torch.__version__} CPU fp32; query "
+                                                   f"({r['query']}, {r['s_query']:.1f} s) not in the metric")}
+            except Exception as e:
+                line["cpu_baseline"] = {"value": None, "unit": "rays/s", "cores": cores, "kind": "port", "sample": "unavailable: " + repr(e)[:300]}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

@@ -65,6 +65,8 @@ _SIGS = {
     "hnr_linear_tc_bwd_weight": (C.c_int, [vp, i64, vp, i64, C.POINTER(vp), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), vp, vp, i64,
                                            i64, i64, C.c_int, vp]),
     "hnr_adam_step": (C.c_int, [vp, vp, vp, vp, i64, f32c, f32c, f32c, f32c, f32c, i64, vp]),
+    "hnr_adam_multi": (C.c_int, [i64, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), f32c, f32c, f32c, f32c, f32c,
+                                 i64, vp, vp]),
     "hnr_frame_rays": (C.c_int, [vp, i64, i64, i64, i64, i64, vp, vp, C.c_int, vp, vp, vp, vp, vp]),
     "hnr_frame_views": (C.c_int, [vp, vp, i64, i64, vp, vp]),
     "hnr_mlp_tc_packed_bytes": (i64, [i64]),

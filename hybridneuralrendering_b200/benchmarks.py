@@ -13,14 +13,20 @@ from . import ops
 TRAIN_WORKLOAD = "ScanNet scene0241_01-shaped hybrid training step: 640x480 frames, 4096-ray batch, 8 reference-view feature maps, 2M points"
 
 
-def build_train_case(dev, points: int = 2_000_000, views: int = 8, seed: int = 0):
+LARGE_WORKLOAD = "large-scale scene: 8M neural points, 1296x968 frames, 4096-ray rasters sharded across the GPUs with NCCL gradient allreduce over NVLink"
+
+
+def build_train_case(dev, points: int = 2_000_000, views: int = 8, seed: int = 0, size=(6.0, 5.0, 3.0), H: int = 480, W: int = 640,
+                     max_o: int = 1_000_000):
+    """net + frame of a training step: room-shaped point cloud (replicated: the same on every rank), one 4096-ray dilated-patch
+    raster (8x8 patches of 8x8; `seed` moves the patches, i.e. every rank of a data-parallel run gets its own rays)"""
     from . import NeuralPoints, NeuralPointsRayMarching, PointAggregator, make_opt
     from . import synthetic as syn
     opt = make_opt("scannet", use_nearest=views, SR=24, is_train=True, drop_ratio=0.5, dilation_setup="8_8_1_8",
-                   max_o=1_000_000)       # >= occupied voxels of the 2M-point room (generator must respect max_o)
-    xyz = syn.room_scene(points, 0)                        # the point cloud is replicated: same on every rank
+                   max_o=max_o)           # >= occupied voxels of the room (SURVEY.md §8d: generator must respect max_o)
+    xyz = syn.room_scene(points, 0, size=size)
     att = syn.point_attributes(np.random.default_rng(0), len(xyz))
-    fr = syn.room_frame(H=480, W=640, V=views, patch_num=8, patch_size=8, seed=seed)
+    fr = syn.room_frame(H=H, W=W, V=views, patch_num=8, patch_size=8, seed=seed, size=size)
     c = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     pts = NeuralPoints(32, len(xyz), opt, dev)
     pts.set_points(c(xyz), c(att["emb"])[None], points_color=c(att["color"])[None], points_dir=c(att["dir"])[None],
@@ -33,79 +39,132 @@ def build_train_case(dev, points: int = 2_000_000, views: int = 8, seed: int = 0
     return net, frame
 
 
+def make_optimizers(net):
+    """the reference's two Adam groups (mvs_points_volumetric_model.py:94-104: network lr 5e-4, point parameters lr 2e-3), each stepped
+    by ONE multi-tensor launch (optim.FusedAdam)"""
+    from .optim import FusedAdam
+    opt_net = FusedAdam([p for n, p in net.named_parameters() if p.requires_grad and not n.startswith("neural_points.")], lr=5e-4)
+    opt_pts = FusedAdam([p for n, p in net.named_parameters() if p.requires_grad and n.startswith("neural_points.")], lr=2e-3)
+    return [opt_net, opt_pts]
+
+
+def _device_max(ms: float, dev, world: int) -> float:
+    import torch.distributed as dist
+    if world <= 1:
+        return ms
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
 def train_step_benchmark(dev, steps: int = 5, warmup: int = 3, world: int = 1, points: int = 2_000_000, views: int = 8,
-                         rank: int = 0, stage_split: bool = True, prefetch: bool = True) -> Dict:
-    """fwd + loss + bwd (+ gradient all-reduce over NCCL when world > 1) timed with CUDA events; Adam timed separately.
-    Returns a dict; 'value' is THIS rank's rays/s -- the caller aggregates over ranks with the max-over-ranks time."""
+                         rank: int = 0, stage_split: bool = True, prefetch: bool = True, size=(6.0, 5.0, 3.0), H: int = 480, W: int = 640,
+                         max_o: int = 1_000_000, e2e: bool = True, workload: str = TRAIN_WORKLOAD) -> Dict:
+    """One training step = forward + loss + backward (+ NCCL gradient all-reduce when world > 1) + both Adam steps, through
+    parallel.train_step, on this rank's own 4096-ray raster; the next step's voxel query is software-pipelined one step ahead
+    (`prefetch`).  `steps` steps are timed as ONE region between barriers (CUDA events, L2 flushed between steps), max over ranks.
+    Returns a dict; 'value' = rays of ALL ranks / that time."""
     import torch.distributed as dist
     from . import parallel
-    from .renderer import training_loss
-    # weak scaling: every rank gets the SAME amount of work (the same 4096-ray batch; gradients are still all-reduced), so that the
-    # max-over-ranks time measures the collective and not the spread of valid-sample counts between different batches
-    net, frame = build_train_case(dev, points, views, seed=0)
+    net, frame = build_train_case(dev, points, views, seed=rank, size=size, H=H, W=W, max_o=max_o)
     agg = net.aggregator
     R = frame["raydir"].shape[1]
-    params = [p for p in net.parameters() if p.requires_grad]
-    opt_net = torch.optim.Adam([p for n, p in net.named_parameters() if p.requires_grad and not n.startswith("neural_points.")], lr=5e-4)
-    from .optim import FusedAdam
-    opt_pts = FusedAdam([p for n, p in net.named_parameters() if p.requires_grad and n.startswith("neural_points.")], lr=2e-3)
+    opts = make_optimizers(net)
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+    nxt = frame if prefetch else None
 
-    ar = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        parallel.train_step(net, frame, opts, next_frame_shard=nxt)
+    parallel.flush_pending(net)
+    barrier()
+    ops.LAUNCHES = 0
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(steps):
+        flush.zero_()
+        loss, _ = parallel.train_step(net, frame, opts, next_frame_shard=nxt)
+    parallel.flush_pending(net)
+    e.record()
+    barrier()
+    launches = ops.LAUNCHES
+    ms_step = _device_max(s.elapsed_time(e) / steps, dev, world)
+    res = {"metric": "train rays/s (fwd+bwd)", "value": world * R / (ms_step * 1e-3), "unit": "rays/s", "ms_per_step": ms_step,
+           "rays_per_step_per_gpu": R, "points": points, "views": views, "loss": float(loss), "launches_per_step": launches // steps,
+           "step": "forward + loss + backward" + (" + NCCL gradient all-reduce" if world > 1 else "") + " + Adam (network + point tables)",
+           "config": workload}
+    # ---- end to end: the frame dict arrives in pinned host memory every step, the loss goes back to the host every step
+    if e2e:
+        host = {k: v.cpu().pin_memory() for k, v in frame.items() if torch.is_tensor(v)}
+        rest = {k: v for k, v in frame.items() if not torch.is_tensor(v)}
+        up = lambda: dict(rest, **{k: v.to(dev, non_blocking=True) for k, v in host.items()})
+        loss_host = torch.zeros(steps + 2).pin_memory()
+        cur = up()
+        for _ in range(2):
+            n2 = up()
+            parallel.train_step(net, cur, opts, next_frame_shard=n2 if prefetch else None)
+            cur = n2
+        parallel.flush_pending(net)
+        barrier()
+        s.record()
+        for i in range(steps):
+            flush.zero_()
+            n2 = up()                                   # the NEXT step's frame (its query is launched before this step's backward)
+            loss, _ = parallel.train_step(net, cur, opts, next_frame_shard=n2 if prefetch else None)
+            loss_host[i:i + 1].copy_(loss.reshape(1), non_blocking=True)
+            cur = n2
+        parallel.flush_pending(net)
+        e.record()
+        barrier()
+        ms_e2e = _device_max(s.elapsed_time(e) / steps, dev, world)
+        res["e2e"] = {"value": world * R / (ms_e2e * 1e-3), "unit": "rays/s", "ms_per_step": ms_e2e,
+                      "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in host.values())), "d2h_bytes_per_step": 4 + 8,
+                      "what": "frame dict (rays, ground truth, camera, 8 reference views) copied from pinned host memory every step; loss and the "
+                              "query's two counts read back every step"}
+    # ---- where the time goes: per-launch CUDA events of one more step (world == 1 only: the timers serialise nothing but add events)
+    stages = {}
+    if stage_split:
+        barrier()
+        ops.TIMERS = []
+        with ops.tag("step"):
+            parallel.train_step(net, frame, opts, next_frame_shard=nxt)
+        parallel.flush_pending(net)
+        torch.cuda.synchronize()
+        for tg, a, b in ops.TIMERS:
+            tg = tg.split("[")[0]
+            stages[tg] = stages.get(tg, 0.0) + a.elapsed_time(b)
+        ops.TIMERS = None
+    # forward + backward alone (no optimiser), for continuity with round 1's "ms_fwd_bwd"
+    from .renderer import training_loss
+    params = [p for p in net.parameters() if p.requires_grad]
 
     def fwd_bwd():
         for p in params:
             p.grad = None
         out = net(**frame)
-        loss = training_loss(out, frame["gt_image"])
+        l = training_loss(out, frame["gt_image"])
         if prefetch:
-            net.prefetch_query(**frame)       # the NEXT step's voxel query (one query per step, software-pipelined one step ahead)
-        with ops.tag("backward"):
-            loss.backward()
-        if world > 1:
-            ar[0].record()
-            parallel.allreduce_gradients(params, (out["ray_mask"] > 0).sum())
-            ar[1].record()
-        return out, loss
-
-    for _ in range(warmup):
+            net.prefetch_query(**frame)
+        l.backward()
+    for _ in range(2):
         fwd_bwd()
-        opt_net.step(); opt_pts.step()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-          for _ in range(steps)]
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-        torch.cuda.synchronize()
-    ops.LAUNCHES = 0
-    for s, m, e in ev:
+    barrier()
+    s.record()
+    for _ in range(steps):
         flush.zero_()
-        s.record()
-        out, loss = fwd_bwd()
-        m.record()
-        opt_net.step(); opt_pts.step()
-        e.record()
-    torch.cuda.synchronize()
-    launches = ops.LAUNCHES
-    t_fb = sum(s.elapsed_time(m) for s, m, e in ev) / steps
-    t_opt = sum(m.elapsed_time(e) for s, m, e in ev) / steps
-    stages = {}
-    if stage_split:
-        ops.TIMERS = []
         fwd_bwd()
-        torch.cuda.synchronize()
-        for tag, s, e in ops.TIMERS:
-            tag = tag.split("[")[0]
-            stages[tag] = stages.get(tag, 0.0) + s.elapsed_time(e)
-        ops.TIMERS = None
+    e.record()
+    barrier()
+    res["ms_fwd_bwd"] = s.elapsed_time(e) / steps
     ex = net.last_extras
-    if world > 1:
-        torch.cuda.synchronize()
-        stages["allreduce (NCCL + scaling, device time of the last step)"] = ar[0].elapsed_time(ar[1])
-    return {"metric": "train rays/s (fwd+bwd)", "value": R / (t_fb * 1e-3), "unit": "rays/s", "ms_fwd_bwd": t_fb, "ms_adam": t_opt,
-            "rays": R, "kept_rays": int(ex.n_rays), "valid_samples": int(ex.n_valid), "valid_neighbours": agg.last_valid_neighbours(),
-            "points": points, "views": views, "loss": float(loss.detach()), "launches_per_step": launches // steps,
-            "stage_ms": {k: round(v, 3) for k, v in sorted(stages.items())}, "config": TRAIN_WORKLOAD}
+    res.update({"kept_rays": int(ex.n_rays), "valid_samples": int(ex.n_valid), "valid_neighbours": agg.last_valid_neighbours(),
+                "stage_ms": {k: round(v, 3) for k, v in sorted(stages.items())}})
+    return res
 
 
 BLUR_WORKLOAD = "full model with blur handling: 32x32 patch rays (4x4 dilated patches of 8x8) + pre-defined degradation-kernel convolution, fwd+bwd"

@@ -41,7 +41,87 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
     }
 }
 
+// ---- multi-tensor form: one launch for every tensor of a parameter group ----
+constexpr int ADAM_MAX_T = 64;
+struct AdamMulti {
+    float* p[ADAM_MAX_T];
+    const float* g[ADAM_MAX_T];
+    float* m[ADAM_MAX_T];
+    float* v[ADAM_MAX_T];
+    int64_t n[ADAM_MAX_T];
+    int32_t blk0[ADAM_MAX_T + 1];       // first block of tensor t (a block covers 1024 elements)
+    int32_t nt;
+};
+
+__global__ void __launch_bounds__(256) adam_multi_kernel(const __grid_constant__ AdamMulti A, float b1, float b2, float step_size,
+                                                         float inv_bc2_sqrt, float eps, float wd, const int32_t* __restrict__ guard) {
+    // range guard of the split-fp16 forward kernels (ops.status_word): a step whose activations saturated must not be applied.
+    // The host raises at its next synchronisation point; until then the parameters stay untouched.
+    if (guard && *guard != 0) return;
+    int t = 0;
+    for (int q = 1; q < A.nt; ++q)
+        if ((int)blockIdx.x >= A.blk0[q]) t = q;
+    const int64_t n = A.n[t];
+    float* __restrict__ p = A.p[t];
+    const float* __restrict__ g = A.g[t];
+    float* __restrict__ m = A.m[t];
+    float* __restrict__ v = A.v[t];
+    const int64_t i = ((int64_t)(blockIdx.x - A.blk0[t]) * 256 + threadIdx.x) * 4;
+    const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+    if (vec && i + 4 <= n) {
+        const int64_t i4 = i >> 2;
+        float4 pp = reinterpret_cast<float4*>(p)[i4], gg = reinterpret_cast<const float4*>(g)[i4];
+        float4 mm = reinterpret_cast<float4*>(m)[i4], vv = reinterpret_cast<float4*>(v)[i4];
+        float* P = &pp.x; float* G = &gg.x; float* M = &mm.x; float* V = &vv.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float gk = G[k] + wd * P[k];
+            M[k] = M[k] + (1.f - b1) * (gk - M[k]);
+            V[k] = b2 * V[k] + (1.f - b2) * gk * gk;
+            P[k] = P[k] - step_size * (M[k] / (sqrtf(V[k]) * inv_bc2_sqrt + eps));
+        }
+        reinterpret_cast<float4*>(p)[i4] = pp;
+        reinterpret_cast<float4*>(m)[i4] = mm;
+        reinterpret_cast<float4*>(v)[i4] = vv;
+    } else {
+        for (int64_t j = i; j < n && j < i + 4; ++j) {
+            const float gk = g[j] + wd * p[j];
+            const float mj = m[j] + (1.f - b1) * (gk - m[j]);
+            const float vj = b2 * v[j] + (1.f - b2) * gk * gk;
+            m[j] = mj; v[j] = vj;
+            p[j] = p[j] - step_size * (mj / (sqrtf(vj) * inv_bc2_sqrt + eps));
+        }
+    }
+}
+
 }  // namespace
+
+// Adam step over nt <= 64 tensors in ONE launch (same arithmetic as hnr_adam_step; all tensors share the hyper-parameters and the
+// step count).  p/g/m/v/n: HOST arrays of device pointers / element counts.  guard (optional device word): the launch is a no-op
+// when *guard != 0.
+extern "C" int hnr_adam_multi(int64_t nt, float* const* p, const float* const* g, float* const* m, float* const* v, const int64_t* n,
+                              float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step, const int32_t* guard,
+                              void* stream) {
+    HNR_CHECK_ARG(nt >= 0 && nt <= ADAM_MAX_T, "adam_multi: at most 64 tensors per launch");
+    HNR_CHECK_ARG(step >= 1, "adam_multi: step counts from 1");
+    if (nt == 0) return HNR_OK;
+    AdamMulti A{};
+    int64_t blk = 0;
+    for (int t = 0; t < nt; ++t) {
+        A.p[t] = p[t]; A.g[t] = g[t]; A.m[t] = m[t]; A.v[t] = v[t]; A.n[t] = n[t];
+        A.blk0[t] = (int32_t)blk;
+        blk += hnr_cdiv(n[t], 1024);
+        HNR_CHECK_ARG(blk < (1ll << 31), "adam_multi: too many elements");
+    }
+    A.blk0[nt] = (int32_t)blk;
+    A.nt = (int32_t)nt;
+    if (blk == 0) return HNR_OK;
+    const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+    adam_multi_kernel<<<(unsigned)blk, 256, 0, (cudaStream_t)stream>>>(A, beta1, beta2, (float)((double)lr / bc1), (float)(1.0 / sqrt(bc2)), eps,
+                                                                      weight_decay, guard);
+    HNR_CHECK_LAUNCH("adam_multi");
+    return HNR_OK;
+}
 
 // one Adam step over n contiguous fp32 elements (p, g, m, v 16-byte aligned); step = 1-based step count AFTER this update
 extern "C" int hnr_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,

@@ -383,7 +383,8 @@ knn_kernel(const float* __restrict__ sample_loc, const int32_t* __restrict__ nsa
     if (threadIdx.x == 0) nvalid[ray] = s_valid;
 }
 
-// ---- third generation (NOT the default yet: selected with HNR_KNN_V3=1, to be A/B-ed and promoted in round 2) ----
+// ---- third generation: the default since round 2 (A/B on B200: bit-exact in the query suites incl. the comparison with the
+//      reference's own kernels, query stage of the 800x800 frame 6.46 -> 4.96 ms; HNR_KNN_V2=1 selects the batched kernel above) ----
 // The batched kernel above is instruction-issue bound (profiles/r1_knn_batched_ncu.md: IPC 3.2 of 4, ~800 warp instructions
 // per sample).  Two of its biggest items are removed here:
 //   * shell sizes are compile-time for the shipped kernel_size = 3 (shell 0 = the sample's own voxel, shell 1 = the 26
@@ -642,8 +643,8 @@ extern "C" int hnr_query(const float* campos, const float* camrot, const float* 
     ray_select_kernel<<<(unsigned)hnr_cdiv(R * 32, 256), 256, 0, st>>>(campos, raydir, ts, ts_stride, R, (int)D, (int)SR, *g, occ_bits,
                                                                       sample_loc_full, nsamp);
     static const bool knn_per_voxel = getenv("HNR_KNN_PER_VOXEL") != nullptr;      // A/B switch: the first-generation voxel-by-voxel walk
-    static const bool knn_v3 = getenv("HNR_KNN_V3") != nullptr;                    // third generation, not promoted yet (<= 2 shells only)
-    if (knn_v3 && g->layers <= 2)
+    static const bool knn_v2 = getenv("HNR_KNN_V2") != nullptr;                    // A/B switch: second-generation batched walk
+    if (!knn_v2 && !knn_per_voxel && g->layers <= 2)                                // third generation (compile-time shells, <= 2 of them)
         knn_kernel_v3<<<(unsigned)R, 128, 0, st>>>(sample_loc_full, nsamp, R, (int)SR, (int)K, *g, cell_start, (const float4*)pts_sorted,
                                                    pidx_full, nvalid);
     else if (knn_per_voxel)

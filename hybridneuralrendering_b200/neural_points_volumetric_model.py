@@ -36,6 +36,10 @@ class NeuralPointsRayMarching(nn.Module):
         self.opt = opt
         self.neural_points = neural_points
         self.near_far: Optional[tuple] = None     # set to (near, far) floats to skip the per-call D2H read
+        # one-shot callback run after the query and before the first kernel that reads the point tables: a data-parallel training
+        # loop parks its deferred point-table optimiser step here (parallel.train_step), so that the gradient all-reduce of the
+        # previous step overlaps with this forward's packing, pyramid and query
+        self.before_point_read = None
 
     def forward(self, campos, raydir, gt_image=None, bg_color=None, camrotc2w=None, pixel_idx=None, near=None, far=None, focal=None,
                 h=None, w=None, intrinsic=None, aux_image=None, c2w=None, c2w_nearest=None, images_nearest=None, campos_nearest=None,
@@ -54,6 +58,9 @@ class NeuralPointsRayMarching(nn.Module):
         views = self.aggregator.prepare_views(images_nearest, c2w_nearest[0, :V]) if V > 0 else None
         sample_pidx, sample_loc, sample_loc_w, sample_ray_dirs, ray_mask_tensor, vsize, extras = self.neural_points.query(
             inputs, near=None if nf is None else nf[0], far=None if nf is None else nf[1])
+        if self.before_point_read is not None:
+            cb, self.before_point_read = self.before_point_read, None
+            cb()
         decoded, ray_valid, weight, conf_coefficient = self.aggregator.forward_fused(
             self.neural_points, sample_pidx, sample_loc, sample_loc_w, sample_ray_dirs, campos, camrotc2w, extras=extras,
             img_n=images_nearest, c2w_n=None if V == 0 else c2w_nearest[0, :V], intrinsic_n=None if V == 0 else intrinsic_nearest[0],

@@ -75,30 +75,38 @@ def _unflatten_into(flat: torch.Tensor, tensors: Sequence[torch.Tensor]) -> None
         off += n
 
 
-def allreduce_gradients(params: Iterable[torch.nn.Parameter], n_local_valid: torch.Tensor, group=None,
-                        bucket_bytes: int = 64 << 20) -> torch.Tensor:
-    """Scale every existing .grad by n_local/n_global (the global-mean normalisation) and SUM all-reduce
-    them in buckets (small tensors coalesced; tensors >= bucket_bytes reduced in place).  Parameters
-    whose grad is None on this rank (e.g. it saw no valid ray) take part with zeros so the collective
-    sequence is identical on all ranks.  Returns n_global (tensor).  Asynchronous ops are all waited
-    for before returning."""
-    params = [p for p in params if p.requires_grad]
+def global_mean_scale(n_local_valid: torch.Tensor, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(scale, n_global) with scale = n_local / n_global as DEVICE tensors (one scalar all-reduce, no host sync).  Multiplying the
+    local loss (a mean over the local ray-masked rays) by `scale` BEFORE backward makes the SUM of the ranks' gradients the
+    gradient of the global-mean loss -- without a scaling pass over the 39*N-float point-gradient tables afterwards."""
     n_local = n_local_valid.detach().to(torch.float32).reshape(1)
     n_global = n_local.clone()
     dist.all_reduce(n_global, op=dist.ReduceOp.SUM, group=group)
-    scale = n_local / torch.clamp(n_global, min=1.0)
+    return n_local / torch.clamp(n_global, min=1.0), n_global
+
+
+def allreduce_gradients(params: Iterable[torch.nn.Parameter], n_local_valid: Optional[torch.Tensor] = None, group=None,
+                        bucket_bytes: int = 64 << 20, prescaled: bool = False, defer_large: bool = False):
+    """SUM all-reduce every gradient: small tensors coalesced into buckets, tensors >= bucket_bytes reduced in place.  Parameters
+    whose grad is None on this rank (e.g. it saw no valid ray) take part with zeros so the collective sequence is identical on all
+    ranks.  prescaled=False: the gradients are first scaled by n_local/n_global (global-mean normalisation); prescaled=True: the
+    caller already scaled its loss with global_mean_scale().  defer_large=True: the in-place reductions of the large tensors are
+    launched LAST and returned un-waited as [(work, tensor)] -- the caller overlaps them with whatever does not read those
+    gradients (train_step: the MLP optimiser step and the query / pyramid / packing of the next forward).
+    Returns n_global (or None when prescaled) and, with defer_large, the pending list."""
+    params = [p for p in params if p.requires_grad]
+    n_global = None
+    if not prescaled:
+        scale, n_global = global_mean_scale(n_local_valid, group)
     for p in params:
         if p.grad is None:
             p.grad = torch.zeros_like(p)
-        p.grad.mul_(scale.to(p.grad.dtype))
-    small, handles = [], []
-    for p in params:
-        g = p.grad
-        if g.numel() * g.element_size() >= bucket_bytes:
-            handles.append((dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group, async_op=True), None, None))
-        else:
-            small.append(g)
-    # coalesce the small gradients (MLP + conv weights: 449,381 floats = 1.8 MB) into as few buckets as fit
+        if not prescaled:
+            p.grad.mul_(scale.to(p.grad.dtype))
+    small = [p.grad for p in params if p.grad.numel() * p.grad.element_size() < bucket_bytes]
+    large = [p.grad for p in params if p.grad.numel() * p.grad.element_size() >= bucket_bytes]
+    handles = []
+    # small gradients first (MLP + conv weights: 449,381 floats = 1.8 MB): their consumer, the MLP optimiser step, is next in line
     bucket, size = [], 0
     def flush():
         nonlocal bucket, size
@@ -113,36 +121,83 @@ def allreduce_gradients(params: Iterable[torch.nn.Parameter], n_local_valid: tor
         bucket.append(g)
         size += nb
     flush()
+    pending = [(dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group, async_op=True), g) for g in large]
     for h, flat, tensors in handles:
         h.wait()
-        if flat is not None:
-            _unflatten_into(flat, tensors)
+        _unflatten_into(flat, tensors)
+    if defer_large:
+        return n_global, pending
+    for h, _ in pending:
+        h.wait()
     return n_global
 
 
+def flush_pending(net) -> None:
+    """apply a deferred point-table update now (call before evaluating, checkpointing or pruning / growing points)"""
+    cb = getattr(net, "before_point_read", None)
+    if cb is not None:
+        net.before_point_read = None
+        cb()
+
+
 def train_step(net, frame_shard: Dict[str, torch.Tensor], optimizers: Sequence[torch.optim.Optimizer], group=None,
-               zero_one_weight: float = 1e-4, next_frame_shard: Optional[Dict[str, torch.Tensor]] = None):
-    """one data-parallel training step on this rank's ray shard: forward (fused hot path), loss, backward,
-    gradient all-reduce with global-mean normalisation, optimiser steps.  Returns (loss, n_global_valid).
-    `next_frame_shard`: the shard of the NEXT step, if known -- its voxel query is enqueued before this step's backward pass
-    so that the next forward does not stall at the query's read-back (NeuralPointsRayMarching.prefetch_query)."""
+               zero_one_weight: float = 1e-4, next_frame_shard: Optional[Dict[str, torch.Tensor]] = None, large_bytes: int = 64 << 20):
+    """One data-parallel training step on this rank's rays: forward (fused hot path), loss, backward, gradient all-reduce with
+    global-mean normalisation, optimiser steps.  Returns (loss, n_global_valid), both device tensors.
+
+    Every rank must hold WHOLE dilated-patch rasters (its own (PN*PS)^2-ray batch, the unit the reference's patch drop and blur
+    module work on); the global batch is the union of the ranks' rasters.
+    Overlap (world > 1): the loss is pre-scaled by n_local/n_global (no scaling pass over the tables); the small MLP bucket is
+    reduced first and its optimiser stepped at once; the in-place all-reduce of the point tables (39*N floats) is left in flight
+    and the optimiser(s) that own those tables step at the LAST possible moment -- inside the next forward, after its query and
+    pyramid but before the first kernel that reads the tables (`net.before_point_read`), or at flush_pending(net).
+    `next_frame_shard`: the shard of the NEXT step, if known -- its voxel query is enqueued before this step's backward pass so
+    that the next forward does not stall at the query's read-back (NeuralPointsRayMarching.prefetch_query)."""
+    from . import ops
     from .renderer import training_loss
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    opt = getattr(net, "opt", None)
+    if world > 1 and opt is not None and getattr(opt, "is_train", False) and getattr(opt, "drop_ratio", 0) > 0 and getattr(opt, "use_nearest", 0) > 0:
+        toks = str(opt.dilation_setup).split("_")
+        if frame_shard["raydir"].shape[1] != (int(toks[0]) * int(toks[1])) ** 2:
+            raise NotImplementedError("data-parallel training with the patch drop needs whole (PN*PS)^2-ray rasters per rank: the reference's "
+                                      "drop positions (point_aggregators.py:1222-1237) index the raster of ONE batch; give every rank its "
+                                      "own raster instead of slicing one with shard_frame")
     for o in optimizers:
         o.zero_grad(set_to_none=True)
-    out = net(**frame_shard)
+    out = net(**frame_shard)                        # a deferred point update of the previous step is applied inside (before_point_read)
+    flush_pending(net)                               # ... or here, if the forward had nothing to read (no kept ray)
     n_local = (out["ray_mask"] > 0).sum()
+    scale = n_global = None
+    if world > 1:
+        scale, n_global = global_mean_scale(n_local, group)
     if next_frame_shard is not None and getattr(net, "near_far", None) is not None:
         net.prefetch_query(**next_frame_shard)
     if out["coarse_raycolor"].shape[1] > 0:
         loss = training_loss(out, frame_shard["gt_image"], zero_one_weight)
-        loss.backward()
+        with ops.tag("backward"):
+            (loss * scale[0] if scale is not None else loss).backward()
     else:
         loss = torch.zeros((), device=out["ray_mask"].device)
+    if world == 1:
+        for o in optimizers:
+            o.step()
+        return loss.detach(), n_local
     params = [p for o in optimizers for g in o.param_groups for p in g["params"]]
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        n_global = allreduce_gradients(params, n_local, group)
-    else:
-        n_global = n_local
+    is_large = lambda p: p.numel() * p.element_size() >= large_bytes
+    _, pending = allreduce_gradients(params, None, group, bucket_bytes=large_bytes, prescaled=True, defer_large=True)
+    late = [o for o in optimizers if any(is_large(p) for g in o.param_groups for p in g["params"])]
     for o in optimizers:
-        o.step()
+        if o not in late:
+            o.step()
+
+    def apply_late():
+        for h, _ in pending:
+            h.wait()
+        for o in late:
+            o.step()
+    if late and hasattr(net, "before_point_read"):
+        net.before_point_read = apply_late
+    else:
+        apply_late()
     return loss.detach(), n_global

@@ -10,7 +10,7 @@ from . import ops
 from .renderer import render_rays
 
 FLOP_PER_NEIGHBOUR = 542_720            # 2*(284*256 + 256*256 + 263*256 + 256*256 + 256), SURVEY.md §8d
-DRAM_BYTES_PER_LAUNCH_NCU = 330_913_792  # measured, see profiles/r1_nbr_mlp_f16_ncu.md (85.5 MB read + 245.4 MB written)
+DRAM_BYTES_PER_LAUNCH_NCU = 337_587_200  # measured, see profiles/r2_nbr_mlp_f16_ncu.md (90.4 MB read + 247.2 MB written)
 
 
 def stage_times(net, frame, chunk_rays: int) -> Dict[str, float]:
@@ -73,7 +73,7 @@ def dominant_kernel_roofline(net, frame, chunk_rays: int, peaks_and_kind) -> Dic
     return {"bound": "tensor", "kernel": "nbr_mlp_f16_kernel: fused per-neighbour MLP (gather + block1 + block3 + density head + K-sum)",
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
             "traffic": DRAM_BYTES_PER_LAUNCH_NCU, "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch of 262,144 valid "
-            "samples, ncu --set full (profiles/r1_nbr_mlp_f16_ncu.md); algorithmic HBM bytes per launch = 168 B x neighbours in + 1124 B x samples out",
+            "samples, ncu --set full (profiles/r2_nbr_mlp_f16_ncu.md); algorithmic HBM bytes per launch = 168 B x neighbours in + 1124 B x samples out",
             "algorithmic_flop_per_launch": FLOP_PER_NEIGHBOUR * units["valid_neighbours"] / nl if nl else None,
             "peak_basis": basis, "launches": nl, "kernel_ms_per_step": ms, "kernel_ms_per_launch": ms / nl if nl else None,
             "share_of_step": ms / total if total else None,
@@ -88,14 +88,17 @@ def step_roofline(units: Dict[str, int], views: int, rays: int, depth_samples: i
     Bytes and FLOPs per unit are the table of SURVEY.md 8(d) (compulsory traffic only).  Counts: M = valid neighbour rows,
     Nv = valid samples, R'' = kept rays (all measured on this run's inputs).  The candidate-point term `16*Cand` of the neighbour
     search is not counted by the product and is left out, which only LOWERS the roofline time (conservative fraction).
-    Tensor peaks: the fp32-accurate forward runs 3 FP16 MMAs per product (peak = bf16_tflops_sustained / 3), the backward 3 TF32
-    MMAs (TF32 dense = bf16 / 2 -> / 6).  train=True adds the backward rows (FLOPs x2, gather recompute + scatter-add RMW,
+    Tensor peaks: the fp32-accurate forward runs 3 FP16 MMAs per product (peak = bf16_tflops_sustained / 3); since round 2 the fused
+    backward runs on the same kind::f16 pipe (3 BF16 MMAs per product), so its peak is the same -- `frac`.  `frac_tf32_basis` keeps
+    round 1's denominator for the backward (3 TF32 MMAs per product; TF32 dense sustained as MEASURED by scripts/measure_tf32_peak.py
+    when profiles/r2_tf32_peak.json exists, else bf16 / 2) so that the two rounds stay comparable.  train=True adds the backward rows (FLOPs x2, gather recompute + scatter-add RMW,
     image-gather scatter, compositing backward, pyramid dgrad/wgrad) and the dense zero-filled point-gradient tables (39*N floats)."""
     M, Nv, Rk = int(units["valid_neighbours"]), int(units["valid_samples"]), int(units["kept_rays"])
     V = int(views)
     hbm = float(peaks["hbm_gbs"]) * 1e9
     t_fwd = float(peaks["bf16_tflops_sustained"]) / 3.0 * 1e12
-    t_bwd = float(peaks["bf16_tflops_sustained"]) / 6.0 * 1e12
+    t_bwd = t_fwd
+    t_bwd_tf32 = float(peaks.get("tf32_tflops_sustained", float(peaks["bf16_tflops_sustained"]) / 2.0)) / 3.0 * 1e12
     nbr_flop = FLOP_PER_NEIGHBOUR * M
     smp_flop = (154_184 + 39_040 * V) * Nv
     st = {   # stage: (bytes, fwd flops, bwd flops)
@@ -110,13 +113,16 @@ def step_roofline(units: Dict[str, int], views: int, rays: int, depth_samples: i
     }
     if train and points:
         st["dense point-gradient tables (zero fill)"] = (39 * 4 * points, 0, 0)
-    rows, total = {}, 0.0
+    rows, total, total_tf32 = {}, 0.0, 0.0
     for k, (b, f, g) in st.items():
         ms = max(b / hbm, f / t_fwd + g / t_bwd) * 1e3
         rows[k] = {"bytes": int(b), "flop": int(f + g), "roofline_ms": round(ms, 4), "bound": "tensor" if f else "hbm"}
         total += ms
+        total_tf32 += max(b / hbm, f / t_fwd + g / t_bwd_tf32) * 1e3
     return {"definition": "sum over stages of max(bytes / HBM peak, FLOPs / tensor peak) / measured step time (SURVEY.md 8d)",
             "roofline_ms": total, "measured_ms": measured_ms, "frac": total / measured_ms if measured_ms else None,
+            "roofline_ms_tf32_basis": total_tf32, "frac_tf32_basis": total_tf32 / measured_ms if (measured_ms and train) else None,
             "hbm_peak_gbs": peaks["hbm_gbs"], "tensor_peak_fwd_tflops": t_fwd / 1e12, "tensor_peak_bwd_tflops": t_bwd / 1e12,
+            "tensor_peak_bwd_tf32_basis_tflops": t_bwd_tf32 / 1e12,
             "tensor_share_of_roofline": sum(r["roofline_ms"] for r in rows.values() if r["bound"] == "tensor") / total if total else None,
             "stages": rows}

@@ -37,6 +37,14 @@ def render_rays(net, frame: Dict[str, torch.Tensor], chunk_rays: Optional[int] =
             ids = net.last_extras.ray_ids.long()
             if ids.numel():
                 out.index_copy_(0, ids + r0, o["coarse_raycolor"][0])
+    # range guard of the split-fp16 kernels: the queries above only checked the frames BEFORE them; check this frame's last
+    # chunk too (one event wait -- the caller reads the image next anyway), so that a saturated image is never returned silently
+    from . import ops
+    ops.status_fetch_async(dev)
+    ev = torch.cuda.Event()
+    ev.record()
+    ev.synchronize()
+    ops.status_check(dev)
     return out
 
 

@@ -296,6 +296,10 @@ int hnr_blur_learn_bwd(const float* pred, const float* raw, int64_t ld_raw, cons
  * ------------------------------------------------------------------------------------------- */
 int hnr_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                   float weight_decay, int64_t step, void* stream);
+/* the same step over nt <= 64 tensors in one launch (p/g/m/v/n: host arrays); guard: optional device word, the update is skipped
+ * on the device when *guard != 0 (the saturation status of the split-fp16 kernels: a bad step is never applied). */
+int hnr_adam_multi(int64_t nt, float* const* p, const float* const* g, float* const* m, float* const* v, const int64_t* n, float lr,
+                   float beta1, float beta2, float eps, float weight_decay, int64_t step, const int32_t* guard, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Frame-dict producer on the device: the per-item arithmetic of ScannetFtDataset.__getitem__

@@ -12,7 +12,11 @@ import os
 import sys
 import types
 
+# /root/reference where it exists (build container), else the byte-for-byte copy staged by oracle/stage_reference.py (GPU box)
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "pyref")
 REF_ROOT = os.environ.get("HNR_REFERENCE_ROOT", "/root/reference")
+if not os.path.isdir(os.path.join(REF_ROOT, "models", "aggregators")) and os.path.isdir(os.path.join(_STAGED, "models", "aggregators")):
+    REF_ROOT = _STAGED
 
 
 def available() -> bool:

@@ -379,33 +379,6 @@ def blur_predictor_params(seed: int, patch_size: int = 8, kernel_size: int = 9, 
 # ----------------------------------------------------------------------------------------------
 # weights
 # ----------------------------------------------------------------------------------------------
-LAYER_SHAPES = {
-    "block1.0": (256, 284), "block1.2": (256, 256),
-    "block3.0": (256, 263), "block3.2": (256, 256),
-    "alpha_branch.0": (1, 256),
-    "color_feature_branch.0": (128, 280), "color_feature_branch.2": (128, 128), "color_feature_branch.4": (128, 128),
-    "aux_merge_weight_block.0": (64, 176), "aux_merge_weight_block.2": (64, 64),
-    "aux_merge_weight_block.4": (64, 64), "aux_merge_weight_block.6": (1, 64),
-    "color_mixup_block.0": (45, 90), "color_mixup_block.2": (45, 45), "color_mixup_block.4": (45, 45),
-    "color_final_block.0": (3, 128),
-}
-CONV_SHAPES = {
-    "aux_block_s1.0": (6, 3, 3, 3), "aux_block_s1.2": (6, 6, 3, 3),
-    "aux_block_s2.0": (12, 6, 3, 3), "aux_block_s2.2": (12, 12, 3, 3),
-    "aux_block_s3.0": (24, 12, 3, 3), "aux_block_s3.2": (24, 24, 3, 3),
-}
-
-
-def random_params(seed: int = 0, dtype=torch.float32, bias_scale: float = 0.05) -> Dict[str, torch.Tensor]:
-    """Xavier-like random weights with the shipped layer shapes, drawn from a
-    numpy PCG64 stream so the values are stable across torch versions.  Biases are non-zero on
-    purpose so parity tests exercise them."""
-    rng = np.random.default_rng(seed)
-    P = {}
-    for name, shp in {**LAYER_SHAPES, **CONV_SHAPES}.items():
-        fan_out = shp[0] * (int(np.prod(shp[2:])) if len(shp) > 2 else 1)
-        fan_in = int(np.prod(shp[1:]))
-        bound = math.sqrt(2.0) * math.sqrt(6.0 / (fan_in + fan_out))
-        P[name + ".weight"] = torch.from_numpy(((rng.random(shp) * 2 - 1) * bound).astype(np.float32)).to(dtype)
-        P[name + ".bias"] = torch.from_numpy(((rng.random(shp[0]) * 2 - 1) * bias_scale).astype(np.float32)).to(dtype)
-    return P
+# the seeded weight generator lives with the other synthetic-input generators (product side, no oracle import needed by bench.py);
+# re-exported here because the tests and the golden generator call it through the oracle
+from hybridneuralrendering_b200.synthetic import CONV_SHAPES, LAYER_SHAPES, random_aggregator_params as random_params  # noqa: E402,F401

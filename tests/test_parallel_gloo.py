@@ -58,6 +58,40 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
+def _worker_prescaled(rank, world, port, out_dir):
+    """the overlapped form train_step uses: loss pre-scaled by n_local/n_global, small bucket first, large tensors left in flight"""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    params = _toy()
+    idx, gt, valid = _data()
+    b, e = parallel.shard_patches(idx.shape[0], 64, rank, world)
+    n_local = valid[b:e].sum()
+    scale, n_global = parallel.global_mean_scale(n_local)
+    if int(n_local) > 0:
+        (_loss(params, idx[b:e], gt[b:e], valid[b:e]) * scale[0]).backward()
+    _, pending = parallel.allreduce_gradients(params, None, bucket_bytes=1 << 16, prescaled=True, defer_large=True)
+    assert len(pending) == 1 and pending[0][1] is params[0].grad          # the "point table" is the one large tensor
+    small_done = [p.grad.clone() for p in params[1:]]                      # usable before the large reduction is waited for
+    for h, _ in pending:
+        h.wait()
+    torch.save({"grads": [params[0].grad.clone()] + small_done, "n_global": n_global, "range": (b, e)}, os.path.join(out_dir, f"r{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_prescaled_overlapped_allreduce_matches_full_batch_gradients(tmp_path):
+    world = 2
+    mp.spawn(_worker_prescaled, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    params = _toy()
+    idx, gt, valid = _data()
+    _loss(params, idx, gt, valid).backward()
+    outs = [torch.load(os.path.join(tmp_path, f"r{r}.pt")) for r in range(world)]
+    assert float(outs[0]["n_global"]) == float(valid.sum())
+    for r in range(world):
+        for p, g in zip(params, outs[r]["grads"]):
+            ref = p.grad if p.grad is not None else torch.zeros_like(p)
+            np.testing.assert_allclose(g.numpy(), ref.numpy(), rtol=1e-5, atol=1e-8)
+
+
 def test_shard_patches_partition():
     for R, world in ((3136, 8), (4096, 3), (64, 4)):
         spans = [parallel.shard_patches(R, 64, r, world) for r in range(world)]
