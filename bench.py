@@ -168,7 +168,7 @@ def run_reference(args, rank):
             "dtype": "f32", "data": "synthetic", "config": {"workload": TRAIN_WORKLOAD, "sample": sample},
             "cpu_baseline": {"value": r["value"], "unit": "rays/s", "cores": cores, "kind": r["kind"], "sample": sample},
             "e2e": {"value": r["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 # ======================================================================================================================
@@ -327,7 +327,7 @@ def main():
                                        "(1.8 MB) and of the dense point-gradient tables (312 MB) overlapped with the next forward's query / pyramid / packing")
                        if world > 1 else "1 GPU"},
             "e2e": tr.get("e2e"), "gpu_launches": tr["launches_per_step"] * steps, "clocks": clk.summary(),
-            "train": {k: tr[k] for k in ("ms_per_step", "ms_fwd_bwd", "kept_rays", "valid_samples", "valid_neighbours", "loss", "launches_per_step", "stage_ms")}}
+            "train": {k: tr[k] for k in ("ms_per_step", "ms_fwd_bwd", "kept_rays", "valid_samples", "valid_neighbours", "loss", "launches_per_step", "stage_ms", "ranks") if k in tr}}
     if top is not None:
         line["roofline"] = {"bound": top["bound"], "achieved": top["achieved"], "peak": top["peak"], "unit": top["unit"], "frac": top["frac"],
                             "traffic": None, "kernel": top["kernel"], "kernel_ms": top["ms"], "note": top["note"],
@@ -345,6 +345,8 @@ def main():
         line["large_scene"] = {k: lg[k] for k in ("metric", "value", "unit", "ms_per_step", "ms_fwd_bwd", "rays_per_step_per_gpu", "points", "views", "kept_rays",
                                                   "valid_samples", "step", "config")}
         line["large_scene"]["n_gpus"] = world
+        if "ranks" in lg:
+            line["large_scene"]["ranks"] = lg["ranks"]
         line["large_scene"]["allreduce_bytes"] = 39 * 4 * lg["points"] if world > 1 else 0
         torch.cuda.empty_cache()
 
@@ -377,8 +379,9 @@ def main():
             except Exception as e:
                 line["cpu_baseline"] = {"value": None, "unit": "rays/s", "cores": cores, "kind": "port", "sample": "unavailable: " + repr(e)[:300]}
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -93,7 +93,8 @@ def train_step_benchmark(dev, steps: int = 5, warmup: int = 3, world: int = 1, p
     e.record()
     barrier()
     launches = ops.LAUNCHES
-    ms_step = _device_max(s.elapsed_time(e) / steps, dev, world)
+    ms_local = s.elapsed_time(e) / steps
+    ms_step = _device_max(ms_local, dev, world)
     res = {"metric": "train rays/s (fwd+bwd)", "value": world * R / (ms_step * 1e-3), "unit": "rays/s", "ms_per_step": ms_step,
            "rays_per_step_per_gpu": R, "points": points, "views": views, "loss": float(loss), "launches_per_step": launches // steps,
            "step": "forward + loss + backward" + (" + NCCL gradient all-reduce" if world > 1 else "") + " + Adam (network + point tables)",
@@ -164,6 +165,16 @@ def train_step_benchmark(dev, steps: int = 5, warmup: int = 3, world: int = 1, p
     ex = net.last_extras
     res.update({"kept_rays": int(ex.n_rays), "valid_samples": int(ex.n_valid), "valid_neighbours": agg.last_valid_neighbours(),
                 "stage_ms": {k: round(v, 3) for k, v in sorted(stages.items())}})
+    if world > 1:
+        # per-rank view (every rank trains on its own raster: the slowest rank sets the step time) and the same step WITHOUT the
+        # gradient exchange, so that the exposed cost of the collective can be read off
+        for _ in range(2):
+            fwd_bwd()
+        barrier()
+        mine = {"rank": rank, "ms_step_local": round(ms_local, 3), "ms_fwd_bwd_no_collective": round(res["ms_fwd_bwd"], 3), "valid_samples": int(ex.n_valid)}
+        allr = [None] * world
+        dist.all_gather_object(allr, mine)
+        res["ranks"] = allr
     return res
 
 

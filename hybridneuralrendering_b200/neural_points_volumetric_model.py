@@ -120,24 +120,42 @@ class NeuralPointsRayMarching(nn.Module):
         output["shading_avg_embedding"] = torch.sum(em * w, dim=-2)
 
 
-def fill_invalid(output: Dict[str, torch.Tensor], bg_color: Optional[torch.Tensor], ray_ids: Optional[torch.Tensor] = None):
-    """scatter the R'' valid-ray results back to all R rays (reference :87-126).  With `ray_ids`
-    (from the query) no host sync is needed; otherwise falls back to nonzero(ray_mask)."""
+def fill_invalid(output: Dict[str, torch.Tensor], bg_color: Optional[torch.Tensor], ray_ids: Optional[torch.Tensor] = None,
+                 bg_ray: Optional[torch.Tensor] = None, tonemap_func=None):
+    """scatter the R'' valid-ray results back to all R rays (reference models/neural_points_volumetric_model.py:87-126): misses get the
+    (tone-mapped) background colour, transmittance 1, opacity 0; also `coarse_mask` = 1 - coarse_is_background, the patch colours,
+    the `bg_ray` variant (per-ray background added under the kept rays' colours) and -- with opt.prob == 1 -- the unmasked probe
+    tensors point growing reads (`unmask`, :128-140: rays that hit nothing get zeros).  With `ray_ids` (from the query) no host
+    sync is needed; otherwise falls back to nonzero(ray_mask)."""
     ray_mask = output["ray_mask"]
     B, R = ray_mask.shape
     if ray_ids is None:
         ray_ids = torch.nonzero(ray_mask[0] > 0, as_tuple=False).view(-1)
     idx = ray_ids.long()
     dev = ray_mask.device
+    tm = tonemap_func if tonemap_func is not None else (lambda t: t)
     out = dict(output)
     c = output["coarse_raycolor"]
-    full = (bg_color.reshape(1, 1, 3).to(c).expand(B, R, 3) if bg_color is not None else torch.zeros((B, R, 3), device=dev)).clone()
-    out["coarse_raycolor"] = full.index_copy(1, idx, c)
+    isbg = torch.ones((B, R, 1), device=dev, dtype=output["coarse_is_background"].dtype).index_copy(1, idx, output["coarse_is_background"])
+    out["coarse_is_background"] = isbg
+    out["coarse_mask"] = 1 - isbg
+    if bg_ray is not None:
+        out["coarse_raycolor"] = (isbg * bg_ray.to(c)).index_add(1, idx, c)
+    else:
+        full = tm((bg_color.reshape(1, 1, 3).to(c).expand(B, R, 3) if bg_color is not None else torch.zeros((B, R, 3), device=dev)).clone())
+        out["coarse_raycolor"] = full.index_copy(1, idx, c)
+        cp = output.get("coarse_raycolor_patch")
+        if cp is not None:
+            out["coarse_raycolor_patch"] = full.repeat(1, 1, cp.shape[-1] // 3).index_copy(1, idx, cp)
     op = output["coarse_point_opacity"]
-    out["coarse_point_opacity"] = torch.zeros((B, R, op.shape[-1]), device=dev).index_copy(1, idx, op)
-    out["coarse_is_background"] = torch.ones((B, R, 1), device=dev).index_copy(1, idx, output["coarse_is_background"])
+    out["coarse_point_opacity"] = torch.zeros((B, R, op.shape[-1]), device=dev, dtype=op.dtype).index_copy(1, idx, op)
     out["queried_shading"] = torch.ones((B, R, 3), device=dev).index_copy(1, idx, output["queried_shading"])
     for k in ("weight", "blend_weight", "conf_coefficient"):
+        if k in output and output[k] is not None:
+            t = output[k]
+            out[k] = torch.zeros((B, R) + tuple(t.shape[2:]), device=dev, dtype=t.dtype).index_copy(1, idx, t)
+    for k in ("ray_max_sample_loc_w", "ray_max_shading_opacity", "shading_avg_color", "shading_avg_dir", "shading_avg_conf",
+              "shading_avg_embedding", "ray_max_far_dist"):
         if k in output and output[k] is not None:
             t = output[k]
             out[k] = torch.zeros((B, R) + tuple(t.shape[2:]), device=dev, dtype=t.dtype).index_copy(1, idx, t)

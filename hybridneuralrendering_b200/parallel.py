@@ -141,7 +141,7 @@ def flush_pending(net) -> None:
 
 
 def train_step(net, frame_shard: Dict[str, torch.Tensor], optimizers: Sequence[torch.optim.Optimizer], group=None,
-               zero_one_weight: float = 1e-4, next_frame_shard: Optional[Dict[str, torch.Tensor]] = None, large_bytes: int = 64 << 20):
+               zero_one_weight: float = 1e-4, next_frame_shard: Optional[Dict[str, torch.Tensor]] = None, large_bytes: int = 4 << 20):
     """One data-parallel training step on this rank's rays: forward (fused hot path), loss, backward, gradient all-reduce with
     global-mean normalisation, optimiser steps.  Returns (loss, n_global_valid), both device tensors.
 

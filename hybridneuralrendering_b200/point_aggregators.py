@@ -159,6 +159,9 @@ class PointAggregator(nn.Module):
         off = [k for k in ("tradition_attention", "refine_blend", "dynamic_weight", "add_idx", "separate_color_decoder",
                            "large_color_final_block", "use_2D_CNN", "disable_viewdirs", "disable_color_feature", "learnable_blur_kernel_conv",
                            "downweight_blurry_feats", "dist_xyz_deno") if getattr(opt, k, 0)]
+        if getattr(opt, "xyz_grad", 0):
+            raise NotImplementedError("xyz_grad > 0 is not implemented: no kernel produces a gradient w.r.t. the point positions (every shipped "
+                                      "script trains with xyz_grad=0; the distance encodings and inverse-distance weights are treated as data)")
         if bad or off:
             raise NotImplementedError(f"PointAggregator: unsupported options {bad} / enabled flags {off}; only the shipped "
                                       "configuration (SURVEY.md §8d) is implemented, there is no fallback path")

@@ -74,8 +74,33 @@ def _lin(x, P, name):
     return F.linear(x, P[name + ".weight"], P[name + ".bias"])
 
 
+KINK_TAP = None      # tests set this to a list: every LeakyReLU then records min |pre-activation| per row (see kink_free_rays)
+
+
 def _act(x):
+    if KINK_TAP is not None:
+        KINK_TAP.append(x.detach().abs().amin(dim=-1).reshape(-1))
     return F.leaky_relu(x, LRELU_SLOPE)
+
+
+def kink_free_rays(taps, sample_pnt_mask: torch.Tensor, ray_valid: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    """(R,) bool: rays none of whose hidden units has a pre-activation within `eps` of the LeakyReLU kink.  LeakyReLU' jumps by a
+    factor 100 at 0, so two correct fp32 implementations that sum in a different order may take different slopes for such a unit;
+    gradient parity tests mask those rays out of the colour loss (their gradient paths are then exactly zero on both sides).
+    taps: the KINK_TAP list of one aggregate() call; rows are compacted valid neighbours (block1 / block3) or valid samples."""
+    B, R, SR, K = sample_pnt_mask.shape
+    nbr_ray = torch.nonzero(sample_pnt_mask.reshape(-1)).reshape(-1) // (SR * K)
+    smp_ray = torch.nonzero(ray_valid.reshape(-1)).reshape(-1) // SR
+    ok = torch.ones(R, dtype=torch.bool)
+    for mn in taps:
+        if mn.numel() == nbr_ray.numel():
+            rows = nbr_ray
+        elif mn.numel() == smp_ray.numel():
+            rows = smp_ray
+        else:
+            continue            # activations of the image pyramid (per pixel, not per ray)
+        ok[rows[mn < eps]] = False
+    return ok
 
 
 def drop_patch_positions(patch_size: int, patch_num: int, drop_ratio: float) -> np.ndarray:

@@ -12,13 +12,19 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
-def layer_errors(R=64, SR=24, empty=0.4, seed=3, N=4000):
+def layer_errors(R=64, SR=24, empty=0.4, seed=3, N=4000, emb_range=None, weight_scale=1.0, return_status=False):
     from helpers import build_aggregator, cuda
     from hybridneuralrendering_b200 import mlp_tc, ops
     from hybridneuralrendering_b200 import synthetic as syn
     from oracle import render_oracle as ro
     d = syn.render_stage_inputs(seed=seed, N=N, R=R, SR=SR, K=8, V=2, H=32, W=40, empty_frac=empty)
+    if emb_range is not None:           # wider embeddings than the U(-0.5, 0.5) initialisation (trained checkpoints)
+        d["emb"] = ((np.random.default_rng(seed + 1).random(d["emb"].shape, dtype=np.float32) * 2 - 1) * emb_range).astype(np.float32)
     P = ro.random_params(seed)
+    if weight_scale != 1.0:
+        for k in list(P):
+            if k.split(".")[0] in ("block1", "block3") and k.endswith("weight"):
+                P[k] = P[k] * weight_scale
     agg = build_aggregator(P, use_nearest=2)
     S = R * SR
     xyz, emb, color, dirs, conf = (cuda(d[k]) for k in ("xyz", "emb", "color", "dir", "conf"))
@@ -33,6 +39,8 @@ def layer_errors(R=64, SR=24, empty=0.4, seed=3, N=4000):
         vlist = torch.nonzero(valid).view(-1).to(torch.int32)
         X0, E = ops.NbrFeaturesFn.apply(emb, color, dirs, xyz, None, pidx, None, vlist, loc_w, loc_pers, raydirs, cam)
         pack = mlp_tc.pack_mlp_f16(agg.block1, agg.block3)
+        torch.cuda.synchronize()
+        ops.status_word(xyz.device).zero_()
         sigma, X5, dbg, araw_k = mlp_tc.forward_f16(tables, pidx, vlist, loc_w, loc_pers, raydirs, cam, weight, confc, pack,
                                             agg.alpha_branch[0].weight, agg.alpha_branch[0].bias, debug=True)
         torch.cuda.synchronize()
@@ -58,7 +66,9 @@ def layer_errors(R=64, SR=24, empty=0.4, seed=3, N=4000):
         _, X5_ref = ops.AlphaKSumFn.apply(h4.float(), confc, agg.alpha_branch[0].weight, agg.alpha_branch[0].bias, weight, vlist, raydirs, cam)
         errs.append((float((X5[:, 256:] - X5_ref[:, 256:]).abs().max()), 1.0))
         errs.append((float((araw_k.double().view(Nv, 8) - araw).abs().max()), float(araw.abs().max())))
-    return errs
+        status = int(ops.status_word(xyz.device)[0])
+        ops.status_word(xyz.device).zero_()
+    return (errs, status) if return_status else errs
 
 
 if __name__ == "__main__":

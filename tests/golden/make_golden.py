@@ -213,8 +213,17 @@ def projection_case():
     fr = syn.room_frame(H=48, W=64, V=3, patch_num=2, patch_size=2, seed=1)
     loc_w = T((rng.random((1, 4, 5, 3)) * np.array([6, 5, 3])).astype(np.float32))
     xy = [NeuralPointsRayMarching.w2iproject(None, loc_w[0], T(fr["intrinsic_nearest"][0]), T(fr["c2w_nearest"][0, v]), None) for v in range(3)]
+    # the delta-view loop is inline in NeuralPointsRayMarching.forward (:296-310): run THOSE source lines, read from the reference file
+    import inspect, textwrap, types
+    src = inspect.getsource(NeuralPointsRayMarching.forward).splitlines()
+    a = next(i for i, l in enumerate(src) if "delta_sample_viewdir_nearest = []" in l)
+    b = next(i for i, l in enumerate(src) if "delta_sample_viewdir_nearest = torch.stack(delta_sample_viewdir_nearest)" in l)
+    env = dict(torch=torch, sample_loc_w=loc_w, campos=T(fr["campos"]), campos_nearest=T(fr["campos_nearest"]),
+               self=types.SimpleNamespace(opt=types.SimpleNamespace(use_nearest=3)))
+    exec(textwrap.dedent("\n".join(src[a:b + 1])), env)
     np.savez_compressed(os.path.join(OUT, "proj.npz"), loc_w=loc_w.numpy(), intrinsic=fr["intrinsic_nearest"][0], c2w_n=fr["c2w_nearest"][0],
-                        xy=torch.stack(xy).numpy())
+                        xy=torch.stack(xy).numpy(), campos=fr["campos"], campos_n=fr["campos_nearest"][0],
+                        delta_view=env["delta_sample_viewdir_nearest"].numpy())
     print("proj ok")
 
 
@@ -379,6 +388,9 @@ if __name__ == "__main__":
         # the largest row index the reference's (misaligned) patch drop touches
         agg_case_tables("agg_eval_sr80", R=64, SR=80, V=4, H=60, W=80, is_train=False, drop_ratio=0.0, dilation_setup="7_8_1_8", seed=21, empty_frac=0.5)
         agg_case_tables("agg_train_sr24", R=1792, SR=24, V=8, H=48, W=64, is_train=True, drop_ratio=0.5, dilation_setup="7_8_1_8", seed=22, empty_frac=0.9)
+        sys.exit(0)
+    if "--only-proj" in sys.argv:
+        projection_case()
         sys.exit(0)
     if "--only-learnable-blur" in sys.argv:
         learnable_blur_case()

@@ -118,8 +118,10 @@ def test_projection_kernel_matches_reference_golden():
     G = load_golden("proj")
     loc = cuda(G["loc_w"])[0].reshape(-1, 3)
     w2c = torch.linalg.inv(cuda(G["c2w_n"]))
-    xy, delta = ops.project_views(loc, w2c, cuda(G["intrinsic"]), torch.zeros(3).cuda(), torch.zeros(3, 3).cuda())
+    xy, delta = ops.project_views(loc, w2c, cuda(G["intrinsic"]), cuda(G["campos"]).reshape(-1), cuda(G["campos_n"]))
     assert_close(xy.view(G["xy"].shape), G["xy"], 1e-5, 1e-3)
+    # delta view directions: the reference's own lines (neural_points_volumetric_model.py:296-310) produced the golden
+    assert_close(delta.view(G["delta_view"].shape), G["delta_view"], 1e-5, 1e-6)
 
 
 def test_image_gather_equals_interpolate_then_lookup():
@@ -214,3 +216,86 @@ def test_dropin_train_step_matches_reference_golden_shipped_train_shape():
         assert_close(p.grad, G[key], RTOL, grad_atol(G[key]), k)          # rtol 1e-4 + 1e-4 x max magnitude (north_star)
         n += 1
     assert n >= 40
+
+
+def test_neural_points_forward_returns_the_reference_14_tuple():
+    """G1 drop-in: NeuralPoints.forward (reference models/neural_points/neural_points.py:702-733) -- tuple order, shapes, dtypes, the
+    clamp(pidx, 0) aliasing of masked slots to point 0, and the values of every gather; then the drop-in PointAggregator.forward on
+    that tuple equals the fused path on the same frame."""
+    from hybridneuralrendering_b200 import NeuralPoints, PointAggregator, make_opt
+    opt = make_opt("scannet", use_nearest=2, SR=24)
+    xyz = syn.room_scene(30000, 4)
+    att = syn.point_attributes(np.random.default_rng(4), len(xyz))
+    fr = syn.room_frame(H=48, W=64, V=2, patch_num=4, patch_size=4, seed=6)
+    pts = NeuralPoints(32, len(xyz), opt, torch.device("cuda"))
+    pts.set_points(cuda(xyz), cuda(att["emb"])[None], points_color=cuda(att["color"])[None], points_dir=cuda(att["dir"])[None],
+                   points_conf=cuda(att["conf"])[None], parameter=True)
+    inputs = {k: cuda(fr[k]) for k in ("pixel_idx", "camrotc2w", "campos", "near", "far", "intrinsic", "raydir")}
+    inputs.update(h=fr["h"], w=fr["w"])
+    with torch.no_grad():
+        tup = pts(inputs)
+        pidx, loc, loc_w, dirs, ray_mask, vsize, _ = pts.query(inputs)
+    assert len(tup) == 14
+    (s_color, s_Rw2c, s_dir, s_conf, s_emb, s_xyz_pers, s_xyz, s_mask, s_loc, s_loc_w, s_dirs, s_raymask, s_vsize, s_gvs) = tup
+    B, R, SR, K = pidx.shape
+    assert R > 50 and s_mask.dtype == torch.bool and s_raymask.dtype == torch.int8 and s_raymask.shape == (1, fr["raydir"].shape[1])
+    assert s_emb.shape == (1, R, SR, K, 32) and s_xyz.shape == s_xyz_pers.shape == s_color.shape == s_dir.shape == (1, R, SR, K, 3)
+    assert s_conf.shape == (1, R, SR, K, 1) and s_Rw2c.shape == (3, 3) and s_loc.shape == s_loc_w.shape == s_dirs.shape == (1, R, SR, 3)
+    assert torch.equal(s_mask, pidx >= 0) and torch.equal(s_loc_w, loc_w) and torch.equal(s_loc, loc) and torch.equal(s_raymask, ray_mask)
+    idx = pidx.clamp(min=0).long()                                      # masked slots alias point 0 (:711)
+    assert torch.equal(s_emb, pts.points_embeding[0][idx]) and torch.equal(s_xyz, pts.xyz[idx]) and torch.equal(s_conf, pts.points_conf[0][idx])
+    assert bool((~s_mask).any()) and torch.equal(s_color[~s_mask], pts.points_color[0, :1].expand(int((~s_mask).sum()), 3))
+    cam = pts.xyz - cuda(fr["campos"])                                   # w2pers (:607-613)
+    xc = cam @ cuda(fr["camrotc2w"])[0]
+    pers = torch.stack([xc[:, 0] / xc[:, 2], xc[:, 1] / xc[:, 2], xc[:, 2]], -1)
+    assert_close(s_xyz_pers, pers[idx], 1e-6, 1e-6)
+    # the drop-in aggregator on the tuple == the fused path on the frame
+    P = ro.random_params(3)
+    agg = PointAggregator(opt).cuda()
+    agg.load_state_dict(P, strict=False)
+    lw = loc_w.reshape(-1, 3)
+    xy = ro.project_to_views(loc_w[0].cpu(), T(fr["intrinsic_nearest"][0]), T(fr["c2w_nearest"][0])).cuda()
+    dv = ro.delta_viewdirs(loc_w[0].cpu(), T(fr["campos"][0]), T(fr["campos_nearest"][0])).cuda()
+    with torch.no_grad():
+        dec_a, valid_a, _, _ = agg(s_color, s_Rw2c, s_dir, s_conf, s_emb, s_xyz_pers, s_xyz, s_mask, s_loc, s_loc_w, s_dirs, s_vsize, s_gvs,
+                                   img_n=cuda(fr["images_nearest"]), sample_loc_i_n=xy, delta_viewdir_n=dv)
+        from hybridneuralrendering_b200 import ops
+        _, w2c = agg.prepare_views(cuda(fr["images_nearest"]), cuda(fr["c2w_nearest"])[0])
+        xy_k, _ = ops.project_views(lw, w2c, cuda(fr["intrinsic_nearest"][0]).reshape(3, 3), cuda(fr["campos"]).reshape(-1)[:3], cuda(fr["campos_nearest"][0]))
+        dec_b, valid_b, _, _ = agg(s_color, s_Rw2c, s_dir, s_conf, s_emb, s_xyz_pers, s_xyz, s_mask, s_loc, s_loc_w, s_dirs, s_vsize, s_gvs,
+                                   img_n=cuda(fr["images_nearest"]), sample_loc_i_n=xy_k.view(2, R, SR, 2), delta_viewdir_n=dv)
+        dec_c, valid_c, _, _ = agg.forward_fused(pts, pidx, loc, loc_w, dirs, cuda(fr["campos"]), cuda(fr["camrotc2w"]), img_n=cuda(fr["images_nearest"]),
+                                                 c2w_n=cuda(fr["c2w_nearest"])[0], intrinsic_n=cuda(fr["intrinsic_nearest"])[0], campos_n=cuda(fr["campos_nearest"])[0])
+    assert torch.equal(valid_a, valid_c) and float((xy_k.view(2, R, SR, 2) - xy).abs().max()) < 1e-3
+    assert_close(dec_b, dec_c, RTOL, 1e-6)           # same projections (the kernel's) on both paths: every sample
+    assert int(((dec_a - dec_c).abs().amax(-1) > 1e-4 * dec_c.abs().amax(-1) + 1e-6).sum()) <= max(2, int(0.002 * valid_a.numel()))
+
+
+def test_fill_invalid_matches_reference_semantics():
+    """fill_invalid (reference :87-126): kept rays scattered into all R rays, misses = background colour / transmittance 1 / opacity 0,
+    coarse_mask, patch colours, bg_ray variant, probe tensors unmasked with zeros"""
+    from hybridneuralrendering_b200.neural_points_volumetric_model import fill_invalid
+    g = torch.Generator().manual_seed(0)
+    R, Rk, SR = 40, 17, 6
+    mask = torch.zeros(1, R, dtype=torch.int8)
+    ids = torch.randperm(R, generator=g)[:Rk].sort()[0]
+    mask[0, ids] = 1
+    out = {"ray_mask": mask.cuda(), "coarse_raycolor": torch.rand(1, Rk, 3, generator=g).cuda(), "coarse_raycolor_patch": torch.rand(1, Rk, 3, generator=g).cuda(),
+           "coarse_point_opacity": torch.rand(1, Rk, SR, generator=g).cuda(), "coarse_is_background": torch.rand(1, Rk, 1, generator=g).cuda(),
+           "queried_shading": torch.zeros(1, Rk, 3).cuda(), "ray_max_far_dist": torch.rand(1, Rk, 1, generator=g).cuda(), "shading_avg_color": None}
+    bg = torch.tensor([[1.0, 0.5, 0.25]]).cuda()
+    for rid in (None, ids.int().cuda()):
+        f = fill_invalid(out, bg, rid)
+        miss = (mask[0] == 0).cuda()
+        assert torch.equal(f["coarse_raycolor"][0, ids.cuda()], out["coarse_raycolor"][0]) and torch.equal(f["coarse_raycolor"][0, miss], bg.expand(int(miss.sum()), 3))
+        assert torch.equal(f["coarse_raycolor_patch"][0, ids.cuda()], out["coarse_raycolor_patch"][0])
+        assert torch.equal(f["coarse_is_background"][0, miss], torch.ones(int(miss.sum()), 1).cuda())
+        assert torch.equal(f["coarse_mask"], 1 - f["coarse_is_background"])
+        assert float(f["coarse_point_opacity"][0, miss].abs().max()) == 0 and torch.equal(f["coarse_point_opacity"][0, ids.cuda()], out["coarse_point_opacity"][0])
+        assert torch.equal(f["queried_shading"][0, miss], torch.ones(int(miss.sum()), 3).cuda())
+        assert f["ray_max_far_dist"].shape == (1, R, 1) and float(f["ray_max_far_dist"][0, miss].abs().max()) == 0
+    bg_ray = torch.rand(1, R, 3, generator=g).cuda()
+    f = fill_invalid(out, bg, ids.int().cuda(), bg_ray=bg_ray)
+    ref = f["coarse_is_background"] * bg_ray
+    ref[0, ids.cuda()] += out["coarse_raycolor"][0]
+    assert_close(f["coarse_raycolor"], ref, 1e-6, 1e-7)

@@ -218,3 +218,26 @@ def test_fp16_split_range_guard_raises_instead_of_diverging_silently():
             ops.status_check(dev)
         ops.status_fetch_async(dev); torch.cuda.synchronize()
         ops.status_check(dev)                                        # the flag is cleared once reported
+
+
+def test_f16_kernel_wide_range_embeddings_and_weights():
+    """trained checkpoints have wider embeddings than the U(-0.5, 0.5) initialisation.  |emb| <= 4 and every block1 / block3 weight
+    scaled x1 .. x16 through the fused 3xFP16 kernel (debug taps) vs fp64 on the same gathered features: while the range guard
+    (saturating fp16 packs of the x64-scaled activations, |h| < 1023) stays silent, every layer keeps fp32-level accuracy
+    (1e-5 of the layer's scale); once hidden activations leave that range the guard MUST fire -- the host then raises instead of
+    returning silently saturated values.  Measured on B200: silent up to x4 (|h| up to ~600), fires from x8."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
+    from debug_nbr_f16 import layer_errors
+    fired_at = []
+    for ws in (1.0, 2.0, 4.0, 8.0, 16.0):
+        errs, status = layer_errors(R=64, SR=24, empty=0.4, seed=11, emb_range=4.0, weight_scale=ws, return_status=True)
+        hmax = max(scale for (_, scale) in errs[:3])            # layers 0..2 feed the next layer as split fp16 (x64); layer 3 leaves in fp32
+        if status & 1:
+            fired_at.append(ws)
+            assert hmax * 64.0 > 60000.0, (ws, hmax)            # the guard fires only when the range really is exceeded
+        else:
+            assert hmax * 64.0 < 65504.0, (ws, hmax)
+            for name, (e, scale) in zip(["layer0", "layer1", "layer2", "layer3", "sigma", "ksum", "viewpe", "araw"], errs):
+                assert e <= 1e-5 * scale + 1e-7, (ws, name, e, scale)
+    assert 4.0 not in fired_at and 16.0 in fired_at, fired_at

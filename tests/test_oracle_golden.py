@@ -107,6 +107,8 @@ def test_projection_matches_reference():
     G = _load("proj")
     xy = ro.project_to_views(T(G["loc_w"])[0], T(G["intrinsic"]), T(G["c2w_n"]))
     np.testing.assert_allclose(xy.numpy(), G["xy"], rtol=1e-6, atol=1e-4)
+    dv = ro.delta_viewdirs(T(G["loc_w"])[0], T(G["campos"])[0], T(G["campos_n"]))
+    np.testing.assert_allclose(dv.numpy(), G["delta_view"], rtol=1e-6, atol=1e-7)
 
 
 def test_blur_matches_reference():
