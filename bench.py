@@ -248,6 +248,47 @@ def render_benchmark(dev, steps, warmup, pk):
                        "use_nearest": V, "SR": int(opt.SR), "K": int(opt.K), "l2": "flushed between frames (256 MB write)"}}
 
 
+def config0_product(dev, repeats=5, warmup=3):
+    """BASELINE.json configs[0] on the product: the drop-in PointAggregator.forward on the SAME gathered tensors (1024 rays x 80 samples,
+    K = 8 precomputed neighbours, 200K points, V = 4) + ray_dist + ray_march + loss, forward and backward, CUDA events"""
+    from hybridneuralrendering_b200 import PointAggregator, make_opt
+    from hybridneuralrendering_b200 import synthetic as syn
+    from hybridneuralrendering_b200.diff_ray_marching import ray_march_from_depth
+    d = syn.render_stage_inputs(seed=0)
+    g = syn.gather_neighbours(d)
+    c = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    agg = PointAggregator(make_opt(use_nearest=4, is_train=False)).to(dev)
+    agg.load_state_dict(syn.random_aggregator_params(0), strict=False)
+    leaf = {k: c(g[k]).requires_grad_(True) for k in ("sampled_embedding", "sampled_color", "sampled_dir", "sampled_conf")}
+    fixed = [c(g["sampled_xyz_pers"]), c(g["sampled_xyz"]), c(g["sample_pnt_mask"]), c(d["sample_loc"]), c(d["sample_loc_w"]), c(d["sample_ray_dirs"])]
+    img, xy, dv = c(d["images_nearest"]), c(d["sample_loc_i_n"]), c(d["delta_viewdir_n"])
+    R = d["sample_pidx"].shape[1]
+    gt = c(np.random.default_rng(7).random((1, R, 3), dtype=np.float32))
+    bg = torch.ones(1, 3, device=dev)
+
+    def step():
+        for t in list(leaf.values()) + list(agg.parameters()):
+            t.grad = None
+        out = agg(leaf["sampled_color"], torch.eye(3, device=dev), leaf["sampled_dir"], leaf["sampled_conf"], leaf["sampled_embedding"], *fixed,
+                  d["vsize"], 0, img_n=img, sample_loc_i_n=xy, delta_viewdir_n=dv)
+        color = ray_march_from_depth(fixed[3], out[1], out[0], float(d["vsize"][2]), 1, bg)[0]
+        loss = torch.nn.functional.mse_loss(color, gt)
+        loss.backward()
+        return loss
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(repeats):
+        loss = step()
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / repeats
+    return {"value": R / (ms * 1e-3), "unit": "rays/s", "ms_fwd_bwd": ms, "rays": R, "loss": float(loss.detach()),
+            "path": "drop-in PointAggregator.forward (gathered tensors, as the reference calls it) + ray_march, fwd + bwd"}
+
+
 def train_kernel_rooflines(tr, pk):
     """roofline records of the three big kernels of the fused training path from the per-launch CUDA events of one step"""
     peaks_d, kind = pk
@@ -378,6 +419,15 @@ def main():
                                                    f"({r['query']}, {r['s_query']:.1f} s) not in the metric")}
             except Exception as e:
                 line["cpu_baseline"] = {"value": None, "unit": "rays/s", "cores": cores, "kind": "port", "sample": "unavailable: " + repr(e)[:300]}
+            # BASELINE.json configs[0] / BASELINE.md §3: the render stage on precomputed neighbours, reference on the host cores vs the product
+            try:
+                from oracle import reference_pipeline as rp
+                c0 = rp.config0_reference("cpu", repeats=3, warmup=1)
+                line["config0"] = {"workload": "render stage on CPU: diff_ray_marching + point_aggregators fwd/bwd, synthetic 200K neural points (32-ch), 1024 rays x 80 "
+                                               "samples, K=8 precomputed neighbours",
+                                   "reference_cpu": dict(c0, cores=cores, torch=torch.__version__), "product_gpu": config0_product(dev)}
+            except Exception as e:
+                line["config0"] = {"unavailable": repr(e)[:300]}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

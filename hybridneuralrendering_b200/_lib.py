@@ -94,6 +94,8 @@ _SIGS = {
                                               C.POINTER(vp), vp]),
     "hnr_chain_bwd_f16": (C.c_int, [C.c_int, C.POINTER(i64), C.POINTER(i64), i64, C.c_int, vp, i64, vp, i64, C.POINTER(vp), C.POINTER(vp), vp,
                                     C.POINTER(i64), vp, i64, i64, vp]),
+    "hnr_pyramid_fwd": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), i64, i64, i64, vp]),
+    "hnr_pyramid_bwd": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), i64, i64, i64, vp]),
     "hnr_pack_job_bytes": (i64, []),
     "hnr_bias_job_bytes": (i64, []),
     "hnr_pack_weights": (C.c_int, [vp, i64, i64, vp, i64, vp, vp]),

@@ -581,6 +581,54 @@ def _x0_cols(dev):
 # --------------------------------------------------------------------------------------------
 # image branch
 # --------------------------------------------------------------------------------------------
+class PyramidFn(torch.autograd.Function):
+    """feature pyramid of the image branch (csrc/pyramid.cu): img (V,H,W,3) NHWC + the 12 conv parameters of aux_block_s1/s2/s3 ->
+    levels (V,H/2,W/2,6), (V,H/4,W/4,12), (V,H/8,W/8,24) NHWC.  Exact fp32, forward and backward on own kernels (no cuDNN, no
+    layout conversions).  No gradient flows to the images."""
+
+    @staticmethod
+    def forward(ctx, img, *params):
+        img = _f32c(img)
+        require_cuda(img, *params)
+        V, H, W, _ = img.shape
+        ws = [_f32c(p) for p in params[0::2]]
+        bs = [_f32c(p) for p in params[1::2]]
+        d = lambda x: (x - 1) // 2 + 1
+        hs, wd = [d(H)], [d(W)]
+        for _ in range(2):
+            hs.append(d(hs[-1])); wd.append(d(wd[-1]))
+        chans = (6, 6, 12, 12, 24, 24)
+        act = [torch.empty((V, hs[i // 2], wd[i // 2], chans[i]), device=img.device, dtype=torch.float32) for i in range(6)]
+        with _launch(6, name="pyramid_fwd"):
+            check(lib().hnr_pyramid_fwd(ptr(img), ptr_array(ws), ptr_array(bs), ptr_array(act), V, H, W, stream()), "pyramid_fwd")
+        ctx.save_for_backward(img, *ws, *act)
+        ctx.mark_non_differentiable(act[0], act[2], act[4])
+        return act[1], act[3], act[5]
+
+    @staticmethod
+    def backward(ctx, d1, d2, d3):
+        sv = ctx.saved_tensors
+        img, ws, act = sv[0], list(sv[1:7]), list(sv[7:13])
+        V, H, W, _ = img.shape
+        dev = img.device
+        flat = torch.zeros(sum(w.numel() + w.shape[0] for w in ws), device=dev, dtype=torch.float32)       # one fill for all 12 gradients
+        dws, dbs, o = [], [], 0
+        for w in ws:
+            dws.append(flat[o:o + w.numel()].view_as(w)); o += w.numel()
+            dbs.append(flat[o:o + w.shape[0]]); o += w.shape[0]
+        scratch = [torch.empty_like(act[i]) for i in (4, 3, 2, 1, 0)]
+        c = lambda t: _f32c(t) if t is not None else None
+        if d3 is None:
+            d3 = torch.zeros_like(act[5])
+        with _launch(11, name="pyramid_bwd"):
+            check(lib().hnr_pyramid_bwd(ptr(img), ptr_array(ws), ptr_array(act), ptr_array([c(d1), c(d2), c(d3)]), ptr_array(dws), ptr_array(dbs),
+                                        ptr_array(scratch), V, H, W, stream()), "pyramid_bwd")
+        grads = []
+        for dw, db in zip(dws, dbs):
+            grads += [dw, db]
+        return (None, *grads)
+
+
 def project_views(loc_w: torch.Tensor, w2c: torch.Tensor, Kmat: torch.Tensor, campos: torch.Tensor, campos_n: torch.Tensor):
     """loc_w (S,3), w2c (V,4,4), Kmat (3,3), campos (3,), campos_n (V,3) -> xy (V,S,2), delta (V,S,3)."""
     S, V = loc_w.shape[0], w2c.shape[0]

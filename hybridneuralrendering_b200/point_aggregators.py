@@ -143,6 +143,9 @@ class PointAggregator(nn.Module):
         self.mlp_engine = "tc"
         # valid samples decoded per pass in no-grad mode (bounds activation memory); HNR_MAX_VALID_CHUNK = A/B override
         self.max_valid_chunk = int(os.environ.get("HNR_MAX_VALID_CHUNK", "262144"))
+        # image pyramid on own kernels (csrc/pyramid.cu); False = the six convolutions through cuDNN in exact fp32 (_ExactConvPyramid, kept
+        # as the cross-check of the own kernels in the tests)
+        self.own_pyramid = os.environ.get("HNR_OWN_PYRAMID", "1") != "0"
         self.fused_train_forward = True      # graph-recording forwards of the per-neighbour stage also use the fused kernel
         # backward of the per-neighbour stage: fused data-gradient chain + one image-fed weight-gradient launch (nbr_bwd_f16.cu,
         # wgrad_img.cu); False = layer-by-layer tensor-core kernels (kept as the cross-check of the fused path in the tests)
@@ -184,6 +187,9 @@ class PointAggregator(nn.Module):
         params = []
         for blk in (self.aux_block_s1, self.aux_block_s2, self.aux_block_s3):
             params += [blk[0].weight, blk[0].bias, blk[2].weight, blk[2].bias]
+        if self.own_pyramid:
+            imgc = img.contiguous()
+            return [imgc] + list(ops.PyramidFn.apply(imgc, *params))
         s1, s2, s3 = _ExactConvPyramid.apply(img.permute(0, 3, 1, 2), *params)
         return [img.contiguous()] + [t.permute(0, 2, 3, 1).contiguous() for t in (s1, s2, s3)]
 

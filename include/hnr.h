@@ -227,6 +227,15 @@ int hnr_chain_f16_forward_train(const float* const* src, const int64_t* src_ld, 
 int hnr_chain_bwd_f16(int nlayer, const int64_t* Np, const int64_t* N, int64_t NX, int act_top, const float* dY, int64_t lddy,
                       const float* Ytop, int64_t ldyt, const void* const* gimg, void* const* dzimg, const void* wpackT,
                       const int64_t* w_off, float* dX, int64_t ldx, int64_t M, void* stream);
+/* Feature pyramid of the image branch (csrc/pyramid.cu): the six 3x3 convolutions + LeakyReLU of aux_block_s1/s2/s3
+ * (models/aggregators/point_aggregators.py:598-630, :1047-1063), exact fp32, NHWC, forward and backward.  w/b: six torch-layout
+ * (Cout,Cin,3,3) / (Cout) tensors; act: the six activated outputs (act[1], act[3], act[5] are the levels the lookup reads);
+ * backward: dlev[3] level gradients (NULL = zero for the two finer ones), dw/db accumulate, scratch: 5 buffers shaped like
+ * act[4], act[3], act[2], act[1], act[0]. */
+int hnr_pyramid_fwd(const float* img, const float* const* w, const float* const* b, float* const* act, int64_t V, int64_t H, int64_t W,
+                    void* stream);
+int hnr_pyramid_bwd(const float* img, const float* const* w, const float* const* act, const float* const* dlev, float* const* dw,
+                    float* const* db, float* const* scratch, int64_t V, int64_t H, int64_t W, void* stream);
 /* One-launch re-packing of every weight image of the training step (csrc/pack.cu): device-resident job tables built by
  * hybridneuralrendering_b200/packer.py (struct layouts there and in pack.cu; sizes exported for the consistency check). */
 int64_t hnr_pack_job_bytes(void);

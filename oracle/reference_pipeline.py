@@ -143,3 +143,60 @@ class ReferenceStep:
         sync()
         t2 = time.perf_counter()
         return t1 - t0, t2 - t1, int(R), float(loss.detach())
+
+
+def config0_reference(device: str = "cpu", repeats: int = 3, warmup: int = 1):
+    """BASELINE.json configs[0] / BASELINE.md §3: the render stage alone -- PointAggregator.forward + ray_dist + ray_march, forward
+    AND backward -- of the unmodified reference on synthetic 200K neural points (32 channels), 1024 rays x 80 samples, K = 8
+    PRECOMPUTED neighbours (50 % of the samples empty), V = 4 reference images 120x160 (hybridneuralrendering_b200.synthetic.
+    render_stage_inputs(seed=0), SURVEY.md §8d recipe).  -> dict(rays, s_fwd, s_bwd (medians), rays/s, valid samples / neighbours, kind)"""
+    from hybridneuralrendering_b200 import synthetic as syn
+    dev = torch.device(device)
+    d = syn.render_stage_inputs(seed=0)
+    g = syn.gather_neighbours(d)
+    P = ro.random_params(0)
+    R, SR, V = d["sample_pidx"].shape[1], d["sample_pidx"].shape[2], 4
+    c = lambda a: T(np.ascontiguousarray(a)).to(dev)
+    use_ref = ref_import.available()
+    if use_ref:
+        agg = ref_import.aggregator(ref_import.shipped_opt(use_nearest=V, is_train=False))
+        agg.load_state_dict(P, strict=False)
+        agg = agg.to(dev)
+        dr, drf = ref_import.rendering()
+        params = list(agg.parameters())
+    else:
+        Pd = {k: v.to(dev).clone().requires_grad_(True) for k, v in P.items()}
+        cfg = ro.AggCfg(use_nearest=V)
+        params = list(Pd.values())
+    leaf = {k: c(g[k]).requires_grad_(True) for k in ("sampled_embedding", "sampled_color", "sampled_dir", "sampled_conf")}
+    fixed = [c(g["sampled_xyz_pers"]), c(g["sampled_xyz"]), c(g["sample_pnt_mask"]), c(d["sample_loc"]), c(d["sample_loc_w"]), c(d["sample_ray_dirs"])]
+    img, xy, dv = c(d["images_nearest"]), c(d["sample_loc_i_n"]), c(d["delta_viewdir_n"])
+    gt = c(np.random.default_rng(7).random((1, R, 3), dtype=np.float32))
+    vz = float(d["vsize"][2])
+    sync = (lambda: torch.cuda.synchronize()) if dev.type == "cuda" else (lambda: None)
+    tf, tb = [], []
+    for i in range(warmup + repeats):
+        for t in list(leaf.values()) + params:
+            t.grad = None
+        sync()
+        t0 = time.perf_counter()
+        a = (leaf["sampled_color"], torch.eye(3, device=dev), leaf["sampled_dir"], leaf["sampled_conf"], leaf["sampled_embedding"], *fixed)
+        if use_ref:
+            out = agg(*a, d["vsize"], 0, img_n=img, sample_loc_i_n=xy, delta_viewdir_n=dv, frame_weight_n=None, vid_angle_n=None)
+        else:
+            out = ro.aggregate(Pd, cfg, *a, img_n=img, sample_loc_i_n=xy, delta_viewdir_n=dv)
+        decoded, ray_valid = out[0], out[1]
+        rd = ro.ray_dist_from_depth(fixed[3][..., 2], ray_valid, vz)
+        bg = torch.ones(1, 3, device=dev)
+        color = dr.ray_march(rd, ray_valid, decoded, drf.radiance_render, drf.alpha_blend, bg)[0] if use_ref else ro.ray_march(rd, ray_valid, decoded, bg)[0]
+        loss = torch.nn.functional.mse_loss(color, gt)
+        sync()
+        t1 = time.perf_counter()
+        loss.backward()
+        sync()
+        t2 = time.perf_counter()
+        if i >= warmup:
+            tf.append(t1 - t0); tb.append(t2 - t1)
+    sf, sb = float(np.median(tf)), float(np.median(tb))
+    return {"rays": R, "samples_per_ray": SR, "valid_samples": int(ray_valid.sum()), "valid_neighbours": int((d["sample_pidx"] >= 0).sum()),
+            "s_fwd": sf, "s_bwd": sb, "value": R / (sf + sb), "unit": "rays/s", "kind": "reference" if use_ref else "port", "loss": float(loss.detach())}

@@ -258,3 +258,42 @@ def test_fused_adam_matches_torch_adam_dense_semantics():
         oa.step(); ob.step()
     for a, b in zip(pa, pb):
         assert_close(a, b, 1e-6, 1e-7)
+
+
+@pytest.mark.parametrize("V,H,W", [(2, 48, 64), (3, 37, 51), (1, 121, 162)])
+def test_own_pyramid_kernels_match_torch_conv(V, H, W):
+    """csrc/pyramid.cu (six 3x3 convolutions + LeakyReLU, NHWC, exact fp32) vs torch conv2d in fp64: the three levels, and every weight /
+    bias gradient for random level gradients (odd sizes included: stride-2 output size floor((H-1)/2)+1)"""
+    from hybridneuralrendering_b200 import ops
+    from hybridneuralrendering_b200.point_aggregators import _conv_block
+    torch.manual_seed(V * H)
+    blocks = [_conv_block(3, 6).cuda(), _conv_block(6, 12).cuda(), _conv_block(12, 24).cuda()]
+    for blk in blocks:
+        for m in (blk[0], blk[2]):
+            torch.nn.init.normal_(m.weight, std=0.3)
+            torch.nn.init.normal_(m.bias, std=0.1)
+    params = []
+    for blk in blocks:
+        params += [blk[0].weight, blk[0].bias, blk[2].weight, blk[2].bias]
+    img = torch.rand(V, H, W, 3, device="cuda")
+    lv = ops.PyramidFn.apply(img, *params)
+    gs = [torch.randn_like(t) for t in lv]
+    gs[1][:, ::3] = 0                          # sparse level gradients, like the image gather's scatter
+    torch.autograd.backward(lv, gs)
+    got = [p.grad.clone() for p in params]
+    # fp64 reference
+    pd = [p.detach().double().requires_grad_(True) for p in params]
+    x = img.double().permute(0, 3, 1, 2)
+    outs = []
+    for i in range(3):
+        x = torch.nn.functional.leaky_relu(torch.nn.functional.conv2d(x, pd[4 * i], pd[4 * i + 1], stride=2, padding=1), 0.01)
+        x = torch.nn.functional.leaky_relu(torch.nn.functional.conv2d(x, pd[4 * i + 2], pd[4 * i + 3], stride=1, padding=1), 0.01)
+        outs.append(x)
+    for a, b in zip(lv, outs):
+        assert a.shape == b.permute(0, 2, 3, 1).shape
+        assert_close(a, b.permute(0, 2, 3, 1), 1e-5, 1e-6)
+    # gradients: drop upstream gradient where a pre-activation is within 1e-6 of the LeakyReLU kink? not needed: fp32 vs fp64 on the
+    # same side of 0 except for |x| < 1e-7 -- measure-zero for these random inputs
+    torch.autograd.backward(outs, [g.double().permute(0, 3, 1, 2) for g in gs])
+    for a, r in zip(got, pd):
+        assert_close(a, r.grad, 1e-4, 1e-5 * float(r.grad.abs().max()))
