@@ -84,16 +84,15 @@ _SIGS = {
     "hnr_nbr_bwd_f16_packed_bytes": (i64, []),
     "hnr_nbr_bwd_f16": (C.c_int, [vp] * 8 + [i64, i64, vp, i64, vp]),
     "hnr_dz_extras_bwd": (C.c_int, [vp, vp, i64, i64, i64, vp, vp]),
-    "hnr_wgrad_img": (C.c_int, [C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), C.POINTER(i64), C.POINTER(vp),
-                                C.POINTER(i64), i64, vp]),
     "hnr_wgrad_img_jobs": (C.c_int, [C.c_int, C.POINTER(vp), C.POINTER(i64), C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), C.POINTER(i64),
-                                     C.POINTER(vp), C.POINTER(i64), C.POINTER(i64), vp]),
+                                     C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), vp]),
     "hnr_chain_f16_forward_train": (C.c_int, [C.POINTER(vp), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), f32c, C.c_int, C.POINTER(i64),
                                               C.POINTER(i64), C.POINTER(i64), C.POINTER(C.c_int), vp, C.POINTER(i64), vp, C.POINTER(f32c),
                                               C.POINTER(f32c), C.POINTER(vp), C.POINTER(i64), vp, i64, vp, vp, C.c_int, vp, i64, vp, vp,
                                               C.POINTER(vp), vp]),
     "hnr_chain_bwd_f16": (C.c_int, [C.c_int, C.POINTER(i64), C.POINTER(i64), i64, C.c_int, vp, i64, vp, i64, C.POINTER(vp), C.POINTER(vp), vp,
                                     C.POINTER(i64), vp, i64, i64, vp]),
+    "hnr_train_loss": (C.c_int, [vp, vp, vp, i64, vp, i64, f32c, f32c, vp, vp, vp, vp]),
     "hnr_pyramid_fwd": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), i64, i64, i64, vp]),
     "hnr_pyramid_bwd": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), i64, i64, i64, vp]),
     "hnr_pack_job_bytes": (i64, []),

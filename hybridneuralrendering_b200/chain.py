@@ -40,6 +40,15 @@ def _cols_index(cols0, device):
     return ent
 
 
+def _cols_map32(cols0, kp, device):
+    """device int32 map kernel input column -> reference column (-1 = padding), padded to kp entries; cached per device"""
+    key = (str(device), tuple(cols0), kp, "map32")
+    ent = _IDX_CACHE.get(key)
+    if ent is None:
+        ent = _IDX_CACHE[key] = torch.tensor(list(cols0) + [-1] * (kp - len(cols0)), device=device, dtype=torch.int32)
+    return ent
+
+
 def _cols_real(cols0, device):
     """(reference column, kernel column) index tensors of the real (non-padding) columns of a column order, cached per device"""
     key = (str(device), tuple(cols0), "real")
@@ -259,23 +268,24 @@ def chain_backward_fused(pc: PackedChain, pb: PackedChainBwd, Ws, images, y_top:
         check(lib().hnr_chain_bwd_f16(nl, i64_array(pc.Np), i64_array(pc.N), NX, act_top, ptr(dY), dY.stride(0), ptr(y_top), y_top.stride(0),
                                       ptr_array(himg + [None] * (4 - len(himg))), ptr_array(dz + [None] * (4 - nl)), ptr(pb.wpack),
                                       i64_array(pb.w_off), ptr(dX), ldx, M, stream()), "chain_bwd_f16")
-    gw = torch.zeros((nl, NMAX, WG_LDO), device=dev, dtype=torch.float32)
+    # ONE zero fill for the chain's parameter-shaped gradients; the weight-gradient kernel accumulates straight into them (layer 0 through
+    # the column map of the kernel's source order)
+    sizes = []
+    for l in range(nl):
+        sizes += [Ws[l].numel(), Ws[l].shape[0]]
+    pad4 = lambda n_: (n_ + 3) // 4 * 4                           # 16-byte aligned views
+    flat = torch.zeros(sum(pad4(n_) for n_ in sizes), device=dev, dtype=torch.float32)
+    dWs, dbs, o = [], [], 0
+    for l in range(nl):
+        dWs.append(flat[o:o + sizes[2 * l]].view_as(Ws[l])); o += pad4(sizes[2 * l])
+        dbs.append(flat[o:o + sizes[2 * l + 1]]); o += pad4(sizes[2 * l + 1])
+    cmap = _cols_map32(cols0, pc.Kp[0], dev) if cols0 is not None else None
     rp = mlp_tc.rows_padded(M)
     with ops._launch(name="wgrad_img"):
         check(lib().hnr_wgrad_img_jobs(nl, ptr_array(dz), i64_array(pc.Np), ptr_array([x0img] + himg), None, i64_array([pc.Kp[0]] + pc.Np[:-1]),
-                                       i64_array([0] * nl), ptr_array([gw[l] for l in range(nl)]), i64_array([WG_LDO] * nl),
-                                       i64_array([rp] * nl), stream()), "wgrad_img_jobs")
-    dWs, dbs = [], []
-    for l in range(nl):
-        N, K = Ws[l].shape
-        cb = pc.Kp[0] if l == 0 else pc.Np[l - 1]
-        if l == 0 and cols0 is not None:
-            ref_idx, kern_idx = _cols_real(cols0, dev)                    # no boolean-mask indexing: that would synchronise with the device
-            dW = torch.zeros((N, K), device=dev, dtype=torch.float32).index_copy_(1, ref_idx, gw[0][:N].index_select(1, kern_idx))
-        else:
-            dW = gw[l][:N, :K].contiguous()
-        dWs.append(dW)
-        dbs.append(gw[l][:N, cb].contiguous())
+                                       i64_array([0] * nl), ptr_array(dWs), ptr_array(dbs), ptr_array([cmap] + [None] * (nl - 1)),
+                                       i64_array([w.shape[0] for w in Ws]), i64_array([w.shape[1] for w in Ws]), i64_array([rp] * nl), stream()),
+              "wgrad_img_jobs")
     d_srcs, off = [], 0
     for i, k in enumerate(ks):
         g = None

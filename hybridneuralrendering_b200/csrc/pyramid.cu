@@ -104,65 +104,94 @@ __global__ void __launch_bounds__(128) conv_bwd_data_kernel(const float* __restr
 }
 
 // ---------------------------------------------------------------------------------------------------------------- weight gradient
-// One block = one strip of TW output pixels of one output row.  Shared memory: gated gradients g[TW][COUT] and the three input rows
-// of the strip's halo in[3][TW*STRIDE + 2][CIN].  Thread t owns weights t, t + 256, ... (index = (tap * CIN + ci) * COUT + co).
+// dW[co][ci][ky][kx] = sum over pixels of g[p][co] * in[p * STRIDE - 1 + k][ci],  g = dOut * act'(Out);  db[co] = sum g[p][co].
+// A block walks `rb` output rows of one 64-pixel strip.  Per row it stages the gated gradients g[64][COUT] and the three input rows
+// of the halo in shared memory (channels zero-padded to multiples of 4).  A thread owns a 4 (co) x 4 (ci) x 3 (kx) register tile of
+// one kernel row ky -- per pixel one float4 of g and three float4 of the inputs feed 48 FMAs (1 shared-memory read per 12 FMAs;
+// the first version read two operands per FMA and serialised ~2400 same-address global atomics per weight).  The 256 threads form
+// NG = 256 / TPG pixel groups (TPG = tiles per kernel row x 3); groups are folded in shared memory, then one global atomic per
+// weight and block.
 template <int CIN, int COUT, int STRIDE>
 __global__ void __launch_bounds__(256) conv_bwd_weight_kernel(const float* __restrict__ dOut, const float* __restrict__ Out, const float* __restrict__ In,
-                                                              float* __restrict__ dW, float* __restrict__ db, int V, int Hi, int Wi, int Ho, int Wo) {
+                                                              float* __restrict__ dW, float* __restrict__ db, int V, int Hi, int Wi, int Ho, int Wo, int rb) {
     constexpr int TW = 64;
-    constexpr int RB = 4;                       // output rows per block: 4x fewer atomics per weight
     constexpr int IW = TW * STRIDE + 2;
+    constexpr int CP = (CIN + 3) / 4 * 4, OP = (COUT + 3) / 4 * 4, NCI = CP / 4, NCO = OP / 4;
+    constexpr int TPG = NCO * NCI * 3;
+    constexpr int NG = 256 / TPG;
     constexpr int NW = 9 * CIN * COUT;
-    constexpr int PER = (NW + 255) / 256;
-    __shared__ float g[TW][COUT + 1];
-    __shared__ float xin[3][IW][CIN + 1];
-    const int strips = (Wo + TW - 1) / TW, rgroups = (Ho + RB - 1) / RB;
+    static_assert(NG >= 1, "tile count");
+    __shared__ __align__(16) float g[TW][OP];
+    __shared__ __align__(16) float xin[3][IW][CP];
+    __shared__ float red[NW + COUT];
+    const int strips = (Wo + TW - 1) / TW, rgroups = (Ho + rb - 1) / rb;
     const int sx = blockIdx.x % strips, rg = (blockIdx.x / strips) % rgroups, v = blockIdx.x / (strips * rgroups);
-    const int ox0 = sx * TW;
-    float acc[PER];
+    const int ox0 = sx * TW, ix0 = ox0 * STRIDE - 1;
+    const int t = threadIdx.x, grp = t / TPG, u = t - grp * TPG;
+    const bool worker = grp < NG;
+    const int ky = u / (NCO * NCI), co4 = (u / NCI) % NCO, ci4 = u % NCI;
+    float acc[3][4][4];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int d = 0; d < 4; ++d) acc[a][c][d] = 0.f;
     float bsum = 0.f;
+    for (int i = t; i < NW + COUT; i += 256) red[i] = 0.f;
+    const int oy_end = min(Ho, rg * rb + rb);
+    for (int oy = rg * rb; oy < oy_end; ++oy) {
+        __syncthreads();
+        for (int i = t; i < TW * OP; i += 256) {
+            const int px = i / OP, co = i - px * OP, ox = ox0 + px;
+            float val = 0.f;
+            if (ox < Wo && co < COUT) {
+                const int64_t p = ((int64_t)v * Ho + oy) * Wo + ox;
+                val = dOut[p * COUT + co] * lrelu_g(Out[p * COUT + co]);
+            }
+            g[px][co] = val;
+        }
+        for (int i = t; i < 3 * IW * CP; i += 256) {
+            const int ci = i % CP, xx = (i / CP) % IW, kr = i / (CP * IW);
+            const int iy = oy * STRIDE - 1 + kr, ix = ix0 + xx;
+            xin[kr][xx][ci] = (ci < CIN && iy >= 0 && iy < Hi && ix >= 0 && ix < Wi) ? In[(((int64_t)v * Hi + iy) * Wi + ix) * CIN + ci] : 0.f;
+        }
+        __syncthreads();
+        if (worker) {
+            for (int px = grp; px < TW; px += NG) {
+                const float4 gv = *reinterpret_cast<const float4*>(&g[px][co4 * 4]);
+                const float gg[4] = {gv.x, gv.y, gv.z, gv.w};
 #pragma unroll
-    for (int k = 0; k < PER; ++k) acc[k] = 0.f;
-    for (int oy = rg * RB; oy < min(Ho, rg * RB + RB); ++oy) {
+                for (int kx = 0; kx < 3; ++kx) {
+                    const float4 xv = *reinterpret_cast<const float4*>(&xin[ky][px * STRIDE + kx][ci4 * 4]);
+                    const float xx[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+#pragma unroll
+                        for (int d = 0; d < 4; ++d) acc[kx][c][d] = fmaf(gg[c], xx[d], acc[kx][c][d]);
+                }
+            }
+        }
+        if (t < COUT)
+            for (int px = 0; px < TW; ++px) bsum += g[px][t];
+    }
     __syncthreads();
-    for (int i = threadIdx.x; i < TW * COUT; i += 256) {
-        const int px = i / COUT, co = i - px * COUT, ox = ox0 + px;
-        float val = 0.f;
-        if (ox < Wo) {
-            const int64_t p = ((int64_t)v * Ho + oy) * Wo + ox;
-            val = dOut[p * COUT + co] * lrelu_g(Out[p * COUT + co]);
-        }
-        g[px][co] = val;
+    if (worker) {
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+                for (int d = 0; d < 4; ++d) {
+                    const int co = co4 * 4 + c, ci = ci4 * 4 + d;
+                    if (co < COUT && ci < CIN && acc[kx][c][d] != 0.f) atomicAdd(&red[(co * CIN + ci) * 9 + ky * 3 + kx], acc[kx][c][d]);
+                }
     }
-    const int ix0 = ox0 * STRIDE - 1;
-    for (int i = threadIdx.x; i < 3 * IW * CIN; i += 256) {
-        const int ci = i % CIN, xx = (i / CIN) % IW, ky = i / (CIN * IW);
-        const int iy = oy * STRIDE - 1 + ky, ix = ix0 + xx;
-        xin[ky][xx][ci] = (iy >= 0 && iy < Hi && ix >= 0 && ix < Wi) ? In[(((int64_t)v * Hi + iy) * Wi + ix) * CIN + ci] : 0.f;
-    }
+    if (t < COUT) red[NW + t] = bsum;
     __syncthreads();
-#pragma unroll
-    for (int k = 0; k < PER; ++k) {
-        const int w = threadIdx.x + k * 256;
-        if (w < NW) {
-            const int co = w % COUT, ci = (w / COUT) % CIN, tap = w / (COUT * CIN), ky = tap / 3, kx = tap - ky * 3;
-            float a = 0.f;
-            for (int px = 0; px < TW; ++px) a = fmaf(g[px][co], xin[ky][px * STRIDE + kx][ci], a);
-            acc[k] += a;
-        }
-    }
-    if (threadIdx.x < COUT)
-        for (int px = 0; px < TW; ++px) bsum += g[px][threadIdx.x];
-    }
-#pragma unroll
-    for (int k = 0; k < PER; ++k) {
-        const int w = threadIdx.x + k * 256;
-        if (w < NW && acc[k] != 0.f) {
-            const int co = w % COUT, ci = (w / COUT) % CIN, tap = w / (COUT * CIN);
-            atomicAdd(dW + (co * CIN + ci) * 9 + tap, acc[k]);
-        }
-    }
-    if (threadIdx.x < COUT && bsum != 0.f) atomicAdd(db + threadIdx.x, bsum);
+    for (int i = t; i < NW; i += 256)
+        if (red[i] != 0.f) atomicAdd(dW + i, red[i]);
+    if (t < COUT && red[NW + t] != 0.f) atomicAdd(db + t, red[NW + t]);
 }
 
 template <int CIN, int COUT, int STRIDE>
@@ -174,8 +203,12 @@ int launch_fwd(const float* in, const float* W, const float* b, float* out, int 
 template <int CIN, int COUT, int STRIDE>
 int launch_bwd(const float* dOut, const float* Out, const float* In, const float* W, const float* ext, float* dIn, float* dW, float* db, int V,
                int Hi, int Wi, int Ho, int Wo, cudaStream_t st) {
-    const int strips = (Wo + 63) / 64, rgroups = (Ho + 3) / 4;
-    conv_bwd_weight_kernel<CIN, COUT, STRIDE><<<(unsigned)(strips * rgroups * V), 256, 0, st>>>(dOut, Out, In, dW, db, V, Hi, Wi, Ho, Wo);
+    // rows per block: ~4 blocks per SM overall (few global atomics per weight, enough blocks to fill the machine)
+    const int strips = (Wo + 63) / 64;
+    int rb = (int)hnr_cdiv((int64_t)strips * Ho * V, 4 * HNR_NUM_SMS);
+    if (rb < 1) rb = 1;
+    const int rgroups = (Ho + rb - 1) / rb;
+    conv_bwd_weight_kernel<CIN, COUT, STRIDE><<<(unsigned)(strips * rgroups * V), 256, 0, st>>>(dOut, Out, In, dW, db, V, Hi, Wi, Ho, Wo, rb);
     if (dIn) {
         const int64_t n = (int64_t)V * Hi * Wi;
         conv_bwd_data_kernel<CIN, COUT, STRIDE><<<(unsigned)hnr_cdiv(n, 128), 128, 0, st>>>(dOut, Out, W, ext, dIn, V, Hi, Wi, Ho, Wo);

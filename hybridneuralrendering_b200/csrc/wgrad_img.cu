@@ -42,8 +42,10 @@ struct WJob {
     const uint8_t* a;      // dZ image, ca columns (the layer's padded output width)
     const uint8_t* b;      // X image, cb columns
     const uint8_t* e;      // optional extra image, ce columns (NULL: none)
-    float* out;            // (ca, ldo) fp32, += : columns [0, cb) dW vs X, [cb, cb+ce) dW vs extra, column cb+ce = db
-    int ca, cb, ce, ldo;
+    float* dw;             // (n_rows, k_cols) fp32 row-major, += : operand column c lands in dW column colmap[c] (identity when NULL; < 0 or
+    float* db;             //   >= k_cols: dropped -- padding columns); db (n_rows) += column sums of dZ
+    const int32_t* colmap;
+    int ca, cb, ce, n_rows, k_cols;
     int nhalf;             // ceil(ca / 128): 128-row blocks of the output, one per CTA of a group
     int cta_begin;         // first CTA of this job; the job owns CTAs [cta_begin, next job's cta_begin), a multiple of nhalf
     int64_t nslab;         // 32-row slabs of this job's images
@@ -181,18 +183,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_img_kernel(const __grid_con
         tc_fence_after();
         const int q = warp & 3;                                     // TMEM lane quarter this warp may read
         const int n = half * 128 + q * 32 + lane;
-        const bool live = q * 32 + lane < hw;
+        const bool live = q * 32 + lane < hw && n < J.n_rows;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-        float* o = J.out + (int64_t)n * J.ldo;
+        float* o = J.dw + (int64_t)n * J.k_cols;
         for (int c0 = 0; c0 < ct + 16; c0 += 16) {
             float v[16];
             tmem_ld16(taddr + c0, v);
             if (!live) continue;
             if (c0 < ct) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) atomicAdd(o + c0 + i, v[i]);
-            } else {
-                atomicAdd(o + ct, v[0]);                            // every column of the ones block holds db
+                for (int i = 0; i < 16; ++i) {
+                    const int col = J.colmap ? J.colmap[c0 + i] : c0 + i;
+                    if (col >= 0 && col < J.k_cols) atomicAdd(o + col, v[i]);
+                }
+            } else if (J.db) {
+                atomicAdd(J.db + n, v[0]);                          // every column of the ones block holds db
             }
         }
         tc_fence_before();
@@ -205,12 +210,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_img_kernel(const __grid_con
 
 // Weight + bias gradients of up to 4 layers in one launch.  Per job i: a[i] = split image of dZ (ca[i] columns = the layer's
 // padded output width, multiple of 16, <= 256), b[i] = split image of the layer input (cb[i] columns, multiple of 16, <= 288),
-// e[i] = optional extra input image (ce[i] columns, 0 or 16), out[i] = (ca[i], ldo[i]) fp32 accumulated into (zero it first):
-// columns [0, cb+ce) = dW in operand-column order, column cb+ce = db.  rows_pad[i] % 128 == 0 rows per image; padding rows of
-// the dZ images must be zero and those of the input images finite.
+// e[i] = optional extra input image (ce[i] columns, 0 or 16).  Results are ACCUMULATED (zero them first) straight into the
+// parameter-shaped gradients: dw[i] (n_rows[i], k_cols[i]) row-major -- operand column c goes to column colmap[i][c] (device int32
+// array of cb+ce entries; NULL = identity; entries < 0 or >= k_cols are padding and dropped) -- and db[i] (n_rows[i]) (may be NULL).
+// rows_pad[i] % 128 == 0 rows per image; padding rows of the dZ images must be zero and those of the input images finite.
 extern "C" int hnr_wgrad_img_jobs(int njob, const void* const* a, const int64_t* ca, const void* const* b, const void* const* e,
-                                  const int64_t* cb, const int64_t* ce, float* const* out, const int64_t* ldo, const int64_t* rows_pad,
-                                  void* stream) {
+                                  const int64_t* cb, const int64_t* ce, float* const* dw, float* const* db, const int32_t* const* colmap,
+                                  const int64_t* n_rows, const int64_t* k_cols, const int64_t* rows_pad, void* stream) {
     HNR_CHECK_ARG(njob >= 1 && njob <= MAXJOB, "wgrad_img: 1..4 jobs");
     WArgs A{};
     A.njob = njob;
@@ -221,7 +227,7 @@ extern "C" int hnr_wgrad_img_jobs(int njob, const void* const* a, const int64_t*
         HNR_CHECK_ARG(rows_pad[i] % 128 == 0, "wgrad_img: rows_pad must be a multiple of 128");
         HNR_CHECK_ARG(ca[i] >= 16 && ca[i] % 16 == 0 && ca[i] <= 256, "wgrad_img: dZ width");
         HNR_CHECK_ARG(cb[i] > 0 && cb[i] % 16 == 0 && (ce[i] == 0 || ce[i] == 16) && cb[i] + ce[i] <= B_MAX_COLS, "wgrad_img: operand widths");
-        HNR_CHECK_ARG(ldo[i] >= cb[i] + ce[i] + 1, "wgrad_img: ldo too small");
+        HNR_CHECK_ARG(n_rows[i] > 0 && n_rows[i] <= ca[i] && k_cols[i] > 0 && dw[i], "wgrad_img: gradient shape");
         nhalf[i] = (int)((ca[i] + 127) / 128);
         cost[i] = (double)rows_pad[i] * (double)(ca[i] + nhalf[i] * (cb[i] + ce[i]));
         total += cost[i];
@@ -243,7 +249,8 @@ extern "C" int hnr_wgrad_img_jobs(int njob, const void* const* a, const int64_t*
     for (int i = 0; i < njob; ++i) {
         WJob& J = A.job[i];
         J.a = (const uint8_t*)a[i]; J.b = (const uint8_t*)b[i]; J.e = (e && ce[i]) ? (const uint8_t*)e[i] : nullptr;
-        J.ca = (int)ca[i]; J.cb = (int)cb[i]; J.ce = J.e ? (int)ce[i] : 0; J.out = out[i]; J.ldo = (int)ldo[i]; J.cta_begin = cta;
+        J.ca = (int)ca[i]; J.cb = (int)cb[i]; J.ce = J.e ? (int)ce[i] : 0; J.dw = dw[i]; J.db = db ? db[i] : nullptr;
+        J.colmap = colmap ? colmap[i] : nullptr; J.n_rows = (int)n_rows[i]; J.k_cols = (int)k_cols[i]; J.cta_begin = cta;
         J.nhalf = nhalf[i]; J.nslab = rows_pad[i] / img::SLAB;
         cta += groups[i] * nhalf[i];
     }
@@ -260,13 +267,4 @@ extern "C" int hnr_wgrad_img_jobs(int njob, const void* const* a, const int64_t*
     wgrad_img_kernel<<<cta, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(A);
     HNR_CHECK_LAUNCH("wgrad_img");
     return HNR_OK;
-}
-
-// the per-neighbour MLP's form: every dZ image 256 columns wide, one row count
-extern "C" int hnr_wgrad_img(int njob, const void* const* a, const void* const* b, const void* const* e, const int64_t* cb,
-                             const int64_t* ce, float* const* out, const int64_t* ldo, int64_t rows_pad, void* stream) {
-    HNR_CHECK_ARG(njob >= 1 && njob <= MAXJOB, "wgrad_img: 1..4 jobs");
-    int64_t ca[MAXJOB], rp[MAXJOB];
-    for (int i = 0; i < njob; ++i) { ca[i] = 256; rp[i] = rows_pad; }
-    return hnr_wgrad_img_jobs(njob, a, ca, b, e, cb, ce, out, ldo, rp, stream);
 }

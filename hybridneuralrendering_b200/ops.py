@@ -521,8 +521,17 @@ class NbrMlpTrainFn(torch.autograd.Function):
         d_sigma, dX5 = _f32c(d_sigma), _f32c(dX5)
         dz = [mlp_tc.image_empty(rows, HID, dev) for _ in range(4)]                 # dZ_0 .. dZ_3
         d_wc = torch.empty((Nv, K), device=dev, dtype=torch.float32)
-        small = torch.zeros(HID + 1 + 4 * HID * WG_LDO, device=dev, dtype=torch.float32)   # one fill: d_walpha | d_balpha | 4 x (256, 320)
-        d_wa, d_ba, gw = small[:HID], small[HID:HID + 1], small[HID + 1:].view(4, HID, WG_LDO)
+        # ONE zero fill for every small gradient of this stage: d_walpha | d_balpha | dW1, db1, ... dW4, db4 (parameter-shaped views; the
+        # weight-gradient kernel accumulates straight into them through its column maps)
+        shapes = [(HID, X0_W), (HID,), (HID, HID), (HID,), (HID, HID + E_W), (HID,), (HID, HID), (HID,)]
+        sizes = [HID, 1] + [int(torch.Size(sh).numel()) for sh in shapes]
+        pad4 = lambda n_: (n_ + 3) // 4 * 4                       # 16-byte aligned views: the fused Adam takes its vector path
+        small = torch.zeros(sum(pad4(n_) for n_ in sizes), device=dev, dtype=torch.float32)
+        views, o = [], 0
+        for n_ in sizes:
+            views.append(small[o:o + n_]); o += pad4(n_)
+        d_wa, d_ba = views[0], views[1]
+        gW = [views[2 + i].view(shapes[i]) for i in range(8)]
         with _launch(name="alpha_ksum_bwd"):
             check(lib().hnr_alpha_ksum_bwd_img(ptr(h3), ptr(weight), ptr(confc), ptr(vlist), ptr(w_alpha), ptr(araw), ptr(d_sigma), ptr(dX5),
                                                Nv, K, ptr(dz[3]), ptr(d_wc), ptr(d_wa), ptr(d_ba), stream()), "alpha_ksum_bwd_img")
@@ -539,18 +548,14 @@ class NbrMlpTrainFn(torch.autograd.Function):
         W3c = _f32c(W3)
         with _launch(name="dz_extras_bwd"):
             check(lib().hnr_dz_extras_bwd(ptr(dz[2]), ptr(W3c), W3c.stride(0), HID, rows, ptr(dE), stream()), "dz_extras_bwd")
+        x0map, e3map = _wgrad_colmaps(dev)
         with _launch(name="wgrad_img"):
-            check(lib().hnr_wgrad_img(4, ptr_array(dz), ptr_array([x0img, h0, h1, h2]), ptr_array([None, None, eimg, None]),
-                                      i64_array([mlp_tc.X0_IMG_W, HID, HID, HID]), i64_array([0, 0, mlp_tc.E_IMG_W, 0]),
-                                      ptr_array([gw[0], gw[1], gw[2], gw[3]]), i64_array([WG_LDO] * 4), mlp_tc.rows_padded(rows), stream()),
-                  "wgrad_img")
-        ref_idx, kern_idx = _x0_cols(dev)
-        dW1 = torch.zeros((HID, X0_W), device=dev, dtype=torch.float32).index_copy_(1, ref_idx, gw[0].index_select(1, kern_idx))
-        db1 = gw[0][:, mlp_tc.X0_IMG_W]
-        dW2, db2 = gw[1][:, :HID], gw[1][:, HID]
-        dW3 = torch.cat([gw[2][:, :HID], gw[2][:, HID:HID + E_W]], dim=1)
-        db3 = gw[2][:, HID + mlp_tc.E_IMG_W]
-        dW4, db4 = gw[3][:, :HID], gw[3][:, HID]
+            check(lib().hnr_wgrad_img_jobs(4, ptr_array(dz), i64_array([HID] * 4), ptr_array([x0img, h0, h1, h2]), ptr_array([None, None, eimg, None]),
+                                           i64_array([mlp_tc.X0_IMG_W, HID, HID, HID]), i64_array([0, 0, mlp_tc.E_IMG_W, 0]),
+                                           ptr_array([gW[0], gW[2], gW[4], gW[6]]), ptr_array([gW[1], gW[3], gW[5], gW[7]]),
+                                           ptr_array([x0map, None, e3map, None]), i64_array([HID] * 4), i64_array([X0_W, HID, HID + E_W, HID]),
+                                           i64_array([mlp_tc.rows_padded(rows)] * 4), stream()), "wgrad_img_jobs")
+        dW1, db1, dW2, db2, dW3, db3, dW4, db4 = gW
         ne, nc, nd = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
         d_emb = torch.zeros(ctx.shapes[0], device=dev, dtype=torch.float32) if ne else None
         d_col = torch.zeros(ctx.shapes[1], device=dev, dtype=torch.float32) if nc else None
@@ -559,10 +564,23 @@ class NbrMlpTrainFn(torch.autograd.Function):
             with _launch(name="nbr_features_bwd"):
                 check(lib().hnr_nbr_features_bwd_ld(ptr(dX0), X0_GRAD_W, ptr(dE), ptr(emb), ptr(pidx), None, ptr(vlist), ptr(raydirs),
                                                     ptr(ctx.cam), Nv, K, ptr(d_emb), ptr(d_col), ptr(d_dir), stream()), "nbr_features_bwd_ld")
-        return (d_emb, d_col, d_dir, d_confc, dW1, db1, dW2, db2, dW3, db3, dW4, db4, d_wa.clone().view(ctx.shapes[3]), d_ba.clone().view(ctx.shapes[4]), None)
+        return (d_emb, d_col, d_dir, d_confc, dW1, db1, dW2, db2, dW3, db3, dW4, db4, d_wa.view(ctx.shapes[3]), d_ba.view(ctx.shapes[4]), None)
 
 
-WG_LDO = 320          # row stride of the weight-gradient scratch of hnr_wgrad_img (>= 288 + 16 + 1)
+_WG_MAPS = {}
+
+
+def _wgrad_colmaps(dev):
+    """device int32 column maps of hnr_wgrad_img_jobs for the per-neighbour MLP, cached per device: layer 0 (288 kernel-order
+    columns -> reference column of the 284-wide block1 input, -1 = padding) and layer 2 ([H_1 256 | extras 16] -> 263 columns)"""
+    key = str(dev)
+    if key not in _WG_MAPS:
+        from . import mlp_tc
+        _WG_MAPS[key] = (torch.tensor(mlp_tc.layer1_column_order_f16(), device=dev, dtype=torch.int32),
+                         torch.tensor(list(range(HID + E_W)) + [-1] * (mlp_tc.E_IMG_W - E_W), device=dev, dtype=torch.int32))
+    return _WG_MAPS[key]
+
+
 _X0_COLS = {}
 
 
@@ -581,6 +599,33 @@ def _x0_cols(dev):
 # --------------------------------------------------------------------------------------------
 # image branch
 # --------------------------------------------------------------------------------------------
+class TrainLossFn(torch.autograd.Function):
+    """training loss of the hot path in one launch (csrc/loss.cu): masked MSE (+1e-6) x frame_weight + zero-one regulariser on
+    conf_coefficient; the gradients are computed by the same launch and only scaled in backward."""
+
+    @staticmethod
+    def forward(ctx, color, confc, gt, ray_ids, frame_weight: float, zero_one_weight: float):
+        color = _f32c(color)
+        gt2 = _f32c(gt).reshape(-1, 3)
+        n_rays = color.numel() // 3
+        cc = _f32c(confc) if confc is not None else None
+        dev = color.device
+        loss = torch.zeros((), device=dev, dtype=torch.float32)
+        d_color = torch.empty_like(color)
+        d_cc = torch.empty_like(cc) if cc is not None else None
+        with _launch(name="train_loss"):
+            check(lib().hnr_train_loss(ptr(color), ptr(gt2), ptr(ray_ids), n_rays, ptr(cc), cc.numel() if cc is not None else 0, float(frame_weight),
+                                       float(zero_one_weight), ptr(loss), ptr(d_color), ptr(d_cc), stream()), "train_loss")
+        ctx.save_for_backward(d_color, d_cc if d_cc is not None else torch.empty(0, device=dev))
+        ctx.has_cc = cc is not None
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        d_color, d_cc = ctx.saved_tensors
+        return d_color * g, (d_cc * g if ctx.has_cc else None), None, None, None, None
+
+
 class PyramidFn(torch.autograd.Function):
     """feature pyramid of the image branch (csrc/pyramid.cu): img (V,H,W,3) NHWC + the 12 conv parameters of aux_block_s1/s2/s3 ->
     levels (V,H/2,W/2,6), (V,H/4,W/4,12), (V,H/8,W/8,24) NHWC.  Exact fp32, forward and backward on own kernels (no cuDNN, no

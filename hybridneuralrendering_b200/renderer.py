@@ -52,6 +52,11 @@ def training_loss(output: Dict[str, torch.Tensor], gt_image: torch.Tensor, zero_
     """MSE on ray-masked colours (+1e-6) scaled by frame_weight, plus the zero-one regulariser on
     conf_coefficient (reference models/base_rendering_model.py:1114-1118, :1198-1240).
     `output` is the un-filled output of NeuralPointsRayMarching (R'' kept rays)."""
+    if output.get("ray_ids") is not None and output["coarse_raycolor"].is_cuda:
+        # fused: one launch computes the value and both gradients (csrc/loss.cu); gt is looked up through the query's kept-ray list
+        from . import ops
+        cc = output.get("conf_coefficient") if zero_one_weight > 0 else None
+        return ops.TrainLossFn.apply(output["coarse_raycolor"], cc, gt_image, output["ray_ids"], float(frame_weight), float(zero_one_weight))
     if output.get("ray_ids") is not None:
         gt = gt_image.index_select(1, output["ray_ids"].long())       # kept-ray list from the query: no nonzero(), no host sync
     else:

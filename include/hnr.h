@@ -207,12 +207,12 @@ int hnr_nbr_bwd_f16(const void* dz3, const void* h2, const void* h1, const void*
 /* dE (rows,7) = dZ (image) . W[:, k0:k0+7]: gradient of block3's extra inputs */
 int hnr_dz_extras_bwd(const void* dz, const float* W, int64_t ldw, int64_t k0, int64_t rows, float* dE, void* stream);
 /* weight + bias gradients of up to 4 layers in ONE launch, operands bulk-copied from the images as MN-major UMMA tiles
- * (csrc/wgrad_img.cu).  Job i: out[i] (256, ldo[i]) += [dZ^T X | dZ^T E | dZ^T 1]. */
-int hnr_wgrad_img(int njob, const void* const* a, const void* const* b, const void* const* e, const int64_t* cb, const int64_t* ce,
-                  float* const* out, const int64_t* ldo, int64_t rows_pad, void* stream);
-/* generic form: per-job dZ width ca[i] (the layer's padded output width, <= 256) and row count rows_pad[i] */
+ * (csrc/wgrad_img.cu).  Job i accumulates dZ_i^T [X_i | E_i] straight into the parameter-shaped dw[i] (n_rows, k_cols) through an
+ * optional column map (kernel input-column order -> reference column, < 0 = padding) and the column sums of dZ_i into db[i];
+ * ca[i] = dZ image width (the layer's padded output width, <= 256), rows_pad[i] = image rows. */
 int hnr_wgrad_img_jobs(int njob, const void* const* a, const int64_t* ca, const void* const* b, const void* const* e, const int64_t* cb,
-                       const int64_t* ce, float* const* out, const int64_t* ldo, const int64_t* rows_pad, void* stream);
+                       const int64_t* ce, float* const* dw, float* const* db, const int32_t* const* colmap, const int64_t* n_rows,
+                       const int64_t* k_cols, const int64_t* rows_pad, void* stream);
 /* Fused training path of the per-sample chains (color_feature_branch, aux_merge_weight_block, color_mixup_block;
  * point_aggregators.py:1028-1037, :1188-1217, :1285-1334).  hnr_chain_f16_forward_train = hnr_chain_f16_forward that also saves
  * the concatenated input (x0img, Kp[0] columns) and the inner outputs (himg[l], Np[l] columns) as split images;
@@ -227,6 +227,10 @@ int hnr_chain_f16_forward_train(const float* const* src, const int64_t* src_ld, 
 int hnr_chain_bwd_f16(int nlayer, const int64_t* Np, const int64_t* N, int64_t NX, int act_top, const float* dY, int64_t lddy,
                       const float* Ytop, int64_t ldyt, const void* const* gimg, void* const* dzimg, const void* wpackT,
                       const int64_t* w_off, float* dX, int64_t ldx, int64_t M, void* stream);
+/* Training loss in one launch (csrc/loss.cu): masked MSE (+1e-6) x frame_weight + zero-one regulariser on conf_coefficient
+ * (models/base_rendering_model.py:1114-1118, :1205-1206, :1229-1240); value and both gradients.  loss must be zeroed by the caller. */
+int hnr_train_loss(const float* color, const float* gt, const int32_t* ray_ids, int64_t n_rays, const float* confc, int64_t n_conf,
+                   float frame_weight, float zero_one_weight, float* loss, float* d_color, float* d_confc, void* stream);
 /* Feature pyramid of the image branch (csrc/pyramid.cu): the six 3x3 convolutions + LeakyReLU of aux_block_s1/s2/s3
  * (models/aggregators/point_aggregators.py:598-630, :1047-1063), exact fp32, NHWC, forward and backward.  w/b: six torch-layout
  * (Cout,Cin,3,3) / (Cout) tensors; act: the six activated outputs (act[1], act[3], act[5] are the levels the lookup reads);

@@ -291,9 +291,31 @@ def test_own_pyramid_kernels_match_torch_conv(V, H, W):
         outs.append(x)
     for a, b in zip(lv, outs):
         assert a.shape == b.permute(0, 2, 3, 1).shape
-        assert_close(a, b.permute(0, 2, 3, 1), 1e-5, 1e-6)
+        assert_close(a, b.permute(0, 2, 3, 1), 1e-5, 2e-6 * float(b.abs().max()))
     # gradients: drop upstream gradient where a pre-activation is within 1e-6 of the LeakyReLU kink? not needed: fp32 vs fp64 on the
     # same side of 0 except for |x| < 1e-7 -- measure-zero for these random inputs
     torch.autograd.backward(outs, [g.double().permute(0, 3, 1, 2) for g in gs])
     for a, r in zip(got, pd):
         assert_close(a, r.grad, 1e-4, 1e-5 * float(r.grad.abs().max()))
+
+
+def test_fused_training_loss_matches_torch():
+    """csrc/loss.cu: masked MSE (+1e-6) x frame_weight + 1e-4 x zero-one regulariser (base_rendering_model.py:1114-1118, :1229-1240) in
+    one launch vs the same expression in torch fp64 -- value and both gradients, incl. conf values outside the clamp"""
+    from hybridneuralrendering_b200.renderer import training_loss
+    g = torch.Generator().manual_seed(3)
+    R, Rk, SR, K = 500, 333, 24, 8
+    ids = torch.randperm(R, generator=g)[:Rk].sort()[0].int().cuda()
+    color = torch.rand(1, Rk, 3, generator=g).cuda().requires_grad_(True)
+    cc = (torch.rand(1, Rk, SR, K, generator=g) * 1.2 - 0.1).cuda().requires_grad_(True)        # some values beyond [1e-3, 1 - 1e-3]
+    gt = torch.rand(1, R, 3, generator=g).cuda()
+    out = {"coarse_raycolor": color, "conf_coefficient": cc, "ray_ids": ids, "ray_mask": None}
+    loss = training_loss(out, gt, 1e-4, 0.7)
+    (loss * 3.0).backward()
+    c64, cc64 = color.detach().double().requires_grad_(True), cc.detach().double().requires_grad_(True)
+    v = cc64.clamp(1e-3, 1 - 1e-3)
+    ref = (torch.nn.functional.mse_loss(c64, gt.double()[:, ids.long()]) + 1e-6) * 0.7 + 1e-4 * torch.mean(torch.log(v) + torch.log(1 - v))
+    (ref * 3.0).backward()
+    assert_close(loss, ref, 1e-5, 1e-8)
+    assert_close(color.grad, c64.grad, 1e-5, 1e-10)
+    assert_close(cc.grad, cc64.grad, 1e-5, 1e-12)

@@ -50,18 +50,24 @@ def test_wgrad_img_matches_fp64(rows):
     a = [mlp_tc.dense_to_image(t) for t in dz]
     b = [mlp_tc.dense_to_image(t) for t in xs]
     e = [mlp_tc.dense_to_image(t) if t is not None else None for t in es]
-    out = torch.zeros((4, 256, 320), device=dev)
-    check(lib().hnr_wgrad_img(4, ptr_array(a), ptr_array(b), ptr_array(e), i64_array([s[0] for s in shapes]), i64_array([s[1] for s in shapes]),
-                              ptr_array([out[i] for i in range(4)]), i64_array([320] * 4), mlp_tc.rows_padded(rows), stream()), "wgrad_img")
+    dW = [torch.zeros((256, cb + ce), device=dev) for cb, ce in shapes]
+    db = [torch.zeros(256, device=dev) for _ in shapes]
+    # job 0 goes through a column map (reversed columns), the others are identity
+    rev = torch.arange(287, -1, -1, device=dev, dtype=torch.int32)
+    check(lib().hnr_wgrad_img_jobs(4, ptr_array(a), i64_array([256] * 4), ptr_array(b), ptr_array(e), i64_array([s[0] for s in shapes]),
+                                   i64_array([s[1] for s in shapes]), ptr_array(dW), ptr_array(db), ptr_array([rev, None, None, None]),
+                                   i64_array([256] * 4), i64_array([s[0] + s[1] for s in shapes]), i64_array([mlp_tc.rows_padded(rows)] * 4), stream()),
+          "wgrad_img_jobs")
     torch.cuda.synchronize()
     for i, (cb, ce) in enumerate(shapes):
         ref = dz[i].double().t() @ xs[i].double()
-        assert _rel_max(out[i][:, :cb], ref) < TOL, (i, "dW", _rel_max(out[i][:, :cb], ref))
+        got = dW[i][:, :cb].flip(1) if i == 0 else dW[i][:, :cb]
+        assert _rel_max(got, ref) < TOL, (i, "dW", _rel_max(got, ref))
         if ce:
             refe = dz[i].double().t() @ es[i].double()
-            assert _rel_max(out[i][:, cb:cb + ce], refe) < TOL, (i, "dW extras")
+            assert _rel_max(dW[i][:, cb:cb + ce], refe) < TOL, (i, "dW extras")
         refb = dz[i].double().sum(0)
-        assert _rel_max(out[i][:, cb + ce], refb) < TOL, (i, "db", _rel_max(out[i][:, cb + ce], refb))
+        assert _rel_max(db[i], refb) < TOL, (i, "db", _rel_max(db[i], refb))
 
 
 @pytest.mark.parametrize("rows", [128 * 3 + 40, 128 * 148 * 2 + 77])
