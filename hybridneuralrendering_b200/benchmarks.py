@@ -85,18 +85,22 @@ def train_step_benchmark(dev, steps: int = 5, warmup: int = 3, world: int = 1, p
     barrier()
     ops.LAUNCHES = 0
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    import time as _time
     s.record()
+    t_host = _time.perf_counter()
     for _ in range(steps):
         flush.zero_()
         loss, _ = parallel.train_step(net, frame, opts, next_frame_shard=nxt)
     parallel.flush_pending(net)
     e.record()
+    host_ms = (_time.perf_counter() - t_host) / steps * 1e3           # time the HOST needs to issue a step (no synchronisation in the loop)
     barrier()
     launches = ops.LAUNCHES
     ms_local = s.elapsed_time(e) / steps
     ms_step = _device_max(ms_local, dev, world)
     res = {"metric": "train rays/s (fwd+bwd)", "value": world * R / (ms_step * 1e-3), "unit": "rays/s", "ms_per_step": ms_step,
            "rays_per_step_per_gpu": R, "points": points, "views": views, "loss": float(loss), "launches_per_step": launches // steps,
+           "host_issue_ms_per_step": host_ms,
            "step": "forward + loss + backward" + (" + NCCL gradient all-reduce" if world > 1 else "") + " + Adam (network + point tables)",
            "config": workload}
     # ---- end to end: the frame dict arrives in pinned host memory every step, the loss goes back to the host every step
@@ -171,7 +175,7 @@ def train_step_benchmark(dev, steps: int = 5, warmup: int = 3, world: int = 1, p
         for _ in range(2):
             fwd_bwd()
         barrier()
-        mine = {"rank": rank, "ms_step_local": round(ms_local, 3), "ms_fwd_bwd_no_collective": round(res["ms_fwd_bwd"], 3), "valid_samples": int(ex.n_valid)}
+        mine = {"rank": rank, "ms_step_local": round(ms_local, 3), "host_issue_ms_per_step": round(host_ms, 3), "ms_fwd_bwd_no_collective": round(res["ms_fwd_bwd"], 3), "valid_samples": int(ex.n_valid)}
         allr = [None] * world
         dist.all_gather_object(allr, mine)
         res["ranks"] = allr

@@ -248,7 +248,7 @@ WG_LDO = 320
 
 
 def chain_backward_fused(pc: PackedChain, pb: PackedChainBwd, Ws, images, y_top: torch.Tensor, dY: torch.Tensor, M: int, acts, ks, mods,
-                         need_src, cols0):
+                         need_src, cols0, params=None):
     """data gradients (one fused launch) + weight / bias gradients (one image-fed launch) of a chain.
     Returns ([d_src_i | None], [dW_l], [db_l])."""
     from . import mlp_tc
@@ -281,11 +281,22 @@ def chain_backward_fused(pc: PackedChain, pb: PackedChainBwd, Ws, images, y_top:
         dbs.append(flat[o:o + sizes[2 * l + 1]]); o += pad4(sizes[2 * l + 1])
     cmap = _cols_map32(cols0, pc.Kp[0], dev) if cols0 is not None else None
     rp = mlp_tc.rows_padded(M)
-    with ops._launch(name="wgrad_img"):
-        check(lib().hnr_wgrad_img_jobs(nl, ptr_array(dz), i64_array(pc.Np), ptr_array([x0img] + himg), None, i64_array([pc.Kp[0]] + pc.Np[:-1]),
-                                       i64_array([0] * nl), ptr_array(dWs), ptr_array(dbs), ptr_array([cmap] + [None] * (nl - 1)),
-                                       i64_array([w.shape[0] for w in Ws]), i64_array([w.shape[1] for w in Ws]), i64_array([rp] * nl), stream()),
-              "wgrad_img_jobs")
+    aW, ab = [ops.alias(t) for t in dWs], [ops.alias(t) for t in dbs]       # a parked launch refers to aliases only (ops.alias)
+    shapes = ([w.shape[0] for w in Ws], [w.shape[1] for w in Ws])
+
+    def launch_wgrad():
+        with ops._launch(name="wgrad_img"):
+            check(lib().hnr_wgrad_img_jobs(nl, ptr_array(dz), i64_array(pc.Np), ptr_array([x0img] + himg), None, i64_array([pc.Kp[0]] + pc.Np[:-1]),
+                                           i64_array([0] * nl), ptr_array(aW), ptr_array(ab), ptr_array([cmap] + [None] * (nl - 1)),
+                                           i64_array(shapes[0]), i64_array(shapes[1]), i64_array([rp] * nl), stream()),
+                  "wgrad_img_jobs")
+    pairs = []
+    if params is not None:              # (weight, bias) parameters of the layers, in order: lets a training loop defer this launch
+        for l in range(nl):
+            pairs += [(params[2 * l], aW[l]), (params[2 * l + 1], ab[l])]
+        ops._wgrad_launch(launch_wgrad, pairs)
+    else:
+        launch_wgrad()
     d_srcs, off = [], 0
     for i, k in enumerate(ks):
         g = None
@@ -320,6 +331,7 @@ class ChainFn(torch.autograd.Function):
             y, h, images = chain_forward(pc, srcs, M=M, mods=mods, out=True, res=res, head=head, save_images=True)
             ctx.cfg = (acts, mods, M, has_res, head_act, nlayer, nsrc, cols0)
             ctx.pc, ctx.pb, ctx.ks = pc, pb, [s_.shape[1] for s_ in srcs]
+            ctx.wparams = list(tensors[0:2 * nlayer])
             ctx.nimg = len(images[1])
             ctx.save_for_backward(*Ws, *([head[0]] if head else []), images[0], *images[1], y, *([h] if head else []))
             if head is not None:
@@ -407,7 +419,7 @@ class ChainFn(torch.autograd.Function):
         d_res = dcur if has_res else None
         need = [ctx.needs_input_grad[10 + 2 * nlayer + (2 if head_act >= 0 else 0) + i] for i in range(nsrc)]
         modl = list(mods) + [0] * (nsrc - len(mods))
-        d_srcs, gW, gb = chain_backward_fused(ctx.pc, ctx.pb, Ws, (x0img, himg), y, dcur, M, acts, ctx.ks, modl, need, cols0)
+        d_srcs, gW, gb = chain_backward_fused(ctx.pc, ctx.pb, Ws, (x0img, himg), y, dcur, M, acts, ctx.ks, modl, need, cols0, params=ctx.wparams)
         grads = []
         for l in range(nlayer):
             grads += [gW[l], gb[l]]

@@ -488,6 +488,51 @@ class NbrMlpFusedFn(torch.autograd.Function):
         return (d_emb, d_col, d_dir, d_confc, dW1, db1, dW2, db2, dW3, db3, dW4, db4, d_wa.view(ctx.shapes[3]), d_ba.view(ctx.shapes[4]), None)
 
 
+# Deferred weight gradients.  The weight-gradient launches (wgrad_img: ~1.4 ms per step) depend on nothing that follows them in the
+# backward pass and nothing in the backward pass depends on them.  Inside `with defer_weight_gradients() as d:` the fused backward
+# functions hand autograd their (zeroed) parameter-shaped gradient buffers at once and park the launch in `d`; the training loop
+# runs `d.run()` after loss.backward() returned -- a data-parallel loop first starts the all-reduce of the point tables, so that the
+# collective overlaps with the weight-gradient kernels instead of being exposed (parallel.train_step).
+_DEFER = None
+
+
+class defer_weight_gradients:
+    def __init__(self):
+        self.jobs = []          # (launch closure, [(parameter, gradient buffer)])
+
+    def __enter__(self):
+        global _DEFER
+        self._prev, _DEFER = _DEFER, self
+        return self
+
+    def __exit__(self, *a):
+        global _DEFER
+        _DEFER = self._prev
+
+    def run(self):
+        for fn, pairs in self.jobs:
+            fn()
+            for p, buf in pairs:
+                # autograd normally adopts the returned buffer as p.grad (same storage: nothing to do); if it cloned it instead (the clone
+                # was taken before the launch above filled the buffer), add the result to the clone
+                if p.grad is not None and p.grad.data_ptr() != buf.data_ptr():
+                    p.grad.add_(buf.view_as(p.grad))
+        self.jobs = []
+
+
+def alias(t: torch.Tensor) -> torch.Tensor:
+    """another tensor object on the same memory, NOT a view of `t`: a parked launch must not keep the gradient tensor itself alive, or
+    autograd (which adopts a returned gradient as p.grad only when nobody else references it) would clone it before it is filled"""
+    return torch.empty(0, dtype=t.dtype, device=t.device).set_(t.untyped_storage(), t.storage_offset(), t.size(), t.stride())
+
+
+def _wgrad_launch(fn, pairs):
+    if _DEFER is not None:
+        _DEFER.jobs.append((fn, pairs))
+    else:
+        fn()
+
+
 class NbrMlpTrainFn(torch.autograd.Function):
     """Fully fused training path of the per-neighbour stage (round 2).  Forward: nbr_mlp_f16 in save mode -- the layer-0 input,
     the block3 extras and the four layers' outputs go to HBM as split bf16 images (csrc/img_common.cuh).  Backward: three
@@ -507,6 +552,7 @@ class NbrMlpTrainFn(torch.autograd.Function):
                                                          weight, confc_c, pack, w_alpha, b_alpha)
         ctx.save_for_backward(emb, confc_c, W3, _f32c(w_alpha).view(-1), araw, pidx, vlist, raydirs, weight, packT, imgs["x0"], imgs["e"],
                               imgs["h0"], imgs["h1"], imgs["h2"], imgs["h3"])
+        ctx.wparams = (W1, b1, W2, b2, W3, b3, W4, b4)
         ctx.cam, ctx.Nv, ctx.K = cam, Nv, K
         ctx.shapes = (emb.shape, color.shape, dirs.shape, w_alpha.shape, b_alpha.shape)
         return sigma, X5
@@ -549,12 +595,17 @@ class NbrMlpTrainFn(torch.autograd.Function):
         with _launch(name="dz_extras_bwd"):
             check(lib().hnr_dz_extras_bwd(ptr(dz[2]), ptr(W3c), W3c.stride(0), HID, rows, ptr(dE), stream()), "dz_extras_bwd")
         x0map, e3map = _wgrad_colmaps(dev)
-        with _launch(name="wgrad_img"):
-            check(lib().hnr_wgrad_img_jobs(4, ptr_array(dz), i64_array([HID] * 4), ptr_array([x0img, h0, h1, h2]), ptr_array([None, None, eimg, None]),
-                                           i64_array([mlp_tc.X0_IMG_W, HID, HID, HID]), i64_array([0, 0, mlp_tc.E_IMG_W, 0]),
-                                           ptr_array([gW[0], gW[2], gW[4], gW[6]]), ptr_array([gW[1], gW[3], gW[5], gW[7]]),
-                                           ptr_array([x0map, None, e3map, None]), i64_array([HID] * 4), i64_array([X0_W, HID, HID + E_W, HID]),
-                                           i64_array([mlp_tc.rows_padded(rows)] * 4), stream()), "wgrad_img_jobs")
+        rows_pad = mlp_tc.rows_padded(rows)
+        ga = [alias(t) for t in gW]             # the parked launch refers to aliases only (see alias())
+
+        def launch_wgrad():
+            with _launch(name="wgrad_img"):
+                check(lib().hnr_wgrad_img_jobs(4, ptr_array(dz), i64_array([HID] * 4), ptr_array([x0img, h0, h1, h2]), ptr_array([None, None, eimg, None]),
+                                               i64_array([mlp_tc.X0_IMG_W, HID, HID, HID]), i64_array([0, 0, mlp_tc.E_IMG_W, 0]),
+                                               ptr_array([ga[0], ga[2], ga[4], ga[6]]), ptr_array([ga[1], ga[3], ga[5], ga[7]]),
+                                               ptr_array([x0map, None, e3map, None]), i64_array([HID] * 4), i64_array([X0_W, HID, HID + E_W, HID]),
+                                               i64_array([rows_pad] * 4), stream()), "wgrad_img_jobs")
+        _wgrad_launch(launch_wgrad, list(zip(ctx.wparams, ga)))
         dW1, db1, dW2, db2, dW3, db3, dW4, db4 = gW
         ne, nc, nd = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
         d_emb = torch.zeros(ctx.shapes[0], device=dev, dtype=torch.float32) if ne else None

@@ -173,19 +173,28 @@ def train_step(net, frame_shard: Dict[str, torch.Tensor], optimizers: Sequence[t
         scale, n_global = global_mean_scale(n_local, group)
     if next_frame_shard is not None and getattr(net, "near_far", None) is not None:
         net.prefetch_query(**next_frame_shard)
-    if out["coarse_raycolor"].shape[1] > 0:
-        loss = training_loss(out, frame_shard["gt_image"], zero_one_weight)
-        with ops.tag("backward"):
-            (loss * scale[0] if scale is not None else loss).backward()
-    else:
-        loss = torch.zeros((), device=out["ray_mask"].device)
+    # the weight-gradient launches are parked during backward and issued below, AFTER the all-reduce of the point tables has been
+    # started: ~1.4 ms of kernels that nothing else waits for cover the collective (ops.defer_weight_gradients)
+    with ops.defer_weight_gradients() as deferred:
+        if out["coarse_raycolor"].shape[1] > 0:
+            loss = training_loss(out, frame_shard["gt_image"], zero_one_weight)
+            with ops.tag("backward"):
+                (loss * scale[0] if scale is not None else loss).backward()
+        else:
+            loss = torch.zeros((), device=out["ray_mask"].device)
     if world == 1:
+        with ops.tag("backward"):
+            deferred.run()
         for o in optimizers:
             o.step()
         return loss.detach(), n_local
     params = [p for o in optimizers for g in o.param_groups for p in g["params"]]
     is_large = lambda p: p.numel() * p.element_size() >= large_bytes
-    _, pending = allreduce_gradients(params, None, group, bucket_bytes=large_bytes, prescaled=True, defer_large=True)
+    large_params = [p for p in params if is_large(p)]
+    _, pending = allreduce_gradients(large_params, None, group, bucket_bytes=large_bytes, prescaled=True, defer_large=True)
+    with ops.tag("backward"):
+        deferred.run()
+    allreduce_gradients([p for p in params if not is_large(p)], None, group, bucket_bytes=64 << 20, prescaled=True)
     late = [o for o in optimizers if any(is_large(p) for g in o.param_groups for p in g["params"])]
     for o in optimizers:
         if o not in late:

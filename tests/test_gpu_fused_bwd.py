@@ -304,3 +304,36 @@ def test_one_launch_repack_equals_tensor_op_packers():
         assert torch.equal(tp.pb[k].wpack, ref.pb[k].wpack), k
     torch.cuda.synchronize()
     assert int(ops.status_word(torch.device("cuda"))[0]) == 0
+
+
+def test_train_step_with_deferred_weight_gradients_equals_plain_backward():
+    """parallel.train_step parks the weight-gradient launches during backward and issues them afterwards (so that a data-parallel run
+    can start the point-table all-reduce first): the gradients left in p.grad must equal those of a plain loss.backward()"""
+    from hybridneuralrendering_b200 import parallel
+    from hybridneuralrendering_b200.optim import FusedAdam
+    from hybridneuralrendering_b200.renderer import training_loss
+    opt = make_opt("scannet", use_nearest=2, SR=24, is_train=True, drop_ratio=0.5, dilation_setup="4_4_1_8")
+    xyz = syn.room_scene(30000, 9)
+    att = syn.point_attributes(np.random.default_rng(9), len(xyz))
+    fr = syn.room_frame(H=48, W=64, V=2, patch_num=4, patch_size=4, seed=5)
+    P = ro.random_params(10)
+    frame = {k: (cuda(v) if isinstance(v, np.ndarray) and v.dtype.kind == "f" else v) for k, v in fr.items()}
+    res = []
+    for deferred in (True, False):
+        net = _build(opt, xyz, att, P)
+        net.near_far = (0.1, 8.0)
+        torch.manual_seed(3)
+        if deferred:
+            opts = [FusedAdam([p for p in net.parameters() if p.requires_grad], lr=0.0)]       # lr 0: the step leaves the parameters alone
+            loss, _ = parallel.train_step(net, frame, opts)
+        else:
+            loss = training_loss(net(**frame), frame["gt_image"])
+            loss.backward()
+        torch.cuda.synchronize()
+        res.append((float(loss), {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}))
+    (la, ga), (lb, gb) = res
+    assert la == lb and set(ga) == set(gb) and len(ga) > 40
+    for k in ga:
+        a, b = ga[k].double(), gb[k].double()
+        # same kernels, same inputs; only the atomics' arrival order differs between two runs
+        assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max()) + 1e-30, k
