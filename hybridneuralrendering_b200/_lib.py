@@ -69,9 +69,6 @@ _SIGS = {
                                  i64, vp, vp]),
     "hnr_frame_rays": (C.c_int, [vp, i64, i64, i64, i64, i64, vp, vp, C.c_int, vp, vp, vp, vp, vp]),
     "hnr_frame_views": (C.c_int, [vp, vp, i64, i64, vp, vp]),
-    "hnr_mlp_tc_packed_bytes": (i64, [i64]),
-    "hnr_mlp_tc_gemm_test": (C.c_int, [vp, i64, i64, vp, i64, vp, vp]),
-    "hnr_mlp_tc_forward": (C.c_int, [vp] * 17 + [i64, i64, vp, vp, vp]),
     "hnr_nbr_mlp_f16_packed_bytes": (i64, []),
     "hnr_chain_f16_chunk_bytes": (i64, [i64]),
     "hnr_chain_f16_set_trace": (None, [vp]),

@@ -54,8 +54,8 @@ def status_check(dev) -> None:
         _STATUS[key][1].zero_()
         raise RuntimeError(f"hybridneuralrendering_b200: a split-fp16 tensor-core kernel saturated an activation (status {bits}: "
                            "1 = per-neighbour MLP activation, 2 = per-sample chain value, 4 = weight beyond the fixed training scale); "
-                           "hidden activations beyond +-1000 (weights beyond +-58 in training) do not fit the fp16 split -- set "
-                           "aggregator.mlp_engine = 'tc_tf32' / fused_train_forward = False (3xTF32, fp32 exponent range) for this model")
+                           "hidden activations beyond +-1000 (weights beyond +-58 in training) do not fit the x64-scaled fp16 split of the fused "
+                           "kernels; nothing was applied from this step (the fused Adam skips a flagged step on the device)")
 
 
 # optional per-launch device timing (CUDA events on the launching stream); used by profiling.py / bench.py

@@ -137,9 +137,8 @@ class PointAggregator(nn.Module):
                   self.color_final_block):
             _init_seq(m)
         self.shading_patch_size = 1
-        # per-neighbour MLP engine for no-grad forwards: "tc" = fused tcgen05 3xFP16 kernel (nbr_mlp_f16.cu), "tc_tf32" = the
-        # first-generation 3xTF32 kernel (mlp_tc.cu), "simt" = exact-fp32 layer kernels.  Forwards that record a graph
-        # always use the layer kernels.
+        # "tc": the product path -- fused tcgen05 kernels (3xFP16 forward, 3xBF16 backward).  "simt": exact-fp32 layer kernels, kept ONLY
+        # as an independent cross-check of the tensor-core path in tests/ (not a user-selectable backend: there is one engine)
         self.mlp_engine = "tc"
         # valid samples decoded per pass in no-grad mode (bounds activation memory); HNR_MAX_VALID_CHUNK = A/B override
         self.max_valid_chunk = int(os.environ.get("HNR_MAX_VALID_CHUNK", "262144"))
@@ -251,16 +250,12 @@ class PointAggregator(nn.Module):
         b1, b3 = self.block1, self.block3
         # per-neighbour MLP engine: the fused tensor-core kernel for no-grad forwards; forwards that record a graph use
         # the layer kernels (their backward needs the saved activations)
-        use_tc = self.mlp_engine in ("tc", "tc_tf32") and not torch.is_grad_enabled() and K == 8 and mask is None
+        use_tc = self.mlp_engine == "tc" and not torch.is_grad_enabled() and K == 8 and mask is None
         if use_tc:
             from . import mlp_tc
             pack = self._packed_weights()
             with ops.tag("nbr_mlp"):
-                if self.mlp_engine == "tc":
-                    sigma, X5 = mlp_tc.forward_f16(tables, pidx, vlist, loc_w, loc_pers, raydirs, cam, weight, confc, pack,
-                                                   self.alpha_branch[0].weight, self.alpha_branch[0].bias)
-                else:
-                    sigma, X5 = mlp_tc.forward(tables, pidx, vlist, loc_w, loc_pers, raydirs, cam, weight, confc, pack[0], pack[1],
+                sigma, X5 = mlp_tc.forward_f16(tables, pidx, vlist, loc_w, loc_pers, raydirs, cam, weight, confc, pack,
                                                self.alpha_branch[0].weight, self.alpha_branch[0].bias)
         elif self.mlp_engine == "tc" and torch.is_grad_enabled() and K == 8 and mask is None and self.fused_train_forward:
             # training: the same fused kernel, with the four layers' activations saved for the tensor-core backward
@@ -385,18 +380,15 @@ class PointAggregator(nn.Module):
         return levels, w2c
 
     def _packed_weights(self):
-        """TF32 hi/lo images of block1/block3 for the tensor-core kernel, re-packed when a weight changes"""
+        """fp16 hi/lo images of block1/block3 for the fused tensor-core kernel, re-packed when a weight changes"""
         ps = [self.block1[0].weight, self.block1[2].weight, self.block3[0].weight, self.block3[2].weight,
               self.block1[0].bias, self.block1[2].bias, self.block3[0].bias, self.block3[2].bias]
         train = torch.is_grad_enabled()
         key = (self.mlp_engine, train) + tuple((p.data_ptr(), p._version) for p in ps)
         if getattr(self, "_pack_key", None) != key:
             from . import mlp_tc
-            if self.mlp_engine == "tc":
-                # graph-recording forwards re-pack after every optimiser step: fixed weight scale, no host read-back
-                self._wpack_cache = mlp_tc.pack_mlp_f16(self.block1, self.block3, weight_scale=mlp_tc.TRAIN_WEIGHT_SCALE if train else None)
-            else:
-                self._wpack_cache = mlp_tc.pack_mlp(self.block1, self.block3)
+            # graph-recording forwards re-pack after every optimiser step: fixed weight scale, no host read-back
+            self._wpack_cache = mlp_tc.pack_mlp_f16(self.block1, self.block3, weight_scale=mlp_tc.TRAIN_WEIGHT_SCALE if train else None)
             self._pack_key = key
         return self._wpack_cache
 
@@ -472,7 +464,10 @@ class PointAggregator(nn.Module):
             return torch.zeros((1, 0, SR, 4), device=dev), torch.zeros((1, 0, SR), dtype=torch.bool, device=dev), None, None
         if points.Rw2c is not None and points.Rw2c.dim() != 2:
             raise NotImplementedError("per-point Rw2c is not supported")
-        tables = (points.xyz, None, points.points_embeding[0], points.points_color[0], points.points_dir[0], points.points_conf.reshape(-1))
+        # (N, C) VIEWS of the (1, N, C) parameters: the backward of a view is a view, whereas `param[0]` (select) costs a zero fill and
+        # a copy of the whole 39*N-float gradient tables in backward
+        v2 = lambda p: p.view(p.shape[-2], p.shape[-1])
+        tables = (points.xyz, None, v2(points.points_embeding), v2(points.points_color), v2(points.points_dir), points.points_conf.reshape(-1))
         cam = ops.make_cam(campos, camrotc2w, points.Rw2c)
         loc_w = sample_loc_w.reshape(S, 3)
         levels = xy = delta = None

@@ -149,20 +149,8 @@ int hnr_linear_tc_bwd_weight(const float* dY, int64_t lddy, const float* Y, int6
                              const int64_t* a_k, const int64_t* a_mod, float* dW, float* db, int64_t M, int64_t N, int64_t K, int act,
                              void* stream);
 
-/* Fused per-neighbour MLP on tcgen05 tensor cores (3xTF32, fp32 accuracy), inference path: gather from the
- * point tables + block1 + block3 + density head + weighted K-sum in one persistent kernel (csrc/mlp_tc.cu).
- * Same arithmetic as hnr_nbr_features + 4 x hnr_linear_fwd + hnr_alpha_ksum_fwd
- * (point_aggregators.py:921-972, :1002-1036).  wpack/bias: images built by hybridneuralrendering_b200/mlp_tc.py. */
-int64_t hnr_mlp_tc_packed_bytes(int64_t Kp);
-int hnr_mlp_tc_gemm_test(const float* a, int64_t rows, int64_t ld, const void* wpack, int64_t Kp, float* out /* rows,256 */,
-                         void* stream);
-int hnr_mlp_tc_forward(const float* xyz, const float* xyz_pers, const float* emb, const float* color, const float* dir,
-                       const int32_t* pidx, const int32_t* vlist, const float* loc_w, const float* loc_pers, const float* raydirs,
-                       const float* cam, const float* weight, const float* confc, const void* wpack, const float* bias /* 4,256 */,
-                       const float* walpha, const float* balpha, int64_t Nv, int64_t K, float* sigma /* Nv */, float* X5 /* Nv,280 */,
-                       void* stream);
-
-/* Second generation of the same fused stage: 3xFP16 split on tcgen05.mma.kind::f16 (twice the TF32 rate, fp32
+/* Fused per-neighbour stage (gather, encodings, block1, block3, density head, weighted K-sum; SURVEY 8a rows G1 + A1-A3;
+ * reference: models/neural_points/neural_points.py:708-720, models/aggregators/point_aggregators.py:921-1026): 3xFP16 split on tcgen05.mma.kind::f16 (twice the TF32 rate, fp32
  * accuracy: 22 mantissa bits), activations kept in shared memory directly in the UMMA operand layout, two TMEM
  * accumulators so that epilogue l overlaps the MMAs of layer l+1 (csrc/nbr_mlp_f16.cu).  wpack: 67 chunk images in
  * consumption order; bias (4,256) with rows 0..2 pre-multiplied by the next layer's input scale; mul[4]: accumulator ->

@@ -10,32 +10,6 @@ from oracle import render_oracle as ro
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("rows,K", [(128, 8), (128, 64), (300, 256), (1000, 284), (128 * 150 + 5, 263)])
-def test_tc_gemm_matches_fp64(rows, K):
-    """one layer through the whole tensor-core machinery (bulk-copy ring, UMMA descriptors, TMEM epilogue):
-    fp32-level accuracy from 3 TF32 MMAs per product"""
-    from hybridneuralrendering_b200 import mlp_tc
-    rng = np.random.default_rng(rows + K)
-    a = T(rng.standard_normal((rows, K)).astype(np.float32))
-    W = T((rng.standard_normal((256, K)) * 0.1).astype(np.float32))
-    out = mlp_tc.gemm_test(a.cuda(), W.cuda())
-    ref = a.double() @ W.double().t()
-    scale = float(ref.abs().max())
-    err = float((out.cpu().double() - ref).abs().max())
-    fp32_err = float(((a.cuda() @ W.cuda().t()).cpu().double() - ref).abs().max())      # torch fp32 (no TF32) for scale
-    assert err <= 1e-5 * scale and err <= 30 * max(fp32_err, 1e-7 * scale), (err, fp32_err, scale)   # plain TF32 sits near 1e-3 * scale
-
-
-def test_packing_layout_roundtrip():
-    from hybridneuralrendering_b200 import mlp_tc
-    W = torch.arange(256 * 16, dtype=torch.float32).view(256, 16).cuda() / 7.0
-    img = mlp_tc.pack_layer(W).view(torch.float32).view(2, 2, 2, 32, 8, 4)     # (chunk, hi|lo, k half, row group, row, 4)
-    rec = (img[:, 0] + img[:, 1]).permute(2, 3, 0, 1, 4).reshape(256, 16)
-    assert torch.equal(rec, W)
-    assert int((img[:, 0].contiguous().view(torch.int32) & 8191).abs().sum()) == 0    # hi parts are TF32-representable
-    assert sorted(c for c in mlp_tc.layer1_column_order() if c >= 0) == list(range(284))
-
-
 @pytest.mark.parametrize("R,SR,empty", [(64, 24, 0.4), (37, 80, 0.2), (3, 5, 0.0)])
 def test_fused_tc_path_matches_exact_fp32_path(R, SR, empty):
     from hybridneuralrendering_b200 import NeuralPoints, make_opt
