@@ -13,20 +13,22 @@ from . import ops
 TRAIN_WORKLOAD = "ScanNet scene0241_01-shaped hybrid training step: 640x480 frames, 4096-ray batch, 8 reference-view feature maps, 2M points"
 
 
+FRAME_SET = 8          # distinct frames a training benchmark cycles through (see train_step_benchmark)
+
 LARGE_WORKLOAD = "large-scale scene: 8M neural points, 1296x968 frames, 4096-ray rasters sharded across the GPUs with NCCL gradient allreduce over NVLink"
 
 
 def build_train_case(dev, points: int = 2_000_000, views: int = 8, seed: int = 0, size=(6.0, 5.0, 3.0), H: int = 480, W: int = 640,
-                     max_o: int = 1_000_000):
-    """net + frame of a training step: room-shaped point cloud (replicated: the same on every rank), one 4096-ray dilated-patch
-    raster (8x8 patches of 8x8; `seed` moves the patches, i.e. every rank of a data-parallel run gets its own rays)"""
+                     max_o: int = 1_000_000, n_frames: int = 1):
+    """net + frame of a training step: room-shaped point cloud (replicated: the same on every rank), 4096-ray dilated-patch
+    rasters (8x8 patches of 8x8; the seed moves the camera and the patches).  n_frames > 1: returns a LIST of frames with seeds
+    seed, seed + 1, ... -- a training loop sees a different frame every step."""
     from . import NeuralPoints, NeuralPointsRayMarching, PointAggregator, make_opt
     from . import synthetic as syn
     opt = make_opt("scannet", use_nearest=views, SR=24, is_train=True, drop_ratio=0.5, dilation_setup="8_8_1_8",
                    max_o=max_o)           # >= occupied voxels of the room (SURVEY.md §8d: generator must respect max_o)
     xyz = syn.room_scene(points, 0, size=size)
     att = syn.point_attributes(np.random.default_rng(0), len(xyz))
-    fr = syn.room_frame(H=H, W=W, V=views, patch_num=8, patch_size=8, seed=seed, size=size)
     c = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     pts = NeuralPoints(32, len(xyz), opt, dev)
     pts.set_points(c(xyz), c(att["emb"])[None], points_color=c(att["color"])[None], points_dir=c(att["dir"])[None],
@@ -35,8 +37,11 @@ def build_train_case(dev, points: int = 2_000_000, views: int = 8, seed: int = 0
     agg = PointAggregator(opt).to(dev)
     net = NeuralPointsRayMarching(aggregator=agg, neural_points=pts, opt=opt).to(dev)
     net.near_far = (0.1, 8.0)
-    frame = {k: (c(v) if isinstance(v, np.ndarray) and v.dtype.kind == "f" else v) for k, v in fr.items()}
-    return net, frame
+    frames = []
+    for i in range(n_frames):
+        fr = syn.room_frame(H=H, W=W, V=views, patch_num=8, patch_size=8, seed=seed + i, size=size)
+        frames.append({k: (c(v) if isinstance(v, np.ndarray) and v.dtype.kind == "f" else v) for k, v in fr.items()})
+    return net, (frames[0] if n_frames == 1 else frames)
 
 
 def make_optimizers(net):
@@ -66,12 +71,22 @@ def train_step_benchmark(dev, steps: int = 5, warmup: int = 3, world: int = 1, p
     Returns a dict; 'value' = rays of ALL ranks / that time."""
     import torch.distributed as dist
     from . import parallel
-    net, frame = build_train_case(dev, points, views, seed=rank, size=size, H=H, W=W, max_o=max_o)
+    # FRAME_SET distinct frames (camera pose, patch positions, reference views), the same set on every rank; rank r trains on frame
+    # (r + step) % FRAME_SET: every step all ranks hold different rasters (as a data-parallel loader would hand them out), and over a run
+    # every rank -- and the 1-GPU run -- sees the same mix of light and heavy frames (75 k .. 83 k valid samples per 4096 rays)
+    net, frames = build_train_case(dev, points, views, seed=0, size=size, H=H, W=W, max_o=max_o, n_frames=FRAME_SET)
+    frame = frames[rank % FRAME_SET]
     agg = net.aggregator
     R = frame["raydir"].shape[1]
     opts = make_optimizers(net)
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
-    nxt = frame if prefetch else None
+    it = [0]
+
+    def next_pair():
+        """(frame of this step, frame of the next step)"""
+        i = it[0]
+        it[0] += 1
+        return frames[(rank + i) % FRAME_SET], frames[(rank + i + 1) % FRAME_SET]
 
     def barrier():
         torch.cuda.synchronize()
@@ -80,7 +95,8 @@ def train_step_benchmark(dev, steps: int = 5, warmup: int = 3, world: int = 1, p
             torch.cuda.synchronize()
 
     for _ in range(warmup):
-        parallel.train_step(net, frame, opts, next_frame_shard=nxt)
+        cur, nx = next_pair()
+        parallel.train_step(net, cur, opts, next_frame_shard=nx if prefetch else None)
     parallel.flush_pending(net)
     barrier()
     ops.LAUNCHES = 0
@@ -90,7 +106,8 @@ def train_step_benchmark(dev, steps: int = 5, warmup: int = 3, world: int = 1, p
     t_host = _time.perf_counter()
     for _ in range(steps):
         flush.zero_()
-        loss, _ = parallel.train_step(net, frame, opts, next_frame_shard=nxt)
+        cur, nx = next_pair()
+        loss, _ = parallel.train_step(net, cur, opts, next_frame_shard=nx if prefetch else None)
     parallel.flush_pending(net)
     e.record()
     host_ms = (_time.perf_counter() - t_host) / steps * 1e3           # time the HOST needs to issue a step (no synchronisation in the loop)
@@ -100,14 +117,21 @@ def train_step_benchmark(dev, steps: int = 5, warmup: int = 3, world: int = 1, p
     ms_step = _device_max(ms_local, dev, world)
     res = {"metric": "train rays/s (fwd+bwd)", "value": world * R / (ms_step * 1e-3), "unit": "rays/s", "ms_per_step": ms_step,
            "rays_per_step_per_gpu": R, "points": points, "views": views, "loss": float(loss), "launches_per_step": launches // steps,
-           "host_issue_ms_per_step": host_ms,
+           "host_issue_ms_per_step": host_ms, "frame_set": FRAME_SET,
            "step": "forward + loss + backward" + (" + NCCL gradient all-reduce" if world > 1 else "") + " + Adam (network + point tables)",
            "config": workload}
+    nxt = frame if prefetch else None
     # ---- end to end: the frame dict arrives in pinned host memory every step, the loss goes back to the host every step
     if e2e:
-        host = {k: v.cpu().pin_memory() for k, v in frame.items() if torch.is_tensor(v)}
+        hosts = [{k: v.cpu().pin_memory() for k, v in f.items() if torch.is_tensor(v)} for f in frames]
         rest = {k: v for k, v in frame.items() if not torch.is_tensor(v)}
-        up = lambda: dict(rest, **{k: v.to(dev, non_blocking=True) for k, v in host.items()})
+        host = hosts[0]
+        cnt = [0]
+
+        def up():
+            h = hosts[(rank + cnt[0]) % FRAME_SET]
+            cnt[0] += 1
+            return dict(rest, **{k: v.to(dev, non_blocking=True) for k, v in h.items()})
         loss_host = torch.zeros(steps + 2).pin_memory()
         cur = up()
         for _ in range(2):
@@ -155,7 +179,11 @@ def train_step_benchmark(dev, steps: int = 5, warmup: int = 3, world: int = 1, p
         l = training_loss(out, frame["gt_image"])
         if prefetch:
             net.prefetch_query(**frame)
-        l.backward()
+        # as parallel.train_step issues it: the gradient tails (weight gradients, image-branch tail) parked during backward and run on
+        # two streams afterwards
+        with ops.defer_weight_gradients() as deferred:
+            l.backward()
+        deferred.run()
     for _ in range(2):
         fwd_bwd()
     barrier()

@@ -16,8 +16,12 @@
 //     no-swizzle K-major UMMA layout; layers >= 1: the epilogue of layer l writes layer l+1's A operand directly in
 //     that layout (hi+lo fp16 = the 4 bytes of the fp32 value) and releases it to the MMA warp per 32 columns;
 //   * weights come pre-split / pre-tiled from the host (chain.py), one cp.async.bulk per 16-wide K chunk;
-//   * warp roles: 4 epilogue warps (thread = row = TMEM lane), 4 generator warps (thread = row, three K chunks of
-//     loads in flight: the chains are bound by reading their inputs), 1 MMA warp, 1 bulk-copy warp.
+//   * warp roles: 8 worker warps that first generate the tile's layer-0 operand (two chunk pairs of loads in flight per
+//     warp: the chains are bound by the latency of reading their inputs) and then run the epilogues of its layers (thread =
+//     row = TMEM lane, the 32-column blocks split between the two warps of a lane quarter), 1 MMA warp, 1 bulk-copy warp.
+//     A tile's phases depend on each other serially, so sharing the warps costs no overlap (the second CTA on the SM
+//     supplies it) and puts two warps per scheduler on every phase; clock64 traces (scripts/trace_chain.py) showed the
+//     round-1 split (4 generator + 4 epilogue warps, one pair in flight) at ~0.1 IPC per warp on pure latency chains.
 // Optional fp32 copies of every layer's output (Y_l) make the same kernel usable as the forward of a training step.
 #include <cuda_fp16.h>
 #include <limits.h>
@@ -25,7 +29,13 @@
 
 #include "common.cuh"
 #include "hnr.h"
+// the clock64 event trace (scripts/trace_chain.py) costs predicated instructions in every hot loop of an issue-bound kernel: it is
+// compiled in only with -DHNR_CHAIN_TRACE
+#ifdef HNR_CHAIN_TRACE
 #define TRACE_SRC A.trace
+#else
+#define TRACE_SRC ((long long*)nullptr)
+#endif
 #include "tc_common.cuh"
 #include "img_common.cuh"
 
@@ -41,7 +51,7 @@ constexpr int W_STAGE = 2 * NMAX * KC * 2;   // 8192
 constexpr int A_PART = TM * KC * 2;          // 4096
 constexpr int A_STAGE = 2 * A_PART;          // 8192
 constexpr int ACT_PART = TM * NMAX * 2;      // 32768
-constexpr int NTHREADS = 320;            // warps 0-3 epilogue, 4-7 generators, 8 MMA, 9 bulk copy
+constexpr int NTHREADS = 320;            // warps 0-7 workers (layer-0 generation + epilogues), 8 MMA, 9 bulk copy
 
 constexpr int OFF_W = 0;
 constexpr int OFF_A = OFF_W + NSW * W_STAGE;           // 16384
@@ -78,6 +88,7 @@ struct ChainArgs {
     // inner layers' outputs (Np[l] columns), rows padded to the tile -- operands of chain_bwd_f16.cu / wgrad_img.cu.  NULL = off
     uint8_t* x0img;
     uint8_t* himg[MAXL];
+    int variant;                 // bring-up / profiling switches (HNR_CHAIN_VARIANT): 1 = no L2 prefetch, 2 = L1-bypassing loads, 4 = no source loads at all
     long long* trace;            // optional event trace of CTA 0 (bring-up / profiling): [count, (clock, id, a, b) ...]
 };
 
@@ -106,21 +117,72 @@ __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
     hi = make_uint4(h[0], h[1], h[2], h[3]);
     lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
-// mbarrier wait for warps that are ahead of the pipeline anyway: poll, then sleep between polls (polling, sleeping and
-// try_wait with a suspend-time hint were measured to perform identically here; sleeping leaves the issue slots to the others)
+// mbarrier wait for warps that are ahead of the pipeline anyway.  The kernel is instruction-issue bound (ncu: IPC 2.0 of 4 with a
+// quarter of all executed instructions in try_wait / nanosleep polling loops), so the wait is left to the hardware: try_wait with a
+// suspend-time hint parks the warp until the phase completes or the hint expires.  (`ns` is kept for the call sites' documentation.)
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, unsigned ns) {
+    (void)ns;
     uint32_t done;
     for (;;) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
-            : "r"(bar), "r"(parity)
+            : "r"(bar), "r"(parity), "r"(20000u)
             : "memory");
         if (done) break;
-        __nanosleep(ns);
     }
+}
+// epilogue of an INNER layer for a block of W (32 or 16) accumulator columns of one row: bias, LeakyReLU / identity, optional split
+// bf16 image of the output (training), fp16 hi/lo split into the next layer's A operand, release of the block to the MMA warp
+template <int W>
+__device__ __forceinline__ void epi_inner_block(uint32_t taddr, int c0, const float* __restrict__ bl, float mul, float inv_next, bool do_lrelu,
+                                                uint8_t* himg, int np, int64_t m, uint8_t* dst, int32_t* status, uint32_t bar_block, int lane) {
+    float y[W];
+    float4 bb[W / 4];
+#pragma unroll
+    for (int i4 = 0; i4 < W / 4; ++i4) bb[i4] = __ldg(reinterpret_cast<const float4*>(bl + c0) + i4);     // in flight together with the TMEM load
+    if constexpr (W == 32) tmem_ld32(taddr + c0, y); else tmem_ld16(taddr + c0, y);
+#pragma unroll
+    for (int i4 = 0; i4 < W / 4; ++i4) {
+        y[4 * i4 + 0] = fmaf(y[4 * i4 + 0], mul, bb[i4].x);
+        y[4 * i4 + 1] = fmaf(y[4 * i4 + 1], mul, bb[i4].y);
+        y[4 * i4 + 2] = fmaf(y[4 * i4 + 2], mul, bb[i4].z);
+        y[4 * i4 + 3] = fmaf(y[4 * i4 + 3], mul, bb[i4].w);
+    }
+    if (do_lrelu) {
+#pragma unroll
+        for (int i = 0; i < W; ++i) y[i] = fmaxf(y[i], 0.01f * y[i]);
+    }
+    if (himg) {
+        uint8_t* gp = himg + img::piece_off(m, c0 >> 3, np);
+        const int64_t pl = img::plane_bytes(np);
+#pragma unroll
+        for (int g = 0; g < W / 8; ++g) {
+            float u[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) u[i] = y[8 * g + i] * inv_next;
+            uint4 hi, lo;
+            img::split8_bf16(u, hi, lo);
+            *reinterpret_cast<uint4*>(gp + 512 * g) = hi;
+            *reinterpret_cast<uint4*>(gp + 512 * g + pl) = lo;
+        }
+    }
+    float am = 0.f;
+#pragma unroll
+    for (int i = 0; i < W; ++i) am = fmaxf(am, fabsf(y[i]));
+    if (am > 65000.f && status) atomicOr(status, 2);
+#pragma unroll
+    for (int g = 0; g < W / 8; ++g) {
+        uint4 hi, lo;
+        split8(y + 8 * g, hi, lo);
+        *reinterpret_cast<uint4*>(dst + g * A_LBO) = hi;
+        *reinterpret_cast<uint4*>(dst + g * A_LBO + ACT_PART) = lo;
+    }
+    fence_proxy_async();                    // the block (32 columns, or the 16-column tail) is complete: release it to the MMA warp
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_block);
 }
 __host__ __device__ constexpr uint32_t idesc_f16(int N) {   // D=f32, A=B=f16, both K-major, M=128
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
@@ -141,7 +203,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) chain_f16_kernel(const __grid_con
         for (int s = 0; s < NSW; ++s) { mbar_init(bar_wfull + 8 * s, 1); mbar_init(bar_wempty + 8 * s, 1); }
         for (int s = 0; s < NSA; ++s) { mbar_init(bar_afull + 8 * s, 4); mbar_init(bar_aempty + 8 * s, 1); }
         for (int s = 0; s < 4; ++s) mbar_init(bar_actfull + 8 * s, 4);
-        for (int s = 0; s < 2; ++s) { mbar_init(bar_accfull + 8 * s, 1); mbar_init(bar_accfree + 8 * s, 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(bar_accfull + 8 * s, 1); mbar_init(bar_accfree + 8 * s, 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 8) tmem_alloc(smem_u32(tmem_slot), 2 * NMAX);
@@ -228,133 +290,180 @@ __global__ void __launch_bounds__(NTHREADS, 2) chain_f16_kernel(const __grid_con
                 }
             }
         }
-    } else if (warp >= 4) {
-        // ================= generators: fp32 source rows -> split fp16 operand chunks =================
+    } else {
+        // ================= worker warps 0-7: layer-0 operand generation, then the epilogues of the tile's layers =================
+        // A tile's phases are serially dependent anyway (its second CTA on the SM supplies the overlap), so the same eight warps do
+        // both jobs: two warps per scheduler work on every phase instead of one.  wq = TMEM lane quarter = 32-row group,
+        // half = which half of the K-chunk pairs (generation) / of the 32-column blocks (epilogue) this warp owns.
+        const int wq = warp & 3, half = warp >> 2;
         TRACE_DECL(1);
-        if (tid != 128) tr__ = nullptr;
-        // Line-coalesced loads: a step covers a PAIR of K chunks = 32 columns = 128 bytes of every row.  lane = (row-in-4,
-        // 16-byte piece), so one load instruction reads 4 rows x one full 128-byte line; a warp owns 32 rows (8 instructions).
-        // Each lane converts its own 4 columns and stores 8-byte hi / lo pieces straight into the two operand stages.
+        if (tid != 0) tr__ = nullptr;
         const int nc0 = A.Kp[0] / KC, npair = (nc0 + 1) / 2;
         const float sc = A.in_scale;
-        const int gw = warp - 4, rsub = lane >> 3, piece = lane & 7;
-        const int ktot = A.k[0] + A.k[1] + A.k[2], b1 = A.k[0], b2 = A.k[0] + A.k[1];
-        uint32_t ait = 0;
-        // the row offsets of this lane's 8 rows are cached per (tile, source), so a step's loads cost one address each
-        int cur_src = -1;
-        int64_t cur_tile = -1;
-        const float* sbase_p = nullptr;
-        int rowoff[8];                                   // element offset of the row relative to the tile's first row in the cached source; INT_MIN = row beyond M
+        const int rsub = lane >> 3, piece = lane & 7;
+        const int ktot = A.k[0] + A.k[1] + A.k[2], kb1 = A.k[0], kb2 = A.k[0] + A.k[1];
+        uint32_t abase = 0;                              // layer-0 chunks issued by this CTA in earlier tiles (operand-ring position)
+        const int r = 32 * wq + lane;                    // epilogue: thread = row = TMEM lane
+        const uint32_t lane_base = (uint32_t)(32 * wq) << 16;
+        uint8_t* act_hi = smem + OFF_ACT;
+        float* dotbuf = reinterpret_cast<float*>(smem + OFF_A);      // head partial sums (the operand ring is idle during the epilogues)
+        uint32_t use[2] = {0, 0};
+
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int64_t m0 = tile * TM;
-            for (int p = 0; p < npair; ++p) {
+            // ---------------- generation: fp32 source rows -> split fp16 operand chunks (canonical K-major UMMA layout) ----------------
+            // Line-coalesced loads: a step covers a PAIR of K chunks = 32 columns = 128 bytes of every row.  lane = (row-in-4,
+            // 16-byte piece), so one load instruction reads 4 rows x one full 128-byte line; a warp owns 32 rows (8 instructions).
+            // The loads of a warp's NEXT pair are issued before the current pair is converted (two pairs in flight per warp).
+            // A warp's work is cut into UNITS of half a pair (rows 4j .. 4j+3 of its 8 row slots, j = unit & 1): the loads of
+            // the next unit are in flight while the current one is converted (16 + 16 data registers).
+            const int live_rows = (int)min((int64_t)TM, A.M - m0);
+            // per-tile source descriptors: pointer to the source row of the tile's first row, and the first tile row that wraps around
+            // a shared-row-block source (mod > 0); INT_MAX = no wrap inside this tile
+            const float* sb[3];
+            int wrap[3];
+#pragma unroll
+            for (int s_ = 0; s_ < 3; ++s_) {
+                const int64_t smod = A.mod[s_];
+                const int64_t first = smod > 0 ? m0 % smod : m0;
+                sb[s_] = A.src[s_] ? A.src[s_] + first * A.ld[s_] : nullptr;
+                wrap[s_] = (smod > 0 && first + TM > smod) ? (int)(smod - first) : INT_MAX;
+            }
+            auto load_unit = [&](int u, float4 (&v)[4]) {
+                const int p = half + 2 * (u >> 1), j = u & 1;
                 const int col0 = 32 * p + 4 * piece;
                 const bool have1 = 2 * p + 1 < nc0;      // second chunk of the pair exists
                 const bool mine = piece < 4 || have1;
-                int s_ = 0, k_ = col0;
-                if (k_ >= b1) { k_ -= b1; s_ = 1; if (col0 >= b2) { k_ = col0 - b2; s_ = 2; } }
+                const int s_ = col0 < kb1 ? 0 : (col0 < kb2 ? 1 : 2);
+                const int k_ = col0 - (s_ == 0 ? 0 : (s_ == 1 ? kb1 : kb2));
                 const int ks_ = s_ == 0 ? A.k[0] : (s_ == 1 ? A.k[1] : A.k[2]);
                 const bool whole = col0 + 4 <= ktot && k_ + 4 <= ks_;
-                float4 v[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int i = 0; i < 4; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (mine && whole) {
                     const int sld = s_ == 0 ? A.ld[0] : (s_ == 1 ? A.ld[1] : A.ld[2]);
-                    if (s_ != cur_src || tile != cur_tile) {
-                        const int64_t smod = s_ == 0 ? A.mod[0] : (s_ == 1 ? A.mod[1] : A.mod[2]);
-                        const int64_t first = smod > 0 ? m0 % smod : m0;          // source row of the tile's first row
-                        sbase_p = (s_ == 0 ? A.src[0] : (s_ == 1 ? A.src[1] : A.src[2])) + first * sld;
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int r = 32 * gw + 4 * i + rsub;
-                            int64_t rr = first + r;
-                            if (smod > 0 && rr >= smod) rr %= smod;
-                            rowoff[i] = (m0 + r < A.M) ? (int)((rr - first) * sld) : INT_MIN;
-                        }
-                        cur_src = s_; cur_tile = tile;
-                    }
-                    const float* cb = sbase_p + k_;
+                    const float* cb = (s_ == 0 ? sb[0] : (s_ == 1 ? sb[1] : sb[2])) + k_;
+                    const int wr = s_ == 0 ? wrap[0] : (s_ == 1 ? wrap[1] : wrap[2]);
                     const bool vec = ((reinterpret_cast<uintptr_t>(cb) & 15) == 0) && ((sld & 3) == 0);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        if (rowoff[i] != INT_MIN) {
-                            const float* qd = cb + rowoff[i];
+                    for (int i = 0; i < 4; ++i) {
+                        const int rr_ = 32 * wq + 4 * (4 * j + i) + rsub;
+                        if (rr_ < live_rows) {
+                            int ro = rr_;                                       // row relative to the tile's first source row
+                            if (rr_ >= wr) {                                    // rare: the tile straddles the end of a shared-row-block source
+                                const int64_t smod = A.mod[s_], first = m0 % smod;
+                                ro = (int)((first + rr_) % smod - first);
+                            }
+                            const float* qd = cb + (int64_t)ro * sld;
+                            if (A.variant & 4) continue;
                             if (vec) v[i] = __ldg(reinterpret_cast<const float4*>(qd));
                             else v[i] = make_float4(__ldg(qd), __ldg(qd + 1), __ldg(qd + 2), __ldg(qd + 3));
                         }
                     }
                 } else if (mine) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int r = 32 * gw + 4 * i + rsub;
-                        if (m0 + r < A.M) {
+                    for (int i = 0; i < 4; ++i) {
+                        const int rr_ = 32 * wq + 4 * (4 * j + i) + rsub;
+                        if (rr_ < live_rows) {
                             float e[4];
 #pragma unroll
-                            for (int u = 0; u < 4; ++u) {            // straddles two sources or the zero padding: per element
-                                const int c = col0 + u;
-                                e[u] = 0.f;
+                            for (int q = 0; q < 4; ++q) {            // straddles two sources or the zero padding: per element
+                                const int c = col0 + q;
+                                e[q] = 0.f;
                                 if (c < ktot) {
-                                    const int su = c < b1 ? 0 : (c < b2 ? 1 : 2);
-                                    const int ku = c - (su == 0 ? 0 : (su == 1 ? b1 : b2));
-                                    const int64_t rr = A.mod[su] > 0 ? (m0 + r) % A.mod[su] : m0 + r;
-                                    e[u] = __ldg(A.src[su] + rr * A.ld[su] + ku);
+                                    const int su = c < kb1 ? 0 : (c < kb2 ? 1 : 2);
+                                    const int ku = c - (su == 0 ? 0 : (su == 1 ? kb1 : kb2));
+                                    const int64_t rr = A.mod[su] > 0 ? (m0 + rr_) % A.mod[su] : m0 + rr_;
+                                    e[q] = __ldg(A.src[su] + rr * A.ld[su] + ku);
                                 }
                             }
                             v[i] = make_float4(e[0], e[1], e[2], e[3]);
                         }
                     }
                 }
+            };
+            auto put_unit = [&](int u, const float4 (&v)[4]) {
+                const int p = half + 2 * (u >> 1), j = u & 1;
+                const int col0 = 32 * p + 4 * piece;
+                const bool have1 = 2 * p + 1 < nc0;
+                const bool mine = piece < 4 || have1;
                 if (A.x0img && mine) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int64_t m = m0 + 32 * gw + 4 * i + rsub;
+                    for (int i = 0; i < 4; ++i) {
+                        const int64_t mr = m0 + 32 * wq + 4 * (4 * j + i) + rsub;
                         const uint32_t h0 = img::pack_bf16(v[i].x, v[i].y), h1 = img::pack_bf16(v[i].z, v[i].w);
                         const uint32_t l0 = img::pack_bf16(v[i].x - img::bf16_lo_f(h0), v[i].y - img::bf16_hi_f(h0));
                         const uint32_t l1 = img::pack_bf16(v[i].z - img::bf16_lo_f(h1), v[i].w - img::bf16_hi_f(h1));
-                        uint8_t* gp = A.x0img + img::piece_off(m, col0 >> 3, A.Kp[0]) + (col0 & 7) * 2;
+                        uint8_t* gp = A.x0img + img::piece_off(mr, col0 >> 3, A.Kp[0]) + (col0 & 7) * 2;
                         *reinterpret_cast<uint2*>(gp) = make_uint2(h0, h1);
                         *reinterpret_cast<uint2*>(gp + img::plane_bytes(A.Kp[0])) = make_uint2(l0, l1);
                     }
                 }
-                TRACE(10, p, 0);
+                const uint32_t ait = abase + 2 * (uint32_t)p;
                 const uint32_t st0 = ait % NSA, ph0 = (ait / NSA) & 1, st1 = (ait + 1) % NSA, ph1 = ((ait + 1) / NSA) & 1;
-                ait += have1 ? 2 : 1;
-                mbar_wait_relaxed(bar_aempty + 8 * st0, ph0 ^ 1, 32);
-                if (have1) mbar_wait_relaxed(bar_aempty + 8 * st1, ph1 ^ 1, 32);
-                TRACE(11, p, 0);
+                if (j == 0) {
+                    TRACE(10, p, 0);
+                    mbar_wait_relaxed(bar_aempty + 8 * st0, ph0 ^ 1, 32);
+                    if (have1) mbar_wait_relaxed(bar_aempty + 8 * st1, ph1 ^ 1, 32);
+                    TRACE(11, p, 0);
+                }
                 if (mine) {
                     uint8_t* stage = smem + OFF_A + (piece < 4 ? st0 : st1) * A_STAGE + ((piece >> 1) & 1) * A_LBO + (piece & 1) * 8;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int r = 32 * gw + 4 * i + rsub;
+                    for (int i = 0; i < 4; ++i) {
+                        const int rr_ = 32 * wq + 4 * (4 * j + i) + rsub;
                         const float a = v[i].x * sc, b = v[i].y * sc, c = v[i].z * sc, d = v[i].w * sc;
                         if (fmaxf(fmaxf(fabsf(a), fabsf(b)), fmaxf(fabsf(c), fabsf(d))) > 65000.f && A.status) atomicOr(A.status, 2);
                         const uint32_t h0 = pack_sat(a, b), h1 = pack_sat(c, d);
                         const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&h0)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&h1));
                         const uint32_t l0 = pack_sat(a - f0.x, b - f0.y), l1 = pack_sat(c - f1.x, d - f1.y);
-                        *reinterpret_cast<uint2*>(stage + r * 16) = make_uint2(h0, h1);
-                        *reinterpret_cast<uint2*>(stage + A_PART + r * 16) = make_uint2(l0, l1);
+                        *reinterpret_cast<uint2*>(stage + rr_ * 16) = make_uint2(h0, h1);
+                        *reinterpret_cast<uint2*>(stage + A_PART + rr_ * 16) = make_uint2(l0, l1);
                     }
                 }
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(bar_afull + 8 * st0);
-                    if (have1) mbar_arrive(bar_afull + 8 * st1);
+                if (j == 1) {
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive(bar_afull + 8 * st0);
+                        if (have1) mbar_arrive(bar_afull + 8 * st1);
+                    }
+                    TRACE(12, p, 0);
                 }
-                TRACE(12, p, 0);
+            };
+            // the NEXT tile's source rows are requested into L2 a whole tile time ahead (no registers involved): this tile's loads
+            // then pay an L2 hit instead of an HBM round trip
+            {
+                const int64_t tn = tile + gridDim.x, mrow = tn * TM + (tid & 127);
+                if (tn < ntiles && mrow < A.M && !(A.variant & 1)) {
+#pragma unroll
+                    for (int s_ = 0; s_ < 3; ++s_) {
+                        const int ks_ = A.k[s_];
+                        if (ks_ > 0) {
+                            const int64_t rr = A.mod[s_] > 0 ? mrow % A.mod[s_] : mrow;
+                            const char* rb = reinterpret_cast<const char*>(A.src[s_] + rr * A.ld[s_]);
+                            const char* re = rb + 4 * ks_;
+                            for (const char* q = reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(rb) & ~(uintptr_t)127) + 128 * (tid >> 7); q < re; q += 256)
+                                asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+                        }
+                    }
+                }
             }
-        }
-    } else {
-        // ================= epilogue warps: thread = row = TMEM lane, 16 columns per step =================
-        const int r = tid;
-        const uint32_t lane_base = (uint32_t)(32 * warp) << 16;
-        uint8_t* act_hi = smem + OFF_ACT;
-        uint32_t use[2] = {0, 0};
-        TRACE_DECL(2);
-        if (r != 0) tr__ = nullptr;
-        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const int64_t m = tile * TM + r;
+            {
+                float4 va[4], vb[4];
+                const int nu = 2 * ((npair - half + 1) / 2);          // this warp's pairs: half, half + 2, ...
+                if (nu > 0) load_unit(0, va);
+                for (int u = 0; u < nu; u += 2) {
+                    load_unit(u + 1, vb);
+                    put_unit(u, va);
+                    if (u + 2 < nu) load_unit(u + 2, va);
+                    put_unit(u + 1, vb);
+                }
+            }
+            abase += (uint32_t)nc0;
+
+            // ---------------- epilogues: thread = row = TMEM lane; this warp's half of the 32-column blocks ----------------
+            const int64_t m = m0 + r;
             const bool live = m < A.M;
 #pragma unroll 1
             for (int l = 0; l < nl; ++l) {
@@ -376,19 +485,49 @@ __global__ void __launch_bounds__(NTHREADS, 2) chain_f16_kernel(const __grid_con
                 const bool staged = last && yvec && ldy == n && (n & 31) == 0;
                 float4* stg = reinterpret_cast<float4*>(smem + OFF_ACT);
                 float dot = 0.f;
+                const int nblk = (np + 31) >> 5, bsplit = (nblk + 1) >> 1;
+                const int cbeg = half == 0 ? 0 : 32 * bsplit, cend = half == 0 ? min(np, 32 * bsplit) : np;
+                if (!last) {
+                    // inner layer: whole 32-column blocks (16-column tail), nothing leaves the SM except the optional training image
 #pragma unroll 1
-                for (int c0 = 0; c0 < np; c0 += 16) {
+                    for (int c0 = cbeg; c0 < cend; c0 += 32) {
+                        uint8_t* dst = act_hi + (c0 >> 3) * A_LBO + r * 16;
+                        if (c0 + 32 <= cend)
+                            epi_inner_block<32>(taddr, c0, bl, mul, inv_next, act == HNR_ACT_LRELU, A.himg[l], np, m, dst, A.status, bar_actfull + 8 * (c0 >> 5), lane);
+                        else
+                            epi_inner_block<16>(taddr, c0, bl, mul, inv_next, act == HNR_ACT_LRELU, A.himg[l], np, m, dst, A.status, bar_actfull + 8 * (c0 >> 5), lane);
+                    }
+                    if (yout) {
+                        // (inference never asks for inner outputs; the layer-by-layer training cross-check does) re-read the block from
+                        // TMEM -- tcgen05.ld is warp-collective: every lane executes it, only the stores depend on the row being live
+#pragma unroll 1
+                        for (int c0 = cbeg; c0 < cend; c0 += 16) {
+                            float y[16];
+                            tmem_ld16(taddr + c0, y);
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                float t = fmaf(y[i], mul, __ldg(bl + c0 + i));
+                                if (act == HNR_ACT_LRELU) t = fmaxf(t, 0.01f * t);
+                                if (live && c0 + i < n) yout[m * ldy + c0 + i] = t * inv_next;
+                            }
+                        }
+                    }
+                } else {
+#pragma unroll 1
+                for (int c0 = cbeg; c0 < cend; c0 += 16) {
                     float y[16];
-                    tmem_ld16(taddr + c0, y);
-                    TRACE(21, l, c0);                                               // TMEM load done
+                    tmem_ld16_nowait(taddr + c0, y);
                     const float4* b4 = reinterpret_cast<const float4*>(bl + c0);
+                    float4 bb[4];
+#pragma unroll
+                    for (int i4 = 0; i4 < 4; ++i4) bb[i4] = __ldg(b4 + i4);          // in flight together with the TMEM load
+                    tmem_ld_wait(y);
 #pragma unroll
                     for (int i4 = 0; i4 < 4; ++i4) {
-                        const float4 bb = __ldg(b4 + i4);
-                        y[4 * i4 + 0] = fmaf(y[4 * i4 + 0], mul, bb.x);
-                        y[4 * i4 + 1] = fmaf(y[4 * i4 + 1], mul, bb.y);
-                        y[4 * i4 + 2] = fmaf(y[4 * i4 + 2], mul, bb.z);
-                        y[4 * i4 + 3] = fmaf(y[4 * i4 + 3], mul, bb.w);
+                        y[4 * i4 + 0] = fmaf(y[4 * i4 + 0], mul, bb[i4].x);
+                        y[4 * i4 + 1] = fmaf(y[4 * i4 + 1], mul, bb[i4].y);
+                        y[4 * i4 + 2] = fmaf(y[4 * i4 + 2], mul, bb[i4].z);
+                        y[4 * i4 + 3] = fmaf(y[4 * i4 + 3], mul, bb[i4].w);
                     }
                     if (act == HNR_ACT_LRELU) {
 #pragma unroll
@@ -397,20 +536,18 @@ __global__ void __launch_bounds__(NTHREADS, 2) chain_f16_kernel(const __grid_con
 #pragma unroll
                         for (int i = 0; i < 16; ++i) y[i] = apply_act(y[i], act);
                     }
-                    if (last) {
-                        if (A.res && live) {
+                    if (A.res && live) {
 #pragma unroll
-                            for (int i = 0; i < 16; ++i)
-                                if (c0 + i < n) y[i] += __ldg(A.res + m * A.ldres + c0 + i);
-                        }
-                        if (A.head_w) {
-                            const float4* h4 = reinterpret_cast<const float4*>(A.head_w + c0);      // zero padded to 128 by the host
+                        for (int i = 0; i < 16; ++i)
+                            if (c0 + i < n) y[i] += __ldg(A.res + m * A.ldres + c0 + i);
+                    }
+                    if (A.head_w) {
+                        const float4* h4 = reinterpret_cast<const float4*>(A.head_w + c0);      // zero padded to 128 by the host
 #pragma unroll
-                            for (int i4 = 0; i4 < 4; ++i4) {
-                                const float4 hh = __ldg(h4 + i4);
-                                dot = fmaf(y[4 * i4 + 0], hh.x, dot); dot = fmaf(y[4 * i4 + 1], hh.y, dot);
-                                dot = fmaf(y[4 * i4 + 2], hh.z, dot); dot = fmaf(y[4 * i4 + 3], hh.w, dot);
-                            }
+                        for (int i4 = 0; i4 < 4; ++i4) {
+                            const float4 hh = __ldg(h4 + i4);
+                            dot = fmaf(y[4 * i4 + 0], hh.x, dot); dot = fmaf(y[4 * i4 + 1], hh.y, dot);
+                            dot = fmaf(y[4 * i4 + 2], hh.z, dot); dot = fmaf(y[4 * i4 + 3], hh.w, dot);
                         }
                     }
                     if (staged) {
@@ -430,54 +567,29 @@ __global__ void __launch_bounds__(NTHREADS, 2) chain_f16_kernel(const __grid_con
                                 if (c0 + i < n) o[i] = y[i] * inv_next;
                         }
                     }
-                    if (!last && A.himg[l]) {
-                        float u[16];
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) u[i] = y[i] * inv_next;
-                        uint4 hi, lo;
-                        uint8_t* gp = A.himg[l] + img::piece_off(m, c0 >> 3, np);
-                        img::split8_bf16(u, hi, lo);
-                        *reinterpret_cast<uint4*>(gp) = hi;
-                        *reinterpret_cast<uint4*>(gp + img::plane_bytes(np)) = lo;
-                        img::split8_bf16(u + 8, hi, lo);
-                        *reinterpret_cast<uint4*>(gp + 512) = hi;
-                        *reinterpret_cast<uint4*>(gp + 512 + img::plane_bytes(np)) = lo;
-                    }
-                    if (!last) {
-                        float am = 0.f;
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) am = fmaxf(am, fabsf(y[i]));
-                        if (am > 65000.f && A.status) atomicOr(A.status, 2);
-                        uint4 hi, lo;
-                        uint8_t* dst = act_hi + (c0 >> 3) * A_LBO + r * 16;
-                        split8(y, hi, lo);
-                        *reinterpret_cast<uint4*>(dst) = hi;
-                        *reinterpret_cast<uint4*>(dst + ACT_PART) = lo;
-                        split8(y + 8, hi, lo);
-                        *reinterpret_cast<uint4*>(dst + A_LBO) = hi;
-                        *reinterpret_cast<uint4*>(dst + A_LBO + ACT_PART) = lo;
-                        if ((c0 & 16) || c0 + 16 >= np) {            // a 32-column block (or the tail) is complete: release it to the MMA warp
-                            fence_proxy_async();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(bar_actfull + 8 * (c0 >> 5));
-                        }
-                    }
                 }
-                if (staged) {
-                    asm volatile("bar.sync 1, 128;" ::: "memory");                // all four epilogue warps have staged their rows
-                    const int gpr = n >> 2;                                        // granules per row (multiple of 8)
-                    for (int idx = tid; idx < TM * gpr; idx += 128) {
-                        const int row = idx / gpr, g = idx - row * gpr;
-                        const int64_t mm = tile * TM + row;
-                        if (mm < A.M) reinterpret_cast<float4*>(yout + mm * ldy)[g] = stg[row * gpr + (g ^ (row & 7))];
-                    }
-                    asm volatile("bar.sync 1, 128;" ::: "memory");                // staging consumed before the next tile's epilogue writes the activation
                 }
-                TRACE(22, l, 0);                                                    // epilogue of the layer done
+                // this warp has read its part of the accumulator
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_accfree + 8 * b);
-                if (last && A.head_w && live) A.head_out[m] = apply_act(dot + A.head_b[0], A.head_act);
+                if (staged) {
+                    asm volatile("bar.sync 1, 256;" ::: "memory");                // all eight worker warps have staged their columns
+                    const int gpr = n >> 2;                                        // granules per row (multiple of 8)
+                    for (int row = warp; row < TM; row += 8) {
+                        const int64_t mm = m0 + row;
+                        if (mm < A.M)
+                            for (int g = lane; g < gpr; g += 32) reinterpret_cast<float4*>(yout + mm * ldy)[g] = stg[row * gpr + (g ^ (row & 7))];
+                    }
+                    asm volatile("bar.sync 1, 256;" ::: "memory");                // staging consumed before anybody writes the activation buffer again
+                }
+                if (last && A.head_w) {
+                    if (half == 1) dotbuf[r] = dot;
+                    asm volatile("bar.sync 2, 256;" ::: "memory");
+                    if (half == 0 && live) A.head_out[m] = apply_act(dot + dotbuf[r] + A.head_b[0], A.head_act);
+                    asm volatile("bar.sync 2, 256;" ::: "memory");                // partial sums consumed before the next tile's generation overwrites the ring
+                }
+                TRACE(22, l, 0);                                                    // epilogue of the layer done
             }
         }
     }
@@ -528,6 +640,7 @@ static int chain_f16_launch(const float* const* src, const int64_t* src_ld, cons
     A.in_scale = in_scale; A.nlayer = nlayer; A.wpack = (const uint8_t*)wpack; A.bias = bias; A.res = res; A.ldres = (int)ldres;
     A.head_w = head_w; A.head_b = head_b; A.head_act = head_act; A.head_out = head_out; A.M = M;
     A.trace = g_trace;
+    { const char* e = getenv("HNR_CHAIN_VARIANT"); A.variant = e ? atoi(e) : 0; }
     A.status = status;
     A.x0img = (uint8_t*)x0img;
     for (int l = 0; l < nlayer; ++l) A.himg[l] = (himg && l < nlayer - 1) ? (uint8_t*)himg[l] : nullptr;

@@ -488,17 +488,28 @@ class NbrMlpFusedFn(torch.autograd.Function):
         return (d_emb, d_col, d_dir, d_confc, dW1, db1, dW2, db2, dW3, db3, dW4, db4, d_wa.view(ctx.shapes[3]), d_ba.view(ctx.shapes[4]), None)
 
 
-# Deferred weight gradients.  The weight-gradient launches (wgrad_img: ~1.4 ms per step) depend on nothing that follows them in the
-# backward pass and nothing in the backward pass depends on them.  Inside `with defer_weight_gradients() as d:` the fused backward
-# functions hand autograd their (zeroed) parameter-shaped gradient buffers at once and park the launch in `d`; the training loop
-# runs `d.run()` after loss.backward() returned -- a data-parallel loop first starts the all-reduce of the point tables, so that the
-# collective overlaps with the weight-gradient kernels instead of being exposed (parallel.train_step).
+# Deferred gradient tails.  The weight-gradient launches (wgrad_img: ~1.4 ms per step) and the tail of the image branch
+# (image_gather_bwd -> pyramid_bwd: ~1.1 ms) depend on nothing that follows them in the backward pass and nothing in the backward pass
+# depends on them: they only produce parameter gradients.  Inside `with defer_weight_gradients() as d:` the backward functions hand
+# autograd their (zeroed) gradient buffers at once and park the launch in `d`; the training loop runs `d.run()` after loss.backward()
+# returned -- a data-parallel loop first starts the all-reduce of the point tables, so that the collective overlaps with these kernels
+# instead of being exposed (parallel.train_step).  Jobs of lane 1 (the image-branch tail: small grids, latency / atomics bound) are
+# issued on a side stream and run CONCURRENTLY with lane 0 (wgrad_img: HBM bound, 192-thread CTAs with few registers).
 _DEFER = None
+_SIDE = {}
+
+
+def side_stream(dev) -> "torch.cuda.Stream":
+    key = torch.device(dev).index or 0
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=dev)
+    return _SIDE[key]
 
 
 class defer_weight_gradients:
-    def __init__(self):
-        self.jobs = []          # (launch closure, [(parameter, gradient buffer)])
+    def __init__(self, side: bool = True):
+        self.jobs = []          # (launch closure, [(parameter, gradient buffer)], lane)
+        self.side = side and os.environ.get("HNR_SIDE_STREAM", "1") != "0"
 
     def __enter__(self):
         global _DEFER
@@ -510,8 +521,25 @@ class defer_weight_gradients:
         _DEFER = self._prev
 
     def run(self):
-        for fn, pairs in self.jobs:
+        lane1 = [j for j in self.jobs if j[2] == 1]
+        lane0 = [j for j in self.jobs if j[2] == 0]
+        main = torch.cuda.current_stream()
+        side = None
+        if lane1 and self.side and lane0:
+            side = side_stream(main.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                for fn, _, _ in lane1:
+                    fn()
+        else:
+            lane0 = self.jobs
+        for fn, _, _ in lane0:
             fn()
+        if side is not None:
+            # every buffer the side lane touched was allocated on `main` and is still referenced by self.jobs here: nothing can be
+            # recycled before the join below
+            main.wait_stream(side)
+        for _, pairs, _ in self.jobs:
             for p, buf in pairs:
                 # autograd normally adopts the returned buffer as p.grad (same storage: nothing to do); if it cloned it instead (the clone
                 # was taken before the launch above filled the buffer), add the result to the clone
@@ -526,9 +554,9 @@ def alias(t: torch.Tensor) -> torch.Tensor:
     return torch.empty(0, dtype=t.dtype, device=t.device).set_(t.untyped_storage(), t.storage_offset(), t.size(), t.stride())
 
 
-def _wgrad_launch(fn, pairs):
+def _wgrad_launch(fn, pairs, lane: int = 0):
     if _DEFER is not None:
-        _DEFER.jobs.append((fn, pairs))
+        _DEFER.jobs.append((fn, pairs, lane))
     else:
         fn()
 
@@ -698,6 +726,7 @@ class PyramidFn(torch.autograd.Function):
         with _launch(6, name="pyramid_fwd"):
             check(lib().hnr_pyramid_fwd(ptr(img), ptr_array(ws), ptr_array(bs), ptr_array(act), V, H, W, stream()), "pyramid_fwd")
         ctx.save_for_backward(img, *ws, *act)
+        ctx.wparams = list(params)
         ctx.mark_non_differentiable(act[0], act[2], act[4])
         return act[1], act[3], act[5]
 
@@ -716,9 +745,18 @@ class PyramidFn(torch.autograd.Function):
         c = lambda t: _f32c(t) if t is not None else None
         if d3 is None:
             d3 = torch.zeros_like(act[5])
-        with _launch(11, name="pyramid_bwd"):
-            check(lib().hnr_pyramid_bwd(ptr(img), ptr_array(ws), ptr_array(act), ptr_array([c(d1), c(d2), c(d3)]), ptr_array(dws), ptr_array(dbs),
-                                        ptr_array(scratch), V, H, W, stream()), "pyramid_bwd")
+        ds = [c(d1), c(d2), c(d3)]
+        aw, ab = [alias(t) for t in dws], [alias(t) for t in dbs]          # the parked launch refers to aliases only (see alias())
+
+        def launch():
+            with _launch(11, name="pyramid_bwd"):
+                check(lib().hnr_pyramid_bwd(ptr(img), ptr_array(ws), ptr_array(act), ptr_array(ds), ptr_array(aw), ptr_array(ab),
+                                            ptr_array(scratch), V, H, W, stream()), "pyramid_bwd")
+        pairs = []
+        for i in range(6):
+            pairs += [(ctx.wparams[2 * i], aw[i]), (ctx.wparams[2 * i + 1], ab[i])]
+        _wgrad_launch(launch, pairs, lane=1)
+        del flat
         grads = []
         for dw, db in zip(dws, dbs):
             grads += [dw, db]
@@ -765,9 +803,14 @@ class ImageGatherFn(torch.autograd.Function):
         V, S, Nv = ctx.dims
         grads = [None] + [torch.zeros(s, device=xy.device, dtype=torch.float32) for s in ctx.shapes[1:]]
         d_aux = _f32c(d_aux)
-        with _launch(name="image_gather_bwd"):
-            check(lib().hnr_image_gather_bwd(ptr_array(grads), i64_array(ctx.hw), ptr(xy), ptr(vlist), ptr(d_aux), V, S, Nv, stream()),
-                  "image_gather_bwd")
+        hw = ctx.hw
+
+        def launch():
+            with _launch(name="image_gather_bwd"):
+                check(lib().hnr_image_gather_bwd(ptr_array(grads), i64_array(hw), ptr(xy), ptr(vlist), ptr(d_aux), V, S, Nv, stream()),
+                      "image_gather_bwd")
+        # the pyramid gradients feed pyramid_bwd only, which is parked behind this launch on the same lane (in order)
+        _wgrad_launch(launch, [], lane=1)
         return None, grads[1], grads[2], grads[3], None, None
 
 

@@ -68,11 +68,13 @@ def _flatten(tensors: Sequence[torch.Tensor]) -> torch.Tensor:
 
 
 def _unflatten_into(flat: torch.Tensor, tensors: Sequence[torch.Tensor]) -> None:
-    off = 0
+    off, views = 0, []
     for t in tensors:
         n = t.numel()
-        t.copy_(flat[off:off + n].view_as(t))
+        views.append(flat[off:off + n].view_as(t))
         off += n
+    if views:
+        torch._foreach_copy_(list(tensors), views)             # one multi-tensor launch instead of one copy per parameter
 
 
 def global_mean_scale(n_local_valid: torch.Tensor, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -132,6 +134,21 @@ def allreduce_gradients(params: Iterable[torch.nn.Parameter], n_local_valid: Opt
     return n_global
 
 
+_SMALL_GROUPS = {}
+
+
+def small_bucket_group(group=None):
+    """a SECOND communicator over the same ranks for the small (MLP + conv) gradient bucket.  Collectives of one communicator
+    execute in issue order on one stream: on the main group the 1.8 MB bucket would queue behind the 312 MB..1.25 GB point-table
+    all-reduce that train_step starts first, and the network's optimiser step (and with it the next forward) would wait for the
+    big transfer.  Created collectively on first use (every rank reaches train_step's first call together)."""
+    key = id(group)
+    if key not in _SMALL_GROUPS:
+        ranks = dist.get_process_group_ranks(group) if group is not None else None
+        _SMALL_GROUPS[key] = dist.new_group(ranks=ranks)
+    return _SMALL_GROUPS[key]
+
+
 def flush_pending(net) -> None:
     """apply a deferred point-table update now (call before evaluating, checkpointing or pruning / growing points)"""
     cb = getattr(net, "before_point_read", None)
@@ -147,8 +164,10 @@ def train_step(net, frame_shard: Dict[str, torch.Tensor], optimizers: Sequence[t
 
     Every rank must hold WHOLE dilated-patch rasters (its own (PN*PS)^2-ray batch, the unit the reference's patch drop and blur
     module work on); the global batch is the union of the ranks' rasters.
-    Overlap (world > 1): the loss is pre-scaled by n_local/n_global (no scaling pass over the tables); the small MLP bucket is
-    reduced first and its optimiser stepped at once; the in-place all-reduce of the point tables (39*N floats) is left in flight
+    Overlap (world > 1): the loss is pre-scaled by n_local/n_global (no scaling pass over the tables); the in-place all-reduce of
+    the point tables (39*N floats) is started as soon as backward has produced them, BEFORE the parked gradient tails (weight
+    gradients, image-branch tail: ops.defer_weight_gradients) are issued; the small MLP bucket is reduced on its own communicator
+    (small_bucket_group) and its optimiser stepped at once; the all-reduce of the point tables is left in flight
     and the optimiser(s) that own those tables step at the LAST possible moment -- inside the next forward, after its query and
     pyramid but before the first kernel that reads the tables (`net.before_point_read`), or at flush_pending(net).
     `next_frame_shard`: the shard of the NEXT step, if known -- its voxel query is enqueued before this step's backward pass so
@@ -194,7 +213,7 @@ def train_step(net, frame_shard: Dict[str, torch.Tensor], optimizers: Sequence[t
     _, pending = allreduce_gradients(large_params, None, group, bucket_bytes=large_bytes, prescaled=True, defer_large=True)
     with ops.tag("backward"):
         deferred.run()
-    allreduce_gradients([p for p in params if not is_large(p)], None, group, bucket_bytes=64 << 20, prescaled=True)
+    allreduce_gradients([p for p in params if not is_large(p)], None, small_bucket_group(group), bucket_bytes=64 << 20, prescaled=True)
     late = [o for o in optimizers if any(is_large(p) for g in o.param_groups for p in g["params"])]
     for o in optimizers:
         if o not in late:

@@ -54,6 +54,9 @@ def main():
         t = timeit(lambda: chain.chain_forward(am, [g, aux, dv], M=V * Nv, mods=(Nv, 0, 0), out=False, head=(hw, hb, 2)))
         fl = 2 * (176 * 64 + 2 * 64 * 64 + 64) * V * Nv
         print(f"am  chain: {t:.3f} ms  {fl / t / 1e9:.1f} TFLOP/s-equiv  in {(176) * 4 * V * Nv / t / 1e6:.0f} GB/s")
+        aux48 = torch.randn(V * Nv, 48, device="cuda")
+        t = timeit(lambda: chain.chain_forward(am, [g, aux48], M=V * Nv, mods=(Nv, 0), out=False, head=(hw, hb, 2)))
+        print(f"am  chain (48-wide aligned rows, inference layout): {t:.3f} ms  {fl / t / 1e9:.1f} TFLOP/s-equiv")
         t = timeit(lambda: chain.chain_forward(cm, [g[:, :45], merged], res=g[:, :45]))
         fl = 2 * (90 * 45 + 2 * 45 * 45) * Nv
         print(f"cm  chain: {t:.3f} ms  {fl / t / 1e9:.1f} TFLOP/s-equiv")

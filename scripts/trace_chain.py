@@ -17,6 +17,15 @@ with torch.no_grad():
         pc = chain.PackedChain(layers, [1, 1, 1], 280)
         X = torch.randn(Nv, 280, device="cuda")
         run = lambda: chain.chain_forward(pc, [X])
+    elif which == "am":
+        V = 4
+        layers, kin = [], 176
+        for w in (64, 64, 64):
+            layers.append(torch.nn.Linear(kin, w).cuda()); kin = w
+        head = torch.nn.Linear(64, 1).cuda()
+        pc = chain.PackedChain(layers, [1, 1, 1], 176)
+        g = torch.randn(Nv, 128, device="cuda"); aux = torch.randn(V * Nv, 48, device="cuda")
+        run = lambda: chain.chain_forward(pc, [g, aux], M=V * Nv, mods=(Nv, 0), out=False, head=(head.weight, head.bias, 2))
     else:
         layers, kin = [], 90
         for w in (45, 45, 45):
@@ -39,5 +48,9 @@ ev.sort()
 t0 = ev[0][0]
 names = {1: "mma.ready", 2: "mma.issued", 10: "gen.data", 11: "gen.free", 12: "gen.deliv", 20: "epi.acc", 21: "epi.ld", 22: "epi.done"}
 print("events", len(ev))
+# per-tile summary: time between successive 'epi.done' of the last layer
+last = max(e[3] for e in ev if e[2] == 22)
+done = [e[0] - t0 for e in ev if e[2] == 22 and e[3] == last]
+print("tile completion times (cycles):", done[:12], "mean period", (done[-1] - done[0]) / max(1, len(done) - 1))
 for e in ev[:int(sys.argv[2]) if len(sys.argv) > 2 else 400]:
     print(f"{e[0] - t0:8d} {'  ' * e[1]}{names.get(e[2], e[2]):11s} {e[3]:4d} {e[4]:6d}")
