@@ -44,6 +44,8 @@ _SIGS = {
     "hnr_image_gather_bwd": (C.c_int, [C.POINTER(vp), C.POINTER(i64), vp, vp, vp, i64, i64, i64, vp]),
     "hnr_blend_fwd": (C.c_int, [vp, vp, vp, vp, i64, i64, i64, vp, i64, vp]),
     "hnr_blend_bwd": (C.c_int, [vp, vp, vp, vp, vp, i64, i64, vp, vp, vp]),
+    "hnr_blend_bwd_ld": (C.c_int, [vp, i64, vp, vp, vp, vp, i64, i64, vp, i64, vp, vp]),
+    "hnr_image_gather_bwd_ld": (C.c_int, [C.POINTER(vp), C.POINTER(i64), vp, vp, vp, i64, i64, i64, i64, vp]),
     "hnr_linear_fwd": (C.c_int, [C.POINTER(vp), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), vp, vp, vp, i64, vp, i64, i64, i64,
                                  i64, C.c_int, vp]),
     "hnr_linear_bwd_data": (C.c_int, [vp, i64, vp, i64, vp, C.POINTER(vp), C.POINTER(i64), C.POINTER(i64), i64, i64, i64, C.c_int, vp]),

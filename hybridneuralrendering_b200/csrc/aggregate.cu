@@ -448,7 +448,7 @@ __device__ __forceinline__ void bilin_setup(int dst, int in_size, int out_size, 
 template <bool BWD>
 __global__ void __launch_bounds__(256)
 image_gather_kernel(hnr_pyramid_t P, const float* __restrict__ xy, const int32_t* __restrict__ vlist, int V, int64_t S, int64_t Nv,
-                    float* __restrict__ aux, float* __restrict__ ok, const float* __restrict__ d_aux) {
+                    float* __restrict__ aux, float* __restrict__ ok, const float* __restrict__ d_aux, int d_ld = AUX_C) {
     const int lane = threadIdx.x & 31;
     const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (wid >= (int64_t)V * Nv) return;
@@ -483,7 +483,7 @@ image_gather_kernel(hnr_pyramid_t P, const float* __restrict__ xy, const int32_t
             aux[wid * AUX_C + ch] = val;
         } else {
             if (zero || l == 0) continue;
-            float g = d_aux[wid * AUX_C + ch];
+            float g = d_aux[wid * d_ld + ch];
             if (g == 0.f) continue;
             int y0, y1, x0, x1; float ly0, ly1, lx0, lx1;
             bilin_setup(py, P.h[l], H, y0, y1, ly0, ly1);
@@ -589,7 +589,7 @@ __global__ void blend_fwd_kernel(const float* __restrict__ aux, const float* __r
 __global__ void __launch_bounds__(256)
 blend_bwd_kernel(const float* __restrict__ aux, const float* __restrict__ sig, const float* __restrict__ ok,
                  const uint8_t* __restrict__ keep, const float* __restrict__ d_merged, int V, int64_t Nv, float* __restrict__ d_aux,
-                 float* __restrict__ d_sig) {
+                 float* __restrict__ d_sig, int ald, int dld) {
     const int lane = threadIdx.x & 31;
     const int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (n >= Nv) return;
@@ -603,7 +603,7 @@ blend_bwd_kernel(const float* __restrict__ aux, const float* __restrict__ sig, c
         dm[j] = (c < AUX_C && kept) ? d_merged[n * AUX_C + c] : 0.f;
         float num = 0.f;
         if (c < AUX_C)
-            for (int v = 0; v < V; ++v) num += aux[((int64_t)v * Nv + n) * AUX_C + c] * sig[(int64_t)v * Nv + n] * ok[(int64_t)v * Nv + n];
+            for (int v = 0; v < V; ++v) num += aux[((int64_t)v * Nv + n) * ald + c] * sig[(int64_t)v * Nv + n] * ok[(int64_t)v * Nv + n];
         mr[j] = num / den;
     }
     for (int v = 0; v < V; ++v) {
@@ -613,9 +613,11 @@ blend_bwd_kernel(const float* __restrict__ aux, const float* __restrict__ sig, c
         for (int j = 0; j < 2; ++j) {
             int c = lane + 32 * j;
             if (c < AUX_C) {
-                float a = aux[r * AUX_C + c];
-                d_aux[r * AUX_C + c] = dm[j] * w / den;
+                float a = aux[r * ald + c];
+                d_aux[r * dld + c] = dm[j] * w / den;
                 part += dm[j] * (a - mr[j]);
+            } else if (c < dld) {
+                d_aux[r * dld + c] = 0.f;                  // padding columns of 48-wide rows
             }
         }
         part = warp_sum(part);
@@ -777,14 +779,20 @@ extern "C" int hnr_image_gather_fwd(const float* const* levels, const int64_t* l
     return HNR_OK;
 }
 
-extern "C" int hnr_image_gather_bwd(float* const* level_grads, const int64_t* level_hw, const float* xy, const int32_t* vlist,
-                                    const float* d_aux, int64_t V, int64_t S, int64_t Nv, void* stream) {
+extern "C" int hnr_image_gather_bwd_ld(float* const* level_grads, const int64_t* level_hw, const float* xy, const int32_t* vlist,
+                                       const float* d_aux, int64_t d_ld, int64_t V, int64_t S, int64_t Nv, void* stream) {
     if (V * Nv == 0) return HNR_OK;
+    HNR_CHECK_ARG(d_ld >= AUX_C, "image_gather_bwd: d_aux row stride must be >= 45");
     hnr_pyramid_t P;
     fill_pyramid(P, nullptr, level_grads, level_hw);
-    image_gather_kernel<true><<<warp_blocks(V * Nv), 256, 0, (cudaStream_t)stream>>>(P, xy, vlist, (int)V, S, Nv, nullptr, nullptr, d_aux);
+    image_gather_kernel<true><<<warp_blocks(V * Nv), 256, 0, (cudaStream_t)stream>>>(P, xy, vlist, (int)V, S, Nv, nullptr, nullptr, d_aux, (int)d_ld);
     HNR_CHECK_LAUNCH("image_gather_bwd");
     return HNR_OK;
+}
+
+extern "C" int hnr_image_gather_bwd(float* const* level_grads, const int64_t* level_hw, const float* xy, const int32_t* vlist,
+                                    const float* d_aux, int64_t V, int64_t S, int64_t Nv, void* stream) {
+    return hnr_image_gather_bwd_ld(level_grads, level_hw, xy, vlist, d_aux, AUX_C, V, S, Nv, stream);
 }
 
 extern "C" int hnr_blend_fwd(const float* aux, const float* sig, const float* ok, const uint8_t* keep, int64_t V, int64_t Nv,
@@ -797,10 +805,17 @@ extern "C" int hnr_blend_fwd(const float* aux, const float* sig, const float* ok
     return HNR_OK;
 }
 
-extern "C" int hnr_blend_bwd(const float* aux, const float* sig, const float* ok, const uint8_t* keep, const float* d_merged, int64_t V,
-                             int64_t Nv, float* d_aux, float* d_sig, void* stream) {
+extern "C" int hnr_blend_bwd_ld(const float* aux, int64_t aux_ld, const float* sig, const float* ok, const uint8_t* keep, const float* d_merged,
+                                int64_t V, int64_t Nv, float* d_aux, int64_t d_aux_ld, float* d_sig, void* stream) {
     if (Nv == 0) return HNR_OK;
-    blend_bwd_kernel<<<warp_blocks(Nv), 256, 0, (cudaStream_t)stream>>>(aux, sig, ok, keep, d_merged, (int)V, Nv, d_aux, d_sig);
+    HNR_CHECK_ARG(aux_ld >= AUX_C && d_aux_ld >= AUX_C && d_aux_ld <= 64, "blend_bwd: row strides must be in [45, 64]");
+    blend_bwd_kernel<<<warp_blocks(Nv), 256, 0, (cudaStream_t)stream>>>(aux, sig, ok, keep, d_merged, (int)V, Nv, d_aux, d_sig, (int)aux_ld,
+                                                                        (int)d_aux_ld);
     HNR_CHECK_LAUNCH("blend_bwd");
     return HNR_OK;
+}
+
+extern "C" int hnr_blend_bwd(const float* aux, const float* sig, const float* ok, const uint8_t* keep, const float* d_merged, int64_t V,
+                             int64_t Nv, float* d_aux, float* d_sig, void* stream) {
+    return hnr_blend_bwd_ld(aux, AUX_C, sig, ok, keep, d_merged, V, Nv, d_aux, AUX_C, d_sig, stream);
 }

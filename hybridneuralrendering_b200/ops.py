@@ -777,22 +777,26 @@ def project_views(loc_w: torch.Tensor, w2c: torch.Tensor, Kmat: torch.Tensor, ca
 
 
 class ImageGatherFn(torch.autograd.Function):
-    """levels NHWC (V,H,W,3),(V,h1,w1,6),(V,h2,w2,12),(V,h3,w3,24); xy (V,S,2) -> aux (V,Nv,45), ok (V,Nv)."""
+    """levels NHWC (V,H,W,3),(V,h1,w1,6),(V,h2,w2,12),(V,h3,w3,24); xy (V,S,2) -> aux (V,Nv,45), ok (V,Nv).
+    With `delta` (V,S,3): 48-wide rows [aux 45 | dview 3] (16-byte aligned: the blend-weight chain reads them with vector loads);
+    the incoming gradient then has 48-wide rows too, of which columns 45..47 (the view-direction difference: data) are ignored."""
 
     @staticmethod
-    def forward(ctx, l0, l1, l2, l3, xy, vlist):
+    def forward(ctx, l0, l1, l2, l3, xy, vlist, delta=None):
         lv = [_f32c(l) for l in (l0, l1, l2, l3)]
         require_cuda(*lv, xy, vlist)
         V, S, Nv = xy.shape[0], xy.shape[1], vlist.shape[0]
         hw = []
         for l in lv:
             hw += [l.shape[1], l.shape[2]]
-        aux = torch.empty((V, Nv, AUX_C), device=xy.device, dtype=torch.float32)
+        ld = AUX_C if delta is None else AUX_LD
+        aux = torch.empty((V, Nv, ld), device=xy.device, dtype=torch.float32)
         ok = torch.empty((V, Nv), device=xy.device, dtype=torch.float32)
+        d = _f32c(delta.reshape(V, S, 3)) if delta is not None else None
         with _launch():
-            check(lib().hnr_image_gather_fwd(ptr_array(lv), i64_array(hw), ptr(xy), ptr(vlist), V, S, Nv, ptr(aux), ptr(ok), AUX_C, None,
+            check(lib().hnr_image_gather_fwd(ptr_array(lv), i64_array(hw), ptr(xy), ptr(vlist), V, S, Nv, ptr(aux), ptr(ok), ld, ptr(d),
                                              stream()), "image_gather_fwd")
-        ctx.hw, ctx.shapes, ctx.dims = hw, [l.shape for l in lv], (V, S, Nv)
+        ctx.hw, ctx.shapes, ctx.dims, ctx.ld = hw, [l.shape for l in lv], (V, S, Nv), ld
         ctx.save_for_backward(xy, vlist)
         ctx.mark_non_differentiable(ok)
         return aux, ok
@@ -803,15 +807,15 @@ class ImageGatherFn(torch.autograd.Function):
         V, S, Nv = ctx.dims
         grads = [None] + [torch.zeros(s, device=xy.device, dtype=torch.float32) for s in ctx.shapes[1:]]
         d_aux = _f32c(d_aux)
-        hw = ctx.hw
+        hw, ld = ctx.hw, ctx.ld
 
         def launch():
             with _launch(name="image_gather_bwd"):
-                check(lib().hnr_image_gather_bwd(ptr_array(grads), i64_array(hw), ptr(xy), ptr(vlist), ptr(d_aux), V, S, Nv, stream()),
+                check(lib().hnr_image_gather_bwd_ld(ptr_array(grads), i64_array(hw), ptr(xy), ptr(vlist), ptr(d_aux), ld, V, S, Nv, stream()),
                       "image_gather_bwd")
         # the pyramid gradients feed pyramid_bwd only, which is parked behind this launch on the same lane (in order)
         _wgrad_launch(launch, [], lane=1)
-        return None, grads[1], grads[2], grads[3], None, None
+        return None, grads[1], grads[2], grads[3], None, None, None
 
 
 AUX_LD = 48        # 16-byte aligned row stride of the no-grad image-branch tensors: [aux 45 | dview 3] and [merged 45 | 0 0 0]
@@ -844,15 +848,15 @@ def blend_padded(aux48, sig, ok, keep):
 
 
 class BlendFn(torch.autograd.Function):
-    """aux (V,Nv,45), sig (V*Nv,1), ok (V,Nv), keep (Nv) u8|None -> merged (Nv,45)."""
+    """aux (V,Nv,45 | 48), sig (V*Nv,1), ok (V,Nv), keep (Nv) u8|None -> merged (Nv,45)."""
 
     @staticmethod
     def forward(ctx, aux, sig, ok, keep):
         aux, sig = _f32c(aux), _f32c(sig)
-        V, Nv = aux.shape[0], aux.shape[1]
+        V, Nv, ld = aux.shape[0], aux.shape[1], aux.shape[2]
         merged = torch.empty((Nv, AUX_C), device=aux.device, dtype=torch.float32)
         with _launch():
-            check(lib().hnr_blend_fwd(ptr(aux), ptr(sig), ptr(ok), ptr(keep), V, Nv, AUX_C, ptr(merged), AUX_C, stream()), "blend_fwd")
+            check(lib().hnr_blend_fwd(ptr(aux), ptr(sig), ptr(ok), ptr(keep), V, Nv, ld, ptr(merged), AUX_C, stream()), "blend_fwd")
         ctx.save_for_backward(aux, sig, ok, keep if keep is not None else torch.empty(0, device=aux.device))
         ctx.has_keep = keep is not None
         return merged
@@ -860,12 +864,12 @@ class BlendFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_merged):
         aux, sig, ok, keep = ctx.saved_tensors
-        V, Nv = aux.shape[0], aux.shape[1]
+        V, Nv, ld = aux.shape[0], aux.shape[1], aux.shape[2]
         d_aux = torch.empty_like(aux)
         d_sig = torch.empty_like(sig)
         with _launch(name="blend_bwd"):
-            check(lib().hnr_blend_bwd(ptr(aux), ptr(sig), ptr(ok), ptr(keep) if ctx.has_keep else None, ptr(_f32c(d_merged)), V, Nv,
-                                      ptr(d_aux), ptr(d_sig), stream()), "blend_bwd")
+            check(lib().hnr_blend_bwd_ld(ptr(aux), ld, ptr(sig), ptr(ok), ptr(keep) if ctx.has_keep else None, ptr(_f32c(d_merged)), V, Nv,
+                                         ptr(d_aux), ld, ptr(d_sig), stream()), "blend_bwd")
         return d_aux, d_sig, None, None
 
 

@@ -317,6 +317,18 @@ class PointAggregator(nn.Module):
                                           head=(am[6].weight, am[6].bias, ACT_SIGMOID))[1]
             with ops.tag("blend"):
                 merged = ops.blend_padded(aux48, sig, ok, self._keep_mask(R, SR, vlist))
+        elif V > 0 and fused_t:
+            # training: the same 48-wide aligned rows [aux 45 | dview 3] as in inference (the blend-weight chain reads them with vector
+            # loads; 45-wide rows cost it 4x the load instructions); gradient rows are 48 wide, columns 45..47 are ignored
+            with ops.tag("image_gather"):
+                aux, ok = ops.ImageGatherFn.apply(levels[0], levels[1], levels[2], levels[3], xy, vlist, delta)
+            am = self.aux_merge_weight_block
+            with ops.tag("sample_mlp"):
+                c0 = self._AM_COLS0                                                      # kernel source order [g | aux | dview]
+                sig = chain.chain_train(tp.pc["am"], [am[0], am[2], am[4]], [ACT_LRELU] * 3, [g, aux.view(V * Nv, ops.AUX_LD)], M=V * Nv,
+                                        mods=(Nv, 0), head=(am[6], ACT_SIGMOID), cols0=c0, pb=tp.pb["am"])[1]
+            with ops.tag("blend"):
+                merged = ops.BlendFn.apply(aux, sig, ok, self._keep_mask(R, SR, vlist))
         elif V > 0:
             with ops.tag("image_gather"):
                 aux, ok = ops.ImageGatherFn.apply(levels[0], levels[1], levels[2], levels[3], xy, vlist)

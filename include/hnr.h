@@ -107,11 +107,17 @@ int hnr_image_gather_fwd(const float* const* levels, const int64_t* level_hw /* 
                          45..47 of a 48-wide row (the blend-weight net's input [aux | dview] in one aligned block) */, void* stream);
 int hnr_image_gather_bwd(float* const* level_grads, const int64_t* level_hw, const float* xy, const int32_t* vlist, const float* d_aux,
                          int64_t V, int64_t S, int64_t Nv, void* stream);
+/* same with a row stride for d_aux (48 = the aligned training rows [aux 45 | dview 3]; columns >= 45 are ignored) */
+int hnr_image_gather_bwd_ld(float* const* level_grads, const int64_t* level_hw, const float* xy, const int32_t* vlist, const float* d_aux,
+                            int64_t d_ld, int64_t V, int64_t S, int64_t Nv, void* stream);
 /* multi-view blend (:1199-1217) + train-time drop (:1222-1237) */
 int hnr_blend_fwd(const float* aux, const float* sig, const float* ok, const uint8_t* keep, int64_t V, int64_t Nv, int64_t aux_ld,
                   float* merged, int64_t merged_ld /* 45, or 48 with zero padding */, void* stream);
 int hnr_blend_bwd(const float* aux, const float* sig, const float* ok, const uint8_t* keep, const float* d_merged, int64_t V,
                   int64_t Nv, float* d_aux, float* d_sig, void* stream);
+/* same with row strides for aux and d_aux (45..64; padding columns of d_aux are zero-filled) */
+int hnr_blend_bwd_ld(const float* aux, int64_t aux_ld, const float* sig, const float* ok, const uint8_t* keep, const float* d_merged,
+                     int64_t V, int64_t Nv, float* d_aux, int64_t d_aux_ld, float* d_sig, void* stream);
 
 /* dense layers: y = act(concat(A0,A1,A2) W^T + b [+res]); W (N,K) row-major as nn.Linear
  * (layers built at point_aggregators.py:484-683).  act: 0 none, 1 LeakyReLU(0.01), 2 sigmoid,
