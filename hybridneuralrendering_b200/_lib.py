@@ -44,6 +44,8 @@ _SIGS = {
     "hnr_image_gather_bwd": (C.c_int, [C.POINTER(vp), C.POINTER(i64), vp, vp, vp, i64, i64, i64, vp]),
     "hnr_blend_fwd": (C.c_int, [vp, vp, vp, vp, i64, i64, i64, vp, i64, vp]),
     "hnr_blend_bwd": (C.c_int, [vp, vp, vp, vp, vp, i64, i64, vp, vp, vp]),
+    "hnr_peer_sum_f32": (C.c_int, [C.POINTER(vp), C.c_int, i64, vp, vp]),
+    "hnr_multimem_sum_f32": (C.c_int, [vp, i64, vp, vp]),
     "hnr_blend_bwd_ld": (C.c_int, [vp, i64, vp, vp, vp, vp, i64, i64, vp, i64, vp, vp]),
     "hnr_image_gather_bwd_ld": (C.c_int, [C.POINTER(vp), C.POINTER(i64), vp, vp, vp, i64, i64, i64, i64, vp]),
     "hnr_linear_fwd": (C.c_int, [C.POINTER(vp), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), vp, vp, vp, i64, vp, i64, i64, i64,
@@ -132,7 +134,14 @@ def ptr(t: Optional[torch.Tensor]):
     return C.c_void_p(t.data_ptr())
 
 
+_RAW_STREAM = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream():
+    """raw handle of torch's current stream on the current device.  torch.cuda.current_stream() builds a Stream object through several
+    Python layers (~20 us; ~60 launches per training step): the raw-stream accessor is ~50x cheaper"""
+    if _RAW_STREAM is not None:
+        return C.c_void_p(_RAW_STREAM(torch.cuda.current_device()))
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 

@@ -94,7 +94,9 @@ def train_step_benchmark(dev, steps: int = 5, warmup: int = 3, world: int = 1, p
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(warmup):
+    # at least one pass over the whole frame set: every frame has its own valid-sample count, i.e. its own activation sizes, and the
+    # caching allocator serves a new size with a cudaMalloc (a device synchronisation) the first time it sees it
+    for _ in range(max(warmup, FRAME_SET + 1)):
         cur, nx = next_pair()
         parallel.train_step(net, cur, opts, next_frame_shard=nx if prefetch else None)
     parallel.flush_pending(net)

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(PKG, "build")
 LIB = os.path.join(PKG, "libhnr.so")
-SOURCES = ["api.cu", "composite.cu", "blur.cu", "blur_learn.cu", "linear_simt.cu", "aggregate.cu", "query.cu", "linear_tc.cu", "nbr_mlp_f16.cu", "chain_f16.cu", "wgrad_tc.cu", "adam.cu", "frame.cu", "nbr_bwd_f16.cu", "wgrad_img.cu", "chain_bwd_f16.cu", "pack.cu", "pyramid.cu", "loss.cu"]
+SOURCES = ["api.cu", "composite.cu", "blur.cu", "blur_learn.cu", "linear_simt.cu", "aggregate.cu", "query.cu", "linear_tc.cu", "nbr_mlp_f16.cu", "chain_f16.cu", "wgrad_tc.cu", "adam.cu", "frame.cu", "nbr_bwd_f16.cu", "wgrad_img.cu", "chain_bwd_f16.cu", "pack.cu", "pyramid.cu", "loss.cu", "peer.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-I", os.path.join(ROOT, "include"), "-I", CSRC]
 

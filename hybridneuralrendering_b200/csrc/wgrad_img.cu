@@ -6,7 +6,7 @@
 // images, so a 32-row slab plane is a canonical MN-major UMMA operand (SBO = 512 B between 8-column groups, LBO = 128 B
 // between 8-row groups).  No thread ever touches an operand element:
 //   * one bulk-copy warp streams slabs (A = a 128-column half of dZ, B = all columns of X [+ an extra image, e.g. the 16-wide
-//     block3 extras]) through a 4-stage ring;
+//     block3 extras]) through a 3-stage ring;
 //   * one MMA warp issues, per 16 rows, kind::f16 (bf16) MMAs with M = 128 (n), N = up to 256 (+ a second block for inputs
 //     wider than 256), 3 per product (hi*hi + lo*hi + hi*lo), plus two MMAs against a constant block of ones that yield db;
 //     the accumulator (128 lanes x <= 304 fp32 columns) stays in TMEM for the CTA's whole share of the rows;
@@ -26,7 +26,10 @@ namespace {
 using namespace tc;
 
 constexpr int MAXJOB = 4;
-constexpr int NSTAGE = 4;
+// 3 stages x 55 KB keep ~160 KB of bulk copies in flight per SM (HBM needs ~45 KB to cover its latency at 44 GB/s per SM) and leave
+// ~60 KB of shared memory to the small-grid kernels of the image-branch tail, which run on a side stream CONCURRENTLY with this
+// kernel (ops.defer_weight_gradients): with 4 stages (222 KB) nothing else could be resident on the SM and the two lanes serialised
+constexpr int NSTAGE = 3;
 constexpr int A_BYTES = 2 * 16 * 512;           // hi + lo plane of a 128-column half: 16384
 constexpr int B_MAX_COLS = 288 + 16;            // widest [X | extra]
 constexpr int B_PLANE_MAX = B_MAX_COLS / 8 * 512;   // 19456

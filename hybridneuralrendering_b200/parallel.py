@@ -134,6 +134,71 @@ def allreduce_gradients(params: Iterable[torch.nn.Parameter], n_local_valid: Opt
     return n_global
 
 
+class PeerBucket:
+    """SUM all-reduce of a small set of fp32 gradients through NVLink peer memory (csrc/peer.cu) instead of an NCCL collective: the
+    gradients are copied into a symmetric buffer (one multi-tensor launch), a device-side barrier makes every rank's copy visible,
+    ONE own kernel per rank reads all copies over NVLink and sums them in rank order (bit-identical on every rank), a second barrier
+    releases the buffers.  Plumbing (symmetric allocation, rendezvous, barrier) is torch.distributed._symmetric_memory."""
+
+    def __init__(self, numel: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.n = (int(numel) + 3) // 4 * 4
+        self.buf = symm_mem.empty(self.n, dtype=torch.float32, device=device)
+        self.buf.zero_()
+        self.hdl = symm_mem.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        self.world = int(self.hdl.world_size)
+        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self.multicast = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
+        self.out = torch.empty(self.n, dtype=torch.float32, device=device)
+        if self.world > 16 or len(self.ptrs) != self.world:
+            raise RuntimeError("PeerBucket: unsupported world size")
+
+    def allreduce_(self, grads: Sequence[torch.Tensor], use_multimem: bool = False) -> None:
+        """in place: every tensor of `grads` becomes the sum over the ranks"""
+        import ctypes as C
+        from . import ops
+        from ._lib import check, lib, ptr, stream
+        views_in, views_out, off = [], [], 0
+        for g in grads:
+            n = g.numel()
+            views_in.append(self.buf[off:off + n].view_as(g))
+            views_out.append(self.out[off:off + n].view_as(g))
+            off += n
+        assert off <= self.n
+        torch._foreach_copy_(views_in, list(grads))
+        self.hdl.barrier(channel=0)                      # every rank's copy is complete
+        with ops._launch(name="peer_sum"):
+            if use_multimem and self.multicast:
+                check(lib().hnr_multimem_sum_f32(C.c_void_p(self.multicast), self.n, ptr(self.out), stream()), "multimem_sum")
+            else:
+                arr = (C.c_void_p * self.world)(*self.ptrs)
+                check(lib().hnr_peer_sum_f32(arr, self.world, self.n, ptr(self.out), stream()), "peer_sum")
+        self.hdl.barrier(channel=1)                      # every rank has read every copy: the buffers may be overwritten
+        torch._foreach_copy_(list(grads), views_out)
+
+
+_PEER_BUCKETS = {}
+_PEER_DISABLED = [False]
+
+
+def peer_bucket(numel: int, device, group=None) -> Optional[PeerBucket]:
+    """the PeerBucket for this (group, size), created collectively on first use; None when peer memory cannot be set up on this
+    system (no NVLink peer access / non-CUDA backend): the caller then uses an NCCL collective on small_bucket_group()"""
+    import os
+    if _PEER_DISABLED[0] or os.environ.get("HNR_SMALL_BUCKET", "peer") == "nccl" or torch.device(device).type != "cuda":
+        return None
+    key = (id(group), int(numel), torch.device(device).index)
+    if key not in _PEER_BUCKETS:
+        try:
+            _PEER_BUCKETS[key] = PeerBucket(numel, device, group)
+        except Exception as e:                              # noqa: BLE001 -- any failure here means "not available on this box"
+            import warnings
+            warnings.warn(f"hybridneuralrendering_b200: NVLink peer-memory all-reduce unavailable ({e!r}); the small gradient bucket uses NCCL")
+            _PEER_DISABLED[0] = True
+            return None
+    return _PEER_BUCKETS[key]
+
+
 _SMALL_GROUPS = {}
 
 
@@ -158,7 +223,8 @@ def flush_pending(net) -> None:
 
 
 def train_step(net, frame_shard: Dict[str, torch.Tensor], optimizers: Sequence[torch.optim.Optimizer], group=None,
-               zero_one_weight: float = 1e-4, next_frame_shard: Optional[Dict[str, torch.Tensor]] = None, large_bytes: int = 4 << 20):
+               zero_one_weight: float = 1e-4, next_frame_shard: Optional[Dict[str, torch.Tensor]] = None, large_bytes: int = 4 << 20,
+               timeline: Optional[list] = None):
     """One data-parallel training step on this rank's rays: forward (fused hot path), loss, backward, gradient all-reduce with
     global-mean normalisation, optimiser steps.  Returns (loss, n_global_valid), both device tensors.
 
@@ -176,6 +242,14 @@ def train_step(net, frame_shard: Dict[str, torch.Tensor], optimizers: Sequence[t
     from .renderer import training_loss
     world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
     opt = getattr(net, "opt", None)
+
+    def mark(name):
+        """profiling aid (scripts/dp_timeline.py): a CUDA event on the main stream at this point of the step"""
+        if timeline is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            timeline.append((name, ev))
+    mark("start")
     if world > 1 and opt is not None and getattr(opt, "is_train", False) and getattr(opt, "drop_ratio", 0) > 0 and getattr(opt, "use_nearest", 0) > 0:
         toks = str(opt.dilation_setup).split("_")
         if frame_shard["raydir"].shape[1] != (int(toks[0]) * int(toks[1])) ** 2:
@@ -186,6 +260,7 @@ def train_step(net, frame_shard: Dict[str, torch.Tensor], optimizers: Sequence[t
         o.zero_grad(set_to_none=True)
     out = net(**frame_shard)                        # a deferred point update of the previous step is applied inside (before_point_read)
     flush_pending(net)                               # ... or here, if the forward had nothing to read (no kept ray)
+    mark("forward_end")
     n_local = (out["ray_mask"] > 0).sum()
     scale = n_global = None
     if world > 1:
@@ -201,11 +276,14 @@ def train_step(net, frame_shard: Dict[str, torch.Tensor], optimizers: Sequence[t
                 (loss * scale[0] if scale is not None else loss).backward()
         else:
             loss = torch.zeros((), device=out["ray_mask"].device)
+    mark("backward_end")
     if world == 1:
         with ops.tag("backward"):
             deferred.run()
+        mark("tails_end")
         for o in optimizers:
             o.step()
+        mark("end")
         return loss.detach(), n_local
     params = [p for o in optimizers for g in o.param_groups for p in g["params"]]
     is_large = lambda p: p.numel() * p.element_size() >= large_bytes
@@ -213,17 +291,33 @@ def train_step(net, frame_shard: Dict[str, torch.Tensor], optimizers: Sequence[t
     _, pending = allreduce_gradients(large_params, None, group, bucket_bytes=large_bytes, prescaled=True, defer_large=True)
     with ops.tag("backward"):
         deferred.run()
-    allreduce_gradients([p for p in params if not is_large(p)], None, small_bucket_group(group), bucket_bytes=64 << 20, prescaled=True)
+    mark("tails_end")
+    small_params = [p for p in params if not is_large(p) and p.requires_grad]
+    for p in small_params:
+        if p.grad is None:
+            p.grad = torch.zeros_like(p)
+    pb = peer_bucket(sum(p.numel() for p in small_params), small_params[0].device, group) if small_params else None
+    if pb is not None:
+        # the network's gradients (1.8 MB): own one-shot all-reduce over NVLink peer memory (csrc/peer.cu)
+        import os
+        pb.allreduce_([p.grad for p in small_params], use_multimem=os.environ.get("HNR_SMALL_BUCKET") == "multimem")
+    else:
+        allreduce_gradients(small_params, None, small_bucket_group(group), bucket_bytes=64 << 20, prescaled=True)
+    mark("small_bucket_done")
     late = [o for o in optimizers if any(is_large(p) for g in o.param_groups for p in g["params"])]
     for o in optimizers:
         if o not in late:
             o.step()
+    mark("end")
 
     def apply_late():
+        mark("late_begin")                           # (inside the NEXT forward: after its packing / pyramid / query)
         for h, _ in pending:
             h.wait()
+        mark("late_allreduce_done")
         for o in late:
             o.step()
+        mark("late_end")
     if late and hasattr(net, "before_point_read"):
         net.before_point_read = apply_late
     else:

@@ -325,6 +325,13 @@ int hnr_frame_rays(const int32_t* patches, int64_t patch_num, int64_t patch_size
                    float* gt_image, void* stream);
 int hnr_frame_views(const uint8_t* bank, const int32_t* view_ids, int64_t n_views, int64_t frame_bytes, float* out, void* stream);
 
+/* ---- multi-GPU: one-shot SUM all-reduce of a small fp32 buffer over NVLink peer memory (csrc/peer.cu).  No reference
+ * counterpart (the reference is single-GPU); semantic = ncclAllReduce(ncclSum).  `peers`: device addresses of the
+ * `world` copies of a symmetric buffer as mapped into this process, in rank order; result bit-identical on every rank. */
+int hnr_peer_sum_f32(const void* const* peers, int world, int64_t n, float* out, void* stream);
+/* the same with ONE multimem.ld_reduce per 16 bytes on the buffer's multicast address (reduction inside the NVSwitch) */
+int hnr_multimem_sum_f32(const void* mc, int64_t n, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
