@@ -162,9 +162,11 @@ def train_step_benchmark(dev, steps: int = 5, warmup: int = 3, world: int = 1, p
     if stage_split:
         barrier()
         ops.TIMERS = []
+        ops.SIDE_LANE = False                 # per-kernel times: nothing runs beside the kernel being timed
         with ops.tag("step"):
             parallel.train_step(net, frame, opts, next_frame_shard=nxt)
         parallel.flush_pending(net)
+        ops.SIDE_LANE = True
         torch.cuda.synchronize()
         for tg, a, b in ops.TIMERS:
             tg = tg.split("[")[0]

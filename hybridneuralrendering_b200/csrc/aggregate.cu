@@ -565,6 +565,54 @@ image_gather_fwd_v2_kernel(hnr_pyramid_t P, const float* __restrict__ xy, const 
     if (l != 1) { o[ch0 + 2] = r2; o[ch0 + 3] = r3; }
 }
 
+// Backward of the lookup with the forward's lane mapping: 16 sub-lanes per (view, sample), sub-lane q < 12 owns one float4 (levels 3, 2)
+// or float2 (level 1) channel group of one pyramid level and scatters its gradient to the 4 taps with VECTOR reductions
+// (red.global.add.v4.f32 / .v2.f32, sm_90+): 48 reduction instructions per (view, sample) instead of 168 scalar atomics -- the
+// kernel is bound by the L2 atomic units.  Level 0 (the rgb image) receives no gradient.
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void red_add_v2(float* p, float a, float b) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+__global__ void __launch_bounds__(256)
+image_gather_bwd_v2_kernel(hnr_pyramid_t P, const float* __restrict__ xy, const int32_t* __restrict__ vlist, int V, int64_t S, int64_t Nv,
+                           const float* __restrict__ d_aux, int d_ld) {
+    const int q = threadIdx.x & 15;
+    const int64_t pair = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    if (pair >= (int64_t)V * Nv || q > 11) return;
+    const int v = (int)(pair / Nv);
+    const int64_t n = pair - (int64_t)v * Nv;
+    const int64_t s = vlist[n];
+    const float2 f = *reinterpret_cast<const float2*>(xy + ((int64_t)v * S + s) * 2);
+    const int px = (int)f.x, py = (int)f.y;
+    const int H = P.h[0], W = P.w[0];
+    const bool inb = !(px < 0 || px >= W || py < 0 || py >= H);
+    if (!inb || (px == 0 && py == 0)) return;                // zeroed slot: no gradient
+    const int l = q < 6 ? 3 : (q < 9 ? 2 : 1);
+    const int grp = q < 6 ? q : (q < 9 ? q - 6 : q - 9);
+    const int ch0 = l == 3 ? 21 + 4 * grp : (l == 2 ? 9 + 4 * grp : 3 + 2 * grp);
+    const float* gp = d_aux + pair * d_ld + ch0;
+    const float g0 = gp[0], g1 = gp[1], g2 = l != 1 ? gp[2] : 0.f, g3 = l != 1 ? gp[3] : 0.f;
+    if (g0 == 0.f && g1 == 0.f && g2 == 0.f && g3 == 0.f) return;
+    int y0, y1, x0, x1; float ly0, ly1, lx0, lx1;
+    const int hl = l == 3 ? P.h[3] : (l == 2 ? P.h[2] : P.h[1]), wl = l == 3 ? P.w[3] : (l == 2 ? P.w[2] : P.w[1]);
+    const int C = l == 3 ? 24 : (l == 2 ? 12 : 6);
+    float* lv = l == 3 ? P.grad[3] : (l == 2 ? P.grad[2] : P.grad[1]);
+    bilin_setup(py, hl, H, y0, y1, ly0, ly1);
+    bilin_setup(px, wl, W, x0, x1, lx0, lx1);
+    float* b = lv + (int64_t)v * hl * wl * C + (l == 1 ? 2 * grp : 4 * grp);
+    const int o00 = (y0 * wl + x0) * C, o01 = (y0 * wl + x1) * C, o10 = (y1 * wl + x0) * C, o11 = (y1 * wl + x1) * C;
+    const float w00 = ly0 * lx0, w01 = ly0 * lx1, w10 = ly1 * lx0, w11 = ly1 * lx1;
+    if (l == 1) {
+        red_add_v2(b + o00, g0 * w00, g1 * w00); red_add_v2(b + o01, g0 * w01, g1 * w01);
+        red_add_v2(b + o10, g0 * w10, g1 * w10); red_add_v2(b + o11, g0 * w11, g1 * w11);
+    } else {
+        red_add_v4(b + o00, g0 * w00, g1 * w00, g2 * w00, g3 * w00); red_add_v4(b + o01, g0 * w01, g1 * w01, g2 * w01, g3 * w01);
+        red_add_v4(b + o10, g0 * w10, g1 * w10, g2 * w10, g3 * w10); red_add_v4(b + o11, g0 * w11, g1 * w11, g2 * w11, g3 * w11);
+    }
+}
+
 // ------------------------------------------------------------------ I3: learned multi-view blend
 // thread per (sample, channel): merged = keep * sum_v aux_v w_v / (sum_v w_v + 1e-6), w_v = sig_v * ok_v
 __global__ void blend_fwd_kernel(const float* __restrict__ aux, const float* __restrict__ sig, const float* __restrict__ ok,
@@ -785,7 +833,14 @@ extern "C" int hnr_image_gather_bwd_ld(float* const* level_grads, const int64_t*
     HNR_CHECK_ARG(d_ld >= AUX_C, "image_gather_bwd: d_aux row stride must be >= 45");
     hnr_pyramid_t P;
     fill_pyramid(P, nullptr, level_grads, level_hw);
-    image_gather_kernel<true><<<warp_blocks(V * Nv), 256, 0, (cudaStream_t)stream>>>(P, xy, vlist, (int)V, S, Nv, nullptr, nullptr, d_aux, (int)d_ld);
+    // vector reductions need the standard 6 / 12 / 24-channel pyramid with 8- / 16-byte aligned gradient tensors
+    const bool vec_ok = P.c[1] == 6 && P.c[2] == 12 && P.c[3] == 24 && (reinterpret_cast<uintptr_t>(level_grads[1]) & 7) == 0 &&
+                        (reinterpret_cast<uintptr_t>(level_grads[2]) & 15) == 0 && (reinterpret_cast<uintptr_t>(level_grads[3]) & 15) == 0 &&
+                        (reinterpret_cast<uintptr_t>(xy) & 7) == 0 && (int64_t)P.h[1] * P.w[1] * 24 < (1ll << 31);
+    if (vec_ok)
+        image_gather_bwd_v2_kernel<<<(unsigned)hnr_cdiv(V * Nv * 16, 256), 256, 0, (cudaStream_t)stream>>>(P, xy, vlist, (int)V, S, Nv, d_aux, (int)d_ld);
+    else
+        image_gather_kernel<true><<<warp_blocks(V * Nv), 256, 0, (cudaStream_t)stream>>>(P, xy, vlist, (int)V, S, Nv, nullptr, nullptr, d_aux, (int)d_ld);
     HNR_CHECK_LAUNCH("image_gather_bwd");
     return HNR_OK;
 }

@@ -497,6 +497,7 @@ class NbrMlpFusedFn(torch.autograd.Function):
 # issued on a side stream and run CONCURRENTLY with lane 0 (wgrad_img: HBM bound, 192-thread CTAs with few registers).
 _DEFER = None
 _SIDE = {}
+SIDE_LANE = True        # False: the image-branch tail runs on the main stream behind the weight gradients (clean per-kernel timings)
 
 
 def side_stream(dev) -> "torch.cuda.Stream":
@@ -509,7 +510,7 @@ def side_stream(dev) -> "torch.cuda.Stream":
 class defer_weight_gradients:
     def __init__(self, side: bool = True):
         self.jobs = []          # (launch closure, [(parameter, gradient buffer)], lane)
-        self.side = side and os.environ.get("HNR_SIDE_STREAM", "1") != "0"
+        self.side = side and SIDE_LANE and os.environ.get("HNR_SIDE_STREAM", "1") != "0"
 
     def __enter__(self):
         global _DEFER

@@ -319,3 +319,58 @@ def test_fused_training_loss_matches_torch():
     assert_close(loss, ref, 1e-5, 1e-8)
     assert_close(color.grad, c64.grad, 1e-5, 1e-10)
     assert_close(cc.grad, cc64.grad, 1e-5, 1e-12)
+
+
+@pytest.mark.parametrize("world,n", [(1, 64), (3, 4096), (8, 354624)])
+def test_peer_sum_kernel_sums_in_rank_order(world, n):
+    """csrc/peer.cu on one device: `world` local buffers stand in for the peers' copies of the symmetric buffer.  The sum must be the
+    fp32 sum in rank order (what makes the result bit-identical on every rank of a data-parallel run); the multi-process path over
+    real NVLink peers is checked by scripts/check_peer_allreduce.py against NCCL (bit-identical replicas, 2 and 8 GPUs)."""
+    import ctypes as C
+    from hybridneuralrendering_b200._lib import check, lib, ptr
+    g = torch.Generator(device="cuda").manual_seed(world)
+    bufs = [torch.randn(n, device="cuda", generator=g) * (10.0 ** (r % 3)) for r in range(world)]
+    out = torch.empty(n, device="cuda")
+    arr = (C.c_void_p * world)(*[b.data_ptr() for b in bufs])
+    check(lib().hnr_peer_sum_f32(arr, world, n, ptr(out), None), "peer_sum")
+    ref = torch.zeros(n, device="cuda")
+    for b in bufs:
+        ref = ref + b                      # same order, same fp32 additions
+    assert torch.equal(out, ref)
+    with pytest.raises(RuntimeError):
+        check(lib().hnr_peer_sum_f32(arr, world, n - 1, ptr(out), None), "peer_sum")          # n % 4 != 0 is rejected
+
+
+def test_strided_blend_and_image_gather_backward_match_the_dense_entry_points():
+    """the 48-wide aligned training rows [aux 45 | dview 3]: hnr_blend_bwd_ld / hnr_image_gather_bwd_ld on strided rows give what the
+    45-wide entry points give on packed rows (padding columns of d_aux zero-filled, columns >= 45 of the incoming gradient ignored)"""
+    from hybridneuralrendering_b200 import ops
+    from hybridneuralrendering_b200._lib import check, i64_array, lib, ptr, ptr_array
+    rng = np.random.default_rng(11)
+    V, Nv, S = 3, 517, 700
+    aux = cuda(rng.standard_normal((V, Nv, 45)).astype(np.float32))
+    aux48 = torch.zeros((V, Nv, 48), device="cuda"); aux48[..., :45] = aux; aux48[..., 45:] = 7.0
+    sig = cuda(rng.random((V * Nv, 1)).astype(np.float32))
+    okm = cuda((rng.random((V, Nv)) > 0.2).astype(np.float32))
+    keep = cuda((rng.random(Nv) > 0.3).astype(np.uint8))
+    dm = cuda(rng.standard_normal((Nv, 45)).astype(np.float32))
+    d_aux, d_sig = torch.empty_like(aux), torch.empty_like(sig)
+    check(lib().hnr_blend_bwd(ptr(aux), ptr(sig), ptr(okm), ptr(keep), ptr(dm), V, Nv, ptr(d_aux), ptr(d_sig), None), "blend_bwd")
+    d_aux48, d_sig2 = torch.full_like(aux48, float("nan")), torch.empty_like(sig)
+    check(lib().hnr_blend_bwd_ld(ptr(aux48), 48, ptr(sig), ptr(okm), ptr(keep), ptr(dm), V, Nv, ptr(d_aux48), 48, ptr(d_sig2), None), "blend_bwd_ld")
+    assert torch.equal(d_aux48[..., :45], d_aux) and torch.equal(d_sig2, d_sig) and float(d_aux48[..., 45:].abs().max()) == 0.0
+    # image-gather backward: gradient rows 45 vs 48 wide
+    H, W = 24, 32
+    shapes = [(V, H, W, 3), (V, 12, 16, 6), (V, 6, 8, 12), (V, 3, 4, 24)]
+    hw = [x for s in shapes for x in s[1:3]]
+    xy = cuda((rng.random((V, S, 2)) * np.array([W + 4, H + 4]) - 2).astype(np.float32))
+    vlist = cuda(np.sort(rng.choice(S, Nv, replace=False)).astype(np.int32))
+    g45 = cuda(rng.standard_normal((V, Nv, 45)).astype(np.float32))
+    g48 = torch.full((V, Nv, 48), 3.0, device="cuda"); g48[..., :45] = g45
+    res = []
+    for g, ld in ((g45, 45), (g48, 48)):
+        grads = [None] + [torch.zeros(s, device="cuda") for s in shapes[1:]]
+        check(lib().hnr_image_gather_bwd_ld(ptr_array(grads), i64_array(hw), ptr(xy), ptr(vlist), ptr(g), ld, V, S, Nv, None), "image_gather_bwd_ld")
+        res.append(grads[1:])
+    for a, b in zip(*res):
+        assert float((a - b).abs().max()) <= 1e-5 * float(a.abs().max() + 1e-30)          # atomics: arrival order only
