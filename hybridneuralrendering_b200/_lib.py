@@ -44,6 +44,7 @@ _SIGS = {
     "hnr_image_gather_bwd": (C.c_int, [C.POINTER(vp), C.POINTER(i64), vp, vp, vp, i64, i64, i64, vp]),
     "hnr_blend_fwd": (C.c_int, [vp, vp, vp, vp, i64, i64, i64, vp, i64, vp]),
     "hnr_blend_bwd": (C.c_int, [vp, vp, vp, vp, vp, i64, i64, vp, vp, vp]),
+    "hnr_linear_head_bwd": (C.c_int, [vp, vp, C.c_int, vp, vp, i64, i64, i64, vp, i64, vp, vp, vp]),
     "hnr_peer_sum_f32": (C.c_int, [C.POINTER(vp), C.c_int, i64, vp, vp]),
     "hnr_multimem_sum_f32": (C.c_int, [vp, i64, vp, vp]),
     "hnr_blend_bwd_ld": (C.c_int, [vp, i64, vp, vp, vp, vp, i64, i64, vp, i64, vp, vp]),
@@ -81,7 +82,7 @@ _SIGS = {
                                         C.POINTER(f32c), C.POINTER(vp), C.POINTER(i64), vp, i64, vp, vp, C.c_int, vp, i64, vp, vp]),
     "hnr_nbr_mlp_f16_forward": (C.c_int, [vp] * 17 + [C.POINTER(C.c_float), f32c, f32c, f32c, i64, i64, vp, vp, vp, vp, vp, vp]),
     "hnr_nbr_mlp_f16_forward_train": (C.c_int, [vp] * 17 + [C.POINTER(C.c_float), f32c, f32c, f32c, i64, i64] + [vp] * 11),
-    "hnr_alpha_ksum_bwd_img": (C.c_int, [vp] * 8 + [i64, i64, vp, vp, vp, vp, vp]),
+    "hnr_alpha_ksum_bwd_img": (C.c_int, [vp] * 8 + [i64, i64, vp, vp, vp, vp, vp, vp]),
     "hnr_nbr_bwd_f16_packed_bytes": (i64, []),
     "hnr_nbr_bwd_f16": (C.c_int, [vp] * 8 + [i64, i64, vp, i64, vp]),
     "hnr_dz_extras_bwd": (C.c_int, [vp, vp, i64, i64, i64, vp, vp]),

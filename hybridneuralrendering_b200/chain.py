@@ -412,7 +412,7 @@ class ChainFn(torch.autograd.Function):
         h = sv[p] if head_act >= 0 else None
         g_head = [None, None]
         if head_act >= 0:
-            (dcur,), dWh, dbh = ops.linear_backward(head_W, h, [y], (), dH, head_act, [True])
+            dcur, dWh, dbh = ops.linear_head_backward(head_W, h, y, dH, head_act)
             g_head = [dWh, dbh]
         else:
             dcur = dY

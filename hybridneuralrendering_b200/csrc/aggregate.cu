@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(256)
 alpha_ksum_bwd_img_kernel(const uint8_t* __restrict__ himg, const float* __restrict__ weight, const float* __restrict__ confc,
                           const int32_t* __restrict__ vlist, const float* __restrict__ w_alpha, const float* __restrict__ alpha_raw,
                           const float* __restrict__ d_sigma, const float* __restrict__ dX5, int64_t Nv, uint8_t* __restrict__ dzimg,
-                          float* __restrict__ d_wc, float* __restrict__ d_walpha, float* __restrict__ d_balpha) {
+                          float* __restrict__ d_wc, float* __restrict__ d_walpha, float* __restrict__ d_balpha, float* __restrict__ d_confc) {
     constexpr int KK = 8;
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -327,7 +327,10 @@ alpha_ksum_bwd_img_kernel(const uint8_t* __restrict__ himg, const float* __restr
 #pragma unroll
             for (int i = 0; i < 8; ++i) hd = fmaf(h[i], g[i], hd);
             hd = warp_sum(hd);
-            if (lane == 0) d_wc[row] = sp * ds + hd;
+            if (lane == 0) {
+                d_wc[row] = sp * ds + hd;
+                if (d_confc) d_confc[s * KK + k] = (sp * ds + hd) * weight[s * KK + k];      // straight into the (S, K) gradient of conf_coefficient
+            }
             float o[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -757,13 +760,13 @@ extern "C" int hnr_alpha_ksum_bwd(const float* H, const float* weight, const flo
 // image (dz3img; rows beyond Nv*8 are left to the consumer, hnr_nbr_bwd_f16 zeroes them).
 extern "C" int hnr_alpha_ksum_bwd_img(const void* h3img, const float* weight, const float* confc, const int32_t* vlist, const float* w_alpha,
                                       const float* alpha_raw, const float* d_sigma, const float* dX5, int64_t Nv, int64_t K, void* dz3img,
-                                      float* d_wc, float* d_walpha, float* d_balpha, void* stream) {
+                                      float* d_wc, float* d_walpha, float* d_balpha, float* d_confc, void* stream) {
     HNR_CHECK_ARG(K == 8, "alpha_ksum_bwd_img: K must be 8");
     if (Nv == 0) return HNR_OK;
     int64_t blocks = hnr_cdiv(Nv, 8);
     if (blocks > 4 * HNR_NUM_SMS) blocks = 4 * HNR_NUM_SMS;
     alpha_ksum_bwd_img_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const uint8_t*)h3img, weight, confc, vlist, w_alpha, alpha_raw,
-                                                                                 d_sigma, dX5, Nv, (uint8_t*)dz3img, d_wc, d_walpha, d_balpha);
+                                                                                 d_sigma, dX5, Nv, (uint8_t*)dz3img, d_wc, d_walpha, d_balpha, d_confc);
     HNR_CHECK_LAUNCH("alpha_ksum_bwd_img");
     return HNR_OK;
 }

@@ -455,3 +455,69 @@ extern "C" int hnr_linear_bwd_weight(const float* dY, int64_t lddy, const float*
     HNR_CHECK_LAUNCH("linear_bwd_weight");
     return HNR_OK;
 }
+
+// ------------------------------------------------------------------------------------------------------------------------------
+// Backward of a ONE-output layer h = act(y . w + b) in a single pass over its input rows (the sigmoid head of the blend-weight net:
+// 64 -> 1 over V*Nv = 602 k rows per training step, models/aggregators/point_aggregators.py:1199-1217).  Per row m:
+//     s = dH[m] * act'(h[m])        dY[m, :] = s * w        dW += s * y[m, :]        db += s
+// The generic kernels made two passes (data gradient 143 us + weight gradient 145 us, each reading or writing the 154 MB of y / dY)
+// with one row per warp slot; here K/4 lanes own one row (float4 per lane), 8 row groups are in flight per warp, y is read once and
+// dY written once.  K must be 64 or 128.
+template <int LPR>      // lanes per row: K / 4 (16 or 32)
+__global__ void __launch_bounds__(256) linear_head_bwd_kernel(const float* __restrict__ dH, const float* __restrict__ Hout, int act,
+                                                              const float* __restrict__ w, const float* __restrict__ Y, int64_t ldy,
+                                                              int64_t M, float* __restrict__ dY, int64_t lddy, float* __restrict__ dW,
+                                                              float* __restrict__ db) {
+    constexpr int RPW = 32 / LPR;           // rows per warp instruction
+    constexpr int UNROLL = 8;
+    __shared__ float sW[4 * LPR + 1];
+    for (int i = threadIdx.x; i < 4 * LPR + 1; i += blockDim.x) sW[i] = 0.f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, l = lane % LPR, rsub = lane / LPR;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const float4 w4 = __ldg(reinterpret_cast<const float4*>(w) + l);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float bs = 0.f;
+    for (int64_t m0 = warp0 * (RPW * UNROLL); m0 < M; m0 += nwarps * (RPW * UNROLL)) {
+        float4 y[UNROLL];
+        float sv[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const int64_t m = m0 + u * RPW + rsub;
+            y[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            sv[u] = 0.f;
+            if (m < M) {
+                y[u] = __ldg(reinterpret_cast<const float4*>(Y + m * ldy) + l);
+                sv[u] = __ldg(dH + m) * act_grad_from_out(__ldg(Hout + m), act);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const int64_t m = m0 + u * RPW + rsub;
+            const float sc = sv[u];
+            if (m < M) reinterpret_cast<float4*>(dY + m * lddy)[l] = make_float4(sc * w4.x, sc * w4.y, sc * w4.z, sc * w4.w);
+            acc.x = fmaf(sc, y[u].x, acc.x); acc.y = fmaf(sc, y[u].y, acc.y); acc.z = fmaf(sc, y[u].z, acc.z); acc.w = fmaf(sc, y[u].w, acc.w);
+            if (l == 0) bs += sc;
+        }
+    }
+    atomicAdd(&sW[4 * l + 0], acc.x); atomicAdd(&sW[4 * l + 1], acc.y); atomicAdd(&sW[4 * l + 2], acc.z); atomicAdd(&sW[4 * l + 3], acc.w);
+    if (l == 0) atomicAdd(&sW[4 * LPR], bs);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 4 * LPR; i += blockDim.x) atomicAdd(&dW[i], sW[i]);
+    if (threadIdx.x == 0 && db) atomicAdd(db, sW[4 * LPR]);
+}
+
+extern "C" int hnr_linear_head_bwd(const float* dH, const float* Hout, int act, const float* w, const float* Y, int64_t ldy, int64_t M,
+                                   int64_t K, float* dY, int64_t lddy, float* dW, float* db, void* stream) {
+    if (M == 0) return HNR_OK;
+    HNR_CHECK_ARG(K == 64 || K == 128, "linear_head_bwd: K must be 64 or 128");
+    HNR_CHECK_ARG(ldy % 4 == 0 && lddy % 4 == 0 && ((reinterpret_cast<uintptr_t>(Y) | reinterpret_cast<uintptr_t>(dY) | reinterpret_cast<uintptr_t>(w)) & 15) == 0,
+                  "linear_head_bwd: rows must be 16-byte aligned");
+    const int rpw = K == 64 ? 2 : 1;
+    const int64_t blocks = hnr_cdiv(M, 8 * rpw * 8 * 2);           // >= 2 iterations per warp before the CTA-level reduction
+    const int g = (int)(blocks < 8 * HNR_NUM_SMS ? (blocks < 1 ? 1 : blocks) : 8 * HNR_NUM_SMS);
+    if (K == 64) linear_head_bwd_kernel<16><<<g, 256, 0, (cudaStream_t)stream>>>(dH, Hout, act, w, Y, ldy, M, dY, lddy, dW, db);
+    else linear_head_bwd_kernel<32><<<g, 256, 0, (cudaStream_t)stream>>>(dH, Hout, act, w, Y, ldy, M, dY, lddy, dW, db);
+    HNR_CHECK_LAUNCH("linear_head_bwd");
+    return HNR_OK;
+}

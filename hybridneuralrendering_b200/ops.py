@@ -293,6 +293,23 @@ def linear_backward(W, Y, srcs, mods, dY, act: int, need_src, need_w: bool = Tru
     return d_srcs, dW, db
 
 
+def linear_head_backward(head_W: torch.Tensor, h: torch.Tensor, y: torch.Tensor, dH: torch.Tensor, act: int):
+    """gradients of the one-output layer h = act(y . w + b): (dY (M,K), dW (1,K), db (1,)) in ONE pass over y (csrc/linear_simt.cu
+    linear_head_bwd_kernel) when K is 64 or 128 and the rows are 16-byte aligned; the generic kernels otherwise."""
+    y, dH, h = _rows2d(y), _f32c(dH), _f32c(h)
+    M, K = y.shape
+    w = _f32c(head_W).view(-1)
+    if K in (64, 128) and y.stride(0) % 4 == 0 and y.data_ptr() % 16 == 0 and M > 0:
+        dY = torch.empty((M, K), device=y.device, dtype=torch.float32)
+        g = torch.zeros(K + 4, device=y.device, dtype=torch.float32)          # dW | db in one zero fill (16-byte aligned views)
+        with _launch(name="linear_head_bwd"):
+            check(lib().hnr_linear_head_bwd(ptr(dH), ptr(h), int(act), ptr(w), ptr(y), y.stride(0), M, K, ptr(dY), K, ptr(g), ptr(g[K:]),
+                                            stream()), "linear_head_bwd")
+        return dY, g[:K].view(1, K), g[K:K + 1]
+    (dY,), dW, db = linear_backward(head_W, h, [y], (), dH, act, [True])
+    return dY, dW, db
+
+
 def linear_head(srcs: Sequence[torch.Tensor], W, b, act: int, head_W, head_b, head_act: int, mods: Sequence[int] = (),
                 M: Optional[int] = None) -> torch.Tensor:
     """no-grad fusion of a dense layer with a following 1-output layer: head_act(act(cat(srcs) W^T + b) head_W^T + head_b)
@@ -607,14 +624,11 @@ class NbrMlpTrainFn(torch.autograd.Function):
             views.append(small[o:o + n_]); o += pad4(n_)
         d_wa, d_ba = views[0], views[1]
         gW = [views[2 + i].view(shapes[i]) for i in range(8)]
+        # the gradient of conf_coefficient (S,K) is written by the same kernel at the valid samples' rows (was: long + gather + mul + index_copy)
+        d_confc = torch.zeros_like(confc) if ctx.needs_input_grad[3] else None
         with _launch(name="alpha_ksum_bwd"):
             check(lib().hnr_alpha_ksum_bwd_img(ptr(h3), ptr(weight), ptr(confc), ptr(vlist), ptr(w_alpha), ptr(araw), ptr(d_sigma), ptr(dX5),
-                                               Nv, K, ptr(dz[3]), ptr(d_wc), ptr(d_wa), ptr(d_ba), stream()), "alpha_ksum_bwd_img")
-        d_confc = None
-        if ctx.needs_input_grad[3]:
-            vl = vlist.long()
-            d_confc = torch.zeros_like(confc)
-            d_confc.index_copy_(0, vl, d_wc * weight.index_select(0, vl))
+                                               Nv, K, ptr(dz[3]), ptr(d_wc), ptr(d_wa), ptr(d_ba), ptr(d_confc), stream()), "alpha_ksum_bwd_img")
         dX0 = torch.empty((rows, X0_GRAD_W), device=dev, dtype=torch.float32)
         with _launch(name="nbr_bwd_chain"):
             check(lib().hnr_nbr_bwd_f16(ptr(dz[3]), ptr(h2), ptr(h1), ptr(h0), ptr(dz[2]), ptr(dz[1]), ptr(dz[0]), ptr(dX0), X0_GRAD_W,
@@ -872,6 +886,24 @@ class BlendFn(torch.autograd.Function):
             check(lib().hnr_blend_bwd_ld(ptr(aux), ld, ptr(sig), ptr(ok), ptr(keep) if ctx.has_keep else None, ptr(_f32c(d_merged)), V, Nv,
                                          ptr(d_aux), ld, ptr(d_sig), stream()), "blend_bwd")
         return d_aux, d_sig, None, None
+
+
+class ScatterRowsFn(torch.autograd.Function):
+    """out (S,C) = zeros; out[idx] = src (Nv,C): the decoded [sigma | rgb] rows of the valid samples scattered back to all sample
+    slots.  Same result as zeros.index_copy(0, idx, src); its backward reads grad[idx] with the element-wise index kernel instead of
+    index_select's one-block-per-row gather (42 us for 75 k rows of 4 floats)."""
+
+    @staticmethod
+    def forward(ctx, src, idx, S: int):
+        out = torch.zeros((S, src.shape[1]), device=src.device, dtype=src.dtype)
+        out.index_copy_(0, idx, src)
+        ctx.save_for_backward(idx)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        return g[idx], None, None
 
 
 # --------------------------------------------------------------------------------------------

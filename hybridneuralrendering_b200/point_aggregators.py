@@ -231,7 +231,9 @@ class PointAggregator(nn.Module):
         if Nv == 0:
             return decoded, valid.bool(), weight, confc
         args = (tables, pidx, mask, loc_pers, loc_w, raydirs, cam, R, SR, levels, xy, delta, weight, confc)
-        if torch.is_grad_enabled() or Nv <= self.max_valid_chunk:
+        if torch.is_grad_enabled():
+            decoded = ops.ScatterRowsFn.apply(self._decode(vlist, *args), vlist.long(), S)
+        elif Nv <= self.max_valid_chunk:
             decoded = decoded.index_copy(0, vlist.long(), self._decode(vlist, *args))
         else:
             # inference over many samples (full frames): bound the activation memory by walking the valid-sample

@@ -131,6 +131,10 @@ int hnr_linear_bwd_data(const float* dY, int64_t lddy, const float* Y, int64_t l
 int hnr_linear_bwd_weight(const float* dY, int64_t lddy, const float* Y, int64_t ldy, const float* const* a_ptr, const int64_t* a_ld,
                           const int64_t* a_k, const int64_t* a_mod, float* dW, float* db, int64_t M, int64_t N, int64_t K, int act,
                           void* stream);
+/* backward of a ONE-output layer h = act(y.w + b) in one pass (csrc/linear_simt.cu; the sigmoid head of the blend-weight net,
+ * point_aggregators.py:1199-1217): dY[m,:] = dH[m] act'(h[m]) w, dW (K) += sum_m s_m y[m,:], db (1) += sum_m s_m.  K = 64 or 128. */
+int hnr_linear_head_bwd(const float* dH, const float* Hout, int act, const float* w, const float* Y, int64_t ldy, int64_t M, int64_t K,
+                        float* dY, int64_t lddy, float* dW, float* db, void* stream);
 /* data gradient of a narrow column slice [k0, k0+kn), kn <= 8, of a layer with N = 128 or 256 outputs: dA (M, kn) =
  * (dY * act'(Y)) (M,N) . W[:, k0:k0+kn]; W (N, ldw) row-major.  HBM-bound (one read of dY and Y); dY / Y rows 16-byte aligned. */
 int hnr_linear_bwd_data_narrow(const float* dY, int64_t lddy, const float* Y, int64_t ldy, int act, const float* W, int64_t ldw,
@@ -188,10 +192,11 @@ int hnr_nbr_mlp_f16_forward_train(const float* xyz, const float* xyz_pers, const
                                   float scale0, float scale2, float inv_act, int64_t Nv, int64_t K, float* sigma, float* X5,
                                   void* x0img, void* eimg, void* h0img, void* h1img, void* h2img, void* h3img, float* araw,
                                   int32_t* status, void* stream);
-/* backward of the density head + weighted K-sum (:1002-1036) from / to images: reads h3img, writes dz3img = dH * act'(H_3) */
+/* backward of the density head + weighted K-sum (:1002-1036) from / to images: reads h3img, writes dz3img = dH * act'(H_3);
+ * d_confc (S,K; pre-zeroed) or NULL: the gradient of conf_coefficient, d_wc * weight, written at the valid samples' rows */
 int hnr_alpha_ksum_bwd_img(const void* h3img, const float* weight, const float* confc, const int32_t* vlist, const float* w_alpha,
                            const float* alpha_raw, const float* d_sigma, const float* dX5, int64_t Nv, int64_t K, void* dz3img,
-                           float* d_wc, float* d_walpha, float* d_balpha, void* stream);
+                           float* d_wc, float* d_walpha, float* d_balpha, float* d_confc, void* stream);
 /* fused data-gradient chain dZ_3 -> dZ_2 -> dZ_1 -> dZ_0 -> dX0 (csrc/nbr_bwd_f16.cu; 3 x bf16 split on tcgen05, gradient
  * tile resident in shared memory / TMEM across the four layers).  wpackT: hnr_nbr_bwd_f16_packed_bytes() bytes built by
  * mlp_tc.pack_mlp_bwd.  dX0 (rows, ldx): the first nx0 input-gradient columns of layer 0. */

@@ -374,3 +374,23 @@ def test_strided_blend_and_image_gather_backward_match_the_dense_entry_points():
         res.append(grads[1:])
     for a, b in zip(*res):
         assert float((a - b).abs().max()) <= 1e-5 * float(a.abs().max() + 1e-30)          # atomics: arrival order only
+
+
+@pytest.mark.parametrize("M,K,act", [(5000, 64, 2), (777, 128, 2), (130, 64, 1), (300, 45, 2)])
+def test_one_pass_head_backward_matches_torch(M, K, act):
+    """ops.linear_head_backward (one pass over y for a one-output layer; generic kernels for widths other than 64 / 128) vs autograd"""
+    from hybridneuralrendering_b200 import ops
+    rng = np.random.default_rng(M + K)
+    y = cuda(rng.standard_normal((M, K)).astype(np.float32))
+    W = cuda((rng.standard_normal((1, K)) * 0.3).astype(np.float32))
+    b = cuda(np.array([0.1], np.float32))
+    dH = cuda(rng.standard_normal((M, 1)).astype(np.float32))
+    yd, Wd, bd = y.double().requires_grad_(True), W.double().requires_grad_(True), b.double().requires_grad_(True)
+    pre = yd @ Wd.t() + bd
+    hd = torch.sigmoid(pre) if act == 2 else torch.nn.functional.leaky_relu(pre, 0.01)
+    hd.backward(dH.double())
+    dY, dW, db = ops.linear_head_backward(W, hd.detach().float(), y, dH, act)
+    assert dW.shape == W.shape and db.shape == b.shape
+    assert_close(dY, yd.grad, RTOL, grad_atol(yd.grad))
+    assert_close(dW, Wd.grad, RTOL, grad_atol(Wd.grad))
+    assert_close(db, bd.grad, RTOL, grad_atol(bd.grad))
