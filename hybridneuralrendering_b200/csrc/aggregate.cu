@@ -284,6 +284,7 @@ alpha_ksum_bwd_kernel(const float* __restrict__ H, const float* __restrict__ wei
 // Same backward for the fused training path: the saved layer-3 output is read from its split image (img_common.cuh; lane = one
 // 8-column group = one 16-byte piece per plane) and the result is written as the GATED gradient dZ_3 = dH * act'(H) in the
 // same format -- the first operand of the fused data-gradient chain (nbr_bwd_f16.cu) and of the weight-gradient kernel.
+// (forcing two CTAs per SM with __launch_bounds__(256, 2) spills and is slower: 0.40 -> 0.51 ms)
 __global__ void __launch_bounds__(256)
 alpha_ksum_bwd_img_kernel(const uint8_t* __restrict__ himg, const float* __restrict__ weight, const float* __restrict__ confc,
                           const int32_t* __restrict__ vlist, const float* __restrict__ w_alpha, const float* __restrict__ alpha_raw,
