@@ -92,6 +92,11 @@ _SIGS = {
                                               C.POINTER(i64), C.POINTER(i64), C.POINTER(C.c_int), vp, C.POINTER(i64), vp, C.POINTER(f32c),
                                               C.POINTER(f32c), C.POINTER(vp), C.POINTER(i64), vp, i64, vp, vp, C.c_int, vp, i64, vp, vp,
                                               C.POINTER(vp), vp]),
+    "hnr_chain_f16_forward_add0": (C.c_int, [C.POINTER(vp), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), f32c, C.c_int, C.POINTER(i64),
+                                             C.POINTER(i64), C.POINTER(i64), C.POINTER(C.c_int), vp, C.POINTER(i64), vp, C.POINTER(f32c),
+                                             C.POINTER(f32c), C.POINTER(vp), C.POINTER(i64), vp, i64, vp, vp, C.c_int, vp, i64, vp, vp,
+                                             C.POINTER(vp), vp, i64, i64, f32c, vp]),
+    "hnr_img_sum_views": (C.c_int, [vp, i64, i64, i64, vp, i64, vp]),
     "hnr_chain_bwd_f16": (C.c_int, [C.c_int, C.POINTER(i64), C.POINTER(i64), i64, C.c_int, vp, i64, vp, i64, C.POINTER(vp), C.POINTER(vp), vp,
                                     C.POINTER(i64), vp, i64, i64, vp]),
     "hnr_train_loss": (C.c_int, [vp, vp, vp, i64, vp, i64, f32c, f32c, vp, vp, vp, vp]),

@@ -96,7 +96,9 @@ class PackedChain:
             W = lin.weight
             if l == 0 and cols0 is not None:
                 # cols0[k'] = reference input column presented at kernel column k' (-1 = padding column with zero weight)
-                assert sorted(c for c in cols0 if c >= 0) == list(range(W.shape[1])) and len(cols0) == k_in
+                # a permutation of the reference columns, or (partial chains: layer-0 addend) a subset of them
+                real = [c for c in cols0 if c >= 0]
+                assert len(set(real)) == len(real) and max(real) < W.shape[1] and len(cols0) == k_in
                 idx, mask = _cols_index(cols0, W.device)
                 W = W.detach().index_select(1, idx) * mask
             img, sw, Np = pack_chain_layer(W, Kp[l], weight_scale)
@@ -137,9 +139,11 @@ def packed_chain(owner, name: str, layers, acts, k_in: int, cols0=None, weight_s
 
 
 def chain_forward(pc: PackedChain, srcs: Sequence[torch.Tensor], M: Optional[int] = None, mods: Sequence[int] = (),
-                  out: bool = True, res: Optional[torch.Tensor] = None, head=None, keep_inner: bool = False, save_images: bool = False):
+                  out: bool = True, res: Optional[torch.Tensor] = None, head=None, keep_inner: bool = False, save_images: bool = False,
+                  add0=None):
     """run the chain over M rows.  srcs: 2-D fp32 tensors with unit inner stride (row stride free); concat widths must sum to
     the first layer's K.  head = (weight (1,N) , bias (1,), act) fuses a 1-output layer on the last output.
+    add0 = (A (rows, >= Np[0]) fp32 with 16-byte aligned rows, mod): A[m % mod] is added to layer 0's pre-activation.
     Returns (Y_last or None, head_out or None, [inner Y_l] if keep_inner)."""
     srcs = [ops._rows2d(s) for s in srcs]
     assert 1 <= len(srcs) <= 3
@@ -168,6 +172,24 @@ def chain_forward(pc: PackedChain, srcs: Sequence[torch.Tensor], M: Optional[int
     resv = ops._rows2d(res) if res is not None else None
     f4 = lambda v: (C.c_float * len(v))(*v)
     i4 = lambda v: (C.c_int * len(v))(*[int(x) for x in v])
+    if add0 is not None:
+        A0, amod = add0
+        assert A0.dtype == torch.float32 and A0.stride(1) == 1 and A0.shape[1] >= pc.Np[0] and not keep_inner
+        x0img = himg = None
+        if save_images:
+            from . import mlp_tc
+            x0img = mlp_tc.image_empty(M, pc.Kp[0], dev)
+            himg = [mlp_tc.image_empty(M, pc.Np[l], dev) for l in range(nl - 1)]
+        with ops._launch():
+            check(lib().hnr_chain_f16_forward_add0(ptr_array(padded), i64_array(lds), i64_array(ks), i64_array(modl), float(pc.in_scale), nl,
+                                                   i64_array(pc.Kp), i64_array(pc.N), i64_array(pc.Np), i4(pc.acts), ptr(pc.wpack),
+                                                   i64_array(pc.w_off), ptr(pc.bias), f4(pc.mul), f4(pc.inv_next), ptr_array(Ys),
+                                                   i64_array([y.stride(0) if y is not None else 0 for y in Ys]), ptr(resv),
+                                                   resv.stride(0) if resv is not None else 0, ptr(hw), ptr(hb), hact, ptr(head_out), M,
+                                                   ptr(ops.status_word(dev)), ptr(x0img),
+                                                   ptr_array(himg + [None] * (4 - len(himg))) if himg is not None else None, ptr(A0), A0.stride(0),
+                                                   int(amod), float(ACT_SCALE), stream()), "chain_f16_forward_add0")
+        return Ys[nl - 1], head_out, ((x0img, himg) if save_images else Ys[:-1])
     if save_images:
         # training forward: the concatenated input and the inner outputs go to HBM as split images (csrc/img_common.cuh)
         from . import mlp_tc
@@ -248,9 +270,10 @@ WG_LDO = 320
 
 
 def chain_backward_fused(pc: PackedChain, pb: PackedChainBwd, Ws, images, y_top: torch.Tensor, dY: torch.Tensor, M: int, acts, ks, mods,
-                         need_src, cols0, params=None):
+                         need_src, cols0, params=None, add0_mod: int = 0):
     """data gradients (one fused launch) + weight / bias gradients (one image-fed launch) of a chain.
-    Returns ([d_src_i | None], [dW_l], [db_l])."""
+    add0_mod > 0: also returns the gradient of the layer-0 addend (sum over the M / add0_mod views of dZ_0).
+    Returns ([d_src_i | None], [dW_l], [db_l][, d_add0])."""
     from . import mlp_tc
     x0img, himg = images
     nl = pc.nlayer
@@ -293,7 +316,7 @@ def chain_backward_fused(pc: PackedChain, pb: PackedChainBwd, Ws, images, y_top:
     pairs = []
     if params is not None:              # (weight, bias) parameters of the layers, in order: lets a training loop defer this launch
         for l in range(nl):
-            pairs += [(params[2 * l], aW[l]), (params[2 * l + 1], ab[l])]
+            pairs += [(params[2 * l], aW[l])] + ([(params[2 * l + 1], ab[l])] if params[2 * l + 1] is not None else [])
         ops._wgrad_launch(launch_wgrad, pairs)
     else:
         launch_wgrad()
@@ -306,6 +329,12 @@ def chain_backward_fused(pc: PackedChain, pb: PackedChainBwd, Ws, images, y_top:
                 g = g.reshape(-1, mods[i], k).sum(dim=0)
         d_srcs.append(g)
         off += k
+    if add0_mod > 0:
+        assert M % add0_mod == 0
+        d_add0 = torch.empty((add0_mod, pc.Np[0]), device=dev, dtype=torch.float32)
+        with ops._launch(name="img_sum_views"):
+            check(lib().hnr_img_sum_views(ptr(dz[0]), pc.Np[0], add0_mod, M // add0_mod, ptr(d_add0), pc.Np[0], stream()), "img_sum_views")
+        return d_srcs, dWs, dbs, d_add0
     return d_srcs, dWs, dbs
 
 
@@ -315,8 +344,8 @@ class ChainFn(torch.autograd.Function):
     sequence of ops.linear calls.  apply(pc, layers_params..., ) is wrapped by chain_train()."""
 
     @staticmethod
-    def forward(ctx, pc, acts, mods, M, has_res, head_act, nlayer, nsrc, cols0, pb, *tensors):
-        # tensors = [W_0, b_0, ..., W_{n-1}, b_{n-1}] + ([head_W, head_b] if head_act >= 0) + srcs + ([res] if has_res)
+    def forward(ctx, pc, acts, mods, M, has_res, head_act, nlayer, nsrc, cols0, pb, add0_mod, *tensors):
+        # tensors = [W_0, b_0, ..., W_{n-1}, b_{n-1}] + ([head_W, head_b] if head_act >= 0) + srcs + ([res] if has_res) + ([add0] if add0_mod)
         k = 2 * nlayer
         Ws, bs = list(tensors[0:k:2]), list(tensors[1:k:2])
         head = None
@@ -325,10 +354,13 @@ class ChainFn(torch.autograd.Function):
             k += 2
         srcs = list(tensors[k:k + nsrc])
         res = tensors[k + nsrc] if has_res else None
+        add0 = (tensors[k + nsrc + (1 if has_res else 0)], add0_mod) if add0_mod else None
         fused = FUSED_BWD and pb is not None
         ctx.fused = fused
+        ctx.add0_mod = add0_mod
+        assert add0 is None or fused, "the layer-0 addend needs the fused backward"
         if fused:
-            y, h, images = chain_forward(pc, srcs, M=M, mods=mods, out=True, res=res, head=head, save_images=True)
+            y, h, images = chain_forward(pc, srcs, M=M, mods=mods, out=True, res=res, head=head, save_images=True, add0=add0)
             ctx.cfg = (acts, mods, M, has_res, head_act, nlayer, nsrc, cols0)
             ctx.pc, ctx.pb, ctx.ks = pc, pb, [s_.shape[1] for s_ in srcs]
             ctx.wparams = list(tensors[0:2 * nlayer])
@@ -377,7 +409,7 @@ class ChainFn(torch.autograd.Function):
         d_srcs = [None] * nsrc
         for l in reversed(range(nlayer)):
             ins = srcs if l == 0 else [Ys[l - 1]]
-            need = [ctx.needs_input_grad[10 + 2 * nlayer + (2 if head_act >= 0 else 0) + i] for i in range(nsrc)] if l == 0 else [True]
+            need = [ctx.needs_input_grad[11 + 2 * nlayer + (2 if head_act >= 0 else 0) + i] for i in range(nsrc)] if l == 0 else [True]
             Wl = Ws[l]
             if l == 0 and cols0 is not None:         # the kernel's source order is a column permutation of the reference weight
                 idx = _cols_index(cols0, Wl.device)[0]
@@ -397,7 +429,7 @@ class ChainFn(torch.autograd.Function):
         grads += list(d_srcs)
         if has_res:
             grads.append(d_res)
-        return (None,) * 10 + tuple(grads)
+        return (None,) * 11 + tuple(grads)
 
     @staticmethod
     def _backward_fused(ctx, sv, dY, dH):
@@ -417,21 +449,26 @@ class ChainFn(torch.autograd.Function):
         else:
             dcur = dY
         d_res = dcur if has_res else None
-        need = [ctx.needs_input_grad[10 + 2 * nlayer + (2 if head_act >= 0 else 0) + i] for i in range(nsrc)]
+        need = [ctx.needs_input_grad[11 + 2 * nlayer + (2 if head_act >= 0 else 0) + i] for i in range(nsrc)]
         modl = list(mods) + [0] * (nsrc - len(mods))
-        d_srcs, gW, gb = chain_backward_fused(ctx.pc, ctx.pb, Ws, (x0img, himg), y, dcur, M, acts, ctx.ks, modl, need, cols0, params=ctx.wparams)
+        r = chain_backward_fused(ctx.pc, ctx.pb, Ws, (x0img, himg), y, dcur, M, acts, ctx.ks, modl, need, cols0, params=ctx.wparams,
+                                 add0_mod=ctx.add0_mod)
+        d_srcs, gW, gb = r[0], r[1], r[2]
         grads = []
         for l in range(nlayer):
-            grads += [gW[l], gb[l]]
+            grads += [gW[l], gb[l] if ctx.wparams[2 * l + 1] is not None else None]
         if head_act >= 0:
             grads += g_head
         grads += list(d_srcs)
         if has_res:
             grads.append(d_res)
-        return (None,) * 10 + tuple(grads)
+        if ctx.add0_mod:
+            grads.append(r[3])
+        return (None,) * 11 + tuple(grads)
 
 
-def chain_train(pc: PackedChain, layers, acts, srcs, M=None, mods=(), res=None, head=None, cols0=None, pb: Optional[PackedChainBwd] = None):
+def chain_train(pc: PackedChain, layers, acts, srcs, M=None, mods=(), res=None, head=None, cols0=None, pb: Optional[PackedChainBwd] = None,
+                add0=None):
     """autograd-aware fused chain.  layers: the nn.Linear modules (their parameters receive gradients); head = (nn.Linear, act) or
     None.  Returns (y_last, head_out | None).  NOTE: with a residual the last activation must be 'none' (as in the mix-up block):
     the saved output then includes the residual, which the identity derivative never reads."""
@@ -449,6 +486,10 @@ def chain_train(pc: PackedChain, layers, acts, srcs, M=None, mods=(), res=None, 
     tensors += srcs
     if res is not None:
         tensors.append(res)
+    add0_mod = 0
+    if add0 is not None:                     # (A (rows, Np[0]) fp32, mod): added to layer 0's pre-activation, receives a gradient
+        tensors.append(add0[0])
+        add0_mod = int(add0[1])
     y, h = ChainFn.apply(pc, tuple(acts), tuple(mods), M, res is not None, head_act, len(layers), len(srcs),
-                         tuple(cols0) if cols0 is not None else None, pb, *tensors)
+                         tuple(cols0) if cols0 is not None else None, pb, add0_mod, *tensors)
     return y, (h if head is not None else None)

@@ -405,3 +405,37 @@ extern "C" int hnr_chain_bwd_f16(int nlayer, const int64_t* Np, const int64_t* N
     HNR_CHECK_LAUNCH("chain_bwd_f16");
     return HNR_OK;
 }
+
+// out[n, :] = sum over v < V of the fp32 value (hi + lo) of row v*Nv + n of a split image with C columns: the gradient of a layer-0
+// addend shared by the V views of a sample (hnr_chain_f16_forward_add0), read from the dZ_0 image the data-gradient chain wrote.
+// thread = (column group of 8, sample n) with n fastest: 32 consecutive samples read 512 contiguous bytes of a slab plane.
+namespace {
+__global__ void __launch_bounds__(256) img_sum_views_kernel(const uint8_t* __restrict__ im, int C, int64_t Nv, int V, float* __restrict__ out, int ldo) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t n = idx % Nv;
+    const int g = (int)(idx / Nv);
+    if (g >= C / 8) return;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const int64_t pl = img::plane_bytes(C);
+    for (int v = 0; v < V; ++v) {
+        const uint8_t* p = im + img::piece_off((int64_t)v * Nv + n, g, C);
+        const uint4 hi = __ldg(reinterpret_cast<const uint4*>(p)), lo = __ldg(reinterpret_cast<const uint4*>(p + pl));
+        float t[8];
+        img::join8_bf16(hi, lo, t);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += t[i];
+    }
+    float4* o = reinterpret_cast<float4*>(out + n * ldo + 8 * g);
+    o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+}
+}  // namespace
+
+extern "C" int hnr_img_sum_views(const void* im, int64_t C, int64_t Nv, int64_t V, float* out, int64_t ldo, void* stream) {
+    HNR_CHECK_ARG(C % 8 == 0 && ldo % 4 == 0 && ldo >= C && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "img_sum_views: C % 8, aligned output rows");
+    if (Nv == 0 || V == 0) return HNR_OK;
+    const int64_t total = Nv * (C / 8);
+    img_sum_views_kernel<<<(unsigned)hnr_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint8_t*)im, (int)C, Nv, (int)V, out, (int)ldo);
+    HNR_CHECK_LAUNCH("img_sum_views");
+    return HNR_OK;
+}

@@ -88,6 +88,13 @@ struct ChainArgs {
     // inner layers' outputs (Np[l] columns), rows padded to the tile -- operands of chain_bwd_f16.cu / wgrad_img.cu.  NULL = off
     uint8_t* x0img;
     uint8_t* himg[MAXL];
+    // optional addend of layer 0's pre-activation: row (m % add0_mod) of an fp32 (rows, N[0]) matrix, times add0_scale.  Used by the
+    // blend-weight net: its first layer's input [g | aux_v | dview_v] shares g between the V views of a sample, so W0g.g is computed
+    // once per sample by another launch and added here; this chain then only reads the 48 view-dependent columns
+    const float* add0;
+    int ld_add0;
+    int64_t mod_add0;
+    float add0_scale;
     int variant;                 // bring-up / profiling switches (HNR_CHAIN_VARIANT): 1 = no L2 prefetch, 2 = L1-bypassing loads, 4 = no source loads at all
     long long* trace;            // optional event trace of CTA 0 (bring-up / profiling): [count, (clock, id, a, b) ...]
 };
@@ -138,11 +145,20 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity,
 // bf16 image of the output (training), fp16 hi/lo split into the next layer's A operand, release of the block to the MMA warp
 template <int W>
 __device__ __forceinline__ void epi_inner_block(uint32_t taddr, int c0, const float* __restrict__ bl, float mul, float inv_next, bool do_lrelu,
-                                                uint8_t* himg, int np, int64_t m, uint8_t* dst, int32_t* status, uint32_t bar_block, int lane) {
+                                                uint8_t* himg, int np, int64_t m, uint8_t* dst, int32_t* status, uint32_t bar_block, int lane,
+                                                const float* __restrict__ addrow, float add_scale) {
     float y[W];
     float4 bb[W / 4];
 #pragma unroll
     for (int i4 = 0; i4 < W / 4; ++i4) bb[i4] = __ldg(reinterpret_cast<const float4*>(bl + c0) + i4);     // in flight together with the TMEM load
+    if (addrow) {                                  // bias + scaled addend (rows beyond M pass NULL: their values are never used)
+#pragma unroll
+        for (int i4 = 0; i4 < W / 4; ++i4) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(addrow + c0) + i4);
+            bb[i4].x = fmaf(a.x, add_scale, bb[i4].x); bb[i4].y = fmaf(a.y, add_scale, bb[i4].y);
+            bb[i4].z = fmaf(a.z, add_scale, bb[i4].z); bb[i4].w = fmaf(a.w, add_scale, bb[i4].w);
+        }
+    }
     if constexpr (W == 32) tmem_ld32(taddr + c0, y); else tmem_ld16(taddr + c0, y);
 #pragma unroll
     for (int i4 = 0; i4 < W / 4; ++i4) {
@@ -489,13 +505,16 @@ __global__ void __launch_bounds__(NTHREADS, 2) chain_f16_kernel(const __grid_con
                 const int cbeg = half == 0 ? 0 : 32 * bsplit, cend = half == 0 ? min(np, 32 * bsplit) : np;
                 if (!last) {
                     // inner layer: whole 32-column blocks (16-column tail), nothing leaves the SM except the optional training image
+                    const float* addrow = (l == 0 && A.add0 && live) ? A.add0 + (A.mod_add0 > 0 ? m % A.mod_add0 : m) * A.ld_add0 : nullptr;
 #pragma unroll 1
                     for (int c0 = cbeg; c0 < cend; c0 += 32) {
                         uint8_t* dst = act_hi + (c0 >> 3) * A_LBO + r * 16;
                         if (c0 + 32 <= cend)
-                            epi_inner_block<32>(taddr, c0, bl, mul, inv_next, act == HNR_ACT_LRELU, A.himg[l], np, m, dst, A.status, bar_actfull + 8 * (c0 >> 5), lane);
+                            epi_inner_block<32>(taddr, c0, bl, mul, inv_next, act == HNR_ACT_LRELU, A.himg[l], np, m, dst, A.status, bar_actfull + 8 * (c0 >> 5), lane,
+                                                addrow, A.add0_scale);
                         else
-                            epi_inner_block<16>(taddr, c0, bl, mul, inv_next, act == HNR_ACT_LRELU, A.himg[l], np, m, dst, A.status, bar_actfull + 8 * (c0 >> 5), lane);
+                            epi_inner_block<16>(taddr, c0, bl, mul, inv_next, act == HNR_ACT_LRELU, A.himg[l], np, m, dst, A.status, bar_actfull + 8 * (c0 >> 5), lane,
+                                                addrow, A.add0_scale);
                     }
                     if (yout) {
                         // (inference never asks for inner outputs; the layer-by-layer training cross-check does) re-read the block from
@@ -507,6 +526,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) chain_f16_kernel(const __grid_con
 #pragma unroll
                             for (int i = 0; i < 16; ++i) {
                                 float t = fmaf(y[i], mul, __ldg(bl + c0 + i));
+                                if (addrow) t = fmaf(__ldg(addrow + c0 + i), A.add0_scale, t);
                                 if (act == HNR_ACT_LRELU) t = fmaxf(t, 0.01f * t);
                                 if (live && c0 + i < n) yout[m * ldy + c0 + i] = t * inv_next;
                             }
@@ -617,8 +637,11 @@ static int chain_f16_launch(const float* const* src, const int64_t* src_ld, cons
                             const void* wpack, const int64_t* w_off, const float* bias, const float* mul, const float* inv_next,
                             float* const* Y, const int64_t* ldy, const float* res, int64_t ldres, const float* head_w,
                             const float* head_b, int head_act, float* head_out, int64_t M, int32_t* status, void* x0img,
-                            void* const* himg, void* stream) {
+                            void* const* himg, void* stream, const float* add0 = nullptr, int64_t add0_ld = 0, int64_t add0_mod = 0,
+                            float add0_scale = 0.f) {
     HNR_CHECK_ARG(nlayer >= 1 && nlayer <= MAXL, "chain_f16_forward: 1..4 layers");
+    HNR_CHECK_ARG(!add0 || (nlayer >= 2 && add0_ld % 4 == 0 && add0_ld >= Np[0] && (reinterpret_cast<uintptr_t>(add0) & 15) == 0),
+                  "chain_f16_forward: the layer-0 addend needs >= 2 layers and 16-byte aligned rows of at least Np[0] floats");
     if (M == 0) return HNR_OK;
     ChainArgs A{};
     int64_t ksum = 0;
@@ -639,6 +662,7 @@ static int chain_f16_launch(const float* const* src, const int64_t* src_ld, cons
     HNR_CHECK_ARG(!head_w || (head_b && head_out), "chain_f16_forward: head needs head_b and head_out");
     A.in_scale = in_scale; A.nlayer = nlayer; A.wpack = (const uint8_t*)wpack; A.bias = bias; A.res = res; A.ldres = (int)ldres;
     A.head_w = head_w; A.head_b = head_b; A.head_act = head_act; A.head_out = head_out; A.M = M;
+    A.add0 = add0; A.ld_add0 = (int)add0_ld; A.mod_add0 = add0_mod; A.add0_scale = add0_scale;
     A.trace = g_trace;
     { const char* e = getenv("HNR_CHAIN_VARIANT"); A.variant = e ? atoi(e) : 0; }
     A.status = status;
@@ -676,4 +700,19 @@ extern "C" int hnr_chain_f16_forward_train(const float* const* src, const int64_
     HNR_CHECK_ARG(x0img && himg, "chain_f16_forward_train: images required");
     return chain_f16_launch(src, src_ld, src_k, src_mod, in_scale, nlayer, Kp, N, Np, act, wpack, w_off, bias, mul, inv_next, Y, ldy, res, ldres,
                             head_w, head_b, head_act, head_out, M, status, x0img, himg, stream);
+}
+
+// The same with an addend of layer 0's pre-activation (see ChainArgs::add0): y_0 = act(x_0 W_0^T + b_0 + add0[m % add0_mod, :]).
+// add0 rows must hold Np[0] floats (zero padded), 16-byte aligned; add0_scale = the chain's activation scale (chain.py ACT_SCALE).
+// x0img / himg may be NULL (inference) or the training images of hnr_chain_f16_forward_train.
+extern "C" int hnr_chain_f16_forward_add0(const float* const* src, const int64_t* src_ld, const int64_t* src_k, const int64_t* src_mod,
+                                          float in_scale, int nlayer, const int64_t* Kp, const int64_t* N, const int64_t* Np, const int* act,
+                                          const void* wpack, const int64_t* w_off, const float* bias, const float* mul, const float* inv_next,
+                                          float* const* Y, const int64_t* ldy, const float* res, int64_t ldres, const float* head_w,
+                                          const float* head_b, int head_act, float* head_out, int64_t M, int32_t* status, void* x0img,
+                                          void* const* himg, const float* add0, int64_t add0_ld, int64_t add0_mod, float add0_scale,
+                                          void* stream) {
+    HNR_CHECK_ARG(add0 != nullptr, "chain_f16_forward_add0: addend required");
+    return chain_f16_launch(src, src_ld, src_k, src_mod, in_scale, nlayer, Kp, N, Np, act, wpack, w_off, bias, mul, inv_next, Y, ldy, res, ldres,
+                            head_w, head_b, head_act, head_out, M, status, x0img, x0img ? himg : nullptr, stream, add0, add0_ld, add0_mod, add0_scale);
 }

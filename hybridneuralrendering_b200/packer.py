@@ -29,6 +29,17 @@ class BiasJob(C.Structure):
 
 
 AM_COLS0 = list(range(45, 173)) + list(range(45)) + [173, 174, 175]     # blend-weight net, kernel source order [g | aux | dview]
+# the blend-weight net's first layer split in two (chain.py add0): the 128 columns that multiply g (shared by the V views of a sample)
+# run as a one-layer chain per SAMPLE, the 48 view-dependent columns [aux 45 | dview 3] per (view, sample)
+AMG_COLS = list(range(45, 173))
+AM_COLS48 = list(range(45)) + [173, 174, 175]
+
+
+class _NoBias:
+    """a layer that shares another layer's weight tensor and has no bias (the g part of the blend-weight net's first layer)"""
+
+    def __init__(self, lin):
+        self.weight, self.bias = lin.weight, None
 
 
 class TrainPacker:
@@ -48,7 +59,11 @@ class TrainPacker:
         self.pc: Dict[str, chain.PackedChain] = {}
         self.pb: Dict[str, Optional[chain.PackedChainBwd]] = {}
         specs = [("cf", [cf[0], cf[2], cf[4]], [ACT_LRELU] * 3, ops.X5_W, None, 256)]
-        if int(agg.opt.use_nearest) > 0:
+        if int(agg.opt.use_nearest) > 0 and with_bwd:
+            specs.append(("amg", [_NoBias(am[0])], [ACT_NONE], 128, AMG_COLS, 128))
+            specs.append(("am", [am[0], am[2], am[4]], [ACT_LRELU] * 3, 48, AM_COLS48, 48))
+        elif int(agg.opt.use_nearest) > 0:
+            # layer-by-layer backward (the tests' cross-check of the fused path): the unsplit 176-wide first layer, sources [g | aux | dview]
             specs.append(("am", [am[0], am[2], am[4]], [ACT_LRELU] * 3, 176, AM_COLS0, 176))
         specs.append(("cm", [cm[0], cm[2], cm[4]], [ACT_LRELU, ACT_LRELU, ACT_NONE], 90, None, 96))
         for name, layers, acts, k_in, cols0, nx in specs:
@@ -103,7 +118,8 @@ class TrainPacker:
             for l, lin in enumerate(layers):
                 n = add(lin.weight, pc.wpack, pc.w_off[l], pc.Np[l], pc.Kp[l], 0, 0, TS, cols0 if l == 0 else None)
                 assert pc.w_off[l] + n == (pc.w_off[l + 1] if l + 1 < nl else pc.wpack.numel())
-                add_bias(lin.bias, pc.bias[l], chain.ACT_SCALE if l < nl - 1 else 1.0)
+                if lin.bias is not None:
+                    add_bias(lin.bias, pc.bias[l], chain.ACT_SCALE if l < nl - 1 else 1.0)
             if pb is not None:
                 for l, lin in enumerate(layers):
                     rows = nx if l == 0 else pc.Np[l - 1]

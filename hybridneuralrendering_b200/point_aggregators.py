@@ -312,11 +312,14 @@ class PointAggregator(nn.Module):
                 aux48, ok = ops.image_gather_padded(levels, xy, vlist, delta)
             am = self.aux_merge_weight_block
             with ops.tag("sample_mlp"):
-                # kernel source order [g | aux | dview]
-                pc = chain.packed_chain(self, "am", [am[0], am[2], am[4]], [ACT_LRELU] * 3, 176,
-                                        cols0=list(range(45, 173)) + list(range(45)) + [173, 174, 175])
-                sig = chain.chain_forward(pc, [g, aux48.view(V * Nv, ops.AUX_LD)], M=V * Nv, mods=(Nv, 0), out=False,
-                                          head=(am[6].weight, am[6].bias, ACT_SIGMOID))[1]
+                # first layer split (packer.AMG_COLS / AM_COLS48): W0g.g once per sample (one-layer chain), the chain over the V views
+                # reads only the 48 view-dependent columns [aux | dview] and adds row (m mod Nv) of that product
+                from .packer import AM_COLS48, AMG_COLS, _NoBias
+                pcg = chain.packed_chain(self, "amg", [_NoBias(am[0])], [ACT_NONE], 128, cols0=AMG_COLS)
+                G = chain.chain_forward(pcg, [g])[0]
+                pc = chain.packed_chain(self, "am", [am[0], am[2], am[4]], [ACT_LRELU] * 3, 48, cols0=AM_COLS48)
+                sig = chain.chain_forward(pc, [aux48.view(V * Nv, ops.AUX_LD)], M=V * Nv, out=False,
+                                          head=(am[6].weight, am[6].bias, ACT_SIGMOID), add0=(G, Nv))[1]
             with ops.tag("blend"):
                 merged = ops.blend_padded(aux48, sig, ok, self._keep_mask(R, SR, vlist))
         elif V > 0 and fused_t:
@@ -326,9 +329,16 @@ class PointAggregator(nn.Module):
                 aux, ok = ops.ImageGatherFn.apply(levels[0], levels[1], levels[2], levels[3], xy, vlist, delta)
             am = self.aux_merge_weight_block
             with ops.tag("sample_mlp"):
-                c0 = self._AM_COLS0                                                      # kernel source order [g | aux | dview]
-                sig = chain.chain_train(tp.pc["am"], [am[0], am[2], am[4]], [ACT_LRELU] * 3, [g, aux.view(V * Nv, ops.AUX_LD)], M=V * Nv,
-                                        mods=(Nv, 0), head=(am[6], ACT_SIGMOID), cols0=c0, pb=tp.pb["am"])[1]
+                # first layer split as in inference: W0g.g once per sample (its gradient = the sum of dZ_0 over the V views), the chain
+                # over the views reads / differentiates only the 48 view-dependent columns
+                from .packer import AM_COLS48, AMG_COLS, _NoBias
+                if "amg" in tp.pc:
+                    G = chain.chain_train(tp.pc["amg"], [_NoBias(am[0])], [ACT_NONE], [g], cols0=AMG_COLS, pb=tp.pb["amg"])[0]
+                    sig = chain.chain_train(tp.pc["am"], [am[0], am[2], am[4]], [ACT_LRELU] * 3, [aux.view(V * Nv, ops.AUX_LD)], M=V * Nv,
+                                            head=(am[6], ACT_SIGMOID), cols0=AM_COLS48, pb=tp.pb["am"], add0=(G, Nv))[1]
+                else:       # layer-by-layer backward (cross-check): unsplit first layer, kernel source order [g | aux | dview]
+                    sig = chain.chain_train(tp.pc["am"], [am[0], am[2], am[4]], [ACT_LRELU] * 3, [g, aux.view(V * Nv, ops.AUX_LD)], M=V * Nv,
+                                            mods=(Nv, 0), head=(am[6], ACT_SIGMOID), cols0=self._AM_COLS0, pb=None)[1]
             with ops.tag("blend"):
                 merged = ops.BlendFn.apply(aux, sig, ok, self._keep_mask(R, SR, vlist))
         elif V > 0:

@@ -223,6 +223,17 @@ int hnr_chain_f16_forward_train(const float* const* src, const int64_t* src_ld, 
                                 float* const* Y, const int64_t* ldy, const float* res, int64_t ldres, const float* head_w,
                                 const float* head_b, int head_act, float* head_out, int64_t M, int32_t* status, void* x0img,
                                 void* const* himg, void* stream);
+/* hnr_chain_f16_forward(_train) with an addend of layer 0's pre-activation: y_0 = act(x_0 W_0^T + b_0 + add0[m % add0_mod, :]).  Used for
+ * aux_merge_weight_block (:1199-1217): its first layer's input [g | aux_v | dview_v] shares g between the V views of a sample, so
+ * W_0g g is computed once per sample (a one-layer chain) and this chain reads only the 48 view-dependent columns.  x0img / himg NULL =
+ * inference.  hnr_img_sum_views: the addend's gradient, sum over the V views of the dZ_0 image rows (out (Nv, ldo) fp32). */
+int hnr_chain_f16_forward_add0(const float* const* src, const int64_t* src_ld, const int64_t* src_k, const int64_t* src_mod, float in_scale,
+                               int nlayer, const int64_t* Kp, const int64_t* N, const int64_t* Np, const int* act, const void* wpack,
+                               const int64_t* w_off, const float* bias, const float* mul, const float* inv_next, float* const* Y,
+                               const int64_t* ldy, const float* res, int64_t ldres, const float* head_w, const float* head_b, int head_act,
+                               float* head_out, int64_t M, int32_t* status, void* x0img, void* const* himg, const float* add0,
+                               int64_t add0_ld, int64_t add0_mod, float add0_scale, void* stream);
+int hnr_img_sum_views(const void* img, int64_t C, int64_t Nv, int64_t V, float* out, int64_t ldo, void* stream);
 int hnr_chain_bwd_f16(int nlayer, const int64_t* Np, const int64_t* N, int64_t NX, int act_top, const float* dY, int64_t lddy,
                       const float* Ytop, int64_t ldyt, const void* const* gimg, void* const* dzimg, const void* wpackT,
                       const int64_t* w_off, float* dX, int64_t ldx, int64_t M, void* stream);

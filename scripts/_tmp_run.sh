@@ -1,5 +1,5 @@
 cd /root/repo
-timeout 300 python -m pytest tests/test_gpu_fused_bwd.py tests/test_gpu_e2e.py -x -q --timeout 120 2>&1 | tail -2
-timeout 300 python scripts/train_step_bench.py --steps 10 > gpurun_out/r2_train_m.json 2> gpurun_out/r2_train_m.err; echo "train rc=$?"
-python -c "
-import json; d=json.loads(open('gpurun_out/r2_train_m.json').read().strip().splitlines()[-1]); print(d['ms_per_step'], d['ms_fwd_bwd'], d['host_issue_ms_per_step'], d['e2e']['ms_per_step'], d['launches_per_step']); print(d['stage_ms']['backward/alpha_ksum_bwd'])"
+timeout 600 python -m pytest tests -m gpu -x -q --timeout 120 2>&1 | tail -2
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 900 python bench.py --no-large --no-extras --no-cpu-baseline > gpurun_out/r2_bench_split.json 2> gpurun_out/r2_bench_split.err; echo "bench rc=$?"
+timeout 100 python scripts/bench_chain.py 2>&1 | grep chain

@@ -337,3 +337,58 @@ def test_train_step_with_deferred_weight_gradients_equals_plain_backward():
         a, b = ga[k].double(), gb[k].double()
         # same kernels, same inputs; only the atomics' arrival order differs between two runs
         assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max()) + 1e-30, k
+
+
+def test_split_first_layer_of_the_blend_weight_net_matches_fp64():
+    """aux_merge_weight_block with its first layer split (chain.py add0): W0g.g once per sample through a one-layer no-bias chain, the
+    chain over the V views on the 48 view-dependent columns plus the addend -- outputs and ALL gradients (g, aux, the shared first-layer
+    weight, biases, head) vs fp64 autograd over the unsplit 176 -> 64 -> 64 -> 64 -> 1 net"""
+    from hybridneuralrendering_b200 import chain
+    from hybridneuralrendering_b200.packer import AM_COLS48, AMG_COLS, _NoBias
+    T = torch.from_numpy
+    rng = np.random.default_rng(5)
+    V, Nv = 4, 777
+    M = V * Nv
+    g = T(rng.standard_normal((Nv, 128)).astype(np.float32)).cuda().requires_grad_(True)
+    aux = T(rng.standard_normal((M, 48)).astype(np.float32)).cuda().requires_grad_(True)        # [aux 45 | dview 3]
+    lins, kin = [], 176
+    for w in (64, 64, 64):
+        lin = torch.nn.Linear(kin, w).cuda()
+        with torch.no_grad():
+            lin.weight.copy_(T((rng.standard_normal((w, kin)) * (1.5 / np.sqrt(kin))).astype(np.float32)))
+            lin.bias.copy_(T((rng.standard_normal(w) * 0.1).astype(np.float32)))
+        lins.append(lin)
+        kin = w
+    head = torch.nn.Linear(64, 1).cuda()
+    # fp64 reference: reference column order of the first layer is [aux 45 | g 128 | dview 3]
+    gd, ad = g.detach().double().requires_grad_(True), aux.detach().double().requires_grad_(True)
+    P64 = [(l.weight.detach().double().requires_grad_(True), l.bias.detach().double().requires_grad_(True)) for l in lins + [head]]
+    x = torch.cat([ad[:, :45], gd.repeat(V, 1), ad[:, 45:]], 1)
+    for W, b in P64[:3]:
+        x = torch.nn.functional.leaky_relu(x @ W.t() + b, 0.01)
+    href = torch.sigmoid(x @ P64[3][0].t() + P64[3][1])
+    dH = T(rng.standard_normal((M, 1)).astype(np.float32)).cuda()
+    href.backward(dH.double())
+    # product
+    pcg = chain.PackedChain([_NoBias(lins[0])], [0], 128, cols0=AMG_COLS, weight_scale=chain.TRAIN_WEIGHT_SCALE)
+    pbg = chain.PackedChainBwd([_NoBias(lins[0])], pcg, 128, cols0=AMG_COLS)
+    pc = chain.PackedChain(lins, [1, 1, 1], 48, cols0=AM_COLS48, weight_scale=chain.TRAIN_WEIGHT_SCALE)
+    pb = chain.PackedChainBwd(lins, pc, 48, cols0=AM_COLS48)
+    G = chain.chain_train(pcg, [_NoBias(lins[0])], [0], [g], cols0=AMG_COLS, pb=pbg)[0]
+    h = chain.chain_train(pc, lins, [1, 1, 1], [aux], M=M, head=(head, 2), cols0=AM_COLS48, pb=pb, add0=(G, Nv))[1]
+    assert float((h.double() - href).abs().max()) < 2e-5
+    h.backward(dH)
+    torch.cuda.synchronize()
+    assert int(ops.status_word(torch.device("cuda"))[0]) == 0
+    def close(a, b, name):
+        assert float((a.double() - b).abs().max()) <= TOL * float(b.abs().max()) + 1e-30, (name, float((a.double() - b).abs().max()), float(b.abs().max()))
+    close(g.grad, gd.grad, "g")
+    close(aux.grad, ad.grad, "aux | dview")
+    for i, (lin, (W, b)) in enumerate(zip(lins + [head], P64)):
+        close(lin.weight.grad, W.grad, f"W{i}")
+        close(lin.bias.grad, b.grad, f"b{i}")
+    # inference path: same numbers without the tape
+    with torch.no_grad():
+        G2 = chain.chain_forward(pcg, [g.detach()])[0]
+        h2 = chain.chain_forward(pc, [aux.detach()], M=M, out=False, head=(head.weight, head.bias, 2), add0=(G2, Nv))[1]
+    assert torch.equal(h2, h.detach())
