@@ -1,8 +1,8 @@
 cd /root/repo
-timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus 8 --steps 10 --warmup 3 > gpurun_out/r2_bench_n8e.json 2> gpurun_out/r2_bench_n8e.err; echo "rc=$?"
+timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29542 bench.py --gpus 8 --steps 10 --warmup 3 > gpurun_out/r2_bench_n8f.json 2> gpurun_out/r2_bench_n8f.err; echo "rc=$?"
 python - <<'PY'
 import json
-for line in open('gpurun_out/r2_bench_n8e.json'):
+for line in open('gpurun_out/r2_bench_n8f.json'):
     if line.startswith('{'):
         d=json.loads(line)
         print(d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], d['e2e']['ms_per_step'])
