@@ -355,6 +355,9 @@ class ChainFn(torch.autograd.Function):
         srcs = list(tensors[k:k + nsrc])
         res = tensors[k + nsrc] if has_res else None
         add0 = (tensors[k + nsrc + (1 if has_res else 0)], add0_mod) if add0_mod else None
+        # gradients of outputs nobody differentiates (the last layer's output when only the head is used) arrive as None instead of a
+        # materialised zero tensor (a 154 MB fill per step for the blend-weight net)
+        ctx.set_materialize_grads(False)
         fused = FUSED_BWD and pb is not None
         ctx.fused = fused
         ctx.add0_mod = add0_mod
@@ -382,6 +385,10 @@ class ChainFn(torch.autograd.Function):
     def backward(ctx, dY, dH):
         acts, mods, M, has_res, head_act, nlayer, nsrc, cols0 = ctx.cfg
         sv = list(ctx.saved_tensors)
+        if head_act < 0 and dY is None:                      # the chain's output was not used at all
+            dY = torch.zeros((M, ctx.pc.N[-1] if hasattr(ctx, "pc") else sv[nlayer - 1].shape[0]), device=sv[0].device, dtype=torch.float32)
+        if head_act >= 0 and dH is None:
+            dH = torch.zeros((M, 1), device=sv[0].device, dtype=torch.float32)
         if ctx.fused:
             return ChainFn._backward_fused(ctx, sv, dY, dH)
         Ws = sv[:nlayer]; p = nlayer

@@ -890,8 +890,8 @@ class BlendFn(torch.autograd.Function):
 
 class ScatterRowsFn(torch.autograd.Function):
     """out (S,C) = zeros; out[idx] = src (Nv,C): the decoded [sigma | rgb] rows of the valid samples scattered back to all sample
-    slots.  Same result as zeros.index_copy(0, idx, src); its backward reads grad[idx] with the element-wise index kernel instead of
-    index_select's one-block-per-row gather (42 us for 75 k rows of 4 floats)."""
+    slots.  Same result as zeros.index_copy(0, idx, src); its backward is an element-wise torch.gather instead of index_select's (and
+    grad[idx]'s) one-block-per-row gather kernel (42 us for 75 k rows of 4 floats)."""
 
     @staticmethod
     def forward(ctx, src, idx, S: int):
@@ -903,7 +903,7 @@ class ScatterRowsFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         (idx,) = ctx.saved_tensors
-        return g[idx], None, None
+        return torch.gather(g, 0, idx.unsqueeze(1).expand(-1, g.shape[1])), None, None
 
 
 # --------------------------------------------------------------------------------------------
