@@ -81,6 +81,7 @@ _SIGS = {
                                         C.POINTER(i64), C.POINTER(i64), C.POINTER(C.c_int), vp, C.POINTER(i64), vp, C.POINTER(f32c),
                                         C.POINTER(f32c), C.POINTER(vp), C.POINTER(i64), vp, i64, vp, vp, C.c_int, vp, i64, vp, vp]),
     "hnr_nbr_mlp_f16_forward": (C.c_int, [vp] * 17 + [C.POINTER(C.c_float), f32c, f32c, f32c, i64, i64, vp, vp, vp, vp, vp, vp]),
+    "hnr_nbr_mlp_f16_forward_pp": (C.c_int, [vp] * 17 + [C.POINTER(C.c_float), f32c, f32c, f32c, i64, i64, vp, vp, vp, vp]),
     "hnr_nbr_mlp_f16_forward_train": (C.c_int, [vp] * 17 + [C.POINTER(C.c_float), f32c, f32c, f32c, i64, i64] + [vp] * 11),
     "hnr_alpha_ksum_bwd_img": (C.c_int, [vp] * 8 + [i64, i64, vp, vp, vp, vp, vp, vp]),
     "hnr_nbr_bwd_f16_packed_bytes": (i64, []),

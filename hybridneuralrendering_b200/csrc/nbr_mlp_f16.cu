@@ -57,7 +57,8 @@ constexpr int OFF_BIAS = OFF_ACT + 2 * ACT_PART;           // 221184  (4,256) fp
 constexpr int OFF_WALPHA = OFF_BIAS + NLAYER * HID * 4;    // 225280
 constexpr int OFF_WC = OFF_WALPHA + HID * 4;               // 226304  neighbour weight * conf, double buffered
 constexpr int OFF_ARAW = OFF_WC + 2 * TM * 4;              // 227328  density-head partial dot products of the two epilogue groups
-constexpr int OFF_BAR = OFF_ARAW + 2 * TM * 4;             // 228352
+constexpr int OFF_GIDX = OFF_ARAW + 2 * TM * 4;            // 228352  point index of every row (per-point layer-0 partial), double buffered
+constexpr int OFF_BAR = OFF_GIDX + 2 * TM * 4;             // 229376
 constexpr int NBAR = 2 * NSW + 2 * NSA + 2 + 8 + 2 + 1 + 1;
 constexpr int SMEM_BYTES = OFF_BAR + NBAR * 8 + 16;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
@@ -79,6 +80,13 @@ struct F16Args {
     float inv_scale0, inv_scale2;
     float inv_act;                      // 1 / input scale of layers 1..3 (the saved activations are unscaled)
     int32_t* status;                    // optional: bit 0 is set when a scaled activation left fp16's range and was saturated
+    // per-point layer-0 partial (inference): 224 of layer 0's 284 inputs -- the embedding and its positional encoding -- depend on the
+    // POINT only, and a point is the neighbour of ~28 samples of a frame.  pp (N_points, 256) fp32 = W1[:, :224] . [emb | PE(emb)] is
+    // computed once per (weights, point set); the kernel then generates only the 4 distance-encoding chunks of layer 0 (nc0 = 4, wpack
+    // starting at chunk 14) and the layer-0 epilogue adds pp[point] * pp_scale to the pre-activation.  NULL = off (nc0 = 18).
+    const float* pp;
+    float pp_scale;
+    int nc0;
     int64_t Nv;
     float mul[NLAYER];             // accumulator -> (scaled) pre-activation factor per layer
     float scale0, scale2;          // input scales of layer 0 (generated features) and layer 2 (extras chunk)
@@ -240,8 +248,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) nbr_mlp_f16_kernel(F16Args A) {
         if (warp == 13 && lane == 0) {
             // ================= bulk-copy producer: one 16 KB weight chunk image per stage =================
             uint32_t it = 0;
+            const int nchunk = A.nc0 + NC1 + NC2 + NC3;
             for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                for (int c = 0; c < NCHUNK_TILE; ++c, ++it) {
+                for (int c = 0; c < nchunk; ++c, ++it) {
                     const uint32_t s = it % NSW, ph = (it / NSW) & 1;
                     mbar_wait_relaxed(bar_wempty + 8 * s, ph ^ 1, 64);
                     mbar_arrive_expect_tx(bar_wfull + 8 * s, W_STAGE);
@@ -277,7 +286,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nbr_mlp_f16_kernel(F16Args A) {
                 const uint32_t acc0 = tmem_base, acc1 = tmem_base + HID;
                 // ---- layer 0: operands from the generator ring (accumulator 0 was last read by epilogue 2 of the previous tile)
                 if (ti > 0) mbar_wait(bar_accempty0, (ti - 1) & 1);
-                for (int c = 0; c < NC0; ++c, ++ait) {
+                for (int c = 0; c < A.nc0; ++c, ++ait) {
                     const uint32_t s = ait % NSA, ph = (ait / NSA) & 1;
                     mbar_wait_relaxed(bar_afull + 8 * s, ph, 20);
                     const uint32_t a = a_base + s * A_STAGE;
@@ -339,10 +348,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) nbr_mlp_f16_kernel(F16Args A) {
             const int64_t s = s_cur, g = g_cur;
             const bool live = live_cur;
             // ---- issue every load of this row, then the index loads of the next tile ----
+            const bool use_pp = MODE == 0 && A.pp != nullptr;
             float4 e4[8];
             const float4* ep = reinterpret_cast<const float4*>(A.emb + g * FEAT);
+            if (!use_pp) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) e4[i] = __ldg(ep + i);
+                for (int i = 0; i < 8; ++i) e4[i] = __ldg(ep + i);
+            } else {
+                // the epilogue of layer 0 reads this point's 1 KB row of the partial one tile later: request it into L2 now
+                const char* prow = reinterpret_cast<const char*>(A.pp + g * HID);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(prow + 128 * i));
+            }
             const float px = A.xyz[g * 3], py = A.xyz[g * 3 + 1], pz = A.xyz[g * 3 + 2];
             const float dx = A.dir[g * 3], dy = A.dir[g * 3 + 1], dz = A.dir[g * 3 + 2];
             const float c0 = A.color[g * 3], c1 = A.color[g * 3 + 1], c2 = A.color[g * 3 + 2];
@@ -395,6 +412,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nbr_mlp_f16_kernel(F16Args A) {
                 store_chunk16(smem + OFF_E + p * A_STAGE, r, ev);
                 if (MODE == 2) store_chunk16_img(A.eimg, 16, row, 0, ev, A.inv_scale2);
                 wc_s[p * TM + r] = wgt;
+                reinterpret_cast<int32_t*>(smem + OFF_GIDX)[p * TM + r] = (int32_t)g;
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_efull + 8 * p);
@@ -419,8 +437,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) nbr_mlp_f16_kernel(F16Args A) {
 #pragma unroll
             for (int i = 0; i < 60; ++i) pe[i] *= sc0;
             pe[60] = pe[61] = pe[62] = pe[63] = 0.f;
+            if (!use_pp) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) sincos_fast(ef[i], &sn[i], &cs[i]);
+                for (int i = 0; i < 32; ++i) sincos_fast(ef[i], &sn[i], &cs[i]);
+            }
             int chunk_no = 0;
             auto put = [&](const float* v) {
                 if (MODE == 2) store_chunk16_img(A.x0img, NC0 * KC, row, chunk_no, v, A.inv_scale0);
@@ -433,6 +453,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nbr_mlp_f16_kernel(F16Args A) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_afull + 8 * st);
             };
+            if (!use_pp) {
             {   // raw embedding: 2 chunks
                 float v[16];
 #pragma unroll
@@ -460,6 +481,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nbr_mlp_f16_kernel(F16Args A) {
                     put(v);
                 }
             }
+            }
 #pragma unroll
             for (int c = 0; c < 4; ++c) put(pe + c * 16);
         }
@@ -485,18 +507,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) nbr_mlp_f16_kernel(F16Args A) {
                 uint32_t va[32], vb[32];
                 tmem_ld32_issue(taddr, va);
                 float amax = 0.f;                                      // largest scaled pre-activation magnitude of this thread's blocks
+                // per-point layer-0 partial: this row's point (written by the generators with the extras chunk of this tile)
+                const float* pprow = nullptr;
+                if (MODE == 0 && l == 0 && A.pp) {
+                    const uint32_t p = ti & 1;
+                    mbar_wait_relaxed(bar_efull + 8 * p, (ti >> 1) & 1, 20);
+                    pprow = A.pp + (int64_t)reinterpret_cast<const int32_t*>(smem + OFF_GIDX)[p * TM + r] * HID + wg * 32;
+                }
+                const float pps = A.pp_scale;
                 if (l < NLAYER - 1) {
 #pragma unroll
                     for (int jj = 0; jj < 4; ++jj) {
                         const int j = 2 * jj + wg;                     // column block
                         uint32_t(&cur)[32] = (jj & 1) ? vb : va;
                         uint32_t(&nxt)[32] = (jj & 1) ? va : vb;
+                        float4 pq[8];
+                        if (MODE == 0 && pprow) {                      // in flight while the TMEM load completes
+#pragma unroll
+                            for (int i4 = 0; i4 < 8; ++i4) pq[i4] = __ldg(reinterpret_cast<const float4*>(pprow + jj * 64) + i4);
+                        }
                         tmem_ld_wait(cur);
                         if (jj + 1 < 4) tmem_ld32_issue(taddr + (jj + 1) * 64, nxt);
                         float y[32];
 #pragma unroll
                         for (int i4 = 0; i4 < 8; ++i4) {
-                            const float4 bb = bl4[jj * 16 + i4];
+                            float4 bb = bl4[jj * 16 + i4];
+                            if (MODE == 0 && pprow) {
+                                bb.x = fmaf(pq[i4].x, pps, bb.x); bb.y = fmaf(pq[i4].y, pps, bb.y);
+                                bb.z = fmaf(pq[i4].z, pps, bb.z); bb.w = fmaf(pq[i4].w, pps, bb.w);
+                            }
                             const float t0 = fmaf(__uint_as_float(cur[4 * i4 + 0]), mul, bb.x), t1 = fmaf(__uint_as_float(cur[4 * i4 + 1]), mul, bb.y);
                             const float t2 = fmaf(__uint_as_float(cur[4 * i4 + 2]), mul, bb.z), t3 = fmaf(__uint_as_float(cur[4 * i4 + 3]), mul, bb.w);
                             y[4 * i4 + 0] = fmaxf(t0, 0.01f * t0); y[4 * i4 + 1] = fmaxf(t1, 0.01f * t1);
@@ -671,7 +710,33 @@ extern "C" int hnr_nbr_mlp_f16_forward(const float* xyz, const float* xyz_pers, 
     A.Nv = Nv;
     for (int l = 0; l < NLAYER; ++l) A.mul[l] = mul[l];
     A.scale0 = scale0; A.scale2 = scale2; A.inv_act = inv_act; A.araw = araw; A.status = status;
+    A.nc0 = NC0;
     return nbr_mlp_f16_launch(A, dbg ? 1 : 0, stream);
+}
+
+// Inference with the per-point layer-0 partial (see F16Args::pp): pp (N_points, 256) fp32 = block1[0].weight[:, :224] . [emb | PE(emb)]
+// of every point (unscaled), e.g. from hnr_linear_tc_fwd over the point table; wpack = the SAME image as for hnr_nbr_mlp_f16_forward
+// (the kernel starts at the distance-encoding chunks of layer 0).  The embedding table is not read.
+extern "C" int hnr_nbr_mlp_f16_forward_pp(const float* xyz, const float* xyz_pers, const float* pp, const float* color, const float* dir,
+                                          const int32_t* pidx, const int32_t* vlist, const float* loc_w, const float* loc_pers,
+                                          const float* raydirs, const float* cam, const float* weight, const float* confc, const void* wpack,
+                                          const float* bias, const float* walpha, const float* balpha, const float* mul, float scale0,
+                                          float scale2, float inv_act, int64_t Nv, int64_t K, float* sigma, float* X5, int32_t* status,
+                                          void* stream) {
+    HNR_CHECK_ARG(K == 8, "nbr_mlp_f16_forward_pp: K must be 8 (128-row tiles hold 16 whole samples)");
+    HNR_CHECK_ARG(pp != nullptr && (reinterpret_cast<uintptr_t>(pp) & 15) == 0, "nbr_mlp_f16_forward_pp: 16-byte aligned per-point partial required");
+    if (Nv == 0) return HNR_OK;
+    F16Args A{};
+    A.xyz = xyz; A.xyz_pers = xyz_pers; A.emb = nullptr; A.color = color; A.dir = dir; A.pidx = pidx; A.vlist = vlist;
+    A.loc_w = loc_w; A.loc_pers = loc_pers; A.raydirs = raydirs; A.cam = cam; A.weight = weight; A.confc = confc;
+    constexpr int NC0_PP = 4;                                  // the distance-encoding chunks are the last 4 of layer 0's 18
+    A.wpack = (const uint8_t*)wpack + (size_t)(NC0 - NC0_PP) * W_STAGE; A.bias = bias; A.walpha = walpha; A.balpha = balpha;
+    A.sigma = sigma; A.X5 = X5; A.dbg = nullptr;
+    A.Nv = Nv;
+    for (int l = 0; l < NLAYER; ++l) A.mul[l] = mul[l];
+    A.scale0 = scale0; A.scale2 = scale2; A.inv_act = inv_act; A.araw = nullptr; A.status = status;
+    A.pp = pp; A.pp_scale = 1.f / inv_act; A.nc0 = NC0_PP;
+    return nbr_mlp_f16_launch(A, 0, stream);
 }
 
 // Training forward: same arithmetic, and everything the fused backward needs is saved as split images (img_common.cuh; every
@@ -698,5 +763,6 @@ extern "C" int hnr_nbr_mlp_f16_forward_train(const float* xyz, const float* xyz_
     A.x0img = (uint8_t*)x0img; A.eimg = (uint8_t*)eimg;
     A.himg[0] = (uint8_t*)h0img; A.himg[1] = (uint8_t*)h1img; A.himg[2] = (uint8_t*)h2img; A.himg[3] = (uint8_t*)h3img;
     A.inv_scale0 = 1.f / scale0; A.inv_scale2 = 1.f / scale2;
+    A.nc0 = NC0;
     return nbr_mlp_f16_launch(A, 2, stream);
 }

@@ -109,7 +109,26 @@ def pack_mlp_f16(block1, block3, act_scale: float = ACT_SCALE, weight_scale: Opt
     return wpack, bias, mul, s_in[0], s_in[2]
 
 
-def forward_f16(tables, pidx, vlist, loc_w, loc_pers, raydirs, cam, weight, confc, pack, w_alpha, b_alpha, debug: bool = False):
+def point_partial(emb: torch.Tensor, W1: torch.Tensor) -> torch.Tensor:
+    """per-point layer-0 partial pp (N, 256) = W1[:, :224] . [emb | PE(emb)] (reference column order, point_aggregators.py:931-939,
+    networks.py:175-189: [emb 32 | (c*3+f)*2+{sin,cos} of 2^f e_c]), through the own 3xTF32 layer kernel.  Computed once per (weights,
+    point set) for inference: the fused kernel then skips 14 of layer 0's 18 operand chunks (hnr_nbr_mlp_f16_forward_pp)."""
+    with torch.no_grad():
+        e = emb.detach().float().reshape(-1, emb.shape[-1])
+        assert e.shape[1] == 32 and W1.shape == (256, 284)
+        out = torch.empty((e.shape[0], 256), device=e.device, dtype=torch.float32)
+        Wp = W1.detach()[:, :224].contiguous()
+        freqs = torch.tensor([1.0, 2.0, 4.0], device=e.device)
+        step = 1 << 18                                     # bounds the temporary [emb | PE(emb)] rows (224 floats per point)
+        for i0 in range(0, e.shape[0], step):
+            ec = e[i0:i0 + step]
+            arg = ec[:, :, None] * freqs                   # (n, 32, 3)
+            pe = torch.stack([torch.sin(arg), torch.cos(arg)], dim=-1).reshape(ec.shape[0], 192)
+            out[i0:i0 + step] = ops.linear([torch.cat([ec, pe], dim=1)], Wp, None, ops.ACT_NONE)
+        return out
+
+
+def forward_f16(tables, pidx, vlist, loc_w, loc_pers, raydirs, cam, weight, confc, pack, w_alpha, b_alpha, debug: bool = False, pp=None):
     """fused gather + per-neighbour MLP + density head + weighted K-sum, 3xFP16 tensor-core kernel.
     Returns sigma (Nv,1), X5 (Nv,280) [, acts (4, Nv*8, 256) activations of the four layers, araw (Nv*8) density
     pre-activations when debug -- what the training forward saves for the backward pass]."""
@@ -124,6 +143,14 @@ def forward_f16(tables, pidx, vlist, loc_w, loc_pers, raydirs, cam, weight, conf
     wa = w_alpha.detach().float().contiguous().view(-1)
     ba = b_alpha.detach().float().contiguous().view(-1)
     mul_c = (C.c_float * 4)(*mul)
+    if pp is not None and not debug:
+        # per-point layer-0 partial (inference): the kernel generates only the distance-encoding chunks of layer 0
+        with ops._launch():
+            check(lib().hnr_nbr_mlp_f16_forward_pp(ptr(xyz), ptr(xyz_pers), ptr(pp), ptr(color), ptr(dirs), ptr(pidx), ptr(vlist), ptr(loc_w),
+                                                   ptr(loc_pers), ptr(raydirs), ptr(cam), ptr(weight), ptr(confc), ptr(wpack), ptr(bias), ptr(wa),
+                                                   ptr(ba), mul_c, float(s0), float(s2), 1.0 / ACT_SCALE, Nv, K, ptr(sigma), ptr(X5),
+                                                   ptr(ops.status_word(pidx.device)), stream()), "nbr_mlp_f16_forward_pp")
+        return sigma, X5
     with ops._launch():
         check(lib().hnr_nbr_mlp_f16_forward(ptr(xyz), ptr(xyz_pers), ptr(emb), ptr(color), ptr(dirs), ptr(pidx), ptr(vlist), ptr(loc_w),
                                             ptr(loc_pers), ptr(raydirs), ptr(cam), ptr(weight), ptr(confc), ptr(wpack), ptr(bias), ptr(wa),

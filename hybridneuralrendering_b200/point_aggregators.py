@@ -258,7 +258,7 @@ class PointAggregator(nn.Module):
             pack = self._packed_weights()
             with ops.tag("nbr_mlp"):
                 sigma, X5 = mlp_tc.forward_f16(tables, pidx, vlist, loc_w, loc_pers, raydirs, cam, weight, confc, pack,
-                                               self.alpha_branch[0].weight, self.alpha_branch[0].bias)
+                                               self.alpha_branch[0].weight, self.alpha_branch[0].bias, pp=self._point_partial(emb, Nv))
         elif self.mlp_engine == "tc" and torch.is_grad_enabled() and K == 8 and mask is None and self.fused_train_forward:
             # training: the same fused kernel, with the four layers' activations saved for the tensor-core backward
             tp = self._train_packs()
@@ -402,6 +402,26 @@ class PointAggregator(nn.Module):
         levels = self.feature_pyramid(img_n)
         w2c = torch.linalg.inv_ex(c2w_n.reshape(-1, 4, 4).float())[0]        # inv() reads its info flag back (host sync)
         return levels, w2c
+
+    def _point_partial(self, emb, Nv: int):
+        """per-point layer-0 partial of the per-neighbour MLP for no-grad forwards (mlp_tc.point_partial), cached per (embedding table,
+        first-layer weight) version.  OFF by default (HNR_POINT_PARTIAL=1 enables it): measured on the 800x800 frame it is neutral
+        within run-to-run noise (nbr_mlp 40.4 vs 41.6 ms on the same box, the whole frame 69.8 vs 71.8 ms with every other stage
+        equally faster in that run) -- skipping 14 of layer 0's 18 generated chunks is paid back by the 1 KB gather per neighbour row
+        in the layer-0 epilogue, and the table costs 1 KB per point.  Kept as a verified A/B (tests/test_gpu_mlp_tc.py)."""
+        if os.environ.get("HNR_POINT_PARTIAL", "0") != "1" or emb.shape[-1] != 32:
+            return None
+        W1 = self.block1[0].weight
+        N = emb.shape[0] if emb.dim() == 2 else emb.shape[-2]
+        key = (emb.data_ptr(), emb._version, N, W1.data_ptr(), W1._version)
+        ent = getattr(self, "_pp_cache", None)
+        if ent is not None and ent[0] == key:
+            return ent[1]
+        if Nv * 8 < N // 4:        # building the table costs one 224 -> 256 layer per POINT: only when enough neighbour rows use it
+            return None
+        from . import mlp_tc
+        self._pp_cache = (key, mlp_tc.point_partial(emb, W1))
+        return self._pp_cache[1]
 
     def _packed_weights(self):
         """fp16 hi/lo images of block1/block3 for the fused tensor-core kernel, re-packed when a weight changes"""

@@ -185,6 +185,16 @@ int hnr_nbr_mlp_f16_forward(const float* xyz, const float* xyz_pers, const float
  * ------------------------------------------------------------------------------------------- */
 /* forward that saves its operands: x0img 288 columns (layer-0 input, kernel column order = mlp_tc.layer1_column_order_f16),
  * eimg 16 columns (block3 extras), h0..h3img 256 columns (layer outputs), araw (Nv*8) density pre-activations. */
+/* hnr_nbr_mlp_f16_forward with the per-point layer-0 partial (inference): 224 of block1[0]'s 284 inputs -- the embedding and its
+ * positional encoding (point_aggregators.py:931-939) -- depend on the POINT only, and a point is the neighbour of many samples.
+ * pp (N_points, 256) fp32 = block1[0].weight[:, :224] . [emb | PE(emb)] per point (unscaled), computed once per (weights, point
+ * set); the kernel generates only the 4 distance-encoding chunks of layer 0 and adds pp[point] in the layer-0 epilogue.  Same
+ * wpack / bias / mul as hnr_nbr_mlp_f16_forward; the embedding table is not read. */
+int hnr_nbr_mlp_f16_forward_pp(const float* xyz, const float* xyz_pers, const float* pp, const float* color, const float* dir,
+                               const int32_t* pidx, const int32_t* vlist, const float* loc_w, const float* loc_pers, const float* raydirs,
+                               const float* cam, const float* weight, const float* confc, const void* wpack, const float* bias,
+                               const float* walpha, const float* balpha, const float* mul /* host, 4 */, float scale0, float scale2,
+                               float inv_act, int64_t Nv, int64_t K, float* sigma, float* X5, int32_t* status, void* stream);
 int hnr_nbr_mlp_f16_forward_train(const float* xyz, const float* xyz_pers, const float* emb, const float* color, const float* dir,
                                   const int32_t* pidx, const int32_t* vlist, const float* loc_w, const float* loc_pers,
                                   const float* raydirs, const float* cam, const float* weight, const float* confc, const void* wpack,

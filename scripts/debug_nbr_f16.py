@@ -12,7 +12,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
-def layer_errors(R=64, SR=24, empty=0.4, seed=3, N=4000, emb_range=None, weight_scale=1.0, return_status=False):
+def layer_errors(R=64, SR=24, empty=0.4, seed=3, N=4000, emb_range=None, weight_scale=1.0, return_status=False, with_pp=False):
     from helpers import build_aggregator, cuda
     from hybridneuralrendering_b200 import mlp_tc, ops
     from hybridneuralrendering_b200 import synthetic as syn
@@ -66,6 +66,15 @@ def layer_errors(R=64, SR=24, empty=0.4, seed=3, N=4000, emb_range=None, weight_
         _, X5_ref = ops.AlphaKSumFn.apply(h4.float(), confc, agg.alpha_branch[0].weight, agg.alpha_branch[0].bias, weight, vlist, raydirs, cam)
         errs.append((float((X5[:, 256:] - X5_ref[:, 256:]).abs().max()), 1.0))
         errs.append((float((araw_k.double().view(Nv, 8) - araw).abs().max()), float(araw.abs().max())))
+        if with_pp:
+            # inference with the per-point layer-0 partial (hnr_nbr_mlp_f16_forward_pp): same heads against the same fp64 references
+            pp = mlp_tc.point_partial(emb, agg.block1[0].weight)
+            sig2, X52 = mlp_tc.forward_f16(tables, pidx, vlist, loc_w, loc_pers, raydirs, cam, weight, confc, pack,
+                                           agg.alpha_branch[0].weight, agg.alpha_branch[0].bias, pp=pp)
+            torch.cuda.synchronize()
+            errs.append((float((sig2.double() - sig_ref).abs().max()), float(sig_ref.abs().max())))
+            errs.append((float((X52[:, :256].double() - x5_ref).abs().max()), float(x5_ref.abs().max())))
+            errs.append((float((X52[:, 256:] - X5_ref[:, 256:]).abs().max()), 1.0))
         status = int(ops.status_word(xyz.device)[0])
         ops.status_word(xyz.device).zero_()
     return (errs, status) if return_status else errs

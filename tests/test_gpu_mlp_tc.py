@@ -85,6 +85,19 @@ def test_f16_kernel_layers_match_fp64(R, SR, empty):
         assert e <= 1e-5 * scale + 1e-7, (name, e, scale)
 
 
+@pytest.mark.parametrize("R,SR,empty", [(3, 5, 0.0), (64, 24, 0.4), (300, 80, 0.2)])
+def test_f16_kernel_with_per_point_partial_matches_fp64(R, SR, empty):
+    """inference variant with the per-point layer-0 partial (W1[:, :224].[emb | PE(emb)] per point, added in the layer-0 epilogue;
+    only the distance-encoding chunks are generated): density, K-sum and view encoding against the same fp64 references"""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
+    from debug_nbr_f16 import layer_errors
+    errs = layer_errors(R=R, SR=SR, empty=empty, seed=R + SR, with_pp=True)
+    for name, (e, scale) in zip(["sigma_pp", "ksum_pp", "viewpe_pp"], errs[8:]):
+        assert e <= 1e-5 * scale + 1e-7, (name, e, scale)
+    assert len(errs) == 11
+
+
 def test_f16_packing_roundtrip():
     from hybridneuralrendering_b200 import mlp_tc
     W = (torch.arange(256 * 32, dtype=torch.float32).view(256, 32).cuda() - 4000.0) / 7000.0
