@@ -36,6 +36,12 @@ RENDER_WORKLOAD = "NeRF-synthetic lego-shaped full-frame render 800x800, synthet
 FLOP_NBR_FWD = 542_720                                   # per valid neighbour row, SURVEY.md 8d
 FLOP_NBR_DGRAD = 2 * (3 * 256 * 256 + 256 * 224)         # dZ_3 -> dZ_2 -> dZ_1 -> dZ_0 -> dX0 (224 needed input columns)
 BYTES_WGRAD_ROW = 4 * (4 * 256 + 288 + 256 + 272 + 256)  # every dZ / input image read once, 4 bytes per element
+# dram__bytes_read.sum + dram__bytes_write.sum of one configs[2] training step, from the committed `ncu --set full` capture
+# profiles/r2f_train_kernels_ncu.md (same command as scripts/train_step_bench.py, one frame of the benchmark's frame set)
+NCU_TRAFFIC = {"nbr_mlp": 0.132934e9 + 3.252108e9,
+               "backward/nbr_bwd_chain": 1.588010e9 + 2.353657e9,
+               "backward/wgrad_img": (0.102070 + 1.203327 + 0.282054 + 5.085762) * 1e9 + (3.554 + 5.230 + 6.924 + 5.667) * 1e6}   # its 4 launches
+NCU_TRAFFIC_SOURCE = "profiles/r2f_train_kernels_ncu.md (ncu --set full, same step; summed over the kernel's launches of one step like `achieved`)"
 
 
 def peaks():
@@ -303,7 +309,8 @@ def train_kernel_rooflines(tr, pk):
         if not ms:
             return
         ach = work / (ms * 1e-3) / (1e12 if bound == "tensor" else 1e9)
-        out.append({"kernel": name, "bound": bound, "ms": ms, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak, "work_per_launch": work, "note": note})
+        out.append({"kernel": name, "bound": bound, "ms": ms, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak, "work_per_launch": work,
+                    "traffic": NCU_TRAFFIC.get(tag), "note": note})
 
     rec("nbr_mlp_f16_kernel<2> (fused per-neighbour forward, training mode: saves its operands as split images)", "nbr_mlp", "tensor",
         FLOP_NBR_FWD * M, tens, "TFLOP/s", "542,720 FLOP x valid neighbours; peak = bf16_tflops_sustained/3 (3 f16 MMAs per fp32-accurate product)")
@@ -318,6 +325,7 @@ def train_kernel_rooflines(tr, pk):
         ach = work / (ws * 1e-3) / 1e9
         out.append({"kernel": "wgrad_img_kernel (all weight/bias gradients from MN-major slab images, 4 launches per step)", "bound": "hbm", "ms": ws,
                     "achieved": ach, "peak": peaks_d["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks_d["hbm_gbs"], "work_per_launch": work,
+                    "traffic": NCU_TRAFFIC["backward/wgrad_img"],
                     "note": "every dZ / input image read once (4 B per element); the two 128-row halves of a layer re-read the input image through L2"})
     return out
 
@@ -371,7 +379,8 @@ def main():
             "train": {k: tr[k] for k in ("ms_per_step", "ms_fwd_bwd", "kept_rays", "valid_samples", "valid_neighbours", "loss", "launches_per_step", "stage_ms", "ranks") if k in tr}}
     if top is not None:
         line["roofline"] = {"bound": top["bound"], "achieved": top["achieved"], "peak": top["peak"], "unit": top["unit"], "frac": top["frac"],
-                            "traffic": None, "kernel": top["kernel"], "kernel_ms": top["ms"], "note": top["note"],
+                            "traffic": top.get("traffic"), "traffic_source": NCU_TRAFFIC_SOURCE, "kernel": top["kernel"], "kernel_ms": top["ms"],
+                            "note": top["note"],
                             "peak_source": f"MEASURED_PEAKS.json ({pk[1]}), sustained figures (kernels timed inside a long step)",
                             "kernels": roofs, "step": step_roof}
     else:
