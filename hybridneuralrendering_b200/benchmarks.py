@@ -128,7 +128,9 @@ def train_step_benchmark(dev, steps: int = 5, warmup: int = 3, world: int = 1, p
         hosts = [{k: v.cpu().pin_memory() for k, v in f.items() if torch.is_tensor(v)} for f in frames]
         rest = {k: v for k, v in frame.items() if not torch.is_tensor(v)}
         host = hosts[0]
-        cnt = [0]
+        # the timed steps of this loop train on the SAME frames, in the same order, as the timed steps of the resident loop above (the
+        # frames differ by +-5 % in valid samples; two warm-up steps precede the timed ones here)
+        cnt = [max(warmup, FRAME_SET + 1) - 2]
 
         # double-buffered loader, as a training loop would run it: the host->device copy of a frame is issued on a copy stream one step
         # BEFORE the step that first touches it (its query is prefetched during the previous step), so the 29.6 MB transfer overlaps

@@ -172,8 +172,11 @@ class NeuralPoints(nn.Module):
         """launch the voxel query of a FUTURE forward now (kernels + asynchronous read-back, no host wait).  The next query() with
         the same ray / camera tensors and the same point set picks the result up; anything else discards it.  The query does not
         depend on trainable state (xyz_grad = 0), so a training loop can issue it one step ahead."""
+        # the key holds addresses: the tuple also keeps the tensors alive, so the allocator cannot hand the same address to a different
+        # frame while the result is pending (a recycled address with equal shape / version would otherwise match)
         self._pending = (self._query_key(inputs, near, far),
-                         self.querier.query_launch(self.xyz[None, ...], near, far, inputs["raydir"], inputs["campos"], inputs["camrotc2w"]))
+                         self.querier.query_launch(self.xyz[None, ...], near, far, inputs["raydir"], inputs["campos"], inputs["camrotc2w"]),
+                         (inputs["raydir"], inputs["campos"], inputs["camrotc2w"]))
 
     def forward(self, inputs):
         """(:702-733) returns the reference's 14-tuple with materialised neighbour gathers."""

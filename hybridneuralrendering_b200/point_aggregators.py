@@ -7,9 +7,11 @@ with the reference, same ``forward`` signature and return tuple (:1427-1522).
 
 The arithmetic runs in libhnr kernels: neighbour features are generated straight from the point
 tables (fused path) or from the gathered tensors (drop-in ``forward``), the dense layers run on the
-hand-written kernels (``ops.linear`` / ``mlp_tc``), the image features are read from the conv
-pyramid with the bilinear-upsample arithmetic folded in.  Only the six tiny pyramid convolutions
-stay in torch/cuDNN.
+hand-written tcgen05 kernels (fused per-neighbour MLP ``mlp_tc`` / ``ops.NbrMlpTrainFn``, per-sample
+chains ``chain``), the image features are read from the conv pyramid (own kernels, ``csrc/pyramid.cu``)
+with the bilinear-upsample arithmetic folded in.  The cuDNN pyramid (``_ExactConvPyramid``) and the
+exact-fp32 layer kernels (``ops.linear``, ``mlp_engine = "simt"``) are kept only as the tests'
+independent cross-checks of those kernels.
 
 Supported configuration = the one every shipped script uses: ``viewmlp``,
 ``agg_intrp_order=2``, ``agg_distance_kernel=linear``, ``agg_dist_pers=20``, ``LeakyReLU``,
@@ -179,7 +181,7 @@ class PointAggregator(nn.Module):
         diff = sampled_conf - torch.clamp(sampled_conf, min=min, max=max)
         return sampled_conf - diff.detach()
 
-    # ------------------------------------------------------------------ image pyramid (torch/cuDNN, 6 tiny convs)
+    # ------------------------------------------------------------------ image pyramid (own kernels; cuDNN = cross-check)
     def feature_pyramid(self, img_n: torch.Tensor):
         """img_n (1,V,H,W,3) -> NHWC levels [(V,H,W,3),(V,h1,w1,6),(V,h2,w2,12),(V,h3,w3,24)]"""
         img = img_n[0]
@@ -250,8 +252,8 @@ class PointAggregator(nn.Module):
         S, K = pidx.shape
         Nv = vlist.shape[0]
         b1, b3 = self.block1, self.block3
-        # per-neighbour MLP engine: the fused tensor-core kernel for no-grad forwards; forwards that record a graph use
-        # the layer kernels (their backward needs the saved activations)
+        # per-neighbour MLP: the fused tensor-core kernel; graph-recording forwards run it in training mode (operands saved as split
+        # images for the fused backward).  The layer kernels below serve the gathered-tensor drop-in forward (mask given) and the tests
         use_tc = self.mlp_engine == "tc" and not torch.is_grad_enabled() and K == 8 and mask is None
         if use_tc:
             from . import mlp_tc
