@@ -335,8 +335,12 @@ def test_train_step_with_deferred_weight_gradients_equals_plain_backward():
     assert la == lb and set(ga) == set(gb) and len(ga) > 40
     for k in ga:
         a, b = ga[k].double(), gb[k].double()
-        # same kernels, same inputs; only the atomics' arrival order differs between two runs
-        assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max()) + 1e-30, k
+        # same kernels, same inputs; only the arrival order of the fp32 atomics differs between two runs.  Measured over 35 repetitions
+        # (scripts/stress_deferred.py, profiles/r2_stress_deferred*.txt; also with the allocator's free blocks poisoned with NaN): the
+        # largest spread is on ONE scalar, the bias gradient of the blend-weight head (a cancelling sum over V*Nv terms), up to 6.9e-6 x
+        # its magnitude between two PLAIN backward passes and 6.1e-6 deferred-vs-plain; every other tensor stays below 5e-7.  The bound is
+        # 5e-5 (half of the 1e-4 gradient bar): 1e-5 sat inside that scalar's run-to-run tail and failed about once in a hundred runs
+        assert float((a - b).abs().max()) <= 5e-5 * float(b.abs().max()) + 1e-30, k
 
 
 def test_split_first_layer_of_the_blend_weight_net_matches_fp64():
