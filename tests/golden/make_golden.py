@@ -379,6 +379,9 @@ def frame_case():
 
 
 if __name__ == "__main__":
+    # bit-reproducible files: torch's multi-threaded CPU index_put_(accumulate=True) -- the backward of the table gathers `tab[k][idx]`
+    # of agg_case_tables -- adds with atomics in arrival order; deterministic mode makes it (and nothing else used here) sequential
+    torch.use_deterministic_algorithms(True, warn_only=True)
     if "--only-frame" in sys.argv:
         frame_case()
         sys.exit(0)
