@@ -421,7 +421,7 @@ def main():
             cores = os.cpu_count() or 1
             torch.set_num_threads(cores)
             try:
-                r = reference_step_times("cpu", 2048 if cores >= 8 else 512, 1, 1)
+                r = reference_step_times("cpu", 2048 if cores >= 8 else 512, 3, 1)          # mean of 3 timed passes after one warm-up (~6 s of host work)
                 line["cpu_baseline"] = {"value": r["value"], "unit": "rays/s", "cores": cores, "kind": r["kind"],
                                         "sample": (f"first {r['rays']} rays (whole patches) of the same 4096-ray batch, fwd {r['s_fwd']:.1f} s + bwd {r['s_bwd']:.1f} s of "
                                                    f"PointAggregator.forward + ray_dist + ray_march + loss + backward, torch {torch.__version__} CPU fp32; query "
