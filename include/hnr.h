@@ -148,7 +148,8 @@ int hnr_linear_tc_fwd(const float* const* a_ptr, const int64_t* a_ld, const int6
                       int64_t ldy, int64_t M, int64_t N, int64_t K, int act, const float* head_w /* N or NULL */,
                       const float* head_b, int head_act, float* out_head /* M */, void* stream);
 
-/* Tensor-core backward of a dense layer (training path), 3xTF32:
+/* Tensor-core backward of a dense layer (training path), 3xTF32 -- autograd of the nn.Linear layers of
+ * models/aggregators/point_aggregators.py:484-754 as called at :921-1026 (per-neighbour) and :1028-1037, :1188-1217, :1285-1334:
  *   hnr_linear_tc_bwd_data:   dX (M, Kout <= 256 columns per call) = (dY * act'(Y)) (M,N) . W (N, K-slice); wpackT = image of
  *                             the transposed weight slice (csrc/linear_tc.cu; replaces hnr_linear_bwd_data)
  *   hnr_linear_tc_bwd_weight: dW (N,K) += (dY * act'(Y))^T . concat(X), db += column sums; reduction over the M rows with the
