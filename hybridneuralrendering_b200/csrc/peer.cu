@@ -1,13 +1,16 @@
 // One-shot SUM all-reduce of a small fp32 buffer over NVLink peer memory: the data-parallel training step reduces
 // the network's gradients (MLPs + pyramid convolutions: 449,381 floats = 1.8 MB) every step.  As an NCCL collective that message is
-// pure latency -- and it queues for SM resources behind the 312 MB point-table all-reduce and the gradient-tail kernels that run at
-// the same time (0.55 ms of main-stream time per step at 8 GPUs, scripts/dp_timeline.py).  Here every rank keeps its local
+// pure latency -- and on the main communicator it queues behind the 312 MB point-table all-reduce that train_step starts first.  Here every rank keeps its local
 // gradients in a SYMMETRIC buffer (the same allocation mapped into every peer's address space); after a device-side barrier one
 // kernel per rank reads all W peer copies straight over NVLink / NVSwitch and writes the sum to local memory:
 //   * peer_sum_kernel:      W unicast loads per element, summed in rank order -> bit-identical result on every rank;
 //   * multimem_sum_kernel:  ONE multimem.ld_reduce per 16 bytes on the multicast address -- the NVSwitch pulls the W copies and
 //                           adds them in the switch (NVLS), 1/W of the NVLink ingress of the unicast version.
-// 1.8 MB x 8 peers = 14 MB per rank over 900 GB/s links: ~20 us plus two barriers, against ~550 us.
+// 1.8 MB x 8 peers = 14 MB per rank over 900 GB/s links: the kernel itself takes ~10-20 us.  Measured honestly (DESIGN.md 6,
+// profiles/r2_peer_check_n*.txt, r2_dp_timeline_n8*.txt): with its two multi-tensor copies and two barrier launches the call costs
+// ~150 us in isolation (NCCL reduces this message in 19-32 us back to back), and inside the step the interval up to the barrier is
+// 0.55-0.66 ms with EITHER implementation -- that is where the ranks' load imbalance surfaces.  What the own path buys is independence
+// from the NCCL stream's issue order (the message does not queue behind the big all-reduce) and a defined summation order.
 // The reference has no multi-GPU path; the semantic is NCCL's ncclAllReduce(ncclSum) on the same buffer.
 #include "common.cuh"
 #include "hnr.h"
