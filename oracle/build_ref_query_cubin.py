@@ -6,7 +6,7 @@ models/neural_points/query_point_indices_worldcoords.py:108-524 and JIT-compiles
 the `#define KN <K>` concatenation the same way the reference does, and runs nvcc on it.  Only the
 compiled cubin (a build output) lands in oracle/_ref/; no reference source is written into the repo
 (the temporary .cu lives under /tmp and is deleted).  The cubin travels to the GPU box with the
-snapshot, where tests/test_query_vs_reference_gpu.py launches the reference kernels through
+snapshot, where tests/test_gpu_query_vs_reference.py launches the reference kernels through
 cuda.bindings to validate both the numpy restatement (oracle/query_oracle.py) and the CUDA product.
 """
 import os
