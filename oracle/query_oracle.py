@@ -22,7 +22,7 @@ replacement); the deterministic canonical form used here and by
     slots (x-major shell walk, replace-farthest buffer) for information.
 
 Parity pinning: misc.npz pins ray_candidates against the reference's torch generator on CPU; the
-kernels themselves can only run on a GPU, so tests/test_query_vs_reference_gpu.py runs the
+kernels themselves can only run on a GPU, so tests/test_gpu_query_vs_reference.py runs the
 reference's own compiled kernels (oracle/_ref/ref_query_k8.cubin, built by
 oracle/build_ref_query_cubin.py) on the B200 box against this file and against the product.
 """
