@@ -2,7 +2,7 @@
 """Dense TF32 tensor throughput of this GPU, measured the way MEASURED_PEAKS.json measures bf16 (SURVEY.md 8d asks for it: the
 3xTF32 backward kernels are compared against bf16_sustained / 2 "derived" until this number exists).
 
-    python scripts/measure_tf32_peak.py [--json profiles/tf32_peak.json]
+    python scripts/measure_tf32_peak.py [--json profiles/r2_tf32_peak.json]      (the file bench.py reads the measured TF32 peak from)
 
 torch.matmul fp32 8192^3 with TF32 enabled: best of 10 (burst) and back to back for 4 s (sustained), CUDA events."""
 import argparse
